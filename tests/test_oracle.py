@@ -1,0 +1,104 @@
+"""Pin the CPU oracle (oracle/bert_oracle.py) against outputs of the real
+reference minted by oracle/make_goldens.py (HF BertModel eager + the reference's
+own wrappers, run in the build container).  fp32 vs fp32: tolerance 2e-5 relative
+(summation-order differences only)."""
+import os
+
+import torch
+
+from conftest import GOLDEN, rel_err
+from oracle import bert_oracle as O
+
+TOL = 2e-5
+
+
+def _load(name):
+    return torch.load(os.path.join(GOLDEN, name), weights_only=False)
+
+
+def test_tiny_forward_matches_reference():
+    g = _load("tiny_bert.pt")
+    cfg = O.OracleConfig(**g["config"])
+    out = O.bert_model(g["state_dict"], cfg, g["input_ids"], g["attention_mask"], g["token_type_ids"])
+    assert rel_err(out.last_hidden_state, g["last_hidden_state"]) < TOL
+    assert rel_err(out.pooler_output, g["pooler_output"]) < TOL
+    assert len(out.hidden_states) == len(g["hidden_states"]) == cfg.num_hidden_layers + 1
+    for a, b in zip(out.hidden_states, g["hidden_states"]):
+        assert rel_err(a, b) < TOL
+    assert len(out.attentions) == cfg.num_hidden_layers
+    for a, b in zip(out.attentions, g["attentions"]):
+        assert a.shape == b.shape
+        assert rel_err(a, b) < TOL
+
+
+def test_tiny_loss_logits_argmax_match_reference_wrapper():
+    g = _load("tiny_bert.pt")
+    cfg = O.OracleConfig(**g["config"])
+    loss, logits = O.topicseg_loss(g["state_dict"], cfg, g["cls_w"], g["cls_b"], g["input_ids"],
+                                   g["attention_mask"], g["token_type_ids"], g["labels"])
+    # bert_for_ts.py wrapper output: (loss, logits[B,2,S,2], cos)
+    assert abs(float(loss) - float(g["wrapper_loss"])) < 1e-5
+    assert abs(float(loss) - float(g["loss"])) < 1e-5
+    assert rel_err(logits, g["wrapper_logits"][:, 0]) < TOL
+    keep = g["labels"] != -100
+    assert torch.equal(O.boundary_argmax(logits)[keep], g["wrapper_logits"][:, 0].argmax(-1)[keep])
+
+
+def test_tiny_gradients_match_reference_autograd():
+    g = _load("tiny_bert.pt")
+    cfg = O.OracleConfig(**g["config"])
+    sd = {k: v.clone().requires_grad_(True) for k, v in g["state_dict"].items()}
+    w = g["cls_w"].clone().requires_grad_(True)
+    b = g["cls_b"].clone().requires_grad_(True)
+    loss, _ = O.topicseg_loss(sd, cfg, w, b, g["input_ids"], g["attention_mask"], g["token_type_ids"], g["labels"])
+    loss.backward()
+    for k, ref in g["grads"].items():
+        got = {"classifier.weight": w, "classifier.bias": b}.get(k, sd.get(k))
+        assert got is not None and got.grad is not None, k
+        # key.bias gradients are mathematically zero (softmax is shift-invariant per query row):
+        # both sides hold rounding noise there, so the bound is absolute + relative.
+        err = float((got.grad.double() - ref.double()).norm())
+        assert err <= 5e-5 * float(ref.double().norm()) + 1e-7, (k, err)
+    # pooler gets no gradient (bert_for_ts.py:20 ignores it)
+    assert sd["pooler.dense.weight"].grad is None
+
+
+def test_bert_base_forward_matches_reference():
+    g = _load("bert_base_2x128.pt")
+    cfg = O.OracleConfig(**g["config"])
+    sd = O.random_state_dict(cfg, seed=g["weight_seed"])
+    out = O.bert_model(sd, cfg, g["input_ids"], g["attention_mask"], g["token_type_ids"])
+    assert rel_err(out.last_hidden_state, g["last_hidden_state"]) < TOL
+    assert rel_err(out.pooler_output, g["pooler_output"]) < TOL
+    assert rel_err(out.hidden_states[6][:, :16], g["hidden_state_6"]) < TOL
+    diag = torch.diagonal(out.attentions[0][:, 9], dim1=1, dim2=2)
+    assert rel_err(diag, g["attn_l0_h9_diag"]) < TOL
+    logits = O.token_cls_logits(out.last_hidden_state, g["cls_w"], g["cls_b"])
+    assert rel_err(logits, g["logits"]) < TOL
+    margin = (g["logits"][..., 0] - g["logits"][..., 1]).abs()
+    safe = margin > 1e-4
+    assert torch.equal(logits.argmax(-1)[safe], g["logits"].argmax(-1)[safe])
+    # ditto pooling plumbing (evaluation_ditto.py:125-155): shapes and finiteness
+    pooled = O.ditto_pool(out, g["attention_mask"], layer=0, head=9)
+    assert pooled.shape == (2, cfg.hidden_size) and torch.isfinite(pooled).all()
+
+
+def test_mmvts_layers_match_in_tree_reference():
+    g = _load("mmvts_layers.pt")
+    cfg = O.OracleConfig(hidden_size=g["H"], num_attention_heads=g["heads"], intermediate_size=g["I"],
+                         num_hidden_layers=1)
+    add = O.additive_key_mask(g["mask01"], torch.float32, fill=-1000000.0)
+    y, _ = O.bert_layer(g["self_sd"], "", cfg, g["x"], add)
+    assert rel_err(y, g["y_self"]) < TOL
+    yc = O.bert_cross_layer(g["cross_sd"], "", cfg, g["x"], g["kv"], add, add)
+    assert rel_err(yc, g["y_cross"]) < TOL
+
+
+def test_mask_fill_values_agree():
+    """finfo.min (HF), -1e6 (mmvts), -1e4 (TF fork) give the same result whenever every row keeps a key."""
+    g = _load("tiny_bert.pt")
+    cfg = O.OracleConfig(**g["config"])
+    args = (g["state_dict"], cfg, g["input_ids"], g["attention_mask"], g["token_type_ids"])
+    a = O.bert_model(*args).last_hidden_state
+    for fill in (-1e6, -1e4):
+        assert rel_err(O.bert_model(*args, mask_fill=fill).last_hidden_state, a) < 1e-6
