@@ -1,0 +1,124 @@
+/*
+ * libb200enc — C ABI of the B200-native (sm_100a) transformer-encoder hot path.
+ *
+ * The reference (alibaba-damo-academy/SpokenNLP) has no FFI: its encoder arithmetic is PyTorch library calls
+ * made by HuggingFace `BertModel`.  Each entry point below replaces the library call(s) named
+ * in its comment; the Python host package `spokennlp_b200` binds them with ctypes behind a
+ * drop-in `BertModel`.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated otherwise
+ *   - the caller owns all memory (activations, workspaces, outputs); the library never allocates device memory
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no call synchronises
+ *   - return 0 on success, <0 on error (B200_ERR_*); b200_last_error() gives a thread-local message
+ *   - fp16 activations / compute copies of weights ("half"), fp32 master parameters, biases, LN params,
+ *     statistics, logits and gradients; all row pitches ("ld") are in ELEMENTS and must be multiples of 8
+ */
+#ifndef B200ENC_H_
+#define B200ENC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_ERR_SHAPE (-1)       /* bad shape / alignment / unsupported combination */
+#define B200_ERR_DTYPE (-2)
+#define B200_ERR_CUDA (-3)        /* CUDA launch / driver error, see b200_last_error() */
+
+/* epilogues of b200_gemm_f16 */
+#define B200_EPI_STORE 0          /* out = acc */
+#define B200_EPI_BIAS 1           /* out = acc + bias[n]                      (nn.Linear: QKV projection, bert_model.py:271,293-296) */
+#define B200_EPI_BIAS_GELU 2      /* out = gelu_erf(acc + bias[n]); out2 = pre-activation (BertIntermediate, bert_model.py:436-439) */
+#define B200_EPI_BIAS_RES 3       /* out = acc + bias[n] + aux[m,n]           (dense + residual of BertSelfOutput / BertOutput, :371-375, :449-453) */
+#define B200_EPI_DGELU 4          /* out = acc * gelu'(aux[m,n])              (autograd of :436-439) */
+#define B200_EPI_ADD 5            /* out = acc + aux[m,n]                     (dgrad + residual-branch gradient) */
+#define B200_EPI_ATOMIC 6         /* out(fp32) += alpha * acc                 (wgrad, split-K) */
+
+#define B200_DT_F16 0
+#define B200_DT_F32 1
+
+const char* b200_last_error(void);
+int b200_version(void);
+/* number of kernels this library has launched in this process (bench.py reports it as gpu_launches) */
+long long b200_launch_count(void);
+
+/*
+ * C[M,N] = epilogue(A * B^T) on tcgen05 tensor cores (fp16 x fp16 -> fp32 in TMEM).
+ *   a_layout 0: A stored [M,K] row-major (K contiguous)      1: A stored [K,M] row-major (M contiguous)
+ *   b_layout 0: B stored [N,K] row-major (torch Linear.weight) 1: B stored [K,N] row-major
+ * Replaces torch.nn.functional.linear and its autograd (dgrad: b_layout=1 on the same weight; wgrad:
+ * a_layout=b_layout=1 on dY and X) — SURVEY.md K2, K4, K5, K6, K8.
+ * Supported (a_layout,b_layout,epilogue,out_dtype): (0,0,{STORE,BIAS,BIAS_GELU,BIAS_RES},{F16,F32*}),
+ * (0,1,{STORE,ADD,DGELU},F16), (1,1,ATOMIC,F32).  (*F32 for STORE and BIAS_RES only.)
+ * alpha: optional device scalar multiplied into the accumulator.  k_splits > 1 only with EPI_ATOMIC.
+ */
+int b200_gemm_f16(const void* A, int lda, int a_layout, const void* B, int ldb, int b_layout, int M, int N, int K,
+                  int epilogue, const float* bias, const void* aux, int ld_aux, void* out, int ld_out, int out_dtype,
+                  void* out2, int ld_out2, const float* alpha, int k_splits, void* stream);
+
+/*
+ * Fused attention forward, head_dim 64: ctx = softmax(Q K^T / 8 + key_bias) V  (BertSelfAttention.forward,
+ * bert_model.py:309-350; HF eager_attention_forward).  Q: [B*Sq, ldq] with head h at columns q_col0 + 64h;
+ * K, V: [B*Sk, ldkv] at k_col0 / v_col0 + 64h (self-attention: all three inside the packed [tokens,3H] QKV buffer).
+ * key_bias: optional [B,Sk] additive fp32 (0 keep / -inf drop, or any finite additive mask); kv_len: optional [B] int32.
+ * ctx: [B*Sq, ld_out] fp16; lse2: optional [B,heads,Sq] fp32 log2-domain log-sum-exp saved for the backward.
+ */
+int b200_attn_fwd(const void* q, int ldq, int q_col0, const void* kv, int ldkv, int k_col0, int v_col0, const float* key_bias,
+                  const int32_t* kv_len, void* ctx, int ld_out, float* lse2, int B, int heads, int Sq, int Sk, void* stream);
+
+/* P[b,h,i,j] for output_attentions=True (ditto/evaluation_ditto.py:121-127); needs lse2 from b200_attn_fwd. */
+int b200_attn_probs(const void* q, int ldq, int q_col0, const void* k, int ldk, int k_col0, const float* key_bias,
+                    const float* lse2, float* probs, int B, int heads, int Sq, int Sk, void* stream);
+
+/* key_bias[b,s] = mask01 ? 0 : -inf ; kv_len[b] = 1 + last kept key  (HF create_bidirectional_mask / mmvts -1e6 masks) */
+int b200_mask_to_bias(const void* mask, int mask_dtype /*0=int64,1=f32,2=int32*/, float* key_bias, int32_t* kv_len, int B, int S,
+                      void* stream);
+
+/* y = LayerNorm(x) * gamma + beta (eps inside sqrt, biased variance; torch.nn.LayerNorm in bert_model.py:368,446).
+ * x: [rows,H] fp32 (x_dtype=1) or fp16 (0) pre-LN sum; y fp16; y32 optional fp32 copy; mean/rstd optional [rows]. */
+int b200_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, void* y, float* y32, float* mean,
+                       float* rstd, int rows, int H, float eps, void* stream);
+
+/* LayerNorm backward.  dy (+ optional dy2) fp16, x pre-LN sum, saved mean/rstd.  dx fp16 = grad wrt the pre-LN sum;
+ * dgamma/dbeta (and optional dbias = column sums of dx) are ACCUMULATED in fp32, scaled by *alpha (device, optional). */
+int b200_layernorm_bwd(const void* dy, const void* dy2, const void* x, int x_dtype, const float* mean, const float* rstd,
+                       const float* gamma, void* dx, float* dgamma, float* dbeta, float* dbias, const float* alpha, int rows, int H,
+                       void* stream);
+
+/* y = LN(word[ids] + pos[pos_ids] + type[tt])  (BertEmbeddings.forward, bert_model.py:184-210).  Tables fp32.
+ * ids/tt/pos: int64 [rows]; tt/pos may be null (0 / row % S); inputs_embeds optional fp32 [rows,H] instead of the gather. */
+int b200_embed_ln_fwd(const int64_t* ids, const int64_t* tt, const int64_t* pos, const float* inputs_embeds, const float* word,
+                      const float* pos_tab, const float* type_tab, const float* gamma, const float* beta, void* y, float* y32,
+                      int rows, int S, int H, float eps, void* stream);
+int b200_embed_ln_bwd(const void* dy, const void* dy2, const int64_t* ids, const int64_t* tt, const int64_t* pos, const float* word,
+                      const float* pos_tab, const float* type_tab, const float* gamma, float* dword, float* dpos, float* dtype_tab,
+                      float* dgamma, float* dbeta, const float* alpha, int rows, int S, int H, float eps, void* stream);
+
+/* Token-classification head: logits[rows,C] = h . W^T + b, C in {2,3} (LossCalculator.classifier, loss_calculator.py:17,42;
+ * modeling_ponet.py:43,83-84; TSSP tssp.py:26-34).  argmax optional int32 [rows] (np.argmax, ts_sentence_seq_labeling.py:1143). */
+int b200_cls_head_fwd(const void* h, const float* W, const float* b, float* logits, int32_t* argmax, int rows, int H, int C,
+                      void* stream);
+/* stats[0] += sum_i w_i * nll_i, stats[1] += sum_i w_i over rows with label != -100 (CrossEntropyLoss, utils.py:173-182). */
+int b200_ce_stats(const float* logits, const int64_t* labels, const float* class_weight, float* stats, int rows, int C, void* stream);
+/* backward of head + mean CE: dh = *scale * dlogits . W (fp16), dW += dlogits^T h, db += sum dlogits. */
+int b200_cls_head_bwd(const void* h, const float* logits, const int64_t* labels, const float* class_weight, const float* stats,
+                      const float* W, const float* scale, void* dh, float* dW, float* db, int rows, int H, int C, void* stream);
+
+/* db[n] += *alpha * sum_m dy[m,n]   (bias gradients) */
+int b200_colsum(const void* dy, int ld, float* db, const float* alpha, int rows, int cols, void* stream);
+
+/* casts: n must be a multiple of 8 */
+int b200_cast_f32_to_f16(const float* src, void* dst, size_t n, void* stream);
+int b200_cast_f16_to_f32(const void* src, float* dst, size_t n, void* stream);
+/* scale[0] = power of two bringing amax|src| to ~target, scale[1] = 1/scale[0]; dst = fp16(src * scale[0]).
+ * `amax_slot` is a 4-byte device scratch.  Used to carry an fp32 upstream gradient into the fp16 backward. */
+int b200_scale_cast_grad(const float* src, void* dst, size_t n, float target, float* scale, void* amax_slot, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ENC_H_ */

@@ -1,0 +1,395 @@
+// C ABI of libb200enc (see include/b200enc.h): argument checking, TMA tensor-map construction, launches.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+
+#include "../../include/b200enc.h"
+#include "attn_bwd.cuh"
+#include "attn_fwd.cuh"
+#include "gemm.cuh"
+#include "optim.cuh"
+#include "rowwise.cuh"
+
+using namespace b200;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(B200_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return B200_OK;
+}
+
+// ---- cuTensorMapEncodeTiled is resolved at run time: the build box has no libcuda.so -------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  uint64_t rows, cols, ld;
+  uint32_t box_rows;
+  bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    h ^= k.rows * 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    h ^= k.cols * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2);
+    h ^= (k.ld * 31 + k.box_rows) * 0x165667B19E3779F9ull + (h << 6) + (h >> 2);
+    return h;
+  }
+};
+std::mutex g_map_mu;
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+
+// 2D fp16 tensor [rows, cols] with row pitch ld (elements); box = 64 columns (128 B, SWIZZLE_128B) x box_rows.
+int get_tmap(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, CUtensorMap* out) {
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld % 8) || cols == 0 || rows == 0 || box_rows == 0 || box_rows > 256)
+    return fail(B200_ERR_SHAPE, "tensor map: ptr %p rows %llu cols %llu ld %llu box_rows %u violates 16B alignment / ld%%8", ptr,
+                (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
+  const MapKey key{ptr, rows, cols, ld, box_rows};
+  {
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) {
+      *out = it->second;
+      return B200_OK;
+    }
+  }
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(B200_ERR_CUDA, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {ld * 2};
+  const cuuint32_t box[2] = {64, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B200_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", static_cast<int>(r));
+  {
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    if (g_maps.size() > 65536) g_maps.clear();
+    g_maps.emplace(key, m);
+  }
+  *out = m;
+  return B200_OK;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <typename K>
+int set_smem(K kern, int bytes) {
+  const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return fail(B200_ERR_CUDA, "cudaFuncSetAttribute(smem=%d): %s", bytes, cudaGetErrorString(e));
+  return B200_OK;
+}
+
+template <int BN, int A_MN, int B_MN, int EPI, typename OutT>
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, cudaStream_t s) {
+  auto kern = gemm_f16_kernel<BN, A_MN, B_MN, EPI, OutT>;
+  static int configured = set_smem(kern, GemmSmem<BN>::TOTAL);
+  if (configured != B200_OK) return configured;
+  const int m_tiles = (g.M + GEMM_BM - 1) / GEMM_BM, n_tiles = (g.N + BN - 1) / BN;
+  const int units = m_tiles * n_tiles * (g.k_splits > 0 ? g.k_splits : 1);
+  const int grid = units < sm_count() ? units : sm_count();
+  kern<<<grid, GEMM_THREADS, GemmSmem<BN>::TOTAL, s>>>(ta, tb, g);
+  return check_launch("gemm_f16_kernel");
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b200_last_error(void) { return g_err.c_str(); }
+int b200_version(void) { return 100; }
+long long b200_launch_count(void) { return g_launches.load(); }
+
+int b200_gemm_f16(const void* A, int lda, int a_layout, const void* B, int ldb, int b_layout, int M, int N, int K, int epilogue,
+                  const float* bias, const void* aux, int ld_aux, void* out, int ld_out, int out_dtype, void* out2, int ld_out2,
+                  const float* alpha, int k_splits, void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return fail(B200_ERR_SHAPE, "gemm: empty problem %dx%dx%d", M, N, K);
+  if ((N % 4) || (ld_out % 4)) return fail(B200_ERR_SHAPE, "gemm: N and ld_out must be multiples of 4 (N=%d ld_out=%d)", N, ld_out);
+  if (!A || !B || !out) return fail(B200_ERR_SHAPE, "gemm: null operand");
+  const bool needs_bias = epilogue == EPI_BIAS || epilogue == EPI_BIAS_GELU || epilogue == EPI_BIAS_RES;
+  const bool needs_aux = epilogue == EPI_BIAS_RES || epilogue == EPI_DGELU || epilogue == EPI_ADD;
+  if (needs_bias && !bias) return fail(B200_ERR_SHAPE, "gemm: epilogue %d needs bias", epilogue);
+  if (needs_aux && (!aux || (ld_aux % 4))) return fail(B200_ERR_SHAPE, "gemm: epilogue %d needs aux with ld%%4==0", epilogue);
+  if (k_splits > 1 && epilogue != EPI_ATOMIC) return fail(B200_ERR_SHAPE, "gemm: split-K only with the atomic epilogue");
+  constexpr int BN = 256;
+  CUtensorMap ta, tb;
+  int rc;
+  // K-major operand: matrix [MN, K], box 64(K) x tile rows.  MN-major operand: matrix [K, MN], box 64(MN) x 64(K rows).
+  rc = a_layout == 0 ? get_tmap(A, M, K, lda, GEMM_BM, &ta) : get_tmap(A, K, M, lda, GEMM_BK, &ta);
+  if (rc) return rc;
+  rc = b_layout == 0 ? get_tmap(B, N, K, ldb, BN, &tb) : get_tmap(B, K, N, ldb, GEMM_BK, &tb);
+  if (rc) return rc;
+  GemmArgs g{M, N, K, k_splits > 0 ? k_splits : 1, bias, static_cast<const __half*>(aux), ld_aux, out, ld_out,
+             static_cast<__half*>(out2), ld_out2, alpha};
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int key = a_layout * 1000 + b_layout * 100 + epilogue * 10 + out_dtype;
+  switch (key) {
+    case 0 * 1000 + 0 * 100 + EPI_STORE * 10 + B200_DT_F16: return launch_gemm<BN, 0, 0, EPI_STORE, __half>(ta, tb, g, s);
+    case 0 * 1000 + 0 * 100 + EPI_STORE * 10 + B200_DT_F32: return launch_gemm<BN, 0, 0, EPI_STORE, float>(ta, tb, g, s);
+    case 0 * 1000 + 0 * 100 + EPI_BIAS * 10 + B200_DT_F16: return launch_gemm<BN, 0, 0, EPI_BIAS, __half>(ta, tb, g, s);
+    case 0 * 1000 + 0 * 100 + EPI_BIAS_GELU * 10 + B200_DT_F16: return launch_gemm<BN, 0, 0, EPI_BIAS_GELU, __half>(ta, tb, g, s);
+    case 0 * 1000 + 0 * 100 + EPI_BIAS_RES * 10 + B200_DT_F16: return launch_gemm<BN, 0, 0, EPI_BIAS_RES, __half>(ta, tb, g, s);
+    case 0 * 1000 + 0 * 100 + EPI_BIAS_RES * 10 + B200_DT_F32: return launch_gemm<BN, 0, 0, EPI_BIAS_RES, float>(ta, tb, g, s);
+    case 0 * 1000 + 1 * 100 + EPI_STORE * 10 + B200_DT_F16: return launch_gemm<BN, 0, 1, EPI_STORE, __half>(ta, tb, g, s);
+    case 0 * 1000 + 1 * 100 + EPI_ADD * 10 + B200_DT_F16: return launch_gemm<BN, 0, 1, EPI_ADD, __half>(ta, tb, g, s);
+    case 0 * 1000 + 1 * 100 + EPI_DGELU * 10 + B200_DT_F16: return launch_gemm<BN, 0, 1, EPI_DGELU, __half>(ta, tb, g, s);
+    case 1 * 1000 + 1 * 100 + EPI_ATOMIC * 10 + B200_DT_F32: return launch_gemm<BN, 1, 1, EPI_ATOMIC, float>(ta, tb, g, s);
+    default:
+      return fail(B200_ERR_SHAPE, "gemm: unsupported (a_layout=%d, b_layout=%d, epilogue=%d, out_dtype=%d)", a_layout, b_layout,
+                  epilogue, out_dtype);
+  }
+}
+
+int b200_attn_fwd(const void* q, int ldq, int q_col0, const void* kv, int ldkv, int k_col0, int v_col0, const float* key_bias,
+                  const int32_t* kv_len, void* ctx, int ld_out, float* lse2, int B, int heads, int Sq, int Sk, void* stream) {
+  if (B <= 0 || heads <= 0 || Sq <= 0 || Sk <= 0) return fail(B200_ERR_SHAPE, "attn_fwd: empty problem");
+  if ((q_col0 % 8) || (k_col0 % 8) || (v_col0 % 8) || (ld_out % 8)) return fail(B200_ERR_SHAPE, "attn_fwd: column offsets / ld_out must be multiples of 8");
+  CUtensorMap tq, tkv;
+  int rc = get_tmap(q, static_cast<uint64_t>(B) * Sq, ldq, ldq, ATT_BQ, &tq);
+  if (rc) return rc;
+  rc = get_tmap(kv, static_cast<uint64_t>(B) * Sk, ldkv, ldkv, ATT_BK, &tkv);
+  if (rc) return rc;
+  static int configured = set_smem(attn_fwd_kernel, AttnFwdSmem::TOTAL);
+  if (configured != B200_OK) return configured;
+  AttnFwdArgs a{B, heads, Sq, Sk, q_col0, k_col0, v_col0, key_bias, kv_len, static_cast<__half*>(ctx), ld_out, lse2,
+                1.4426950408889634f / 8.0f};
+  dim3 grid((Sq + 2 * ATT_BQ - 1) / (2 * ATT_BQ), heads, B);
+  attn_fwd_kernel<<<grid, ATT_THREADS, AttnFwdSmem::TOTAL, static_cast<cudaStream_t>(stream)>>>(tq, tkv, a);
+  return check_launch("attn_fwd_kernel");
+}
+
+int b200_attn_probs(const void* q, int ldq, int q_col0, const void* k, int ldk, int k_col0, const float* key_bias, const float* lse2,
+                    float* probs, int B, int heads, int Sq, int Sk, void* stream) {
+  if (!lse2 || !probs) return fail(B200_ERR_SHAPE, "attn_probs: lse2 and probs are required");
+  dim3 grid((Sk + 31) / 32, (Sq + 31) / 32, B * heads);
+  attn_probs_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(q) + q_col0, ldq,
+                                                                        static_cast<const __half*>(k) + k_col0, ldk, key_bias, lse2,
+                                                                        probs, B, heads, Sq, Sk, 1.4426950408889634f / 8.0f);
+  return check_launch("attn_probs_kernel");
+}
+
+}  // extern "C"
+
+namespace {
+template <typename T>
+__global__ void mask_to_bias_kernel(const T* __restrict__ mask, float* __restrict__ bias, int32_t* __restrict__ kv_len, int S) {
+  const int b = blockIdx.x;
+  int last = 0;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    const bool keep = mask[static_cast<size_t>(b) * S + s] != T(0);
+    bias[static_cast<size_t>(b) * S + s] = keep ? 0.f : -INFINITY;
+    if (keep) last = s + 1;
+  }
+  __shared__ int red[32];
+  for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int m = 0;
+    for (int i = 0; i < (blockDim.x + 31) / 32; ++i) m = max(m, red[i]);
+    if (kv_len) kv_len[b] = m;
+  }
+}
+}  // namespace
+
+extern "C" {
+
+int b200_mask_to_bias(const void* mask, int mask_dtype, float* key_bias, int32_t* kv_len, int B, int S, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (mask_dtype == 0) mask_to_bias_kernel<int64_t><<<B, 256, 0, s>>>(static_cast<const int64_t*>(mask), key_bias, kv_len, S);
+  else if (mask_dtype == 1) mask_to_bias_kernel<float><<<B, 256, 0, s>>>(static_cast<const float*>(mask), key_bias, kv_len, S);
+  else if (mask_dtype == 2) mask_to_bias_kernel<int32_t><<<B, 256, 0, s>>>(static_cast<const int32_t*>(mask), key_bias, kv_len, S);
+  else return fail(B200_ERR_DTYPE, "mask_to_bias: dtype %d", mask_dtype);
+  return check_launch("mask_to_bias_kernel");
+}
+
+static int check_row_shape(const char* who, int rows, int H) {
+  if (rows <= 0 || H <= 0 || (H % 8) || H > ROW_MAXV * 256) return fail(B200_ERR_SHAPE, "%s: rows=%d H=%d (need H%%8==0, H<=%d)", who, rows, H, ROW_MAXV * 256);
+  return B200_OK;
+}
+
+int b200_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, void* y, float* y32, float* mean, float* rstd,
+                       int rows, int H, float eps, void* stream) {
+  if (int rc = check_row_shape("layernorm_fwd", rows, H)) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int grid = (rows + ROW_WARPS - 1) / ROW_WARPS;
+  if (x_dtype == B200_DT_F32)
+    ln_fwd_kernel<float><<<grid, ROW_WARPS * 32, 0, s>>>(static_cast<const float*>(x), gamma, beta, static_cast<__half*>(y), y32, mean, rstd, rows, H, eps);
+  else
+    ln_fwd_kernel<__half><<<grid, ROW_WARPS * 32, 0, s>>>(static_cast<const __half*>(x), gamma, beta, static_cast<__half*>(y), y32, mean, rstd, rows, H, eps);
+  return check_launch("ln_fwd_kernel");
+}
+
+int b200_layernorm_bwd(const void* dy, const void* dy2, const void* x, int x_dtype, const float* mean, const float* rstd, const float* gamma,
+                       void* dx, float* dgamma, float* dbeta, float* dbias, const float* alpha, int rows, int H, void* stream) {
+  if (int rc = check_row_shape("layernorm_bwd", rows, H)) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int grid = (rows + ROW_WARPS - 1) / ROW_WARPS;
+  const int cap = sm_count() * 8;
+  if (grid > cap) grid = cap;
+  const size_t smem = 3 * ROW_WARPS * H * sizeof(float);
+  if (x_dtype == B200_DT_F32) {
+    static int c = set_smem(ln_bwd_kernel<float>, 3 * ROW_WARPS * ROW_MAXV * 256 * 4);
+    if (c) return c;
+    ln_bwd_kernel<float><<<grid, ROW_WARPS * 32, smem, s>>>(static_cast<const __half*>(dy), static_cast<const __half*>(dy2), static_cast<const float*>(x),
+                                                           mean, rstd, gamma, static_cast<__half*>(dx), dgamma, dbeta, dbias, alpha, rows, H);
+  } else {
+    static int c = set_smem(ln_bwd_kernel<__half>, 3 * ROW_WARPS * ROW_MAXV * 256 * 4);
+    if (c) return c;
+    ln_bwd_kernel<__half><<<grid, ROW_WARPS * 32, smem, s>>>(static_cast<const __half*>(dy), static_cast<const __half*>(dy2), static_cast<const __half*>(x),
+                                                            mean, rstd, gamma, static_cast<__half*>(dx), dgamma, dbeta, dbias, alpha, rows, H);
+  }
+  return check_launch("ln_bwd_kernel");
+}
+
+int b200_embed_ln_fwd(const int64_t* ids, const int64_t* tt, const int64_t* pos, const float* inputs_embeds, const float* word,
+                      const float* pos_tab, const float* type_tab, const float* gamma, const float* beta, void* y, float* y32, int rows, int S,
+                      int H, float eps, void* stream) {
+  if (int rc = check_row_shape("embed_ln_fwd", rows, H)) return rc;
+  if (!ids && !inputs_embeds) return fail(B200_ERR_SHAPE, "embed_ln_fwd: need input_ids or inputs_embeds");
+  const int grid = (rows + ROW_WARPS - 1) / ROW_WARPS;
+  embed_ln_fwd_kernel<<<grid, ROW_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(ids, tt, pos, inputs_embeds, word, pos_tab, type_tab, gamma,
+                                                                                      beta, static_cast<__half*>(y), y32, rows, S, H, eps);
+  return check_launch("embed_ln_fwd_kernel");
+}
+
+int b200_embed_ln_bwd(const void* dy, const void* dy2, const int64_t* ids, const int64_t* tt, const int64_t* pos, const float* word,
+                      const float* pos_tab, const float* type_tab, const float* gamma, float* dword, float* dpos, float* dtype_tab,
+                      float* dgamma, float* dbeta, const float* alpha, int rows, int S, int H, float eps, void* stream) {
+  if (int rc = check_row_shape("embed_ln_bwd", rows, H)) return rc;
+  const int grid = (rows + ROW_WARPS - 1) / ROW_WARPS;
+  embed_ln_bwd_kernel<<<grid, ROW_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(dy), static_cast<const __half*>(dy2), ids, tt, pos, word, pos_tab, type_tab, gamma, dword, dpos, dtype_tab,
+      dgamma, dbeta, alpha, rows, S, H, eps);
+  return check_launch("embed_ln_bwd_kernel");
+}
+
+int b200_cls_head_fwd(const void* h, const float* W, const float* b, float* logits, int32_t* argmax, int rows, int H, int C, void* stream) {
+  if (int rc = check_row_shape("cls_head_fwd", rows, H)) return rc;
+  const int grid = (rows + ROW_WARPS - 1) / ROW_WARPS;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (C == 2) cls_head_fwd_kernel<2><<<grid, ROW_WARPS * 32, 0, s>>>(static_cast<const __half*>(h), W, b, logits, argmax, rows, H);
+  else if (C == 3) cls_head_fwd_kernel<3><<<grid, ROW_WARPS * 32, 0, s>>>(static_cast<const __half*>(h), W, b, logits, argmax, rows, H);
+  else return fail(B200_ERR_SHAPE, "cls_head_fwd: C=%d (2 or 3)", C);
+  return check_launch("cls_head_fwd_kernel");
+}
+
+int b200_ce_stats(const float* logits, const int64_t* labels, const float* class_weight, float* stats, int rows, int C, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int grid = (rows + 255) / 256;
+  if (grid > 592) grid = 592;
+  if (C == 2) ce_stats_kernel<2><<<grid, 256, 0, s>>>(logits, labels, class_weight, stats, rows);
+  else if (C == 3) ce_stats_kernel<3><<<grid, 256, 0, s>>>(logits, labels, class_weight, stats, rows);
+  else return fail(B200_ERR_SHAPE, "ce_stats: C=%d (2 or 3)", C);
+  return check_launch("ce_stats_kernel");
+}
+
+int b200_cls_head_bwd(const void* h, const float* logits, const int64_t* labels, const float* class_weight, const float* stats, const float* W,
+                      const float* scale, void* dh, float* dW, float* db, int rows, int H, int C, void* stream) {
+  if (int rc = check_row_shape("cls_head_bwd", rows, H)) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int grid = (rows + ROW_WARPS - 1) / ROW_WARPS;
+  const int cap = sm_count() * 8;
+  if (grid > cap) grid = cap;
+  const size_t smem = static_cast<size_t>(ROW_WARPS) * C * H * sizeof(float);
+  if (C == 2) {
+    static int c = set_smem(cls_head_bwd_kernel<2>, ROW_WARPS * 2 * ROW_MAXV * 256 * 4);
+    if (c) return c;
+    cls_head_bwd_kernel<2><<<grid, ROW_WARPS * 32, smem, s>>>(static_cast<const __half*>(h), logits, labels, class_weight, stats, W, scale,
+                                                             static_cast<__half*>(dh), dW, db, rows, H);
+  } else if (C == 3) {
+    static int c = set_smem(cls_head_bwd_kernel<3>, ROW_WARPS * 3 * ROW_MAXV * 256 * 4);
+    if (c) return c;
+    cls_head_bwd_kernel<3><<<grid, ROW_WARPS * 32, smem, s>>>(static_cast<const __half*>(h), logits, labels, class_weight, stats, W, scale,
+                                                             static_cast<__half*>(dh), dW, db, rows, H);
+  } else {
+    return fail(B200_ERR_SHAPE, "cls_head_bwd: C=%d (2 or 3)", C);
+  }
+  return check_launch("cls_head_bwd_kernel");
+}
+
+int b200_colsum(const void* dy, int ld, float* db, const float* alpha, int rows, int cols, void* stream) {
+  if ((cols % 8) || (ld % 8)) return fail(B200_ERR_SHAPE, "colsum: cols/ld must be multiples of 8");
+  int slabs = (rows + 511) / 512;
+  if (slabs < 1) slabs = 1;
+  const int rpb = (rows + slabs - 1) / slabs;
+  dim3 grid((cols + 63) / 64, slabs);
+  colsum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(dy), ld, db, alpha, rows, cols, rpb);
+  return check_launch("colsum_kernel");
+}
+
+static int stream_grid(size_t n8) {
+  size_t g = (n8 + 255) / 256;
+  const size_t cap = static_cast<size_t>(sm_count()) * 16;
+  return static_cast<int>(g < cap ? (g ? g : 1) : cap);
+}
+
+int b200_cast_f32_to_f16(const float* src, void* dst, size_t n, void* stream) {
+  if (n % 8) return fail(B200_ERR_SHAPE, "cast: n %% 8 != 0");
+  cast_f32_f16_kernel<<<stream_grid(n / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, static_cast<__half*>(dst), n / 8);
+  return check_launch("cast_f32_f16_kernel");
+}
+int b200_cast_f16_to_f32(const void* src, float* dst, size_t n, void* stream) {
+  if (n % 8) return fail(B200_ERR_SHAPE, "cast: n %% 8 != 0");
+  cast_f16_f32_kernel<<<stream_grid(n / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(src), dst, n / 8);
+  return check_launch("cast_f16_f32_kernel");
+}
+int b200_scale_cast_grad(const float* src, void* dst, size_t n, float target, float* scale, void* amax_slot, void* stream) {
+  if (n % 8) return fail(B200_ERR_SHAPE, "scale_cast: n %% 8 != 0");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaMemsetAsync(amax_slot, 0, 4, s);
+  amax_f32_kernel<<<stream_grid(n / 8), 256, 0, s>>>(src, n, static_cast<unsigned int*>(amax_slot));
+  if (int rc = check_launch("amax_f32_kernel")) return rc;
+  pick_scale_kernel<<<1, 1, 0, s>>>(static_cast<const unsigned int*>(amax_slot), target, scale);
+  if (int rc = check_launch("pick_scale_kernel")) return rc;
+  scale_cast_f32_f16_kernel<<<stream_grid(n / 8), 256, 0, s>>>(src, scale, static_cast<__half*>(dst), n / 8);
+  return check_launch("scale_cast_f32_f16_kernel");
+}
+
+}  // extern "C"
+
+#include "api_train.inc"

@@ -1,0 +1,532 @@
+// HBM-bound row-wise kernels: warp-per-row, 128-bit vectorised, warp-shuffle
+// reductions, fp32 statistics.  Rows hold H <= 1024 elements (H % 8 == 0) and stay in registers between the
+// statistics pass and the normalisation pass, so every activation byte is read exactly once.
+#pragma once
+#include "ptx.cuh"
+
+namespace b200 {
+
+constexpr int ROW_MAXV = 4;          // 4 x (32 lanes x 8 elements) = 1024 columns max
+constexpr int ROW_WARPS = 4;
+
+struct Vec8 {
+  float v[8];
+};
+
+__device__ __forceinline__ Vec8 load8(const __half* p) {
+  const uint4 raw = *reinterpret_cast<const uint4*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&raw);
+  Vec8 r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(h[i]);
+    r.v[2 * i] = f.x;
+    r.v[2 * i + 1] = f.y;
+  }
+  return r;
+}
+__device__ __forceinline__ Vec8 load8(const float* p) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  Vec8 r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ void store8(__half* p, const Vec8& r) {
+  uint4 raw;
+  __half2* h = reinterpret_cast<__half2*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(r.v[2 * i], r.v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = raw;
+}
+__device__ __forceinline__ void store8(float* p, const Vec8& r) {
+  *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+
+// Row statistics over values already in registers.  Two-pass (mean, then centred variance) like the reference.
+__device__ __forceinline__ void row_stats(const Vec8 (&x)[ROW_MAXV], int nv_lane, int H, float eps, float& mean, float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < ROW_MAXV; ++i)
+    if (i < nv_lane)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += x[i].v[j];
+  mean = warp_sum(s) / H;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < ROW_MAXV; ++i)
+    if (i < nv_lane)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = x[i].v[j] - mean;
+        q = fmaf(d, d, q);
+      }
+  rstd = rsqrtf(warp_sum(q) / H + eps);
+}
+
+// number of 8-wide vectors this lane owns: vector index = i*32 + lane, valid while (i*32+lane)*8 < H
+__device__ __forceinline__ int lane_vecs(int H, int lane) {
+  const int nvec = H >> 3;
+  return (nvec - lane + 31) / 32 > 0 ? (nvec - lane + 31) / 32 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------ K7: LayerNorm fwd
+// y = (x - mean) * rstd * gamma + beta.  x: fp32 or fp16 pre-LN sum; y: fp16 (+ optional fp32 copy).
+template <typename InT>
+__global__ void __launch_bounds__(ROW_WARPS * 32) ln_fwd_kernel(const InT* __restrict__ x, const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, __half* __restrict__ y,
+                                                                 float* __restrict__ y32, float* __restrict__ mean_out,
+                                                                 float* __restrict__ rstd_out, int rows, int H, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nv = lane_vecs(H, lane);
+  Vec8 v[ROW_MAXV];
+  const InT* xr = x + static_cast<size_t>(row) * H;
+#pragma unroll
+  for (int i = 0; i < ROW_MAXV; ++i)
+    if (i < nv) v[i] = load8(xr + (i * 32 + lane) * 8);
+  float mean, rstd;
+  row_stats(v, nv, H, eps, mean, rstd);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+#pragma unroll
+  for (int i = 0; i < ROW_MAXV; ++i)
+    if (i < nv) {
+      const int c = (i * 32 + lane) * 8;
+      const Vec8 g = load8(gamma + c), b = load8(beta + c);
+      Vec8 o;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o.v[j] = fmaf((v[i].v[j] - mean) * rstd, g.v[j], b.v[j]);
+      store8(y + static_cast<size_t>(row) * H + c, o);
+      if (y32) store8(y32 + static_cast<size_t>(row) * H + c, o);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K10: LayerNorm bwd
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
+// dgamma += alpha * sum_rows dy * xhat;  dbeta += alpha * sum_rows dy;  dbias += alpha * sum_rows dx (optional: the
+// bias of the dense layer that produced the pre-LN sum).  `dy2` (optional) is a second upstream gradient added to dy
+// (the residual branch that by-passes the next block).
+template <typename InT>
+__global__ void __launch_bounds__(ROW_WARPS * 32) ln_bwd_kernel(const __half* __restrict__ dy, const __half* __restrict__ dy2,
+                                                                 const InT* __restrict__ x, const float* __restrict__ mean_in,
+                                                                 const float* __restrict__ rstd_in, const float* __restrict__ gamma,
+                                                                 __half* __restrict__ dx, float* __restrict__ dgamma,
+                                                                 float* __restrict__ dbeta, float* __restrict__ dbias,
+                                                                 const float* __restrict__ alpha_ptr, int rows, int H) {
+  extern __shared__ float red[];   // [3][ROW_WARPS][H]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nv = lane_vecs(H, lane);
+  Vec8 ag[ROW_MAXV], ab[ROW_MAXV], ad[ROW_MAXV];
+#pragma unroll
+  for (int i = 0; i < ROW_MAXV; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ag[i].v[j] = ab[i].v[j] = ad[i].v[j] = 0.f;
+  Vec8 gm[ROW_MAXV];
+#pragma unroll
+  for (int i = 0; i < ROW_MAXV; ++i)
+    if (i < nv) gm[i] = load8(gamma + (i * 32 + lane) * 8);
+
+  for (int row = blockIdx.x * ROW_WARPS + warp; row < rows; row += gridDim.x * ROW_WARPS) {
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    Vec8 xh[ROW_MAXV], g[ROW_MAXV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < ROW_MAXV; ++i)
+      if (i < nv) {
+        const size_t off = static_cast<size_t>(row) * H + (i * 32 + lane) * 8;
+        const Vec8 xv = load8(x + off);
+        Vec8 d = load8(dy + off);
+        if (dy2) {
+          const Vec8 d2 = load8(dy2 + off);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d.v[j] += d2.v[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[i].v[j] = (xv.v[j] - mean) * rstd;
+          g[i].v[j] = d.v[j] * gm[i].v[j];
+          s1 += g[i].v[j];
+          s2 = fmaf(g[i].v[j], xh[i].v[j], s2);
+          ag[i].v[j] = fmaf(d.v[j], xh[i].v[j], ag[i].v[j]);
+          ab[i].v[j] += d.v[j];
+        }
+      }
+    s1 = warp_sum(s1) / H;
+    s2 = warp_sum(s2) / H;
+#pragma unroll
+    for (int i = 0; i < ROW_MAXV; ++i)
+      if (i < nv) {
+        Vec8 o;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          o.v[j] = rstd * (g[i].v[j] - s1 - xh[i].v[j] * s2);
+          ad[i].v[j] += o.v[j];
+        }
+        store8(dx + static_cast<size_t>(row) * H + (i * 32 + lane) * 8, o);
+      }
+  }
+  // block reduction of the column sums, then one atomic per column per block
+  float* rg = red;
+  float* rb = red + ROW_WARPS * H;
+  float* rd = red + 2 * ROW_WARPS * H;
+#pragma unroll
+  for (int i = 0; i < ROW_MAXV; ++i)
+    if (i < nv) {
+      const int c = (i * 32 + lane) * 8;
+      store8(rg + warp * H + c, ag[i]);
+      store8(rb + warp * H + c, ab[i]);
+      store8(rd + warp * H + c, ad[i]);
+    }
+  __syncthreads();
+  const float alpha = alpha_ptr ? *alpha_ptr : 1.0f;
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    float a = 0.f, b = 0.f, d = 0.f;
+#pragma unroll
+    for (int w = 0; w < ROW_WARPS; ++w) {
+      a += rg[w * H + c];
+      b += rb[w * H + c];
+      d += rd[w * H + c];
+    }
+    atomicAdd(dgamma + c, a * alpha);
+    atomicAdd(dbeta + c, b * alpha);
+    if (dbias) atomicAdd(dbias + c, d * alpha);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K1: embeddings
+// y = LN(word[ids] + pos[pos_ids] + type[tt]); tables are the fp32 master parameters (gathered rows, 128-bit loads).
+// bert_model.py:184-210.  `inputs_embeds` (fp32 [rows,H]) replaces the word gather when given.
+__global__ void __launch_bounds__(ROW_WARPS * 32) embed_ln_fwd_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ tt,
+                                                                       const int64_t* __restrict__ pos, const float* __restrict__ inputs_embeds,
+                                                                       const float* __restrict__ word, const float* __restrict__ pos_tab,
+                                                                       const float* __restrict__ type_tab, const float* __restrict__ gamma,
+                                                                       const float* __restrict__ beta, __half* __restrict__ y,
+                                                                       float* __restrict__ y32, int rows, int S, int H, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nv = lane_vecs(H, lane);
+  const float* w = inputs_embeds ? inputs_embeds + static_cast<size_t>(row) * H : word + static_cast<size_t>(ids[row]) * H;
+  const float* p = pos_tab + static_cast<size_t>(pos ? pos[row] : (row % S)) * H;
+  const float* t = type_tab + static_cast<size_t>(tt ? tt[row] : 0) * H;
+  Vec8 v[ROW_MAXV];
+#pragma unroll
+  for (int i = 0; i < ROW_MAXV; ++i)
+    if (i < nv) {
+      const int c = (i * 32 + lane) * 8;
+      const Vec8 a = load8(w + c), b = load8(p + c), d = load8(t + c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[i].v[j] = a.v[j] + d.v[j] + b.v[j];
+    }
+  float mean, rstd;
+  row_stats(v, nv, H, eps, mean, rstd);
+#pragma unroll
+  for (int i = 0; i < ROW_MAXV; ++i)
+    if (i < nv) {
+      const int c = (i * 32 + lane) * 8;
+      const Vec8 g = load8(gamma + c), b = load8(beta + c);
+      Vec8 o;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o.v[j] = fmaf((v[i].v[j] - mean) * rstd, g.v[j], b.v[j]);
+      store8(y + static_cast<size_t>(row) * H + c, o);
+      if (y32) store8(y32 + static_cast<size_t>(row) * H + c, o);
+    }
+}
+
+// Backward of the embedding block: recompute the pre-LN sum and its statistics (cheaper than saving them), LN bwd,
+// then scatter-add dx into the three fp32 gradient tables.
+__global__ void __launch_bounds__(ROW_WARPS * 32) embed_ln_bwd_kernel(const __half* __restrict__ dy, const __half* __restrict__ dy2,
+                                                                       const int64_t* __restrict__ ids, const int64_t* __restrict__ tt,
+                                                                       const int64_t* __restrict__ pos, const float* __restrict__ word,
+                                                                       const float* __restrict__ pos_tab, const float* __restrict__ type_tab,
+                                                                       const float* __restrict__ gamma, float* __restrict__ dword,
+                                                                       float* __restrict__ dpos, float* __restrict__ dtype_tab,
+                                                                       float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                       const float* __restrict__ alpha_ptr, int rows, int S, int H, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float alpha = alpha_ptr ? *alpha_ptr : 1.0f;
+  const int nv = lane_vecs(H, lane);
+  const size_t wi = static_cast<size_t>(ids[row]), pi = static_cast<size_t>(pos ? pos[row] : (row % S)), ti = static_cast<size_t>(tt ? tt[row] : 0);
+  Vec8 v[ROW_MAXV];
+#pragma unroll
+  for (int i = 0; i < ROW_MAXV; ++i)
+    if (i < nv) {
+      const int c = (i * 32 + lane) * 8;
+      const Vec8 a = load8(word + wi * H + c), b = load8(pos_tab + pi * H + c), d = load8(type_tab + ti * H + c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[i].v[j] = a.v[j] + d.v[j] + b.v[j];
+    }
+  float mean, rstd;
+  row_stats(v, nv, H, eps, mean, rstd);
+  Vec8 g[ROW_MAXV], d[ROW_MAXV];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < ROW_MAXV; ++i)
+    if (i < nv) {
+      const int c = (i * 32 + lane) * 8;
+      const size_t off = static_cast<size_t>(row) * H + c;
+      d[i] = load8(dy + off);
+      if (dy2) {
+        const Vec8 d2 = load8(dy2 + off);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[i].v[j] += d2.v[j];
+      }
+      const Vec8 gm = load8(gamma + c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[i].v[j] = (v[i].v[j] - mean) * rstd;      // xhat
+        g[i].v[j] = d[i].v[j] * gm.v[j];
+        s1 += g[i].v[j];
+        s2 = fmaf(g[i].v[j], v[i].v[j], s2);
+      }
+    }
+  s1 = warp_sum(s1) / H;
+  s2 = warp_sum(s2) / H;
+#pragma unroll
+  for (int i = 0; i < ROW_MAXV; ++i)
+    if (i < nv) {
+      const int c = (i * 32 + lane) * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float dxv = rstd * (g[i].v[j] - s1 - v[i].v[j] * s2) * alpha;
+        atomicAdd(dword + wi * H + c + j, dxv);
+        atomicAdd(dpos + pi * H + c + j, dxv);
+        atomicAdd(dtype_tab + ti * H + c + j, dxv);
+        atomicAdd(dgamma + c + j, d[i].v[j] * v[i].v[j] * alpha);
+        atomicAdd(dbeta + c + j, d[i].v[j] * alpha);
+      }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K11: token-cls head
+// logits[row, c] = h[row,:] . W[c,:] + b[c]   (C <= 4 classes; Linear(H -> 2/3): loss_calculator.py:17,42,
+// modeling_ponet.py:43,83-84).  HBM-bound GEMV-like: each warp streams one row with 128-bit loads.
+template <int C>
+__global__ void __launch_bounds__(ROW_WARPS * 32) cls_head_fwd_kernel(const __half* __restrict__ h, const float* __restrict__ W,
+                                                                       const float* __restrict__ b, float* __restrict__ logits,
+                                                                       int32_t* __restrict__ argmax_out, int rows, int H) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nv = lane_vecs(H, lane);
+  float acc[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) acc[c] = 0.f;
+#pragma unroll
+  for (int i = 0; i < ROW_MAXV; ++i)
+    if (i < nv) {
+      const int col = (i * 32 + lane) * 8;
+      const Vec8 x = load8(h + static_cast<size_t>(row) * H + col);
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const Vec8 w = load8(W + static_cast<size_t>(c) * H + col);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[c] = fmaf(x.v[j], w.v[j], acc[c]);
+      }
+    }
+#pragma unroll
+  for (int c = 0; c < C; ++c) acc[c] = warp_sum(acc[c]) + b[c];
+  if (lane == 0) {
+    int best = 0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      logits[static_cast<size_t>(row) * C + c] = acc[c];
+      if (acc[c] > acc[best]) best = c;     // first maximum wins, like np.argmax
+    }
+    if (argmax_out) argmax_out[row] = best;
+  }
+}
+
+// Cross-entropy statistics over logits (ignore_index = -100, optional class weights): stats[0] += sum w*nll,
+// stats[1] += sum w.   utils.py:173-182 (gamma == 0 path).
+template <int C>
+__global__ void ce_stats_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, const float* __restrict__ cw,
+                                float* __restrict__ stats, int rows) {
+  float l = 0.f, w = 0.f;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
+    const int64_t y = labels[r];
+    if (y < 0 || y >= C) continue;
+    float m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < C; ++c) m = fmaxf(m, logits[static_cast<size_t>(r) * C + c]);
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) s += expf(logits[static_cast<size_t>(r) * C + c] - m);
+    const float wy = cw ? cw[y] : 1.0f;
+    l += wy * (m + logf(s) - logits[static_cast<size_t>(r) * C + y]);
+    w += wy;
+  }
+  l = warp_sum(l);
+  w = warp_sum(w);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(stats, l);
+    atomicAdd(stats + 1, w);
+  }
+}
+
+// Backward of head + mean CE in one pass over h: dlogits = w_y (softmax - onehot) / sum_w;
+// dh = scale * dlogits . W (fp16);  dW += dlogits^T h;  db += sum dlogits.
+template <int C>
+__global__ void __launch_bounds__(ROW_WARPS * 32) cls_head_bwd_kernel(const __half* __restrict__ h, const float* __restrict__ logits,
+                                                                       const int64_t* __restrict__ labels, const float* __restrict__ cw,
+                                                                       const float* __restrict__ stats, const float* __restrict__ W,
+                                                                       const float* __restrict__ scale_ptr, __half* __restrict__ dh,
+                                                                       float* __restrict__ dW, float* __restrict__ db, int rows, int H) {
+  extern __shared__ float red[];   // [ROW_WARPS][C][H]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nv = lane_vecs(H, lane);
+  const float inv_w = 1.0f / stats[1];
+  const float scale = scale_ptr ? *scale_ptr : 1.0f;
+  Vec8 aw[C][ROW_MAXV];
+  float abias[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    abias[c] = 0.f;
+#pragma unroll
+    for (int i = 0; i < ROW_MAXV; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) aw[c][i].v[j] = 0.f;
+  }
+  for (int row = blockIdx.x * ROW_WARPS + warp; row < rows; row += gridDim.x * ROW_WARPS) {
+    const int64_t y = labels[row];
+    float dl[C];
+    const bool valid = (y >= 0 && y < C);
+    if (valid) {
+      float m = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < C; ++c) m = fmaxf(m, logits[static_cast<size_t>(row) * C + c]);
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        dl[c] = expf(logits[static_cast<size_t>(row) * C + c] - m);
+        s += dl[c];
+      }
+      const float wy = (cw ? cw[y] : 1.0f) * inv_w;
+#pragma unroll
+      for (int c = 0; c < C; ++c) dl[c] = wy * (dl[c] / s - (c == y ? 1.0f : 0.0f));
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) dl[c] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < ROW_MAXV; ++i)
+      if (i < nv) {
+        const int col = (i * 32 + lane) * 8;
+        const size_t off = static_cast<size_t>(row) * H + col;
+        Vec8 o;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o.v[j] = 0.f;
+        if (valid) {
+          const Vec8 x = load8(h + off);
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const Vec8 w = load8(W + static_cast<size_t>(c) * H + col);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              o.v[j] = fmaf(dl[c] * scale, w.v[j], o.v[j]);
+              aw[c][i].v[j] = fmaf(dl[c], x.v[j], aw[c][i].v[j]);
+            }
+          }
+        }
+        store8(dh + off, o);
+      }
+    if (valid && lane == 0)
+#pragma unroll
+      for (int c = 0; c < C; ++c) abias[c] += dl[c];
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+#pragma unroll
+    for (int i = 0; i < ROW_MAXV; ++i)
+      if (i < nv) store8(red + (warp * C + c) * H + (i * 32 + lane) * 8, aw[c][i]);
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < C * H; idx += blockDim.x) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < ROW_WARPS; ++w) a += red[w * C * H + idx];
+    atomicAdd(dW + idx, a);
+  }
+  if (lane == 0)
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      if (abias[c] != 0.f) atomicAdd(db + c, abias[c]);
+}
+
+// ------------------------------------------------------------------------------------------------ misc streaming kernels
+// db[n] += alpha * sum_m dY[m, n]  (bias gradients of QKV / FFN-up).  Each block: 64 columns x a slab of rows.
+__global__ void __launch_bounds__(256) colsum_kernel(const __half* __restrict__ dy, int ld, float* __restrict__ db,
+                                                     const float* __restrict__ alpha_ptr, int rows, int cols, int rows_per_block) {
+  __shared__ float red[32][65];
+  const int cg = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int c0 = blockIdx.x * 64 + cg * 8;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(rows, r0 + rows_per_block);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (c0 < cols)
+    for (int r = r0 + rl; r < r1; r += 32) {
+      const Vec8 v = load8(dy + static_cast<size_t>(r) * ld + c0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v.v[j];
+    }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[rl][cg * 8 + j] = acc[j];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) s += red[r][threadIdx.x];
+    const int c = blockIdx.x * 64 + threadIdx.x;
+    if (c < cols) atomicAdd(db + c, s * (alpha_ptr ? *alpha_ptr : 1.0f));
+  }
+}
+
+// fp32 -> fp16 (parameter compute copies)
+__global__ void cast_f32_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t n8) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n8; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    store8(dst + i * 8, load8(src + i * 8));
+}
+// fp16 -> fp32
+__global__ void cast_f16_f32_kernel(const __half* __restrict__ src, float* __restrict__ dst, size_t n8) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n8; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    store8(dst + i * 8, load8(src + i * 8));
+}
+
+// amax(|x|) over an fp32 tensor -> slot[0] (as float bits via atomicMax on uint: valid for non-negative floats)
+__global__ void amax_f32_kernel(const float* __restrict__ x, size_t n, unsigned int* __restrict__ slot) {
+  float m = 0.f;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    m = fmaxf(m, fabsf(x[i]));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) atomicMax(slot, __float_as_uint(m));
+}
+// scale[0] = 2^floor(log2(target / amax)), scale[1] = 1/scale[0]   (power of two: exact to apply and undo)
+__global__ void pick_scale_kernel(const unsigned int* __restrict__ amax_slot, float target, float* __restrict__ scale) {
+  const float a = __uint_as_float(*amax_slot);
+  float s = 1.0f;
+  if (a > 0.f && isfinite(a)) s = exp2f(floorf(log2f(target / a)));
+  s = fminf(fmaxf(s, 1.0f), 16777216.0f);
+  scale[0] = s;
+  scale[1] = 1.0f / s;
+}
+// dst(fp16) = src(fp32) * scale[0]
+__global__ void scale_cast_f32_f16_kernel(const float* __restrict__ src, const float* __restrict__ scale, __half* __restrict__ dst, size_t n8) {
+  const float s = scale ? scale[0] : 1.0f;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n8; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    Vec8 v = load8(src + i * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v.v[j] *= s;
+    store8(dst + i * 8, v);
+  }
+}
+
+}  // namespace b200

@@ -1,0 +1,186 @@
+"""Tensor-level wrappers over the C ABI: each function takes torch CUDA tensors, checks
+dtype/contiguity, and enqueues one library call on torch's current stream.  PyTorch is used
+for device memory and streams only; no arithmetic happens here."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import lib as L
+from .lib import (DT_F16, DT_F32, EPI_ADD, EPI_ATOMIC, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_DGELU,  # noqa: F401
+                  EPI_STORE)
+
+Tensor = torch.Tensor
+
+
+def _ptr(t: Optional[Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _req(t: Tensor, dtype, name: str):
+    if not t.is_cuda:
+        raise L.B200Error(f"{name}: expected a CUDA tensor (the B200 path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise L.B200Error(f"{name}: expected {dtype}, got {t.dtype}")
+    if t.stride(-1) != 1:
+        raise L.B200Error(f"{name}: last dim must be contiguous")
+    return t
+
+
+def _dt(t: Tensor) -> int:
+    return DT_F32 if t.dtype == torch.float32 else DT_F16
+
+
+def gemm(a: Tensor, b: Tensor, out: Tensor, *, a_layout: int = 0, b_layout: int = 0, epilogue: int = EPI_STORE,
+         bias: Optional[Tensor] = None, aux: Optional[Tensor] = None, out2: Optional[Tensor] = None,
+         alpha: Optional[Tensor] = None, k_splits: int = 1) -> Tensor:
+    """out[M,N] = epilogue(A @ B^T).  a_layout/b_layout = 1 means the operand is stored transposed
+    ([K,M] / [K,N] row-major) and is fed MN-major to the tensor core."""
+    _req(a, torch.float16, "A"), _req(b, torch.float16, "B")
+    M = a.shape[0] if a_layout == 0 else a.shape[1]
+    K = a.shape[1] if a_layout == 0 else a.shape[0]
+    N = b.shape[0] if b_layout == 0 else b.shape[1]
+    Kb = b.shape[1] if b_layout == 0 else b.shape[0]
+    if K != Kb or tuple(out.shape) != (M, N):
+        raise L.B200Error(f"gemm: shape mismatch A{tuple(a.shape)}/{a_layout} B{tuple(b.shape)}/{b_layout} out{tuple(out.shape)}")
+    rc = L.load().b200_gemm_f16(_ptr(a), a.stride(0), a_layout, _ptr(b), b.stride(0), b_layout, M, N, K, epilogue,
+                                _ptr(bias), _ptr(aux), aux.stride(0) if aux is not None else 0, _ptr(out), out.stride(0),
+                                _dt(out), _ptr(out2), out2.stride(0) if out2 is not None else 0, _ptr(alpha), k_splits,
+                                _stream())
+    L.check(rc, "b200_gemm_f16")
+    return out
+
+
+def wgrad_splits(M_out: int, N_in: int, K_tokens: int, sms: int = 148) -> int:
+    """Split-K factor for a weight-gradient GEMM so the persistent grid fills the SMs."""
+    tiles = ((M_out + 127) // 128) * ((N_in + 255) // 256)
+    kb = (K_tokens + 63) // 64
+    s = max(1, min(kb, (2 * sms + tiles - 1) // tiles))
+    while s > 1 and (kb + s - 1) // s * (s - 1) >= kb:   # avoid empty splits
+        s -= 1
+    return s
+
+
+def attn_fwd(q: Tensor, kv: Tensor, ctx: Tensor, B: int, heads: int, Sq: int, Sk: int, *, q_col0: int, k_col0: int,
+             v_col0: int, key_bias: Optional[Tensor] = None, kv_len: Optional[Tensor] = None,
+             lse2: Optional[Tensor] = None) -> Tensor:
+    _req(q, torch.float16, "q"), _req(kv, torch.float16, "kv"), _req(ctx, torch.float16, "ctx")
+    rc = L.load().b200_attn_fwd(_ptr(q), q.stride(0), q_col0, _ptr(kv), kv.stride(0), k_col0, v_col0, _ptr(key_bias),
+                                _ptr(kv_len), _ptr(ctx), ctx.stride(0), _ptr(lse2), B, heads, Sq, Sk, _stream())
+    L.check(rc, "b200_attn_fwd")
+    return ctx
+
+
+def attn_probs(q: Tensor, k: Tensor, lse2: Tensor, B: int, heads: int, Sq: int, Sk: int, *, q_col0: int, k_col0: int,
+               key_bias: Optional[Tensor] = None) -> Tensor:
+    probs = torch.empty(B, heads, Sq, Sk, dtype=torch.float32, device=q.device)
+    rc = L.load().b200_attn_probs(_ptr(q), q.stride(0), q_col0, _ptr(k), k.stride(0), k_col0, _ptr(key_bias), _ptr(lse2),
+                                  _ptr(probs), B, heads, Sq, Sk, _stream())
+    L.check(rc, "b200_attn_probs")
+    return probs
+
+
+def mask_to_bias(mask: Tensor):
+    """[B,S] 0/1 mask -> (key_bias fp32 [B,S], kv_len int32 [B])."""
+    B, S = mask.shape
+    mask = mask.contiguous()
+    code = {torch.int64: 0, torch.float32: 1, torch.int32: 2}.get(mask.dtype)
+    if code is None:
+        mask = mask.to(torch.int64)
+        code = 0
+    bias = torch.empty(B, S, dtype=torch.float32, device=mask.device)
+    kv_len = torch.empty(B, dtype=torch.int32, device=mask.device)
+    L.check(L.load().b200_mask_to_bias(_ptr(mask), code, _ptr(bias), _ptr(kv_len), B, S, _stream()), "b200_mask_to_bias")
+    return bias, kv_len
+
+
+def layernorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, eps: float, *, y: Optional[Tensor] = None,
+                  y32: Optional[Tensor] = None, mean: Optional[Tensor] = None, rstd: Optional[Tensor] = None) -> Tensor:
+    rows, H = x.shape
+    if y is None:
+        y = torch.empty(rows, H, dtype=torch.float16, device=x.device)
+    rc = L.load().b200_layernorm_fwd(_ptr(x), _dt(x), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(y32), _ptr(mean), _ptr(rstd),
+                                     rows, H, float(eps), _stream())
+    L.check(rc, "b200_layernorm_fwd")
+    return y
+
+
+def layernorm_bwd(dy: Tensor, x: Tensor, mean: Tensor, rstd: Tensor, gamma: Tensor, dx: Tensor, dgamma: Tensor,
+                  dbeta: Tensor, *, dy2: Optional[Tensor] = None, dbias: Optional[Tensor] = None,
+                  alpha: Optional[Tensor] = None) -> Tensor:
+    rows, H = x.shape
+    rc = L.load().b200_layernorm_bwd(_ptr(dy), _ptr(dy2), _ptr(x), _dt(x), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dx),
+                                     _ptr(dgamma), _ptr(dbeta), _ptr(dbias), _ptr(alpha), rows, H, _stream())
+    L.check(rc, "b200_layernorm_bwd")
+    return dx
+
+
+def embed_ln_fwd(ids, tt, pos, inputs_embeds, word, pos_tab, type_tab, gamma, beta, eps, rows, S, H, *, y=None, y32=None):
+    if y is None:
+        y = torch.empty(rows, H, dtype=torch.float16, device=word.device)
+    rc = L.load().b200_embed_ln_fwd(_ptr(ids), _ptr(tt), _ptr(pos), _ptr(inputs_embeds), _ptr(word), _ptr(pos_tab),
+                                    _ptr(type_tab), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(y32), rows, S, H, float(eps),
+                                    _stream())
+    L.check(rc, "b200_embed_ln_fwd")
+    return y
+
+
+def embed_ln_bwd(dy, dy2, ids, tt, pos, word, pos_tab, type_tab, gamma, dword, dpos, dtype_tab, dgamma, dbeta, alpha, eps,
+                 rows, S, H):
+    rc = L.load().b200_embed_ln_bwd(_ptr(dy), _ptr(dy2), _ptr(ids), _ptr(tt), _ptr(pos), _ptr(word), _ptr(pos_tab),
+                                    _ptr(type_tab), _ptr(gamma), _ptr(dword), _ptr(dpos), _ptr(dtype_tab), _ptr(dgamma),
+                                    _ptr(dbeta), _ptr(alpha), rows, S, H, float(eps), _stream())
+    L.check(rc, "b200_embed_ln_bwd")
+
+
+def cls_head_fwd(h: Tensor, W: Tensor, b: Tensor, *, want_argmax: bool = False):
+    rows, H = h.shape
+    Cn = W.shape[0]
+    logits = torch.empty(rows, Cn, dtype=torch.float32, device=h.device)
+    am = torch.empty(rows, dtype=torch.int32, device=h.device) if want_argmax else None
+    rc = L.load().b200_cls_head_fwd(_ptr(h), _ptr(W), _ptr(b), _ptr(logits), _ptr(am), rows, H, Cn, _stream())
+    L.check(rc, "b200_cls_head_fwd")
+    return (logits, am) if want_argmax else logits
+
+
+def ce_stats(logits: Tensor, labels: Tensor, stats: Tensor, class_weight: Optional[Tensor] = None) -> Tensor:
+    rows, Cn = logits.shape
+    L.check(L.load().b200_ce_stats(_ptr(logits), _ptr(labels), _ptr(class_weight), _ptr(stats), rows, Cn, _stream()),
+            "b200_ce_stats")
+    return stats
+
+
+def cls_head_bwd(h, logits, labels, stats, W, dh, dW, db, *, class_weight=None, scale=None):
+    rows, H = h.shape
+    rc = L.load().b200_cls_head_bwd(_ptr(h), _ptr(logits), _ptr(labels), _ptr(class_weight), _ptr(stats), _ptr(W),
+                                    _ptr(scale), _ptr(dh), _ptr(dW), _ptr(db), rows, H, W.shape[0], _stream())
+    L.check(rc, "b200_cls_head_bwd")
+    return dh
+
+
+def colsum(dy: Tensor, db: Tensor, alpha: Optional[Tensor] = None) -> Tensor:
+    rows, cols = dy.shape
+    L.check(L.load().b200_colsum(_ptr(dy), dy.stride(0), _ptr(db), _ptr(alpha), rows, cols, _stream()), "b200_colsum")
+    return db
+
+
+def cast_f32_to_f16(src: Tensor, dst: Tensor) -> Tensor:
+    L.check(L.load().b200_cast_f32_to_f16(_ptr(src), _ptr(dst), src.numel(), _stream()), "b200_cast_f32_to_f16")
+    return dst
+
+
+def cast_f16_to_f32(src: Tensor, dst: Tensor) -> Tensor:
+    L.check(L.load().b200_cast_f16_to_f32(_ptr(src), _ptr(dst), src.numel(), _stream()), "b200_cast_f16_to_f32")
+    return dst
+
+
+def scale_cast_grad(src: Tensor, dst: Tensor, scale: Tensor, amax_slot: Tensor, target: float = 1024.0) -> Tensor:
+    rc = L.load().b200_scale_cast_grad(_ptr(src), _ptr(dst), src.numel(), float(target), _ptr(scale), _ptr(amax_slot), _stream())
+    L.check(rc, "b200_scale_cast_grad")
+    return dst

@@ -1,0 +1,285 @@
+"""Per-kernel parity (GPU): every entry point of libb200enc.so against a plain fp32 PyTorch statement of the
+same op on the same inputs.  Tolerances are written beside each check: the kernels consume fp16 operands and
+accumulate in fp32, the references consume the SAME fp16-rounded operands in fp32, so the residual error is the
+output rounding (fp16: 2^-11 relative) plus summation order."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    from spokennlp_b200 import ops
+    return ops
+
+
+def _err_report(got, ref, name, block=64):
+    got = got.double()
+    ref = ref.double()
+    diff = (got - ref).abs()
+    rel = float((got - ref).norm() / ref.norm().clamp_min(1e-30))
+    msg = [f"{name}: rel_fro={rel:.3e} max_abs={float(diff.max()):.3e} ref_absmax={float(ref.abs().max()):.3e}"]
+    if got.dim() == 2 and rel > 1e-2:
+        R, Cc = got.shape
+        rb, cb = min(8, (R + block - 1) // block), min(12, (Cc + block - 1) // block)
+        msg.append(f"per-{block}x{block}-block rel error (first {rb}x{cb} blocks):")
+        for i in range(rb):
+            row = []
+            for j in range(cb):
+                g = got[i * block:(i + 1) * block, j * block:(j + 1) * block]
+                r = ref[i * block:(i + 1) * block, j * block:(j + 1) * block]
+                row.append(f"{float((g - r).norm() / r.norm().clamp_min(1e-30)):.2f}")
+            msg.append(" ".join(row))
+    return rel, "\n".join(msg)
+
+
+def _rand16(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, generator=g, device="cuda") * scale).half()
+
+
+# ----------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 256, 128), (384, 768, 768), (300, 768, 1536), (2048, 2304, 768),
+                                   (16384, 768, 3072)])
+def test_gemm_kmajor_store_f32(M, N, K):
+    ops = _cuda()
+    a, b = _rand16(M, K, seed=1), _rand16(N, K, seed=2)
+    out = torch.empty(M, N, dtype=torch.float32, device="cuda")
+    ops.gemm(a, b, out)
+    ref = a.float() @ b.float().t()
+    rel, msg = _err_report(out, ref, f"gemm(0,0) {M}x{N}x{K}")
+    assert rel < 1e-5, msg          # fp32 accumulate of identical operands: summation order only
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 768, 2304), (16384, 768, 2304), (16384, 3072, 768)])
+def test_gemm_dgrad_b_mn_major(M, N, K):
+    """dX[M,N] = dY[M,K] @ W[K,N] with W stored [K,N] row-major (b_layout=1): no transposed weight copy."""
+    ops = _cuda()
+    dy, w = _rand16(M, K, seed=3), _rand16(K, N, seed=4, scale=0.05)
+    out = torch.empty(M, N, dtype=torch.float16, device="cuda")
+    ops.gemm(dy, w, out, b_layout=1)
+    ref = dy.float() @ w.float()
+    rel, msg = _err_report(out, ref, f"gemm(0,1) {M}x{N}x{K}")
+    assert rel < 5e-4, msg          # fp16 output rounding
+
+
+@pytest.mark.parametrize("Mo,Ni,T", [(128, 256, 64), (768, 768, 1024), (2304, 768, 16384), (768, 3072, 16384)])
+def test_gemm_wgrad_both_mn_major_atomic(Mo, Ni, T):
+    """dW[Mo,Ni] += alpha * dY[T,Mo]^T @ X[T,Ni]: both operands MN-major, split-K fp32 reduction."""
+    ops = _cuda()
+    dy, x = _rand16(T, Mo, seed=5), _rand16(T, Ni, seed=6)
+    out = torch.full((Mo, Ni), 0.5, dtype=torch.float32, device="cuda")
+    alpha = torch.tensor([0.25], device="cuda")
+    splits = ops.wgrad_splits(Mo, Ni, T)
+    ops.gemm(dy, x, out, a_layout=1, b_layout=1, epilogue=ops.EPI_ATOMIC, alpha=alpha, k_splits=splits)
+    ref = 0.5 + 0.25 * (dy.float().t() @ x.float())
+    rel, msg = _err_report(out, ref, f"gemm(1,1) {Mo}x{Ni}x{T} splits={splits}")
+    assert rel < 2e-5, msg
+
+
+def test_gemm_epilogues():
+    ops = _cuda()
+    M, N, K = 1024, 768, 768
+    a, w = _rand16(M, K, seed=7), _rand16(N, K, seed=8, scale=0.05)
+    bias = torch.randn(N, device="cuda") * 0.1
+    res = _rand16(M, N, seed=9)
+    acc = a.float() @ w.float().t()
+
+    out = torch.empty(M, N, dtype=torch.float16, device="cuda")
+    ops.gemm(a, w, out, epilogue=ops.EPI_BIAS, bias=bias)
+    rel, msg = _err_report(out, acc + bias, "EPI_BIAS")
+    assert rel < 5e-4, msg
+
+    z = torch.empty_like(out)
+    ops.gemm(a, w, out, epilogue=ops.EPI_BIAS_GELU, bias=bias, out2=z)
+    rel, msg = _err_report(out, torch.nn.functional.gelu(acc + bias), "EPI_BIAS_GELU")
+    assert rel < 5e-4, msg
+    rel, msg = _err_report(z, acc + bias, "EPI_BIAS_GELU pre-activation")
+    assert rel < 5e-4, msg
+
+    o32 = torch.empty(M, N, dtype=torch.float32, device="cuda")
+    ops.gemm(a, w, o32, epilogue=ops.EPI_BIAS_RES, bias=bias, aux=res)
+    rel, msg = _err_report(o32, acc + bias + res.float(), "EPI_BIAS_RES f32")
+    assert rel < 1e-5, msg
+    ops.gemm(a, w, out, epilogue=ops.EPI_BIAS_RES, bias=bias, aux=res)
+    rel, msg = _err_report(out, acc + bias + res.float(), "EPI_BIAS_RES f16")
+    assert rel < 5e-4, msg
+
+    # dgrad-side epilogues (W stored [K,N])
+    wt = w.t().contiguous()          # [K, N] row-major
+    zz = _rand16(M, N, seed=10)
+    ops.gemm(a, wt, out, b_layout=1, epilogue=ops.EPI_ADD, aux=res)
+    rel, msg = _err_report(out, acc + res.float(), "EPI_ADD")
+    assert rel < 5e-4, msg
+    ops.gemm(a, wt, out, b_layout=1, epilogue=ops.EPI_DGELU, aux=zz)
+    zf = zz.float().requires_grad_(True)
+    torch.nn.functional.gelu(zf).sum().backward()
+    rel, msg = _err_report(out, acc * zf.grad, "EPI_DGELU")
+    assert rel < 5e-4, msg
+
+
+# ----------------------------------------------------------------------------------------------- row-wise kernels
+@pytest.mark.parametrize("rows,H,dt", [(1000, 768, torch.float32), (1000, 768, torch.float16), (77, 128, torch.float32),
+                                       (16384, 768, torch.float32)])
+def test_layernorm_fwd_bwd(rows, H, dt):
+    ops = _cuda()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = (torch.randn(rows, H, generator=g, device="cuda") * 2 + 0.3).to(dt)
+    gamma = 1 + 0.1 * torch.randn(H, generator=g, device="cuda")
+    beta = 0.1 * torch.randn(H, generator=g, device="cuda")
+    mean = torch.empty(rows, device="cuda")
+    rstd = torch.empty(rows, device="cuda")
+    y = ops.layernorm_fwd(x, gamma, beta, 1e-12, mean=mean, rstd=rstd)
+    xf = x.float().requires_grad_(True)
+    gf, bf = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xf, (H,), gf, bf, 1e-12)
+    rel, msg = _err_report(y, ref.detach(), "ln_fwd")
+    assert rel < 4e-4, msg          # fp16 output rounding
+    dy = _rand16(rows, H, seed=3, scale=0.01)
+    dy2 = _rand16(rows, H, seed=4, scale=0.01)
+    ref.backward(dy.float() + dy2.float())
+    dx = torch.empty(rows, H, dtype=torch.float16, device="cuda")
+    dgamma, dbeta, dbias = torch.zeros(H, device="cuda"), torch.zeros(H, device="cuda"), torch.zeros(H, device="cuda")
+    alpha = torch.tensor([0.5], device="cuda")
+    ops.layernorm_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, dy2=dy2, dbias=dbias, alpha=alpha)
+    rel, msg = _err_report(dx, xf.grad, "ln_bwd dx")
+    assert rel < 6e-4, msg
+    rel, msg = _err_report(dgamma, 0.5 * gf.grad, "ln_bwd dgamma")
+    assert rel < 1e-4, msg
+    rel, msg = _err_report(dbeta, 0.5 * bf.grad, "ln_bwd dbeta")
+    assert rel < 1e-4, msg
+    rel, msg = _err_report(dbias, 0.5 * xf.grad.sum(0), "ln_bwd dbias")
+    assert rel < 2e-3 or float((dbias - 0.5 * xf.grad.sum(0)).abs().max()) < 1e-4, msg   # sums of ~zero-mean values
+
+
+def test_embed_ln_fwd_bwd():
+    ops = _cuda()
+    B, S, H, V = 4, 128, 768, 1000
+    g = torch.Generator(device="cuda").manual_seed(0)
+    word = torch.randn(V, H, generator=g, device="cuda") * 0.02
+    pos_tab = torch.randn(512, H, generator=g, device="cuda") * 0.02
+    type_tab = torch.randn(2, H, generator=g, device="cuda") * 0.02
+    gamma = 1 + 0.1 * torch.randn(H, generator=g, device="cuda")
+    beta = 0.1 * torch.randn(H, generator=g, device="cuda")
+    ids = torch.randint(0, V, (B, S), generator=g, device="cuda")
+    tt = torch.randint(0, 2, (B, S), generator=g, device="cuda")
+    y = ops.embed_ln_fwd(ids, tt, None, None, word, pos_tab, type_tab, gamma, beta, 1e-12, B * S, S, H)
+    params = [t.clone().requires_grad_(True) for t in (word, pos_tab, type_tab, gamma, beta)]
+    e = params[0][ids] + params[1][torch.arange(S, device="cuda")][None] + params[2][tt]
+    ref = torch.nn.functional.layer_norm(e, (H,), params[3], params[4], 1e-12)
+    rel, msg = _err_report(y, ref.detach().reshape(B * S, H), "embed_ln_fwd")
+    assert rel < 4e-4, msg
+    dy = _rand16(B * S, H, seed=5, scale=0.01)
+    ref.backward(dy.float().view(B, S, H))
+    grads = [torch.zeros_like(t) for t in (word, pos_tab, type_tab, gamma, beta)]
+    ops.embed_ln_bwd(dy, None, ids, tt, None, word, pos_tab, type_tab, gamma, *grads, None, 1e-12, B * S, S, H)
+    for got, p, nm in zip(grads, params, ("dword", "dpos", "dtype", "dgamma", "dbeta")):
+        rel, msg = _err_report(got, p.grad, "embed_ln_bwd " + nm)
+        assert rel < 2e-4, msg
+
+
+@pytest.mark.parametrize("Cn", [2, 3])
+def test_cls_head_ce_fwd_bwd(Cn):
+    ops = _cuda()
+    rows, H = 4096, 768
+    h = _rand16(rows, H, seed=1)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    W = torch.randn(Cn, H, generator=g, device="cuda") * 0.05
+    b = torch.randn(Cn, generator=g, device="cuda") * 0.05
+    labels = torch.full((rows,), -100, dtype=torch.long, device="cuda")
+    idx = torch.arange(1, rows, 20, device="cuda")
+    labels[idx] = torch.randint(0, Cn, (len(idx),), generator=g, device="cuda")
+    logits, am = ops.cls_head_fwd(h, W, b, want_argmax=True)
+    hf = h.float().requires_grad_(True)
+    Wf, bf = W.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref_logits = hf @ Wf.t() + bf
+    rel, msg = _err_report(logits, ref_logits.detach(), "cls_head_fwd")
+    assert rel < 1e-5, msg
+    margin = ref_logits.detach().sort(-1).values
+    safe = (margin[:, -1] - margin[:, -2]) > 1e-4
+    assert torch.equal(am.long()[safe], ref_logits.argmax(-1)[safe])
+    stats = torch.zeros(2, device="cuda")
+    ops.ce_stats(logits, labels, stats)
+    loss = torch.nn.functional.cross_entropy(ref_logits, labels)
+    assert abs(float(stats[0] / stats[1]) - float(loss)) < 1e-5
+    loss.backward()
+    dh = torch.empty(rows, H, dtype=torch.float16, device="cuda")
+    dW, db = torch.zeros_like(W), torch.zeros_like(b)
+    scale = torch.tensor([1024.0], device="cuda")
+    ops.cls_head_bwd(h, logits, labels, stats, W, dh, dW, db, scale=scale)
+    rel, msg = _err_report(dh.float() / 1024.0, hf.grad, "cls_head_bwd dh")
+    assert rel < 6e-4, msg
+    rel, msg = _err_report(dW, Wf.grad, "cls_head_bwd dW")
+    assert rel < 1e-4, msg
+    rel, msg = _err_report(db, bf.grad, "cls_head_bwd db")
+    assert rel < 1e-4, msg
+
+
+def test_colsum_casts_and_grad_scaling():
+    ops = _cuda()
+    dy = _rand16(5000, 2304, seed=1)
+    db = torch.zeros(2304, device="cuda")
+    ops.colsum(dy, db, torch.tensor([2.0], device="cuda"))
+    rel, msg = _err_report(db, 2.0 * dy.float().sum(0), "colsum")
+    assert rel < 1e-4, msg
+    src = torch.randn(8 * 1000, device="cuda")
+    h = torch.empty(8 * 1000, dtype=torch.float16, device="cuda")
+    ops.cast_f32_to_f16(src, h)
+    assert torch.equal(h, src.half())
+    back = torch.empty_like(src)
+    ops.cast_f16_to_f32(h, back)
+    assert torch.equal(back, h.float())
+    g = src * 1e-6
+    scale = torch.zeros(2, device="cuda")
+    slot = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ops.scale_cast_grad(g, h, scale, slot, target=1024.0)
+    s = float(scale[0])
+    assert s == 2.0 ** math.floor(math.log2(1024.0 / float(g.abs().max()))) and abs(float(scale[1]) * s - 1) < 1e-7
+    assert torch.equal(h, (g * s).half())
+
+
+# ----------------------------------------------------------------------------------------------- attention
+def _attn_ref(qkv, B, S, heads, key_bias):
+    H = heads * 64
+    q, k, v = qkv.float().view(B, S, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-1, -2)) / 8.0
+    if key_bias is not None:
+        s = s + key_bias[:, None, None, :]
+    p = torch.softmax(s, dim=-1)
+    ctx = (p @ v).permute(0, 2, 1, 3).reshape(B * S, H)
+    return ctx, p, torch.logsumexp(s, dim=-1)
+
+
+@pytest.mark.parametrize("B,S,heads,masked", [(1, 128, 1, False), (2, 256, 2, False), (2, 512, 12, False), (3, 512, 12, True),
+                                              (2, 300, 12, True), (4, 128, 12, True), (2, 1024, 4, True)])
+def test_attn_fwd(B, S, heads, masked):
+    ops = _cuda()
+    H = heads * 64
+    qkv = _rand16(B * S, 3 * H, seed=B * 1000 + S)
+    key_bias = kv_len = None
+    if masked:
+        g = torch.Generator().manual_seed(S)
+        lens = torch.randint(S // 3, S + 1, (B,), generator=g)
+        lens[0] = S
+        mask = (torch.arange(S)[None, :] < lens[:, None]).long().cuda()
+        if B > 2:
+            mask[2, 5] = 0          # a hole inside the kept range: handled by the bias, not by kv_len
+        key_bias, kv_len = ops.mask_to_bias(mask)
+        assert torch.equal(kv_len.cpu().long(), lens)
+    ctx = torch.empty(B * S, H, dtype=torch.float16, device="cuda")
+    lse2 = torch.empty(B, heads, S, dtype=torch.float32, device="cuda")
+    ops.attn_fwd(qkv, qkv, ctx, B, heads, S, S, q_col0=0, k_col0=H, v_col0=2 * H, key_bias=key_bias, kv_len=kv_len, lse2=lse2)
+    ref_ctx, ref_p, ref_lse = _attn_ref(qkv, B, S, heads, key_bias)
+    rel, msg = _err_report(ctx, ref_ctx, f"attn_fwd B{B} S{S} h{heads} masked={masked}")
+    assert rel < 1.5e-3, msg         # P is rounded to fp16 before P.V (2^-11 per element), ctx rounded to fp16
+    rel, msg = _err_report(lse2 * math.log(2.0), ref_lse, "attn_fwd lse")
+    assert rel < 1e-5, msg
+    probs = ops.attn_probs(qkv, qkv, lse2, B, heads, S, S, q_col0=0, k_col0=H, key_bias=key_bias)
+    rel, msg = _err_report(probs.view(-1, S), ref_p.reshape(-1, S), "attn_probs")
+    assert rel < 1e-4, msg
