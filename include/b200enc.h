@@ -118,6 +118,27 @@ int b200_cast_f16_to_f32(const void* src, float* dst, size_t n, void* stream);
  * `amax_slot` is a 4-byte device scratch.  Used to carry an fp32 upstream gradient into the fp16 backward. */
 int b200_scale_cast_grad(const float* src, void* dst, size_t n, float target, float* scale, void* amax_slot, void* stream);
 
+/*
+ * Fused attention backward (autograd of bert_model.py:309-350), head_dim 64.  Inputs as b200_attn_fwd plus
+ * dctx/ctx [B*Sq, heads*64] fp16 and the saved lse2.  Writes dq into dq[:, dq_col0 + 64h ...] (fp16, pitch ld_dq) and
+ * dk / dv into dkv[:, dk_col0 / dv_col0 + 64h ...] (pitch ld_dkv) — for self-attention all three are column ranges of
+ * one packed [tokens, 3H] gradient buffer, ready to be the A operand of the QKV dgrad/wgrad GEMMs.
+ * workspace: caller-owned, b200_attn_bwd_workspace(B, heads, Sq) bytes (delta + fp32 dQ accumulator).
+ */
+size_t b200_attn_bwd_workspace(int B, int heads, int Sq);
+int b200_attn_bwd(const void* q, int ldq, int q_col0, const void* kv, int ldkv, int k_col0, int v_col0, const void* dctx, int ld_dctx,
+                  const void* ctx, int ld_ctx, const float* key_bias, const int32_t* kv_len, const float* lse2, void* workspace,
+                  void* dq, int ld_dq, int dq_col0, void* dkv, int ld_dkv, int dk_col0, int dv_col0, int B, int heads, int Sq, int Sk,
+                  void* stream);
+
+/* Optimizer over the flat fp32 parameter / gradient buffers (HF Trainer defaults: AdamW, clip_grad_norm_ 1.0).
+ * sumsq[0] += sum g^2 (caller zeroes); coef = {grad multiplier incl. clipping, finite flag, norm};
+ * adamw_step skips the update when coef[1] == 0 and always refreshes the fp16 compute copy p16 (optional). */
+int b200_grad_sumsq(const float* g, size_t n, float* sumsq, void* stream);
+int b200_clip_coef(const float* sumsq, float max_norm, float grad_mult, float* coef, void* stream);
+int b200_adamw_step(float* p, const float* g, float* m, float* v, void* p16, size_t n, float lr, float beta1, float beta2, float eps,
+                    float weight_decay, float bias_corr1, float bias_corr2, const float* coef, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

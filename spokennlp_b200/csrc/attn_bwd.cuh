@@ -1,2 +1,322 @@
+// Fused attention backward for head_dim 64 on tcgen05 — the autograd of bert_model.py:309-350.
+//
+// One CTA owns one 128-key block of one (batch, head) and walks the query blocks.  Everything is computed in the
+// TRANSPOSED orientation (TMEM lane == key row), so that the two tiles the softmax threads write, P^T and dS^T
+// ([key, query], fp16, 128B-swizzled), feed all three gradient MMAs without any transposition:
+//     S^T  = K   Q^T          (A = K  K-major,  B = Q  K-major)     recompute scores
+//     dP^T = V   dO^T         (A = V  K-major,  B = dO K-major)
+//     P^T  = exp2(S^T c + bias_k - lse2_q),   dS^T = P^T o (dP^T - delta_q) / sqrt(d)        [CUDA cores, row per thread]
+//     dV  += P^T  dO          (A = P^T  K-major, B = dO MN-major)   accumulates in TMEM over query blocks
+//     dK  += dS^T Q           (A = dS^T K-major, B = Q  MN-major)   accumulates in TMEM over query blocks
+//     dQ_i = dS   K           (A = dS^T viewed MN-major, B = K MN-major) -> fp32 red.global.add into dq_acc
+// Q / K / V / dO tiles are read in place from the packed projection buffers with TMA; MN-major views of the same
+// swizzled smem tiles are selected purely through the UMMA descriptors.
 #pragma once
-#include "ptx.cuh"
+#include "attn_fwd.cuh"
+
+namespace b200 {
+
+constexpr int ATTB_THREADS = 192;   // warp 0 TMA, warp 1 MMA, warps 2-5 softmax/epilogue
+
+struct AttnBwdArgs {
+  int B, heads, Sq, Sk;
+  int q_col0, k_col0, v_col0;       // head-0 columns inside the Q map / KV map
+  const float* key_bias;            // [B,Sk] or null
+  const int* kv_len;                // [B] or null
+  const float* lse2;                // [B,heads,Sq]
+  const float* delta;               // [B,heads,Sq]  rowsum(dO o O)
+  float* dq_acc;                    // [B*Sq, ld_dq] fp32, zero-initialised by the caller; head h at columns 64h
+  int ld_dq;
+  __half* dk;                       // [B*Sk, ld_dkv]; head h at columns dk_col0 + 64h
+  __half* dv;
+  int ld_dkv, dk_col0, dv_col0;
+  float scale_log2;                 // log2(e)/sqrt(d)
+  float inv_sqrt_d;
+};
+
+struct AttnBwdSmem {
+  static constexpr int T = ATT_BK * ATT_D * 2;                 // 16 KB tile
+  static constexpr int OFF_K = 0;
+  static constexpr int OFF_V = OFF_K + T;
+  static constexpr int OFF_QDO = OFF_V + T;                    // 2 stages x (Q_i, dO_i)
+  static constexpr int OFF_P = OFF_QDO + 2 * 2 * T;            // P^T  [128 keys][128 q] fp16 = 32 KB
+  static constexpr int OFF_DS = OFF_P + 2 * T;                 // dS^T 32 KB
+  static constexpr int OFF_STAT = OFF_DS + 2 * T;              // [2 buffers][2 (lse2, delta)][128] floats
+  static constexpr int OFF_BAR = OFF_STAT + 2 * 2 * 128 * 4;
+  static constexpr int TOTAL = OFF_BAR + 256 + 1024;
+};
+
+__global__ void __launch_bounds__(ATTB_THREADS, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                const __grid_constant__ CUtensorMap tmDO, const AttnBwdArgs a) {
+  using S = AttnBwdSmem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
+  uint64_t* kv_full = bars;            // 1
+  uint64_t* qdo_full = bars + 1;       // 2
+  uint64_t* qdo_empty = bars + 3;      // 2
+  uint64_t* s_full = bars + 5;         // 1
+  uint64_t* ds_full = bars + 6;        // 1 (128 arrivals)
+  uint64_t* fin = bars + 7;            // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int k0 = blockIdx.x * ATT_BK;
+  int kv_len = a.kv_len ? a.kv_len[b] : a.Sk;
+  kv_len = max(1, min(kv_len, a.Sk));
+  const int nq = (a.Sq + ATT_BQ - 1) / ATT_BQ;
+  const bool dead_block = k0 >= kv_len;      // every key of this block is masked: dK = dV = 0, no dQ contribution
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+    tma_prefetch_desc(&tmDO);
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&qdo_full[i], 1);
+      mbar_init(&qdo_empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(ds_full, 128);
+    mbar_init(fin, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  // TMEM columns: S^T [0,128)  dP^T [128,256)  dV [256,320)  dK [320,384)  dQ [384,448)
+
+  if (dead_block) {
+    if (warp >= 2) {
+      const int r = (warp & 3) * 32 + lane;
+      if (k0 + r < a.Sk) {
+        const size_t row = static_cast<size_t>(b) * a.Sk + k0 + r;
+        const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          *reinterpret_cast<uint4*>(a.dk + row * a.ld_dkv + a.dk_col0 + h * ATT_D + i * 8) = z;
+          *reinterpret_cast<uint4*>(a.dv + row * a.ld_dkv + a.dv_col0 + h * ATT_D + i * 8) = z;
+        }
+      }
+    }
+  } else if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(kv_full, 2 * S::T);
+      tma_load_2d(smem + S::OFF_K, &tmKV, kv_full, a.k_col0 + h * ATT_D, b * a.Sk + k0);
+      tma_load_2d(smem + S::OFF_V, &tmKV, kv_full, a.v_col0 + h * ATT_D, b * a.Sk + k0);
+      for (int i = 0; i < nq; ++i) {
+        const int st = i & 1;
+        mbar_wait(&qdo_empty[st], ((i >> 1) & 1) ^ 1);
+        mbar_expect_tx(&qdo_full[st], 2 * S::T);
+        uint8_t* dst = smem + S::OFF_QDO + st * 2 * S::T;
+        tma_load_2d(dst, &tmQ, &qdo_full[st], a.q_col0 + h * ATT_D, b * a.Sq + i * ATT_BQ);
+        tma_load_2d(dst + S::T, &tmDO, &qdo_full[st], h * ATT_D, b * a.Sq + i * ATT_BQ);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    constexpr uint32_t idesc_s = make_idesc_f16(128, 128, 0, 0);
+    constexpr uint32_t idesc_g = make_idesc_f16(128, 64, 0, 1);     // dV, dK : A K-major, B MN-major
+    constexpr uint32_t idesc_q = make_idesc_f16(128, 64, 1, 1);     // dQ     : both MN-major
+    const uint32_t ka = smem_u32(smem + S::OFF_K), va = smem_u32(smem + S::OFF_V);
+    const uint32_t pa = smem_u32(smem + S::OFF_P), dsa = smem_u32(smem + S::OFF_DS);
+    auto issue_scores = [&](int st) {
+      const uint32_t qa = smem_u32(smem + S::OFF_QDO + st * 2 * S::T), doa = qa + S::T;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+        umma_ss(tmem + 0, make_smem_desc(ka + kk * 32, 0, 1024), make_smem_desc(qa + kk * 32, 0, 1024), idesc_s, kk > 0);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+        umma_ss(tmem + 128, make_smem_desc(va + kk * 32, 0, 1024), make_smem_desc(doa + kk * 32, 0, 1024), idesc_s, kk > 0);
+      umma_commit(s_full);
+    };
+    mbar_wait(kv_full, 0);
+    mbar_wait(&qdo_full[0], 0);
+    tc_fence_after();
+    if (lane == 0) issue_scores(0);
+    __syncwarp();
+    for (int i = 0; i < nq; ++i) {
+      const int st = i & 1;
+      mbar_wait(ds_full, i & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t qa = smem_u32(smem + S::OFF_QDO + st * 2 * S::T), doa = qa + S::T;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)        // dV += P^T dO
+          umma_ss(tmem + 256, make_smem_desc(pa + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024), make_smem_desc(doa + kk * 2048, 8192, 1024),
+                  idesc_g, (i > 0 || kk > 0) ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)        // dK += dS^T Q
+          umma_ss(tmem + 320, make_smem_desc(dsa + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024), make_smem_desc(qa + kk * 2048, 8192, 1024),
+                  idesc_g, (i > 0 || kk > 0) ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)        // dQ_i = dS K   (A = dS^T tile viewed MN-major: M = query, K = key rows)
+          umma_ss(tmem + 384, make_smem_desc(dsa + kk * 2048, 16384, 1024), make_smem_desc(ka + kk * 2048, 8192, 1024), idesc_q, kk > 0);
+        umma_commit(&qdo_empty[st]);
+      }
+      __syncwarp();
+      if (i + 1 < nq) {
+        mbar_wait(&qdo_full[st ^ 1], ((i + 1) >> 1) & 1);
+        tc_fence_after();
+        if (lane == 0) issue_scores(st ^ 1);
+      } else if (lane == 0) {
+        umma_commit(fin);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int qd = warp & 3;
+    const int r = qd * 32 + lane;                 // key row inside the block == TMEM lane
+    const int t = threadIdx.x - 64;               // 0..127
+    const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
+    float* stat = reinterpret_cast<float*>(smem + S::OFF_STAT);
+    uint8_t* p_row = smem + S::OFF_P + r * 128;
+    uint8_t* ds_row = smem + S::OFF_DS + r * 128;
+    const int key = k0 + r;
+    float bias = -INFINITY;
+    if (key < kv_len) bias = a.key_bias ? a.key_bias[static_cast<size_t>(b) * a.Sk + key] * 1.4426950408889634f : 0.f;
+    const size_t stat_base = (static_cast<size_t>(b) * a.heads + h) * a.Sq;
+
+    auto drain_dq = [&](int i) {                  // dQ_i tile: TMEM lane == query row
+      const int q = i * ATT_BQ + r;
+      uint32_t o[2][32];
+      tmem_ld_x32(tmem + lane_addr + 384, o[0]);
+      tmem_ld_x32(tmem + lane_addr + 384 + 32, o[1]);
+      tmem_wait_ld();
+      if (q < a.Sq) {
+        float* dst = a.dq_acc + (static_cast<size_t>(b) * a.Sq + q) * a.ld_dq + h * ATT_D;
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            red_add_v4(dst + c * 32 + k * 4, __uint_as_float(o[c][4 * k]), __uint_as_float(o[c][4 * k + 1]),
+                       __uint_as_float(o[c][4 * k + 2]), __uint_as_float(o[c][4 * k + 3]));
+      }
+    };
+
+    for (int i = 0; i < nq; ++i) {
+      {  // per-query statistics of block i; queries past Sq get lse = +inf (P = 0) and delta = 0
+        const int q = i * ATT_BQ + t;
+        float* sb = stat + (i & 1) * 256;
+        sb[t] = q < a.Sq ? a.lse2[stat_base + q] : INFINITY;
+        sb[128 + t] = q < a.Sq ? a.delta[stat_base + q] : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      const float* lse_s = stat + (i & 1) * 256;
+      const float* del_s = lse_s + 128;
+      mbar_wait(s_full, i & 1);
+      tc_fence_after();
+      if (i > 0) drain_dq(i - 1);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t sv[32], dp[32];
+        tmem_ld_x32(tmem + lane_addr + c * 32, sv);
+        tmem_ld_x32(tmem + lane_addr + 128 + c * 32, dp);
+        tmem_wait_ld();
+        uint32_t pk[16], dk[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int q0i = c * 32 + 2 * e;
+          const float p0 = fast_exp2(fmaf(__uint_as_float(sv[2 * e]), a.scale_log2, bias) - lse_s[q0i]);
+          const float p1 = fast_exp2(fmaf(__uint_as_float(sv[2 * e + 1]), a.scale_log2, bias) - lse_s[q0i + 1]);
+          const float d0 = p0 * (__uint_as_float(dp[2 * e]) - del_s[q0i]) * a.inv_sqrt_d;
+          const float d1 = p1 * (__uint_as_float(dp[2 * e + 1]) - del_s[q0i + 1]) * a.inv_sqrt_d;
+          const __half2 hp = __floats2half2_rn(p0, p1), hd = __floats2half2_rn(d0, d1);
+          pk[e] = *reinterpret_cast<const uint32_t*>(&hp);
+          dk[e] = *reinterpret_cast<const uint32_t*>(&hd);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int ch = 4 * c + e;
+          const int off = (ch >> 3) * 16384 + (((ch & 7) ^ (r & 7)) << 4);
+          *reinterpret_cast<uint4*>(p_row + off) = make_uint4(pk[4 * e], pk[4 * e + 1], pk[4 * e + 2], pk[4 * e + 3]);
+          *reinterpret_cast<uint4*>(ds_row + off) = make_uint4(dk[4 * e], dk[4 * e + 1], dk[4 * e + 2], dk[4 * e + 3]);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(ds_full);
+    }
+    mbar_wait(fin, 0);
+    tc_fence_after();
+    drain_dq(nq - 1);
+    // dV, dK: TMEM lane == key row
+    uint32_t o[2][32];
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+      tmem_ld_x32(tmem + lane_addr + 256 + which * 64, o[0]);
+      tmem_ld_x32(tmem + lane_addr + 256 + which * 64 + 32, o[1]);
+      tmem_wait_ld();
+      if (key < a.Sk) {
+        __half* dst = (which == 0 ? a.dv + a.dv_col0 : a.dk + a.dk_col0) + (static_cast<size_t>(b) * a.Sk + key) * a.ld_dkv + h * ATT_D;
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            uint32_t w[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const __half2 hv = __floats2half2_rn(__uint_as_float(o[c][8 * e + 2 * k]), __uint_as_float(o[c][8 * e + 2 * k + 1]));
+              w[k] = *reinterpret_cast<const uint32_t*>(&hv);
+            }
+            *reinterpret_cast<uint4*>(dst + c * 32 + e * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// delta[b,h,q] = sum_d dO[q, 64h+d] * O[q, 64h+d]   (one warp per token row; 8 lanes share a head)
+__global__ void __launch_bounds__(128) attn_delta_kernel(const __half* __restrict__ dout, int ld_do, const __half* __restrict__ out, int ld_o,
+                                                         float* __restrict__ delta, int B, int heads, int Sq) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= B * Sq) return;
+  const int b = row / Sq, q = row % Sq;
+  const int nvec = heads * 8;
+  for (int v = lane; v < nvec; v += 32) {
+    const uint4 ra = *reinterpret_cast<const uint4*>(dout + static_cast<size_t>(row) * ld_do + v * 8);
+    const uint4 rb = *reinterpret_cast<const uint4*>(out + static_cast<size_t>(row) * ld_o + v * 8);
+    const __half2* ha = reinterpret_cast<const __half2*>(&ra);
+    const __half2* hb = reinterpret_cast<const __half2*>(&rb);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 x = __half22float2(ha[i]), y = __half22float2(hb[i]);
+      s = fmaf(x.x, y.x, s);
+      s = fmaf(x.y, y.y, s);
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if ((lane & 7) == 0) delta[(static_cast<size_t>(b) * heads + (v >> 3)) * Sq + q] = s;
+  }
+}
+
+// dq(fp16, strided) = dq_acc(fp32)
+__global__ void dq_cast_kernel(const float* __restrict__ src, int ld_src, __half* __restrict__ dst, int ld_dst, int rows, int cols8) {
+  const size_t total = static_cast<size_t>(rows) * cols8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t r = i / cols8, c = (i % cols8) * 8;
+    const float4 x = *reinterpret_cast<const float4*>(src + r * ld_src + c);
+    const float4 y = *reinterpret_cast<const float4*>(src + r * ld_src + c + 4);
+    __half2 h[4] = {__floats2half2_rn(x.x, x.y), __floats2half2_rn(x.z, x.w), __floats2half2_rn(y.x, y.y), __floats2half2_rn(y.z, y.w)};
+    *reinterpret_cast<uint4*>(dst + r * ld_dst + c) = *reinterpret_cast<uint4*>(h);
+  }
+}
+
+}  // namespace b200

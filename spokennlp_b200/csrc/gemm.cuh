@@ -57,10 +57,6 @@ struct GemmSmem {
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // + barriers + alignment slack
 };
 
-__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
 template <int BN, int A_MN, int B_MN, int EPI, typename OutT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {

@@ -180,6 +180,11 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_mn_maj
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// fire-and-forget vectorised fp32 reduction into global memory (split-K wgrad, dQ accumulation)
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // ----------------------------------------------------------------------------- small math helpers
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -36,8 +36,13 @@ _PROTOS = {
     "b200_cast_f32_to_f16": [_p, _p, _sz, _p],
     "b200_cast_f16_to_f32": [_p, _p, _sz, _p],
     "b200_scale_cast_grad": [_p, _p, _sz, _f, _p, _p, _p],
+    "b200_attn_bwd_workspace": [_i, _i, _i],
+    "b200_attn_bwd": [_p, _i, _i, _p, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p],
+    "b200_grad_sumsq": [_p, _sz, _p, _p],
+    "b200_clip_coef": [_p, _f, _f, _p, _p],
+    "b200_adamw_step": [_p, _p, _p, _p, _p, _sz, _f, _f, _f, _f, _f, _f, _f, _p, _p],
 }
-_RESTYPE = {"b200_last_error": C.c_char_p, "b200_launch_count": _ll, "b200_version": _i}
+_RESTYPE = {"b200_last_error": C.c_char_p, "b200_launch_count": _ll, "b200_version": _i, "b200_attn_bwd_workspace": _sz}
 
 _lock = threading.Lock()
 _lib = None

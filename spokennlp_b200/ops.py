@@ -184,3 +184,38 @@ def scale_cast_grad(src: Tensor, dst: Tensor, scale: Tensor, amax_slot: Tensor, 
     rc = L.load().b200_scale_cast_grad(_ptr(src), _ptr(dst), src.numel(), float(target), _ptr(scale), _ptr(amax_slot), _stream())
     L.check(rc, "b200_scale_cast_grad")
     return dst
+
+
+def attn_bwd_workspace(B: int, heads: int, Sq: int, device) -> Tensor:
+    n = int(L.load().b200_attn_bwd_workspace(B, heads, Sq))
+    return torch.empty(n // 4, dtype=torch.float32, device=device)
+
+
+def attn_bwd(q: Tensor, kv: Tensor, dctx: Tensor, ctx: Tensor, lse2: Tensor, dq: Tensor, dkv: Tensor, workspace: Tensor,
+             B: int, heads: int, Sq: int, Sk: int, *, q_col0: int, k_col0: int, v_col0: int, dq_col0: int, dk_col0: int,
+             dv_col0: int, key_bias: Optional[Tensor] = None, kv_len: Optional[Tensor] = None) -> None:
+    for t, n in ((q, "q"), (kv, "kv"), (dctx, "dctx"), (ctx, "ctx"), (dq, "dq"), (dkv, "dkv")):
+        _req(t, torch.float16, n)
+    rc = L.load().b200_attn_bwd(_ptr(q), q.stride(0), q_col0, _ptr(kv), kv.stride(0), k_col0, v_col0, _ptr(dctx), dctx.stride(0),
+                                _ptr(ctx), ctx.stride(0), _ptr(key_bias), _ptr(kv_len), _ptr(lse2), _ptr(workspace), _ptr(dq),
+                                dq.stride(0), dq_col0, _ptr(dkv), dkv.stride(0), dk_col0, dv_col0, B, heads, Sq, Sk, _stream())
+    L.check(rc, "b200_attn_bwd")
+
+
+def grad_sumsq(g: Tensor, sumsq: Tensor) -> Tensor:
+    L.check(L.load().b200_grad_sumsq(_ptr(g), g.numel(), _ptr(sumsq), _stream()), "b200_grad_sumsq")
+    return sumsq
+
+
+def clip_coef(sumsq: Tensor, coef: Tensor, max_norm: float, grad_mult: float = 1.0) -> Tensor:
+    L.check(L.load().b200_clip_coef(_ptr(sumsq), float(max_norm), float(grad_mult), _ptr(coef), _stream()), "b200_clip_coef")
+    return coef
+
+
+def adamw_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, p16: Optional[Tensor], *, lr: float, beta1: float = 0.9,
+               beta2: float = 0.999, eps: float = 1e-8, weight_decay: float = 0.0, step: int = 1,
+               coef: Optional[Tensor] = None) -> None:
+    bc1, bc2 = 1.0 - beta1 ** step, 1.0 - beta2 ** step
+    rc = L.load().b200_adamw_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(p16), p.numel(), lr, beta1, beta2, eps, weight_decay,
+                                  bc1, bc2, _ptr(coef), _stream())
+    L.check(rc, "b200_adamw_step")

@@ -235,7 +235,7 @@ def test_colsum_casts_and_grad_scaling():
     back = torch.empty_like(src)
     ops.cast_f16_to_f32(h, back)
     assert torch.equal(back, h.float())
-    g = src * 1e-6
+    g = src * 1e-4
     scale = torch.zeros(2, device="cuda")
     slot = torch.zeros(1, dtype=torch.int32, device="cuda")
     ops.scale_cast_grad(g, h, scale, slot, target=1024.0)
@@ -283,3 +283,71 @@ def test_attn_fwd(B, S, heads, masked):
     probs = ops.attn_probs(qkv, qkv, lse2, B, heads, S, S, q_col0=0, k_col0=H, key_bias=key_bias)
     rel, msg = _err_report(probs.view(-1, S), ref_p.reshape(-1, S), "attn_probs")
     assert rel < 1e-4, msg
+
+
+@pytest.mark.parametrize("B,S,heads,masked", [(1, 128, 1, False), (2, 256, 2, False), (2, 512, 12, True), (2, 300, 4, True)])
+def test_attn_bwd(B, S, heads, masked):
+    ops = _cuda()
+    H = heads * 64
+    qkv = _rand16(B * S, 3 * H, seed=B * 77 + S)
+    key_bias = kv_len = None
+    if masked:
+        g = torch.Generator().manual_seed(S + 1)
+        lens = torch.randint(S // 3, S + 1, (B,), generator=g)
+        lens[0] = S
+        mask = (torch.arange(S)[None, :] < lens[:, None]).long().cuda()
+        mask[1, 3] = 0
+        key_bias, kv_len = ops.mask_to_bias(mask)
+    ctx = torch.empty(B * S, H, dtype=torch.float16, device="cuda")
+    lse2 = torch.empty(B, heads, S, dtype=torch.float32, device="cuda")
+    ops.attn_fwd(qkv, qkv, ctx, B, heads, S, S, q_col0=0, k_col0=H, v_col0=2 * H, key_bias=key_bias, kv_len=kv_len, lse2=lse2)
+    dctx = _rand16(B * S, H, seed=5, scale=0.5)
+    dqkv = torch.full((B * S, 3 * H), float("nan"), dtype=torch.float16, device="cuda")
+    ws = ops.attn_bwd_workspace(B, heads, S, "cuda")
+    ops.attn_bwd(qkv, qkv, dctx, ctx, lse2, dqkv, dqkv, ws, B, heads, S, S, q_col0=0, k_col0=H, v_col0=2 * H, dq_col0=0,
+                 dk_col0=H, dv_col0=2 * H, key_bias=key_bias, kv_len=kv_len)
+    # reference: autograd through the fp32 statement of attention on the same fp16-rounded inputs
+    x = qkv.float().requires_grad_(True)
+    q, k, v = x.view(B, S, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-1, -2)) / 8.0
+    if key_bias is not None:
+        s = s + key_bias[:, None, None, :]
+    ref_ctx = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(B * S, H)
+    ref_ctx.backward(dctx.float())
+    assert torch.isfinite(dqkv.float()).all(), "attn_bwd left unwritten / non-finite gradient entries"
+    for nm, c0 in (("dq", 0), ("dk", H), ("dv", 2 * H)):
+        rel, msg = _err_report(dqkv[:, c0:c0 + H], x.grad[:, c0:c0 + H], f"attn_bwd {nm} B{B} S{S} h{heads} masked={masked}")
+        assert rel < 3e-3, msg       # P^T, dS^T are rounded to fp16 before the gradient MMAs
+
+
+def test_optimizer_kernels():
+    ops = _cuda()
+    n = 8 * 12345
+    g0 = torch.Generator(device="cuda").manual_seed(0)
+    p = torch.randn(n, generator=g0, device="cuda")
+    g = torch.randn(n, generator=g0, device="cuda") * 3
+    ref_p = p.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([ref_p], lr=5e-5, weight_decay=0.01)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    p16 = torch.empty(n, dtype=torch.float16, device="cuda")
+    sumsq, coef = torch.zeros(1, device="cuda"), torch.zeros(3, device="cuda")
+    for step in (1, 2, 3):
+        ref_p.grad = g.clone() / 4          # grad_mult = 1/4 (e.g. mean over 4 ranks)
+        norm = torch.nn.utils.clip_grad_norm_([ref_p], 1.0)
+        opt.step()
+        sumsq.zero_()
+        ops.grad_sumsq(g, sumsq)
+        ops.clip_coef(sumsq, coef, 1.0, 0.25)
+        assert abs(float(coef[2]) - float(norm)) < 1e-3 * float(norm)
+        ops.adamw_step(p, g, m, v, p16, lr=5e-5, weight_decay=0.01, step=step, coef=coef)
+        rel, msg = _err_report(p, ref_p.detach(), f"adamw step {step}")
+        assert rel < 1e-6, msg
+        assert torch.equal(p16, p.half())
+    # non-finite gradients: the step is skipped, parameters untouched
+    g[5] = float("inf")
+    before = p.clone()
+    sumsq.zero_()
+    ops.grad_sumsq(g, sumsq)
+    ops.clip_coef(sumsq, coef, 1.0, 1.0)
+    ops.adamw_step(p, g, m, v, p16, lr=5e-5, step=4, coef=coef)
+    assert float(coef[1]) == 0.0 and torch.equal(p, before)
