@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""Headline benchmark: 512-token sequences/second of BERT-base topic-segmentation fine-tuning on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run, one rank per GPU)
+    python bench.py --impl reference ...                     (the reference's CPU path on the host cores)
+
+A "step" = one fine-tuning step on one synthetic batch of 32 x 512-token windows per GPU (BASELINE config 2,
+SURVEY.md §8d): embeddings -> 12 encoder layers -> token-cls head -> CE -> full backward -> gradient allreduce ->
+clip(1.0) -> AdamW.  value = whole-job sequences/s with the batch already resident in HBM; e2e = same through
+`DataParallelTrainer.step_from_host` with pinned-host inputs copied every step and the loss read back.
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEQ, BATCH, VOCAB = 512, 32, 30523
+FLOP_PER_SEQ = 289_910_292_480            # fwd+bwd, SURVEY.md §8d / BASELINE.md §3
+CFG = dict(hidden_size=768, num_attention_heads=12, intermediate_size=3072, num_hidden_layers=12, vocab_size=VOCAB,
+           max_position_embeddings=512, type_vocab_size=2)
+
+
+def synth_batch(torch, batch, seq, seed, padded=False):
+    """SURVEY.md §8d synthetic inputs for config 2."""
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(1000, 30522, (batch, seq), generator=g)
+    ids[:, 0] = 101
+    bos = torch.arange(1, seq, 20)
+    ids[:, bos] = 30522
+    mask = torch.ones(batch, seq, dtype=torch.long)
+    if padded:
+        lens = torch.randint(seq // 2, seq + 1, (batch,), generator=g)
+        mask = (torch.arange(seq)[None, :] < lens[:, None]).long()
+    tt = torch.zeros(batch, seq, dtype=torch.long)
+    labels = torch.full((batch, seq), -100, dtype=torch.long)
+    labels[:, bos] = (torch.rand(batch, len(bos), generator=g) < 0.85).long()
+    labels = torch.where(mask.bool(), labels, torch.full_like(labels, -100))
+    return ids, mask, tt, labels
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ reference (CPU) arm
+def cpu_reference_step_fn(torch, batch):
+    """The reference's own implementation of the path on host cores: HuggingFace `BertModel` (eager, fp32) — the class
+    bert_for_ts.py:7 imports — + Linear(768,2) + CE + backward + clip + AdamW.  Falls back to the oracle port."""
+    ids, mask, tt, labels = synth_batch(torch, batch, SEQ, 1234)
+    try:
+        from transformers import BertConfig, BertModel
+        cfg = BertConfig(attn_implementation="eager", hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, **CFG)
+        torch.manual_seed(0)
+        bert = BertModel(cfg, add_pooling_layer=False)
+        head = torch.nn.Linear(768, 2)
+        params = list(bert.parameters()) + list(head.parameters())
+        opt = torch.optim.AdamW(params, lr=5e-5, weight_decay=0.0)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            h = bert(ids, attention_mask=mask, token_type_ids=tt, return_dict=False)[0]
+            loss = torch.nn.functional.cross_entropy(head(h).view(-1, 2), labels.view(-1))
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(params, 1.0)
+            opt.step()
+            return float(loss.detach())
+        return step, "reference"
+    except Exception:
+        from oracle import bert_oracle as O
+        ocfg = O.OracleConfig(**CFG)
+        sd = {k: v.requires_grad_(not k.startswith("pooler")) for k, v in O.random_state_dict(ocfg, 0).items()}
+        w = (torch.randn(2, 768) * 0.02).requires_grad_(True)
+        b = torch.zeros(2, requires_grad=True)
+        params = [p for p in sd.values() if p.requires_grad] + [w, b]
+        opt = torch.optim.AdamW(params, lr=5e-5, weight_decay=0.0)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            loss, _ = O.topicseg_loss(sd, ocfg, w, b, ids, mask, tt, labels)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(params, 1.0)
+            opt.step()
+            return float(loss.detach())
+        return step, "port"
+
+
+def time_cpu_reference(torch, steps, warmup, batch):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step, kind = cpu_reference_step_fn(torch, batch)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(1, steps)
+    return {"value": batch / dt, "unit": "seq/s", "cores": cores, "kind": kind, "ms_per_step": dt * 1e3,
+            "sample": f"{steps} fwd+bwd+AdamW steps of [{batch},{SEQ}] BERT-base fp32 on {cores} host threads "
+                      f"(throughput is linear in batch)"}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    steps, warmup = max(1, min(args.steps, 20)), max(1, min(args.warmup, 2))
+    r = time_cpu_reference(torch, steps, warmup, batch=1)
+    line = {"impl": "reference", "metric": "512-tok seq/sec BERT-base topic-seg fine-tune", "value": r["value"], "unit": "seq/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": "emnlp2023-topic_segmentation BERT-base fine-tune, 512-tok windows (CPU reference path; "
+                                   "each step is a bounded [1,512] sample of the bsz-32 workload)", "seq_len": SEQ,
+                       "global_batch": 1, "parallelism": "cpu"},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def time_kernel(torch, fn, iters=20, warmup=3):
+    for _ in range(warmup):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e-3
+
+
+def kernel_rooflines(torch, ops, peaks):
+    """Live per-kernel numbers on the bench shapes (each kernel timed alone with CUDA events on the launch stream;
+    operands >> L2 for the big GEMMs)."""
+    M, H, I = BATCH * SEQ, 768, 3072
+    dev = "cuda"
+    f16 = torch.float16
+    x = torch.randn(M, H, device=dev, dtype=f16)
+    w1 = torch.randn(I, H, device=dev, dtype=f16) * 0.02
+    b1 = torch.zeros(I, device=dev)
+    h = torch.empty(M, I, device=dev, dtype=f16)
+    z = torch.empty(M, I, device=dev, dtype=f16)
+    out = {}
+    t = time_kernel(torch, lambda: ops.gemm(x, w1, h, epilogue=ops.EPI_BIAS_GELU, bias=b1, out2=z))
+    flops = 2.0 * M * H * I
+    out["gemm_ffn_up_gelu"] = {"bound": "tensor", "achieved": flops / t / 1e12, "unit": "TFLOP/s", "ms": t * 1e3}
+    w2 = torch.randn(H, I, device=dev, dtype=f16) * 0.02
+    pre = torch.empty(M, H, device=dev, dtype=torch.float32)
+    bo = torch.zeros(H, device=dev)
+    t = time_kernel(torch, lambda: ops.gemm(h, w2, pre, epilogue=ops.EPI_BIAS_RES, bias=bo, aux=x))
+    out["gemm_ffn_down_res"] = {"bound": "tensor", "achieved": flops / t / 1e12, "unit": "TFLOP/s", "ms": t * 1e3}
+    gw = torch.zeros(I, H, device=dev)
+    t = time_kernel(torch, lambda: ops.gemm(h, x, gw, a_layout=1, b_layout=1, epilogue=ops.EPI_ATOMIC, k_splits=ops.wgrad_splits(I, H, M)))
+    out["gemm_wgrad_ffn_up"] = {"bound": "tensor", "achieved": flops / t / 1e12, "unit": "TFLOP/s", "ms": t * 1e3}
+    qkv = torch.randn(M, 3 * H, device=dev, dtype=f16)
+    ctx = torch.empty(M, H, device=dev, dtype=f16)
+    lse = torch.empty(BATCH, 12, SEQ, device=dev)
+    t = time_kernel(torch, lambda: ops.attn_fwd(qkv, qkv, ctx, BATCH, 12, SEQ, SEQ, q_col0=0, k_col0=H, v_col0=2 * H, lse2=lse))
+    aflops = 4.0 * BATCH * SEQ * SEQ * H
+    out["attn_fwd"] = {"bound": "tensor", "achieved": aflops / t / 1e12, "unit": "TFLOP/s", "ms": t * 1e3}
+    dqkv = torch.empty_like(qkv)
+    ws = ops.attn_bwd_workspace(BATCH, 12, SEQ, dev)
+    t = time_kernel(torch, lambda: ops.attn_bwd(qkv, qkv, ctx, ctx, lse, dqkv, dqkv, ws, BATCH, 12, SEQ, SEQ, q_col0=0, k_col0=H,
+                                                v_col0=2 * H, dq_col0=0, dk_col0=H, dv_col0=2 * H))
+    out["attn_bwd"] = {"bound": "tensor", "achieved": 2 * aflops / t / 1e12, "unit": "TFLOP/s", "ms": t * 1e3}
+    g, b = torch.ones(H, device=dev), torch.zeros(H, device=dev)
+    y = torch.empty(M, H, device=dev, dtype=f16)
+    t = time_kernel(torch, lambda: ops.layernorm_fwd(pre, g, b, 1e-12, y=y))
+    out["layernorm_fwd"] = {"bound": "hbm", "achieved": M * H * (4 + 2) / t / 1e9, "unit": "GB/s", "ms": t * 1e3}
+    W = torch.randn(2, H, device=dev) * 0.02
+    t = time_kernel(torch, lambda: ops.cls_head_fwd(y, W, torch.zeros(2, device=dev)))
+    out["cls_head_fwd"] = {"bound": "hbm", "achieved": (M * H * 2 + M * 8) / t / 1e9, "unit": "GB/s", "ms": t * 1e3}
+    for v in out.values():
+        peak = peaks["bf16_tflops"] if v["bound"] == "tensor" else peaks["hbm_gbs"]
+        v["peak"], v["frac"] = peak, v["achieved"] / peak
+    return out
+
+
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from transformers import BertConfig
+    from spokennlp_b200 import lib, ops
+    from spokennlp_b200.trainer import DataParallelTrainer, TopicSegModel
+
+    torch.manual_seed(0)
+    cfg = BertConfig(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, **CFG)
+    model = TopicSegModel(cfg)
+    trainer = DataParallelTrainer(model, lr=5e-5, total_steps=10 * (args.steps + args.warmup) + 1000)
+    host = [t.pin_memory() for t in synth_batch(torch, BATCH, SEQ, 1234 + rank)]
+    dev = [t.cuda(non_blocking=True) for t in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) * 1e-3
+
+    for _ in range(max(3, args.warmup)):
+        trainer.step(*dev)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.launch_count()
+    secs = timed(lambda: trainer.step(*dev), args.steps)
+    launches = lib.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * BATCH * args.steps / secs
+
+    # end to end: pinned host batch -> H2D every step, loss read back every step
+    h2d = sum(t.numel() * t.element_size() for t in host)
+
+    def e2e_step():
+        batch = [t.cuda(non_blocking=True) for t in host]
+        trainer.step(*batch)
+        return trainer.loss_value()          # D2H of the 2-float loss statistics (synchronises)
+    for _ in range(2):
+        e2e_step()
+    e2e_secs = timed(e2e_step, args.steps)
+    e2e_value = world * BATCH * args.steps / e2e_secs
+    loss = trainer.loss_value()
+
+    if rank == 0:
+        peaks, peak_src = load_peaks()
+        kr = kernel_rooflines(torch, ops, peaks)
+        dom = kr["gemm_ffn_up_gelu"]
+        cpu = time_cpu_reference(torch, steps=3, warmup=1, batch=2) if (world == 1 and not args.no_cpu_baseline) else None
+        line = {
+            "metric": "512-tok seq/sec BERT-base topic-seg fine-tune", "value": value, "unit": "seq/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp16 operands, fp32 accumulate/master", "data": "synthetic",
+            "config": {"workload": "emnlp2023-topic_segmentation BERT-base fine-tune, 512-tok windows, bsz 32/GPU "
+                                   "(fwd + bwd + grad allreduce + clip + AdamW)", "seq_len": SEQ, "batch_per_gpu": BATCH,
+                       "global_batch": BATCH * world, "parallelism": f"dp{world}", "dropout": 0.0,
+                       "l2": "per-step working set ~5.4 GB of activations >> 126 MB L2 (no explicit flush needed)"},
+            "encoder_flop_util": {"flop_per_seq": FLOP_PER_SEQ, "achieved_tflops_per_gpu": value / world * FLOP_PER_SEQ / 1e12,
+                                  "peak_tflops_sustained": peaks["bf16_tflops_sustained"], "peak_source": peak_src,
+                                  "frac_of_sustained": value / world * FLOP_PER_SEQ / 1e12 / peaks["bf16_tflops_sustained"]},
+            "roofline": {"kernel": "gemm_f16_kernel<256,K,K,BIAS_GELU> (FFN-up 16384x3072x768)", "bound": "tensor",
+                         "achieved": dom["achieved"], "peak": dom["peak"], "unit": "TFLOP/s", "frac": dom["frac"], "traffic": None,
+                         "peak_source": peak_src + " bf16 burst (kernel timed alone)"},
+            "kernels": kr,
+            "e2e": {"value": e2e_value, "unit": "seq/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
+                    "ms_per_step": e2e_secs / args.steps * 1e3},
+            "gpu_launches": launches, "clocks": clocks, "final_loss": loss,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # convenience: re-launch under torch.distributed.run, one rank per GPU (what the driver does itself)
+        import socket
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0))
+            port = s.getsockname()[1]
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr",
+               "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

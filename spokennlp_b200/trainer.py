@@ -1,0 +1,176 @@
+"""Data-parallel fine-tuning step for the topic-segmentation path (BASELINE config 2).
+
+What one step replaces in the reference: `BertWithDAForSentenceLabelingTopicSegmentation.forward`
+(bert_for_ts.py:35-113, `ts_score_predictor == "lt"` path: encoder -> Linear(H,2) -> CE over [BOS] rows),
+`loss.backward()`, DDP's gradient allreduce, `clip_grad_norm_(1.0)`, `AdamW.step`, linear-decay schedule
+(HF Trainer defaults).  HF `Trainer` itself cannot be constructed here (no `accelerate`).
+
+One process per GPU.  The only inter-GPU exchange is the gradient allreduce (NCCL over NVLink), issued per encoder
+layer as soon as that layer's weight gradients are complete so that it overlaps the rest of the backward.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+from . import ops
+from .engine import EMB_NAMES, EncoderEngine, FlatParams, layer_param_names
+from .modeling_bert import BertModel
+
+
+class TopicSegModel(nn.Module):
+    """Encoder + token-classification head with the reference wrapper's parameter names
+    (`bert.*`, `loss_calculator.classifier.*`: bert_for_ts.py:23, loss_calculator.py:17)."""
+
+    def __init__(self, config, num_labels: int = 2):
+        super().__init__()
+        self.config = config
+        self.bert = BertModel(config, add_pooling_layer=False)
+        self.loss_calculator = nn.Module()
+        self.loss_calculator.classifier = nn.Linear(config.hidden_size, num_labels)
+        nn.init.normal_(self.loss_calculator.classifier.weight, std=config.initializer_range)
+        nn.init.zeros_(self.loss_calculator.classifier.bias)
+
+
+class DataParallelTrainer:
+    def __init__(self, model: TopicSegModel, *, lr: float = 5e-5, total_steps: int = 1000, max_grad_norm: float = 1.0,
+                 weight_decay: float = 0.0, loss_scale: float = 32768.0, device: Optional[torch.device] = None):
+        self.model = model
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        cfg = model.config
+        own = dict(model.named_parameters())
+        names = ["bert." + n for n in EMB_NAMES]
+        self.layer_first = []
+        for i in range(cfg.num_hidden_layers):
+            self.layer_first.append("bert." + layer_param_names(i)[0])
+            names += ["bert." + n for n in layer_param_names(i)]
+        names += ["loss_calculator.classifier.weight", "loss_calculator.classifier.bias"]
+        flat = FlatParams([(n, own[n]) for n in names], self.device)
+        # the engine addresses parameters by their BertModel-relative names
+        flat_alias = _Aliased(flat, "bert.")
+        self.flat = flat
+        self.engine = EncoderEngine(flat_alias, cfg.hidden_size, cfg.num_attention_heads, cfg.intermediate_size,
+                                    cfg.num_hidden_layers, float(cfg.layer_norm_eps))
+        model.bert._engine = self.engine
+        flat.ensure_grad()
+        self.m = torch.zeros_like(flat.flat32)
+        self.v = torch.zeros_like(flat.flat32)
+        self.lr, self.total_steps, self.max_grad_norm, self.wd = lr, total_steps, max_grad_norm, weight_decay
+        self.step_idx = 0
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.scale = torch.tensor([loss_scale, 1.0 / loss_scale], dtype=torch.float32, device=self.device)
+        self.stats = torch.zeros(2, dtype=torch.float32, device=self.device)
+        self.sumsq = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.coef = torch.zeros(3, dtype=torch.float32, device=self.device)
+        self.num_labels = model.loss_calculator.classifier.weight.shape[0]
+        # gradient buckets: [embeddings | layer 0 | ... | layer L-1 + head], contiguous slices of the flat buffer
+        offs = [flat.offsets[n] for n in self.layer_first] + [flat.numel]
+        self.layer_slices = [(offs[i], offs[i + 1]) for i in range(cfg.num_hidden_layers)]
+        self.emb_slice = (0, offs[0])
+        self._works = []
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _allreduce_slice(self, lo: int, hi: int) -> None:
+        if self.world > 1 and hi > lo:
+            self._works.append(dist.all_reduce(self.flat.grad32[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+
+    def _after_layer(self, i: int) -> None:
+        if i >= 0:
+            self._allreduce_slice(*self.layer_slices[i])
+        else:
+            self._allreduce_slice(*self.emb_slice)
+
+    def forward_backward(self, input_ids, attention_mask, token_type_ids, labels) -> torch.Tensor:
+        """Enqueue forward + backward for one local batch; returns the device scalar loss (no sync)."""
+        eng, flat = self.engine, self.flat
+        B, S = input_ids.shape
+        flat.grad32.zero_()
+        key_bias = kv_len = None
+        if attention_mask is not None:
+            key_bias, kv_len = ops.mask_to_bias(attention_mask)
+        pos = None  # arange(S) per row
+        ids = input_ids.contiguous().view(-1)
+        tt = token_type_ids.contiguous().view(-1) if token_type_ids is not None else None
+        x16, saved, _, _ = eng.forward(ids, tt, pos, None, key_bias, kv_len, B, S, save=True)
+        W32 = flat.view32("loss_calculator.classifier.weight")
+        b32 = flat.view32("loss_calculator.classifier.bias")
+        logits = ops.cls_head_fwd(x16, W32, b32)
+        lab = labels.contiguous().view(-1)
+        self.stats.zero_()
+        ops.ce_stats(logits, lab, self.stats)
+        dh = torch.empty_like(x16)
+        ops.cls_head_bwd(x16, logits, lab, self.stats, W32, dh, flat.viewg("loss_calculator.classifier.weight"),
+                         flat.viewg("loss_calculator.classifier.bias"), scale=self.scale[0:1])
+        self._works = []
+        # the head's gradients live in the last bucket, which is reduced right after the top layer's backward
+        eng.backward(saved, dh, self.scale[1:2], after_layer=self._after_layer)
+        self.last_logits = logits
+        return self.stats
+
+    def optimizer_step(self) -> None:
+        for w in self._works:
+            w.wait()
+        self._works = []
+        flat = self.flat
+        self.step_idx += 1
+        lr = self.lr * max(0.0, 1.0 - (self.step_idx - 1) / max(1, self.total_steps))       # HF linear schedule, 0 warm-up
+        self.sumsq.zero_()
+        ops.grad_sumsq(flat.grad32, self.sumsq)
+        ops.clip_coef(self.sumsq, self.coef, self.max_grad_norm, 1.0 / self.world)
+        ops.adamw_step(flat.flat32, flat.grad32, self.m, self.v, flat.flat16, lr=lr, weight_decay=self.wd,
+                       step=self.step_idx, coef=self.coef)
+        flat.version = flat.cur_version()       # the fused step refreshed the fp16 mirror itself
+
+    def step(self, input_ids, attention_mask, token_type_ids, labels) -> torch.Tensor:
+        stats = self.forward_backward(input_ids, attention_mask, token_type_ids, labels)
+        self.optimizer_step()
+        return stats
+
+    def loss_value(self) -> float:
+        s = self.stats.tolist()     # device -> host read
+        return s[0] / max(s[1], 1e-30)
+
+
+class _Aliased:
+    """FlatParams view that resolves BertModel-relative names inside a larger (prefixed) flat buffer."""
+
+    def __init__(self, flat: FlatParams, prefix: str):
+        self._f, self._p = flat, prefix
+
+    def view32(self, name, extra=()):
+        return self._f.view32(self._p + name, tuple(self._p + e for e in extra))
+
+    def view16(self, name, extra=()):
+        return self._f.view16(self._p + name, tuple(self._p + e for e in extra))
+
+    def viewg(self, name, extra=()):
+        return self._f.viewg(self._p + name, tuple(self._p + e for e in extra))
+
+    def sync_half(self, force: bool = False):
+        return self._f.sync_half(force)
+
+    def intact(self):
+        return self._f.intact()
+
+    @property
+    def names(self):
+        return [n[len(self._p):] for n in self._f.names if n.startswith(self._p)]
+
+    @property
+    def params(self):
+        return {n[len(self._p):]: p for n, p in self._f.params.items() if n.startswith(self._p)}
+
+    @property
+    def flat32(self):
+        return self._f.flat32
+
+    @property
+    def grad32(self):
+        return self._f.grad32
+
+    @grad32.setter
+    def grad32(self, v):
+        self._f.grad32 = v

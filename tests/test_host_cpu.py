@@ -1,0 +1,72 @@
+"""CPU-side checks (no GPU): the C-ABI library builds, loads and exports every symbol include/b200enc.h declares;
+the drop-in module has HF-identical state_dict keys and refuses to run without CUDA (no fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from spokennlp_b200 import lib as L
+    if not os.path.exists(L.LIB_PATH):
+        L.build()
+    return L
+
+
+def test_library_exports_every_declared_symbol(lib):
+    hdr = open(os.path.join(ROOT, "include", "b200enc.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    so = ctypes.CDLL(lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(so, name), f"{name} declared in include/b200enc.h but not exported"
+    bound = set(lib.exported_symbols())
+    assert declared == bound, (declared - bound, bound - declared)
+    assert lib.load().b200_version() >= 100
+
+
+def test_library_reports_errors_without_gpu(lib):
+    so = lib.load()
+    # argument validation happens before any CUDA call, so it is testable here
+    rc = so.b200_gemm_f16(None, 0, 0, None, 0, 0, 0, 0, 0, 0, None, None, 0, None, 0, 0, None, 0, None, 1, None)
+    assert rc == -1 and b"empty problem" in so.b200_last_error()
+    with pytest.raises(lib.B200Error):
+        lib.check(rc, "b200_gemm_f16")
+
+
+def test_dropin_state_dict_keys_match_hf_and_no_cpu_fallback():
+    from transformers import BertConfig
+    from transformers import BertModel as HFBert
+    from spokennlp_b200 import BertModel
+    cfg = BertConfig(hidden_size=128, num_attention_heads=2, intermediate_size=256, num_hidden_layers=2, vocab_size=100,
+                     max_position_embeddings=64)
+    ours, hf = BertModel(cfg), HFBert(cfg)
+    assert list(ours.state_dict().keys()) == list(hf.state_dict().keys())
+    for (k, a), (_, b) in zip(ours.state_dict().items(), hf.state_dict().items()):
+        assert a.shape == b.shape, k
+    ours.load_state_dict(hf.state_dict())                      # reference checkpoints load unchanged
+    nopool = BertModel(cfg, add_pooling_layer=False)
+    assert not any(k.startswith("pooler") for k in nopool.state_dict())
+    ours.resize_token_embeddings(101)                          # ts_sentence_seq_labeling.py:284
+    assert ours.embeddings.word_embeddings.weight.shape[0] == 101
+    from spokennlp_b200.lib import B200Error
+    with pytest.raises(B200Error):
+        ours(torch.zeros(1, 8, dtype=torch.long))
+    with pytest.raises(B200Error):
+        BertModel(BertConfig(hidden_size=96, num_attention_heads=2))   # head_dim != 64
+
+
+def test_wgrad_split_heuristic_never_leaves_empty_splits():
+    from spokennlp_b200.ops import wgrad_splits
+    for Mo, Ni, T in [(768, 768, 16384), (2304, 768, 16384), (3072, 768, 16384), (768, 3072, 16384), (128, 256, 64),
+                      (768, 768, 300), (2304, 768, 4096 * 2)]:
+        s = wgrad_splits(Mo, Ni, T)
+        kb = (T + 63) // 64
+        per = (kb + s - 1) // s
+        assert s >= 1 and per * (s - 1) < kb
