@@ -37,6 +37,7 @@ extern "C" {
 #define B200_EPI_DGELU 4          /* out = acc * gelu'(aux[m,n])              (autograd of :436-439) */
 #define B200_EPI_ADD 5            /* out = acc + aux[m,n]                     (dgrad + residual-branch gradient) */
 #define B200_EPI_ATOMIC 6         /* out(fp32) += alpha * acc                 (wgrad, split-K) */
+#define B200_EPI_BIAS_RES32 7     /* out(fp32) = acc + bias[n] + aux32[m,n]   (as BIAS_RES with the residual stream kept in fp32) */
 
 #define B200_DT_F16 0
 #define B200_DT_F32 1
@@ -52,10 +53,12 @@ long long b200_launch_count(void);
  *   b_layout 0: B stored [N,K] row-major (torch Linear.weight) 1: B stored [K,N] row-major
  * Replaces torch.nn.functional.linear and its autograd (dgrad: b_layout=1 on the same weight; wgrad:
  * a_layout=b_layout=1 on dY and X) — SURVEY.md K2, K4, K5, K6, K8.
- * Supported (a_layout,b_layout,epilogue,out_dtype): (0,0,{STORE,BIAS,BIAS_GELU,BIAS_RES},{F16,F32*}),
- * (0,1,{STORE,ADD,DGELU},F16), (1,1,ATOMIC,F32).  (*F32 for STORE and BIAS_RES only.)
+ * Supported (a_layout,b_layout,epilogue,out_dtype): (0,0,{STORE,BIAS,BIAS_GELU,BIAS_RES,BIAS_RES32},{F16,F32*}),
+ * (0,1,{STORE,ADD,DGELU},F16), (1,1,ATOMIC,F32).  (*F32 for STORE, BIAS_RES, BIAS_RES32; BIAS_RES32 is F32-only.)
  * alpha: optional device scalar multiplied into the accumulator.  k_splits > 1 only with EPI_ATOMIC.
  */
+/* 2 (default): 2-CTA cta_group::2 kernel with TMA epilogue; 1: single-CTA kernel (kept for A/B measurements) */
+void b200_set_gemm_impl(int impl);
 int b200_gemm_f16(const void* A, int lda, int a_layout, const void* B, int ldb, int b_layout, int M, int N, int K,
                   int epilogue, const float* bias, const void* aux, int ld_aux, void* out, int ld_out, int out_dtype,
                   void* out2, int ld_out2, const float* alpha, int k_splits, void* stream);

@@ -11,6 +11,7 @@
 #include "attn_bwd.cuh"
 #include "attn_fwd.cuh"
 #include "gemm.cuh"
+#include "gemm2.cuh"
 #include "optim.cuh"
 #include "rowwise.cuh"
 
@@ -57,7 +58,7 @@ EncodeTiledFn get_encode() {
 struct MapKey {
   const void* ptr;
   uint64_t rows, cols, ld;
-  uint32_t box_rows;
+  uint32_t box_rows;   // bit 31 set: fp32 elements
   bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows; }
 };
 struct MapKeyHash {
@@ -72,12 +73,14 @@ struct MapKeyHash {
 std::mutex g_map_mu;
 std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 
-// 2D fp16 tensor [rows, cols] with row pitch ld (elements); box = 64 columns (128 B, SWIZZLE_128B) x box_rows.
-int get_tmap(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, CUtensorMap* out) {
-  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld % 8) || cols == 0 || rows == 0 || box_rows == 0 || box_rows > 256)
+// 2D tensor [rows, cols] (fp16, or fp32 when f32 is set) with row pitch ld (elements); box = 128 bytes of columns
+// (SWIZZLE_128B) x box_rows.
+int get_tmap(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, CUtensorMap* out, bool f32 = false) {
+  const uint64_t esz = f32 ? 4 : 2;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * esz) % 16) || cols == 0 || rows == 0 || box_rows == 0 || box_rows > 256)
     return fail(B200_ERR_SHAPE, "tensor map: ptr %p rows %llu cols %llu ld %llu box_rows %u violates 16B alignment / ld%%8", ptr,
                 (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
-  const MapKey key{ptr, rows, cols, ld, box_rows};
+  const MapKey key{ptr, rows, cols, ld, box_rows | (f32 ? 0x80000000u : 0u)};
   {
     std::lock_guard<std::mutex> lk(g_map_mu);
     auto it = g_maps.find(key);
@@ -89,11 +92,11 @@ int get_tmap(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(B200_ERR_CUDA, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
   const cuuint64_t dims[2] = {cols, rows};
-  const cuuint64_t strides[1] = {ld * 2};
-  const cuuint32_t box[2] = {64, box_rows};
+  const cuuint64_t strides[1] = {ld * esz};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / esz), box_rows};
   const cuuint32_t estr[2] = {1, 1};
   CUtensorMap m;
-  const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  const CUresult r = enc(&m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(B200_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", static_cast<int>(r));
@@ -136,9 +139,26 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g,
   return check_launch("gemm_f16_kernel");
 }
 
+std::atomic<int> g_gemm_impl{2};
+
+template <int BN, int A_MN, int B_MN, int EPI, typename OutT>
+int launch_gemm2(const Gemm2Maps& maps, const GemmArgs& g, cudaStream_t s) {
+  auto kern = gemm2_f16_kernel<BN, A_MN, B_MN, EPI, OutT>;
+  static int configured = set_smem(kern, Gemm2Smem<BN>::TOTAL);
+  if (configured != B200_OK) return configured;
+  const int m_tiles = (g.M + G2_BM - 1) / G2_BM, n_tiles = (g.N + BN - 1) / BN;
+  const int units = m_tiles * n_tiles * (g.k_splits > 0 ? g.k_splits : 1);
+  const int pairs = sm_count() / 2;
+  const int grid = 2 * (units < pairs ? units : pairs);
+  kern<<<grid, G2_THREADS, Gemm2Smem<BN>::TOTAL, s>>>(maps, g);
+  return check_launch("gemm2_f16_kernel");
+}
+
 }  // namespace
 
 extern "C" {
+
+void b200_set_gemm_impl(int impl) { g_gemm_impl.store(impl == 1 ? 1 : 2); }
 
 const char* b200_last_error(void) { return g_err.c_str(); }
 int b200_version(void) { return 100; }
@@ -150,14 +170,47 @@ int b200_gemm_f16(const void* A, int lda, int a_layout, const void* B, int ldb, 
   if (M <= 0 || N <= 0 || K <= 0) return fail(B200_ERR_SHAPE, "gemm: empty problem %dx%dx%d", M, N, K);
   if ((N % 4) || (ld_out % 4)) return fail(B200_ERR_SHAPE, "gemm: N and ld_out must be multiples of 4 (N=%d ld_out=%d)", N, ld_out);
   if (!A || !B || !out) return fail(B200_ERR_SHAPE, "gemm: null operand");
-  const bool needs_bias = epilogue == EPI_BIAS || epilogue == EPI_BIAS_GELU || epilogue == EPI_BIAS_RES;
-  const bool needs_aux = epilogue == EPI_BIAS_RES || epilogue == EPI_DGELU || epilogue == EPI_ADD;
+  const bool needs_bias = epilogue == EPI_BIAS || epilogue == EPI_BIAS_GELU || epilogue == EPI_BIAS_RES || epilogue == EPI_BIAS_RES32;
+  const bool needs_aux = epilogue == EPI_BIAS_RES || epilogue == EPI_DGELU || epilogue == EPI_ADD || epilogue == EPI_BIAS_RES32;
   if (needs_bias && !bias) return fail(B200_ERR_SHAPE, "gemm: epilogue %d needs bias", epilogue);
   if (needs_aux && (!aux || (ld_aux % 4))) return fail(B200_ERR_SHAPE, "gemm: epilogue %d needs aux with ld%%4==0", epilogue);
   if (k_splits > 1 && epilogue != EPI_ATOMIC) return fail(B200_ERR_SHAPE, "gemm: split-K only with the atomic epilogue");
   constexpr int BN = 256;
-  CUtensorMap ta, tb;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
   int rc;
+  const bool v2_ok = !(epilogue == EPI_BIAS_RES && out_dtype == B200_DT_F32);
+  if (g_gemm_impl.load() == 2 && v2_ok) {
+    // 2-CTA path: per-CTA operand boxes are 128 rows (K-major) / 64x64 (MN-major); epilogue slabs are 32 rows x 128 B
+    Gemm2Maps mp;
+    rc = a_layout == 0 ? get_tmap(A, M, K, lda, 128, &mp.a) : get_tmap(A, K, M, lda, GEMM_BK, &mp.a);
+    if (rc) return rc;
+    rc = b_layout == 0 ? get_tmap(B, N, K, ldb, BN / 2, &mp.b) : get_tmap(B, K, N, ldb, GEMM_BK, &mp.b);
+    if (rc) return rc;
+    const bool o32 = out_dtype == B200_DT_F32;
+    if ((rc = get_tmap(out, M, N, ld_out, 32, &mp.out, o32))) return rc;
+    mp.aux = mp.out;
+    mp.out2 = mp.out;
+    if (needs_aux && (rc = get_tmap(aux, M, N, ld_aux, 32, &mp.aux, epilogue == EPI_BIAS_RES32))) return rc;
+    if (epilogue == EPI_BIAS_GELU && out2 && (rc = get_tmap(out2, M, N, ld_out2, 32, &mp.out2))) return rc;
+    GemmArgs g2{M, N, K, k_splits > 0 ? k_splits : 1, bias, static_cast<const __half*>(aux), ld_aux, out, ld_out,
+                static_cast<__half*>(out2), ld_out2, alpha};
+    switch (a_layout * 1000 + b_layout * 100 + epilogue * 10 + out_dtype) {
+      case 0 * 1000 + 0 * 100 + EPI_STORE * 10 + B200_DT_F16: return launch_gemm2<BN, 0, 0, EPI_STORE, __half>(mp, g2, s);
+      case 0 * 1000 + 0 * 100 + EPI_STORE * 10 + B200_DT_F32: return launch_gemm2<BN, 0, 0, EPI_STORE, float>(mp, g2, s);
+      case 0 * 1000 + 0 * 100 + EPI_BIAS * 10 + B200_DT_F16: return launch_gemm2<BN, 0, 0, EPI_BIAS, __half>(mp, g2, s);
+      case 0 * 1000 + 0 * 100 + EPI_BIAS_GELU * 10 + B200_DT_F16: return launch_gemm2<BN, 0, 0, EPI_BIAS_GELU, __half>(mp, g2, s);
+      case 0 * 1000 + 0 * 100 + EPI_BIAS_RES * 10 + B200_DT_F16: return launch_gemm2<BN, 0, 0, EPI_BIAS_RES, __half>(mp, g2, s);
+      case 0 * 1000 + 0 * 100 + EPI_BIAS_RES32 * 10 + B200_DT_F32: return launch_gemm2<BN, 0, 0, EPI_BIAS_RES32, float>(mp, g2, s);
+      case 0 * 1000 + 1 * 100 + EPI_STORE * 10 + B200_DT_F16: return launch_gemm2<BN, 0, 1, EPI_STORE, __half>(mp, g2, s);
+      case 0 * 1000 + 1 * 100 + EPI_ADD * 10 + B200_DT_F16: return launch_gemm2<BN, 0, 1, EPI_ADD, __half>(mp, g2, s);
+      case 0 * 1000 + 1 * 100 + EPI_DGELU * 10 + B200_DT_F16: return launch_gemm2<BN, 0, 1, EPI_DGELU, __half>(mp, g2, s);
+      case 1 * 1000 + 1 * 100 + EPI_ATOMIC * 10 + B200_DT_F32: return launch_gemm2<BN, 1, 1, EPI_ATOMIC, float>(mp, g2, s);
+      default:
+        return fail(B200_ERR_SHAPE, "gemm: unsupported (a_layout=%d, b_layout=%d, epilogue=%d, out_dtype=%d)", a_layout, b_layout,
+                    epilogue, out_dtype);
+    }
+  }
+  CUtensorMap ta, tb;
   // K-major operand: matrix [MN, K], box 64(K) x tile rows.  MN-major operand: matrix [K, MN], box 64(MN) x 64(K rows).
   rc = a_layout == 0 ? get_tmap(A, M, K, lda, GEMM_BM, &ta) : get_tmap(A, K, M, lda, GEMM_BK, &ta);
   if (rc) return rc;
@@ -165,7 +218,6 @@ int b200_gemm_f16(const void* A, int lda, int a_layout, const void* B, int ldb, 
   if (rc) return rc;
   GemmArgs g{M, N, K, k_splits > 0 ? k_splits : 1, bias, static_cast<const __half*>(aux), ld_aux, out, ld_out,
              static_cast<__half*>(out2), ld_out2, alpha};
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int key = a_layout * 1000 + b_layout * 100 + epilogue * 10 + out_dtype;
   switch (key) {
     case 0 * 1000 + 0 * 100 + EPI_STORE * 10 + B200_DT_F16: return launch_gemm<BN, 0, 0, EPI_STORE, __half>(ta, tb, g, s);
@@ -174,6 +226,7 @@ int b200_gemm_f16(const void* A, int lda, int a_layout, const void* B, int ldb, 
     case 0 * 1000 + 0 * 100 + EPI_BIAS_GELU * 10 + B200_DT_F16: return launch_gemm<BN, 0, 0, EPI_BIAS_GELU, __half>(ta, tb, g, s);
     case 0 * 1000 + 0 * 100 + EPI_BIAS_RES * 10 + B200_DT_F16: return launch_gemm<BN, 0, 0, EPI_BIAS_RES, __half>(ta, tb, g, s);
     case 0 * 1000 + 0 * 100 + EPI_BIAS_RES * 10 + B200_DT_F32: return launch_gemm<BN, 0, 0, EPI_BIAS_RES, float>(ta, tb, g, s);
+    case 0 * 1000 + 0 * 100 + EPI_BIAS_RES32 * 10 + B200_DT_F32: return launch_gemm<BN, 0, 0, EPI_BIAS_RES32, float>(ta, tb, g, s);
     case 0 * 1000 + 1 * 100 + EPI_STORE * 10 + B200_DT_F16: return launch_gemm<BN, 0, 1, EPI_STORE, __half>(ta, tb, g, s);
     case 0 * 1000 + 1 * 100 + EPI_ADD * 10 + B200_DT_F16: return launch_gemm<BN, 0, 1, EPI_ADD, __half>(ta, tb, g, s);
     case 0 * 1000 + 1 * 100 + EPI_DGELU * 10 + B200_DT_F16: return launch_gemm<BN, 0, 1, EPI_DGELU, __half>(ta, tb, g, s);
@@ -301,8 +354,11 @@ int b200_embed_ln_bwd(const void* dy, const void* dy2, const int64_t* ids, const
                       const float* pos_tab, const float* type_tab, const float* gamma, float* dword, float* dpos, float* dtype_tab,
                       float* dgamma, float* dbeta, const float* alpha, int rows, int S, int H, float eps, void* stream) {
   if (int rc = check_row_shape("embed_ln_bwd", rows, H)) return rc;
-  const int grid = (rows + ROW_WARPS - 1) / ROW_WARPS;
-  embed_ln_bwd_kernel<<<grid, ROW_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+  int grid = (rows + ROW_WARPS - 1) / ROW_WARPS;
+  if (grid > sm_count() * 4) grid = sm_count() * 4;
+  static int c = set_smem(embed_ln_bwd_kernel, 3 * ROW_WARPS * ROW_MAXV * 256 * 4);
+  if (c) return c;
+  embed_ln_bwd_kernel<<<grid, ROW_WARPS * 32, 3 * ROW_WARPS * H * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __half*>(dy), static_cast<const __half*>(dy2), ids, tt, pos, word, pos_tab, type_tab, gamma, dword, dpos, dtype_tab,
       dgamma, dbeta, alpha, rows, S, H, eps);
   return check_launch("embed_ln_bwd_kernel");

@@ -32,13 +32,14 @@ enum : int {
   EPI_DGELU = 4,      // out = acc * gelu'(aux[m,n])
   EPI_ADD = 5,        // out = acc + aux[m,n]
   EPI_ATOMIC = 6,     // out(fp32) += alpha * acc   (split-K reduction with red.global.add)
+  EPI_BIAS_RES32 = 7, // out = acc + bias[n] + aux32[m,n]   (fp32 residual stream)
 };
 
 struct GemmArgs {
   int M, N, K;
   int k_splits;
   const float* bias;
-  const __half* aux;
+  const __half* aux;    // fp16 [M, ld_aux]; reinterpreted as const float* by EPI_BIAS_RES32
   int ld_aux;
   void* out;
   int ld_out;
@@ -56,6 +57,81 @@ struct GemmSmem {
   static constexpr int BAR_OFFSET = GEMM_STAGES * STAGE_BYTES + EPI_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // + barriers + alignment slack
 };
+
+// Epilogue of one 32-row x BN-column slab owned by one warp: TMEM -> registers (row per thread) -> warp-private smem
+// transpose -> coalesced bias / activation / residual math and global stores.  `release_acc` is invoked (lane 0) as soon
+// as the accumulator has been read out of TMEM.
+template <int BN, int EPI, typename OutT, typename ReleaseFn>
+__device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& g, float* st, uint32_t tmem_acc, int m0, int n0, int lane, float alpha,
+                                                   bool has_data, ReleaseFn release_acc) {
+  const int cl = (lane & 7) * 4;                // column group handled in the coalesced phase
+  const int rl = lane >> 3;                     // row within a group of 4
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    uint32_t v[32];
+    tmem_ld_x32(tmem_acc + c * 32, v);
+    tmem_wait_ld();
+    if (c == BN / 32 - 1) {                   // accumulator drained: hand the TMEM stage back to the MMA warp
+      tc_fence_before();
+      if (lane == 0) release_acc();
+    }
+    float* my = st + lane * GEMM_STAGE_PITCH;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<float4*>(my + 4 * j) = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                           __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+    __syncwarp();
+    const int gc = n0 + c * 32 + cl;
+    if (gc < g.N && has_data) {
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_RES || EPI == EPI_BIAS_RES32) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + gc));
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + rl;
+        const int gr = m0 + r;
+        if (gr >= g.M) continue;
+        float4 a = *reinterpret_cast<const float4*>(st + r * GEMM_STAGE_PITCH + cl);
+        a.x = fmaf(a.x, alpha, b4.x); a.y = fmaf(a.y, alpha, b4.y); a.z = fmaf(a.z, alpha, b4.z); a.w = fmaf(a.w, alpha, b4.w);
+        if (EPI == EPI_BIAS_RES32) {
+          const float4 r4 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(g.aux) + static_cast<size_t>(gr) * g.ld_aux + gc));
+          a.x += r4.x; a.y += r4.y; a.z += r4.z; a.w += r4.w;
+        }
+        if (EPI == EPI_BIAS_RES || EPI == EPI_DGELU || EPI == EPI_ADD) {
+          const uint2 raw = __ldg(reinterpret_cast<const uint2*>(g.aux + static_cast<size_t>(gr) * g.ld_aux + gc));
+          const float2 x01 = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+          const float2 x23 = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+          if (EPI == EPI_DGELU) {
+            a.x *= gelu_erf_grad(x01.x); a.y *= gelu_erf_grad(x01.y); a.z *= gelu_erf_grad(x23.x); a.w *= gelu_erf_grad(x23.y);
+          } else {
+            a.x += x01.x; a.y += x01.y; a.z += x23.x; a.w += x23.y;
+          }
+        }
+        if (EPI == EPI_BIAS_GELU) {
+          if (g.out2) {
+            __half2 z01 = __floats2half2_rn(a.x, a.y), z23 = __floats2half2_rn(a.z, a.w);
+            uint2 zr;
+            zr.x = *reinterpret_cast<uint32_t*>(&z01);
+            zr.y = *reinterpret_cast<uint32_t*>(&z23);
+            *reinterpret_cast<uint2*>(g.out2 + static_cast<size_t>(gr) * g.ld_out2 + gc) = zr;
+          }
+          a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w);
+        }
+        if (EPI == EPI_ATOMIC) {
+          red_add_v4(reinterpret_cast<float*>(g.out) + static_cast<size_t>(gr) * g.ld_out + gc, a.x, a.y, a.z, a.w);
+        } else if (sizeof(OutT) == 4) {
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + static_cast<size_t>(gr) * g.ld_out + gc) = a;
+        } else {
+          __half2 o01 = __floats2half2_rn(a.x, a.y), o23 = __floats2half2_rn(a.z, a.w);
+          uint2 o;
+          o.x = *reinterpret_cast<uint32_t*>(&o01);
+          o.y = *reinterpret_cast<uint32_t*>(&o23);
+          *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(g.out) + static_cast<size_t>(gr) * g.ld_out + gc) = o;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
 
 template <int BN, int A_MN, int B_MN, int EPI, typename OutT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -181,8 +257,6 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ------------------------------------------------------------------ epilogue (warps 2..5)
     const int q = warp & 3;                       // TMEM lane quadrant this warp may read
     float* st = sEpi + (warp - 2) * 32 * GEMM_STAGE_PITCH;
-    const int cl = (lane & 7) * 4;                // column group handled in the coalesced phase
-    const int rl = lane >> 3;                     // row within a group of 4
     const float alpha = g.alpha ? __ldg(g.alpha) : 1.0f;
     uint32_t acc = 0, acc_phase = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
@@ -192,67 +266,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const bool has_data = kb1 > kb0;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32, v);
-        tmem_wait_ld();
-        if (c == BN / 32 - 1) {                   // accumulator drained: hand the TMEM stage back to the MMA warp
-          tc_fence_before();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        }
-        float* my = st + lane * GEMM_STAGE_PITCH;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(my + 4 * j) = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                                               __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-        __syncwarp();
-        const int gc = n0 + c * 32 + cl;
-        if (gc < g.N && has_data) {
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_RES) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + gc));
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int r = it * 4 + rl;
-            const int gr = m0 + r;
-            if (gr >= g.M) continue;
-            float4 a = *reinterpret_cast<const float4*>(st + r * GEMM_STAGE_PITCH + cl);
-            a.x = fmaf(a.x, alpha, b4.x); a.y = fmaf(a.y, alpha, b4.y); a.z = fmaf(a.z, alpha, b4.z); a.w = fmaf(a.w, alpha, b4.w);
-            if (EPI == EPI_BIAS_RES || EPI == EPI_DGELU || EPI == EPI_ADD) {
-              const uint2 raw = __ldg(reinterpret_cast<const uint2*>(g.aux + static_cast<size_t>(gr) * g.ld_aux + gc));
-              const float2 x01 = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
-              const float2 x23 = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
-              if (EPI == EPI_DGELU) {
-                a.x *= gelu_erf_grad(x01.x); a.y *= gelu_erf_grad(x01.y); a.z *= gelu_erf_grad(x23.x); a.w *= gelu_erf_grad(x23.y);
-              } else {
-                a.x += x01.x; a.y += x01.y; a.z += x23.x; a.w += x23.y;
-              }
-            }
-            if (EPI == EPI_BIAS_GELU) {
-              if (g.out2) {
-                __half2 z01 = __floats2half2_rn(a.x, a.y), z23 = __floats2half2_rn(a.z, a.w);
-                uint2 zr;
-                zr.x = *reinterpret_cast<uint32_t*>(&z01);
-                zr.y = *reinterpret_cast<uint32_t*>(&z23);
-                *reinterpret_cast<uint2*>(g.out2 + static_cast<size_t>(gr) * g.ld_out2 + gc) = zr;
-              }
-              a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w);
-            }
-            if (EPI == EPI_ATOMIC) {
-              red_add_v4(reinterpret_cast<float*>(g.out) + static_cast<size_t>(gr) * g.ld_out + gc, a.x, a.y, a.z, a.w);
-            } else if (sizeof(OutT) == 4) {
-              *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + static_cast<size_t>(gr) * g.ld_out + gc) = a;
-            } else {
-              __half2 o01 = __floats2half2_rn(a.x, a.y), o23 = __floats2half2_rn(a.z, a.w);
-              uint2 o;
-              o.x = *reinterpret_cast<uint32_t*>(&o01);
-              o.y = *reinterpret_cast<uint32_t*>(&o23);
-              *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(g.out) + static_cast<size_t>(gr) * g.ld_out + gc) = o;
-            }
-          }
-        }
-        __syncwarp();
-      }
+      gemm_epilogue_tile<BN, EPI, OutT>(g, st, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN, m0, n0, lane, alpha, has_data,
+                                        [&] { mbar_arrive(&tempty_bar[acc]); });
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }

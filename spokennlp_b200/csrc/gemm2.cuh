@@ -1,0 +1,387 @@
+// 2-CTA (cta_group::2) tcgen05 GEMM with a TMA-driven epilogue — the production path for the encoder's dense
+// contractions.  Same math / operand layouts as gemm.cuh, re-tiled for the B200 SM pair:
+//
+//   * a cluster of two CTAs (one TPC) owns a 256 x 256 output tile; each CTA stages its own 128 rows of A and HALF of
+//     the B tile (128 of 256 rows), so per-SM shared-memory fill and L2->SM traffic drop from 48 KB to 32 KB per
+//     64-wide K block while every tcgen05.mma does 256x256x16;
+//   * the leader CTA's MMA warp issues tcgen05.mma.cta_group::2 for both SMs; completion is multicast to the
+//     mbarriers of both CTAs (smem-slot release, accumulator-ready);
+//   * accumulators: 2 x 256 TMEM columns per CTA (epilogue of tile i overlaps the mainloop of tile i+1);
+//   * epilogue: four warps per CTA, one thread per accumulator row: TMEM -> registers -> bias / GELU / residual /
+//     dGELU math -> fp16/fp32 128B-swizzled staging rows -> TMA store (or TMA reduce-add for split-K wgrad).
+//     Auxiliary row-major inputs (residual, pre-activation) arrive by TMA into the same swizzled staging geometry, so
+//     no thread issues an uncoalesced global access and the aux fetch of chunk c+1 overlaps the math of chunk c.
+#pragma once
+#include "gemm.cuh"
+
+namespace b200 {
+
+constexpr int G2_THREADS = 192;           // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int G2_STAGES = 4;
+constexpr int G2_BM = 256;                // rows per CTA pair
+
+template <int BN>
+struct Gemm2Smem {
+  static constexpr int A_BYTES = 128 * GEMM_BK * 2;          // 16 KB : this CTA's 128 rows of A
+  static constexpr int B_BYTES = (BN / 2) * GEMM_BK * 2;     // 16 KB : this CTA's half of the B tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SLAB = 32 * 128;                      // 4 KB : 32 rows x 128 B staging slab
+  static constexpr int EPI_PER_WARP = 6 * SLAB;              // out x2, aux x2, out2 x2
+  static constexpr int OFF_EPI = G2_STAGES * STAGE_BYTES;
+  static constexpr int OFF_BAR = OFF_EPI + 4 * EPI_PER_WARP;
+  static constexpr int TOTAL = OFF_BAR + 512 + 1024;
+};
+
+// ------------------------------------------------------------------------------------------------ cluster helpers
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion bytes are signalled on an mbarrier that may live in the peer CTA of the pair
+__device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const CUtensorMap* m, uint32_t mbar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :: "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_cg2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// completion of all prior MMAs -> arrive on the barrier at this smem offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3)) : "memory");
+}
+// TMA store / reduce (smem -> global), bulk-group completion
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_wait_group_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+struct Gemm2Maps {
+  CUtensorMap a, b, out, aux, out2;
+};
+
+// Staging slab: 32 rows x 128 B, 128B-swizzled (16-byte chunk c of row r lives at chunk slot c ^ (r & 7)).
+__device__ __forceinline__ uint4* slab_chunk(uint8_t* slab, int row, int chunk) {
+  return reinterpret_cast<uint4*>(slab + row * 128 + ((chunk ^ (row & 7)) << 4));
+}
+
+template <int BN, int A_MN, int B_MN, int EPI, typename OutT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
+  using S = Gemm2Smem<BN>;
+  constexpr bool OUT32 = sizeof(OutT) == 4;
+  constexpr int CW = OUT32 ? 32 : 64;                 // accumulator columns per staging slab (128 B of output per row)
+  constexpr bool HAS_AUX = EPI == EPI_BIAS_RES || EPI == EPI_BIAS_RES32 || EPI == EPI_DGELU || EPI == EPI_ADD;
+  constexpr bool HAS_BIAS = EPI == EPI_BIAS || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_RES || EPI == EPI_BIAS_RES32;
+  static_assert(!(EPI == EPI_BIAS_RES32) || OUT32, "fp32 residual stream implies fp32 output");
+  static_assert(!(EPI == EPI_BIAS_RES || EPI == EPI_DGELU || EPI == EPI_ADD || EPI == EPI_BIAS_GELU) || !OUT32, "fp16-aux epilogues write fp16");
+  static_assert(!(EPI == EPI_ATOMIC) || OUT32, "split-K reduction is fp32");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + G2_STAGES * S::A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
+  uint64_t* empty_bar = full_bar + G2_STAGES;
+  uint64_t* tfull_bar = empty_bar + G2_STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* aux_bar = tempty_bar + 2;                 // [4 warps][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  const int m_tiles = (g.M + G2_BM - 1) / G2_BM;
+  const int n_tiles = (g.N + BN - 1) / BN;
+  const int k_blocks = (g.K + GEMM_BK - 1) / GEMM_BK;
+  const int splits = g.k_splits > 0 ? g.k_splits : 1;
+  const int kb_per_split = (k_blocks + splits - 1) / splits;
+  const int units = m_tiles * n_tiles * splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.a);
+    tma_prefetch_desc(&maps.b);
+    tma_prefetch_desc(&maps.out);
+    if (HAS_AUX) tma_prefetch_desc(&maps.aux);
+    for (int i = 0; i < G2_STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 8);               // 4 epilogue warps x 2 CTAs (only the leader's copy is used)
+    }
+    for (int i = 0; i < 8; ++i) mbar_init(&aux_bar[i], 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_cg2(tmem_slot, 2 * BN);
+    tmem_relinquish_cg2();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode = [&](int u, int& mt, int& nt, int& kb0, int& kb1) {
+    const int sp = u % splits;
+    const int t = u / splits;
+    nt = t % n_tiles;
+    mt = t / n_tiles;
+    kb0 = sp * kb_per_split;
+    kb1 = min(k_blocks, kb0 + kb_per_split);
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int u = pair; u < units; u += n_pairs) {
+        int mt, nt, kb0, kb1;
+        decode(u, mt, nt, kb0, kb1);
+        const int m0 = mt * G2_BM + static_cast<int>(rank) * 128;          // this CTA's A rows
+        const int n0 = nt * BN + static_cast<int>(rank) * (BN / 2);        // this CTA's half of the B tile
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const uint32_t full0 = mapa_u32(smem_u32(&full_bar[stage]), 0);   // the leader's barrier collects both CTAs' bytes
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);
+          uint8_t* a_dst = sA + stage * S::A_BYTES;
+          uint8_t* b_dst = sB + stage * S::B_BYTES;
+          const int k0 = kb * GEMM_BK;
+          if (A_MN) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) tma_load_2d_cg2(a_dst + j * 8192, &maps.a, full0, m0 + 64 * j, k0);
+          } else {
+            tma_load_2d_cg2(a_dst, &maps.a, full0, k0, m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < BN / 128; ++j) tma_load_2d_cg2(b_dst + j * 8192, &maps.b, full0, n0 + 64 * j, k0);
+          } else {
+            tma_load_2d_cg2(b_dst, &maps.b, full0, k0, n0);
+          }
+          if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc_f16(G2_BM, BN, A_MN, B_MN);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int u = pair; u < units; u += n_pairs) {
+        int mt, nt, kb0, kb1;
+        decode(u, mt, nt, kb0, kb1);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_addr = smem_u32(sA + stage * S::A_BYTES);
+            const uint32_t b_addr = smem_u32(sB + stage * S::B_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < GEMM_BK / 16; ++kk) {
+              const uint64_t da = A_MN ? make_smem_desc(a_addr + kk * 2048, 8192, 1024) : make_smem_desc(a_addr + kk * 32, 0, 1024);
+              const uint64_t db = B_MN ? make_smem_desc(b_addr + kk * 2048, 8192, 1024) : make_smem_desc(b_addr + kk * 32, 0, 1024);
+              umma2_ss(d_tmem, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+            }
+            umma2_commit_mc(&empty_bar[stage]);
+            if (kb == kb1 - 1) umma2_commit_mc(&tfull_bar[acc]);
+          }
+          __syncwarp();
+          if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (kb1 <= kb0 && lane == 0) umma2_commit_mc(&tfull_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5, both CTAs)
+    const int q = warp & 3;                               // TMEM lane quadrant
+    const int ew = warp - 2;
+    uint8_t* slabs = smem + S::OFF_EPI + ew * S::EPI_PER_WARP;
+    uint8_t* out_s = slabs;                               // 2 slabs
+    uint8_t* aux_s = slabs + 2 * S::SLAB;                 // 2 slabs
+    uint8_t* out2_s = slabs + 4 * S::SLAB;                // 2 slabs
+    uint64_t* my_aux_bar = aux_bar + ew * 2;
+    const uint32_t tempty0[2] = {mapa_u32(smem_u32(&tempty_bar[0]), 0), mapa_u32(smem_u32(&tempty_bar[1]), 0)};
+    const float alpha = g.alpha ? __ldg(g.alpha) : 1.0f;
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    uint32_t acc = 0, acc_phase = 0;
+    uint32_t aux_uses = 0;                                // slabs fetched so far (buffer = uses & 1, parity = (uses >> 1) & 1)
+    uint32_t out_uses = 0;
+    constexpr int NCH = BN / CW;
+    for (int u = pair; u < units; u += n_pairs) {
+      int mt, nt, kb0, kb1;
+      decode(u, mt, nt, kb0, kb1);
+      const int row0 = mt * G2_BM + static_cast<int>(rank) * 128 + q * 32;     // first output row of this warp
+      const int col0 = nt * BN;
+      const bool has_data = kb1 > kb0;
+      if (HAS_AUX && lane == 0) {                         // aux slab of chunk 0
+        mbar_expect_tx(&my_aux_bar[aux_uses & 1], S::SLAB);
+        tma_load_2d(aux_s + (aux_uses & 1) * S::SLAB, &maps.aux, &my_aux_bar[aux_uses & 1], col0, row0);
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < NCH; ++c) {
+        const int gc0 = col0 + c * CW;
+        if (HAS_AUX && c + 1 < NCH && lane == 0) {        // prefetch the next chunk's aux slab into the other buffer
+          const uint32_t nb = (aux_uses + 1) & 1;
+          mbar_expect_tx(&my_aux_bar[nb], S::SLAB);
+          tma_load_2d(aux_s + nb * S::SLAB, &maps.aux, &my_aux_bar[nb], gc0 + CW, row0);
+        }
+        uint32_t v[CW];
+#pragma unroll
+        for (int i = 0; i < CW / 32; ++i) tmem_ld_x32(tmem_base + lane_addr + acc * BN + c * CW + i * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[i * 32]));
+        tmem_wait_ld();
+        if (c == NCH - 1) {                               // accumulator drained -> hand it back to the leader's MMA warp
+          tc_fence_before();
+          if (lane == 0) mbar_arrive_cluster(tempty0[acc]);
+        }
+        float f[CW];
+#pragma unroll
+        for (int i = 0; i < CW; ++i) f[i] = __uint_as_float(v[i]) * alpha;
+        if (HAS_BIAS) {
+#pragma unroll
+          for (int i = 0; i < CW / 4; ++i) {
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gc0 + 4 * i < g.N) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + gc0 + 4 * i));
+            f[4 * i] += b4.x; f[4 * i + 1] += b4.y; f[4 * i + 2] += b4.z; f[4 * i + 3] += b4.w;
+          }
+        }
+        if (HAS_AUX) {
+          const uint32_t ab = aux_uses & 1;
+          mbar_wait(&my_aux_bar[ab], (aux_uses >> 1) & 1);
+          uint8_t* as = aux_s + ab * S::SLAB;
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            const uint4 raw = *slab_chunk(as, lane, ch);
+            if (EPI == EPI_BIAS_RES32) {                  // 4 fp32 per 16-byte chunk
+              f[4 * ch] += __uint_as_float(raw.x); f[4 * ch + 1] += __uint_as_float(raw.y);
+              f[4 * ch + 2] += __uint_as_float(raw.z); f[4 * ch + 3] += __uint_as_float(raw.w);
+            } else {                                      // 8 fp16 per chunk
+              const __half2* hp = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 x = __half22float2(hp[k]);
+                if (EPI == EPI_DGELU) {
+                  f[8 * ch + 2 * k] *= gelu_erf_grad(x.x);
+                  f[8 * ch + 2 * k + 1] *= gelu_erf_grad(x.y);
+                } else {
+                  f[8 * ch + 2 * k] += x.x;
+                  f[8 * ch + 2 * k + 1] += x.y;
+                }
+              }
+            }
+          }
+          ++aux_uses;
+          __syncwarp();                                   // every lane has consumed the slab before it is refilled
+        }
+        // staging slab of this chunk must no longer be read by the TMA store issued two chunks ago
+        const uint32_t ob = out_uses & 1;
+        if (lane == 0) tma_wait_group_read<1>();
+        __syncwarp();
+        uint8_t* os = out_s + ob * S::SLAB;
+        if (EPI == EPI_BIAS_GELU) {
+          uint8_t* zs = out2_s + ob * S::SLAB;
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            uint32_t zw[4], hw[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float z0 = f[8 * ch + 2 * k], z1 = f[8 * ch + 2 * k + 1];
+              const __half2 hz = __floats2half2_rn(z0, z1), hh = __floats2half2_rn(gelu_erf(z0), gelu_erf(z1));
+              zw[k] = *reinterpret_cast<const uint32_t*>(&hz);
+              hw[k] = *reinterpret_cast<const uint32_t*>(&hh);
+            }
+            *slab_chunk(zs, lane, ch) = make_uint4(zw[0], zw[1], zw[2], zw[3]);
+            *slab_chunk(os, lane, ch) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          }
+        } else if (OUT32) {
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch)
+            *slab_chunk(os, lane, ch) = make_uint4(__float_as_uint(f[4 * ch]), __float_as_uint(f[4 * ch + 1]), __float_as_uint(f[4 * ch + 2]),
+                                                   __float_as_uint(f[4 * ch + 3]));
+        } else {
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            uint32_t w[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const __half2 hv = __floats2half2_rn(f[8 * ch + 2 * k], f[8 * ch + 2 * k + 1]);
+              w[k] = *reinterpret_cast<const uint32_t*>(&hv);
+            }
+            *slab_chunk(os, lane, ch) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (has_data) {
+            if (EPI == EPI_ATOMIC) tma_reduce_add_2d(&maps.out, os, gc0, row0);
+            else tma_store_2d(&maps.out, os, gc0, row0);
+            if (EPI == EPI_BIAS_GELU && g.out2) tma_store_2d(&maps.out2, out2_s + ob * S::SLAB, gc0, row0);
+          }
+          tma_commit_group();
+        }
+        ++out_uses;
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (lane == 0) tma_wait_group_all();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();                                     // the peer may still signal our barriers / read our smem
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_cg2(tmem_base, 2 * BN);
+  }
+}
+
+}  // namespace b200

@@ -240,7 +240,9 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) embed_ln_fwd_kernel(const int6
 }
 
 // Backward of the embedding block: recompute the pre-LN sum and its statistics (cheaper than saving them), LN bwd,
-// then scatter-add dx into the three fp32 gradient tables.
+// then scatter-add dx into the three fp32 gradient tables.  Column-sum-like targets (dgamma, dbeta, the type-0 row
+// that almost every token hits) are accumulated in registers over a grid-stride loop and reduced once per block;
+// word / position rows receive vectorised red.global.add.v4.f32.
 __global__ void __launch_bounds__(ROW_WARPS * 32) embed_ln_bwd_kernel(const __half* __restrict__ dy, const __half* __restrict__ dy2,
                                                                        const int64_t* __restrict__ ids, const int64_t* __restrict__ tt,
                                                                        const int64_t* __restrict__ pos, const float* __restrict__ word,
@@ -249,61 +251,98 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) embed_ln_bwd_kernel(const __ha
                                                                        float* __restrict__ dpos, float* __restrict__ dtype_tab,
                                                                        float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                                        const float* __restrict__ alpha_ptr, int rows, int S, int H, float eps) {
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  extern __shared__ float red[];   // [3][ROW_WARPS][H]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float alpha = alpha_ptr ? *alpha_ptr : 1.0f;
   const int nv = lane_vecs(H, lane);
-  const size_t wi = static_cast<size_t>(ids[row]), pi = static_cast<size_t>(pos ? pos[row] : (row % S)), ti = static_cast<size_t>(tt ? tt[row] : 0);
-  Vec8 v[ROW_MAXV];
+  Vec8 ag[ROW_MAXV], ab[ROW_MAXV], at0[ROW_MAXV], gm[ROW_MAXV];
+#pragma unroll
+  for (int i = 0; i < ROW_MAXV; ++i) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ag[i].v[j] = ab[i].v[j] = at0[i].v[j] = 0.f;
+    if (i < nv) gm[i] = load8(gamma + (i * 32 + lane) * 8);
+  }
+  for (int row = blockIdx.x * ROW_WARPS + warp; row < rows; row += gridDim.x * ROW_WARPS) {
+    const size_t wi = static_cast<size_t>(ids[row]), pi = static_cast<size_t>(pos ? pos[row] : (row % S)), ti = static_cast<size_t>(tt ? tt[row] : 0);
+    Vec8 v[ROW_MAXV];
+#pragma unroll
+    for (int i = 0; i < ROW_MAXV; ++i)
+      if (i < nv) {
+        const int c = (i * 32 + lane) * 8;
+        const Vec8 a = load8(word + wi * H + c), b = load8(pos_tab + pi * H + c), d = load8(type_tab + ti * H + c);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i].v[j] = a.v[j] + d.v[j] + b.v[j];
+      }
+    float mean, rstd;
+    row_stats(v, nv, H, eps, mean, rstd);
+    Vec8 g[ROW_MAXV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < ROW_MAXV; ++i)
+      if (i < nv) {
+        const size_t off = static_cast<size_t>(row) * H + (i * 32 + lane) * 8;
+        Vec8 d = load8(dy + off);
+        if (dy2) {
+          const Vec8 d2 = load8(dy2 + off);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d.v[j] += d2.v[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[i].v[j] = (v[i].v[j] - mean) * rstd;      // xhat
+          g[i].v[j] = d.v[j] * gm[i].v[j];
+          s1 += g[i].v[j];
+          s2 = fmaf(g[i].v[j], v[i].v[j], s2);
+          ag[i].v[j] = fmaf(d.v[j], v[i].v[j], ag[i].v[j]);
+          ab[i].v[j] += d.v[j];
+        }
+      }
+    s1 = warp_sum(s1) / H;
+    s2 = warp_sum(s2) / H;
+#pragma unroll
+    for (int i = 0; i < ROW_MAXV; ++i)
+      if (i < nv) {
+        const int c = (i * 32 + lane) * 8;
+        float dx[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dx[j] = rstd * (g[i].v[j] - s1 - v[i].v[j] * s2) * alpha;
+        red_add_v4(dword + wi * H + c, dx[0], dx[1], dx[2], dx[3]);
+        red_add_v4(dword + wi * H + c + 4, dx[4], dx[5], dx[6], dx[7]);
+        red_add_v4(dpos + pi * H + c, dx[0], dx[1], dx[2], dx[3]);
+        red_add_v4(dpos + pi * H + c + 4, dx[4], dx[5], dx[6], dx[7]);
+        if (ti == 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) at0[i].v[j] += dx[j];
+        } else {
+          red_add_v4(dtype_tab + ti * H + c, dx[0], dx[1], dx[2], dx[3]);
+          red_add_v4(dtype_tab + ti * H + c + 4, dx[4], dx[5], dx[6], dx[7]);
+        }
+      }
+  }
+  float* rg = red;
+  float* rb = red + ROW_WARPS * H;
+  float* rt = red + 2 * ROW_WARPS * H;
 #pragma unroll
   for (int i = 0; i < ROW_MAXV; ++i)
     if (i < nv) {
       const int c = (i * 32 + lane) * 8;
-      const Vec8 a = load8(word + wi * H + c), b = load8(pos_tab + pi * H + c), d = load8(type_tab + ti * H + c);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[i].v[j] = a.v[j] + d.v[j] + b.v[j];
+      store8(rg + warp * H + c, ag[i]);
+      store8(rb + warp * H + c, ab[i]);
+      store8(rt + warp * H + c, at0[i]);
     }
-  float mean, rstd;
-  row_stats(v, nv, H, eps, mean, rstd);
-  Vec8 g[ROW_MAXV], d[ROW_MAXV];
-  float s1 = 0.f, s2 = 0.f;
+  __syncthreads();
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    float a = 0.f, b = 0.f, t = 0.f;
 #pragma unroll
-  for (int i = 0; i < ROW_MAXV; ++i)
-    if (i < nv) {
-      const int c = (i * 32 + lane) * 8;
-      const size_t off = static_cast<size_t>(row) * H + c;
-      d[i] = load8(dy + off);
-      if (dy2) {
-        const Vec8 d2 = load8(dy2 + off);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) d[i].v[j] += d2.v[j];
-      }
-      const Vec8 gm = load8(gamma + c);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        v[i].v[j] = (v[i].v[j] - mean) * rstd;      // xhat
-        g[i].v[j] = d[i].v[j] * gm.v[j];
-        s1 += g[i].v[j];
-        s2 = fmaf(g[i].v[j], v[i].v[j], s2);
-      }
+    for (int w = 0; w < ROW_WARPS; ++w) {
+      a += rg[w * H + c];
+      b += rb[w * H + c];
+      t += rt[w * H + c];
     }
-  s1 = warp_sum(s1) / H;
-  s2 = warp_sum(s2) / H;
-#pragma unroll
-  for (int i = 0; i < ROW_MAXV; ++i)
-    if (i < nv) {
-      const int c = (i * 32 + lane) * 8;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float dxv = rstd * (g[i].v[j] - s1 - v[i].v[j] * s2) * alpha;
-        atomicAdd(dword + wi * H + c + j, dxv);
-        atomicAdd(dpos + pi * H + c + j, dxv);
-        atomicAdd(dtype_tab + ti * H + c + j, dxv);
-        atomicAdd(dgamma + c + j, d[i].v[j] * v[i].v[j] * alpha);
-        atomicAdd(dbeta + c + j, d[i].v[j] * alpha);
-      }
-    }
+    atomicAdd(dgamma + c, a * alpha);
+    atomicAdd(dbeta + c, b * alpha);
+    atomicAdd(dtype_tab + c, t);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ K11: token-cls head

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200enc.so")
 CSRC = os.path.join(_HERE, "csrc")
 
-EPI_STORE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_DGELU, EPI_ADD, EPI_ATOMIC = range(7)
+EPI_STORE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_DGELU, EPI_ADD, EPI_ATOMIC, EPI_BIAS_RES32 = range(8)
 DT_F16, DT_F32 = 0, 1
 
 _p, _i, _f, _sz, _ll = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_longlong
@@ -42,7 +42,7 @@ _PROTOS = {
     "b200_clip_coef": [_p, _f, _f, _p, _p],
     "b200_adamw_step": [_p, _p, _p, _p, _p, _sz, _f, _f, _f, _f, _f, _f, _f, _p, _p],
 }
-_RESTYPE = {"b200_last_error": C.c_char_p, "b200_launch_count": _ll, "b200_version": _i, "b200_attn_bwd_workspace": _sz}
+_RESTYPE = {"b200_set_gemm_impl": None, "b200_last_error": C.c_char_p, "b200_launch_count": _ll, "b200_version": _i, "b200_attn_bwd_workspace": _sz}
 
 _lock = threading.Lock()
 _lib = None
@@ -75,6 +75,7 @@ def load() -> C.CDLL:
                 fn.restype = _RESTYPE.get(name, _i)
             for name, rt in _RESTYPE.items():
                 getattr(lib, name).restype = rt
+            lib.b200_set_gemm_impl.argtypes = [_i]
             _lib = lib
     return _lib
 

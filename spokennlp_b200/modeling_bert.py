@@ -109,18 +109,14 @@ class _EncoderFn(torch.autograd.Function):
     def forward(ctx, model, ids, tt, pos, inputs_embeds, key_bias, kv_len, B, S, want_hidden, want_probs, *params):
         eng: EncoderEngine = model._engine
         need_grad = any(ctx.needs_input_grad[11:])
-        x16, saved, hiddens, probs = eng.forward(ids, tt, pos, inputs_embeds, key_bias, kv_len, B, S, save=need_grad,
+        x16, x32, saved, hiddens, probs = eng.forward(ids, tt, pos, inputs_embeds, key_bias, kv_len, B, S, save=need_grad,
                                                  want_hidden=want_hidden, want_probs=want_probs)
         ctx.model, ctx.saved, ctx.n_params = model, saved, len(params)
         H = eng.H
 
-        def to32(t):
-            out = torch.empty(B, S, H, dtype=torch.float32, device=t.device)
-            return ops.cast_f16_to_f32(t, out)
-
-        outs = [to32(x16)]
+        outs = [x32.view(B, S, H)]             # the fp32 copy the last LayerNorm wrote (no extra cast pass)
         if want_hidden:
-            outs += [to32(h) for h in hiddens]
+            outs += [h.view(B, S, H) for h in hiddens]
         if want_probs:
             outs += probs
         ctx.mark_non_differentiable(*outs[1:])

@@ -9,8 +9,8 @@ from typing import Optional
 import torch
 
 from . import lib as L
-from .lib import (DT_F16, DT_F32, EPI_ADD, EPI_ATOMIC, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_DGELU,  # noqa: F401
-                  EPI_STORE)
+from .lib import (DT_F16, DT_F32, EPI_ADD, EPI_ATOMIC, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_BIAS_RES32,  # noqa: F401
+                  EPI_DGELU, EPI_STORE)
 
 Tensor = torch.Tensor
 
@@ -55,6 +55,11 @@ def gemm(a: Tensor, b: Tensor, out: Tensor, *, a_layout: int = 0, b_layout: int 
                                 _stream())
     L.check(rc, "b200_gemm_f16")
     return out
+
+
+def set_gemm_impl(impl: int) -> None:
+    """2 (default): 2-CTA cta_group::2 GEMM with TMA epilogue; 1: single-CTA kernel (A/B measurements, tests)."""
+    L.load().b200_set_gemm_impl(int(impl))
 
 
 def wgrad_splits(M_out: int, N_in: int, K_tokens: int, sms: int = 148) -> int:

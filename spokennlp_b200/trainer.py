@@ -94,7 +94,7 @@ class DataParallelTrainer:
         pos = None  # arange(S) per row
         ids = input_ids.contiguous().view(-1)
         tt = token_type_ids.contiguous().view(-1) if token_type_ids is not None else None
-        x16, saved, _, _ = eng.forward(ids, tt, pos, None, key_bias, kv_len, B, S, save=True)
+        x16, _, saved, _, _ = eng.forward(ids, tt, pos, None, key_bias, kv_len, B, S, save=True)
         W32 = flat.view32("loss_calculator.classifier.weight")
         b32 = flat.view32("loss_calculator.classifier.bias")
         logits = ops.cls_head_fwd(x16, W32, b32)

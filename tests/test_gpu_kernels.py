@@ -39,6 +39,17 @@ def _err_report(got, ref, name, block=64):
     return rel, "\n".join(msg)
 
 
+@pytest.fixture(params=[2, 1], ids=["gemm2cta", "gemm1cta"])
+def gemm_impl(request):
+    """Run GEMM tests through both kernels: the 2-CTA production path and the single-CTA one."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from spokennlp_b200 import ops
+    ops.set_gemm_impl(request.param)
+    yield request.param
+    ops.set_gemm_impl(2)
+
+
 def _rand16(*shape, scale=1.0, seed=0):
     g = torch.Generator(device="cuda").manual_seed(seed)
     return (torch.randn(*shape, generator=g, device="cuda") * scale).half()
@@ -47,7 +58,7 @@ def _rand16(*shape, scale=1.0, seed=0):
 # ----------------------------------------------------------------------------------------------- GEMM
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 256, 128), (384, 768, 768), (300, 768, 1536), (2048, 2304, 768),
                                    (16384, 768, 3072)])
-def test_gemm_kmajor_store_f32(M, N, K):
+def test_gemm_kmajor_store_f32(M, N, K, gemm_impl):
     ops = _cuda()
     a, b = _rand16(M, K, seed=1), _rand16(N, K, seed=2)
     out = torch.empty(M, N, dtype=torch.float32, device="cuda")
@@ -58,7 +69,7 @@ def test_gemm_kmajor_store_f32(M, N, K):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 768, 2304), (16384, 768, 2304), (16384, 3072, 768)])
-def test_gemm_dgrad_b_mn_major(M, N, K):
+def test_gemm_dgrad_b_mn_major(M, N, K, gemm_impl):
     """dX[M,N] = dY[M,K] @ W[K,N] with W stored [K,N] row-major (b_layout=1): no transposed weight copy."""
     ops = _cuda()
     dy, w = _rand16(M, K, seed=3), _rand16(K, N, seed=4, scale=0.05)
@@ -70,7 +81,7 @@ def test_gemm_dgrad_b_mn_major(M, N, K):
 
 
 @pytest.mark.parametrize("Mo,Ni,T", [(128, 256, 64), (768, 768, 1024), (2304, 768, 16384), (768, 3072, 16384)])
-def test_gemm_wgrad_both_mn_major_atomic(Mo, Ni, T):
+def test_gemm_wgrad_both_mn_major_atomic(Mo, Ni, T, gemm_impl):
     """dW[Mo,Ni] += alpha * dY[T,Mo]^T @ X[T,Ni]: both operands MN-major, split-K fp32 reduction."""
     ops = _cuda()
     dy, x = _rand16(T, Mo, seed=5), _rand16(T, Ni, seed=6)
@@ -83,7 +94,7 @@ def test_gemm_wgrad_both_mn_major_atomic(Mo, Ni, T):
     assert rel < 2e-5, msg
 
 
-def test_gemm_epilogues():
+def test_gemm_epilogues(gemm_impl):
     ops = _cuda()
     M, N, K = 1024, 768, 768
     a, w = _rand16(M, K, seed=7), _rand16(N, K, seed=8, scale=0.05)
@@ -104,8 +115,9 @@ def test_gemm_epilogues():
     assert rel < 5e-4, msg
 
     o32 = torch.empty(M, N, dtype=torch.float32, device="cuda")
-    ops.gemm(a, w, o32, epilogue=ops.EPI_BIAS_RES, bias=bias, aux=res)
-    rel, msg = _err_report(o32, acc + bias + res.float(), "EPI_BIAS_RES f32")
+    res32 = torch.randn(M, N, device="cuda")
+    ops.gemm(a, w, o32, epilogue=ops.EPI_BIAS_RES32, bias=bias, aux=res32)
+    rel, msg = _err_report(o32, acc + bias + res32, "EPI_BIAS_RES32")
     assert rel < 1e-5, msg
     ops.gemm(a, w, out, epilogue=ops.EPI_BIAS_RES, bias=bias, aux=res)
     rel, msg = _err_report(out, acc + bias + res.float(), "EPI_BIAS_RES f16")

@@ -106,7 +106,7 @@ def test_bert_base_forward_matches_reference_golden_and_argmax():
     eng = m.b200_engine()
     ids = g["input_ids"].cuda()
     kb, kl = ops.mask_to_bias(g["attention_mask"].cuda())
-    x16, _, _, _ = eng.forward(ids.view(-1), None, None, None, kb, kl, 2, 128, save=False)
+    x16, _, _, _, _ = eng.forward(ids.view(-1), None, None, None, kb, kl, 2, 128, save=False)
     logits, am = ops.cls_head_fwd(x16, g["cls_w"].cuda(), g["cls_b"].cuda(), want_argmax=True)
     ref_logits = g["logits"].view(-1, 2)
     err = float((logits.cpu() - ref_logits).abs().max())
