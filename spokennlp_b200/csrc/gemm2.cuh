@@ -98,8 +98,8 @@ struct Gemm2Maps {
 };
 
 // Staging slab: 32 rows x 128 B, 128B-swizzled (16-byte chunk c of row r lives at chunk slot c ^ (r & 7)).
-__device__ __forceinline__ uint4* slab_chunk(uint8_t* slab, int row, int chunk) {
-  return reinterpret_cast<uint4*>(slab + row * 128 + ((chunk ^ (row & 7)) << 4));
+__device__ __forceinline__ uint32_t slab_chunk(uint32_t slab_saddr, int row, int chunk) {
+  return slab_saddr + row * 128 + ((chunk ^ (row & 7)) << 4);
 }
 
 template <int BN, int A_MN, int B_MN, int EPI, typename OutT>
@@ -296,10 +296,10 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
         if (HAS_AUX) {
           const uint32_t ab = aux_uses & 1;
           mbar_wait(&my_aux_bar[ab], (aux_uses >> 1) & 1);
-          uint8_t* as = aux_s + ab * S::SLAB;
+          const uint32_t as = smem_u32(aux_s + ab * S::SLAB);
 #pragma unroll
           for (int ch = 0; ch < 8; ++ch) {
-            const uint4 raw = *slab_chunk(as, lane, ch);
+            const uint4 raw = lds128(slab_chunk(as, lane, ch));
             if (EPI == EPI_BIAS_RES32) {                  // 4 fp32 per 16-byte chunk
               f[4 * ch] += __uint_as_float(raw.x); f[4 * ch + 1] += __uint_as_float(raw.y);
               f[4 * ch + 2] += __uint_as_float(raw.z); f[4 * ch + 3] += __uint_as_float(raw.w);
@@ -325,9 +325,10 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
         const uint32_t ob = out_uses & 1;
         if (lane == 0) tma_wait_group_read<1>();
         __syncwarp();
-        uint8_t* os = out_s + ob * S::SLAB;
+        uint8_t* os_ptr = out_s + ob * S::SLAB;
+        const uint32_t os = smem_u32(os_ptr);
         if (EPI == EPI_BIAS_GELU) {
-          uint8_t* zs = out2_s + ob * S::SLAB;
+          const uint32_t zs = smem_u32(out2_s + ob * S::SLAB);
 #pragma unroll
           for (int ch = 0; ch < 8; ++ch) {
             uint32_t zw[4], hw[4];
@@ -338,14 +339,14 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
               zw[k] = *reinterpret_cast<const uint32_t*>(&hz);
               hw[k] = *reinterpret_cast<const uint32_t*>(&hh);
             }
-            *slab_chunk(zs, lane, ch) = make_uint4(zw[0], zw[1], zw[2], zw[3]);
-            *slab_chunk(os, lane, ch) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            sts128(slab_chunk(zs, lane, ch), zw[0], zw[1], zw[2], zw[3]);
+            sts128(slab_chunk(os, lane, ch), hw[0], hw[1], hw[2], hw[3]);
           }
         } else if (OUT32) {
 #pragma unroll
           for (int ch = 0; ch < 8; ++ch)
-            *slab_chunk(os, lane, ch) = make_uint4(__float_as_uint(f[4 * ch]), __float_as_uint(f[4 * ch + 1]), __float_as_uint(f[4 * ch + 2]),
-                                                   __float_as_uint(f[4 * ch + 3]));
+            sts128(slab_chunk(os, lane, ch), __float_as_uint(f[4 * ch]), __float_as_uint(f[4 * ch + 1]), __float_as_uint(f[4 * ch + 2]),
+                   __float_as_uint(f[4 * ch + 3]));
         } else {
 #pragma unroll
           for (int ch = 0; ch < 8; ++ch) {
@@ -355,15 +356,15 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
               const __half2 hv = __floats2half2_rn(f[8 * ch + 2 * k], f[8 * ch + 2 * k + 1]);
               w[k] = *reinterpret_cast<const uint32_t*>(&hv);
             }
-            *slab_chunk(os, lane, ch) = make_uint4(w[0], w[1], w[2], w[3]);
+            sts128(slab_chunk(os, lane, ch), w[0], w[1], w[2], w[3]);
           }
         }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
           if (has_data) {
-            if (EPI == EPI_ATOMIC) tma_reduce_add_2d(&maps.out, os, gc0, row0);
-            else tma_store_2d(&maps.out, os, gc0, row0);
+            if (EPI == EPI_ATOMIC) tma_reduce_add_2d(&maps.out, os_ptr, gc0, row0);
+            else tma_store_2d(&maps.out, os_ptr, gc0, row0);
             if (EPI == EPI_BIAS_GELU && g.out2) tma_store_2d(&maps.out2, out2_s + ob * S::SLAB, gc0, row0);
           }
           tma_commit_group();
