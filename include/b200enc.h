@@ -59,6 +59,8 @@ long long b200_launch_count(void);
  */
 /* 2 (default): 2-CTA cta_group::2 kernel with TMA epilogue; 1: single-CTA kernel (kept for A/B measurements) */
 void b200_set_gemm_impl(int impl);
+/* measurement knobs for the 2-CTA GEMM (results become WRONG when non-zero): 1 skip A loads, 2 skip B loads, 4 skip MMA, 8 skip stores */
+void b200_set_gemm_debug(int bits);
 int b200_gemm_f16(const void* A, int lda, int a_layout, const void* B, int ldb, int b_layout, int M, int N, int K,
                   int epilogue, const float* bias, const void* aux, int ld_aux, void* out, int ld_out, int out_dtype,
                   void* out2, int ld_out2, const float* alpha, int k_splits, void* stream);

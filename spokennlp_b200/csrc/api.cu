@@ -140,17 +140,18 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g,
 }
 
 std::atomic<int> g_gemm_impl{2};
+std::atomic<int> g_gemm_dbg{0};
 
 template <int BN, int A_MN, int B_MN, int EPI, typename OutT>
 int launch_gemm2(const Gemm2Maps& maps, const GemmArgs& g, cudaStream_t s) {
   auto kern = gemm2_f16_kernel<BN, A_MN, B_MN, EPI, OutT>;
-  static int configured = set_smem(kern, Gemm2Smem<BN>::TOTAL);
+  static int configured = set_smem(kern, Gemm2Smem<BN, EPI>::TOTAL);
   if (configured != B200_OK) return configured;
   const int m_tiles = (g.M + G2_BM - 1) / G2_BM, n_tiles = (g.N + BN - 1) / BN;
   const int units = m_tiles * n_tiles * (g.k_splits > 0 ? g.k_splits : 1);
   const int pairs = sm_count() / 2;
   const int grid = 2 * (units < pairs ? units : pairs);
-  kern<<<grid, G2_THREADS, Gemm2Smem<BN>::TOTAL, s>>>(maps, g);
+  kern<<<grid, G2_THREADS, Gemm2Smem<BN, EPI>::TOTAL, s>>>(maps, g);
   return check_launch("gemm2_f16_kernel");
 }
 
@@ -159,6 +160,7 @@ int launch_gemm2(const Gemm2Maps& maps, const GemmArgs& g, cudaStream_t s) {
 extern "C" {
 
 void b200_set_gemm_impl(int impl) { g_gemm_impl.store(impl == 1 ? 1 : 2); }
+void b200_set_gemm_debug(int bits) { g_gemm_dbg.store(bits); }
 
 const char* b200_last_error(void) { return g_err.c_str(); }
 int b200_version(void) { return 100; }
@@ -193,7 +195,7 @@ int b200_gemm_f16(const void* A, int lda, int a_layout, const void* B, int ldb, 
     if (needs_aux && (rc = get_tmap(aux, M, N, ld_aux, 32, &mp.aux, epilogue == EPI_BIAS_RES32))) return rc;
     if (epilogue == EPI_BIAS_GELU && out2 && (rc = get_tmap(out2, M, N, ld_out2, 32, &mp.out2))) return rc;
     GemmArgs g2{M, N, K, k_splits > 0 ? k_splits : 1, bias, static_cast<const __half*>(aux), ld_aux, out, ld_out,
-                static_cast<__half*>(out2), ld_out2, alpha};
+                static_cast<__half*>(out2), ld_out2, alpha, g_gemm_dbg.load()};
     switch (a_layout * 1000 + b_layout * 100 + epilogue * 10 + out_dtype) {
       case 0 * 1000 + 0 * 100 + EPI_STORE * 10 + B200_DT_F16: return launch_gemm2<BN, 0, 0, EPI_STORE, __half>(mp, g2, s);
       case 0 * 1000 + 0 * 100 + EPI_STORE * 10 + B200_DT_F32: return launch_gemm2<BN, 0, 0, EPI_STORE, float>(mp, g2, s);
@@ -217,7 +219,7 @@ int b200_gemm_f16(const void* A, int lda, int a_layout, const void* B, int ldb, 
   rc = b_layout == 0 ? get_tmap(B, N, K, ldb, BN, &tb) : get_tmap(B, K, N, ldb, GEMM_BK, &tb);
   if (rc) return rc;
   GemmArgs g{M, N, K, k_splits > 0 ? k_splits : 1, bias, static_cast<const __half*>(aux), ld_aux, out, ld_out,
-             static_cast<__half*>(out2), ld_out2, alpha};
+             static_cast<__half*>(out2), ld_out2, alpha, 0};
   const int key = a_layout * 1000 + b_layout * 100 + epilogue * 10 + out_dtype;
   switch (key) {
     case 0 * 1000 + 0 * 100 + EPI_STORE * 10 + B200_DT_F16: return launch_gemm<BN, 0, 0, EPI_STORE, __half>(ta, tb, g, s);

@@ -176,9 +176,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int r = qd * 32 + lane;                 // key row inside the block == TMEM lane
     const int t = threadIdx.x - 64;               // 0..127
     const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
-    float* stat = reinterpret_cast<float*>(smem + S::OFF_STAT);
-    uint8_t* p_row = smem + S::OFF_P + r * 128;
-    uint8_t* ds_row = smem + S::OFF_DS + r * 128;
+    const uint32_t stat = smem_u32(smem + S::OFF_STAT);
+    const uint32_t p_row = smem_u32(smem + S::OFF_P) + r * 128;
+    const uint32_t ds_row = smem_u32(smem + S::OFF_DS) + r * 128;
     const int key = k0 + r;
     float bias = -INFINITY;
     if (key < kv_len) bias = a.key_bias ? a.key_bias[static_cast<size_t>(b) * a.Sk + key] * 1.4426950408889634f : 0.f;
@@ -204,13 +204,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int i = 0; i < nq; ++i) {
       {  // per-query statistics of block i; queries past Sq get lse = +inf (P = 0) and delta = 0
         const int q = i * ATT_BQ + t;
-        float* sb = stat + (i & 1) * 256;
-        sb[t] = q < a.Sq ? a.lse2[stat_base + q] : INFINITY;
-        sb[128 + t] = q < a.Sq ? a.delta[stat_base + q] : 0.f;
+        const uint32_t sb = stat + (i & 1) * 1024;
+        sts_f32(sb + t * 4, q < a.Sq ? a.lse2[stat_base + q] : INFINITY);
+        sts_f32(sb + 512 + t * 4, q < a.Sq ? a.delta[stat_base + q] : 0.f);
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
-      const float* lse_s = stat + (i & 1) * 256;
-      const float* del_s = lse_s + 128;
+      const uint32_t lse_s = stat + (i & 1) * 1024;
+      const uint32_t del_s = lse_s + 512;
       mbar_wait(s_full, i & 1);
       tc_fence_after();
       if (i > 0) drain_dq(i - 1);
@@ -224,10 +224,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
           const int q0i = c * 32 + 2 * e;
-          const float p0 = fast_exp2(fmaf(__uint_as_float(sv[2 * e]), a.scale_log2, bias) - lse_s[q0i]);
-          const float p1 = fast_exp2(fmaf(__uint_as_float(sv[2 * e + 1]), a.scale_log2, bias) - lse_s[q0i + 1]);
-          const float d0 = p0 * (__uint_as_float(dp[2 * e]) - del_s[q0i]) * a.inv_sqrt_d;
-          const float d1 = p1 * (__uint_as_float(dp[2 * e + 1]) - del_s[q0i + 1]) * a.inv_sqrt_d;
+          const float p0 = fast_exp2(fmaf(__uint_as_float(sv[2 * e]), a.scale_log2, bias) - lds_f32(lse_s + q0i * 4));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(sv[2 * e + 1]), a.scale_log2, bias) - lds_f32(lse_s + q0i * 4 + 4));
+          const float d0 = p0 * (__uint_as_float(dp[2 * e]) - lds_f32(del_s + q0i * 4)) * a.inv_sqrt_d;
+          const float d1 = p1 * (__uint_as_float(dp[2 * e + 1]) - lds_f32(del_s + q0i * 4 + 4)) * a.inv_sqrt_d;
           const __half2 hp = __floats2half2_rn(p0, p1), hd = __floats2half2_rn(d0, d1);
           pk[e] = *reinterpret_cast<const uint32_t*>(&hp);
           dk[e] = *reinterpret_cast<const uint32_t*>(&hd);
@@ -236,8 +236,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int e = 0; e < 4; ++e) {
           const int ch = 4 * c + e;
           const int off = (ch >> 3) * 16384 + (((ch & 7) ^ (r & 7)) << 4);
-          *reinterpret_cast<uint4*>(p_row + off) = make_uint4(pk[4 * e], pk[4 * e + 1], pk[4 * e + 2], pk[4 * e + 3]);
-          *reinterpret_cast<uint4*>(ds_row + off) = make_uint4(dk[4 * e], dk[4 * e + 1], dk[4 * e + 2], dk[4 * e + 3]);
+          sts128(p_row + off, pk[4 * e], pk[4 * e + 1], pk[4 * e + 2], pk[4 * e + 3]);
+          sts128(ds_row + off, dk[4 * e], dk[4 * e + 1], dk[4 * e + 2], dk[4 * e + 3]);
         }
       }
       fence_proxy_async_smem();

@@ -160,42 +160,55 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int r = qd * 32 + lane;               // row inside the query tile
       const int t = threadIdx.x - 64 - x * 128;   // 0..127 inside the group (bias staging)
       const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
-      float* bias_s = reinterpret_cast<float*>(smem + S::OFF_BIAS) + x * 2 * ATT_BK;
-      uint8_t* p_row = smem + S::OFF_P + x * S::P_BYTES + r * 128;
+      const uint32_t bias_s = smem_u32(smem + S::OFF_BIAS) + x * 2 * ATT_BK * 4;
+      const uint32_t p_row = smem_u32(smem + S::OFF_P + x * S::P_BYTES) + r * 128;
       const float NEG_INF = -INFINITY;
+      const float sc = a.scale_log2;
       float m = NEG_INF, l = 0.f;
       for (int j = 0; j < n_blocks; ++j) {
-        {  // stage this block's key bias (log2 domain); keys past kv_len / Sk are removed
+        // Only blocks that contain a biased / removed key pay for the per-key bias (CTA-uniform decision).
+        const bool biased = (a.key_bias != nullptr) || ((j + 1) * ATT_BK > kv_len);
+        const uint32_t bj = bias_s + (j & 1) * ATT_BK * 4;
+        if (biased) {
           const int key = j * ATT_BK + t;
           float bv = NEG_INF;
           if (key < kv_len) bv = a.key_bias ? a.key_bias[static_cast<size_t>(b) * a.Sk + key] * 1.4426950408889634f : 0.f;
-          bias_s[(j & 1) * ATT_BK + t] = bv;
+          sts_f32(bj + t * 4, bv);
           asm volatile("bar.sync %0, 128;" ::"r"(1 + x) : "memory");
         }
-        const float* bj = bias_s + (j & 1) * ATT_BK;
         mbar_wait(&s_full[x], j & 1);
         tc_fence_after();
-        uint32_t v[4][32];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld_x32(tmem + lane_addr + x * 128 + c * 32, v[c]);
-        tmem_wait_ld();
+        // ---- pass 1: row maximum (scores are re-read from TMEM in pass 2: keeps the register footprint small)
         float mx = NEG_INF;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld_x32(tmem + lane_addr + x * 128 + c * 32, v);
+          tmem_wait_ld();
+          if (biased) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaf(__uint_as_float(v[i]), sc, lds_f32(bj + (c * 32 + i) * 4)));
+          } else {
+            float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float tv = fmaf(__uint_as_float(v[c][i]), a.scale_log2, bj[c * 32 + i]);
-            v[c][i] = __float_as_uint(tv);
-            mx = fmaxf(mx, tv);
+            for (int i = 2; i < 32; i += 2) {
+              m0 = fmaxf(m0, __uint_as_float(v[i]));
+              m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
+            }
+            mx = fmaxf(mx, fmaxf(m0, m1) * sc);
           }
+        }
+        // ---- lazy rescale: keep the running reference max unless some row of this warp grew by more than 2^8
         const float m_new = fmaxf(m, mx);
-        const float m_use = (m_new == NEG_INF) ? 0.f : m_new;
-        const float alpha = fast_exp2(m - m_use);     // m == -inf -> 0
-        float rs = 0.f;
+        const bool grow = (m_new - m) > 8.0f || m == NEG_INF;
+        const bool rescale = __any_sync(0xffffffffu, grow);
+        float m_use = rescale ? m_new : m;
+        if (m_use == NEG_INF) m_use = 0.f;
+        const float alpha = rescale ? fast_exp2(m - m_use) : 1.0f;     // m == -inf -> 0
         if (j > 0) {                              // P.V of block j-1 finished: P smem is free, O may be rescaled
           mbar_wait(&o_full[x], (j - 1) & 1);
           tc_fence_after();
-          if (!__all_sync(0xffffffffu, alpha == 1.0f)) {
+          if (rescale) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               uint32_t o[16];
@@ -208,14 +221,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             tmem_wait_st();
           }
         }
-#pragma unroll
+        // ---- pass 2: p = exp2(s * scale - m_use) (+ bias), row sum, fp16 P into the swizzled smem tile
+        const float neg_m = -m_use;
+        float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll 1
         for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld_x32(tmem + lane_addr + x * 128 + c * 32, v);
+          tmem_wait_ld();
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float p0 = fast_exp2(__uint_as_float(v[c][2 * i]) - m_use);
-            const float p1 = fast_exp2(__uint_as_float(v[c][2 * i + 1]) - m_use);
-            rs += p0 + p1;
+            float t0, t1;
+            if (biased) {
+              t0 = fmaf(__uint_as_float(v[2 * i]), sc, lds_f32(bj + (c * 32 + 2 * i) * 4)) + neg_m;
+              t1 = fmaf(__uint_as_float(v[2 * i + 1]), sc, lds_f32(bj + (c * 32 + 2 * i + 1) * 4)) + neg_m;
+            } else {
+              t0 = fmaf(__uint_as_float(v[2 * i]), sc, neg_m);
+              t1 = fmaf(__uint_as_float(v[2 * i + 1]), sc, neg_m);
+            }
+            const float p0 = fast_exp2(t0), p1 = fast_exp2(t1);
+            rs0 += p0;
+            rs1 += p1;
             const __half2 hp = __floats2half2_rn(p0, p1);
             pk[i] = *reinterpret_cast<const uint32_t*>(&hp);
           }
@@ -223,12 +250,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int ch = 4 * c + i;
-            uint8_t* dst = p_row + (ch >> 3) * 16384 + (((ch & 7) ^ (r & 7)) << 4);
-            *reinterpret_cast<uint4*>(dst) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+            sts128(p_row + (ch >> 3) * 16384 + (((ch & 7) ^ (r & 7)) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
           }
         }
-        l = fmaf(l, alpha, rs);
-        m = m_new;
+        l = fmaf(l, alpha, rs0 + rs1);
+        m = (m_use == 0.f && m_new == NEG_INF) ? NEG_INF : m_use;
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(&p_full[x]);

@@ -46,6 +46,8 @@ struct GemmArgs {
   __half* out2;
   int ld_out2;
   const float* alpha;   // optional device scalar
+  int dbg;              // measurement knobs (gemm2 only): 1 skip A loads, 2 skip B loads, 4 skip MMA issue, 8 skip epilogue stores,
+                        // bits 8..15: L2 prefetch distance in K blocks
 };
 
 template <int BN>

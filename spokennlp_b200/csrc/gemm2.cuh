@@ -17,19 +17,25 @@
 namespace b200 {
 
 constexpr int G2_THREADS = 192;           // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
-constexpr int G2_STAGES = 4;
 constexpr int G2_BM = 256;                // rows per CTA pair
+constexpr int G2_SMEM_MAX = 232448;       // 227 KB opt-in limit per CTA
 
-template <int BN>
+// Shared-memory plan: the operand ring takes whatever the epilogue staging of this variant leaves free
+// (6 stages for plain epilogues, 5 when a residual / pre-activation slab pair is needed).
+template <int BN, int EPI>
 struct Gemm2Smem {
   static constexpr int A_BYTES = 128 * GEMM_BK * 2;          // 16 KB : this CTA's 128 rows of A
   static constexpr int B_BYTES = (BN / 2) * GEMM_BK * 2;     // 16 KB : this CTA's half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int SLAB = 32 * 128;                      // 4 KB : 32 rows x 128 B staging slab
-  static constexpr int EPI_PER_WARP = 6 * SLAB;              // out x2, aux x2, out2 x2
-  static constexpr int OFF_EPI = G2_STAGES * STAGE_BYTES;
+  static constexpr bool AUX = EPI == EPI_BIAS_RES || EPI == EPI_BIAS_RES32 || EPI == EPI_DGELU || EPI == EPI_ADD;
+  static constexpr int SLABS = 2 + (AUX ? 2 : 0) + (EPI == EPI_BIAS_GELU ? 2 : 0);   // out x2 [, aux x2] [, out2 x2]
+  static constexpr int EPI_PER_WARP = SLABS * SLAB;
+  static constexpr int STAGES = (G2_SMEM_MAX - 1024 - 512 - 4 * EPI_PER_WARP) / STAGE_BYTES;
+  static constexpr int OFF_EPI = STAGES * STAGE_BYTES;
   static constexpr int OFF_BAR = OFF_EPI + 4 * EPI_PER_WARP;
   static constexpr int TOTAL = OFF_BAR + 512 + 1024;
+  static_assert(STAGES >= 4 && TOTAL <= G2_SMEM_MAX, "shared-memory plan");
 };
 
 // ------------------------------------------------------------------------------------------------ cluster helpers
@@ -105,7 +111,8 @@ __device__ __forceinline__ uint32_t slab_chunk(uint32_t slab_saddr, int row, int
 template <int BN, int A_MN, int B_MN, int EPI, typename OutT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
-  using S = Gemm2Smem<BN>;
+  using S = Gemm2Smem<BN, EPI>;
+  constexpr int G2_STAGES = S::STAGES;
   constexpr bool OUT32 = sizeof(OutT) == 4;
   constexpr int CW = OUT32 ? 32 : 64;                 // accumulator columns per staging slab (128 B of output per row)
   constexpr bool HAS_AUX = EPI == EPI_BIAS_RES || EPI == EPI_BIAS_RES32 || EPI == EPI_DGELU || EPI == EPI_ADD;
@@ -183,21 +190,27 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           const uint32_t full0 = mapa_u32(smem_u32(&full_bar[stage]), 0);   // the leader's barrier collects both CTAs' bytes
-          if (leader) mbar_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);
+          const bool ld_a = !(g.dbg & 1) || kb == kb0, ld_b = !(g.dbg & 2) || kb == kb0;
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * ((ld_a ? S::A_BYTES : 0) + (ld_b ? S::B_BYTES : 0)));
+          if (!ld_a && !ld_b && !leader) { /* nothing to fetch */ }
           uint8_t* a_dst = sA + stage * S::A_BYTES;
           uint8_t* b_dst = sB + stage * S::B_BYTES;
           const int k0 = kb * GEMM_BK;
-          if (A_MN) {
+          if (ld_a) {
+            if (A_MN) {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) tma_load_2d_cg2(a_dst + j * 8192, &maps.a, full0, m0 + 64 * j, k0);
-          } else {
-            tma_load_2d_cg2(a_dst, &maps.a, full0, k0, m0);
+              for (int j = 0; j < 2; ++j) tma_load_2d_cg2(a_dst + j * 8192, &maps.a, full0, m0 + 64 * j, k0);
+            } else {
+              tma_load_2d_cg2(a_dst, &maps.a, full0, k0, m0);
+            }
           }
-          if (B_MN) {
+          if (ld_b) {
+            if (B_MN) {
 #pragma unroll
-            for (int j = 0; j < BN / 128; ++j) tma_load_2d_cg2(b_dst + j * 8192, &maps.b, full0, n0 + 64 * j, k0);
-          } else {
-            tma_load_2d_cg2(b_dst, &maps.b, full0, k0, n0);
+              for (int j = 0; j < BN / 128; ++j) tma_load_2d_cg2(b_dst + j * 8192, &maps.b, full0, n0 + 64 * j, k0);
+            } else {
+              tma_load_2d_cg2(b_dst, &maps.b, full0, k0, n0);
+            }
           }
           if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
         }
@@ -225,7 +238,7 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
             for (int kk = 0; kk < GEMM_BK / 16; ++kk) {
               const uint64_t da = A_MN ? make_smem_desc(a_addr + kk * 2048, 8192, 1024) : make_smem_desc(a_addr + kk * 32, 0, 1024);
               const uint64_t db = B_MN ? make_smem_desc(b_addr + kk * 2048, 8192, 1024) : make_smem_desc(b_addr + kk * 32, 0, 1024);
-              umma2_ss(d_tmem, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+              if (!(g.dbg & 4)) umma2_ss(d_tmem, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
             }
             umma2_commit_mc(&empty_bar[stage]);
             if (kb == kb1 - 1) umma2_commit_mc(&tfull_bar[acc]);
@@ -244,8 +257,8 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
     const int ew = warp - 2;
     uint8_t* slabs = smem + S::OFF_EPI + ew * S::EPI_PER_WARP;
     uint8_t* out_s = slabs;                               // 2 slabs
-    uint8_t* aux_s = slabs + 2 * S::SLAB;                 // 2 slabs
-    uint8_t* out2_s = slabs + 4 * S::SLAB;                // 2 slabs
+    uint8_t* aux_s = slabs + 2 * S::SLAB;                 // 2 slabs (variants with an auxiliary input)
+    uint8_t* out2_s = slabs + 2 * S::SLAB;                // 2 slabs (GELU variant: pre-activation output)
     uint64_t* my_aux_bar = aux_bar + ew * 2;
     const uint32_t tempty0[2] = {mapa_u32(smem_u32(&tempty_bar[0]), 0), mapa_u32(smem_u32(&tempty_bar[1]), 0)};
     const float alpha = g.alpha ? __ldg(g.alpha) : 1.0f;
@@ -362,7 +375,7 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          if (has_data) {
+          if (has_data && !(g.dbg & 8)) {
             if (EPI == EPI_ATOMIC) tma_reduce_add_2d(&maps.out, os_ptr, gc0, row0);
             else tma_store_2d(&maps.out, os_ptr, gc0, row0);
             if (EPI == EPI_BIAS_GELU && g.out2) tma_store_2d(&maps.out2, out2_s + ob * S::SLAB, gc0, row0);

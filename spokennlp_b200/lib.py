@@ -42,7 +42,7 @@ _PROTOS = {
     "b200_clip_coef": [_p, _f, _f, _p, _p],
     "b200_adamw_step": [_p, _p, _p, _p, _p, _sz, _f, _f, _f, _f, _f, _f, _f, _p, _p],
 }
-_RESTYPE = {"b200_set_gemm_impl": None, "b200_last_error": C.c_char_p, "b200_launch_count": _ll, "b200_version": _i, "b200_attn_bwd_workspace": _sz}
+_RESTYPE = {"b200_set_gemm_impl": None, "b200_set_gemm_debug": None, "b200_last_error": C.c_char_p, "b200_launch_count": _ll, "b200_version": _i, "b200_attn_bwd_workspace": _sz}
 
 _lock = threading.Lock()
 _lib = None
@@ -76,6 +76,7 @@ def load() -> C.CDLL:
             for name, rt in _RESTYPE.items():
                 getattr(lib, name).restype = rt
             lib.b200_set_gemm_impl.argtypes = [_i]
+            lib.b200_set_gemm_debug.argtypes = [_i]
             _lib = lib
     return _lib
 
