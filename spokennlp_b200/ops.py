@@ -63,13 +63,22 @@ def set_gemm_impl(impl: int) -> None:
 
 
 def wgrad_splits(M_out: int, N_in: int, K_tokens: int, sms: int = 148) -> int:
-    """Split-K factor for a weight-gradient GEMM so the persistent grid fills the SMs."""
-    tiles = ((M_out + 127) // 128) * ((N_in + 255) // 256)
+    """Split-K factor for a weight-gradient GEMM (2-CTA kernel: 256 x 256 pair tiles, sms/2 pairs): the smallest split
+    count whose last round of the persistent grid is at least 90 % full, keeping >= 16 K blocks per split."""
+    pairs = max(1, sms // 2)
+    tiles = ((M_out + 255) // 256) * ((N_in + 255) // 256)
     kb = (K_tokens + 63) // 64
-    s = max(1, min(kb, (2 * sms + tiles - 1) // tiles))
-    while s > 1 and (kb + s - 1) // s * (s - 1) >= kb:   # avoid empty splits
-        s -= 1
-    return s
+    best, best_eff = 1, 0.0
+    for s in range(1, max(1, min(kb // 16, 64)) + 1):
+        if (kb + s - 1) // s * (s - 1) >= kb:        # would leave an empty split
+            continue
+        units = tiles * s
+        eff = units / (((units + pairs - 1) // pairs) * pairs)
+        if eff > best_eff + 0.02:
+            best, best_eff = s, eff
+        if best_eff >= 0.9:
+            break
+    return best
 
 
 def attn_fwd(q: Tensor, kv: Tensor, ctx: Tensor, B: int, heads: int, Sq: int, Sk: int, *, q_col0: int, k_col0: int,

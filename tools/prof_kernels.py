@@ -25,6 +25,7 @@ qkv = torch.empty(M, 3 * H, device=dev, dtype=f16)
 h = torch.empty(M, I, device=dev, dtype=f16)
 z = torch.empty(M, I, device=dev, dtype=f16)
 pre = torch.empty(M, H, device=dev, dtype=torch.float32)
+x32 = torch.randn(M, H, device=dev, dtype=torch.float32)
 ctx = torch.empty(M, H, device=dev, dtype=f16)
 lse = torch.empty(B, heads, S, device=dev)
 g, b = torch.ones(H, device=dev), torch.zeros(H, device=dev)
@@ -41,10 +42,10 @@ ws = ops.attn_bwd_workspace(B, heads, S, dev)
 for _ in range(reps):
     ops.gemm(x, wqkv, qkv, epilogue=ops.EPI_BIAS, bias=bq)                                   # QKV projection
     ops.attn_fwd(qkv, qkv, ctx, B, heads, S, S, q_col0=0, k_col0=H, v_col0=2 * H, lse2=lse)   # attention fwd
-    ops.gemm(ctx, wo, pre, epilogue=ops.EPI_BIAS_RES, bias=bo, aux=x)                        # out-proj + residual
+    ops.gemm(ctx, wo, pre, epilogue=ops.EPI_BIAS_RES32, bias=bo, aux=x32)                      # out-proj + residual
     ops.layernorm_fwd(pre, g, b, 1e-12, y=y, mean=mean, rstd=rstd)                           # LN fwd
     ops.gemm(y, w1, h, epilogue=ops.EPI_BIAS_GELU, bias=b1, out2=z)                          # FFN up + GELU
-    ops.gemm(h, w2, pre, epilogue=ops.EPI_BIAS_RES, bias=bo, aux=y)                          # FFN down + residual
+    ops.gemm(h, w2, pre, epilogue=ops.EPI_BIAS_RES32, bias=bo, aux=x32)                        # FFN down + residual
     ops.layernorm_bwd(y, pre, mean, rstd, g, dx, dg, db_, dbias=dbias)                       # LN bwd
     ops.gemm(dx, h, gw2, a_layout=1, b_layout=1, epilogue=ops.EPI_ATOMIC, k_splits=ops.wgrad_splits(H, I, M))    # wgrad FFN down
     ops.gemm(dx, w2, dz, b_layout=1, epilogue=ops.EPI_DGELU, aux=z)                          # dgrad FFN down + dGELU
