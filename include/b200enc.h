@@ -32,9 +32,9 @@ extern "C" {
 /* epilogues of b200_gemm_f16 */
 #define B200_EPI_STORE 0          /* out = acc */
 #define B200_EPI_BIAS 1           /* out = acc + bias[n]                      (nn.Linear: QKV projection, bert_model.py:271,293-296) */
-#define B200_EPI_BIAS_GELU 2      /* out = gelu_erf(acc + bias[n]); out2 = pre-activation (BertIntermediate, bert_model.py:436-439) */
+#define B200_EPI_BIAS_GELU 2      /* z = acc + bias[n]; out = gelu_erf(z); out2 = gelu'(z) saved for the backward (BertIntermediate, bert_model.py:436-439) */
 #define B200_EPI_BIAS_RES 3       /* out = acc + bias[n] + aux[m,n]           (dense + residual of BertSelfOutput / BertOutput, :371-375, :449-453) */
-#define B200_EPI_DGELU 4          /* out = acc * gelu'(aux[m,n])              (autograd of :436-439) */
+#define B200_EPI_DGELU 4          /* out = acc * aux[m,n], aux = gelu'(z) from the forward (autograd of :436-439) */
 #define B200_EPI_ADD 5            /* out = acc + aux[m,n]                     (dgrad + residual-branch gradient) */
 #define B200_EPI_ATOMIC 6         /* out(fp32) += alpha * acc                 (wgrad, split-K) */
 #define B200_EPI_BIAS_RES32 7     /* out(fp32) = acc + bias[n] + aux32[m,n]   (as BIAS_RES with the residual stream kept in fp32) */

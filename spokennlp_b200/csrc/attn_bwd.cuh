@@ -16,7 +16,7 @@
 
 namespace b200 {
 
-constexpr int ATTB_THREADS = 192;   // warp 0 TMA, warp 1 MMA, warps 2-5 softmax/epilogue
+constexpr int ATTB_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 softmax / gradient epilogue
 
 struct AttnBwdArgs {
   int B, heads, Sq, Sk;
@@ -46,6 +46,11 @@ struct AttnBwdSmem {
   static constexpr int TOTAL = OFF_BAR + 256 + 1024;
 };
 
+// Schedule per query block i (tensor core and CUDA cores overlap):
+//   MMA warp : wait ds_full(i) -> issue S^T(i+1), dP^T(i+1) (their TMEM is free: block i was read out) -> s_full(i+1)
+//              -> issue dV += , dK += , dQ(i) = -> grad_done(i)
+//   softmax  : wait s_full(i+1) -> exp / dS math for block i+1 into registers WHILE the gradient MMAs of block i run
+//              -> wait grad_done(i) -> drain dQ(i) (fp32 reduction) -> write P^T / dS^T tiles -> ds_full(i+1)
 __global__ void __launch_bounds__(ATTB_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                 const __grid_constant__ CUtensorMap tmDO, const AttnBwdArgs a) {
@@ -57,8 +62,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* qdo_full = bars + 1;       // 2
   uint64_t* qdo_empty = bars + 3;      // 2
   uint64_t* s_full = bars + 5;         // 1
-  uint64_t* ds_full = bars + 6;        // 1 (128 arrivals)
-  uint64_t* fin = bars + 7;            // 1
+  uint64_t* ds_full = bars + 6;        // 1 (256 arrivals)
+  uint64_t* grad_done = bars + 7;      // 1
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -79,8 +84,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&qdo_empty[i], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(ds_full, 128);
-    mbar_init(fin, 1);
+    mbar_init(ds_full, 256);
+    mbar_init(grad_done, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -94,7 +99,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   // TMEM columns: S^T [0,128)  dP^T [128,256)  dV [256,320)  dK [320,384)  dQ [384,448)
 
   if (dead_block) {
-    if (warp >= 2) {
+    if (warp >= 2 && warp < 6) {
       const int r = (warp & 3) * 32 + lane;
       if (k0 + r < a.Sk) {
         const size_t row = static_cast<size_t>(b) * a.Sk + k0 + r;
@@ -146,6 +151,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int st = i & 1;
       mbar_wait(ds_full, i & 1);
       tc_fence_after();
+      if (i + 1 < nq) {                       // scores of the next block first: the softmax warps start on them at once
+        mbar_wait(&qdo_full[st ^ 1], ((i + 1) >> 1) & 1);
+        tc_fence_after();
+        if (lane == 0) issue_scores(st ^ 1);
+        __syncwarp();
+      }
       if (lane == 0) {
         const uint32_t qa = smem_u32(smem + S::OFF_QDO + st * 2 * S::T), doa = qa + S::T;
 #pragma unroll
@@ -160,114 +171,105 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int kk = 0; kk < 8; ++kk)        // dQ_i = dS K   (A = dS^T tile viewed MN-major: M = query, K = key rows)
           umma_ss(tmem + 384, make_smem_desc(dsa + kk * 2048, 16384, 1024), make_smem_desc(ka + kk * 2048, 8192, 1024), idesc_q, kk > 0);
         umma_commit(&qdo_empty[st]);
-      }
-      __syncwarp();
-      if (i + 1 < nq) {
-        mbar_wait(&qdo_full[st ^ 1], ((i + 1) >> 1) & 1);
-        tc_fence_after();
-        if (lane == 0) issue_scores(st ^ 1);
-      } else if (lane == 0) {
-        umma_commit(fin);
+        umma_commit(grad_done);
       }
       __syncwarp();
     }
   } else {
-    const int qd = warp & 3;
-    const int r = qd * 32 + lane;                 // key row inside the block == TMEM lane
-    const int t = threadIdx.x - 64;               // 0..127
+    const int qd = warp & 3;                      // TMEM lane quadrant
+    const int half = (warp - 2) >> 2;             // which 64 of the 128 query columns (and which 32 of the 64 d columns)
+    const int r = qd * 32 + lane;                 // key row inside the block == TMEM lane (query row for the dQ tile)
+    const int t = threadIdx.x - 64;               // 0..255
     const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
     const uint32_t stat = smem_u32(smem + S::OFF_STAT);
-    const uint32_t p_row = smem_u32(smem + S::OFF_P) + r * 128;
-    const uint32_t ds_row = smem_u32(smem + S::OFF_DS) + r * 128;
+    const uint32_t p_row = smem_u32(smem + S::OFF_P) + half * 16384 + r * 128;
+    const uint32_t ds_row = smem_u32(smem + S::OFF_DS) + half * 16384 + r * 128;
     const int key = k0 + r;
     float bias = -INFINITY;
     if (key < kv_len) bias = a.key_bias ? a.key_bias[static_cast<size_t>(b) * a.Sk + key] * 1.4426950408889634f : 0.f;
     const size_t stat_base = (static_cast<size_t>(b) * a.heads + h) * a.Sq;
 
-    auto drain_dq = [&](int i) {                  // dQ_i tile: TMEM lane == query row
+    auto drain_dq = [&](int i) {                  // dQ_i tile: TMEM lane == query row; this warp owns 32 of the 64 d columns
       const int q = i * ATT_BQ + r;
-      uint32_t o[2][32];
-      tmem_ld_x32(tmem + lane_addr + 384, o[0]);
-      tmem_ld_x32(tmem + lane_addr + 384 + 32, o[1]);
+      uint32_t o[32];
+      tmem_ld_x32(tmem + lane_addr + 384 + half * 32, o);
       tmem_wait_ld();
       if (q < a.Sq) {
-        float* dst = a.dq_acc + (static_cast<size_t>(b) * a.Sq + q) * a.ld_dq + h * ATT_D;
+        float* dst = a.dq_acc + (static_cast<size_t>(b) * a.Sq + q) * a.ld_dq + h * ATT_D + half * 32;
 #pragma unroll
-        for (int c = 0; c < 2; ++c)
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            red_add_v4(dst + c * 32 + k * 4, __uint_as_float(o[c][4 * k]), __uint_as_float(o[c][4 * k + 1]),
-                       __uint_as_float(o[c][4 * k + 2]), __uint_as_float(o[c][4 * k + 3]));
+        for (int k = 0; k < 8; ++k)
+          red_add_v4(dst + k * 4, __uint_as_float(o[4 * k]), __uint_as_float(o[4 * k + 1]), __uint_as_float(o[4 * k + 2]),
+                     __uint_as_float(o[4 * k + 3]));
       }
     };
 
     for (int i = 0; i < nq; ++i) {
-      {  // per-query statistics of block i; queries past Sq get lse = +inf (P = 0) and delta = 0
+      if (t < 128) {  // per-query statistics of block i; queries past Sq get lse = +inf (P = 0) and delta = 0
         const int q = i * ATT_BQ + t;
         const uint32_t sb = stat + (i & 1) * 1024;
         sts_f32(sb + t * 4, q < a.Sq ? a.lse2[stat_base + q] : INFINITY);
         sts_f32(sb + 512 + t * 4, q < a.Sq ? a.delta[stat_base + q] : 0.f);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
-      const uint32_t lse_s = stat + (i & 1) * 1024;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const uint32_t lse_s = stat + (i & 1) * 1024 + half * 256;
       const uint32_t del_s = lse_s + 512;
       mbar_wait(s_full, i & 1);
       tc_fence_after();
-      if (i > 0) drain_dq(i - 1);
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      uint32_t pk[32], dk[32];                    // this thread's 64 P^T / dS^T values, packed fp16
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
         uint32_t sv[32], dp[32];
-        tmem_ld_x32(tmem + lane_addr + c * 32, sv);
-        tmem_ld_x32(tmem + lane_addr + 128 + c * 32, dp);
+        tmem_ld_x32(tmem + lane_addr + half * 64 + c * 32, sv);
+        tmem_ld_x32(tmem + lane_addr + 128 + half * 64 + c * 32, dp);
         tmem_wait_ld();
-        uint32_t pk[16], dk[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
-          const int q0i = c * 32 + 2 * e;
-          const float p0 = fast_exp2(fmaf(__uint_as_float(sv[2 * e]), a.scale_log2, bias) - lds_f32(lse_s + q0i * 4));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(sv[2 * e + 1]), a.scale_log2, bias) - lds_f32(lse_s + q0i * 4 + 4));
-          const float d0 = p0 * (__uint_as_float(dp[2 * e]) - lds_f32(del_s + q0i * 4)) * a.inv_sqrt_d;
-          const float d1 = p1 * (__uint_as_float(dp[2 * e + 1]) - lds_f32(del_s + q0i * 4 + 4)) * a.inv_sqrt_d;
+          const int qi = c * 32 + 2 * e;
+          const float p0 = fast_exp2(fmaf(__uint_as_float(sv[2 * e]), a.scale_log2, bias) - lds_f32(lse_s + qi * 4));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(sv[2 * e + 1]), a.scale_log2, bias) - lds_f32(lse_s + qi * 4 + 4));
+          const float d0 = p0 * (__uint_as_float(dp[2 * e]) - lds_f32(del_s + qi * 4)) * a.inv_sqrt_d;
+          const float d1 = p1 * (__uint_as_float(dp[2 * e + 1]) - lds_f32(del_s + qi * 4 + 4)) * a.inv_sqrt_d;
           const __half2 hp = __floats2half2_rn(p0, p1), hd = __floats2half2_rn(d0, d1);
-          pk[e] = *reinterpret_cast<const uint32_t*>(&hp);
-          dk[e] = *reinterpret_cast<const uint32_t*>(&hd);
+          pk[c * 16 + e] = *reinterpret_cast<const uint32_t*>(&hp);
+          dk[c * 16 + e] = *reinterpret_cast<const uint32_t*>(&hd);
         }
+      }
+      if (i > 0) {                                // gradient MMAs of block i-1 are done: dQ(i-1) is complete, P^T/dS^T are free
+        mbar_wait(grad_done, (i - 1) & 1);
+        tc_fence_after();
+        drain_dq(i - 1);
+      }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int ch = 4 * c + e;
-          const int off = (ch >> 3) * 16384 + (((ch & 7) ^ (r & 7)) << 4);
-          sts128(p_row + off, pk[4 * e], pk[4 * e + 1], pk[4 * e + 2], pk[4 * e + 3]);
-          sts128(ds_row + off, dk[4 * e], dk[4 * e + 1], dk[4 * e + 2], dk[4 * e + 3]);
-        }
+      for (int ch = 0; ch < 8; ++ch) {
+        const int off = ((ch ^ (r & 7)) << 4);
+        sts128(p_row + off, pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+        sts128(ds_row + off, dk[4 * ch], dk[4 * ch + 1], dk[4 * ch + 2], dk[4 * ch + 3]);
       }
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(ds_full);
     }
-    mbar_wait(fin, 0);
+    mbar_wait(grad_done, (nq - 1) & 1);
     tc_fence_after();
     drain_dq(nq - 1);
-    // dV, dK: TMEM lane == key row
-    uint32_t o[2][32];
+    // dV, dK: TMEM lane == key row; this warp owns 32 of the 64 d columns
 #pragma unroll 1
     for (int which = 0; which < 2; ++which) {
-      tmem_ld_x32(tmem + lane_addr + 256 + which * 64, o[0]);
-      tmem_ld_x32(tmem + lane_addr + 256 + which * 64 + 32, o[1]);
+      uint32_t o[32];
+      tmem_ld_x32(tmem + lane_addr + 256 + which * 64 + half * 32, o);
       tmem_wait_ld();
       if (key < a.Sk) {
-        __half* dst = (which == 0 ? a.dv + a.dv_col0 : a.dk + a.dk_col0) + (static_cast<size_t>(b) * a.Sk + key) * a.ld_dkv + h * ATT_D;
+        __half* dst = (which == 0 ? a.dv + a.dv_col0 : a.dk + a.dk_col0) + (static_cast<size_t>(b) * a.Sk + key) * a.ld_dkv + h * ATT_D + half * 32;
 #pragma unroll
-        for (int c = 0; c < 2; ++c)
+        for (int e = 0; e < 4; ++e) {
+          uint32_t w[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            uint32_t w[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const __half2 hv = __floats2half2_rn(__uint_as_float(o[c][8 * e + 2 * k]), __uint_as_float(o[c][8 * e + 2 * k + 1]));
-              w[k] = *reinterpret_cast<const uint32_t*>(&hv);
-            }
-            *reinterpret_cast<uint4*>(dst + c * 32 + e * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+          for (int k = 0; k < 4; ++k) {
+            const __half2 hv = __floats2half2_rn(__uint_as_float(o[8 * e + 2 * k]), __uint_as_float(o[8 * e + 2 * k + 1]));
+            w[k] = *reinterpret_cast<const uint32_t*>(&hv);
           }
+          *reinterpret_cast<uint4*>(dst + e * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
       }
     }
   }

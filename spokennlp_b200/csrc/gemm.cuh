@@ -27,9 +27,9 @@ constexpr int GEMM_STAGE_PITCH = 36;   // floats per staged row (32 + 4 pad -> c
 enum : int {
   EPI_STORE = 0,      // out = acc
   EPI_BIAS = 1,       // out = acc + bias[n]
-  EPI_BIAS_GELU = 2,  // z = acc + bias[n]; out = gelu_erf(z); out2 = z (if given)
+  EPI_BIAS_GELU = 2,  // z = acc + bias[n]; out = gelu_erf(z); out2 = gelu'(z) (if given; consumed by EPI_DGELU)
   EPI_BIAS_RES = 3,   // out = acc + bias[n] + aux[m,n]
-  EPI_DGELU = 4,      // out = acc * gelu'(aux[m,n])
+  EPI_DGELU = 4,      // out = acc * aux[m,n]   (aux = gelu'(z) saved by the forward)
   EPI_ADD = 5,        // out = acc + aux[m,n]
   EPI_ATOMIC = 6,     // out(fp32) += alpha * acc   (split-K reduction with red.global.add)
   EPI_BIAS_RES32 = 7, // out = acc + bias[n] + aux32[m,n]   (fp32 residual stream)

@@ -7,7 +7,7 @@
 //   * the leader CTA's MMA warp issues tcgen05.mma.cta_group::2 for both SMs; completion is multicast to the
 //     mbarriers of both CTAs (smem-slot release, accumulator-ready);
 //   * accumulators: 2 x 256 TMEM columns per CTA (epilogue of tile i overlaps the mainloop of tile i+1);
-//   * epilogue: four warps per CTA, one thread per accumulator row: TMEM -> registers -> bias / GELU / residual /
+//   * epilogue: eight warps per CTA (two per TMEM lane quadrant), one thread per accumulator row: TMEM -> registers -> bias / GELU / residual /
 //     dGELU math -> fp16/fp32 128B-swizzled staging rows -> TMA store (or TMA reduce-add for split-K wgrad).
 //     Auxiliary row-major inputs (residual, pre-activation) arrive by TMA into the same swizzled staging geometry, so
 //     no thread issues an uncoalesced global access and the aux fetch of chunk c+1 overlaps the math of chunk c.
@@ -16,7 +16,7 @@
 
 namespace b200 {
 
-constexpr int G2_THREADS = 192;           // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int G2_THREADS = 320;           // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int G2_BM = 256;                // rows per CTA pair
 constexpr int G2_SMEM_MAX = 232448;       // 227 KB opt-in limit per CTA
 
@@ -29,11 +29,12 @@ struct Gemm2Smem {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int SLAB = 32 * 128;                      // 4 KB : 32 rows x 128 B staging slab
   static constexpr bool AUX = EPI == EPI_BIAS_RES || EPI == EPI_BIAS_RES32 || EPI == EPI_DGELU || EPI == EPI_ADD;
-  static constexpr int SLABS = 2 + (AUX ? 2 : 0) + (EPI == EPI_BIAS_GELU ? 2 : 0);   // out x2 [, aux x2] [, out2 x2]
+  static constexpr int SLABS = 1 + (AUX ? 1 : 0) + (EPI == EPI_BIAS_GELU ? 1 : 0);   // out [, aux] [, out2], single-buffered
   static constexpr int EPI_PER_WARP = SLABS * SLAB;
-  static constexpr int STAGES = (G2_SMEM_MAX - 1024 - 512 - 4 * EPI_PER_WARP) / STAGE_BYTES;
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int STAGES = (G2_SMEM_MAX - 1024 - 512 - EPI_WARPS * EPI_PER_WARP) / STAGE_BYTES;
   static constexpr int OFF_EPI = STAGES * STAGE_BYTES;
-  static constexpr int OFF_BAR = OFF_EPI + 4 * EPI_PER_WARP;
+  static constexpr int OFF_BAR = OFF_EPI + EPI_WARPS * EPI_PER_WARP;
   static constexpr int TOTAL = OFF_BAR + 512 + 1024;
   static_assert(STAGES >= 4 && TOTAL <= G2_SMEM_MAX, "shared-memory plan");
 };
@@ -129,7 +130,7 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
   uint64_t* empty_bar = full_bar + G2_STAGES;
   uint64_t* tfull_bar = empty_bar + G2_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* aux_bar = tempty_bar + 2;                 // [4 warps][2]
+  uint64_t* aux_bar = tempty_bar + 2;                 // [8 warps]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -155,7 +156,7 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 8);               // 4 epilogue warps x 2 CTAs (only the leader's copy is used)
+      mbar_init(&tempty_bar[i], 16);              // 8 epilogue warps x 2 CTAs (only the leader's copy is used)
     }
     for (int i = 0; i < 8; ++i) mbar_init(&aux_bar[i], 1);
     fence_mbar_init();
@@ -252,44 +253,55 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5, both CTAs)
+    // ------------------------------------------------------------------ epilogue (warps 2..9, both CTAs)
+    // Two warps per TMEM lane quadrant: warp (q, half) owns rows 32q..32q+31 and one half of the tile's columns.
+    // Eight warps (two per SM sub-partition) keep the FP32 pipes busy through the dependent erf / exp chains.
     const int q = warp & 3;                               // TMEM lane quadrant
-    const int ew = warp - 2;
+    const int ew = warp - 2;                              // 0..7
+    const int half = ew >> 2;                             // which half of the BN columns
     uint8_t* slabs = smem + S::OFF_EPI + ew * S::EPI_PER_WARP;
-    uint8_t* out_s = slabs;                               // 2 slabs
-    uint8_t* aux_s = slabs + 2 * S::SLAB;                 // 2 slabs (variants with an auxiliary input)
-    uint8_t* out2_s = slabs + 2 * S::SLAB;                // 2 slabs (GELU variant: pre-activation output)
-    uint64_t* my_aux_bar = aux_bar + ew * 2;
+    uint8_t* out_s = slabs;                               // output slab
+    uint8_t* aux_s = slabs + S::SLAB;                     // auxiliary-input slab (variants with aux)
+    uint8_t* out2_s = slabs + S::SLAB;                    // pre-activation slab (GELU variant)
+    uint64_t* my_aux_bar = aux_bar + ew;
     const uint32_t tempty0[2] = {mapa_u32(smem_u32(&tempty_bar[0]), 0), mapa_u32(smem_u32(&tempty_bar[1]), 0)};
     const float alpha = g.alpha ? __ldg(g.alpha) : 1.0f;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     uint32_t acc = 0, acc_phase = 0;
-    uint32_t aux_uses = 0;                                // slabs fetched so far (buffer = uses & 1, parity = (uses >> 1) & 1)
-    uint32_t out_uses = 0;
-    constexpr int NCH = BN / CW;
+    uint32_t aux_uses = 0;                                // parity of the aux barrier = aux_uses & 1
+    constexpr int NCH = BN / CW / 2;                      // chunks per warp per tile
     for (int u = pair; u < units; u += n_pairs) {
       int mt, nt, kb0, kb1;
       decode(u, mt, nt, kb0, kb1);
       const int row0 = mt * G2_BM + static_cast<int>(rank) * 128 + q * 32;     // first output row of this warp
-      const int col0 = nt * BN;
+      const int col0 = nt * BN + half * (BN / 2);                               // first output column of this warp
       const bool has_data = kb1 > kb0;
-      if (HAS_AUX && lane == 0) {                         // aux slab of chunk 0
-        mbar_expect_tx(&my_aux_bar[aux_uses & 1], S::SLAB);
-        tma_load_2d(aux_s + (aux_uses & 1) * S::SLAB, &maps.aux, &my_aux_bar[aux_uses & 1], col0, row0);
+      if (HAS_AUX && lane == 0) {                         // aux slab of the first chunk (lands while the mainloop runs)
+        mbar_expect_tx(my_aux_bar, S::SLAB);
+        tma_load_2d(aux_s, &maps.aux, my_aux_bar, col0, row0);
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c) {
         const int gc0 = col0 + c * CW;
-        if (HAS_AUX && c + 1 < NCH && lane == 0) {        // prefetch the next chunk's aux slab into the other buffer
-          const uint32_t nb = (aux_uses + 1) & 1;
-          mbar_expect_tx(&my_aux_bar[nb], S::SLAB);
-          tma_load_2d(aux_s + nb * S::SLAB, &maps.aux, &my_aux_bar[nb], gc0 + CW, row0);
-        }
         uint32_t v[CW];
 #pragma unroll
-        for (int i = 0; i < CW / 32; ++i) tmem_ld_x32(tmem_base + lane_addr + acc * BN + c * CW + i * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[i * 32]));
+        for (int i = 0; i < CW / 32; ++i)
+          tmem_ld_x32(tmem_base + lane_addr + acc * BN + half * (BN / 2) + c * CW + i * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[i * 32]));
+        uint4 araw[8];
+        if (HAS_AUX) {                                    // consume the aux slab, then refill it for the next chunk
+          mbar_wait(my_aux_bar, aux_uses & 1);
+          ++aux_uses;
+          const uint32_t as = smem_u32(aux_s);
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) araw[ch] = lds128(slab_chunk(as, lane, ch));
+          __syncwarp();
+          if (c + 1 < NCH && lane == 0) {
+            mbar_expect_tx(my_aux_bar, S::SLAB);
+            tma_load_2d(aux_s, &maps.aux, my_aux_bar, gc0 + CW, row0);
+          }
+        }
         tmem_wait_ld();
         if (c == NCH - 1) {                               // accumulator drained -> hand it back to the leader's MMA warp
           tc_fence_before();
@@ -307,12 +319,9 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
           }
         }
         if (HAS_AUX) {
-          const uint32_t ab = aux_uses & 1;
-          mbar_wait(&my_aux_bar[ab], (aux_uses >> 1) & 1);
-          const uint32_t as = smem_u32(aux_s + ab * S::SLAB);
 #pragma unroll
           for (int ch = 0; ch < 8; ++ch) {
-            const uint4 raw = lds128(slab_chunk(as, lane, ch));
+            const uint4 raw = araw[ch];
             if (EPI == EPI_BIAS_RES32) {                  // 4 fp32 per 16-byte chunk
               f[4 * ch] += __uint_as_float(raw.x); f[4 * ch + 1] += __uint_as_float(raw.y);
               f[4 * ch + 2] += __uint_as_float(raw.z); f[4 * ch + 3] += __uint_as_float(raw.w);
@@ -322,8 +331,8 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
               for (int k = 0; k < 4; ++k) {
                 const float2 x = __half22float2(hp[k]);
                 if (EPI == EPI_DGELU) {
-                  f[8 * ch + 2 * k] *= gelu_erf_grad(x.x);
-                  f[8 * ch + 2 * k + 1] *= gelu_erf_grad(x.y);
+                  f[8 * ch + 2 * k] *= x.x;
+                  f[8 * ch + 2 * k + 1] *= x.y;
                 } else {
                   f[8 * ch + 2 * k] += x.x;
                   f[8 * ch + 2 * k + 1] += x.y;
@@ -331,58 +340,51 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
               }
             }
           }
-          ++aux_uses;
-          __syncwarp();                                   // every lane has consumed the slab before it is refilled
         }
-        // staging slab of this chunk must no longer be read by the TMA store issued two chunks ago
-        const uint32_t ob = out_uses & 1;
-        if (lane == 0) tma_wait_group_read<1>();
-        __syncwarp();
-        uint8_t* os_ptr = out_s + ob * S::SLAB;
-        const uint32_t os = smem_u32(os_ptr);
+        uint32_t ow[CW / 2 < 32 ? 32 : CW / 2];          // packed output words of this thread's row segment
+        uint32_t zw[EPI == EPI_BIAS_GELU ? 32 : 1];
         if (EPI == EPI_BIAS_GELU) {
-          const uint32_t zs = smem_u32(out2_s + ob * S::SLAB);
 #pragma unroll
-          for (int ch = 0; ch < 8; ++ch) {
-            uint32_t zw[4], hw[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float z0 = f[8 * ch + 2 * k], z1 = f[8 * ch + 2 * k + 1];
-              const __half2 hz = __floats2half2_rn(z0, z1), hh = __floats2half2_rn(gelu_erf(z0), gelu_erf(z1));
-              zw[k] = *reinterpret_cast<const uint32_t*>(&hz);
-              hw[k] = *reinterpret_cast<const uint32_t*>(&hh);
-            }
-            sts128(slab_chunk(zs, lane, ch), zw[0], zw[1], zw[2], zw[3]);
-            sts128(slab_chunk(os, lane, ch), hw[0], hw[1], hw[2], hw[3]);
+          for (int k = 0; k < 32; ++k) {
+            float y0, y1, d0, d1;
+            gelu_erf_both(f[2 * k], y0, d0);
+            gelu_erf_both(f[2 * k + 1], y1, d1);
+            const __half2 hz = __floats2half2_rn(d0, d1), hh = __floats2half2_rn(y0, y1);
+            zw[k] = *reinterpret_cast<const uint32_t*>(&hz);
+            ow[k] = *reinterpret_cast<const uint32_t*>(&hh);
           }
         } else if (OUT32) {
 #pragma unroll
-          for (int ch = 0; ch < 8; ++ch)
-            sts128(slab_chunk(os, lane, ch), __float_as_uint(f[4 * ch]), __float_as_uint(f[4 * ch + 1]), __float_as_uint(f[4 * ch + 2]),
-                   __float_as_uint(f[4 * ch + 3]));
+          for (int k = 0; k < 32; ++k) ow[k] = __float_as_uint(f[k]);
         } else {
 #pragma unroll
-          for (int ch = 0; ch < 8; ++ch) {
-            uint32_t w[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const __half2 hv = __floats2half2_rn(f[8 * ch + 2 * k], f[8 * ch + 2 * k + 1]);
-              w[k] = *reinterpret_cast<const uint32_t*>(&hv);
-            }
-            sts128(slab_chunk(os, lane, ch), w[0], w[1], w[2], w[3]);
+          for (int k = 0; k < 32; ++k) {
+            const __half2 hv = __floats2half2_rn(f[2 * k], f[2 * k + 1]);
+            ow[k] = *reinterpret_cast<const uint32_t*>(&hv);
           }
+        }
+        // the slab is single-buffered: the TMA store issued for the previous chunk must have finished reading it
+        // (it was issued a whole chunk of math ago, so this wait is normally free)
+        if (lane == 0) tma_wait_group_read<0>();
+        __syncwarp();
+        const uint32_t os = smem_u32(out_s);
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) sts128(slab_chunk(os, lane, ch), ow[4 * ch], ow[4 * ch + 1], ow[4 * ch + 2], ow[4 * ch + 3]);
+        if (EPI == EPI_BIAS_GELU) {
+          const uint32_t zs = smem_u32(out2_s);
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) sts128(slab_chunk(zs, lane, ch), zw[4 * ch], zw[4 * ch + 1], zw[4 * ch + 2], zw[4 * ch + 3]);
         }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
           if (has_data && !(g.dbg & 8)) {
-            if (EPI == EPI_ATOMIC) tma_reduce_add_2d(&maps.out, os_ptr, gc0, row0);
-            else tma_store_2d(&maps.out, os_ptr, gc0, row0);
-            if (EPI == EPI_BIAS_GELU && g.out2) tma_store_2d(&maps.out2, out2_s + ob * S::SLAB, gc0, row0);
+            if (EPI == EPI_ATOMIC) tma_reduce_add_2d(&maps.out, out_s, gc0, row0);
+            else tma_store_2d(&maps.out, out_s, gc0, row0);
+            if (EPI == EPI_BIAS_GELU && g.out2) tma_store_2d(&maps.out2, out2_s, gc0, row0);
           }
           tma_commit_group();
         }
-        ++out_uses;
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;

@@ -243,6 +243,14 @@ __device__ __forceinline__ float fast_erf(float x) {
   return __fdividef(p, q);
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + fast_erf(x * 0.70710678118654752f)); }
+// gelu(x) and d/dx gelu(x) = Phi(x) + x * phi(x) from one erf evaluation (the forward epilogue saves the derivative so
+// that the backward epilogue is a plain multiply)
+__device__ __forceinline__ void gelu_erf_both(float x, float& y, float& dy) {
+  const float cdf = 0.5f * (1.0f + fast_erf(x * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * fast_exp2(-0.7213475204444817f * x * x);   // exp(-x^2/2) = 2^(-x^2/(2 ln 2))
+  y = x * cdf;
+  dy = fmaf(x, pdf, cdf);
+}
 // d/dx gelu(x) = Phi(x) + x * phi(x)
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float cdf = 0.5f * (1.0f + fast_erf(x * 0.70710678118654752f));

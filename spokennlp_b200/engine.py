@@ -120,7 +120,7 @@ class LayerViews:
 class LayerSaved:
     x_in: Tensor = None; qkv: Tensor = None; ctx: Tensor = None; lse2: Tensor = None
     pre1: Tensor = None; mean1: Tensor = None; rstd1: Tensor = None; ln1: Tensor = None
-    z: Tensor = None; h: Tensor = None
+    z: Tensor = None; h: Tensor = None          # z holds gelu'(pre-activation), h = gelu(pre-activation)
     pre2: Tensor = None; mean2: Tensor = None; rstd2: Tensor = None
 
 

@@ -111,7 +111,9 @@ def test_gemm_epilogues(gemm_impl):
     ops.gemm(a, w, out, epilogue=ops.EPI_BIAS_GELU, bias=bias, out2=z)
     rel, msg = _err_report(out, torch.nn.functional.gelu(acc + bias), "EPI_BIAS_GELU")
     assert rel < 5e-4, msg
-    rel, msg = _err_report(z, acc + bias, "EPI_BIAS_GELU pre-activation")
+    zf0 = (acc + bias).clone().requires_grad_(True)
+    torch.nn.functional.gelu(zf0).sum().backward()
+    rel, msg = _err_report(z, zf0.grad, "EPI_BIAS_GELU saved derivative gelu'(z)")
     assert rel < 5e-4, msg
 
     o32 = torch.empty(M, N, dtype=torch.float32, device="cuda")
@@ -129,10 +131,8 @@ def test_gemm_epilogues(gemm_impl):
     ops.gemm(a, wt, out, b_layout=1, epilogue=ops.EPI_ADD, aux=res)
     rel, msg = _err_report(out, acc + res.float(), "EPI_ADD")
     assert rel < 5e-4, msg
-    ops.gemm(a, wt, out, b_layout=1, epilogue=ops.EPI_DGELU, aux=zz)
-    zf = zz.float().requires_grad_(True)
-    torch.nn.functional.gelu(zf).sum().backward()
-    rel, msg = _err_report(out, acc * zf.grad, "EPI_DGELU")
+    ops.gemm(a, wt, out, b_layout=1, epilogue=ops.EPI_DGELU, aux=zz)        # aux holds gelu'(z) saved by the forward
+    rel, msg = _err_report(out, acc * zz.float(), "EPI_DGELU")
     assert rel < 5e-4, msg
 
 
