@@ -54,7 +54,7 @@ long long b200_launch_count(void);
  * Replaces torch.nn.functional.linear and its autograd (dgrad: b_layout=1 on the same weight; wgrad:
  * a_layout=b_layout=1 on dY and X) — SURVEY.md K2, K4, K5, K6, K8.
  * Supported (a_layout,b_layout,epilogue,out_dtype): (0,0,{STORE,BIAS,BIAS_GELU,BIAS_RES,BIAS_RES32},{F16,F32*}),
- * (0,1,{STORE,ADD,DGELU},F16), (1,1,ATOMIC,F32).  (*F32 for STORE, BIAS_RES, BIAS_RES32; BIAS_RES32 is F32-only.)
+ * (0,1,{STORE,ADD,DGELU},F16), (1,1,ATOMIC,F32).  (*F32 for STORE, BIAS, BIAS_RES (single-CTA kernel only), BIAS_RES32; BIAS_RES32 is F32-only.)
  * alpha: optional device scalar multiplied into the accumulator.  k_splits > 1 only with EPI_ATOMIC.
  */
 /* 2 (default): 2-CTA cta_group::2 kernel with TMA epilogue; 1: single-CTA kernel (kept for A/B measurements) */
@@ -122,6 +122,8 @@ int b200_cast_f16_to_f32(const void* src, float* dst, size_t n, void* stream);
 /* scale[0] = power of two bringing amax|src| to ~target, scale[1] = 1/scale[0]; dst = fp16(src * scale[0]).
  * `amax_slot` is a 4-byte device scratch.  Used to carry an fp32 upstream gradient into the fp16 backward. */
 int b200_scale_cast_grad(const float* src, void* dst, size_t n, float target, float* scale, void* amax_slot, void* stream);
+/* dst(fp32) = src(fp16) * scale[1]: hands a scaled fp16 gradient back to an fp32 caller */
+int b200_unscale_cast_grad(const void* src, float* dst, size_t n, const float* scale, void* stream);
 
 /*
  * Fused attention backward (autograd of bert_model.py:309-350), head_dim 64.  Inputs as b200_attn_fwd plus

@@ -200,6 +200,7 @@ int b200_gemm_f16(const void* A, int lda, int a_layout, const void* B, int ldb, 
       case 0 * 1000 + 0 * 100 + EPI_STORE * 10 + B200_DT_F16: return launch_gemm2<BN, 0, 0, EPI_STORE, __half>(mp, g2, s);
       case 0 * 1000 + 0 * 100 + EPI_STORE * 10 + B200_DT_F32: return launch_gemm2<BN, 0, 0, EPI_STORE, float>(mp, g2, s);
       case 0 * 1000 + 0 * 100 + EPI_BIAS * 10 + B200_DT_F16: return launch_gemm2<BN, 0, 0, EPI_BIAS, __half>(mp, g2, s);
+      case 0 * 1000 + 0 * 100 + EPI_BIAS * 10 + B200_DT_F32: return launch_gemm2<BN, 0, 0, EPI_BIAS, float>(mp, g2, s);
       case 0 * 1000 + 0 * 100 + EPI_BIAS_GELU * 10 + B200_DT_F16: return launch_gemm2<BN, 0, 0, EPI_BIAS_GELU, __half>(mp, g2, s);
       case 0 * 1000 + 0 * 100 + EPI_BIAS_RES * 10 + B200_DT_F16: return launch_gemm2<BN, 0, 0, EPI_BIAS_RES, __half>(mp, g2, s);
       case 0 * 1000 + 0 * 100 + EPI_BIAS_RES32 * 10 + B200_DT_F32: return launch_gemm2<BN, 0, 0, EPI_BIAS_RES32, float>(mp, g2, s);
@@ -225,6 +226,7 @@ int b200_gemm_f16(const void* A, int lda, int a_layout, const void* B, int ldb, 
     case 0 * 1000 + 0 * 100 + EPI_STORE * 10 + B200_DT_F16: return launch_gemm<BN, 0, 0, EPI_STORE, __half>(ta, tb, g, s);
     case 0 * 1000 + 0 * 100 + EPI_STORE * 10 + B200_DT_F32: return launch_gemm<BN, 0, 0, EPI_STORE, float>(ta, tb, g, s);
     case 0 * 1000 + 0 * 100 + EPI_BIAS * 10 + B200_DT_F16: return launch_gemm<BN, 0, 0, EPI_BIAS, __half>(ta, tb, g, s);
+    case 0 * 1000 + 0 * 100 + EPI_BIAS * 10 + B200_DT_F32: return launch_gemm<BN, 0, 0, EPI_BIAS, float>(ta, tb, g, s);
     case 0 * 1000 + 0 * 100 + EPI_BIAS_GELU * 10 + B200_DT_F16: return launch_gemm<BN, 0, 0, EPI_BIAS_GELU, __half>(ta, tb, g, s);
     case 0 * 1000 + 0 * 100 + EPI_BIAS_RES * 10 + B200_DT_F16: return launch_gemm<BN, 0, 0, EPI_BIAS_RES, __half>(ta, tb, g, s);
     case 0 * 1000 + 0 * 100 + EPI_BIAS_RES * 10 + B200_DT_F32: return launch_gemm<BN, 0, 0, EPI_BIAS_RES, float>(ta, tb, g, s);
@@ -435,6 +437,11 @@ int b200_cast_f16_to_f32(const void* src, float* dst, size_t n, void* stream) {
   if (n % 8) return fail(B200_ERR_SHAPE, "cast: n %% 8 != 0");
   cast_f16_f32_kernel<<<stream_grid(n / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(src), dst, n / 8);
   return check_launch("cast_f16_f32_kernel");
+}
+int b200_unscale_cast_grad(const void* src, float* dst, size_t n, const float* scale, void* stream) {
+  if (n % 8) return fail(B200_ERR_SHAPE, "unscale_cast: n %% 8 != 0");
+  unscale_cast_f16_f32_kernel<<<stream_grid(n / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(src), scale, dst, n / 8);
+  return check_launch("unscale_cast_f16_f32_kernel");
 }
 int b200_scale_cast_grad(const float* src, void* dst, size_t n, float target, float* scale, void* amax_slot, void* stream) {
   if (n % 8) return fail(B200_ERR_SHAPE, "scale_cast: n %% 8 != 0");

@@ -103,20 +103,22 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& g, float* st,
           const float2 x01 = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
           const float2 x23 = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
           if (EPI == EPI_DGELU) {
-            a.x *= gelu_erf_grad(x01.x); a.y *= gelu_erf_grad(x01.y); a.z *= gelu_erf_grad(x23.x); a.w *= gelu_erf_grad(x23.y);
+            a.x *= x01.x; a.y *= x01.y; a.z *= x23.x; a.w *= x23.y;
           } else {
             a.x += x01.x; a.y += x01.y; a.z += x23.x; a.w += x23.y;
           }
         }
         if (EPI == EPI_BIAS_GELU) {
+          float4 d, y;
+          gelu_erf_both(a.x, y.x, d.x); gelu_erf_both(a.y, y.y, d.y); gelu_erf_both(a.z, y.z, d.z); gelu_erf_both(a.w, y.w, d.w);
+          a = y;
           if (g.out2) {
-            __half2 z01 = __floats2half2_rn(a.x, a.y), z23 = __floats2half2_rn(a.z, a.w);
+            __half2 z01 = __floats2half2_rn(d.x, d.y), z23 = __floats2half2_rn(d.z, d.w);
             uint2 zr;
             zr.x = *reinterpret_cast<uint32_t*>(&z01);
             zr.y = *reinterpret_cast<uint32_t*>(&z23);
             *reinterpret_cast<uint2*>(g.out2 + static_cast<size_t>(gr) * g.ld_out2 + gc) = zr;
           }
-          a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w);
         }
         if (EPI == EPI_ATOMIC) {
           red_add_v4(reinterpret_cast<float*>(g.out) + static_cast<size_t>(gr) * g.ld_out + gc, a.x, a.y, a.z, a.w);

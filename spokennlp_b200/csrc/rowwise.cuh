@@ -540,6 +540,17 @@ __global__ void cast_f16_f32_kernel(const __half* __restrict__ src, float* __res
     store8(dst + i * 8, load8(src + i * 8));
 }
 
+// dst(fp32) = src(fp16) * scale[1]   (carry a scaled fp16 gradient back out to an fp32 autograd graph)
+__global__ void unscale_cast_f16_f32_kernel(const __half* __restrict__ src, const float* __restrict__ scale, float* __restrict__ dst, size_t n8) {
+  const float s = scale ? scale[1] : 1.0f;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n8; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    Vec8 v = load8(src + i * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v.v[j] *= s;
+    store8(dst + i * 8, v);
+  }
+}
+
 // amax(|x|) over an fp32 tensor -> slot[0] (as float bits via atomicMax on uint: valid for non-negative floats)
 __global__ void amax_f32_kernel(const float* __restrict__ x, size_t n, unsigned int* __restrict__ slot) {
   float m = 0.f;

@@ -19,6 +19,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import ops
+from .blocks import AttnSaved, AttnWeights, FfnSaved, FfnWeights, attn_block_bwd, attn_block_fwd, ffn_block_bwd, ffn_block_fwd
 
 Tensor = torch.Tensor
 ALIGN = 64  # elements
@@ -112,16 +113,14 @@ class FlatParams:
 
 @dataclass
 class LayerViews:
-    wqkv: Tensor; bqkv: Tensor; wo: Tensor; bo: Tensor; g1: Tensor; b1: Tensor
-    w1: Tensor; bf1: Tensor; w2: Tensor; bf2: Tensor; g2: Tensor; b2: Tensor
+    attn: AttnWeights
+    ffn: FfnWeights
 
 
 @dataclass
 class LayerSaved:
-    x_in: Tensor = None; qkv: Tensor = None; ctx: Tensor = None; lse2: Tensor = None
-    pre1: Tensor = None; mean1: Tensor = None; rstd1: Tensor = None; ln1: Tensor = None
-    z: Tensor = None; h: Tensor = None          # z holds gelu'(pre-activation), h = gelu(pre-activation)
-    pre2: Tensor = None; mean2: Tensor = None; rstd2: Tensor = None
+    attn: AttnSaved = None
+    ffn: FfnSaved = None
 
 
 @dataclass
@@ -148,8 +147,9 @@ class EncoderEngine:
         f = self.flat
         w = {"p": f.view16, "g": f.viewg}[kind]
         s = {"p": f.view32, "g": f.viewg}[kind]
-        return LayerViews(wqkv=w(n[0], (n[1], n[2])), bqkv=s(n[3], (n[4], n[5])), wo=w(n[6]), bo=s(n[7]), g1=s(n[8]),
-                          b1=s(n[9]), w1=w(n[10]), bf1=s(n[11]), w2=w(n[12]), bf2=s(n[13]), g2=s(n[14]), b2=s(n[15]))
+        return LayerViews(attn=AttnWeights(wqkv=w(n[0], (n[1], n[2])), bqkv=s(n[3], (n[4], n[5])), wo=w(n[6]), bo=s(n[7]),
+                                           g=s(n[8]), b=s(n[9])),
+                          ffn=FfnWeights(w1=w(n[10]), bf1=s(n[11]), w2=w(n[12]), bf2=s(n[13]), g=s(n[14]), b=s(n[15])))
 
     def layer(self, i):
         return self._lv(i, "p")
@@ -169,38 +169,12 @@ class EncoderEngine:
 
     def layer_forward(self, p: LayerViews, x: Tensor, x32: Tensor, B: int, S: int, key_bias, kv_len, save: bool,
                       want_probs: bool = False):
-        """x: fp16 layer input (GEMM operand), x32: the same activations in fp32 (residual stream: keeping the skip
-        connection un-rounded is what holds the 12-layer hidden-state error under 1e-3)."""
-        H, I, M, dev = self.H, self.I, B * S, x.device
-        f16, f32 = torch.float16, torch.float32
-        sv = LayerSaved() if save else None
-        qkv = torch.empty(M, 3 * H, dtype=f16, device=dev)
-        ops.gemm(x, p.wqkv, qkv, epilogue=ops.EPI_BIAS, bias=p.bqkv)
-        ctx = torch.empty(M, H, dtype=f16, device=dev)
-        lse2 = torch.empty(B, self.heads, S, dtype=f32, device=dev) if (save or want_probs) else None
-        ops.attn_fwd(qkv, qkv, ctx, B, self.heads, S, S, q_col0=0, k_col0=H, v_col0=2 * H, key_bias=key_bias, kv_len=kv_len,
-                     lse2=lse2)
-        probs = ops.attn_probs(qkv, qkv, lse2, B, self.heads, S, S, q_col0=0, k_col0=H, key_bias=key_bias) if want_probs else None
-        pre1 = torch.empty(M, H, dtype=f32, device=dev)
-        ops.gemm(ctx, p.wo, pre1, epilogue=ops.EPI_BIAS_RES32, bias=p.bo, aux=x32)
-        mean1 = torch.empty(M, dtype=f32, device=dev) if save else None
-        rstd1 = torch.empty(M, dtype=f32, device=dev) if save else None
-        ln1_32 = torch.empty(M, H, dtype=f32, device=dev)
-        ln1 = ops.layernorm_fwd(pre1, p.g1, p.b1, self.eps, y32=ln1_32, mean=mean1, rstd=rstd1)
-        h = torch.empty(M, I, dtype=f16, device=dev)
-        z = torch.empty(M, I, dtype=f16, device=dev) if save else None
-        ops.gemm(ln1, p.w1, h, epilogue=ops.EPI_BIAS_GELU, bias=p.bf1, out2=z)
-        pre2 = torch.empty(M, H, dtype=f32, device=dev)
-        ops.gemm(h, p.w2, pre2, epilogue=ops.EPI_BIAS_RES32, bias=p.bf2, aux=ln1_32)
-        mean2 = torch.empty(M, dtype=f32, device=dev) if save else None
-        rstd2 = torch.empty(M, dtype=f32, device=dev) if save else None
-        out32 = torch.empty(M, H, dtype=f32, device=dev)
-        out = ops.layernorm_fwd(pre2, p.g2, p.b2, self.eps, y32=out32, mean=mean2, rstd=rstd2)
-        if save:
-            sv.x_in, sv.qkv, sv.ctx, sv.lse2 = x, qkv, ctx, lse2
-            sv.pre1, sv.mean1, sv.rstd1, sv.ln1 = pre1, mean1, rstd1, ln1
-            sv.z, sv.h, sv.pre2, sv.mean2, sv.rstd2 = z, h, pre2, mean2, rstd2
-        return out, out32, sv, probs
+        """One BertLayer (bert_model.py:518-553).  x: fp16 layer input (GEMM operand), x32: the same activations in fp32
+        (residual stream: keeping the skip connection un-rounded holds the 12-layer hidden-state error under 1e-3)."""
+        a16, a32, sva, probs = attn_block_fwd(p.attn, x, x32, B, S, self.heads, self.eps, key_bias, kv_len, save=save,
+                                              want_probs=want_probs)
+        y16, y32, svf = ffn_block_fwd(p.ffn, a16, a32, self.eps, save=save)
+        return y16, y32, (LayerSaved(attn=sva, ffn=svf) if save else None), probs
 
     def forward(self, ids, tt, pos, inputs_embeds, key_bias, kv_len, B: int, S: int, *, save: bool,
                 want_hidden: bool = False, want_probs: bool = False):
@@ -225,36 +199,8 @@ class EncoderEngine:
                        inv_scale: Optional[Tensor], ws: Tensor) -> Tensor:
         """dy: fp16 gradient wrt the layer output (scaled by the loss scale).  Weight/bias/LN gradients are accumulated
         (+=) into the fp32 views `g`, multiplied by *inv_scale.  Returns the gradient wrt the layer input."""
-        H, I, M, dev = self.H, self.I, B * S, dy.device
-        f16 = torch.float16
-        # output LayerNorm  <- BertOutput (bert_model.py:449-453)
-        d_pre2 = torch.empty(M, H, dtype=f16, device=dev)
-        ops.layernorm_bwd(dy, sv.pre2, sv.mean2, sv.rstd2, p.g2, d_pre2, g.g2, g.b2, dbias=g.bf2, alpha=inv_scale)
-        ops.gemm(d_pre2, sv.h, g.w2, a_layout=1, b_layout=1, epilogue=ops.EPI_ATOMIC, alpha=inv_scale,
-                 k_splits=ops.wgrad_splits(H, I, M))
-        dz = torch.empty(M, I, dtype=f16, device=dev)
-        ops.gemm(d_pre2, p.w2, dz, b_layout=1, epilogue=ops.EPI_DGELU, aux=sv.z)
-        ops.colsum(dz, g.bf1, inv_scale)
-        ops.gemm(dz, sv.ln1, g.w1, a_layout=1, b_layout=1, epilogue=ops.EPI_ATOMIC, alpha=inv_scale,
-                 k_splits=ops.wgrad_splits(I, H, M))
-        d_ln1 = torch.empty(M, H, dtype=f16, device=dev)
-        ops.gemm(dz, p.w1, d_ln1, b_layout=1, epilogue=ops.EPI_ADD, aux=d_pre2)
-        # attention output LayerNorm  <- BertSelfOutput (:371-375)
-        d_pre1 = torch.empty(M, H, dtype=f16, device=dev)
-        ops.layernorm_bwd(d_ln1, sv.pre1, sv.mean1, sv.rstd1, p.g1, d_pre1, g.g1, g.b1, dbias=g.bo, alpha=inv_scale)
-        ops.gemm(d_pre1, sv.ctx, g.wo, a_layout=1, b_layout=1, epilogue=ops.EPI_ATOMIC, alpha=inv_scale,
-                 k_splits=ops.wgrad_splits(H, H, M))
-        dctx = torch.empty(M, H, dtype=f16, device=dev)
-        ops.gemm(d_pre1, p.wo, dctx, b_layout=1)
-        # attention core (:309-350)
-        dqkv = torch.empty(M, 3 * H, dtype=f16, device=dev)
-        ops.attn_bwd(sv.qkv, sv.qkv, dctx, sv.ctx, sv.lse2, dqkv, dqkv, ws, B, self.heads, S, S, q_col0=0, k_col0=H,
-                     v_col0=2 * H, dq_col0=0, dk_col0=H, dv_col0=2 * H, key_bias=key_bias, kv_len=kv_len)
-        ops.colsum(dqkv, g.bqkv, inv_scale)
-        ops.gemm(dqkv, sv.x_in, g.wqkv, a_layout=1, b_layout=1, epilogue=ops.EPI_ATOMIC, alpha=inv_scale,
-                 k_splits=ops.wgrad_splits(3 * H, H, M))
-        dx = torch.empty(M, H, dtype=f16, device=dev)
-        ops.gemm(dqkv, p.wqkv, dx, b_layout=1, epilogue=ops.EPI_ADD, aux=d_pre1)
+        d_attn_out = ffn_block_bwd(p.ffn, g.ffn, sv.ffn, dy, inv_scale)
+        dx, _ = attn_block_bwd(p.attn, g.attn, sv.attn, d_attn_out, B, S, self.heads, key_bias, kv_len, inv_scale, ws)
         return dx
 
     def backward(self, saved: Saved, dy: Tensor, inv_scale: Optional[Tensor], *, embeddings: bool = True,

@@ -36,6 +36,7 @@ _PROTOS = {
     "b200_cast_f32_to_f16": [_p, _p, _sz, _p],
     "b200_cast_f16_to_f32": [_p, _p, _sz, _p],
     "b200_scale_cast_grad": [_p, _p, _sz, _f, _p, _p, _p],
+    "b200_unscale_cast_grad": [_p, _p, _sz, _p, _p],
     "b200_attn_bwd_workspace": [_i, _i, _i],
     "b200_attn_bwd": [_p, _i, _i, _p, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "b200_grad_sumsq": [_p, _sz, _p, _p],

@@ -233,3 +233,9 @@ def adamw_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, p16: Optional[Tensor]
     rc = L.load().b200_adamw_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(p16), p.numel(), lr, beta1, beta2, eps, weight_decay,
                                   bc1, bc2, _ptr(coef), _stream())
     L.check(rc, "b200_adamw_step")
+
+
+def unscale_cast_grad(src: Tensor, dst: Tensor, scale: Optional[Tensor]) -> Tensor:
+    """dst(fp32) = src(fp16) * scale[1]."""
+    L.check(L.load().b200_unscale_cast_grad(_ptr(src), _ptr(dst), src.numel(), _ptr(scale), _stream()), "b200_unscale_cast_grad")
+    return dst

@@ -1,0 +1,49 @@
+"""Find the first kernel whose output for rows [0,2) differs between a [32,512] and a [2,512] batch."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from transformers import BertConfig  # noqa: E402
+
+from spokennlp_b200 import BertModel, ops  # noqa: E402
+
+torch.manual_seed(0)
+kw = dict(hidden_size=768, num_attention_heads=12, intermediate_size=3072, num_hidden_layers=2, vocab_size=30523,
+          max_position_embeddings=512, type_vocab_size=2)
+m = BertModel(BertConfig(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, **kw)).cuda().eval()
+gen = torch.Generator().manual_seed(4)
+ids = torch.randint(1000, 30522, (32, 512), generator=gen).cuda()
+mask = torch.ones(32, 512, dtype=torch.long)
+mask[1, 300:] = 0
+mask[5, 17:] = 0
+mask = mask.cuda()
+eng = m.b200_engine()
+
+
+def run(n):
+    kb, kl = ops.mask_to_bias(mask[:n].contiguous())
+    out = eng.forward(ids[:n].contiguous().view(-1), None, None, None, kb, kl, n, 512, save=True)
+    torch.cuda.synchronize()
+    return out
+
+
+for impl in (2, 1):
+    ops.set_gemm_impl(impl)
+    _, _, big, _, _ = run(32)
+    _, _, small, _, _ = run(2)
+    print("gemm impl", impl)
+    for li, (lb, ls) in enumerate(zip(big.layers, small.layers)):
+        for blk in ("attn", "ffn"):
+            sb, ss = getattr(lb, blk), getattr(ls, blk)
+            for name in ("x16", "q", "ctx", "lse2", "pre", "mean", "dact", "h"):
+                tb, ts = getattr(sb, name, None), getattr(ss, name, None)
+                if tb is None:
+                    continue
+                if name == "lse2":
+                    tb, ts = tb[:2], ts
+                else:
+                    tb = tb[:ts.shape[0]]
+                d = float((tb.float() - ts.float()).abs().max())
+                print(f"  layer {li} {blk:4s} {name:5s} max|diff| = {d:.3e}")
