@@ -192,8 +192,9 @@ int b200_gemm_f16(const void* A, int lda, int a_layout, const void* B, int ldb, 
     if ((rc = get_tmap(out, M, N, ld_out, 32, &mp.out, o32))) return rc;
     mp.aux = mp.out;
     mp.out2 = mp.out;
-    if (needs_aux && (rc = get_tmap(aux, M, N, ld_aux, 32, &mp.aux, epilogue == EPI_BIAS_RES32))) return rc;
-    if (epilogue == EPI_BIAS_GELU && out2 && (rc = get_tmap(out2, M, N, ld_out2, 32, &mp.out2))) return rc;
+    if ((needs_aux || out2) && ((N % 8) || (needs_aux && (ld_aux * (epilogue == EPI_BIAS_RES32 ? 4 : 2)) % 16) || (out2 && (ld_out2 % 8)) ||
+                                (needs_aux && (reinterpret_cast<uintptr_t>(aux) & 15)) || (out2 && (reinterpret_cast<uintptr_t>(out2) & 15))))
+      return fail(B200_ERR_SHAPE, "gemm: aux / out2 need N %% 8 == 0 and 16-byte aligned rows");
     GemmArgs g2{M, N, K, k_splits > 0 ? k_splits : 1, bias, static_cast<const __half*>(aux), ld_aux, out, ld_out,
                 static_cast<__half*>(out2), ld_out2, alpha, g_gemm_dbg.load()};
     switch (a_layout * 1000 + b_layout * 100 + epilogue * 10 + out_dtype) {

@@ -9,8 +9,8 @@
 //   * accumulators: 2 x 256 TMEM columns per CTA (epilogue of tile i overlaps the mainloop of tile i+1);
 //   * epilogue: eight warps per CTA (two per TMEM lane quadrant), one thread per accumulator row: TMEM -> registers -> bias / GELU / residual /
 //     dGELU math -> fp16/fp32 128B-swizzled staging rows -> TMA store (or TMA reduce-add for split-K wgrad).
-//     Auxiliary row-major inputs (residual, pre-activation) arrive by TMA into the same swizzled staging geometry, so
-//     no thread issues an uncoalesced global access and the aux fetch of chunk c+1 overlaps the math of chunk c.
+//     Auxiliary row-major inputs (residual, saved activation derivative) are read 128 contiguous bytes per thread
+//     straight into registers one chunk ahead of their use.
 #pragma once
 #include "gemm.cuh"
 
@@ -20,16 +20,14 @@ constexpr int G2_THREADS = 320;           // warp 0 TMA, warp 1 MMA, warps 2..9 
 constexpr int G2_BM = 256;                // rows per CTA pair
 constexpr int G2_SMEM_MAX = 232448;       // 227 KB opt-in limit per CTA
 
-// Shared-memory plan: the operand ring takes whatever the epilogue staging of this variant leaves free
-// (6 stages for plain epilogues, 5 when a residual / pre-activation slab pair is needed).
+// Shared-memory plan: 8 epilogue warps x 2 output slabs (64 KB); the operand ring takes the rest (5 stages of 32 KB).
 template <int BN, int EPI>
 struct Gemm2Smem {
   static constexpr int A_BYTES = 128 * GEMM_BK * 2;          // 16 KB : this CTA's 128 rows of A
   static constexpr int B_BYTES = (BN / 2) * GEMM_BK * 2;     // 16 KB : this CTA's half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int SLAB = 32 * 128;                      // 4 KB : 32 rows x 128 B staging slab
-  static constexpr bool AUX = EPI == EPI_BIAS_RES || EPI == EPI_BIAS_RES32 || EPI == EPI_DGELU || EPI == EPI_ADD;
-  static constexpr int SLABS = 1 + (AUX ? 1 : 0) + (EPI == EPI_BIAS_GELU ? 1 : 0);   // out [, aux] [, out2], single-buffered
+  static constexpr int SLABS = 2;                             // double-buffered output slab per epilogue warp
   static constexpr int EPI_PER_WARP = SLABS * SLAB;
   static constexpr int EPI_WARPS = 8;
   static constexpr int STAGES = (G2_SMEM_MAX - 1024 - 512 - EPI_WARPS * EPI_PER_WARP) / STAGE_BYTES;
@@ -130,8 +128,7 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
   uint64_t* empty_bar = full_bar + G2_STAGES;
   uint64_t* tfull_bar = empty_bar + G2_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* aux_bar = tempty_bar + 2;                 // [8 warps]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 8);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -149,7 +146,6 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
     tma_prefetch_desc(&maps.a);
     tma_prefetch_desc(&maps.b);
     tma_prefetch_desc(&maps.out);
-    if (HAS_AUX) tma_prefetch_desc(&maps.aux);
     for (int i = 0; i < G2_STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -158,7 +154,6 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 16);              // 8 epilogue warps x 2 CTAs (only the leader's copy is used)
     }
-    for (int i = 0; i < 8; ++i) mbar_init(&aux_bar[i], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -254,32 +249,49 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..9, both CTAs)
-    // Two warps per TMEM lane quadrant: warp (q, half) owns rows 32q..32q+31 and one half of the tile's columns.
-    // Eight warps (two per SM sub-partition) keep the FP32 pipes busy through the dependent erf / exp chains.
+    // Two warps per TMEM lane quadrant: warp (q, half) owns rows 32q..32q+31 and one half of the tile's columns; one
+    // thread per accumulator row.  Outputs leave through double-buffered swizzled slabs + TMA store (asynchronous,
+    // fully coalesced).  Auxiliary inputs (residual / saved activation derivative) are fetched straight into registers,
+    // 128 contiguous bytes per thread, one chunk AHEAD of their use, so their latency hides behind the math of the
+    // current chunk without costing shared memory.
     const int q = warp & 3;                               // TMEM lane quadrant
     const int ew = warp - 2;                              // 0..7
     const int half = ew >> 2;                             // which half of the BN columns
-    uint8_t* slabs = smem + S::OFF_EPI + ew * S::EPI_PER_WARP;
-    uint8_t* out_s = slabs;                               // output slab
-    uint8_t* aux_s = slabs + S::SLAB;                     // auxiliary-input slab (variants with aux)
-    uint8_t* out2_s = slabs + S::SLAB;                    // pre-activation slab (GELU variant)
-    uint64_t* my_aux_bar = aux_bar + ew;
+    uint8_t* out_s = smem + S::OFF_EPI + ew * S::EPI_PER_WARP;      // 2 slabs
     const uint32_t tempty0[2] = {mapa_u32(smem_u32(&tempty_bar[0]), 0), mapa_u32(smem_u32(&tempty_bar[1]), 0)};
     const float alpha = g.alpha ? __ldg(g.alpha) : 1.0f;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    uint32_t acc = 0, acc_phase = 0;
-    uint32_t aux_uses = 0;                                // parity of the aux barrier = aux_uses & 1
+    uint32_t acc = 0, acc_phase = 0, out_uses = 0;
     constexpr int NCH = BN / CW / 2;                      // chunks per warp per tile
-    for (int u = pair; u < units; u += n_pairs) {
+    constexpr int AUX_ESZ = EPI == EPI_BIAS_RES32 ? 4 : 2;
+    auto tile_origin = [&](int u, int& row0, int& col0, bool& has_data) {
       int mt, nt, kb0, kb1;
       decode(u, mt, nt, kb0, kb1);
-      const int row0 = mt * G2_BM + static_cast<int>(rank) * 128 + q * 32;     // first output row of this warp
-      const int col0 = nt * BN + half * (BN / 2);                               // first output column of this warp
-      const bool has_data = kb1 > kb0;
-      if (HAS_AUX && lane == 0) {                         // aux slab of the first chunk (lands while the mainloop runs)
-        mbar_expect_tx(my_aux_bar, S::SLAB);
-        tma_load_2d(aux_s, &maps.aux, my_aux_bar, col0, row0);
+      row0 = mt * G2_BM + static_cast<int>(rank) * 128 + q * 32;      // first output row of this warp
+      col0 = nt * BN + half * (BN / 2);                               // first output column of this warp
+      has_data = kb1 > kb0;
+    };
+    // 128 bytes of this thread's aux row for the chunk starting at column gc0 (zeros outside the matrix)
+    auto load_aux = [&](uint4 (&dst)[8], int row, int gc0) {
+      const char* base = reinterpret_cast<const char*>(g.aux) + (static_cast<size_t>(row) * g.ld_aux + gc0) * AUX_ESZ;
+      const bool row_ok = row < g.M;
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        const bool ok = row_ok && (gc0 + ch * (16 / AUX_ESZ)) < g.N;
+        dst[ch] = ok ? __ldg(reinterpret_cast<const uint4*>(base) + ch) : make_uint4(0, 0, 0, 0);
       }
+    };
+    uint4 aux_next[8];
+    if (HAS_AUX && pair < units) {
+      int r0, c0;
+      bool hd;
+      tile_origin(pair, r0, c0, hd);
+      load_aux(aux_next, r0 + lane, c0);
+    }
+    for (int u = pair; u < units; u += n_pairs) {
+      int row0, col0;
+      bool has_data;
+      tile_origin(u, row0, col0, has_data);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
@@ -290,16 +302,16 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
         for (int i = 0; i < CW / 32; ++i)
           tmem_ld_x32(tmem_base + lane_addr + acc * BN + half * (BN / 2) + c * CW + i * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[i * 32]));
         uint4 araw[8];
-        if (HAS_AUX) {                                    // consume the aux slab, then refill it for the next chunk
-          mbar_wait(my_aux_bar, aux_uses & 1);
-          ++aux_uses;
-          const uint32_t as = smem_u32(aux_s);
+        if (HAS_AUX) {
 #pragma unroll
-          for (int ch = 0; ch < 8; ++ch) araw[ch] = lds128(slab_chunk(as, lane, ch));
-          __syncwarp();
-          if (c + 1 < NCH && lane == 0) {
-            mbar_expect_tx(my_aux_bar, S::SLAB);
-            tma_load_2d(aux_s, &maps.aux, my_aux_bar, gc0 + CW, row0);
+          for (int ch = 0; ch < 8; ++ch) araw[ch] = aux_next[ch];
+          if (c + 1 < NCH) {
+            load_aux(aux_next, row0 + lane, gc0 + CW);
+          } else if (u + n_pairs < units) {               // first chunk of this warp's next tile
+            int r1, c1;
+            bool hd;
+            tile_origin(u + n_pairs, r1, c1, hd);
+            load_aux(aux_next, r1 + lane, c1);
           }
         }
         tmem_wait_ld();
@@ -341,9 +353,9 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
             }
           }
         }
-        uint32_t ow[CW / 2 < 32 ? 32 : CW / 2];          // packed output words of this thread's row segment
-        uint32_t zw[EPI == EPI_BIAS_GELU ? 32 : 1];
+        uint32_t ow[32];                                  // packed output words of this thread's 128-byte row segment
         if (EPI == EPI_BIAS_GELU) {
+          uint32_t zw[32];
 #pragma unroll
           for (int k = 0; k < 32; ++k) {
             float y0, y1, d0, d1;
@@ -352,6 +364,12 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
             const __half2 hz = __floats2half2_rn(d0, d1), hh = __floats2half2_rn(y0, y1);
             zw[k] = *reinterpret_cast<const uint32_t*>(&hz);
             ow[k] = *reinterpret_cast<const uint32_t*>(&hh);
+          }
+          if (g.out2 && has_data && row0 + lane < g.M) {  // saved derivative: 128 contiguous bytes per thread, fire-and-forget
+            uint4* dst = reinterpret_cast<uint4*>(g.out2 + static_cast<size_t>(row0 + lane) * g.ld_out2 + gc0);
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch)
+              if (gc0 + ch * 8 < g.N) dst[ch] = make_uint4(zw[4 * ch], zw[4 * ch + 1], zw[4 * ch + 2], zw[4 * ch + 3]);
           }
         } else if (OUT32) {
 #pragma unroll
@@ -363,28 +381,23 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
             ow[k] = *reinterpret_cast<const uint32_t*>(&hv);
           }
         }
-        // the slab is single-buffered: the TMA store issued for the previous chunk must have finished reading it
-        // (it was issued a whole chunk of math ago, so this wait is normally free)
-        if (lane == 0) tma_wait_group_read<0>();
+        // double-buffered slab: the TMA store issued two chunks ago must have finished reading this buffer
+        uint8_t* os_ptr = out_s + (out_uses & 1) * S::SLAB;
+        if (lane == 0) tma_wait_group_read<1>();
         __syncwarp();
-        const uint32_t os = smem_u32(out_s);
+        const uint32_t os = smem_u32(os_ptr);
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) sts128(slab_chunk(os, lane, ch), ow[4 * ch], ow[4 * ch + 1], ow[4 * ch + 2], ow[4 * ch + 3]);
-        if (EPI == EPI_BIAS_GELU) {
-          const uint32_t zs = smem_u32(out2_s);
-#pragma unroll
-          for (int ch = 0; ch < 8; ++ch) sts128(slab_chunk(zs, lane, ch), zw[4 * ch], zw[4 * ch + 1], zw[4 * ch + 2], zw[4 * ch + 3]);
-        }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
           if (has_data && !(g.dbg & 8)) {
-            if (EPI == EPI_ATOMIC) tma_reduce_add_2d(&maps.out, out_s, gc0, row0);
-            else tma_store_2d(&maps.out, out_s, gc0, row0);
-            if (EPI == EPI_BIAS_GELU && g.out2) tma_store_2d(&maps.out2, out2_s, gc0, row0);
+            if (EPI == EPI_ATOMIC) tma_reduce_add_2d(&maps.out, os_ptr, gc0, row0);
+            else tma_store_2d(&maps.out, os_ptr, gc0, row0);
           }
           tma_commit_group();
         }
+        ++out_uses;
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
