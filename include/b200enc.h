@@ -113,6 +113,17 @@ int b200_ce_stats(const float* logits, const int64_t* labels, const float* class
 int b200_cls_head_bwd(const void* h, const float* logits, const int64_t* labels, const float* class_weight, const float* stats,
                       const float* W, const float* scale, void* dh, float* dW, float* db, int rows, int H, int C, void* stream);
 
+/*
+ * PoNet pooling mixer forward (PoNetSelfAttention of modelscope 1.1.0, called at alimeeting4mug/src/models/modeling_ponet.py:68-79;
+ * algorithm restated in oracle/ponet_oracle.py — source absent, parity unpinned).  proj: fp16 [B*S, ld] holding the five
+ * projections [Q | K | O | Sg | Lc] (5H columns); key_bias: optional [B,S] (non-zero = padding); segment_ids int64 [B,S],
+ * monotone, values in [0, nseg).  out: fp16 [B*S, H] = (global + segment-max) * O + local-max3, zero on padding.
+ * workspace: caller-owned, b200_ponet_workspace() bytes.
+ */
+size_t b200_ponet_workspace(int B, int S, int H, int heads, int nseg);
+int b200_ponet_mix_fwd(const void* proj, int ld, const float* key_bias, const int64_t* segment_ids, void* workspace, void* out, int B, int S,
+                       int H, int heads, int nseg, void* stream);
+
 /* db[n] += *alpha * sum_m dy[m,n]   (bias gradients) */
 int b200_colsum(const void* dy, int ld, float* db, const float* alpha, int rows, int cols, void* stream);
 

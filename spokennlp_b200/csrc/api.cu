@@ -13,6 +13,7 @@
 #include "gemm.cuh"
 #include "gemm2.cuh"
 #include "optim.cuh"
+#include "ponet.cuh"
 #include "rowwise.cuh"
 
 using namespace b200;
@@ -192,6 +193,7 @@ int b200_gemm_f16(const void* A, int lda, int a_layout, const void* B, int ldb, 
     if ((rc = get_tmap(out, M, N, ld_out, 32, &mp.out, o32))) return rc;
     mp.aux = mp.out;
     mp.out2 = mp.out;
+    if (epilogue == EPI_BIAS_GELU && out2 && (rc = get_tmap(out2, M, N, ld_out2, 32, &mp.out2))) return rc;
     if ((needs_aux || out2) && ((N % 8) || (needs_aux && (ld_aux * (epilogue == EPI_BIAS_RES32 ? 4 : 2)) % 16) || (out2 && (ld_out2 % 8)) ||
                                 (needs_aux && (reinterpret_cast<uintptr_t>(aux) & 15)) || (out2 && (reinterpret_cast<uintptr_t>(out2) & 15))))
       return fail(B200_ERR_SHAPE, "gemm: aux / out2 need N %% 8 == 0 and 16-byte aligned rows");
@@ -454,6 +456,52 @@ int b200_scale_cast_grad(const float* src, void* dst, size_t n, float target, fl
   if (int rc = check_launch("pick_scale_kernel")) return rc;
   scale_cast_f32_f16_kernel<<<stream_grid(n / 8), 256, 0, s>>>(src, scale, static_cast<__half*>(dst), n / 8);
   return check_launch("scale_cast_f32_f16_kernel");
+}
+
+}  // extern "C"
+
+namespace {
+__global__ void fill_f32_kernel(float* p, float v, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) p[i] = v;
+}
+}  // namespace
+
+extern "C" {
+
+size_t b200_ponet_workspace(int B, int S, int H, int heads, int nseg) {
+  const size_t nchunks = (S + 127) / 128;
+  return (static_cast<size_t>(B) * H * 2 + B + static_cast<size_t>(B) * heads * nchunks * 66 + static_cast<size_t>(B) * nseg * H) * sizeof(float) + 256;
+}
+
+int b200_ponet_mix_fwd(const void* proj, int ld, const float* key_bias, const int64_t* segment_ids, void* workspace, void* out, int B, int S,
+                       int H, int heads, int nseg, void* stream) {
+  if (B <= 0 || S <= 0 || H != heads * 64 || (H % 8) || (ld % 8) || nseg <= 0) return fail(B200_ERR_SHAPE, "ponet_mix_fwd: bad shape");
+  if (!proj || !segment_ids || !workspace || !out) return fail(B200_ERR_SHAPE, "ponet_mix_fwd: null pointer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int nchunks = (S + 127) / 128;
+  float* qsum = static_cast<float*>(workspace);
+  float* cnt = qsum + static_cast<size_t>(B) * H;
+  float* g = cnt + ((B + 3) / 4) * 4;
+  float* part = g + static_cast<size_t>(B) * H;
+  float* segmax = part + static_cast<size_t>(B) * heads * nchunks * 66;
+  segmax += (4 - (reinterpret_cast<uintptr_t>(segmax) / 4) % 4) % 4;      // 16-byte alignment for 128-bit loads
+  cudaMemsetAsync(qsum, 0, (static_cast<size_t>(B) * H + ((B + 3) / 4) * 4) * sizeof(float), s);
+  const size_t nsm = static_cast<size_t>(B) * nseg * H;
+  fill_f32_kernel<<<static_cast<int>((nsm + 255) / 256 < 2368 ? (nsm + 255) / 256 : 2368), 256, 0, s>>>(segmax, -INFINITY, nsm);
+  int rc;
+  if ((rc = check_launch("fill_f32_kernel"))) return rc;
+  const __half* p = static_cast<const __half*>(proj);
+  ponet_qsum_kernel<<<dim3(nchunks, B), H / 8, 0, s>>>(p, ld, key_bias, qsum, cnt, S, H);
+  if ((rc = check_launch("ponet_qsum_kernel"))) return rc;
+  ponet_global_part_kernel<<<dim3(nchunks, heads, B), 128, 0, s>>>(p, ld, key_bias, qsum, cnt, part, S, H, heads);
+  if ((rc = check_launch("ponet_global_part_kernel"))) return rc;
+  ponet_global_comb_kernel<<<dim3(heads, B), 64, 0, s>>>(part, g, nchunks, H, heads);
+  if ((rc = check_launch("ponet_global_comb_kernel"))) return rc;
+  ponet_segmax_kernel<<<dim3((S + 63) / 64, B), H / 8, 0, s>>>(p, ld, key_bias, segment_ids, segmax, S, H, nseg);
+  if ((rc = check_launch("ponet_segmax_kernel"))) return rc;
+  ponet_mix_kernel<<<(B * S + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, s>>>(p, ld, key_bias, segment_ids, g, segmax,
+                                                                                 static_cast<__half*>(out), B, S, H, nseg);
+  return check_launch("ponet_mix_kernel");
 }
 
 }  // extern "C"

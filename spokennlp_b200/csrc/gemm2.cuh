@@ -365,12 +365,26 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
             zw[k] = *reinterpret_cast<const uint32_t*>(&hz);
             ow[k] = *reinterpret_cast<const uint32_t*>(&hh);
           }
-          if (g.out2 && has_data && row0 + lane < g.M) {  // saved derivative: 128 contiguous bytes per thread, fire-and-forget
-            uint4* dst = reinterpret_cast<uint4*>(g.out2 + static_cast<size_t>(row0 + lane) * g.ld_out2 + gc0);
+          // GELU variant: slab 0 carries h, slab 1 the saved derivative, both single-buffered — the erf math of the next
+          // chunk (microseconds) separates a TMA store from the next write to its slab, so the wait below is free.
+          if (lane == 0) tma_wait_group_read<0>();
+          __syncwarp();
+          const uint32_t hs = smem_u32(out_s), ds = smem_u32(out_s + S::SLAB);
 #pragma unroll
-            for (int ch = 0; ch < 8; ++ch)
-              if (gc0 + ch * 8 < g.N) dst[ch] = make_uint4(zw[4 * ch], zw[4 * ch + 1], zw[4 * ch + 2], zw[4 * ch + 3]);
+          for (int ch = 0; ch < 8; ++ch) {
+            sts128(slab_chunk(hs, lane, ch), ow[4 * ch], ow[4 * ch + 1], ow[4 * ch + 2], ow[4 * ch + 3]);
+            sts128(slab_chunk(ds, lane, ch), zw[4 * ch], zw[4 * ch + 1], zw[4 * ch + 2], zw[4 * ch + 3]);
           }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (has_data && !(g.dbg & 8)) {
+              tma_store_2d(&maps.out, out_s, gc0, row0);
+              if (g.out2) tma_store_2d(&maps.out2, out_s + S::SLAB, gc0, row0);
+            }
+            tma_commit_group();
+          }
+          continue;
         } else if (OUT32) {
 #pragma unroll
           for (int k = 0; k < 32; ++k) ow[k] = __float_as_uint(f[k]);

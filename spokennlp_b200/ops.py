@@ -239,3 +239,16 @@ def unscale_cast_grad(src: Tensor, dst: Tensor, scale: Optional[Tensor]) -> Tens
     """dst(fp32) = src(fp16) * scale[1]."""
     L.check(L.load().b200_unscale_cast_grad(_ptr(src), _ptr(dst), src.numel(), _ptr(scale), _stream()), "b200_unscale_cast_grad")
     return dst
+
+
+def ponet_mix_fwd(proj: Tensor, seg_ids: Tensor, out: Tensor, B: int, S: int, heads: int, nseg: int, *,
+                  key_bias: Optional[Tensor] = None) -> Tensor:
+    """PoNet pooling mixer on the packed projections [B*S, 5H] = [Q | K | O | Sg | Lc] (oracle/ponet_oracle.py)."""
+    _req(proj, torch.float16, "proj"), _req(out, torch.float16, "out")
+    H = heads * 64
+    nbytes = int(L.load().b200_ponet_workspace(B, S, H, heads, nseg))
+    ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=proj.device)
+    rc = L.load().b200_ponet_mix_fwd(_ptr(proj), proj.stride(0), _ptr(key_bias), _ptr(seg_ids), _ptr(ws), _ptr(out), B, S, H, heads, nseg,
+                                     _stream())
+    L.check(rc, "b200_ponet_mix_fwd")
+    return out
