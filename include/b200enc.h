@@ -156,6 +156,12 @@ int b200_grad_sumsq(const float* g, size_t n, float* sumsq, void* stream);
 int b200_clip_coef(const float* sumsq, float max_norm, float grad_mult, float* coef, void* stream);
 int b200_adamw_step(float* p, const float* g, float* m, float* v, void* p16, size_t n, float lr, float beta1, float beta2, float eps,
                     float weight_decay, float bias_corr1, float bias_corr2, const float* coef, void* stream);
+/* Same with the hyper-parameters {lr, beta1, beta2, eps, weight_decay, bias_corr1, bias_corr2, -} read from device memory, so a
+ * captured CUDA graph of the whole step can be replayed while the schedule advances (b200_set_hyper runs outside the graph). */
+int b200_set_hyper(float* hyper, float lr, float beta1, float beta2, float eps, float weight_decay, float bias_corr1, float bias_corr2,
+                   void* stream);
+int b200_adamw_step_dev(float* p, const float* g, float* m, float* v, void* p16, size_t n, const float* hyper, const float* coef,
+                        void* stream);
 
 #ifdef __cplusplus
 }

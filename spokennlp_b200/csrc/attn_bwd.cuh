@@ -32,6 +32,7 @@ struct AttnBwdArgs {
   int ld_dkv, dk_col0, dv_col0;
   float scale_log2;                 // log2(e)/sqrt(d)
   float inv_sqrt_d;
+  int dbg;                          // measurement knobs: 0x10000 skip dQ reductions, 0x20000 skip gradient MMAs, 0x40000 skip exp math
 };
 
 struct AttnBwdSmem {
@@ -159,6 +160,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       if (lane == 0) {
         const uint32_t qa = smem_u32(smem + S::OFF_QDO + st * 2 * S::T), doa = qa + S::T;
+        if (!(a.dbg & 0x20000)) {
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)        // dV += P^T dO
           umma_ss(tmem + 256, make_smem_desc(pa + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024), make_smem_desc(doa + kk * 2048, 8192, 1024),
@@ -170,6 +172,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)        // dQ_i = dS K   (A = dS^T tile viewed MN-major: M = query, K = key rows)
           umma_ss(tmem + 384, make_smem_desc(dsa + kk * 2048, 16384, 1024), make_smem_desc(ka + kk * 2048, 8192, 1024), idesc_q, kk > 0);
+        }
         umma_commit(&qdo_empty[st]);
         umma_commit(grad_done);
       }
@@ -194,7 +197,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       uint32_t o[32];
       tmem_ld_x32(tmem + lane_addr + 384 + half * 32, o);
       tmem_wait_ld();
-      if (q < a.Sq) {
+      if (q < a.Sq && !(a.dbg & 0x10000)) {
         float* dst = a.dq_acc + (static_cast<size_t>(b) * a.Sq + q) * a.ld_dq + h * ATT_D + half * 32;
 #pragma unroll
         for (int k = 0; k < 8; ++k)
@@ -222,6 +225,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld_x32(tmem + lane_addr + half * 64 + c * 32, sv);
         tmem_ld_x32(tmem + lane_addr + 128 + half * 64 + c * 32, dp);
         tmem_wait_ld();
+        if (a.dbg & 0x40000) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) pk[c * 16 + e] = dk[c * 16 + e] = sv[e] ^ dp[e];
+          continue;
+        }
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
           const int qi = c * 32 + 2 * e;

@@ -76,4 +76,47 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
   }
 }
 
+// hyper = {lr, beta1, beta2, eps, weight_decay, bias_corr1, bias_corr2, -}: device-resident so that a captured CUDA graph
+// of the training step can be replayed with a new learning rate / step count every iteration.
+__global__ void set_hyper_kernel(float* __restrict__ hyper, float a, float b, float c, float d, float e, float f, float g, float h) {
+  hyper[0] = a; hyper[1] = b; hyper[2] = c; hyper[3] = d; hyper[4] = e; hyper[5] = f; hyper[6] = g; hyper[7] = h;
+}
+__global__ void __launch_bounds__(256) adamw_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                        float* __restrict__ v, __half* __restrict__ p16, size_t n4,
+                                                        const float* __restrict__ hyper, const float* __restrict__ coef) {
+  const float lr = hyper[0], beta1 = hyper[1], beta2 = hyper[2], eps = hyper[3], wd = hyper[4], bc1 = hyper[5], bc2 = hyper[6];
+  const float gm = coef ? coef[0] : 1.0f;
+  const bool ok = coef ? coef[1] != 0.f : true;
+  const float step = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    if (ok) {
+      const float4 gv = reinterpret_cast<const float4*>(g)[i];
+      float4 mv = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+      float* pp = &pv.x;
+      const float* gp = &gv.x;
+      float* mp = &mv.x;
+      float* vp = &vv.x;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float gk = gp[k] * gm;
+        mp[k] = fmaf(beta1, mp[k], (1.f - beta1) * gk);
+        vp[k] = fmaf(beta2, vp[k], (1.f - beta2) * gk * gk);
+        const float denom = sqrtf(vp[k]) * inv_sqrt_bc2 + eps;
+        pp[k] = pp[k] * (1.f - lr * wd) - step * mp[k] / denom;
+      }
+      reinterpret_cast<float4*>(p)[i] = pv;
+      reinterpret_cast<float4*>(m)[i] = mv;
+      reinterpret_cast<float4*>(v)[i] = vv;
+    }
+    if (p16) {
+      const __half2 a = __floats2half2_rn(pv.x, pv.y), b2 = __floats2half2_rn(pv.z, pv.w);
+      uint2 o;
+      o.x = *reinterpret_cast<const uint32_t*>(&a);
+      o.y = *reinterpret_cast<const uint32_t*>(&b2);
+      reinterpret_cast<uint2*>(p16)[i] = o;
+    }
+  }
+}
+
 }  // namespace b200

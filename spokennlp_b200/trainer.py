@@ -71,6 +71,10 @@ class DataParallelTrainer:
         self.layer_slices = [(offs[i], offs[i + 1]) for i in range(cfg.num_hidden_layers)]
         self.emb_slice = (0, offs[0])
         self._works = []
+        self.hyper = torch.zeros(8, dtype=torch.float32, device=self.device)
+        self._graph = None
+        self._static = None
+        self.kernels_per_step = 0
 
     # ------------------------------------------------------------------------------------------------------------
     def _allreduce_slice(self, lo: int, hi: int) -> None:
@@ -110,24 +114,75 @@ class DataParallelTrainer:
         self.last_logits = logits
         return self.stats
 
-    def optimizer_step(self) -> None:
+    def _lr(self) -> float:
+        return self.lr * max(0.0, 1.0 - (self.step_idx - 1) / max(1, self.total_steps))     # HF linear schedule, 0 warm-up
+
+    def optimizer_step(self, *, advance: bool = True) -> None:
+        """Global-norm clip + fused AdamW over the flat buffers.  Hyper-parameters are read from device memory
+        (`self.hyper`, written by `_push_hyper`) so the same launches can live inside a captured CUDA graph."""
         for w in self._works:
             w.wait()
         self._works = []
         flat = self.flat
-        self.step_idx += 1
-        lr = self.lr * max(0.0, 1.0 - (self.step_idx - 1) / max(1, self.total_steps))       # HF linear schedule, 0 warm-up
+        if advance:
+            self.step_idx += 1
+            self._push_hyper()
         self.sumsq.zero_()
         ops.grad_sumsq(flat.grad32, self.sumsq)
         ops.clip_coef(self.sumsq, self.coef, self.max_grad_norm, 1.0 / self.world)
-        ops.adamw_step(flat.flat32, flat.grad32, self.m, self.v, flat.flat16, lr=lr, weight_decay=self.wd,
-                       step=self.step_idx, coef=self.coef)
+        ops.adamw_step_dev(flat.flat32, flat.grad32, self.m, self.v, flat.flat16, self.hyper, self.coef)
         flat.version = flat.cur_version()       # the fused step refreshed the fp16 mirror itself
 
+    def _push_hyper(self) -> None:
+        ops.set_hyper(self.hyper, lr=self._lr(), weight_decay=self.wd, step=max(1, self.step_idx))
+
     def step(self, input_ids, attention_mask, token_type_ids, labels) -> torch.Tensor:
+        if self._graph is not None:
+            return self._replay(input_ids, attention_mask, token_type_ids, labels)
         stats = self.forward_backward(input_ids, attention_mask, token_type_ids, labels)
         self.optimizer_step()
         return stats
+
+    # ---- CUDA graph: one launch per step instead of ~270 ---------------------------------------------------------------
+    def capture(self, input_ids, attention_mask, token_type_ids, labels, warmup: int = 2) -> bool:
+        """Capture forward + backward (+ per-layer allreduce) + optimizer of one step for this batch SHAPE into a CUDA
+        graph.  Later `step()` calls copy their batch into the static input buffers and replay.  The learning-rate
+        schedule keeps advancing because AdamW reads its hyper-parameters from device memory.  Returns False (and stays
+        eager) if capture is not possible in this process."""
+        self._static = [t.clone() if t is not None else None for t in (input_ids, attention_mask, token_type_ids, labels)]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        try:
+            with torch.cuda.stream(side):
+                for _ in range(warmup):                       # warm-up off the capture: lazy init, allocator pools, NCCL
+                    self.forward_backward(*self._static)
+                    self.optimizer_step()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            from . import lib as _lib
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(graph):
+                self.forward_backward(*self._static)
+                self.optimizer_step(advance=False)
+            self.kernels_per_step = _lib.launch_count() - n0
+            self._graph = graph
+            return True
+        except Exception as e:  # noqa: BLE001  (capture is an optimisation; the eager path is the same kernels)
+            import warnings
+            warnings.warn(f"CUDA graph capture of the training step failed ({type(e).__name__}: {e}); staying eager")
+            self._graph = None
+            torch.cuda.synchronize()
+            return False
+
+    def _replay(self, input_ids, attention_mask, token_type_ids, labels) -> torch.Tensor:
+        for dst, src in zip(self._static, (input_ids, attention_mask, token_type_ids, labels)):
+            if dst is not None and src is not dst:
+                dst.copy_(src, non_blocking=True)
+        self.step_idx += 1
+        self._push_hyper()
+        self._graph.replay()
+        return self.stats
 
     def loss_value(self) -> float:
         s = self.stats.tolist()     # device -> host read

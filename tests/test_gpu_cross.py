@@ -63,7 +63,12 @@ def test_cross_layer_gradients_match_oracle_autograd():
 
     def check(name, got, ref):
         err = float((got.double().cpu() - ref.double()).norm())
-        assert err <= 1e-2 * float(ref.double().norm()) + 1e-5, (name, err, float(ref.norm()))
+        scale = float(ref.double().norm())
+        if name.endswith("key.bias"):
+            # mathematically zero (softmax is shift-invariant per query row): both sides hold rounding noise, so the bound
+            # is relative to the query-bias gradient of the same block, a non-degenerate quantity of the same construction
+            scale = float(sd[name.replace("key.bias", "query.bias")].grad.double().norm())
+        assert err <= 1e-2 * scale + 1e-5, (name, err, scale)
     check("x", xg.grad, x.grad)
     check("kv", kvg.grad, kv.grad)
     for k, p in cl.named_parameters():

@@ -54,4 +54,5 @@ def test_ponet_model_forward_matches_restatement():
     for a, b in zip(out.hidden_states, ref):
         assert rel_err(a.cpu()[keep], b[keep]) < 1e-3
     tup = m(ids.cuda(), attention_mask=mask.cuda(), segment_ids=seg.cuda(), return_dict=False)
-    assert torch.equal(tup[0], out.last_hidden_state) and tup[1] is None
+    # (the global branch sums the queries with float atomics: run-to-run differences are rounding-level only)
+    assert torch.allclose(tup[0], out.last_hidden_state, atol=1e-4, rtol=1e-4) and tup[1] is None
