@@ -113,12 +113,12 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) ln_fwd_kernel(const InT* __res
 // bias of the dense layer that produced the pre-LN sum).  `dy2` (optional) is a second upstream gradient added to dy
 // (the residual branch that by-passes the next block).
 template <typename InT>
-__global__ void __launch_bounds__(ROW_WARPS * 32) ln_bwd_kernel(const __half* __restrict__ dy, const __half* __restrict__ dy2,
-                                                                 const InT* __restrict__ x, const float* __restrict__ mean_in,
-                                                                 const float* __restrict__ rstd_in, const float* __restrict__ gamma,
-                                                                 __half* __restrict__ dx, float* __restrict__ dgamma,
-                                                                 float* __restrict__ dbeta, float* __restrict__ dbias,
-                                                                 const float* __restrict__ alpha_ptr, int rows, int H) {
+__global__ void __launch_bounds__(ROW_WARPS * 32, 3) ln_bwd_kernel(const __half* __restrict__ dy, const __half* __restrict__ dy2,
+                                                                    const InT* __restrict__ x, const float* __restrict__ mean_in,
+                                                                    const float* __restrict__ rstd_in, const float* __restrict__ gamma,
+                                                                    __half* __restrict__ dx, float* __restrict__ dgamma,
+                                                                    float* __restrict__ dbeta, float* __restrict__ dbias,
+                                                                    const float* __restrict__ alpha_ptr, int rows, int H) {
   extern __shared__ float red[];   // [3][ROW_WARPS][H]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nv = lane_vecs(H, lane);
@@ -127,34 +127,32 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) ln_bwd_kernel(const __half* __
   for (int i = 0; i < ROW_MAXV; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) ag[i].v[j] = ab[i].v[j] = ad[i].v[j] = 0.f;
-  Vec8 gm[ROW_MAXV];
-#pragma unroll
-  for (int i = 0; i < ROW_MAXV; ++i)
-    if (i < nv) gm[i] = load8(gamma + (i * 32 + lane) * 8);
 
   for (int row = blockIdx.x * ROW_WARPS + warp; row < rows; row += gridDim.x * ROW_WARPS) {
     const float mean = mean_in[row], rstd = rstd_in[row];
-    Vec8 xh[ROW_MAXV], g[ROW_MAXV];
+    Vec8 xh[ROW_MAXV], d[ROW_MAXV];          // gamma is re-read per row (L1-resident) to keep the register footprint at 3 CTAs/SM
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < ROW_MAXV; ++i)
       if (i < nv) {
-        const size_t off = static_cast<size_t>(row) * H + (i * 32 + lane) * 8;
+        const int c = (i * 32 + lane) * 8;
+        const size_t off = static_cast<size_t>(row) * H + c;
         const Vec8 xv = load8(x + off);
-        Vec8 d = load8(dy + off);
+        d[i] = load8(dy + off);
         if (dy2) {
           const Vec8 d2 = load8(dy2 + off);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) d.v[j] += d2.v[j];
+          for (int j = 0; j < 8; ++j) d[i].v[j] += d2.v[j];
         }
+        const Vec8 gm = load8(gamma + c);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           xh[i].v[j] = (xv.v[j] - mean) * rstd;
-          g[i].v[j] = d.v[j] * gm[i].v[j];
-          s1 += g[i].v[j];
-          s2 = fmaf(g[i].v[j], xh[i].v[j], s2);
-          ag[i].v[j] = fmaf(d.v[j], xh[i].v[j], ag[i].v[j]);
-          ab[i].v[j] += d.v[j];
+          const float g = d[i].v[j] * gm.v[j];
+          s1 += g;
+          s2 = fmaf(g, xh[i].v[j], s2);
+          ag[i].v[j] = fmaf(d[i].v[j], xh[i].v[j], ag[i].v[j]);
+          ab[i].v[j] += d[i].v[j];
         }
       }
     s1 = warp_sum(s1) / H;
@@ -162,13 +160,15 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) ln_bwd_kernel(const __half* __
 #pragma unroll
     for (int i = 0; i < ROW_MAXV; ++i)
       if (i < nv) {
+        const int c = (i * 32 + lane) * 8;
+        const Vec8 gm = load8(gamma + c);
         Vec8 o;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          o.v[j] = rstd * (g[i].v[j] - s1 - xh[i].v[j] * s2);
+          o.v[j] = rstd * (d[i].v[j] * gm.v[j] - s1 - xh[i].v[j] * s2);
           ad[i].v[j] += o.v[j];
         }
-        store8(dx + static_cast<size_t>(row) * H + (i * 32 + lane) * 8, o);
+        store8(dx + static_cast<size_t>(row) * H + c, o);
       }
   }
   // block reduction of the column sums, then one atomic per column per block

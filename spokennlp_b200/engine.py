@@ -152,10 +152,20 @@ class EncoderEngine:
                           ffn=FfnWeights(w1=w(n[10]), bf1=s(n[11]), w2=w(n[12]), bf2=s(n[13]), g=s(n[14]), b=s(n[15])))
 
     def layer(self, i):
-        return self._lv(i, "p")
+        c = self.__dict__.setdefault("_pcache", {})
+        key = (i, self.flat.flat16.data_ptr())
+        if key not in c:
+            c[key] = self._lv(i, "p")
+        return c[key]
 
     def layer_grads(self, i):
-        return self._lv(i, "g")
+        c = self.__dict__.setdefault("_gcache", {})
+        key = (i, self.flat.grad32.data_ptr())
+        if key not in c:
+            if len(c) > 4 * self.L:
+                c.clear()
+            c[key] = self._lv(i, "g")
+        return c[key]
 
     # ---- forward -----------------------------------------------------------------------------------------------
     def embed(self, ids, tt, pos, inputs_embeds, B, S):
