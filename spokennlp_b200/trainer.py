@@ -21,6 +21,22 @@ from .engine import EMB_NAMES, EncoderEngine, FlatParams, layer_param_names
 from .modeling_bert import BertModel
 
 
+def gradient_buckets(layer_first_offsets, numel: int):
+    """Contiguous slices of the flat gradient buffer, in the order their gradients become final during backward:
+    [layer L-1 + head], ..., [layer 0], [embeddings].  One allreduce per slice."""
+    offs = list(layer_first_offsets) + [numel]
+    layers = [(offs[i], offs[i + 1]) for i in range(len(layer_first_offsets))]
+    return list(reversed(layers)) + [(0, offs[0])]
+
+
+def allreduce_bucket(flat_grad: torch.Tensor, lo: int, hi: int, group=None, async_op: bool = True):
+    """Sum-allreduce one bucket in place (NCCL on GPUs; gloo in the CPU tests).  Averaging is folded into the optimizer's
+    gradient multiplier (1 / world size), so there is no second pass over the gradients."""
+    if hi <= lo:
+        return None
+    return dist.all_reduce(flat_grad[lo:hi], op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+
 class TopicSegModel(nn.Module):
     """Encoder + token-classification head with the reference wrapper's parameter names
     (`bert.*`, `loss_calculator.classifier.*`: bert_for_ts.py:23, loss_calculator.py:17)."""
@@ -67,9 +83,9 @@ class DataParallelTrainer:
         self.coef = torch.zeros(3, dtype=torch.float32, device=self.device)
         self.num_labels = model.loss_calculator.classifier.weight.shape[0]
         # gradient buckets: [embeddings | layer 0 | ... | layer L-1 + head], contiguous slices of the flat buffer
-        offs = [flat.offsets[n] for n in self.layer_first] + [flat.numel]
-        self.layer_slices = [(offs[i], offs[i + 1]) for i in range(cfg.num_hidden_layers)]
-        self.emb_slice = (0, offs[0])
+        buckets = gradient_buckets([flat.offsets[n] for n in self.layer_first], flat.numel)
+        self.layer_slices = list(reversed(buckets[:-1]))      # indexed by layer
+        self.emb_slice = buckets[-1]
         self._works = []
         self.hyper = torch.zeros(8, dtype=torch.float32, device=self.device)
         self._graph = None
@@ -79,7 +95,7 @@ class DataParallelTrainer:
     # ------------------------------------------------------------------------------------------------------------
     def _allreduce_slice(self, lo: int, hi: int) -> None:
         if self.world > 1 and hi > lo:
-            self._works.append(dist.all_reduce(self.flat.grad32[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+            self._works.append(allreduce_bucket(self.flat.grad32, lo, hi))
 
     def _after_layer(self, i: int) -> None:
         if i >= 0:
@@ -221,6 +237,10 @@ class _Aliased:
     @property
     def flat32(self):
         return self._f.flat32
+
+    @property
+    def flat16(self):
+        return self._f.flat16
 
     @property
     def grad32(self):
