@@ -69,7 +69,8 @@ int b200_gemm_f16(const void* A, int lda, int a_layout, const void* B, int ldb, 
  * Fused attention forward, head_dim 64: ctx = softmax(Q K^T / 8 + key_bias) V  (BertSelfAttention.forward,
  * bert_model.py:309-350; HF eager_attention_forward).  Q: [B*Sq, ldq] with head h at columns q_col0 + 64h;
  * K, V: [B*Sk, ldkv] at k_col0 / v_col0 + 64h (self-attention: all three inside the packed [tokens,3H] QKV buffer).
- * key_bias: optional [B,Sk] additive fp32 (0 keep / -inf drop, or any finite additive mask); kv_len: optional [B] int32.
+ * key_bias: optional [B,Sk] additive fp32 (0 keep / -inf drop, or any finite additive mask); kv_len: optional [B] int32
+ * as produced by b200_mask_to_bias (positive: prefix mask, the bias array is then not read; negative or absent: general bias).
  * ctx: [B*Sq, ld_out] fp16; lse2: optional [B,heads,Sq] fp32 log2-domain log-sum-exp saved for the backward.
  */
 int b200_attn_fwd(const void* q, int ldq, int q_col0, const void* kv, int ldkv, int k_col0, int v_col0, const float* key_bias,
@@ -79,7 +80,8 @@ int b200_attn_fwd(const void* q, int ldq, int q_col0, const void* kv, int ldkv, 
 int b200_attn_probs(const void* q, int ldq, int q_col0, const void* k, int ldk, int k_col0, const float* key_bias,
                     const float* lse2, float* probs, int B, int heads, int Sq, int Sk, void* stream);
 
-/* key_bias[b,s] = mask01 ? 0 : -inf ; kv_len[b] = 1 + last kept key  (HF create_bidirectional_mask / mmvts -1e6 masks) */
+/* key_bias[b,s] = mask01 ? 0 : -inf ; kv_len[b] = +(1 + last kept key) for a right-padded row, -(1 + last kept key) when the kept
+ * range has holes (attention kernels then read the per-key bias)  (HF create_bidirectional_mask / mmvts -1e6 masks) */
 int b200_mask_to_bias(const void* mask, int mask_dtype /*0=int64,1=f32,2=int32*/, float* key_bias, int32_t* kv_len, int B, int S,
                       void* stream);
 

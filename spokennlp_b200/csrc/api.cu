@@ -277,21 +277,35 @@ int b200_attn_probs(const void* q, int ldq, int q_col0, const void* k, int ldk, 
 namespace {
 template <typename T>
 __global__ void mask_to_bias_kernel(const T* __restrict__ mask, float* __restrict__ bias, int32_t* __restrict__ kv_len, int S) {
+  // kv_len[b] = +(last kept key + 1) when the kept keys form a prefix (right padding: the only masks the reference
+  // builds), -(last kept key + 1) when there are holes inside the kept range (kernels then read the per-key bias).
   const int b = blockIdx.x;
-  int last = 0;
+  int last = 0, cnt = 0;
   for (int s = threadIdx.x; s < S; s += blockDim.x) {
     const bool keep = mask[static_cast<size_t>(b) * S + s] != T(0);
     bias[static_cast<size_t>(b) * S + s] = keep ? 0.f : -INFINITY;
-    if (keep) last = s + 1;
+    if (keep) {
+      last = s + 1;
+      ++cnt;
+    }
   }
-  __shared__ int red[32];
-  for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = last;
+  __shared__ int red[32], redc[32];
+  for (int o = 16; o > 0; o >>= 1) {
+    last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[threadIdx.x >> 5] = last;
+    redc[threadIdx.x >> 5] = cnt;
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
-    int m = 0;
-    for (int i = 0; i < (blockDim.x + 31) / 32; ++i) m = max(m, red[i]);
-    if (kv_len) kv_len[b] = m;
+    int m = 0, c = 0;
+    for (int i = 0; i < (blockDim.x + 31) / 32; ++i) {
+      m = max(m, red[i]);
+      c += redc[i];
+    }
+    if (kv_len) kv_len[b] = (c == m) ? m : -m;
   }
 }
 }  // namespace
@@ -329,7 +343,7 @@ int b200_layernorm_bwd(const void* dy, const void* dy2, const void* x, int x_dty
   if (int rc = check_row_shape("layernorm_bwd", rows, H)) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int grid = (rows + ROW_WARPS - 1) / ROW_WARPS;
-  const int cap = sm_count() * 8;
+  const int cap = sm_count() * 3;        // 3 resident CTAs per SM: one wave, and 3x fewer column-sum atomics than an oversubscribed grid
   if (grid > cap) grid = cap;
   const size_t smem = 3 * ROW_WARPS * H * sizeof(float);
   if (x_dtype == B200_DT_F32) {

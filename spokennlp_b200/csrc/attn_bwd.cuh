@@ -42,8 +42,9 @@ struct AttnBwdSmem {
   static constexpr int OFF_QDO = OFF_V + T;                    // 2 stages x (Q_i, dO_i)
   static constexpr int OFF_P = OFF_QDO + 2 * 2 * T;            // P^T  [128 keys][128 q] fp16 = 32 KB
   static constexpr int OFF_DS = OFF_P + 2 * T;                 // dS^T 32 KB
-  static constexpr int OFF_STAT = OFF_DS + 2 * T;              // [2 buffers][2 (lse2, delta)][128] floats
-  static constexpr int OFF_BAR = OFF_STAT + 2 * 2 * 128 * 4;
+  static constexpr int STAT_Q = 2048;                          // queries whose (lse2, delta) are staged at once
+  static constexpr int OFF_STAT = OFF_DS + 2 * T;              // [2 (lse2, delta)][STAT_Q] floats
+  static constexpr int OFF_BAR = OFF_STAT + 2 * STAT_Q * 4;
   static constexpr int TOTAL = OFF_BAR + 256 + 1024;
 };
 
@@ -71,7 +72,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int b = blockIdx.z, h = blockIdx.y;
   const int k0 = blockIdx.x * ATT_BK;
   int kv_len = a.kv_len ? a.kv_len[b] : a.Sk;
-  kv_len = max(1, min(kv_len, a.Sk));
+  const bool general_bias = a.key_bias != nullptr && (a.kv_len == nullptr || kv_len < 0);   // see attn_fwd.cuh
+  kv_len = max(1, min(kv_len < 0 ? -kv_len : kv_len, a.Sk));
   const int nq = (a.Sq + ATT_BQ - 1) / ATT_BQ;
   const bool dead_block = k0 >= kv_len;      // every key of this block is masked: dK = dV = 0, no dQ contribution
 
@@ -97,7 +99,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  // TMEM columns: S^T [0,128)  dP^T [128,256)  dV [256,320)  dK [320,384)  dQ [384,448)
+  // TMEM columns: S^T [0,128)  dP^T [128,256)  dV [256,320)  dK [320,384)  dQ ping-pong [384,448) / [448,512)
 
   if (dead_block) {
     if (warp >= 2 && warp < 6) {
@@ -171,7 +173,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                   idesc_g, (i > 0 || kk > 0) ? 1u : 0u);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)        // dQ_i = dS K   (A = dS^T tile viewed MN-major: M = query, K = key rows)
-          umma_ss(tmem + 384, make_smem_desc(dsa + kk * 2048, 16384, 1024), make_smem_desc(ka + kk * 2048, 8192, 1024), idesc_q, kk > 0);
+          umma_ss(tmem + 384 + (i & 1) * 64, make_smem_desc(dsa + kk * 2048, 16384, 1024), make_smem_desc(ka + kk * 2048, 8192, 1024), idesc_q, kk > 0);
         }
         umma_commit(&qdo_empty[st]);
         umma_commit(grad_done);
@@ -189,13 +191,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t ds_row = smem_u32(smem + S::OFF_DS) + half * 16384 + r * 128;
     const int key = k0 + r;
     float bias = -INFINITY;
-    if (key < kv_len) bias = a.key_bias ? a.key_bias[static_cast<size_t>(b) * a.Sk + key] * 1.4426950408889634f : 0.f;
+    if (key < kv_len) bias = general_bias ? a.key_bias[static_cast<size_t>(b) * a.Sk + key] * 1.4426950408889634f : 0.f;
     const size_t stat_base = (static_cast<size_t>(b) * a.heads + h) * a.Sq;
 
     auto drain_dq = [&](int i) {                  // dQ_i tile: TMEM lane == query row; this warp owns 32 of the 64 d columns
       const int q = i * ATT_BQ + r;
       uint32_t o[32];
-      tmem_ld_x32(tmem + lane_addr + 384 + half * 32, o);
+      tmem_ld_x32(tmem + lane_addr + 384 + (i & 1) * 64 + half * 32, o);
       tmem_wait_ld();
       if (q < a.Sq && !(a.dbg & 0x10000)) {
         float* dst = a.dq_acc + (static_cast<size_t>(b) * a.Sq + q) * a.ld_dq + h * ATT_D + half * 32;
@@ -206,16 +208,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     };
 
+    // (lse2, delta) of the queries are staged STAT_Q at a time (all of them at once for Sq <= 2048), so the hot loop
+    // carries no block-wide barrier; queries past Sq get lse = +inf (P = 0) and delta = 0
+    const int blocks_per_stage = S::STAT_Q / ATT_BQ;
     for (int i = 0; i < nq; ++i) {
-      if (t < 128) {  // per-query statistics of block i; queries past Sq get lse = +inf (P = 0) and delta = 0
-        const int q = i * ATT_BQ + t;
-        const uint32_t sb = stat + (i & 1) * 1024;
-        sts_f32(sb + t * 4, q < a.Sq ? a.lse2[stat_base + q] : INFINITY);
-        sts_f32(sb + 512 + t * 4, q < a.Sq ? a.delta[stat_base + q] : 0.f);
+      if (i % blocks_per_stage == 0) {
+        if (i > 0) asm volatile("bar.sync 1, 256;" ::: "memory");       // everyone is done with the previous stage
+        for (int qq = t; qq < S::STAT_Q; qq += 256) {
+          const int q = i * ATT_BQ + qq;
+          sts_f32(stat + qq * 4, q < a.Sq ? a.lse2[stat_base + q] : INFINITY);
+          sts_f32(stat + S::STAT_Q * 4 + qq * 4, q < a.Sq ? a.delta[stat_base + q] : 0.f);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const uint32_t lse_s = stat + (i & 1) * 1024 + half * 256;
-      const uint32_t del_s = lse_s + 512;
+      const uint32_t lse_s = stat + ((i % blocks_per_stage) * ATT_BQ + half * 64) * 4;
+      const uint32_t del_s = lse_s + S::STAT_Q * 4;
       mbar_wait(s_full, i & 1);
       tc_fence_after();
       uint32_t pk[32], dk[32];                    // this thread's 64 P^T / dS^T values, packed fp16
@@ -245,7 +252,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (i > 0) {                                // gradient MMAs of block i-1 are done: dQ(i-1) is complete, P^T/dS^T are free
         mbar_wait(grad_done, (i - 1) & 1);
         tc_fence_after();
-        drain_dq(i - 1);
       }
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch) {
@@ -256,6 +262,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(ds_full);
+      // dQ(i-1) sits in the other TMEM buffer: reduce it into HBM off the critical path (after releasing the MMA warp)
+      if (i > 0) drain_dq(i - 1);
     }
     mbar_wait(grad_done, (nq - 1) & 1);
     tc_fence_after();

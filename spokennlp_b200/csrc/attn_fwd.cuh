@@ -66,7 +66,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int q0 = blockIdx.x * 2 * ATT_BQ;
   const bool tileB = (q0 + ATT_BQ) < a.Sq;
   int kv_len = a.kv_len ? a.kv_len[b] : a.Sk;
-  kv_len = max(1, min(kv_len, a.Sk));
+  // a negative kv_len (or a bias without kv_len) means "arbitrary additive bias": every key reads its bias value;
+  // otherwise the kept keys are the prefix [0, kv_len) and only the last partial block needs any masking
+  const bool general_bias = a.key_bias != nullptr && (a.kv_len == nullptr || kv_len < 0);
+  kv_len = max(1, min(kv_len < 0 ? -kv_len : kv_len, a.Sk));
   const int n_blocks = (kv_len + ATT_BK - 1) / ATT_BK;
 
   if (warp == 0 && lane == 0) {
@@ -167,12 +170,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       float m = NEG_INF, l = 0.f;
       for (int j = 0; j < n_blocks; ++j) {
         // Only blocks that contain a biased / removed key pay for the per-key bias (CTA-uniform decision).
-        const bool biased = (a.key_bias != nullptr) || ((j + 1) * ATT_BK > kv_len);
+        const bool biased = general_bias || ((j + 1) * ATT_BK > kv_len);
         const uint32_t bj = bias_s + (j & 1) * ATT_BK * 4;
         if (biased) {
           const int key = j * ATT_BK + t;
           float bv = NEG_INF;
-          if (key < kv_len) bv = a.key_bias ? a.key_bias[static_cast<size_t>(b) * a.Sk + key] * 1.4426950408889634f : 0.f;
+          if (key < kv_len) bv = general_bias ? a.key_bias[static_cast<size_t>(b) * a.Sk + key] * 1.4426950408889634f : 0.f;
           sts_f32(bj + t * 4, bv);
           asm volatile("bar.sync %0, 128;" ::"r"(1 + x) : "memory");
         }

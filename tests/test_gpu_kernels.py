@@ -283,7 +283,9 @@ def test_attn_fwd(B, S, heads, masked):
         if B > 2:
             mask[2, 5] = 0          # a hole inside the kept range: handled by the bias, not by kv_len
         key_bias, kv_len = ops.mask_to_bias(mask)
-        assert torch.equal(kv_len.cpu().long(), lens)
+        # +len for a right-padded row, -len when the kept range has a hole (kernels then read the per-key bias)
+        assert torch.equal(kv_len.cpu().long().abs(), lens)
+        assert bool((kv_len.cpu() < 0).any()) == (B > 2)
     ctx = torch.empty(B * S, H, dtype=torch.float16, device="cuda")
     lse2 = torch.empty(B, heads, S, dtype=torch.float32, device="cuda")
     ops.attn_fwd(qkv, qkv, ctx, B, heads, S, S, q_col0=0, k_col0=H, v_col0=2 * H, key_bias=key_bias, kv_len=kv_len, lse2=lse2)
