@@ -126,6 +126,13 @@ size_t b200_ponet_workspace(int B, int S, int H, int heads, int nseg);
 int b200_ponet_mix_fwd(const void* proj, int ld, const float* key_bias, const int64_t* segment_ids, void* workspace, void* out, int B, int S,
                        int H, int heads, int nseg, void* stream);
 
+/* Backward of the mixer: dproj [B*S, ld_d] receives the gradients wrt [Q | K | O | Sg | Lc] (fp16, same scaling as dout).
+ * fwd_workspace: the workspace b200_ponet_mix_fwd filled for this layer (kept by the caller); bwd_workspace: scratch of
+ * b200_ponet_bwd_workspace() bytes. */
+size_t b200_ponet_bwd_workspace(int B, int S, int H, int heads, int nseg);
+int b200_ponet_mix_bwd(const void* proj, int ld, const void* dout, const float* key_bias, const int64_t* segment_ids, const void* fwd_workspace,
+                       void* bwd_workspace, void* dproj, int ld_d, int B, int S, int H, int heads, int nseg, void* stream);
+
 /* db[n] += *alpha * sum_m dy[m,n]   (bias gradients) */
 int b200_colsum(const void* dy, int ld, float* db, const float* alpha, int rows, int cols, void* stream);
 

@@ -518,6 +518,43 @@ int b200_ponet_mix_fwd(const void* proj, int ld, const float* key_bias, const in
   return check_launch("ponet_mix_kernel");
 }
 
+size_t b200_ponet_bwd_workspace(int B, int S, int H, int heads, int nseg) {
+  return (static_cast<size_t>(B) * H * 2 + static_cast<size_t>(B) * heads + static_cast<size_t>(B) * nseg * H) * sizeof(float) + 256;
+}
+
+int b200_ponet_mix_bwd(const void* proj, int ld, const void* dout, const float* key_bias, const int64_t* segment_ids, const void* fwd_workspace,
+                       void* bwd_workspace, void* dproj, int ld_d, int B, int S, int H, int heads, int nseg, void* stream) {
+  if (B <= 0 || S <= 0 || H != heads * 64 || (ld % 8) || (ld_d % 8) || nseg <= 0) return fail(B200_ERR_SHAPE, "ponet_mix_bwd: bad shape");
+  if (!proj || !dout || !segment_ids || !fwd_workspace || !bwd_workspace || !dproj) return fail(B200_ERR_SHAPE, "ponet_mix_bwd: null pointer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int nchunks = (S + 127) / 128;
+  // forward workspace layout (see b200_ponet_mix_fwd)
+  const float* qsum = static_cast<const float*>(fwd_workspace);
+  const float* cnt = qsum + static_cast<size_t>(B) * H;
+  const float* g = cnt + ((B + 3) / 4) * 4;
+  const float* part = g + static_cast<size_t>(B) * H;
+  const float* segmax = part + static_cast<size_t>(B) * heads * nchunks * 66;
+  segmax += (4 - (reinterpret_cast<uintptr_t>(segmax) / 4) % 4) % 4;
+  float* dg = static_cast<float*>(bwd_workspace);
+  float* dqbar = dg + static_cast<size_t>(B) * H;
+  float* segsum = dqbar + static_cast<size_t>(B) * H;
+  float* lse = segsum + static_cast<size_t>(B) * nseg * H;
+  cudaMemsetAsync(dg, 0, (static_cast<size_t>(B) * H * 2 + static_cast<size_t>(B) * nseg * H) * sizeof(float), s);
+  const __half* p = static_cast<const __half*>(proj);
+  const __half* d = static_cast<const __half*>(dout);
+  int rc;
+  ponet_bwd_sums_kernel<<<dim3((S + 63) / 64, B), H / 8, 0, s>>>(p, ld, d, key_bias, segment_ids, dg, segsum, S, H, nseg);
+  if ((rc = check_launch("ponet_bwd_sums_kernel"))) return rc;
+  ponet_global_lse_kernel<<<dim3(heads, B), 32, 0, s>>>(part, lse, nchunks, heads);
+  if ((rc = check_launch("ponet_global_lse_kernel"))) return rc;
+  ponet_bwd_global_kernel<<<dim3(nchunks, heads, B), 128, 0, s>>>(p, ld, key_bias, qsum, cnt, g, lse, dg, dqbar, static_cast<__half*>(dproj), ld_d,
+                                                                  S, H, heads);
+  if ((rc = check_launch("ponet_bwd_global_kernel"))) return rc;
+  ponet_bwd_rows_kernel<<<(B * S + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, s>>>(p, ld, d, key_bias, segment_ids, g, segmax, segsum, dqbar, cnt,
+                                                                                      static_cast<__half*>(dproj), ld_d, B, S, H, nseg);
+  return check_launch("ponet_bwd_rows_kernel");
+}
+
 }  // extern "C"
 
 #include "api_train.inc"

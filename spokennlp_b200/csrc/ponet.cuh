@@ -193,4 +193,206 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) ponet_mix_kernel(const __half*
     }
 }
 
+// ------------------------------------------------------------------------------------------------ backward
+// out_s = (g + seg_s) o O_s + loc_s on kept rows.  With t_s = dout_s o O_s:
+//   dO_s = dout_s o (g + seg_s);   dg = sum_s t_s;   dSg_u = [Sg_u == segmax(seg_u)] * sum_{s in seg_u} t_s;
+//   dLc_u = sum over the (<=3) windows whose arg-max is u of dout_s;
+//   global branch (g = sum_s a_s K_s, a = softmax(qbar.K/8)):  dz_s = a_s (dg.K_s - dg.g),
+//   dK_s = a_s dg + dz_s qbar / 8,  dqbar = sum_s dz_s K_s / 8,  dQ_s = dqbar / cnt on kept rows.
+// Ties in the max operations have measure zero for real activations and are not split.
+
+// pass 1: dg[b,:] and segsum[b,seg,:] (running sums over the contiguous runs).  grid (ceil(S/64), B), block H/8
+__global__ void ponet_bwd_sums_kernel(const __half* __restrict__ proj, int ld, const __half* __restrict__ dout, const float* __restrict__ key_bias,
+                                      const int64_t* __restrict__ seg, float* __restrict__ dg, float* __restrict__ segsum, int S, int H, int nseg) {
+  const int b = blockIdx.y, s0 = blockIdx.x * 64, c = threadIdx.x * 8;
+  if (c >= H) return;
+  float run[8], tot[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) run[j] = tot[j] = 0.f;
+  long cur = -1;
+  for (int s = s0; s < min(S, s0 + 64); ++s) {
+    const size_t row = static_cast<size_t>(b) * S + s;
+    const long id = seg[row];
+    if (id != cur) {
+      if (cur >= 0 && cur < nseg)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(segsum + (static_cast<size_t>(b) * nseg + cur) * H + c + j, run[j]);
+      cur = id;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) run[j] = 0.f;
+    }
+    if (key_bias && key_bias[row] != 0.f) continue;
+    const Vec8 d = load8(dout + row * H + c), o = load8(proj + row * ld + 2 * H + c);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float t = d.v[j] * o.v[j];
+      run[j] += t;
+      tot[j] += t;
+    }
+  }
+  if (cur >= 0 && cur < nseg)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(segsum + (static_cast<size_t>(b) * nseg + cur) * H + c + j, run[j]);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) atomicAdd(dg + static_cast<size_t>(b) * H + c + j, tot[j]);
+}
+
+// forward helper for the backward: lse[b,h] (log2 domain) of the global softmax.  grid (heads, B), block 32
+__global__ void ponet_global_lse_kernel(const float* __restrict__ part, float* __restrict__ lse, int nchunks, int heads) {
+  const int b = blockIdx.y, h = blockIdx.x;
+  const float* src = part + (static_cast<size_t>(b) * heads + h) * nchunks * 66;
+  float m = -INFINITY;
+  for (int c = threadIdx.x; c < nchunks; c += 32) m = fmaxf(m, src[c * 66]);
+  m = warp_max(m);
+  float l = 0.f;
+  for (int c = threadIdx.x; c < nchunks; c += 32) l += src[c * 66] > -INFINITY ? exp2f(src[c * 66] - m) * src[c * 66 + 1] : 0.f;
+  l = warp_sum(l);
+  if (threadIdx.x == 0) lse[b * heads + h] = l > 0.f ? m + log2f(l) : INFINITY;
+}
+
+// pass 2: global branch.  grid (ceil(S/128), heads, B), block 128: thread t <-> key.  Writes dK rows, accumulates dqbar.
+__global__ void __launch_bounds__(128) ponet_bwd_global_kernel(const __half* __restrict__ proj, int ld, const float* __restrict__ key_bias,
+                                                               const float* __restrict__ qsum, const float* __restrict__ cnt,
+                                                               const float* __restrict__ g, const float* __restrict__ lse,
+                                                               const float* __restrict__ dg, float* __restrict__ dqbar,
+                                                               __half* __restrict__ dproj, int ld_d, int S, int H, int heads) {
+  __shared__ float qb[64], dgs[64], acc[4][64];
+  __shared__ float c0s;
+  const int b = blockIdx.z, h = blockIdx.y, t = threadIdx.x, s = blockIdx.x * 128 + t;
+  if (t < 64) {
+    qb[t] = qsum[static_cast<size_t>(b) * H + h * 64 + t] / fmaxf(cnt[b], 1.0f);
+    dgs[t] = dg[static_cast<size_t>(b) * H + h * 64 + t];
+  }
+  __syncthreads();
+  if (t < 32) {
+    float v = dgs[t] * g[static_cast<size_t>(b) * H + h * 64 + t] + dgs[t + 32] * g[static_cast<size_t>(b) * H + h * 64 + t + 32];
+    v = warp_sum(v);
+    if (t == 0) c0s = v;
+  }
+  __syncthreads();
+  const bool valid = s < S && !(key_bias && key_bias[static_cast<size_t>(b) * S + s] != 0.f);
+  float dz = 0.f, a = 0.f;
+  Vec8 kv[8];
+  if (s < S) {
+    const __half* krow = proj + (static_cast<size_t>(b) * S + s) * ld + H + h * 64;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) kv[i] = load8(krow + i * 8);
+  }
+  if (valid) {
+    float z = 0.f, dd = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        z = fmaf(kv[i].v[j], qb[i * 8 + j], z);
+        dd = fmaf(kv[i].v[j], dgs[i * 8 + j], dd);
+      }
+    a = exp2f(z * (0.125f * 1.4426950408889634f) - lse[b * heads + h]);
+    dz = a * (dd - c0s);
+  }
+  if (s < S) {
+    __half* drow = dproj + (static_cast<size_t>(b) * S + s) * ld_d + H + h * 64;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      Vec8 o;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o.v[j] = valid ? fmaf(dz * 0.125f, qb[i * 8 + j], a * dgs[i * 8 + j]) : 0.f;
+      store8(drow + i * 8, o);
+    }
+  }
+  // dqbar[d] += sum_s dz_s K_s[d] / 8 : per-warp shuffle reduction over the 32 keys of the warp, then across warps
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = valid ? dz * kv[i].v[j] * 0.125f : 0.f;
+      v = warp_sum(v);
+      if ((t & 31) == 0) acc[t >> 5][i * 8 + j] = v;
+    }
+  __syncthreads();
+  if (t < 64) atomicAdd(dqbar + static_cast<size_t>(b) * H + h * 64 + t, acc[0][t] + acc[1][t] + acc[2][t] + acc[3][t]);
+}
+
+// pass 3: everything row-local.  warp per token row; writes dQ, dO, dSg, dLc (dK was written by pass 2).
+__global__ void __launch_bounds__(ROW_WARPS * 32) ponet_bwd_rows_kernel(const __half* __restrict__ proj, int ld, const __half* __restrict__ dout,
+                                                                         const float* __restrict__ key_bias, const int64_t* __restrict__ seg,
+                                                                         const float* __restrict__ g, const float* __restrict__ segmax,
+                                                                         const float* __restrict__ segsum, const float* __restrict__ dqbar,
+                                                                         const float* __restrict__ cnt, __half* __restrict__ dproj, int ld_d,
+                                                                         int B, int S, int H, int nseg) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (row >= B * S) return;
+  const int b = row / S, s = row % S;
+  auto padded = [&](int ss) { return key_bias && key_bias[static_cast<size_t>(b) * S + ss] != 0.f; };
+  const bool pad = padded(s);
+  const int nv = lane_vecs(H, lane);
+  const long id = min(static_cast<long>(nseg - 1), max(0l, static_cast<long>(seg[row])));
+  const float inv_cnt = 1.0f / fmaxf(cnt[b], 1.0f);
+  // masked local-branch value of row ss (out of range -> -inf so it never wins a window)
+  auto lc = [&](int ss, int c) {
+    Vec8 v;
+    if (ss < 0 || ss >= S) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v.v[j] = -INFINITY;
+    } else if (padded(ss)) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v.v[j] = PONET_NEG;
+    } else {
+      v = load8(proj + (static_cast<size_t>(b) * S + ss) * ld + 4 * H + c);
+    }
+    return v;
+  };
+  auto dout_row = [&](int ss, int c) {
+    Vec8 v;
+    if (ss < 0 || ss >= S || padded(ss)) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v.v[j] = 0.f;
+    } else {
+      v = load8(dout + (static_cast<size_t>(b) * S + ss) * H + c);
+    }
+    return v;
+  };
+#pragma unroll 1
+  for (int i = 0; i < ROW_MAXV; ++i)
+    if (i < nv) {
+      const int c = (i * 32 + lane) * 8;
+      __half* drow = dproj + static_cast<size_t>(row) * ld_d;
+      Vec8 dq, dO, dsg, dlc;
+      if (pad) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dq.v[j] = dO.v[j] = dsg.v[j] = dlc.v[j] = 0.f;
+      } else {
+        const Vec8 d = load8(dout + static_cast<size_t>(row) * H + c);
+        const Vec8 gv = load8(g + static_cast<size_t>(b) * H + c);
+        const Vec8 sm = load8(segmax + (static_cast<size_t>(b) * nseg + id) * H + c);
+        const Vec8 ss = load8(segsum + (static_cast<size_t>(b) * nseg + id) * H + c);
+        const Vec8 sgv = load8(proj + static_cast<size_t>(row) * ld + 3 * H + c);
+        const Vec8 dqb = load8(dqbar + static_cast<size_t>(b) * H + c);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          dq.v[j] = dqb.v[j] * inv_cnt;
+          dO.v[j] = d.v[j] * (gv.v[j] + sm.v[j]);
+          dsg.v[j] = (sgv.v[j] == sm.v[j]) ? ss.v[j] : 0.f;
+          dlc.v[j] = 0.f;
+        }
+        // dLc_u: u = s is the arg-max of window w (centred at w in {s-1, s, s+1}) iff Lc_s beats the other two taps
+        const Vec8 l0 = lc(s - 2, c), l1 = lc(s - 1, c), l2 = lc(s, c), l3 = lc(s + 1, c), l4 = lc(s + 2, c);
+        const Vec8 dm = dout_row(s - 1, c), dp = dout_row(s + 1, c);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float me = l2.v[j];
+          // first maximum wins inside a window (taps ordered left to right), like an arg-max scan
+          if (me > l0.v[j] && me > l1.v[j]) dlc.v[j] += dm.v[j];                    // window centred at s-1: taps (s-2, s-1, s)
+          if (me >= l3.v[j] && me > l1.v[j]) dlc.v[j] += d.v[j];                    // window centred at s  : taps (s-1, s, s+1)
+          if (me >= l3.v[j] && me >= l4.v[j]) dlc.v[j] += dp.v[j];                  // window centred at s+1: taps (s, s+1, s+2)
+        }
+      }
+      store8(drow + c, dq);
+      store8(drow + 2 * H + c, dO);
+      store8(drow + 3 * H + c, dsg);
+      store8(drow + 4 * H + c, dlc);
+    }
+}
+
 }  // namespace b200

@@ -40,6 +40,8 @@ _PROTOS = {
     "b200_attn_bwd_workspace": [_i, _i, _i],
     "b200_ponet_workspace": [_i, _i, _i, _i, _i],
     "b200_ponet_mix_fwd": [_p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "b200_ponet_bwd_workspace": [_i, _i, _i, _i, _i],
+    "b200_ponet_mix_bwd": [_p, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "b200_attn_bwd": [_p, _i, _i, _p, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "b200_grad_sumsq": [_p, _sz, _p, _p],
     "b200_clip_coef": [_p, _f, _f, _p, _p],
@@ -47,7 +49,7 @@ _PROTOS = {
     "b200_set_hyper": [_p, _f, _f, _f, _f, _f, _f, _f, _p],
     "b200_adamw_step_dev": [_p, _p, _p, _p, _p, _sz, _p, _p, _p],
 }
-_RESTYPE = {"b200_set_gemm_impl": None, "b200_set_gemm_debug": None, "b200_last_error": C.c_char_p, "b200_launch_count": _ll, "b200_version": _i, "b200_attn_bwd_workspace": _sz, "b200_ponet_workspace": _sz}
+_RESTYPE = {"b200_set_gemm_impl": None, "b200_set_gemm_debug": None, "b200_last_error": C.c_char_p, "b200_launch_count": _ll, "b200_version": _i, "b200_attn_bwd_workspace": _sz, "b200_ponet_workspace": _sz, "b200_ponet_bwd_workspace": _sz}
 
 _lock = threading.Lock()
 _lib = None

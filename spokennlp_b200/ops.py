@@ -243,7 +243,8 @@ def unscale_cast_grad(src: Tensor, dst: Tensor, scale: Optional[Tensor]) -> Tens
 
 def ponet_mix_fwd(proj: Tensor, seg_ids: Tensor, out: Tensor, B: int, S: int, heads: int, nseg: int, *,
                   key_bias: Optional[Tensor] = None) -> Tensor:
-    """PoNet pooling mixer on the packed projections [B*S, 5H] = [Q | K | O | Sg | Lc] (oracle/ponet_oracle.py)."""
+    """PoNet pooling mixer on the packed projections [B*S, 5H] = [Q | K | O | Sg | Lc] (oracle/ponet_oracle.py).
+    Returns the workspace the kernels filled (global vector, segment maxima, ...), which the backward consumes."""
     _req(proj, torch.float16, "proj"), _req(out, torch.float16, "out")
     H = heads * 64
     nbytes = int(L.load().b200_ponet_workspace(B, S, H, heads, nseg))
@@ -251,15 +252,16 @@ def ponet_mix_fwd(proj: Tensor, seg_ids: Tensor, out: Tensor, B: int, S: int, he
     rc = L.load().b200_ponet_mix_fwd(_ptr(proj), proj.stride(0), _ptr(key_bias), _ptr(seg_ids), _ptr(ws), _ptr(out), B, S, H, heads, nseg,
                                      _stream())
     L.check(rc, "b200_ponet_mix_fwd")
-    return out
+    return ws
 
 
-def set_hyper(hyper: Tensor, *, lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, weight_decay: float = 0.0,
-              step: int = 1) -> None:
-    rc = L.load().b200_set_hyper(_ptr(hyper), lr, beta1, beta2, eps, weight_decay, 1.0 - beta1 ** step, 1.0 - beta2 ** step, _stream())
-    L.check(rc, "b200_set_hyper")
-
-
-def adamw_step_dev(p: Tensor, g: Tensor, m: Tensor, v: Tensor, p16: Optional[Tensor], hyper: Tensor, coef: Optional[Tensor]) -> None:
-    rc = L.load().b200_adamw_step_dev(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(p16), p.numel(), _ptr(hyper), _ptr(coef), _stream())
-    L.check(rc, "b200_adamw_step_dev")
+def ponet_mix_bwd(proj: Tensor, dout: Tensor, seg_ids: Tensor, fwd_ws: Tensor, dproj: Tensor, B: int, S: int, heads: int, nseg: int, *,
+                  key_bias: Optional[Tensor] = None) -> Tensor:
+    _req(proj, torch.float16, "proj"), _req(dout, torch.float16, "dout"), _req(dproj, torch.float16, "dproj")
+    H = heads * 64
+    nbytes = int(L.load().b200_ponet_bwd_workspace(B, S, H, heads, nseg))
+    ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=proj.device)
+    rc = L.load().b200_ponet_mix_bwd(_ptr(proj), proj.stride(0), _ptr(dout), _ptr(key_bias), _ptr(seg_ids), _ptr(fwd_ws), _ptr(ws), _ptr(dproj),
+                                     dproj.stride(0), B, S, H, heads, nseg, _stream())
+    L.check(rc, "b200_ponet_mix_bwd")
+    return dproj
