@@ -9,8 +9,8 @@ the parameter names follow the public PoNet implementation (`attention.self.dens
 
 Per layer: ONE packed [5H,H] tcgen05 GEMM produces Q|K|O|Sg|Lc; the pooling mixer (global softmax-pooled vector per
 head, segment max, local max-3, fuse) runs as coalesced HBM-bound kernels (`b200_ponet_mix_fwd`); the output dense +
-residual + LayerNorm and the feed-forward block are the same kernels as BERT.  This round ships the forward
-(inference / predict path); the mixer backward is listed as next in DESIGN.md §7.
+residual + LayerNorm and the feed-forward block are the same kernels as BERT.  Forward and backward (fine-tuning) both run
+in the library; gradients reach every parameter through one autograd node.
 """
 from __future__ import annotations
 
@@ -22,7 +22,7 @@ from transformers import PretrainedConfig
 from transformers.modeling_outputs import BaseModelOutputWithPoolingAndCrossAttentions
 
 from . import ops
-from .blocks import FfnWeights, ffn_block_fwd
+from .blocks import FfnWeights, ffn_block_bwd, ffn_block_fwd
 from .engine import EMB_NAMES, FlatParams
 from .lib import B200Error
 from .modeling_bert import BertEmbeddings, BertIntermediate, BertOutput, BertPooler, BertSelfOutput
@@ -81,6 +81,94 @@ def ponet_layer_names(i: int) -> List[str]:
              p + "output.dense.weight", p + "output.dense.bias", p + "output.LayerNorm.weight", p + "output.LayerNorm.bias"])
 
 
+class _PoNetFn(torch.autograd.Function):
+    """Embeddings + L PoNet layers as one autograd node (same bridge as modeling_bert._EncoderFn)."""
+
+    @staticmethod
+    def forward(ctx, model, ids, tt, pos, key_bias, seg, B, S, want_hidden, *params):
+        f: FlatParams = model._flat
+        cfg = model.config
+        H, heads, eps, dev = cfg.hidden_size, cfg.num_attention_heads, float(cfg.layer_norm_eps), ids.device
+        M, nseg = B * S, S + 2
+        save = any(ctx.needs_input_grad[9:])
+        x32 = torch.empty(M, H, dtype=F32, device=dev)
+        x16 = ops.embed_ln_fwd(ids, tt, pos, None, f.view32(EMB_NAMES[0]), f.view32(EMB_NAMES[1]), f.view32(EMB_NAMES[2]),
+                               f.view32(EMB_NAMES[3]), f.view32(EMB_NAMES[4]), eps, M, S, H, y32=x32)
+        hiddens = [x32.view(B, S, H)] if want_hidden else []
+        saved = []
+        for i in range(cfg.num_hidden_layers):
+            n = ponet_layer_names(i)
+            proj = torch.empty(M, 5 * H, dtype=F16, device=dev)
+            ops.gemm(x16, f.view16(n[0], tuple(n[1:5])), proj, epilogue=ops.EPI_BIAS, bias=f.view32(n[5], tuple(n[6:10])))
+            mix = torch.empty(M, H, dtype=F16, device=dev)
+            ws = ops.ponet_mix_fwd(proj, seg, mix, B, S, heads, nseg, key_bias=key_bias)
+            pre = torch.empty(M, H, dtype=F32, device=dev)
+            ops.gemm(mix, f.view16(n[10]), pre, epilogue=ops.EPI_BIAS_RES32, bias=f.view32(n[11]), aux=x32)
+            mean = torch.empty(M, dtype=F32, device=dev) if save else None
+            rstd = torch.empty(M, dtype=F32, device=dev) if save else None
+            a32 = torch.empty(M, H, dtype=F32, device=dev)
+            a16 = ops.layernorm_fwd(pre, f.view32(n[12]), f.view32(n[13]), eps, y32=a32, mean=mean, rstd=rstd)
+            y16, y32, svf = ffn_block_fwd(_ffn_views(f, n, "p"), a16, a32, eps, save=save)
+            if save:
+                saved.append((x16, proj, ws, mix, pre, mean, rstd, svf))
+            x16, x32 = y16, y32
+            if want_hidden:
+                hiddens.append(x32.view(B, S, H))
+        ctx.model, ctx.saved, ctx.meta = model, (saved if save else None), (ids, tt, pos, key_bias, seg, B, S)
+        outs = [x32.view(B, S, H)] + (hiddens if want_hidden else [])
+        ctx.mark_non_differentiable(*outs[1:])
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, g_last, *unused):
+        model, saved = ctx.model, ctx.saved
+        if saved is None:
+            raise B200Error("backward through a forward that ran without grad")
+        ids, tt, pos, key_bias, seg, B, S = ctx.meta
+        f: FlatParams = model._flat
+        cfg = model.config
+        H, heads, eps, dev = cfg.hidden_size, cfg.num_attention_heads, float(cfg.layer_norm_eps), g_last.device
+        M, nseg = B * S, S + 2
+        dy = torch.empty(M, H, dtype=F16, device=dev)
+        scale = torch.empty(2, dtype=F32, device=dev)
+        slot = torch.empty(1, dtype=torch.int32, device=dev)
+        ops.scale_cast_grad(g_last.contiguous().to(F32).view(-1), dy.view(-1), scale, slot, target=1024.0)
+        inv = scale[1:2]
+        keep, f.grad32 = f.grad32, torch.zeros_like(f.flat32)
+        try:
+            for i in reversed(range(cfg.num_hidden_layers)):
+                n = ponet_layer_names(i)
+                x16, proj, ws, mix, pre, mean, rstd, svf = saved[i]
+                saved[i] = None
+                d_a = ffn_block_bwd(_ffn_views(f, n, "p"), _ffn_views(f, n, "g"), svf, dy, inv)
+                d_pre = torch.empty(M, H, dtype=F16, device=dev)
+                ops.layernorm_bwd(d_a, pre, mean, rstd, f.view32(n[12]), d_pre, f.viewg(n[12]), f.viewg(n[13]), dbias=f.viewg(n[11]), alpha=inv)
+                ops.gemm(d_pre, mix, f.viewg(n[10]), a_layout=1, b_layout=1, epilogue=ops.EPI_ATOMIC, alpha=inv, k_splits=ops.wgrad_splits(H, H, M))
+                dmix = torch.empty(M, H, dtype=F16, device=dev)
+                ops.gemm(d_pre, f.view16(n[10]), dmix, b_layout=1)
+                dproj = torch.empty(M, 5 * H, dtype=F16, device=dev)
+                ops.ponet_mix_bwd(proj, dmix, seg, ws, dproj, B, S, heads, nseg, key_bias=key_bias)
+                ops.colsum(dproj, f.viewg(n[5], tuple(n[6:10])), inv)
+                ops.gemm(dproj, x16, f.viewg(n[0], tuple(n[1:5])), a_layout=1, b_layout=1, epilogue=ops.EPI_ATOMIC, alpha=inv,
+                         k_splits=ops.wgrad_splits(5 * H, H, M))
+                dy = torch.empty(M, H, dtype=F16, device=dev)
+                ops.gemm(dproj, f.view16(n[0], tuple(n[1:5])), dy, b_layout=1, epilogue=ops.EPI_ADD, aux=d_pre)
+            ops.embed_ln_bwd(dy, None, ids, tt, pos, f.view32(EMB_NAMES[0]), f.view32(EMB_NAMES[1]), f.view32(EMB_NAMES[2]),
+                             f.view32(EMB_NAMES[3]), f.viewg(EMB_NAMES[0]), f.viewg(EMB_NAMES[1]), f.viewg(EMB_NAMES[2]),
+                             f.viewg(EMB_NAMES[3]), f.viewg(EMB_NAMES[4]), inv, eps, M, S, H)
+            grads = tuple(f.viewg(nm) if f.params[nm].requires_grad else None for nm in f.names)
+        finally:
+            f.grad32 = keep
+        ctx.saved = None
+        return (None,) * 9 + grads
+
+
+def _ffn_views(f: FlatParams, n, kind: str) -> FfnWeights:
+    w = {"p": f.view16, "g": f.viewg}[kind]
+    s = {"p": f.view32, "g": f.viewg}[kind]
+    return FfnWeights(w1=w(n[14]), bf1=s(n[15]), w2=w(n[16]), bf2=s(n[17]), g=s(n[18]), b=s(n[19]))
+
+
 class PoNetModel(nn.Module):
     def __init__(self, config, add_pooling_layer: bool = True):
         super().__init__()
@@ -118,7 +206,6 @@ class PoNetModel(nn.Module):
         self._flat = FlatParams([(n, own[n]) for n in names], device)
         return self._flat
 
-    @torch.no_grad()
     def forward(self, input_ids=None, attention_mask=None, token_type_ids=None, segment_ids=None, position_ids=None, head_mask=None,
                 inputs_embeds=None, output_attentions=None, output_hidden_states=None, return_dict=None, **kwargs):
         cfg = self.config
@@ -133,8 +220,6 @@ class PoNetModel(nn.Module):
         return_dict = True if return_dict is None else return_dict
         B, S = input_ids.shape
         f = self._packed(input_ids.device)
-        H, heads, eps, dev = cfg.hidden_size, cfg.num_attention_heads, float(cfg.layer_norm_eps), input_ids.device
-        M = B * S
         if position_ids is None:
             position_ids = self.embeddings.position_ids[:, :S].expand(B, S)     # honours the driver's in-place 4096 tiling
         pos = position_ids.expand(B, S).contiguous().view(-1)
@@ -143,29 +228,13 @@ class PoNetModel(nn.Module):
         if attention_mask is not None:
             key_bias, _ = ops.mask_to_bias(attention_mask)
         seg = segment_ids.contiguous().to(torch.int64)
-        nseg = S + 2
-        x32 = torch.empty(M, H, dtype=F32, device=dev)
-        x16 = ops.embed_ln_fwd(input_ids.contiguous().view(-1), tt, pos, None, f.view32(EMB_NAMES[0]), f.view32(EMB_NAMES[1]),
-                               f.view32(EMB_NAMES[2]), f.view32(EMB_NAMES[3]), f.view32(EMB_NAMES[4]), eps, M, S, H, y32=x32)
-        hiddens = [x32.view(B, S, H)] if output_hidden_states else None
-        for i in range(cfg.num_hidden_layers):
-            n = ponet_layer_names(i)
-            proj = torch.empty(M, 5 * H, dtype=F16, device=dev)
-            ops.gemm(x16, f.view16(n[0], tuple(n[1:5])), proj, epilogue=ops.EPI_BIAS, bias=f.view32(n[5], tuple(n[6:10])))
-            mix = torch.empty(M, H, dtype=F16, device=dev)
-            ops.ponet_mix_fwd(proj, seg, mix, B, S, heads, nseg, key_bias=key_bias)
-            pre = torch.empty(M, H, dtype=F32, device=dev)
-            ops.gemm(mix, f.view16(n[10]), pre, epilogue=ops.EPI_BIAS_RES32, bias=f.view32(n[11]), aux=x32)
-            a32 = torch.empty(M, H, dtype=F32, device=dev)
-            a16 = ops.layernorm_fwd(pre, f.view32(n[12]), f.view32(n[13]), eps, y32=a32)
-            ffn = FfnWeights(w1=f.view16(n[14]), bf1=f.view32(n[15]), w2=f.view16(n[16]), bf2=f.view32(n[17]), g=f.view32(n[18]),
-                             b=f.view32(n[19]))
-            x16, x32, _ = ffn_block_fwd(ffn, a16, a32, eps, save=False)
-            if output_hidden_states:
-                hiddens.append(x32.view(B, S, H))
-        seq = x32.view(B, S, H)
+        params = [f.params[n] for n in f.names]
+        outs = _PoNetFn.apply(self, input_ids.contiguous().view(-1), tt, pos, key_bias, seg, B, S, bool(output_hidden_states), *params)
+        seq = outs[0]
+        hs = None
+        if output_hidden_states:
+            hs = tuple(outs[1:-1]) + (seq,)
         pooled = self.pooler(seq) if self.pooler is not None else None
-        hs = tuple(hiddens) if output_hidden_states else None
         if not return_dict:
             return (seq, pooled) + ((hs,) if hs is not None else ())
         return BaseModelOutputWithPoolingAndCrossAttentions(last_hidden_state=seq, pooler_output=pooled, hidden_states=hs, attentions=None)

@@ -265,3 +265,14 @@ def ponet_mix_bwd(proj: Tensor, dout: Tensor, seg_ids: Tensor, fwd_ws: Tensor, d
                                      dproj.stride(0), B, S, H, heads, nseg, _stream())
     L.check(rc, "b200_ponet_mix_bwd")
     return dproj
+
+
+def set_hyper(hyper: Tensor, *, lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, weight_decay: float = 0.0,
+              step: int = 1) -> None:
+    rc = L.load().b200_set_hyper(_ptr(hyper), lr, beta1, beta2, eps, weight_decay, 1.0 - beta1 ** step, 1.0 - beta2 ** step, _stream())
+    L.check(rc, "b200_set_hyper")
+
+
+def adamw_step_dev(p: Tensor, g: Tensor, m: Tensor, v: Tensor, p16: Optional[Tensor], hyper: Tensor, coef: Optional[Tensor]) -> None:
+    rc = L.load().b200_adamw_step_dev(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(p16), p.numel(), _ptr(hyper), _ptr(coef), _stream())
+    L.check(rc, "b200_adamw_step_dev")

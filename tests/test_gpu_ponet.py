@@ -56,3 +56,54 @@ def test_ponet_model_forward_matches_restatement():
     tup = m(ids.cuda(), attention_mask=mask.cuda(), segment_ids=seg.cuda(), return_dict=False)
     # (the global branch sums the queries with float atomics: run-to-run differences are rounding-level only)
     assert torch.allclose(tup[0], out.last_hidden_state, atol=1e-4, rtol=1e-4) and tup[1] is None
+
+
+def test_ponet_mixer_backward_matches_restatement_autograd():
+    _setup()
+    from oracle import ponet_oracle as P
+    from spokennlp_b200 import ops
+    B, S, heads = 2, 512, 2
+    H = heads * 64
+    g = torch.Generator().manual_seed(9)
+    proj = torch.randn(B, S, 5 * H, generator=g).half()
+    dout = (torch.randn(B, S, H, generator=g) * 0.5).half()
+    seg, mask = P.synth_segments(B, S, seed=4, pad_from=[512, 333])
+    pf = proj.float().requires_grad_(True)
+    ref = P.ponet_mixer(pf[..., :H], pf[..., H:2 * H], pf[..., 2 * H:3 * H], pf[..., 3 * H:4 * H], pf[..., 4 * H:], mask, seg, heads)
+    ref.backward(dout.float())
+    kb, _ = ops.mask_to_bias(mask.cuda())
+    pc = proj.view(B * S, 5 * H).cuda()
+    out = torch.empty(B * S, H, dtype=torch.float16, device="cuda")
+    ws = ops.ponet_mix_fwd(pc, seg.cuda(), out, B, S, heads, S + 2, key_bias=kb)
+    dproj = torch.full((B * S, 5 * H), float("nan"), dtype=torch.float16, device="cuda")
+    ops.ponet_mix_bwd(pc, dout.view(B * S, H).cuda(), seg.cuda(), ws, dproj, B, S, heads, S + 2, key_bias=kb)
+    got = dproj.float().cpu().view(B, S, 5 * H)
+    assert torch.isfinite(got).all()
+    for name, lo in (("dQ", 0), ("dK", H), ("dO", 2 * H), ("dSg", 3 * H), ("dLc", 4 * H)):
+        e = rel_err(got[..., lo:lo + H], pf.grad[..., lo:lo + H])
+        assert e < 3e-3, (name, e)
+
+
+def test_ponet_model_gradients_match_restatement_autograd():
+    _setup()
+    from oracle import bert_oracle as O
+    from oracle import ponet_oracle as P
+    from spokennlp_b200.modeling_ponet import PoNetConfig, PoNetModel
+    kw = dict(hidden_size=128, num_attention_heads=2, intermediate_size=256, num_hidden_layers=2, vocab_size=200,
+              max_position_embeddings=512, type_vocab_size=2)
+    sd0 = P.random_state_dict(O.OracleConfig(**kw), seed=6)
+    B, S = 2, 384
+    ids = torch.randint(0, 200, (B, S), generator=torch.Generator().manual_seed(2))
+    seg, mask = P.synth_segments(B, S, seed=8, pad_from=[384, 250])
+    w = torch.randn(B, S, 128, generator=torch.Generator().manual_seed(3)) * mask[:, :, None]
+    sd = {k: v.clone().requires_grad_(True) for k, v in sd0.items()}
+    (P.ponet_model(sd, O.OracleConfig(**kw), ids, mask, None, seg)[-1] * w).sum().backward()
+    m = PoNetModel(PoNetConfig(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, **kw), add_pooling_layer=False)
+    m.load_state_dict(sd0)
+    m = m.cuda().train()
+    out = m(ids.cuda(), attention_mask=mask.cuda(), segment_ids=seg.cuda(), return_dict=True).last_hidden_state
+    (out * w.cuda()).sum().backward()
+    for k, p in m.named_parameters():
+        ref = sd[k].grad
+        err = float((p.grad.double().cpu() - ref.double()).norm())
+        assert err <= 1.5e-2 * float(ref.double().norm()) + 1e-5, (k, err, float(ref.norm()))

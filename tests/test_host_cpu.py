@@ -70,3 +70,26 @@ def test_wgrad_split_heuristic_never_leaves_empty_splits():
         kb = (T + 63) // 64
         per = (kb + s - 1) // s
         assert s >= 1 and per * (s - 1) < kb
+
+
+def test_every_ops_and_library_reference_resolves():
+    """Static check (no GPU): every `ops.<name>` used by the host package exists, and every library symbol `ops.py` calls
+    is bound in lib.py — so a refactor cannot leave the GPU-only code paths pointing at missing functions."""
+    import ast
+    import glob
+    from spokennlp_b200 import lib as L
+    from spokennlp_b200 import ops
+    pkg = os.path.join(ROOT, "spokennlp_b200")
+    files = glob.glob(os.path.join(pkg, "*.py")) + [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")] + \
+        glob.glob(os.path.join(ROOT, "tests", "test_gpu_*.py")) + glob.glob(os.path.join(ROOT, "tools", "*.py"))
+    missing = []
+    for f in files:
+        tree = ast.parse(open(f).read())
+        for node in ast.walk(tree):
+            if isinstance(node, ast.Attribute) and isinstance(node.value, ast.Name) and node.value.id == "ops":
+                if not hasattr(ops, node.attr):
+                    missing.append((os.path.basename(f), node.attr))
+    assert not missing, missing
+    src = open(os.path.join(pkg, "ops.py")).read()
+    used = set(re.findall(r"\.(b200_[a-z0-9_]+)\(", src))
+    assert used <= set(L.exported_symbols()), used - set(L.exported_symbols())
