@@ -94,16 +94,16 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ reference (CPU) arm
-def cpu_reference_step_fn(torch, batch):
+def cpu_reference_step_fn(torch, batch, dropout=0.1):
     """The reference's own implementation of the path on host cores: HuggingFace `BertModel` (eager, fp32) — the class
     bert_for_ts.py:7 imports — + Linear(768,2) + CE + backward + clip + AdamW.  Falls back to the oracle port."""
     ids, mask, tt, labels = synth_batch(torch, batch, SEQ, 1234)
     try:
         from transformers import BertConfig, BertModel
-        cfg = BertConfig(attn_implementation="eager", hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, **CFG)
+        cfg = BertConfig(attn_implementation="eager", hidden_dropout_prob=dropout, attention_probs_dropout_prob=dropout, **CFG)
         torch.manual_seed(0)
-        bert = BertModel(cfg, add_pooling_layer=False)
-        head = torch.nn.Linear(768, 2)
+        bert = BertModel(cfg, add_pooling_layer=False).train()
+        head = torch.nn.Sequential(torch.nn.Dropout(dropout), torch.nn.Linear(768, 2)).train()      # bert_for_ts.py:66-67
         params = list(bert.parameters()) + list(head.parameters())
         opt = torch.optim.AdamW(params, lr=5e-5, weight_decay=0.0)
 
@@ -135,10 +135,10 @@ def cpu_reference_step_fn(torch, batch):
         return step, "port"
 
 
-def time_cpu_reference(torch, steps, warmup, batch):
+def time_cpu_reference(torch, steps, warmup, batch, dropout=0.1):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    step, kind = cpu_reference_step_fn(torch, batch)
+    step, kind = cpu_reference_step_fn(torch, batch, dropout)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
@@ -156,13 +156,13 @@ def run_reference_arm(args):
         return
     import torch
     steps, warmup = max(1, min(args.steps, 20)), max(1, min(args.warmup, 2))
-    r = time_cpu_reference(torch, steps, warmup, batch=1)
+    r = time_cpu_reference(torch, steps, warmup, batch=1, dropout=args.dropout)
     line = {"impl": "reference", "metric": "512-tok seq/sec BERT-base topic-seg fine-tune", "value": r["value"], "unit": "seq/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
             "config": {"workload": "emnlp2023-topic_segmentation BERT-base fine-tune, 512-tok windows (CPU reference path; "
                                    "each step is a bounded [1,512] sample of the bsz-32 workload)", "seq_len": SEQ,
-                       "global_batch": 1, "parallelism": "cpu"},
+                       "global_batch": 1, "parallelism": "cpu", "dropout": args.dropout},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -247,7 +247,7 @@ def run_b200_arm(args):
     from spokennlp_b200.trainer import DataParallelTrainer, TopicSegModel
 
     torch.manual_seed(0)
-    cfg = BertConfig(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, **CFG)
+    cfg = BertConfig(hidden_dropout_prob=args.dropout, attention_probs_dropout_prob=args.dropout, **CFG)
     model = TopicSegModel(cfg)
     trainer = DataParallelTrainer(model, lr=5e-5, total_steps=10 * (args.steps + args.warmup) + 1000)
     host = [t.pin_memory() for t in synth_batch(torch, BATCH, SEQ, 1234 + rank)]
@@ -302,14 +302,14 @@ def run_b200_arm(args):
         peaks, peak_src = load_peaks()
         kr = kernel_rooflines(torch, ops, peaks)
         dom = kr["gemm_ffn_up_gelu"]
-        cpu = time_cpu_reference(torch, steps=3, warmup=1, batch=2) if (world == 1 and not args.no_cpu_baseline) else None
+        cpu = time_cpu_reference(torch, steps=3, warmup=1, batch=2, dropout=args.dropout) if (world == 1 and not args.no_cpu_baseline) else None
         line = {
             "metric": "512-tok seq/sec BERT-base topic-seg fine-tune", "value": value, "unit": "seq/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "fp16 operands, fp32 accumulate/master", "data": "synthetic",
             "config": {"workload": "emnlp2023-topic_segmentation BERT-base fine-tune, 512-tok windows, bsz 32/GPU "
                                    "(fwd + bwd + grad allreduce + clip + AdamW)", "seq_len": SEQ, "batch_per_gpu": BATCH,
-                       "global_batch": BATCH * world, "parallelism": f"dp{world}", "dropout": 0.0, "cuda_graph": bool(graphed),
+                       "global_batch": BATCH * world, "parallelism": f"dp{world}", "dropout": args.dropout, "cuda_graph": bool(graphed),
                        "l2": "per-step working set ~5.4 GB of activations >> 126 MB L2 (no explicit flush needed)"},
             "encoder_flop_util": {"flop_per_seq": FLOP_PER_SEQ, "achieved_tflops_per_gpu": value / world * FLOP_PER_SEQ / 1e12,
                                   "peak_tflops_sustained": peaks["bf16_tflops_sustained"], "peak_source": peak_src,
@@ -326,7 +326,14 @@ def run_b200_arm(args):
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Tear-down: a captured step holds NCCL work; destroying the communicator (or letting the interpreter run the
+        # destructors) while the graph is alive can block for ever.  Drop the graph, drain the device, meet the peers once
+        # more, then leave without running NCCL's tear-down (the process is ending anyway).
+        trainer.release_graph()
+        barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
@@ -336,6 +343,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dropout", type=float, default=0.1, help="hidden / attention-probability / classifier dropout (reference default 0.1)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph of the step")
     args = ap.parse_args()
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:

@@ -172,6 +172,39 @@ int b200_set_hyper(float* hyper, float lr, float beta1, float beta2, float eps, 
 int b200_adamw_step_dev(float* p, const float* g, float* m, float* v, void* p16, size_t n, const float* hyper, const float* coef,
                         void* stream);
 
+/*
+ * Dropout-enabled variants (reference: nn.Dropout at bert_model.py:209 (embeddings), :338 (attention probabilities), :373 and
+ * :451 (hidden, before the residual), bert_for_ts.py:66-67 (classifier input)).  Masks are a stateless hash of
+ * (*seed, site, element index): nothing is stored, the backward regenerates the forward's mask from the same (seed, site).
+ * `seed` is a DEVICE pointer to the per-step base seed (so a replayed CUDA graph draws fresh masks); seed == NULL or p == 0
+ * turns dropout off and makes each call identical to its plain counterpart.  Kept elements are scaled by 1/(1-p).
+ */
+int b200_gemm_f16_drop(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int epilogue, const float* bias, const void* aux,
+                       int ld_aux, void* out, int ld_out, int out_dtype, const uint32_t* seed, unsigned site, float p, void* stream);
+/* as b200_layernorm_bwd; additionally dx_drop = dx * mask/(1-p) (what the dense layer's dgrad/wgrad consume; dbias sums dx_drop) */
+int b200_layernorm_bwd_drop(const void* dy, const void* dy2, const void* x, int x_dtype, const float* mean, const float* rstd, const float* gamma,
+                            void* dx, void* dx_drop, float* dgamma, float* dbeta, float* dbias, const float* alpha, int rows, int H,
+                            const uint32_t* seed, unsigned site, float p, void* stream);
+int b200_embed_ln_fwd_drop(const int64_t* ids, const int64_t* tt, const int64_t* pos, const float* inputs_embeds, const float* word,
+                           const float* pos_tab, const float* type_tab, const float* gamma, const float* beta, void* y, float* y32, int rows, int S,
+                           int H, float eps, const uint32_t* seed, unsigned site, float p, void* stream);
+int b200_embed_ln_bwd_drop(const void* dy, const void* dy2, const int64_t* ids, const int64_t* tt, const int64_t* pos, const float* word,
+                           const float* pos_tab, const float* type_tab, const float* gamma, float* dword, float* dpos, float* dtype_tab,
+                           float* dgamma, float* dbeta, const float* alpha, int rows, int S, int H, float eps, const uint32_t* seed,
+                           unsigned site, float p, void* stream);
+int b200_attn_fwd_drop(const void* q, int ldq, int q_col0, const void* kv, int ldkv, int k_col0, int v_col0, const float* key_bias,
+                       const int32_t* kv_len, void* ctx, int ld_out, float* lse2, int B, int heads, int Sq, int Sk, const uint32_t* seed,
+                       unsigned site, float p, void* stream);
+int b200_attn_bwd_drop(const void* q, int ldq, int q_col0, const void* kv, int ldkv, int k_col0, int v_col0, const void* dctx, int ld_dctx,
+                       const void* ctx, int ld_ctx, const float* key_bias, const int32_t* kv_len, const float* lse2, void* workspace,
+                       void* dq, int ld_dq, int dq_col0, void* dkv, int ld_dkv, int dk_col0, int dv_col0, int B, int heads, int Sq, int Sk,
+                       const uint32_t* seed, unsigned site, float p, void* stream);
+int b200_cls_head_fwd_drop(const void* h, const float* W, const float* b, float* logits, int32_t* argmax, int rows, int H, int C,
+                           const uint32_t* seed, unsigned site, float p, void* stream);
+int b200_cls_head_bwd_drop(const void* h, const float* logits, const int64_t* labels, const float* class_weight, const float* stats, const float* W,
+                           const float* scale, void* dh, float* dW, float* db, int rows, int H, int C, const uint32_t* seed, unsigned site,
+                           float p, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -107,8 +107,8 @@ def embeddings(sd: Dict[str, Tensor], cfg: OracleConfig, input_ids: Tensor,
                token_type_ids: Optional[Tensor] = None,
                position_ids: Optional[Tensor] = None,
                inputs_embeds: Optional[Tensor] = None,
-               prefix: str = "embeddings.") -> Tensor:
-    """LN(word[ids] + type[tt] + pos[pos]) — bert_model.py:184-210 (dropout off)."""
+               prefix: str = "embeddings.", masks: Optional[Dict[str, Tensor]] = None) -> Tensor:
+    """LN(word[ids] + type[tt] + pos[pos]) — bert_model.py:184-210; `masks["emb"]` = the dropout multiplier of :209."""
     if inputs_embeds is None:
         inputs_embeds = sd[prefix + "word_embeddings.weight"][input_ids]
     B, S = inputs_embeds.shape[:2]
@@ -119,12 +119,22 @@ def embeddings(sd: Dict[str, Tensor], cfg: OracleConfig, input_ids: Tensor,
     e = (inputs_embeds
          + sd[prefix + "token_type_embeddings.weight"][token_type_ids]
          + sd[prefix + "position_embeddings.weight"][position_ids])
-    return layer_norm(e, sd[prefix + "LayerNorm.weight"], sd[prefix + "LayerNorm.bias"],
-                      cfg.layer_norm_eps)
+    y = layer_norm(e, sd[prefix + "LayerNorm.weight"], sd[prefix + "LayerNorm.bias"],
+                   cfg.layer_norm_eps)
+    return _drop(y, masks, "emb")
+
+
+def _drop(x: Tensor, masks: Optional[Dict[str, Tensor]], key: str) -> Tensor:
+    """nn.Dropout in training mode with the mask made explicit: `masks[key]` holds 0 or 1/(1-p) per element (absent key
+    = identity).  The reference draws its masks from torch's generator; which elements fall is not part of the
+    algorithm, so parity under dropout is "same function of (input, mask)"."""
+    if masks is None or key not in masks:
+        return x
+    return x * masks[key].reshape(x.shape).to(x.dtype)
 
 
 def attention_core(q: Tensor, k: Tensor, v: Tensor, n_heads: int,
-                   add_mask: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
+                   add_mask: Optional[Tensor], prob_mask: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
     """softmax(Q K^T / sqrt(d) + mask) V with head split/merge.
 
     q: [B,Sq,H]; k,v: [B,Sk,H].  Returns (context [B,Sq,H], probs [B,h,Sq,Sk]).
@@ -141,12 +151,13 @@ def attention_core(q: Tensor, k: Tensor, v: Tensor, n_heads: int,
     if add_mask is not None:
         scores = scores + add_mask
     probs = torch.softmax(scores, dim=-1)
-    ctx = (probs @ vh).permute(0, 2, 1, 3).reshape(B, Sq, H)
+    dropped = probs if prob_mask is None else probs * prob_mask.to(probs.dtype)       # bert_model.py:338
+    ctx = (dropped @ vh).permute(0, 2, 1, 3).reshape(B, Sq, H)
     return ctx, probs
 
 
 def self_attention_block(sd, p: str, cfg: OracleConfig, x: Tensor, add_mask,
-                         kv_states: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+                         kv_states: Optional[Tensor] = None, masks: Optional[Dict[str, Tensor]] = None) -> Tuple[Tensor, Tensor]:
     """BertAttention = BertSelfAttention + BertSelfOutput.
 
     `kv_states` (cross-attention, bert_model.py:283-286) makes K/V come from
@@ -156,25 +167,26 @@ def self_attention_block(sd, p: str, cfg: OracleConfig, x: Tensor, add_mask,
     q = linear(x, sd[p + "self.query.weight"], sd[p + "self.query.bias"])
     k = linear(src, sd[p + "self.key.weight"], sd[p + "self.key.bias"])
     v = linear(src, sd[p + "self.value.weight"], sd[p + "self.value.bias"])
-    ctx, probs = attention_core(q, k, v, cfg.num_attention_heads, add_mask)
-    y = linear(ctx, sd[p + "output.dense.weight"], sd[p + "output.dense.bias"])
+    ctx, probs = attention_core(q, k, v, cfg.num_attention_heads, add_mask, None if masks is None else masks.get(p + "probs"))
+    y = _drop(linear(ctx, sd[p + "output.dense.weight"], sd[p + "output.dense.bias"]), masks, p + "out")       # :373
     y = layer_norm(y + x, sd[p + "output.LayerNorm.weight"], sd[p + "output.LayerNorm.bias"],
                    cfg.layer_norm_eps)
     return y, probs
 
 
-def ffn_block(sd, p: str, cfg: OracleConfig, x: Tensor) -> Tensor:
+def ffn_block(sd, p: str, cfg: OracleConfig, x: Tensor, masks: Optional[Dict[str, Tensor]] = None) -> Tensor:
     """BertIntermediate + BertOutput — bert_model.py:436-439, 449-453."""
     h = gelu_erf(linear(x, sd[p + "intermediate.dense.weight"], sd[p + "intermediate.dense.bias"]))
-    y = linear(h, sd[p + "output.dense.weight"], sd[p + "output.dense.bias"])
+    y = _drop(linear(h, sd[p + "output.dense.weight"], sd[p + "output.dense.bias"]), masks, p + "ffn_out")     # :451
     return layer_norm(y + x, sd[p + "output.LayerNorm.weight"], sd[p + "output.LayerNorm.bias"],
                       cfg.layer_norm_eps)
 
 
-def bert_layer(sd, p: str, cfg: OracleConfig, x: Tensor, add_mask) -> Tuple[Tensor, Tensor]:
-    """One BertLayer / BertSelfAttnLayer — bert_model.py:518-553."""
-    a, probs = self_attention_block(sd, p + "attention.", cfg, x, add_mask)
-    return ffn_block(sd, p, cfg, a), probs
+def bert_layer(sd, p: str, cfg: OracleConfig, x: Tensor, add_mask, masks: Optional[Dict[str, Tensor]] = None) -> Tuple[Tensor, Tensor]:
+    """One BertLayer / BertSelfAttnLayer — bert_model.py:518-553.  Dropout multipliers (training mode) are looked up in
+    `masks` under p+"attention.probs", p+"attention.out", p+"ffn_out"."""
+    a, probs = self_attention_block(sd, p + "attention.", cfg, x, add_mask, masks=masks)
+    return ffn_block(sd, p, cfg, a, masks), probs
 
 
 def bert_cross_layer(sd, p: str, cfg: OracleConfig, x: Tensor, kv: Tensor,
@@ -202,13 +214,13 @@ class BertOracleOutput:
 def bert_model(sd: Dict[str, Tensor], cfg: OracleConfig, input_ids: Optional[Tensor] = None,
                attention_mask: Optional[Tensor] = None, token_type_ids: Optional[Tensor] = None,
                position_ids: Optional[Tensor] = None, inputs_embeds: Optional[Tensor] = None,
-               mask_fill: Optional[float] = None) -> BertOracleOutput:
-    """BertModel.forward in eval mode (all dropouts are identity)."""
-    x = embeddings(sd, cfg, input_ids, token_type_ids, position_ids, inputs_embeds)
+               mask_fill: Optional[float] = None, masks: Optional[Dict[str, Tensor]] = None) -> BertOracleOutput:
+    """BertModel.forward; eval mode (dropouts are identity) unless explicit dropout multipliers are given in `masks`."""
+    x = embeddings(sd, cfg, input_ids, token_type_ids, position_ids, inputs_embeds, masks=masks)
     add_mask = additive_key_mask(attention_mask, x.dtype, mask_fill)
     hs, atts = [x], []
     for i in range(cfg.num_hidden_layers):
-        x, probs = bert_layer(sd, f"encoder.layer.{i}.", cfg, x, add_mask)
+        x, probs = bert_layer(sd, f"encoder.layer.{i}.", cfg, x, add_mask, masks)
         hs.append(x)
         atts.append(probs)
     pooled = pooler(sd, x) if "pooler.dense.weight" in sd else None
@@ -266,12 +278,12 @@ def ditto_pool(out: BertOracleOutput, attention_mask: Tensor, layer: int, head: 
 
 def topicseg_loss(sd: Dict[str, Tensor], cfg: OracleConfig, cls_w: Tensor, cls_b: Tensor,
                   input_ids: Tensor, attention_mask: Tensor, token_type_ids: Tensor,
-                  labels: Tensor) -> Tuple[Tensor, Tensor]:
+                  labels: Tensor, masks: Optional[Dict[str, Tensor]] = None) -> Tuple[Tensor, Tensor]:
     """Encoder -> Linear(H->2) -> CE(ignore -100): the `ts_score_predictor == "lt"`
     path of LossCalculator with CSSL/TSSP weights 0 and dropout off.  Used for
     gradient parity (the wrapper itself cannot run backward on CPU: SURVEY §8c trap 1)."""
-    out = bert_model(sd, cfg, input_ids, attention_mask, token_type_ids)
-    logits = token_cls_logits(out.last_hidden_state, cls_w, cls_b)
+    out = bert_model(sd, cfg, input_ids, attention_mask, token_type_ids, masks=masks)
+    logits = token_cls_logits(_drop(out.last_hidden_state, masks, "head"), cls_w, cls_b)       # bert_for_ts.py:66-67
     return cross_entropy(logits, labels), logits
 
 

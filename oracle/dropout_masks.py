@@ -1,0 +1,76 @@
+"""Numpy restatement of the B200 path's counter-based dropout masks (TEST INFRASTRUCTURE ONLY).
+
+Not a restatement of the reference: the reference draws nn.Dropout masks from torch's Philox stream, and which elements
+fall is not part of the algorithm.  The CUDA path instead hashes (step seed, site id, element index) — see
+`spokennlp_b200/csrc/ptx.cuh` (`drop_hash`, `drop_seed`, `drop_pair`) — so that nothing is stored and the backward
+regenerates the forward's mask.  This file repeats that hash on the host so the tests can hand the SAME masks to
+`bert_oracle` (its `masks=` argument) and compare values and gradients under dropout.
+
+Conventions: one 32-bit hash per PAIR of consecutive elements (low 16 bits -> even element, high 16 -> odd element); an
+element is kept iff its 16-bit lane >= round(p * 65536); kept elements are multiplied by 1/(1-p).
+  hidden / embedding / classifier-input sites, tensor [rows, H]:  element index = row * H + col
+  attention-probability sites, tensor [B, heads, Sq, Sk]:         pair index = ((b*heads + h)*Sq + q) * ceil(Sk/2) + key//2
+Site ids: layer*8 + {0: probabilities, 1: attention output dense, 2: FFN output dense, 3/4: cross-attention}, 0xE000
+embeddings, 0xE001 classifier input (spokennlp_b200/engine.py: DropPlan).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+M32 = np.uint64(0xFFFFFFFF)
+
+
+def _hash(idx: np.ndarray, seed: np.ndarray) -> np.ndarray:
+    h = ((idx.astype(np.uint64) ^ seed.astype(np.uint64)) * np.uint64(0x9E3779B1)) & M32
+    h ^= h >> np.uint64(15)
+    h = (h * np.uint64(0x85EBCA6B)) & M32
+    h ^= h >> np.uint64(13)
+    return h
+
+
+def site_seed(base_seed: int, site: int) -> np.ndarray:
+    idx = np.array([(site * 0x632BE5AB + 0x7F4A7C15) & 0xFFFFFFFF], dtype=np.uint64)
+    return _hash(idx, np.array([base_seed & 0xFFFFFFFF], dtype=np.uint64))
+
+
+def _lanes(pairs: np.ndarray, base_seed: int, site: int, p: float):
+    h = _hash(pairs, site_seed(base_seed, site))
+    thr = np.uint64(int(p * 65536.0 + 0.5))
+    scale = np.float32(1.0) / (np.float32(1.0) - np.float32(p))
+    lo = np.where((h & np.uint64(0xFFFF)) >= thr, scale, np.float32(0)).astype(np.float32)
+    hi = np.where((h >> np.uint64(16)) >= thr, scale, np.float32(0)).astype(np.float32)
+    return lo, hi
+
+
+def hidden_mask(base_seed: int, site: int, p: float, rows: int, H: int) -> torch.Tensor:
+    """[rows, H] multipliers (H even)."""
+    pairs = np.arange(rows * H // 2, dtype=np.uint64)
+    lo, hi = _lanes(pairs, base_seed, site, p)
+    return torch.from_numpy(np.stack([lo, hi], axis=1).reshape(rows, H))
+
+
+def prob_mask(base_seed: int, site: int, p: float, B: int, heads: int, Sq: int, Sk: int) -> torch.Tensor:
+    """[B, heads, Sq, Sk] multipliers."""
+    skp = (Sk + 1) // 2
+    pairs = np.arange(B * heads * Sq * skp, dtype=np.uint64)
+    lo, hi = _lanes(pairs, base_seed, site, p)
+    full = np.stack([lo, hi], axis=1).reshape(B, heads, Sq, 2 * skp)
+    return torch.from_numpy(np.ascontiguousarray(full[..., :Sk]))
+
+
+def bert_masks(base_seed: int, p_hidden: float, p_attn: float, n_layers: int, B: int, S: int, H: int, heads: int, head_site: bool = True):
+    """The `masks` dict `bert_oracle.bert_model` / `topicseg_loss` take, for one training forward of the B200 engine."""
+    m = {}
+    if p_hidden > 0:
+        m["emb"] = hidden_mask(base_seed, 0xE000, p_hidden, B * S, H).view(B, S, H)
+        if head_site:
+            m["head"] = hidden_mask(base_seed, 0xE001, p_hidden, B * S, H).view(B, S, H)
+    for i in range(n_layers):
+        pre = f"encoder.layer.{i}."
+        if p_attn > 0:
+            m[pre + "attention.probs"] = prob_mask(base_seed, i * 8 + 0, p_attn, B, heads, S, S)
+        if p_hidden > 0:
+            m[pre + "attention.out"] = hidden_mask(base_seed, i * 8 + 1, p_hidden, B * S, H).view(B, S, H)
+            m[pre + "ffn_out"] = hidden_mask(base_seed, i * 8 + 2, p_hidden, B * S, H).view(B, S, H)
+    return m

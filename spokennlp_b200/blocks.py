@@ -58,6 +58,8 @@ class AttnSaved:
     pre: Tensor = None
     mean: Tensor = None
     rstd: Tensor = None
+    drop_attn: Optional[ops.Dropout] = None      # dropout on the attention probabilities (bert_model.py:338)
+    drop_hidden: Optional[ops.Dropout] = None    # dropout on the output dense, before the residual (bert_model.py:373)
 
 
 @dataclass
@@ -68,11 +70,14 @@ class FfnSaved:
     pre: Tensor = None
     mean: Tensor = None
     rstd: Tensor = None
+    drop_hidden: Optional[ops.Dropout] = None    # bert_model.py:451
 
 
 def attn_block_fwd(p: AttnWeights, x16: Tensor, x32: Tensor, B: int, Sq: int, heads: int, eps: float, key_bias, kv_len, *,
-                   save: bool, want_probs: bool = False, kv16: Optional[Tensor] = None, Sk: Optional[int] = None):
-    """bert_model.py:259-375 (BertSelfAttention + BertSelfOutput).  Returns (y16, y32, saved, probs)."""
+                   save: bool, want_probs: bool = False, kv16: Optional[Tensor] = None, Sk: Optional[int] = None,
+                   drop_attn: Optional[ops.Dropout] = None, drop_hidden: Optional[ops.Dropout] = None):
+    """bert_model.py:259-375 (BertSelfAttention + BertSelfOutput).  Returns (y16, y32, saved, probs).  `probs` are the
+    probabilities BEFORE dropout."""
     H, Mq, dev = heads * 64, B * Sq, x16.device
     cross = kv16 is not None
     Sk = Sk if cross else Sq
@@ -89,21 +94,22 @@ def attn_block_fwd(p: AttnWeights, x16: Tensor, x32: Tensor, B: int, Sq: int, he
         cols = dict(q_col0=0, k_col0=H, v_col0=2 * H)
     ctx = torch.empty(Mq, H, dtype=F16, device=dev)
     lse2 = torch.empty(B, heads, Sq, dtype=F32, device=dev) if (save or want_probs) else None
-    ops.attn_fwd(q, kv, ctx, B, heads, Sq, Sk, key_bias=key_bias, kv_len=kv_len, lse2=lse2, **cols)
+    ops.attn_fwd(q, kv, ctx, B, heads, Sq, Sk, key_bias=key_bias, kv_len=kv_len, lse2=lse2, drop=drop_attn, **cols)
     probs = None
     if want_probs:
         probs = ops.attn_probs(q, kv, lse2, B, heads, Sq, Sk, q_col0=cols["q_col0"], k_col0=cols["k_col0"], key_bias=key_bias)
     pre = torch.empty(Mq, H, dtype=F32, device=dev)
-    ops.gemm(ctx, p.wo, pre, epilogue=ops.EPI_BIAS_RES32, bias=p.bo, aux=x32)
+    ops.gemm(ctx, p.wo, pre, epilogue=ops.EPI_BIAS_RES32, bias=p.bo, aux=x32, drop=drop_hidden)
     mean = torch.empty(Mq, dtype=F32, device=dev) if save else None
     rstd = torch.empty(Mq, dtype=F32, device=dev) if save else None
     y32 = torch.empty(Mq, H, dtype=F32, device=dev)
     y16 = ops.layernorm_fwd(pre, p.g, p.b, eps, y32=y32, mean=mean, rstd=rstd)
-    sv = AttnSaved(x16=x16, kv16=kv16, q=q, kv=kv if cross else None, ctx=ctx, lse2=lse2, pre=pre, mean=mean, rstd=rstd) if save else None
+    sv = AttnSaved(x16=x16, kv16=kv16, q=q, kv=kv if cross else None, ctx=ctx, lse2=lse2, pre=pre, mean=mean, rstd=rstd,
+                   drop_attn=drop_attn, drop_hidden=drop_hidden) if save else None
     return y16, y32, sv, probs
 
 
-def ffn_block_fwd(p: FfnWeights, x16: Tensor, x32: Tensor, eps: float, *, save: bool):
+def ffn_block_fwd(p: FfnWeights, x16: Tensor, x32: Tensor, eps: float, *, save: bool, drop_hidden: Optional[ops.Dropout] = None):
     """bert_model.py:436-453 (BertIntermediate + BertOutput).  Returns (y16, y32, saved)."""
     M, H, dev = x16.shape[0], x16.shape[1], x16.device
     inter = p.w1.shape[0]
@@ -111,13 +117,28 @@ def ffn_block_fwd(p: FfnWeights, x16: Tensor, x32: Tensor, eps: float, *, save: 
     dact = torch.empty(M, inter, dtype=F16, device=dev) if save else None
     ops.gemm(x16, p.w1, h, epilogue=ops.EPI_BIAS_GELU, bias=p.bf1, out2=dact)
     pre = torch.empty(M, H, dtype=F32, device=dev)
-    ops.gemm(h, p.w2, pre, epilogue=ops.EPI_BIAS_RES32, bias=p.bf2, aux=x32)
+    ops.gemm(h, p.w2, pre, epilogue=ops.EPI_BIAS_RES32, bias=p.bf2, aux=x32, drop=drop_hidden)
     mean = torch.empty(M, dtype=F32, device=dev) if save else None
     rstd = torch.empty(M, dtype=F32, device=dev) if save else None
     y32 = torch.empty(M, H, dtype=F32, device=dev)
     y16 = ops.layernorm_fwd(pre, p.g, p.b, eps, y32=y32, mean=mean, rstd=rstd)
-    sv = FfnSaved(x16=x16, dact=dact, h=h, pre=pre, mean=mean, rstd=rstd) if save else None
+    sv = FfnSaved(x16=x16, dact=dact, h=h, pre=pre, mean=mean, rstd=rstd, drop_hidden=drop_hidden) if save else None
     return y16, y32, sv
+
+
+def _ln_bwd(dy, dy2, sv, gamma, dgamma, dbeta, dbias, inv_scale):
+    """LayerNorm backward of a block's closing `LayerNorm(dropout(dense(.)) + x)`.  Returns (d_pre, d_dense): the gradient
+    wrt the pre-LayerNorm sum (what the residual path carries) and wrt the dense output (the same tensor unless hidden
+    dropout is on, in which case it is d_pre times the regenerated forward mask)."""
+    d_pre = torch.empty(dy.shape, dtype=F16, device=dy.device)
+    dr = sv.drop_hidden
+    if dr is None or dr.p <= 0.0:
+        ops.layernorm_bwd(dy, sv.pre, sv.mean, sv.rstd, gamma, d_pre, dgamma, dbeta, dy2=dy2, dbias=dbias, alpha=inv_scale)
+        return d_pre, d_pre
+    d_den = torch.empty_like(d_pre)
+    ops.layernorm_bwd(dy, sv.pre, sv.mean, sv.rstd, gamma, d_pre, dgamma, dbeta, dy2=dy2, dbias=dbias, alpha=inv_scale, dx_drop=d_den,
+                      drop=dr)
+    return d_pre, d_den
 
 
 def ffn_block_bwd(p: FfnWeights, g: FfnWeights, sv: FfnSaved, dy: Tensor, inv_scale, dy2: Optional[Tensor] = None) -> Tensor:
@@ -125,11 +146,10 @@ def ffn_block_bwd(p: FfnWeights, g: FfnWeights, sv: FfnSaved, dy: Tensor, inv_sc
     (dense path + residual path)."""
     M, H = dy.shape
     inter, dev = p.w1.shape[0], dy.device
-    d_pre = torch.empty(M, H, dtype=F16, device=dev)
-    ops.layernorm_bwd(dy, sv.pre, sv.mean, sv.rstd, p.g, d_pre, g.g, g.b, dy2=dy2, dbias=g.bf2, alpha=inv_scale)
-    ops.gemm(d_pre, sv.h, g.w2, a_layout=1, b_layout=1, epilogue=ops.EPI_ATOMIC, alpha=inv_scale, k_splits=ops.wgrad_splits(H, inter, M))
+    d_pre, d_den = _ln_bwd(dy, dy2, sv, p.g, g.g, g.b, g.bf2, inv_scale)
+    ops.gemm(d_den, sv.h, g.w2, a_layout=1, b_layout=1, epilogue=ops.EPI_ATOMIC, alpha=inv_scale, k_splits=ops.wgrad_splits(H, inter, M))
     dz = torch.empty(M, inter, dtype=F16, device=dev)
-    ops.gemm(d_pre, p.w2, dz, b_layout=1, epilogue=ops.EPI_DGELU, aux=sv.dact)
+    ops.gemm(d_den, p.w2, dz, b_layout=1, epilogue=ops.EPI_DGELU, aux=sv.dact)
     ops.colsum(dz, g.bf1, inv_scale)
     ops.gemm(dz, sv.x16, g.w1, a_layout=1, b_layout=1, epilogue=ops.EPI_ATOMIC, alpha=inv_scale, k_splits=ops.wgrad_splits(inter, H, M))
     dx = torch.empty(M, H, dtype=F16, device=dev)
@@ -144,16 +164,15 @@ def attn_block_bwd(p: AttnWeights, g: AttnWeights, sv: AttnSaved, dy: Tensor, B:
     H, Mq, dev = heads * 64, B * Sq, dy.device
     cross = sv.kv16 is not None
     Sk = Sk if cross else Sq
-    d_pre = torch.empty(Mq, H, dtype=F16, device=dev)
-    ops.layernorm_bwd(dy, sv.pre, sv.mean, sv.rstd, p.g, d_pre, g.g, g.b, dy2=dy2, dbias=g.bo, alpha=inv_scale)
-    ops.gemm(d_pre, sv.ctx, g.wo, a_layout=1, b_layout=1, epilogue=ops.EPI_ATOMIC, alpha=inv_scale, k_splits=ops.wgrad_splits(H, H, Mq))
+    d_pre, d_den = _ln_bwd(dy, dy2, sv, p.g, g.g, g.b, g.bo, inv_scale)
+    ops.gemm(d_den, sv.ctx, g.wo, a_layout=1, b_layout=1, epilogue=ops.EPI_ATOMIC, alpha=inv_scale, k_splits=ops.wgrad_splits(H, H, Mq))
     dctx = torch.empty(Mq, H, dtype=F16, device=dev)
-    ops.gemm(d_pre, p.wo, dctx, b_layout=1)
+    ops.gemm(d_den, p.wo, dctx, b_layout=1)
     dx = torch.empty(Mq, H, dtype=F16, device=dev)
     if not cross:
         dqkv = torch.empty(Mq, 3 * H, dtype=F16, device=dev)
         ops.attn_bwd(sv.q, sv.q, dctx, sv.ctx, sv.lse2, dqkv, dqkv, ws, B, heads, Sq, Sq, q_col0=0, k_col0=H, v_col0=2 * H, dq_col0=0,
-                     dk_col0=H, dv_col0=2 * H, key_bias=key_bias, kv_len=kv_len)
+                     dk_col0=H, dv_col0=2 * H, key_bias=key_bias, kv_len=kv_len, drop=sv.drop_attn)
         ops.colsum(dqkv, g.bqkv, inv_scale)
         ops.gemm(dqkv, sv.x16, g.wqkv, a_layout=1, b_layout=1, epilogue=ops.EPI_ATOMIC, alpha=inv_scale,
                  k_splits=ops.wgrad_splits(3 * H, H, Mq))
@@ -163,7 +182,7 @@ def attn_block_bwd(p: AttnWeights, g: AttnWeights, sv: AttnSaved, dy: Tensor, B:
     dq = torch.empty(Mq, H, dtype=F16, device=dev)
     dkv = torch.empty(Mk, 2 * H, dtype=F16, device=dev)
     ops.attn_bwd(sv.q, sv.kv, dctx, sv.ctx, sv.lse2, dq, dkv, ws, B, heads, Sq, Sk, q_col0=0, k_col0=0, v_col0=H, dq_col0=0, dk_col0=0,
-                 dv_col0=H, key_bias=key_bias, kv_len=kv_len)
+                 dv_col0=H, key_bias=key_bias, kv_len=kv_len, drop=sv.drop_attn)
     ops.colsum(dq, g.bq, inv_scale)
     ops.colsum(dkv, g.bkv, inv_scale)
     ops.gemm(dq, sv.x16, g.wq, a_layout=1, b_layout=1, epilogue=ops.EPI_ATOMIC, alpha=inv_scale, k_splits=ops.wgrad_splits(H, H, Mq))

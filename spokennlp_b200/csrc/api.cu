@@ -143,6 +143,12 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g,
 std::atomic<int> g_gemm_impl{2};
 std::atomic<int> g_gemm_dbg{0};
 
+const DropCfg kNoDrop{nullptr, 0, 0, 1.0f};
+DropCfg make_drop(const uint32_t* seed, unsigned site, float p) {
+  if (!seed || p <= 0.f) return kNoDrop;
+  return DropCfg{seed, site, static_cast<uint32_t>(p * 65536.0f + 0.5f), 1.0f / (1.0f - p)};
+}
+
 template <int BN, int A_MN, int B_MN, int EPI, typename OutT>
 int launch_gemm2(const Gemm2Maps& maps, const GemmArgs& g, cudaStream_t s) {
   auto kern = gemm2_f16_kernel<BN, A_MN, B_MN, EPI, OutT>;
@@ -167,9 +173,29 @@ const char* b200_last_error(void) { return g_err.c_str(); }
 int b200_version(void) { return 100; }
 long long b200_launch_count(void) { return g_launches.load(); }
 
+static int gemm_impl(const void* A, int lda, int a_layout, const void* B, int ldb, int b_layout, int M, int N, int K, int epilogue,
+                     const float* bias, const void* aux, int ld_aux, void* out, int ld_out, int out_dtype, void* out2, int ld_out2,
+                     const float* alpha, int k_splits, DropCfg drop, void* stream);
+
 int b200_gemm_f16(const void* A, int lda, int a_layout, const void* B, int ldb, int b_layout, int M, int N, int K, int epilogue,
                   const float* bias, const void* aux, int ld_aux, void* out, int ld_out, int out_dtype, void* out2, int ld_out2,
                   const float* alpha, int k_splits, void* stream) {
+  return gemm_impl(A, lda, a_layout, B, ldb, b_layout, M, N, K, epilogue, bias, aux, ld_aux, out, ld_out, out_dtype, out2, ld_out2, alpha,
+                   k_splits, DropCfg{nullptr, 0, 0, 1.0f}, stream);
+}
+
+int b200_gemm_f16_drop(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int epilogue, const float* bias, const void* aux,
+                       int ld_aux, void* out, int ld_out, int out_dtype, const uint32_t* seed, unsigned site, float p, void* stream) {
+  if (epilogue != EPI_BIAS_RES32 && epilogue != EPI_BIAS_RES) return fail(B200_ERR_SHAPE, "gemm_drop: dropout is fused into the residual epilogues only");
+  if (p < 0.f || p >= 1.f) return fail(B200_ERR_SHAPE, "gemm_drop: p must be in [0,1)");
+  if (g_gemm_impl.load() != 2 && seed && p > 0.f) return fail(B200_ERR_SHAPE, "gemm_drop: dropout needs the 2-CTA kernel");
+  return gemm_impl(A, lda, 0, B, ldb, 0, M, N, K, epilogue, bias, aux, ld_aux, out, ld_out, out_dtype, nullptr, 0, nullptr, 1,
+                   make_drop(seed, site, p), stream);
+}
+
+static int gemm_impl(const void* A, int lda, int a_layout, const void* B, int ldb, int b_layout, int M, int N, int K, int epilogue,
+                     const float* bias, const void* aux, int ld_aux, void* out, int ld_out, int out_dtype, void* out2, int ld_out2,
+                     const float* alpha, int k_splits, DropCfg drop, void* stream) {
   if (M <= 0 || N <= 0 || K <= 0) return fail(B200_ERR_SHAPE, "gemm: empty problem %dx%dx%d", M, N, K);
   if ((N % 4) || (ld_out % 4)) return fail(B200_ERR_SHAPE, "gemm: N and ld_out must be multiples of 4 (N=%d ld_out=%d)", N, ld_out);
   if (!A || !B || !out) return fail(B200_ERR_SHAPE, "gemm: null operand");
@@ -198,7 +224,7 @@ int b200_gemm_f16(const void* A, int lda, int a_layout, const void* B, int ldb, 
                                 (needs_aux && (reinterpret_cast<uintptr_t>(aux) & 15)) || (out2 && (reinterpret_cast<uintptr_t>(out2) & 15))))
       return fail(B200_ERR_SHAPE, "gemm: aux / out2 need N %% 8 == 0 and 16-byte aligned rows");
     GemmArgs g2{M, N, K, k_splits > 0 ? k_splits : 1, bias, static_cast<const __half*>(aux), ld_aux, out, ld_out,
-                static_cast<__half*>(out2), ld_out2, alpha, g_gemm_dbg.load()};
+                static_cast<__half*>(out2), ld_out2, alpha, drop, g_gemm_dbg.load()};
     switch (a_layout * 1000 + b_layout * 100 + epilogue * 10 + out_dtype) {
       case 0 * 1000 + 0 * 100 + EPI_STORE * 10 + B200_DT_F16: return launch_gemm2<BN, 0, 0, EPI_STORE, __half>(mp, g2, s);
       case 0 * 1000 + 0 * 100 + EPI_STORE * 10 + B200_DT_F32: return launch_gemm2<BN, 0, 0, EPI_STORE, float>(mp, g2, s);
@@ -223,7 +249,7 @@ int b200_gemm_f16(const void* A, int lda, int a_layout, const void* B, int ldb, 
   rc = b_layout == 0 ? get_tmap(B, N, K, ldb, BN, &tb) : get_tmap(B, K, N, ldb, GEMM_BK, &tb);
   if (rc) return rc;
   GemmArgs g{M, N, K, k_splits > 0 ? k_splits : 1, bias, static_cast<const __half*>(aux), ld_aux, out, ld_out,
-             static_cast<__half*>(out2), ld_out2, alpha, 0};
+             static_cast<__half*>(out2), ld_out2, alpha, DropCfg{nullptr, 0, 0, 1.0f}, 0};
   const int key = a_layout * 1000 + b_layout * 100 + epilogue * 10 + out_dtype;
   switch (key) {
     case 0 * 1000 + 0 * 100 + EPI_STORE * 10 + B200_DT_F16: return launch_gemm<BN, 0, 0, EPI_STORE, __half>(ta, tb, g, s);
@@ -244,22 +270,31 @@ int b200_gemm_f16(const void* A, int lda, int a_layout, const void* B, int ldb, 
   }
 }
 
-int b200_attn_fwd(const void* q, int ldq, int q_col0, const void* kv, int ldkv, int k_col0, int v_col0, const float* key_bias,
-                  const int32_t* kv_len, void* ctx, int ld_out, float* lse2, int B, int heads, int Sq, int Sk, void* stream) {
+int b200_attn_fwd_drop(const void* q, int ldq, int q_col0, const void* kv, int ldkv, int k_col0, int v_col0, const float* key_bias,
+                       const int32_t* kv_len, void* ctx, int ld_out, float* lse2, int B, int heads, int Sq, int Sk, const uint32_t* seed,
+                       unsigned site, float p, void* stream) {
   if (B <= 0 || heads <= 0 || Sq <= 0 || Sk <= 0) return fail(B200_ERR_SHAPE, "attn_fwd: empty problem");
   if ((q_col0 % 8) || (k_col0 % 8) || (v_col0 % 8) || (ld_out % 8)) return fail(B200_ERR_SHAPE, "attn_fwd: column offsets / ld_out must be multiples of 8");
+  const DropCfg drop = make_drop(seed, site, p);
   CUtensorMap tq, tkv;
   int rc = get_tmap(q, static_cast<uint64_t>(B) * Sq, ldq, ldq, ATT_BQ, &tq);
   if (rc) return rc;
   rc = get_tmap(kv, static_cast<uint64_t>(B) * Sk, ldkv, ldkv, ATT_BK, &tkv);
   if (rc) return rc;
-  static int configured = set_smem(attn_fwd_kernel, AttnFwdSmem::TOTAL);
-  if (configured != B200_OK) return configured;
+  static int c0 = set_smem(attn_fwd_kernel<false>, AttnFwdSmem::TOTAL);
+  static int c1 = set_smem(attn_fwd_kernel<true>, AttnFwdSmem::TOTAL);
+  if (c0 != B200_OK || c1 != B200_OK) return c0 ? c0 : c1;
   AttnFwdArgs a{B, heads, Sq, Sk, q_col0, k_col0, v_col0, key_bias, kv_len, static_cast<__half*>(ctx), ld_out, lse2,
-                1.4426950408889634f / 8.0f};
+                1.4426950408889634f / 8.0f, drop};
   dim3 grid((Sq + 2 * ATT_BQ - 1) / (2 * ATT_BQ), heads, B);
-  attn_fwd_kernel<<<grid, ATT_THREADS, AttnFwdSmem::TOTAL, static_cast<cudaStream_t>(stream)>>>(tq, tkv, a);
+  if (drop.seed_base) attn_fwd_kernel<true><<<grid, ATT_THREADS, AttnFwdSmem::TOTAL, static_cast<cudaStream_t>(stream)>>>(tq, tkv, a);
+  else attn_fwd_kernel<false><<<grid, ATT_THREADS, AttnFwdSmem::TOTAL, static_cast<cudaStream_t>(stream)>>>(tq, tkv, a);
   return check_launch("attn_fwd_kernel");
+}
+
+int b200_attn_fwd(const void* q, int ldq, int q_col0, const void* kv, int ldkv, int k_col0, int v_col0, const float* key_bias,
+                  const int32_t* kv_len, void* ctx, int ld_out, float* lse2, int B, int heads, int Sq, int Sk, void* stream) {
+  return b200_attn_fwd_drop(q, ldq, q_col0, kv, ldkv, k_col0, v_col0, key_bias, kv_len, ctx, ld_out, lse2, B, heads, Sq, Sk, nullptr, 0, 0.f, stream);
 }
 
 int b200_attn_probs(const void* q, int ldq, int q_col0, const void* k, int ldk, int k_col0, const float* key_bias, const float* lse2,
@@ -338,8 +373,25 @@ int b200_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const flo
   return check_launch("ln_fwd_kernel");
 }
 
+static int layernorm_bwd_impl(const void* dy, const void* dy2, const void* x, int x_dtype, const float* mean, const float* rstd, const float* gamma,
+                              void* dx, float* dgamma, float* dbeta, float* dbias, const float* alpha, int rows, int H, void* dx_drop, DropCfg drop,
+                              void* stream);
+
 int b200_layernorm_bwd(const void* dy, const void* dy2, const void* x, int x_dtype, const float* mean, const float* rstd, const float* gamma,
                        void* dx, float* dgamma, float* dbeta, float* dbias, const float* alpha, int rows, int H, void* stream) {
+  return layernorm_bwd_impl(dy, dy2, x, x_dtype, mean, rstd, gamma, dx, dgamma, dbeta, dbias, alpha, rows, H, nullptr, kNoDrop, stream);
+}
+
+int b200_layernorm_bwd_drop(const void* dy, const void* dy2, const void* x, int x_dtype, const float* mean, const float* rstd, const float* gamma,
+                            void* dx, void* dx_drop, float* dgamma, float* dbeta, float* dbias, const float* alpha, int rows, int H,
+                            const uint32_t* seed, unsigned site, float p, void* stream) {
+  if (!dx_drop) return fail(B200_ERR_SHAPE, "layernorm_bwd_drop: dx_drop is required");
+  return layernorm_bwd_impl(dy, dy2, x, x_dtype, mean, rstd, gamma, dx, dgamma, dbeta, dbias, alpha, rows, H, dx_drop, make_drop(seed, site, p), stream);
+}
+
+static int layernorm_bwd_impl(const void* dy, const void* dy2, const void* x, int x_dtype, const float* mean, const float* rstd, const float* gamma,
+                              void* dx, float* dgamma, float* dbeta, float* dbias, const float* alpha, int rows, int H, void* dx_drop, DropCfg drop,
+                              void* stream) {
   if (int rc = check_row_shape("layernorm_bwd", rows, H)) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int grid = (rows + ROW_WARPS - 1) / ROW_WARPS;
@@ -350,30 +402,55 @@ int b200_layernorm_bwd(const void* dy, const void* dy2, const void* x, int x_dty
     static int c = set_smem(ln_bwd_kernel<float>, 3 * ROW_WARPS * ROW_MAXV * 256 * 4);
     if (c) return c;
     ln_bwd_kernel<float><<<grid, ROW_WARPS * 32, smem, s>>>(static_cast<const __half*>(dy), static_cast<const __half*>(dy2), static_cast<const float*>(x),
-                                                           mean, rstd, gamma, static_cast<__half*>(dx), dgamma, dbeta, dbias, alpha, rows, H);
+                                                           mean, rstd, gamma, static_cast<__half*>(dx), dgamma, dbeta, dbias, alpha, rows, H,
+                                                           static_cast<__half*>(dx_drop), drop);
   } else {
     static int c = set_smem(ln_bwd_kernel<__half>, 3 * ROW_WARPS * ROW_MAXV * 256 * 4);
     if (c) return c;
     ln_bwd_kernel<__half><<<grid, ROW_WARPS * 32, smem, s>>>(static_cast<const __half*>(dy), static_cast<const __half*>(dy2), static_cast<const __half*>(x),
-                                                            mean, rstd, gamma, static_cast<__half*>(dx), dgamma, dbeta, dbias, alpha, rows, H);
+                                                            mean, rstd, gamma, static_cast<__half*>(dx), dgamma, dbeta, dbias, alpha, rows, H,
+                                                            static_cast<__half*>(dx_drop), drop);
   }
   return check_launch("ln_bwd_kernel");
 }
 
+int b200_embed_ln_fwd_drop(const int64_t* ids, const int64_t* tt, const int64_t* pos, const float* inputs_embeds, const float* word,
+                           const float* pos_tab, const float* type_tab, const float* gamma, const float* beta, void* y, float* y32, int rows, int S,
+                           int H, float eps, const uint32_t* seed, unsigned site, float p, void* stream);
+
 int b200_embed_ln_fwd(const int64_t* ids, const int64_t* tt, const int64_t* pos, const float* inputs_embeds, const float* word,
                       const float* pos_tab, const float* type_tab, const float* gamma, const float* beta, void* y, float* y32, int rows, int S,
                       int H, float eps, void* stream) {
+  return b200_embed_ln_fwd_drop(ids, tt, pos, inputs_embeds, word, pos_tab, type_tab, gamma, beta, y, y32, rows, S, H, eps, nullptr, 0, 0.f, stream);
+}
+
+int b200_embed_ln_fwd_drop(const int64_t* ids, const int64_t* tt, const int64_t* pos, const float* inputs_embeds, const float* word,
+                           const float* pos_tab, const float* type_tab, const float* gamma, const float* beta, void* y, float* y32, int rows, int S,
+                           int H, float eps, const uint32_t* seed, unsigned site, float p, void* stream) {
   if (int rc = check_row_shape("embed_ln_fwd", rows, H)) return rc;
   if (!ids && !inputs_embeds) return fail(B200_ERR_SHAPE, "embed_ln_fwd: need input_ids or inputs_embeds");
   const int grid = (rows + ROW_WARPS - 1) / ROW_WARPS;
   embed_ln_fwd_kernel<<<grid, ROW_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(ids, tt, pos, inputs_embeds, word, pos_tab, type_tab, gamma,
-                                                                                      beta, static_cast<__half*>(y), y32, rows, S, H, eps);
+                                                                                      beta, static_cast<__half*>(y), y32, rows, S, H, eps, make_drop(seed, site, p));
   return check_launch("embed_ln_fwd_kernel");
 }
+
+int b200_embed_ln_bwd_drop(const void* dy, const void* dy2, const int64_t* ids, const int64_t* tt, const int64_t* pos, const float* word,
+                           const float* pos_tab, const float* type_tab, const float* gamma, float* dword, float* dpos, float* dtype_tab,
+                           float* dgamma, float* dbeta, const float* alpha, int rows, int S, int H, float eps, const uint32_t* seed,
+                           unsigned site, float p, void* stream);
 
 int b200_embed_ln_bwd(const void* dy, const void* dy2, const int64_t* ids, const int64_t* tt, const int64_t* pos, const float* word,
                       const float* pos_tab, const float* type_tab, const float* gamma, float* dword, float* dpos, float* dtype_tab,
                       float* dgamma, float* dbeta, const float* alpha, int rows, int S, int H, float eps, void* stream) {
+  return b200_embed_ln_bwd_drop(dy, dy2, ids, tt, pos, word, pos_tab, type_tab, gamma, dword, dpos, dtype_tab, dgamma, dbeta, alpha, rows, S, H,
+                                eps, nullptr, 0, 0.f, stream);
+}
+
+int b200_embed_ln_bwd_drop(const void* dy, const void* dy2, const int64_t* ids, const int64_t* tt, const int64_t* pos, const float* word,
+                           const float* pos_tab, const float* type_tab, const float* gamma, float* dword, float* dpos, float* dtype_tab,
+                           float* dgamma, float* dbeta, const float* alpha, int rows, int S, int H, float eps, const uint32_t* seed,
+                           unsigned site, float p, void* stream) {
   if (int rc = check_row_shape("embed_ln_bwd", rows, H)) return rc;
   int grid = (rows + ROW_WARPS - 1) / ROW_WARPS;
   if (grid > sm_count() * 4) grid = sm_count() * 4;
@@ -381,16 +458,25 @@ int b200_embed_ln_bwd(const void* dy, const void* dy2, const int64_t* ids, const
   if (c) return c;
   embed_ln_bwd_kernel<<<grid, ROW_WARPS * 32, 3 * ROW_WARPS * H * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __half*>(dy), static_cast<const __half*>(dy2), ids, tt, pos, word, pos_tab, type_tab, gamma, dword, dpos, dtype_tab,
-      dgamma, dbeta, alpha, rows, S, H, eps);
+      dgamma, dbeta, alpha, rows, S, H, eps, make_drop(seed, site, p));
   return check_launch("embed_ln_bwd_kernel");
 }
 
+int b200_cls_head_fwd_drop(const void* h, const float* W, const float* b, float* logits, int32_t* argmax, int rows, int H, int C,
+                           const uint32_t* seed, unsigned site, float p, void* stream);
+
 int b200_cls_head_fwd(const void* h, const float* W, const float* b, float* logits, int32_t* argmax, int rows, int H, int C, void* stream) {
+  return b200_cls_head_fwd_drop(h, W, b, logits, argmax, rows, H, C, nullptr, 0, 0.f, stream);
+}
+
+int b200_cls_head_fwd_drop(const void* h, const float* W, const float* b, float* logits, int32_t* argmax, int rows, int H, int C,
+                           const uint32_t* seed, unsigned site, float p, void* stream) {
   if (int rc = check_row_shape("cls_head_fwd", rows, H)) return rc;
+  const DropCfg drop = make_drop(seed, site, p);
   const int grid = (rows + ROW_WARPS - 1) / ROW_WARPS;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (C == 2) cls_head_fwd_kernel<2><<<grid, ROW_WARPS * 32, 0, s>>>(static_cast<const __half*>(h), W, b, logits, argmax, rows, H);
-  else if (C == 3) cls_head_fwd_kernel<3><<<grid, ROW_WARPS * 32, 0, s>>>(static_cast<const __half*>(h), W, b, logits, argmax, rows, H);
+  if (C == 2) cls_head_fwd_kernel<2><<<grid, ROW_WARPS * 32, 0, s>>>(static_cast<const __half*>(h), W, b, logits, argmax, rows, H, drop);
+  else if (C == 3) cls_head_fwd_kernel<3><<<grid, ROW_WARPS * 32, 0, s>>>(static_cast<const __half*>(h), W, b, logits, argmax, rows, H, drop);
   else return fail(B200_ERR_SHAPE, "cls_head_fwd: C=%d (2 or 3)", C);
   return check_launch("cls_head_fwd_kernel");
 }
@@ -405,9 +491,20 @@ int b200_ce_stats(const float* logits, const int64_t* labels, const float* class
   return check_launch("ce_stats_kernel");
 }
 
+int b200_cls_head_bwd_drop(const void* h, const float* logits, const int64_t* labels, const float* class_weight, const float* stats, const float* W,
+                           const float* scale, void* dh, float* dW, float* db, int rows, int H, int C, const uint32_t* seed, unsigned site,
+                           float p, void* stream);
+
 int b200_cls_head_bwd(const void* h, const float* logits, const int64_t* labels, const float* class_weight, const float* stats, const float* W,
                       const float* scale, void* dh, float* dW, float* db, int rows, int H, int C, void* stream) {
+  return b200_cls_head_bwd_drop(h, logits, labels, class_weight, stats, W, scale, dh, dW, db, rows, H, C, nullptr, 0, 0.f, stream);
+}
+
+int b200_cls_head_bwd_drop(const void* h, const float* logits, const int64_t* labels, const float* class_weight, const float* stats, const float* W,
+                           const float* scale, void* dh, float* dW, float* db, int rows, int H, int C, const uint32_t* seed, unsigned site,
+                           float p, void* stream) {
   if (int rc = check_row_shape("cls_head_bwd", rows, H)) return rc;
+  const DropCfg drop = make_drop(seed, site, p);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int grid = (rows + ROW_WARPS - 1) / ROW_WARPS;
   const int cap = sm_count() * 8;
@@ -417,12 +514,12 @@ int b200_cls_head_bwd(const void* h, const float* logits, const int64_t* labels,
     static int c = set_smem(cls_head_bwd_kernel<2>, ROW_WARPS * 2 * ROW_MAXV * 256 * 4);
     if (c) return c;
     cls_head_bwd_kernel<2><<<grid, ROW_WARPS * 32, smem, s>>>(static_cast<const __half*>(h), logits, labels, class_weight, stats, W, scale,
-                                                             static_cast<__half*>(dh), dW, db, rows, H);
+                                                             static_cast<__half*>(dh), dW, db, rows, H, drop);
   } else if (C == 3) {
     static int c = set_smem(cls_head_bwd_kernel<3>, ROW_WARPS * 3 * ROW_MAXV * 256 * 4);
     if (c) return c;
     cls_head_bwd_kernel<3><<<grid, ROW_WARPS * 32, smem, s>>>(static_cast<const __half*>(h), logits, labels, class_weight, stats, W, scale,
-                                                             static_cast<__half*>(dh), dW, db, rows, H);
+                                                             static_cast<__half*>(dh), dW, db, rows, H, drop);
   } else {
     return fail(B200_ERR_SHAPE, "cls_head_bwd: C=%d (2 or 3)", C);
   }

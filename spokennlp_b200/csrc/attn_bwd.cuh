@@ -33,6 +33,7 @@ struct AttnBwdArgs {
   float scale_log2;                 // log2(e)/sqrt(d)
   float inv_sqrt_d;
   int dbg;                          // measurement knobs: 0x10000 skip dQ reductions, 0x20000 skip gradient MMAs, 0x40000 skip exp math
+  DropCfg drop;                     // the forward's attention-probability dropout (mask regenerated here)
 };
 
 struct AttnBwdSmem {
@@ -53,6 +54,7 @@ struct AttnBwdSmem {
 //              -> issue dV += , dK += , dQ(i) = -> grad_done(i)
 //   softmax  : wait s_full(i+1) -> exp / dS math for block i+1 into registers WHILE the gradient MMAs of block i run
 //              -> wait grad_done(i) -> drain dQ(i) (fp32 reduction) -> write P^T / dS^T tiles -> ds_full(i+1)
+template <bool DROP>
 __global__ void __launch_bounds__(ATTB_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                 const __grid_constant__ CUtensorMap tmDO, const AttnBwdArgs a) {
@@ -193,6 +195,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     float bias = -INFINITY;
     if (key < kv_len) bias = general_bias ? a.key_bias[static_cast<size_t>(b) * a.Sk + key] * 1.4426950408889634f : 0.f;
     const size_t stat_base = (static_cast<size_t>(b) * a.heads + h) * a.Sq;
+    const uint32_t dseed = DROP ? drop_seed(a.drop) : 0u;
 
     auto drain_dq = [&](int i) {                  // dQ_i tile: TMEM lane == query row; this warp owns 32 of the 64 d columns
       const int q = i * ATT_BQ + r;
@@ -240,11 +243,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
           const int qi = c * 32 + 2 * e;
-          const float p0 = fast_exp2(fmaf(__uint_as_float(sv[2 * e]), a.scale_log2, bias) - lds_f32(lse_s + qi * 4));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(sv[2 * e + 1]), a.scale_log2, bias) - lds_f32(lse_s + qi * 4 + 4));
-          const float d0 = p0 * (__uint_as_float(dp[2 * e]) - lds_f32(del_s + qi * 4)) * a.inv_sqrt_d;
-          const float d1 = p1 * (__uint_as_float(dp[2 * e + 1]) - lds_f32(del_s + qi * 4 + 4)) * a.inv_sqrt_d;
-          const __half2 hp = __floats2half2_rn(p0, p1), hd = __floats2half2_rn(d0, d1);
+          float p0 = fast_exp2(fmaf(__uint_as_float(sv[2 * e]), a.scale_log2, bias) - lds_f32(lse_s + qi * 4));
+          float p1 = fast_exp2(fmaf(__uint_as_float(sv[2 * e + 1]), a.scale_log2, bias) - lds_f32(lse_s + qi * 4 + 4));
+          float g0 = __uint_as_float(dp[2 * e]), g1 = __uint_as_float(dp[2 * e + 1]);
+          float pd0 = p0, pd1 = p1;
+          if (DROP) {       // P_drop = P o mask/(1-p) feeds dV; dP flows back through the same mask; delta is unchanged
+            const int q = min(i * ATT_BQ + half * 64 + qi, a.Sq - 1);
+            const uint32_t skp = static_cast<uint32_t>((a.Sk + 1) >> 1), kc = static_cast<uint32_t>(min(key, a.Sk - 1));
+            const uint32_t e0 = (static_cast<uint32_t>(stat_base + q) * skp + (kc >> 1)) * 2u + (kc & 1u);   // (pair, lane) as the forward drew it
+            const float m0 = drop_one(e0, dseed, a.drop.thr16, a.drop.scale);
+            const float m1 = drop_one(e0 + 2u * skp, dseed, a.drop.thr16, a.drop.scale);
+            pd0 *= m0; pd1 *= m1;
+            g0 *= m0; g1 *= m1;
+          }
+          const float d0 = p0 * (g0 - lds_f32(del_s + qi * 4)) * a.inv_sqrt_d;
+          const float d1 = p1 * (g1 - lds_f32(del_s + qi * 4 + 4)) * a.inv_sqrt_d;
+          const __half2 hp = __floats2half2_rn(pd0, pd1), hd = __floats2half2_rn(d0, d1);
           pk[c * 16 + e] = *reinterpret_cast<const uint32_t*>(&hp);
           dk[c * 16 + e] = *reinterpret_cast<const uint32_t*>(&hd);
         }

@@ -33,6 +33,7 @@ struct AttnFwdArgs {
   int ld_out;
   float* lse2;                       // [B, heads, Sq] log2-domain log-sum-exp (for backward), may be null
   float scale_log2;                  // log2(e) / sqrt(d)
+  DropCfg drop;                      // attention-probability dropout (bert_model.py:338), off when seed_base is null
 };
 
 struct AttnFwdSmem {
@@ -47,6 +48,7 @@ struct AttnFwdSmem {
   static constexpr int TOTAL = OFF_BAR + 256 + 1024;
 };
 
+template <bool DROP>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnFwdArgs a) {
   using S = AttnFwdSmem;
@@ -167,6 +169,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint32_t p_row = smem_u32(smem + S::OFF_P + x * S::P_BYTES) + r * 128;
       const float NEG_INF = -INFINITY;
       const float sc = a.scale_log2;
+      // one hash covers two consecutive keys: pair index of (row, key) = ((b*heads + h)*Sq + q) * ceil(Sk/2) + key/2
+      const uint32_t dseed = DROP ? drop_seed(a.drop) : 0u;
+      const uint32_t dbase = DROP ? static_cast<uint32_t>(((static_cast<size_t>(b) * a.heads + h) * a.Sq + min(q0 + x * ATT_BQ + r, a.Sq - 1)) * ((a.Sk + 1) >> 1)) : 0u;
       float m = NEG_INF, l = 0.f;
       for (int j = 0; j < n_blocks; ++j) {
         // Only blocks that contain a biased / removed key pay for the per-key bias (CTA-uniform decision).
@@ -243,9 +248,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               t0 = fmaf(__uint_as_float(v[2 * i]), sc, neg_m);
               t1 = fmaf(__uint_as_float(v[2 * i + 1]), sc, neg_m);
             }
-            const float p0 = fast_exp2(t0), p1 = fast_exp2(t1);
+            float p0 = fast_exp2(t0), p1 = fast_exp2(t1);
             rs0 += p0;
             rs1 += p1;
+            if (DROP) {                               // the row sum (softmax denominator) is taken before dropout
+              float m0, m1;
+              drop_pair(dbase + ((j * ATT_BK + c * 32) >> 1) + i, dseed, a.drop.thr16, a.drop.scale, m0, m1);
+              p0 *= m0;
+              p1 *= m1;
+            }
             const __half2 hp = __floats2half2_rn(p0, p1);
             pk[i] = *reinterpret_cast<const uint32_t*>(&hp);
           }

@@ -46,6 +46,7 @@ struct GemmArgs {
   __half* out2;
   int ld_out2;
   const float* alpha;   // optional device scalar
+  DropCfg drop;         // dropout on (acc + bias) before the residual is added (EPI_BIAS_RES / EPI_BIAS_RES32, gemm2 only)
   int dbg;              // measurement knobs (gemm2 only): 1 skip A loads, 2 skip B loads, 4 skip MMA issue, 8 skip epilogue stores,
                         // bits 8..15: L2 prefetch distance in K blocks
 };

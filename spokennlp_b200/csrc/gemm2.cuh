@@ -330,6 +330,18 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
             f[4 * i] += b4.x; f[4 * i + 1] += b4.y; f[4 * i + 2] += b4.z; f[4 * i + 3] += b4.w;
           }
         }
+        if ((EPI == EPI_BIAS_RES32 || EPI == EPI_BIAS_RES) && g.drop.seed_base != nullptr) {
+          // hidden dropout of BertSelfOutput / BertOutput (bert_model.py:373,451): applied to dense(x)+bias, before the residual
+          const uint32_t seed = drop_seed(g.drop);
+          const uint32_t e0 = static_cast<uint32_t>(row0 + lane) * static_cast<uint32_t>(g.N) + static_cast<uint32_t>(gc0);
+#pragma unroll
+          for (int i = 0; i < CW / 2; ++i) {
+            float m0, m1;
+            drop_pair((e0 >> 1) + i, seed, g.drop.thr16, g.drop.scale, m0, m1);
+            f[2 * i] *= m0;
+            f[2 * i + 1] *= m1;
+          }
+        }
         if (HAS_AUX) {
 #pragma unroll
           for (int ch = 0; ch < 8; ++ch) {

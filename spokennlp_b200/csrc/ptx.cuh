@@ -204,6 +204,38 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// ----------------------------------------------------------------------------- dropout (counter-based, stateless)
+// The keep/drop decision of element `idx` of a tensor is a pure function of (seed, idx): the backward regenerates the
+// forward's mask instead of storing it.  One 32-bit hash decides TWO consecutive elements (16 bits each: keep iff the
+// 16-bit lane >= thr16 = round(p * 65536), so p = 0.1 is met to 1e-5).  `seed` = per-step base seed (device memory, so a
+// replayed CUDA graph still draws fresh masks) mixed with a per-site constant.
+struct DropCfg {
+  const uint32_t* seed_base;   // device pointer, null = dropout off
+  uint32_t site;               // which dropout site of the model (layer * 8 + kind)
+  uint32_t thr16;              // round(p * 65536)
+  float scale;                 // 1 / (1 - p)
+};
+__device__ __forceinline__ uint32_t drop_hash(uint32_t pair_idx, uint32_t seed) {
+  uint32_t h = (pair_idx ^ seed) * 0x9E3779B1u;
+  h ^= h >> 15;
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 13;
+  return h;
+}
+__device__ __forceinline__ uint32_t drop_seed(const DropCfg& d) {
+  return drop_hash(d.site * 0x632BE5ABu + 0x7F4A7C15u, __ldg(d.seed_base));
+}
+// multipliers (0 or scale) for elements 2*pair_idx and 2*pair_idx+1
+__device__ __forceinline__ void drop_pair(uint32_t pair_idx, uint32_t seed, uint32_t thr16, float scale, float& m0, float& m1) {
+  const uint32_t h = drop_hash(pair_idx, seed);
+  m0 = (h & 0xFFFFu) >= thr16 ? scale : 0.f;
+  m1 = (h >> 16) >= thr16 ? scale : 0.f;
+}
+__device__ __forceinline__ float drop_one(uint32_t idx, uint32_t seed, uint32_t thr16, float scale) {
+  const uint32_t h = drop_hash(idx >> 1, seed);
+  return ((idx & 1) ? (h >> 16) : (h & 0xFFFFu)) >= thr16 ? scale : 0.f;
+}
+
 // ----------------------------------------------------------------------------- small math helpers
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

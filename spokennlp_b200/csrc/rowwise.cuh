@@ -45,6 +45,17 @@ __device__ __forceinline__ void store8(float* p, const Vec8& r) {
   *reinterpret_cast<float4*>(p + 4) = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
 }
 
+// multiply the 8 consecutive elements starting at (even) linear index e0 by their dropout multipliers
+__device__ __forceinline__ void drop8(Vec8& v, uint32_t e0, uint32_t seed, const DropCfg& d) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float m0, m1;
+    drop_pair((e0 >> 1) + i, seed, d.thr16, d.scale, m0, m1);
+    v.v[2 * i] *= m0;
+    v.v[2 * i + 1] *= m1;
+  }
+}
+
 // Row statistics over values already in registers.  Two-pass (mean, then centred variance) like the reference.
 __device__ __forceinline__ void row_stats(const Vec8 (&x)[ROW_MAXV], int nv_lane, int H, float eps, float& mean, float& rstd) {
   float s = 0.f;
@@ -118,10 +129,15 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 3) ln_bwd_kernel(const __half*
                                                                     const float* __restrict__ rstd_in, const float* __restrict__ gamma,
                                                                     __half* __restrict__ dx, float* __restrict__ dgamma,
                                                                     float* __restrict__ dbeta, float* __restrict__ dbias,
-                                                                    const float* __restrict__ alpha_ptr, int rows, int H) {
+                                                                    const float* __restrict__ alpha_ptr, int rows, int H,
+                                                                    __half* __restrict__ dx_drop, DropCfg drop) {
+  // dx_drop (optional): dx times the forward's dropout mask of the dense output that fed this LayerNorm — the gradient the
+  // dense layer's dgrad / wgrad / bias-grad consume, while the un-masked dx continues along the residual branch.
   extern __shared__ float red[];   // [3][ROW_WARPS][H]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nv = lane_vecs(H, lane);
+  const bool dropping = dx_drop != nullptr && drop.seed_base != nullptr;
+  const uint32_t dseed = dropping ? drop_seed(drop) : 0u;
   Vec8 ag[ROW_MAXV], ab[ROW_MAXV], ad[ROW_MAXV];
 #pragma unroll
   for (int i = 0; i < ROW_MAXV; ++i)
@@ -164,11 +180,14 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 3) ln_bwd_kernel(const __half*
         const Vec8 gm = load8(gamma + c);
         Vec8 o;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          o.v[j] = rstd * (d[i].v[j] * gm.v[j] - s1 - xh[i].v[j] * s2);
-          ad[i].v[j] += o.v[j];
-        }
+        for (int j = 0; j < 8; ++j) o.v[j] = rstd * (d[i].v[j] * gm.v[j] - s1 - xh[i].v[j] * s2);
         store8(dx + static_cast<size_t>(row) * H + c, o);
+        if (dropping) {
+          drop8(o, static_cast<uint32_t>(row) * static_cast<uint32_t>(H) + c, dseed, drop);
+          store8(dx_drop + static_cast<size_t>(row) * H + c, o);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ad[i].v[j] += o.v[j];
       }
   }
   // block reduction of the column sums, then one atomic per column per block
@@ -207,11 +226,13 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) embed_ln_fwd_kernel(const int6
                                                                        const float* __restrict__ word, const float* __restrict__ pos_tab,
                                                                        const float* __restrict__ type_tab, const float* __restrict__ gamma,
                                                                        const float* __restrict__ beta, __half* __restrict__ y,
-                                                                       float* __restrict__ y32, int rows, int S, int H, float eps) {
+                                                                       float* __restrict__ y32, int rows, int S, int H, float eps,
+                                                                       DropCfg drop) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int nv = lane_vecs(H, lane);
+  const uint32_t dseed = drop.seed_base ? drop_seed(drop) : 0u;
   const float* w = inputs_embeds ? inputs_embeds + static_cast<size_t>(row) * H : word + static_cast<size_t>(ids[row]) * H;
   const float* p = pos_tab + static_cast<size_t>(pos ? pos[row] : (row % S)) * H;
   const float* t = type_tab + static_cast<size_t>(tt ? tt[row] : 0) * H;
@@ -234,6 +255,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) embed_ln_fwd_kernel(const int6
       Vec8 o;
 #pragma unroll
       for (int j = 0; j < 8; ++j) o.v[j] = fmaf((v[i].v[j] - mean) * rstd, g.v[j], b.v[j]);
+      if (drop.seed_base) drop8(o, static_cast<uint32_t>(row) * static_cast<uint32_t>(H) + c, dseed, drop);     // bert_model.py:209
       store8(y + static_cast<size_t>(row) * H + c, o);
       if (y32) store8(y32 + static_cast<size_t>(row) * H + c, o);
     }
@@ -250,10 +272,12 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) embed_ln_bwd_kernel(const __ha
                                                                        const float* __restrict__ gamma, float* __restrict__ dword,
                                                                        float* __restrict__ dpos, float* __restrict__ dtype_tab,
                                                                        float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                                       const float* __restrict__ alpha_ptr, int rows, int S, int H, float eps) {
+                                                                       const float* __restrict__ alpha_ptr, int rows, int S, int H, float eps,
+                                                                       DropCfg drop) {
   extern __shared__ float red[];   // [3][ROW_WARPS][H]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float alpha = alpha_ptr ? *alpha_ptr : 1.0f;
+  const uint32_t dseed = drop.seed_base ? drop_seed(drop) : 0u;
   const int nv = lane_vecs(H, lane);
   Vec8 ag[ROW_MAXV], ab[ROW_MAXV], at0[ROW_MAXV], gm[ROW_MAXV];
 #pragma unroll
@@ -287,6 +311,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) embed_ln_bwd_kernel(const __ha
 #pragma unroll
           for (int j = 0; j < 8; ++j) d.v[j] += d2.v[j];
         }
+        if (drop.seed_base) drop8(d, static_cast<uint32_t>(off), dseed, drop);      // gradient of the embedding dropout
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           v[i].v[j] = (v[i].v[j] - mean) * rstd;      // xhat
@@ -351,11 +376,12 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) embed_ln_bwd_kernel(const __ha
 template <int C>
 __global__ void __launch_bounds__(ROW_WARPS * 32) cls_head_fwd_kernel(const __half* __restrict__ h, const float* __restrict__ W,
                                                                        const float* __restrict__ b, float* __restrict__ logits,
-                                                                       int32_t* __restrict__ argmax_out, int rows, int H) {
+                                                                       int32_t* __restrict__ argmax_out, int rows, int H, DropCfg drop) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int nv = lane_vecs(H, lane);
+  const uint32_t dseed = drop.seed_base ? drop_seed(drop) : 0u;
   float acc[C];
 #pragma unroll
   for (int c = 0; c < C; ++c) acc[c] = 0.f;
@@ -363,7 +389,8 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) cls_head_fwd_kernel(const __ha
   for (int i = 0; i < ROW_MAXV; ++i)
     if (i < nv) {
       const int col = (i * 32 + lane) * 8;
-      const Vec8 x = load8(h + static_cast<size_t>(row) * H + col);
+      Vec8 x = load8(h + static_cast<size_t>(row) * H + col);
+      if (drop.seed_base) drop8(x, static_cast<uint32_t>(row) * static_cast<uint32_t>(H) + col, dseed, drop);   // bert_for_ts.py:66-67
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         const Vec8 w = load8(W + static_cast<size_t>(c) * H + col);
@@ -418,10 +445,12 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) cls_head_bwd_kernel(const __ha
                                                                        const int64_t* __restrict__ labels, const float* __restrict__ cw,
                                                                        const float* __restrict__ stats, const float* __restrict__ W,
                                                                        const float* __restrict__ scale_ptr, __half* __restrict__ dh,
-                                                                       float* __restrict__ dW, float* __restrict__ db, int rows, int H) {
+                                                                       float* __restrict__ dW, float* __restrict__ db, int rows, int H,
+                                                                       DropCfg drop) {
   extern __shared__ float red[];   // [ROW_WARPS][C][H]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nv = lane_vecs(H, lane);
+  const uint32_t dseed = drop.seed_base ? drop_seed(drop) : 0u;
   const float inv_w = 1.0f / stats[1];
   const float scale = scale_ptr ? *scale_ptr : 1.0f;
   Vec8 aw[C][ROW_MAXV];
@@ -464,7 +493,8 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) cls_head_bwd_kernel(const __ha
 #pragma unroll
         for (int j = 0; j < 8; ++j) o.v[j] = 0.f;
         if (valid) {
-          const Vec8 x = load8(h + off);
+          Vec8 x = load8(h + off);
+          if (drop.seed_base) drop8(x, static_cast<uint32_t>(off), dseed, drop);
 #pragma unroll
           for (int c = 0; c < C; ++c) {
             const Vec8 w = load8(W + static_cast<size_t>(c) * H + col);
@@ -474,6 +504,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) cls_head_bwd_kernel(const __ha
               aw[c][i].v[j] = fmaf(dl[c], x.v[j], aw[c][i].v[j]);
             }
           }
+          if (drop.seed_base) drop8(o, static_cast<uint32_t>(off), dseed, drop);
         }
         store8(dh + off, o);
       }

@@ -130,6 +130,24 @@ class Saved:
     key_bias: Optional[Tensor] = None; kv_len: Optional[Tensor] = None
     layers: List[LayerSaved] = field(default_factory=list)
     out: Tensor = None
+    drop_emb: Optional[ops.Dropout] = None
+
+
+class DropPlan:
+    """Where and how hard dropout applies in one training forward (HF BertConfig.hidden_dropout_prob /
+    attention_probs_dropout_prob).  `seed` is a 1-element int32 DEVICE tensor holding this step's base seed; each site
+    hashes it with its own id, the backward regenerates the masks from the same (seed, site)."""
+    EMB, HEAD = 0xE000, 0xE001
+    ATTN, ATTN_OUT, FFN_OUT, XATTN, XATTN_OUT = range(5)
+
+    def __init__(self, seed: Tensor, p_hidden: float, p_attn: float):
+        self.seed, self.p_hidden, self.p_attn = seed, float(p_hidden), float(p_attn)
+
+    def at(self, site: int, p: float) -> Optional[ops.Dropout]:
+        return ops.Dropout(self.seed, site, p) if p > 0.0 else None
+
+    def layer(self, i: int, kind: int) -> Optional[ops.Dropout]:
+        return self.at(i * 8 + kind, self.p_attn if kind in (self.ATTN, self.XATTN) else self.p_hidden)
 
 
 class EncoderEngine:
@@ -168,32 +186,35 @@ class EncoderEngine:
         return c[key]
 
     # ---- forward -----------------------------------------------------------------------------------------------
-    def embed(self, ids, tt, pos, inputs_embeds, B, S):
+    def embed(self, ids, tt, pos, inputs_embeds, B, S, drop=None):
         """Returns the embedding output twice: fp16 (tensor-core operand) and fp32 (residual stream)."""
         f = self.flat
         y32 = torch.empty(B * S, self.H, dtype=torch.float32, device=f.flat32.device)
         y16 = ops.embed_ln_fwd(ids, tt, pos, inputs_embeds, f.view32(EMB_NAMES[0]), f.view32(EMB_NAMES[1]),
                                f.view32(EMB_NAMES[2]), f.view32(EMB_NAMES[3]), f.view32(EMB_NAMES[4]), self.eps, B * S, S,
-                               self.H, y32=y32)
+                               self.H, y32=y32, drop=drop)
         return y16, y32
 
     def layer_forward(self, p: LayerViews, x: Tensor, x32: Tensor, B: int, S: int, key_bias, kv_len, save: bool,
-                      want_probs: bool = False):
+                      want_probs: bool = False, drop: Optional[DropPlan] = None, index: int = 0):
         """One BertLayer (bert_model.py:518-553).  x: fp16 layer input (GEMM operand), x32: the same activations in fp32
         (residual stream: keeping the skip connection un-rounded holds the 12-layer hidden-state error under 1e-3)."""
+        d = (lambda k: drop.layer(index, k)) if drop is not None else (lambda k: None)
         a16, a32, sva, probs = attn_block_fwd(p.attn, x, x32, B, S, self.heads, self.eps, key_bias, kv_len, save=save,
-                                              want_probs=want_probs)
-        y16, y32, svf = ffn_block_fwd(p.ffn, a16, a32, self.eps, save=save)
+                                              want_probs=want_probs, drop_attn=d(DropPlan.ATTN), drop_hidden=d(DropPlan.ATTN_OUT))
+        y16, y32, svf = ffn_block_fwd(p.ffn, a16, a32, self.eps, save=save, drop_hidden=d(DropPlan.FFN_OUT))
         return y16, y32, (LayerSaved(attn=sva, ffn=svf) if save else None), probs
 
     def forward(self, ids, tt, pos, inputs_embeds, key_bias, kv_len, B: int, S: int, *, save: bool,
-                want_hidden: bool = False, want_probs: bool = False):
+                want_hidden: bool = False, want_probs: bool = False, drop: Optional[DropPlan] = None):
+        """`drop` (training only) turns on the reference's dropout sites; None = eval / p=0."""
         self.flat.sync_half()
-        x, x32 = self.embed(ids, tt, pos, inputs_embeds, B, S)
-        saved = Saved(B=B, S=S, ids=ids, tt=tt, pos=pos, key_bias=key_bias, kv_len=kv_len) if save else None
+        drop_emb = drop.at(DropPlan.EMB, drop.p_hidden) if drop is not None else None
+        x, x32 = self.embed(ids, tt, pos, inputs_embeds, B, S, drop=drop_emb)
+        saved = Saved(B=B, S=S, ids=ids, tt=tt, pos=pos, key_bias=key_bias, kv_len=kv_len, drop_emb=drop_emb) if save else None
         hiddens, probs_all = ([x32] if want_hidden else None), ([] if want_probs else None)
         for i in range(self.L):
-            x, x32, sv, probs = self.layer_forward(self.layer(i), x, x32, B, S, key_bias, kv_len, save, want_probs)
+            x, x32, sv, probs = self.layer_forward(self.layer(i), x, x32, B, S, key_bias, kv_len, save, want_probs, drop, i)
             if save:
                 saved.layers.append(sv)
             if want_hidden:
@@ -230,6 +251,6 @@ class EncoderEngine:
             ops.embed_ln_bwd(dy, None, saved.ids, saved.tt, saved.pos, f.view32(EMB_NAMES[0]), f.view32(EMB_NAMES[1]),
                              f.view32(EMB_NAMES[2]), f.view32(EMB_NAMES[3]), f.viewg(EMB_NAMES[0]), f.viewg(EMB_NAMES[1]),
                              f.viewg(EMB_NAMES[2]), f.viewg(EMB_NAMES[3]), f.viewg(EMB_NAMES[4]), inv_scale, self.eps, B * S,
-                             S, self.H)
+                             S, self.H, drop=saved.drop_emb)
         if after_layer is not None:
             after_layer(-1)

@@ -20,7 +20,7 @@ from transformers.modeling_outputs import BaseModelOutputWithPoolingAndCrossAtte
 from transformers.models.bert.modeling_bert import BertPreTrainedModel
 
 from . import ops
-from .engine import EMB_NAMES, EncoderEngine, FlatParams, layer_param_names
+from .engine import EMB_NAMES, DropPlan, EncoderEngine, FlatParams, layer_param_names
 from .lib import B200Error
 
 
@@ -106,11 +106,11 @@ class _EncoderFn(torch.autograd.Function):
     by optional per-layer hidden states and attention probabilities (returned detached)."""
 
     @staticmethod
-    def forward(ctx, model, ids, tt, pos, inputs_embeds, key_bias, kv_len, B, S, want_hidden, want_probs, *params):
+    def forward(ctx, model, ids, tt, pos, inputs_embeds, key_bias, kv_len, B, S, want_hidden, want_probs, drop, *params):
         eng: EncoderEngine = model._engine
-        need_grad = any(ctx.needs_input_grad[11:])
+        need_grad = any(ctx.needs_input_grad[12:])
         x16, x32, saved, hiddens, probs = eng.forward(ids, tt, pos, inputs_embeds, key_bias, kv_len, B, S, save=need_grad,
-                                                 want_hidden=want_hidden, want_probs=want_probs)
+                                                 want_hidden=want_hidden, want_probs=want_probs, drop=drop)
         ctx.model, ctx.saved, ctx.n_params = model, saved, len(params)
         H = eng.H
 
@@ -142,7 +142,7 @@ class _EncoderFn(torch.autograd.Function):
         finally:
             flat.grad32 = keep
         ctx.saved = None
-        return (None,) * 11 + grads
+        return (None,) * 12 + grads
 
 
 # ---------------------------------------------------------------------------- the model
@@ -162,7 +162,6 @@ class BertModel(BertPreTrainedModel):
         self.encoder = BertEncoder(config)
         self.pooler = BertPooler(config) if add_pooling_layer else None
         self._engine: Optional[EncoderEngine] = None
-        self._warned_dropout = False
         self.post_init()
 
     # HF plumbing used by the reference drivers (ts_sentence_seq_labeling.py:284, main_multimodal.py:291)
@@ -213,9 +212,12 @@ class BertModel(BertPreTrainedModel):
         if S > cfg.max_position_embeddings and position_ids is None:
             raise ValueError(f"sequence length {S} > max_position_embeddings {cfg.max_position_embeddings}")
         eng = self.b200_engine(src.device)
-        if self.training and (cfg.hidden_dropout_prob > 0 or cfg.attention_probs_dropout_prob > 0) and not self._warned_dropout:
-            warnings.warn("B200 BertModel: dropout inside the encoder is not applied (deterministic training path)")
-            self._warned_dropout = True
+        drop = None
+        if self.training and (cfg.hidden_dropout_prob > 0 or cfg.attention_probs_dropout_prob > 0):
+            # one fresh base seed per forward, drawn from torch's CPU generator (so torch.manual_seed governs it, as it does
+            # nn.Dropout in the reference); the tensor lives in the saved state until this forward's backward has run
+            seed = torch.randint(0, 2 ** 31 - 1, (1,), dtype=torch.int32).to(src.device, non_blocking=True)
+            drop = DropPlan(seed, cfg.hidden_dropout_prob, cfg.attention_probs_dropout_prob)
 
         ids = input_ids.contiguous().view(-1) if input_ids is not None else None
         emb = inputs_embeds.contiguous().float().view(B * S, -1) if inputs_embeds is not None else None
@@ -232,7 +234,7 @@ class BertModel(BertPreTrainedModel):
 
         params = [p for _, p in self._hot_named_params()]
         outs = _EncoderFn.apply(self, ids, tt, pos, emb, key_bias, kv_len, B, S, bool(output_hidden_states),
-                                bool(output_attentions), *params)
+                                bool(output_attentions), drop, *params)
         seq = outs[0]
         k = 1
         hidden_states = attentions = None

@@ -15,6 +15,20 @@ from .lib import (DT_F16, DT_F32, EPI_ADD, EPI_ATOMIC, EPI_BIAS, EPI_BIAS_GELU, 
 Tensor = torch.Tensor
 
 
+class Dropout:
+    """(device seed tensor, site id, probability) of one dropout site; `None` anywhere means "no dropout"."""
+    __slots__ = ("seed", "site", "p")
+
+    def __init__(self, seed: Tensor, site: int, p: float):
+        self.seed, self.site, self.p = seed, int(site), float(p)
+
+
+def _drop_args(d):
+    if d is None or d.p <= 0.0:
+        return None, 0, 0.0
+    return C.c_void_p(d.seed.data_ptr()), d.site, d.p
+
+
 def _ptr(t: Optional[Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -39,7 +53,7 @@ def _dt(t: Tensor) -> int:
 
 def gemm(a: Tensor, b: Tensor, out: Tensor, *, a_layout: int = 0, b_layout: int = 0, epilogue: int = EPI_STORE,
          bias: Optional[Tensor] = None, aux: Optional[Tensor] = None, out2: Optional[Tensor] = None,
-         alpha: Optional[Tensor] = None, k_splits: int = 1) -> Tensor:
+         alpha: Optional[Tensor] = None, k_splits: int = 1, drop: Optional["Dropout"] = None) -> Tensor:
     """out[M,N] = epilogue(A @ B^T).  a_layout/b_layout = 1 means the operand is stored transposed
     ([K,M] / [K,N] row-major) and is fed MN-major to the tensor core."""
     _req(a, torch.float16, "A"), _req(b, torch.float16, "B")
@@ -49,6 +63,14 @@ def gemm(a: Tensor, b: Tensor, out: Tensor, *, a_layout: int = 0, b_layout: int 
     Kb = b.shape[1] if b_layout == 0 else b.shape[0]
     if K != Kb or tuple(out.shape) != (M, N):
         raise L.B200Error(f"gemm: shape mismatch A{tuple(a.shape)}/{a_layout} B{tuple(b.shape)}/{b_layout} out{tuple(out.shape)}")
+    if drop is not None and drop.p > 0.0:
+        if a_layout or b_layout or out2 is not None or alpha is not None or k_splits != 1:
+            raise L.B200Error("gemm: dropout is fused into the forward residual epilogues only")
+        seed, site, p = _drop_args(drop)
+        rc = L.load().b200_gemm_f16_drop(_ptr(a), a.stride(0), _ptr(b), b.stride(0), M, N, K, epilogue, _ptr(bias), _ptr(aux),
+                                         aux.stride(0) if aux is not None else 0, _ptr(out), out.stride(0), _dt(out), seed, site, p, _stream())
+        L.check(rc, "b200_gemm_f16_drop")
+        return out
     rc = L.load().b200_gemm_f16(_ptr(a), a.stride(0), a_layout, _ptr(b), b.stride(0), b_layout, M, N, K, epilogue,
                                 _ptr(bias), _ptr(aux), aux.stride(0) if aux is not None else 0, _ptr(out), out.stride(0),
                                 _dt(out), _ptr(out2), out2.stride(0) if out2 is not None else 0, _ptr(alpha), k_splits,
@@ -83,10 +105,11 @@ def wgrad_splits(M_out: int, N_in: int, K_tokens: int, sms: int = 148) -> int:
 
 def attn_fwd(q: Tensor, kv: Tensor, ctx: Tensor, B: int, heads: int, Sq: int, Sk: int, *, q_col0: int, k_col0: int,
              v_col0: int, key_bias: Optional[Tensor] = None, kv_len: Optional[Tensor] = None,
-             lse2: Optional[Tensor] = None) -> Tensor:
+             lse2: Optional[Tensor] = None, drop: Optional["Dropout"] = None) -> Tensor:
     _req(q, torch.float16, "q"), _req(kv, torch.float16, "kv"), _req(ctx, torch.float16, "ctx")
-    rc = L.load().b200_attn_fwd(_ptr(q), q.stride(0), q_col0, _ptr(kv), kv.stride(0), k_col0, v_col0, _ptr(key_bias),
-                                _ptr(kv_len), _ptr(ctx), ctx.stride(0), _ptr(lse2), B, heads, Sq, Sk, _stream())
+    seed, site, p = _drop_args(drop)
+    rc = L.load().b200_attn_fwd_drop(_ptr(q), q.stride(0), q_col0, _ptr(kv), kv.stride(0), k_col0, v_col0, _ptr(key_bias),
+                                     _ptr(kv_len), _ptr(ctx), ctx.stride(0), _ptr(lse2), B, heads, Sq, Sk, seed, site, p, _stream())
     L.check(rc, "b200_attn_fwd")
     return ctx
 
@@ -127,38 +150,47 @@ def layernorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, eps: float, *, y: Opti
 
 def layernorm_bwd(dy: Tensor, x: Tensor, mean: Tensor, rstd: Tensor, gamma: Tensor, dx: Tensor, dgamma: Tensor,
                   dbeta: Tensor, *, dy2: Optional[Tensor] = None, dbias: Optional[Tensor] = None,
-                  alpha: Optional[Tensor] = None) -> Tensor:
+                  alpha: Optional[Tensor] = None, dx_drop: Optional[Tensor] = None, drop: Optional["Dropout"] = None) -> Tensor:
     rows, H = x.shape
+    if drop is not None and drop.p > 0.0:
+        seed, site, p = _drop_args(drop)
+        rc = L.load().b200_layernorm_bwd_drop(_ptr(dy), _ptr(dy2), _ptr(x), _dt(x), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dx), _ptr(dx_drop),
+                                              _ptr(dgamma), _ptr(dbeta), _ptr(dbias), _ptr(alpha), rows, H, seed, site, p, _stream())
+        L.check(rc, "b200_layernorm_bwd_drop")
+        return dx
     rc = L.load().b200_layernorm_bwd(_ptr(dy), _ptr(dy2), _ptr(x), _dt(x), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dx),
                                      _ptr(dgamma), _ptr(dbeta), _ptr(dbias), _ptr(alpha), rows, H, _stream())
     L.check(rc, "b200_layernorm_bwd")
     return dx
 
 
-def embed_ln_fwd(ids, tt, pos, inputs_embeds, word, pos_tab, type_tab, gamma, beta, eps, rows, S, H, *, y=None, y32=None):
+def embed_ln_fwd(ids, tt, pos, inputs_embeds, word, pos_tab, type_tab, gamma, beta, eps, rows, S, H, *, y=None, y32=None, drop=None):
     if y is None:
         y = torch.empty(rows, H, dtype=torch.float16, device=word.device)
-    rc = L.load().b200_embed_ln_fwd(_ptr(ids), _ptr(tt), _ptr(pos), _ptr(inputs_embeds), _ptr(word), _ptr(pos_tab),
-                                    _ptr(type_tab), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(y32), rows, S, H, float(eps),
-                                    _stream())
+    seed, site, p = _drop_args(drop)
+    rc = L.load().b200_embed_ln_fwd_drop(_ptr(ids), _ptr(tt), _ptr(pos), _ptr(inputs_embeds), _ptr(word), _ptr(pos_tab),
+                                         _ptr(type_tab), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(y32), rows, S, H, float(eps),
+                                         seed, site, p, _stream())
     L.check(rc, "b200_embed_ln_fwd")
     return y
 
 
 def embed_ln_bwd(dy, dy2, ids, tt, pos, word, pos_tab, type_tab, gamma, dword, dpos, dtype_tab, dgamma, dbeta, alpha, eps,
-                 rows, S, H):
-    rc = L.load().b200_embed_ln_bwd(_ptr(dy), _ptr(dy2), _ptr(ids), _ptr(tt), _ptr(pos), _ptr(word), _ptr(pos_tab),
-                                    _ptr(type_tab), _ptr(gamma), _ptr(dword), _ptr(dpos), _ptr(dtype_tab), _ptr(dgamma),
-                                    _ptr(dbeta), _ptr(alpha), rows, S, H, float(eps), _stream())
+                 rows, S, H, drop=None):
+    seed, site, p = _drop_args(drop)
+    rc = L.load().b200_embed_ln_bwd_drop(_ptr(dy), _ptr(dy2), _ptr(ids), _ptr(tt), _ptr(pos), _ptr(word), _ptr(pos_tab),
+                                         _ptr(type_tab), _ptr(gamma), _ptr(dword), _ptr(dpos), _ptr(dtype_tab), _ptr(dgamma),
+                                         _ptr(dbeta), _ptr(alpha), rows, S, H, float(eps), seed, site, p, _stream())
     L.check(rc, "b200_embed_ln_bwd")
 
 
-def cls_head_fwd(h: Tensor, W: Tensor, b: Tensor, *, want_argmax: bool = False):
+def cls_head_fwd(h: Tensor, W: Tensor, b: Tensor, *, want_argmax: bool = False, drop=None):
     rows, H = h.shape
     Cn = W.shape[0]
     logits = torch.empty(rows, Cn, dtype=torch.float32, device=h.device)
     am = torch.empty(rows, dtype=torch.int32, device=h.device) if want_argmax else None
-    rc = L.load().b200_cls_head_fwd(_ptr(h), _ptr(W), _ptr(b), _ptr(logits), _ptr(am), rows, H, Cn, _stream())
+    seed, site, p = _drop_args(drop)
+    rc = L.load().b200_cls_head_fwd_drop(_ptr(h), _ptr(W), _ptr(b), _ptr(logits), _ptr(am), rows, H, Cn, seed, site, p, _stream())
     L.check(rc, "b200_cls_head_fwd")
     return (logits, am) if want_argmax else logits
 
@@ -170,10 +202,11 @@ def ce_stats(logits: Tensor, labels: Tensor, stats: Tensor, class_weight: Option
     return stats
 
 
-def cls_head_bwd(h, logits, labels, stats, W, dh, dW, db, *, class_weight=None, scale=None):
+def cls_head_bwd(h, logits, labels, stats, W, dh, dW, db, *, class_weight=None, scale=None, drop=None):
     rows, H = h.shape
-    rc = L.load().b200_cls_head_bwd(_ptr(h), _ptr(logits), _ptr(labels), _ptr(class_weight), _ptr(stats), _ptr(W),
-                                    _ptr(scale), _ptr(dh), _ptr(dW), _ptr(db), rows, H, W.shape[0], _stream())
+    seed, site, p = _drop_args(drop)
+    rc = L.load().b200_cls_head_bwd_drop(_ptr(h), _ptr(logits), _ptr(labels), _ptr(class_weight), _ptr(stats), _ptr(W),
+                                         _ptr(scale), _ptr(dh), _ptr(dW), _ptr(db), rows, H, W.shape[0], seed, site, p, _stream())
     L.check(rc, "b200_cls_head_bwd")
     return dh
 
@@ -207,12 +240,14 @@ def attn_bwd_workspace(B: int, heads: int, Sq: int, device) -> Tensor:
 
 def attn_bwd(q: Tensor, kv: Tensor, dctx: Tensor, ctx: Tensor, lse2: Tensor, dq: Tensor, dkv: Tensor, workspace: Tensor,
              B: int, heads: int, Sq: int, Sk: int, *, q_col0: int, k_col0: int, v_col0: int, dq_col0: int, dk_col0: int,
-             dv_col0: int, key_bias: Optional[Tensor] = None, kv_len: Optional[Tensor] = None) -> None:
+             dv_col0: int, key_bias: Optional[Tensor] = None, kv_len: Optional[Tensor] = None, drop=None) -> None:
     for t, n in ((q, "q"), (kv, "kv"), (dctx, "dctx"), (ctx, "ctx"), (dq, "dq"), (dkv, "dkv")):
         _req(t, torch.float16, n)
-    rc = L.load().b200_attn_bwd(_ptr(q), q.stride(0), q_col0, _ptr(kv), kv.stride(0), k_col0, v_col0, _ptr(dctx), dctx.stride(0),
-                                _ptr(ctx), ctx.stride(0), _ptr(key_bias), _ptr(kv_len), _ptr(lse2), _ptr(workspace), _ptr(dq),
-                                dq.stride(0), dq_col0, _ptr(dkv), dkv.stride(0), dk_col0, dv_col0, B, heads, Sq, Sk, _stream())
+    seed, site, p = _drop_args(drop)
+    rc = L.load().b200_attn_bwd_drop(_ptr(q), q.stride(0), q_col0, _ptr(kv), kv.stride(0), k_col0, v_col0, _ptr(dctx), dctx.stride(0),
+                                     _ptr(ctx), ctx.stride(0), _ptr(key_bias), _ptr(kv_len), _ptr(lse2), _ptr(workspace), _ptr(dq),
+                                     dq.stride(0), dq_col0, _ptr(dkv), dkv.stride(0), dk_col0, dv_col0, B, heads, Sq, Sk, seed, site, p,
+                                     _stream())
     L.check(rc, "b200_attn_bwd")
 
 

@@ -17,7 +17,7 @@ import torch.distributed as dist
 from torch import nn
 
 from . import ops
-from .engine import EMB_NAMES, EncoderEngine, FlatParams, layer_param_names
+from .engine import EMB_NAMES, DropPlan, EncoderEngine, FlatParams, layer_param_names
 from .modeling_bert import BertModel
 
 
@@ -53,7 +53,10 @@ class TopicSegModel(nn.Module):
 
 class DataParallelTrainer:
     def __init__(self, model: TopicSegModel, *, lr: float = 5e-5, total_steps: int = 1000, max_grad_norm: float = 1.0,
-                 weight_decay: float = 0.0, loss_scale: float = 32768.0, device: Optional[torch.device] = None):
+                 weight_decay: float = 0.0, loss_scale: float = 32768.0, device: Optional[torch.device] = None,
+                 dropout: bool = True, seed: int = 0):
+        """`dropout=True` honours the config's hidden_dropout_prob / attention_probs_dropout_prob (the reference trains with
+        both at 0.1); `seed` is the base of the per-step dropout seeds."""
         self.model = model
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         cfg = model.config
@@ -77,6 +80,7 @@ class DataParallelTrainer:
         self.lr, self.total_steps, self.max_grad_norm, self.wd = lr, total_steps, max_grad_norm, weight_decay
         self.step_idx = 0
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank() if self.world > 1 else 0
         self.scale = torch.tensor([loss_scale, 1.0 / loss_scale], dtype=torch.float32, device=self.device)
         self.stats = torch.zeros(2, dtype=torch.float32, device=self.device)
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=self.device)
@@ -91,6 +95,12 @@ class DataParallelTrainer:
         self._graph = None
         self._static = None
         self.kernels_per_step = 0
+        # dropout (HF config probabilities; TopicSegModel's classifier dropout = hidden_dropout_prob, bert_for_ts.py:66)
+        self.p_hidden = float(getattr(cfg, "hidden_dropout_prob", 0.0)) if dropout else 0.0
+        self.p_attn = float(getattr(cfg, "attention_probs_dropout_prob", 0.0)) if dropout else 0.0
+        self.seed = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.base_seed = int(seed) & 0x7FFFFFFF
+        self.drop = DropPlan(self.seed, self.p_hidden, self.p_attn) if (self.p_hidden > 0 or self.p_attn > 0) else None
 
     # ------------------------------------------------------------------------------------------------------------
     def _allreduce_slice(self, lo: int, hi: int) -> None:
@@ -114,16 +124,17 @@ class DataParallelTrainer:
         pos = None  # arange(S) per row
         ids = input_ids.contiguous().view(-1)
         tt = token_type_ids.contiguous().view(-1) if token_type_ids is not None else None
-        x16, _, saved, _, _ = eng.forward(ids, tt, pos, None, key_bias, kv_len, B, S, save=True)
+        x16, _, saved, _, _ = eng.forward(ids, tt, pos, None, key_bias, kv_len, B, S, save=True, drop=self.drop)
+        drop_head = self.drop.at(DropPlan.HEAD, self.p_hidden) if self.drop is not None else None
         W32 = flat.view32("loss_calculator.classifier.weight")
         b32 = flat.view32("loss_calculator.classifier.bias")
-        logits = ops.cls_head_fwd(x16, W32, b32)
+        logits = ops.cls_head_fwd(x16, W32, b32, drop=drop_head)
         lab = labels.contiguous().view(-1)
         self.stats.zero_()
         ops.ce_stats(logits, lab, self.stats)
         dh = torch.empty_like(x16)
         ops.cls_head_bwd(x16, logits, lab, self.stats, W32, dh, flat.viewg("loss_calculator.classifier.weight"),
-                         flat.viewg("loss_calculator.classifier.bias"), scale=self.scale[0:1])
+                         flat.viewg("loss_calculator.classifier.bias"), scale=self.scale[0:1], drop=drop_head)
         self._works = []
         # the head's gradients live in the last bucket, which is reduced right after the top layer's backward
         eng.backward(saved, dh, self.scale[1:2], after_layer=self._after_layer)
@@ -150,11 +161,27 @@ class DataParallelTrainer:
         flat.version = flat.cur_version()       # the fused step refreshed the fp16 mirror itself
 
     def _push_hyper(self) -> None:
+        """Per-step device-side state that a replayed graph must see change: learning rate and bias corrections."""
         ops.set_hyper(self.hyper, lr=self._lr(), weight_decay=self.wd, step=max(1, self.step_idx))
+
+    def step_seed(self, step_idx: int) -> int:
+        """Base dropout seed of training step `step_idx` on this rank (ranks draw different masks, as DDP replicas do)."""
+        return (self.base_seed * 1000003 + step_idx * 7919 + self.rank * 104729) & 0x7FFFFFFF
+
+    def _push_seed(self) -> None:
+        """Written OUTSIDE the captured graph, before the step's forward: the kernels read the seed from device memory."""
+        if self.drop is not None:
+            self.seed.fill_(self.step_seed(self.step_idx))
+
+    def release_graph(self) -> None:
+        """Drop the captured step (must precede tearing down the process group: the graph holds NCCL work)."""
+        self._graph = None
+        torch.cuda.synchronize()
 
     def step(self, input_ids, attention_mask, token_type_ids, labels) -> torch.Tensor:
         if self._graph is not None:
             return self._replay(input_ids, attention_mask, token_type_ids, labels)
+        self._push_seed()
         stats = self.forward_backward(input_ids, attention_mask, token_type_ids, labels)
         self.optimizer_step()
         return stats
@@ -195,6 +222,7 @@ class DataParallelTrainer:
         for dst, src in zip(self._static, (input_ids, attention_mask, token_type_ids, labels)):
             if dst is not None and src is not dst:
                 dst.copy_(src, non_blocking=True)
+        self._push_seed()
         self.step_idx += 1
         self._push_hyper()
         self._graph.replay()

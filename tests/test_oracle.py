@@ -102,3 +102,49 @@ def test_mask_fill_values_agree():
     a = O.bert_model(*args).last_hidden_state
     for fill in (-1e6, -1e4):
         assert rel_err(O.bert_model(*args, mask_fill=fill).last_hidden_state, a) < 1e-6
+
+
+def test_dropout_sites_match_hf_training_mode(monkeypatch):
+    """Pins WHERE the oracle applies its explicit dropout multipliers: HF BertModel (eager) is run in train() mode, live in
+    this process, with torch.nn.functional.dropout patched to multiply by the same masks, in call order
+    (embeddings; per layer: probabilities, attention output dense, FFN output dense — bert_model.py:209,338,373,451).
+    Skipped when transformers' BertModel is not importable (it is in this image)."""
+    import pytest
+    tf = pytest.importorskip("transformers")
+    from oracle import dropout_masks as DM
+    g = _load("tiny_bert.pt")
+    c = g["config"]
+    cfg = O.OracleConfig(**c)
+    B, S = g["input_ids"].shape
+    H, L, heads = cfg.hidden_size, cfg.num_hidden_layers, cfg.num_attention_heads
+    masks = DM.bert_masks(1234, 0.1, 0.1, L, B, S, H, heads, head_site=False)
+    order = [masks["emb"]]
+    for i in range(L):
+        p = f"encoder.layer.{i}."
+        order += [masks[p + "attention.probs"], masks[p + "attention.out"], masks[p + "ffn_out"]]
+    queue = list(order)
+
+    def fake_dropout(x, p=0.5, training=True, inplace=False):
+        if not training or p == 0.0:
+            return x
+        m = queue.pop(0)
+        assert m.numel() == x.numel(), (tuple(m.shape), tuple(x.shape))
+        return x * m.reshape(x.shape).to(x.dtype)
+
+    monkeypatch.setattr(torch.nn.functional, "dropout", fake_dropout)
+    hf_cfg = tf.BertConfig(attn_implementation="eager", hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1,
+                           **{k: v for k, v in c.items()})
+    model = tf.BertModel(hf_cfg, add_pooling_layer=False)
+    missing = model.load_state_dict({k: v for k, v in g["state_dict"].items() if not k.startswith("pooler.")}, strict=False)
+    assert not [k for k in missing.missing_keys if "position_ids" not in k]
+    model.train()
+    ref = model(input_ids=g["input_ids"], attention_mask=g["attention_mask"], token_type_ids=g["token_type_ids"]).last_hidden_state
+    assert not queue, f"{len(queue)} masks were never consumed"
+    out = O.bert_model(g["state_dict"], cfg, g["input_ids"], g["attention_mask"], g["token_type_ids"], masks=masks)
+    assert rel_err(out.last_hidden_state, ref.detach()) < TOL
+    # and the masks really bite: eval-mode output differs
+    plain = O.bert_model(g["state_dict"], cfg, g["input_ids"], g["attention_mask"], g["token_type_ids"])
+    assert rel_err(plain.last_hidden_state, ref.detach()) > 1e-2
+    # keep-rate of the hash
+    keep = float((masks["emb"] > 0).float().mean())
+    assert abs(keep - 0.9) < 0.02
