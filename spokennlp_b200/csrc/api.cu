@@ -616,7 +616,7 @@ int b200_ponet_mix_fwd(const void* proj, int ld, const float* key_bias, const in
 }
 
 size_t b200_ponet_bwd_workspace(int B, int S, int H, int heads, int nseg) {
-  return (static_cast<size_t>(B) * H * 2 + static_cast<size_t>(B) * heads + static_cast<size_t>(B) * nseg * H) * sizeof(float) + 256;
+  return (static_cast<size_t>(B) * H * 2 + static_cast<size_t>(B) * heads + 2 * static_cast<size_t>(B) * nseg * H) * sizeof(float) + 256;
 }
 
 int b200_ponet_mix_bwd(const void* proj, int ld, const void* dout, const float* key_bias, const int64_t* segment_ids, const void* fwd_workspace,
@@ -635,19 +635,20 @@ int b200_ponet_mix_bwd(const void* proj, int ld, const void* dout, const float* 
   float* dg = static_cast<float*>(bwd_workspace);
   float* dqbar = dg + static_cast<size_t>(B) * H;
   float* segsum = dqbar + static_cast<size_t>(B) * H;
-  float* lse = segsum + static_cast<size_t>(B) * nseg * H;
-  cudaMemsetAsync(dg, 0, (static_cast<size_t>(B) * H * 2 + static_cast<size_t>(B) * nseg * H) * sizeof(float), s);
+  float* segties = segsum + static_cast<size_t>(B) * nseg * H;
+  float* lse = segties + static_cast<size_t>(B) * nseg * H;
+  cudaMemsetAsync(dg, 0, (static_cast<size_t>(B) * H * 2 + 2 * static_cast<size_t>(B) * nseg * H) * sizeof(float), s);
   const __half* p = static_cast<const __half*>(proj);
   const __half* d = static_cast<const __half*>(dout);
   int rc;
-  ponet_bwd_sums_kernel<<<dim3((S + 63) / 64, B), H / 8, 0, s>>>(p, ld, d, key_bias, segment_ids, dg, segsum, S, H, nseg);
+  ponet_bwd_sums_kernel<<<dim3((S + 63) / 64, B), H / 8, 0, s>>>(p, ld, d, key_bias, segment_ids, segmax, dg, segsum, segties, S, H, nseg);
   if ((rc = check_launch("ponet_bwd_sums_kernel"))) return rc;
   ponet_global_lse_kernel<<<dim3(heads, B), 32, 0, s>>>(part, lse, nchunks, heads);
   if ((rc = check_launch("ponet_global_lse_kernel"))) return rc;
   ponet_bwd_global_kernel<<<dim3(nchunks, heads, B), 128, 0, s>>>(p, ld, key_bias, qsum, cnt, g, lse, dg, dqbar, static_cast<__half*>(dproj), ld_d,
                                                                   S, H, heads);
   if ((rc = check_launch("ponet_bwd_global_kernel"))) return rc;
-  ponet_bwd_rows_kernel<<<(B * S + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, s>>>(p, ld, d, key_bias, segment_ids, g, segmax, segsum, dqbar, cnt,
+  ponet_bwd_rows_kernel<<<(B * S + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, s>>>(p, ld, d, key_bias, segment_ids, g, segmax, segsum, segties, dqbar, cnt,
                                                                                       static_cast<__half*>(dproj), ld_d, B, S, H, nseg);
   return check_launch("ponet_bwd_rows_kernel");
 }

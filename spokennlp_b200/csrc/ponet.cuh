@@ -199,40 +199,52 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) ponet_mix_kernel(const __half*
 //   dLc_u = sum over the (<=3) windows whose arg-max is u of dout_s;
 //   global branch (g = sum_s a_s K_s, a = softmax(qbar.K/8)):  dz_s = a_s (dg.K_s - dg.g),
 //   dK_s = a_s dg + dz_s qbar / 8,  dqbar = sum_s dz_s K_s / 8,  dQ_s = dqbar / cnt on kept rows.
-// Ties in the max operations have measure zero for real activations and are not split.
+// Ties of the segment max are shared evenly (see pass 1); ties inside a local window go to the first row (max_pool1d).
 
-// pass 1: dg[b,:] and segsum[b,seg,:] (running sums over the contiguous runs).  grid (ceil(S/64), B), block H/8
+// pass 1: dg[b,:], segsum[b,seg,:] and segties[b,seg,:] (running sums over the contiguous runs).  grid (ceil(S/64), B), block H/8
+// segties counts the rows of a segment that attain its maximum: the fp16 grid makes exact ties real, and amax's
+// gradient is shared evenly between tied rows (torch scatter_reduce "amax" semantics, which the restatement follows).
 __global__ void ponet_bwd_sums_kernel(const __half* __restrict__ proj, int ld, const __half* __restrict__ dout, const float* __restrict__ key_bias,
-                                      const int64_t* __restrict__ seg, float* __restrict__ dg, float* __restrict__ segsum, int S, int H, int nseg) {
+                                      const int64_t* __restrict__ seg, const float* __restrict__ segmax, float* __restrict__ dg,
+                                      float* __restrict__ segsum, float* __restrict__ segties, int S, int H, int nseg) {
   const int b = blockIdx.y, s0 = blockIdx.x * 64, c = threadIdx.x * 8;
   if (c >= H) return;
-  float run[8], tot[8];
+  float run[8], tot[8], ties[8];
+  Vec8 mx;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) run[j] = tot[j] = 0.f;
+  for (int j = 0; j < 8; ++j) run[j] = tot[j] = ties[j] = mx.v[j] = 0.f;
   long cur = -1;
+  auto flush = [&]() {
+    if (cur >= 0 && cur < nseg) {
+      const size_t o = (static_cast<size_t>(b) * nseg + cur) * H + c;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (run[j] != 0.f) atomicAdd(segsum + o + j, run[j]);
+        if (ties[j] != 0.f) atomicAdd(segties + o + j, ties[j]);
+      }
+    }
+  };
   for (int s = s0; s < min(S, s0 + 64); ++s) {
     const size_t row = static_cast<size_t>(b) * S + s;
     const long id = seg[row];
     if (id != cur) {
-      if (cur >= 0 && cur < nseg)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(segsum + (static_cast<size_t>(b) * nseg + cur) * H + c + j, run[j]);
+      flush();
       cur = id;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) run[j] = 0.f;
+      for (int j = 0; j < 8; ++j) run[j] = ties[j] = 0.f;
+      if (cur >= 0 && cur < nseg) mx = load8(segmax + (static_cast<size_t>(b) * nseg + cur) * H + c);
     }
     if (key_bias && key_bias[row] != 0.f) continue;
-    const Vec8 d = load8(dout + row * H + c), o = load8(proj + row * ld + 2 * H + c);
+    const Vec8 d = load8(dout + row * H + c), o = load8(proj + row * ld + 2 * H + c), sg = load8(proj + row * ld + 3 * H + c);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float t = d.v[j] * o.v[j];
       run[j] += t;
       tot[j] += t;
+      ties[j] += sg.v[j] == mx.v[j] ? 1.f : 0.f;
     }
   }
-  if (cur >= 0 && cur < nseg)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(segsum + (static_cast<size_t>(b) * nseg + cur) * H + c + j, run[j]);
+  flush();
 #pragma unroll
   for (int j = 0; j < 8; ++j) atomicAdd(dg + static_cast<size_t>(b) * H + c + j, tot[j]);
 }
@@ -317,7 +329,8 @@ __global__ void __launch_bounds__(128) ponet_bwd_global_kernel(const __half* __r
 __global__ void __launch_bounds__(ROW_WARPS * 32) ponet_bwd_rows_kernel(const __half* __restrict__ proj, int ld, const __half* __restrict__ dout,
                                                                          const float* __restrict__ key_bias, const int64_t* __restrict__ seg,
                                                                          const float* __restrict__ g, const float* __restrict__ segmax,
-                                                                         const float* __restrict__ segsum, const float* __restrict__ dqbar,
+                                                                         const float* __restrict__ segsum, const float* __restrict__ segties,
+                                                                         const float* __restrict__ dqbar,
                                                                          const float* __restrict__ cnt, __half* __restrict__ dproj, int ld_d,
                                                                          int B, int S, int H, int nseg) {
   const int lane = threadIdx.x & 31;
@@ -367,13 +380,14 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) ponet_bwd_rows_kernel(const __
         const Vec8 gv = load8(g + static_cast<size_t>(b) * H + c);
         const Vec8 sm = load8(segmax + (static_cast<size_t>(b) * nseg + id) * H + c);
         const Vec8 ss = load8(segsum + (static_cast<size_t>(b) * nseg + id) * H + c);
+        const Vec8 st = load8(segties + (static_cast<size_t>(b) * nseg + id) * H + c);
         const Vec8 sgv = load8(proj + static_cast<size_t>(row) * ld + 3 * H + c);
         const Vec8 dqb = load8(dqbar + static_cast<size_t>(b) * H + c);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           dq.v[j] = dqb.v[j] * inv_cnt;
           dO.v[j] = d.v[j] * (gv.v[j] + sm.v[j]);
-          dsg.v[j] = (sgv.v[j] == sm.v[j]) ? ss.v[j] : 0.f;
+          dsg.v[j] = (sgv.v[j] == sm.v[j]) ? ss.v[j] / fmaxf(st.v[j], 1.f) : 0.f;
           dlc.v[j] = 0.f;
         }
         // dLc_u: u = s is the arg-max of window w (centred at w in {s-1, s, s+1}) iff Lc_s beats the other two taps
