@@ -9,7 +9,9 @@
 
 #include "../../include/b200enc.h"
 #include "attn_bwd.cuh"
+#include "attn_bwd2.cuh"
 #include "attn_fwd.cuh"
+#include "attn_fwd2.cuh"
 #include "gemm.cuh"
 #include "gemm2.cuh"
 #include "optim.cuh"
@@ -287,6 +289,16 @@ int b200_attn_fwd_drop(const void* q, int ldq, int q_col0, const void* kv, int l
   AttnFwdArgs a{B, heads, Sq, Sk, q_col0, k_col0, v_col0, key_bias, kv_len, static_cast<__half*>(ctx), ld_out, lse2,
                 1.4426950408889634f / 8.0f, drop};
   dim3 grid((Sq + 2 * ATT_BQ - 1) / (2 * ATT_BQ), heads, B);
+  if (!(g_gemm_dbg.load() & 0x100000)) {      // default: second-generation kernel (0x100000 keeps the first one for A/B runs)
+    static int d0 = set_smem(attn_fwd2_kernel<false>, AttnFwdSmem::TOTAL);
+    static int d1 = set_smem(attn_fwd2_kernel<true>, AttnFwdSmem::TOTAL);
+    if (d0 != B200_OK || d1 != B200_OK) return d0 ? d0 : d1;
+    CUtensorMap to;                             // context output fp16 [B*Sq, ld_out], 64 x 32 patches (one per softmax warp)
+    if ((rc = get_tmap(ctx, static_cast<uint64_t>(B) * Sq, ld_out, ld_out, 32, &to))) return rc;
+    if (drop.seed_base) attn_fwd2_kernel<true><<<grid, ATT2_THREADS, AttnFwdSmem::TOTAL, static_cast<cudaStream_t>(stream)>>>(tq, tkv, to, a);
+    else attn_fwd2_kernel<false><<<grid, ATT2_THREADS, AttnFwdSmem::TOTAL, static_cast<cudaStream_t>(stream)>>>(tq, tkv, to, a);
+    return check_launch("attn_fwd2_kernel");
+  }
   if (drop.seed_base) attn_fwd_kernel<true><<<grid, ATT_THREADS, AttnFwdSmem::TOTAL, static_cast<cudaStream_t>(stream)>>>(tq, tkv, a);
   else attn_fwd_kernel<false><<<grid, ATT_THREADS, AttnFwdSmem::TOTAL, static_cast<cudaStream_t>(stream)>>>(tq, tkv, a);
   return check_launch("attn_fwd_kernel");
@@ -394,6 +406,26 @@ static int layernorm_bwd_impl(const void* dy, const void* dy2, const void* x, in
                               void* stream) {
   if (int rc = check_row_shape("layernorm_bwd", rows, H)) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!(g_gemm_dbg.load() & 0x200000)) {      // default: second-generation kernel (0x200000 keeps the first one for A/B runs)
+    const int tpr = ((H / 8 + 31) / 32) * 32, slots = LNB_THREADS / tpr;
+    int grid2 = (rows + slots * LNB_R - 1) / (slots * LNB_R);
+    if (grid2 > sm_count() * 2) grid2 = sm_count() * 2;
+    const size_t smem2 = (3 * slots * H + 2 * slots * (tpr / 32) * 2 * LNB_R) * sizeof(float);
+    if (x_dtype == B200_DT_F32) {
+      static int c = set_smem(ln_bwd2_kernel<float>, 64 * 1024);
+      if (c) return c;
+      ln_bwd2_kernel<float><<<grid2, LNB_THREADS, smem2, s>>>(static_cast<const __half*>(dy), static_cast<const __half*>(dy2), static_cast<const float*>(x),
+                                                               mean, rstd, gamma, static_cast<__half*>(dx), dgamma, dbeta, dbias, alpha, rows, H, tpr,
+                                                               static_cast<__half*>(dx_drop), drop);
+    } else {
+      static int c = set_smem(ln_bwd2_kernel<__half>, 64 * 1024);
+      if (c) return c;
+      ln_bwd2_kernel<__half><<<grid2, LNB_THREADS, smem2, s>>>(static_cast<const __half*>(dy), static_cast<const __half*>(dy2), static_cast<const __half*>(x),
+                                                                mean, rstd, gamma, static_cast<__half*>(dx), dgamma, dbeta, dbias, alpha, rows, H, tpr,
+                                                                static_cast<__half*>(dx_drop), drop);
+    }
+    return check_launch("ln_bwd2_kernel");
+  }
   int grid = (rows + ROW_WARPS - 1) / ROW_WARPS;
   const int cap = sm_count() * 3;        // 3 resident CTAs per SM: one wave, and 3x fewer column-sum atomics than an oversubscribed grid
   if (grid > cap) grid = cap;

@@ -218,6 +218,129 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 3) ln_bwd_kernel(const __half*
   }
 }
 
+// Second-generation LayerNorm backward.  ln_bwd_kernel keeps a whole row per warp, which costs 72 accumulator registers per
+// lane for the three column sums (dgamma, dbeta, dbias): 168 registers, 12 resident warps per SM, one row in flight per
+// warp — 2.4 TB/s (profiles/r01d).  Here a row is spread over `tpr` threads (one 8-column chunk each, so the column sums
+// are 24 registers), a CTA runs 384 / tpr independent row slots, and every slot pulls LNB_R rows per trip, so an SM keeps
+// 24 warps x LNB_R rows of loads in flight.  The per-row sums cross the slot's warps through shared memory behind a
+// slot-local named barrier (parity-double-buffered: one barrier per trip).
+constexpr int LNB_THREADS = 384;
+constexpr int LNB_R = 2;
+
+template <typename InT>
+__global__ void __launch_bounds__(LNB_THREADS, 2) ln_bwd2_kernel(const __half* __restrict__ dy, const __half* __restrict__ dy2,
+                                                                  const InT* __restrict__ x, const float* __restrict__ mean_in,
+                                                                  const float* __restrict__ rstd_in, const float* __restrict__ gamma,
+                                                                  __half* __restrict__ dx, float* __restrict__ dgamma,
+                                                                  float* __restrict__ dbeta, float* __restrict__ dbias,
+                                                                  const float* __restrict__ alpha_ptr, int rows, int H, int tpr,
+                                                                  __half* __restrict__ dx_drop, DropCfg drop) {
+  extern __shared__ float red[];   // [3][slots][H] column sums, then [2 parities][slots][wps][2 * LNB_R] row-sum partials
+  const int slots = LNB_THREADS / tpr, wps = tpr >> 5;
+  const int slot = threadIdx.x / tpr, tl = threadIdx.x - slot * tpr;
+  const int lane = threadIdx.x & 31, wis = tl >> 5;            // warp inside the slot
+  const int c = tl * 8;
+  const bool active = c < H;
+  float* part = red + 3 * slots * H;
+  const bool dropping = dx_drop != nullptr && drop.seed_base != nullptr;
+  const uint32_t dseed = dropping ? drop_seed(drop) : 0u;
+  const float inv_h = 1.0f / H;
+  Vec8 ag, ab, ad;               // gamma is re-read where needed (L1-resident): 8 fewer live registers
+#pragma unroll
+  for (int j = 0; j < 8; ++j) ag.v[j] = ab.v[j] = ad.v[j] = 0.f;
+  int par = 0;
+  for (int base = (blockIdx.x * slots + slot) * LNB_R; base < rows; base += gridDim.x * slots * LNB_R, par ^= 1) {
+    Vec8 xh[LNB_R], d[LNB_R];
+    float s[2 * LNB_R], rs[LNB_R];
+    Vec8 gm;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gm.v[j] = 0.f;
+    if (active) gm = load8(gamma + c);
+#pragma unroll
+    for (int k = 0; k < LNB_R; ++k) {
+      const int row = base + k;
+      s[2 * k] = s[2 * k + 1] = 0.f;
+      rs[k] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xh[k].v[j] = d[k].v[j] = 0.f;
+      if (row < rows && active) {
+        const size_t off = static_cast<size_t>(row) * H + c;
+        const Vec8 xv = load8(x + off);
+        d[k] = load8(dy + off);
+        if (dy2) {
+          const Vec8 d2 = load8(dy2 + off);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d[k].v[j] += d2.v[j];
+        }
+        const float mean = mean_in[row];
+        rs[k] = rstd_in[row];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[k].v[j] = (xv.v[j] - mean) * rs[k];
+          const float g = d[k].v[j] * gm.v[j];
+          s[2 * k] += g;
+          s[2 * k + 1] = fmaf(g, xh[k].v[j], s[2 * k + 1]);
+          ag.v[j] = fmaf(d[k].v[j], xh[k].v[j], ag.v[j]);
+          ab.v[j] += d[k].v[j];
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 2 * LNB_R; ++k) s[k] = warp_sum(s[k]);
+    if (wps > 1) {
+      float* mine = part + ((par * slots + slot) * wps) * (2 * LNB_R);
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 2 * LNB_R; ++k) mine[wis * 2 * LNB_R + k] = s[k];
+      }
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(tpr) : "memory");
+#pragma unroll
+      for (int k = 0; k < 2 * LNB_R; ++k) {
+        float t = 0.f;
+        for (int w = 0; w < wps; ++w) t += mine[w * 2 * LNB_R + k];
+        s[k] = t;
+      }
+    }
+    if (active) gm = load8(gamma + c);
+#pragma unroll
+    for (int k = 0; k < LNB_R; ++k) {
+      const int row = base + k;
+      if (row < rows && active) {
+        const float m1 = s[2 * k] * inv_h, m2 = s[2 * k + 1] * inv_h;
+        Vec8 o;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o.v[j] = rs[k] * (d[k].v[j] * gm.v[j] - m1 - xh[k].v[j] * m2);
+        store8(dx + static_cast<size_t>(row) * H + c, o);
+        if (dropping) {
+          drop8(o, static_cast<uint32_t>(row) * static_cast<uint32_t>(H) + c, dseed, drop);
+          store8(dx_drop + static_cast<size_t>(row) * H + c, o);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ad.v[j] += o.v[j];
+      }
+    }
+  }
+  // column sums: slots -> one atomic per column per CTA
+  if (active) {
+    store8(red + (0 * slots + slot) * H + c, ag);
+    store8(red + (1 * slots + slot) * H + c, ab);
+    store8(red + (2 * slots + slot) * H + c, ad);
+  }
+  __syncthreads();
+  const float alpha = alpha_ptr ? *alpha_ptr : 1.0f;
+  for (int col = threadIdx.x; col < H; col += blockDim.x) {
+    float a = 0.f, b = 0.f, dd = 0.f;
+    for (int w = 0; w < slots; ++w) {
+      a += red[(0 * slots + w) * H + col];
+      b += red[(1 * slots + w) * H + col];
+      dd += red[(2 * slots + w) * H + col];
+    }
+    atomicAdd(dgamma + col, a * alpha);
+    atomicAdd(dbeta + col, b * alpha);
+    if (dbias) atomicAdd(dbias + col, dd * alpha);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ K1: embeddings
 // y = LN(word[ids] + pos[pos_ids] + type[tt]); tables are the fp32 master parameters (gathered rows, 128-bit loads).
 // bert_model.py:184-210.  `inputs_embeds` (fp32 [rows,H]) replaces the word gather when given.
