@@ -10,8 +10,10 @@
 #include "../../include/b200enc.h"
 #include "attn_bwd.cuh"
 #include "attn_bwd2.cuh"
+#include "attn_bwd3.cuh"
 #include "attn_fwd.cuh"
 #include "attn_fwd2.cuh"
+#include "attn_fwd3.cuh"
 #include "gemm.cuh"
 #include "gemm2.cuh"
 #include "optim.cuh"
@@ -295,6 +297,16 @@ int b200_attn_fwd_drop(const void* q, int ldq, int q_col0, const void* kv, int l
     if (d0 != B200_OK || d1 != B200_OK) return d0 ? d0 : d1;
     CUtensorMap to;                             // context output fp16 [B*Sq, ld_out], 64 x 32 patches (one per softmax warp)
     if ((rc = get_tmap(ctx, static_cast<uint64_t>(B) * Sq, ld_out, ld_out, 32, &to))) return rc;
+    if (!(g_gemm_dbg.load() & 0x400000)) {    // default: persistent kernel, one CTA per SM walking (batch, head, query-pair) items
+      static int e0 = set_smem(attn_fwd3_kernel<false>, AttnFwd3Smem::TOTAL);
+      static int e1 = set_smem(attn_fwd3_kernel<true>, AttnFwd3Smem::TOTAL);
+      if (e0 != B200_OK || e1 != B200_OK) return e0 ? e0 : e1;
+      const long long items = static_cast<long long>(grid.x) * grid.y * grid.z;
+      const int ctas = items < sm_count() ? static_cast<int>(items) : sm_count();
+      if (drop.seed_base) attn_fwd3_kernel<true><<<ctas, ATT2_THREADS, AttnFwd3Smem::TOTAL, static_cast<cudaStream_t>(stream)>>>(tq, tkv, to, a);
+      else attn_fwd3_kernel<false><<<ctas, ATT2_THREADS, AttnFwd3Smem::TOTAL, static_cast<cudaStream_t>(stream)>>>(tq, tkv, to, a);
+      return check_launch("attn_fwd3_kernel");
+    }
     if (drop.seed_base) attn_fwd2_kernel<true><<<grid, ATT2_THREADS, AttnFwdSmem::TOTAL, static_cast<cudaStream_t>(stream)>>>(tq, tkv, to, a);
     else attn_fwd2_kernel<false><<<grid, ATT2_THREADS, AttnFwdSmem::TOTAL, static_cast<cudaStream_t>(stream)>>>(tq, tkv, to, a);
     return check_launch("attn_fwd2_kernel");
@@ -407,23 +419,27 @@ static int layernorm_bwd_impl(const void* dy, const void* dy2, const void* x, in
   if (int rc = check_row_shape("layernorm_bwd", rows, H)) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (!(g_gemm_dbg.load() & 0x200000)) {      // default: second-generation kernel (0x200000 keeps the first one for A/B runs)
-    const int tpr = ((H / 8 + 31) / 32) * 32, slots = LNB_THREADS / tpr;
+    const int wps = (H / 8 + 31) / 32, tpr = 32 * wps, slots = LNB_THREADS / tpr;     // wps in 1..4 (H <= 1024)
     int grid2 = (rows + slots * LNB_R - 1) / (slots * LNB_R);
     if (grid2 > sm_count() * 2) grid2 = sm_count() * 2;
-    const size_t smem2 = (3 * slots * H + 2 * slots * (tpr / 32) * 2 * LNB_R) * sizeof(float);
+    const size_t smem2 = 3 * slots * H * sizeof(float) + 2 * slots * wps * 16;
+    const __half* dyh = static_cast<const __half*>(dy);
+    const __half* dy2h = static_cast<const __half*>(dy2);
+    __half* dxh = static_cast<__half*>(dx);
+    __half* dxd = static_cast<__half*>(dx_drop);
+#define B200_LNB2(T, W)                                                                                                          \
+  do {                                                                                                                           \
+    static int c = set_smem(ln_bwd2_kernel<T, W>, 64 * 1024);                                                                    \
+    if (c) return c;                                                                                                             \
+    ln_bwd2_kernel<T, W><<<grid2, LNB_THREADS, smem2, s>>>(dyh, dy2h, static_cast<const T*>(x), mean, rstd, gamma, dxh, dgamma, \
+                                                          dbeta, dbias, alpha, rows, H, dxd, drop);                              \
+  } while (0)
     if (x_dtype == B200_DT_F32) {
-      static int c = set_smem(ln_bwd2_kernel<float>, 64 * 1024);
-      if (c) return c;
-      ln_bwd2_kernel<float><<<grid2, LNB_THREADS, smem2, s>>>(static_cast<const __half*>(dy), static_cast<const __half*>(dy2), static_cast<const float*>(x),
-                                                               mean, rstd, gamma, static_cast<__half*>(dx), dgamma, dbeta, dbias, alpha, rows, H, tpr,
-                                                               static_cast<__half*>(dx_drop), drop);
+      if (wps == 1) B200_LNB2(float, 1); else if (wps == 2) B200_LNB2(float, 2); else if (wps == 3) B200_LNB2(float, 3); else B200_LNB2(float, 4);
     } else {
-      static int c = set_smem(ln_bwd2_kernel<__half>, 64 * 1024);
-      if (c) return c;
-      ln_bwd2_kernel<__half><<<grid2, LNB_THREADS, smem2, s>>>(static_cast<const __half*>(dy), static_cast<const __half*>(dy2), static_cast<const __half*>(x),
-                                                                mean, rstd, gamma, static_cast<__half*>(dx), dgamma, dbeta, dbias, alpha, rows, H, tpr,
-                                                                static_cast<__half*>(dx_drop), drop);
+      if (wps == 1) B200_LNB2(__half, 1); else if (wps == 2) B200_LNB2(__half, 2); else if (wps == 3) B200_LNB2(__half, 3); else B200_LNB2(__half, 4);
     }
+#undef B200_LNB2
     return check_launch("ln_bwd2_kernel");
   }
   int grid = (rows + ROW_WARPS - 1) / ROW_WARPS;

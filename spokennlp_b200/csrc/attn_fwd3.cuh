@@ -1,0 +1,358 @@
+// Fused attention forward, persistent version (same contract as attn_fwd.cuh / attn_fwd2.cuh).
+//
+// The Sk sweep of attn_fwd2_kernel (profiles/r01e) splits its 74 us at the bench shape into 41 us of per-key-block work and
+// 33 us of per-CTA fixed cost: launch, TMEM allocation, the first TMA round trip, the pipeline ramp and the output drain
+// are all exposed because one CTA owns the SM (200 KB of shared memory, 512 TMEM columns) and the next one cannot start
+// before it has left.  Here ONE CTA per SM stays resident and walks work items (batch, head, 256-query pair):
+//   * the TMA warp runs ahead across item boundaries (Q double-buffered by item parity, K and V in separate 2-stage rings
+//     — K_{j+1} is wanted a whole block earlier than V_{j+1}, so it must not queue behind it),
+//   * the MMA warps issue the first S of the next item while the softmax warps are still writing the previous context,
+//   * barrier phases come from running counters, so nothing is re-initialised between items.
+// Everything inside a block is attn_fwd2_kernel: one pass over the scores, early hand-back of the score buffer, the two
+// query tiles running half a period apart, TMA-stored context rows.
+//   warp 0       TMA producer
+//   warp 1, 2    MMA issuers for query tile A / B
+//   warps 3-10   softmax A (3-6) / softmax B (7-10): one thread per query row
+#pragma once
+#include "attn_fwd2.cuh"
+
+namespace b200 {
+
+struct AttnFwd3Smem {
+  static constexpr int TILE = ATT_BQ * ATT_D * 2;                    // 16 KB: one Q / K / V tile
+  static constexpr int P_BYTES = ATT_BQ * ATT_BK * 2;                // 32 KB per query tile
+  static constexpr int OFF_Q = 0;                                    // [2 item parities][2 tiles]
+  static constexpr int OFF_K = OFF_Q + 4 * TILE;                     // [2 stages]
+  static constexpr int OFF_V = OFF_K + 2 * TILE;                     // [2 stages]
+  static constexpr int OFF_P = OFF_V + 2 * TILE;                     // [2 tiles]
+  static constexpr int OFF_BIAS = OFF_P + 2 * P_BYTES;               // [2 tiles][2 buffers][128] floats
+  static constexpr int OFF_BAR = OFF_BIAS + 2 * 2 * ATT_BK * 4;
+  static constexpr int TOTAL = OFF_BAR + 256 + 1024;
+};
+
+template <bool DROP>
+__global__ void __launch_bounds__(ATT2_THREADS, 1)
+attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                 const __grid_constant__ CUtensorMap tmO, const AttnFwdArgs a) {
+  using S = AttnFwd3Smem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
+  uint64_t* q_full = bars;             // 2
+  uint64_t* q_empty = bars + 2;        // 2 (one arrival per MMA warp)
+  uint64_t* k_full = bars + 4;         // 2
+  uint64_t* k_empty = bars + 6;        // 2 (one arrival per MMA warp)
+  uint64_t* v_full = bars + 8;         // 2
+  uint64_t* v_empty = bars + 10;       // 2 (one arrival per MMA warp)
+  uint64_t* s_full = bars + 12;        // 2 (per tile)
+  uint64_t* s_free = bars + 14;        // 2 (128 arrivals)
+  uint64_t* p_full = bars + 16;        // 2 (128 arrivals)
+  uint64_t* o_full = bars + 18;        // 2
+  uint64_t* b_go = bars + 20;          // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nqp = (a.Sq + 2 * ATT_BQ - 1) / (2 * ATT_BQ);
+  const int n_items = a.B * a.heads * nqp;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+    tma_prefetch_desc(&tmO);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 2);
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 2);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 2);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 128);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&o_full[i], 1);
+    }
+    mbar_init(b_go, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  // TMEM columns: S_A [0,128)  S_B [128,256)  O_A [256,320)  O_B [320,384)
+
+  // per-item geometry, identical in every role
+  struct Item {
+    int b, h, q0, kv_len, n_blocks;
+    bool tileB, general_bias;
+  };
+  auto decode = [&](int item) {
+    Item it;
+    const int qp = item % nqp, bh = item / nqp;
+    it.h = bh % a.heads;
+    it.b = bh / a.heads;
+    it.q0 = qp * 2 * ATT_BQ;
+    it.tileB = (it.q0 + ATT_BQ) < a.Sq;
+    int kv = a.kv_len ? a.kv_len[it.b] : a.Sk;
+    it.general_bias = a.key_bias != nullptr && (a.kv_len == nullptr || kv < 0);   // see attn_fwd.cuh
+    it.kv_len = max(1, min(kv < 0 ? -kv : kv, a.Sk));
+    it.n_blocks = (it.kv_len + ATT_BK - 1) / ATT_BK;
+    return it;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t n = 0, kb = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+        const Item it = decode(item);
+        const uint32_t buf = n & 1;
+        mbar_wait(&q_empty[buf], ((n >> 1) & 1) ^ 1);
+        mbar_expect_tx(&q_full[buf], (it.tileB ? 2 : 1) * S::TILE);
+        uint8_t* qd = smem + S::OFF_Q + buf * 2 * S::TILE;
+        tma_load_2d(qd, &tmQ, &q_full[buf], a.q_col0 + it.h * ATT_D, it.b * a.Sq + it.q0);
+        if (it.tileB) tma_load_2d(qd + S::TILE, &tmQ, &q_full[buf], a.q_col0 + it.h * ATT_D, it.b * a.Sq + it.q0 + ATT_BQ);
+        for (int j = 0; j < it.n_blocks; ++j, ++kb) {
+          const uint32_t s = kb & 1, ph = (kb >> 1) & 1;
+          mbar_wait(&k_empty[s], ph ^ 1);
+          mbar_expect_tx(&k_full[s], S::TILE);
+          tma_load_2d(smem + S::OFF_K + s * S::TILE, &tmKV, &k_full[s], a.k_col0 + it.h * ATT_D, it.b * a.Sk + j * ATT_BK);
+          mbar_wait(&v_empty[s], ph ^ 1);
+          mbar_expect_tx(&v_full[s], S::TILE);
+          tma_load_2d(smem + S::OFF_V + s * S::TILE, &tmKV, &v_full[s], a.v_col0 + it.h * ATT_D, it.b * a.Sk + j * ATT_BK);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp <= 2) {
+    // ------------------------------------------------------------------ MMA issuer of query tile x
+    const int x = warp - 1;
+    constexpr uint32_t idesc_s = make_idesc_f16(128, ATT_BK, 0, 0);
+    constexpr uint32_t idesc_o = make_idesc_f16(128, ATT_D, 0, 1);
+    const uint32_t pa = smem_u32(smem + S::OFF_P + x * S::P_BYTES);
+    uint32_t n = 0, kb = 0, t = 0;     // items seen, K/V ring position, blocks this tile has processed
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+      const Item it = decode(item);
+      const uint32_t buf = n & 1;
+      const int nb = it.n_blocks;
+      if (x == 1 && !it.tileB) {       // no second tile in this item: keep the shared rings' arrival counts balanced
+        mbar_wait(&q_full[buf], (n >> 1) & 1);
+        if (lane == 0) mbar_arrive(&q_empty[buf]);
+        for (int j = 0; j < nb; ++j, ++kb) {
+          const uint32_t s = kb & 1, ph = (kb >> 1) & 1;
+          mbar_wait(&k_full[s], ph);
+          if (lane == 0) mbar_arrive(&k_empty[s]);
+          mbar_wait(&v_full[s], ph);
+          if (lane == 0) mbar_arrive(&v_empty[s]);
+        }
+        __syncwarp();
+        continue;
+      }
+      const uint32_t qa = smem_u32(smem + S::OFF_Q + (buf * 2 + x) * S::TILE);
+      auto issue_s = [&](uint32_t s, bool last) {          // S_x = Q_x K^T from K ring stage s
+        const uint32_t ka = smem_u32(smem + S::OFF_K + s * S::TILE);
+#pragma unroll
+        for (int kk = 0; kk < ATT_D / 16; ++kk)
+          umma_ss(tmem + x * 128, make_smem_desc(qa + kk * 32, 0, 1024), make_smem_desc(ka + kk * 32, 0, 1024), idesc_s, kk > 0);
+        umma_commit(&s_full[x]);
+        umma_commit(&k_empty[s]);
+        if (last) umma_commit(&q_empty[buf]);                // Q of this item is not needed after its last score block
+      };
+      mbar_wait(&q_full[buf], (n >> 1) & 1);
+      mbar_wait(&k_full[kb & 1], (kb >> 1) & 1);
+      if (t > 0) mbar_wait(&s_free[x], (t - 1) & 1);         // the previous block's score rows sit in registers
+      else if (x == 1) mbar_wait(b_go, 0);                   // tile B starts half a period after tile A (attn_fwd2.cuh)
+      tc_fence_after();
+      if (lane == 0) issue_s(kb & 1, nb == 1);
+      __syncwarp();
+      for (int j = 0; j < nb; ++j, ++t, ++kb) {
+        const uint32_t s = kb & 1, ph = (kb >> 1) & 1;
+        if (j + 1 < nb) {                                    // next scores as soon as the softmax threads hold block j
+          const uint32_t s1 = (kb + 1) & 1, ph1 = ((kb + 1) >> 1) & 1;
+          mbar_wait(&k_full[s1], ph1);
+          mbar_wait(&s_free[x], t & 1);
+          tc_fence_after();
+          if (lane == 0) issue_s(s1, j + 2 == nb);
+          __syncwarp();
+        }
+        mbar_wait(&p_full[x], t & 1);
+        mbar_wait(&v_full[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t va = smem_u32(smem + S::OFF_V + s * S::TILE);
+#pragma unroll
+          for (int kk = 0; kk < ATT_BK / 16; ++kk)
+            umma_ss(tmem + 256 + x * 64, make_smem_desc(pa + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024),
+                    make_smem_desc(va + kk * 2048, 8192, 1024), idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+          umma_commit(&o_full[x]);
+          umma_commit(&v_empty[s]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax groups
+    const int x = (warp - 3) >> 2;                // 0 = tile A, 1 = tile B
+    const int qd = warp & 3;                      // TMEM lane quadrant of this warp
+    const int r = qd * 32 + lane;                 // row inside the query tile
+    const int tg = ((warp - 3) & 3) * 32 + lane;  // 0..127 inside the group (bias staging)
+    const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
+    const uint32_t bias_s = smem_u32(smem + S::OFF_BIAS) + x * 2 * ATT_BK * 4;
+    const uint32_t p_row = smem_u32(smem + S::OFF_P + x * S::P_BYTES) + r * 128;
+    const float NEG_INF = -INFINITY;
+    const float sc = a.scale_log2;
+    const float inv_sc = 1.0f / sc;
+    const uint32_t dseed = DROP ? drop_seed(a.drop) : 0u;
+    uint32_t t = 0;                               // blocks this tile has processed (barrier phases)
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const Item it = decode(item);
+      if (x == 1 && !it.tileB) continue;
+      const int b = it.b, h = it.h, kv_len = it.kv_len, n_blocks = it.n_blocks;
+      const int qrow = it.q0 + x * ATT_BQ + r;
+      const uint32_t dbase = DROP ? static_cast<uint32_t>(((static_cast<size_t>(b) * a.heads + h) * a.Sq + min(qrow, a.Sq - 1)) * ((a.Sk + 1) >> 1)) : 0u;
+      float m = NEG_INF, l = 0.f;
+      if (lane == 0) tma_wait_group_read<0>();    // the previous item's context store has read this warp's staging rows
+      __syncwarp();
+      for (int j = 0; j < n_blocks; ++j, ++t) {
+        const bool partial = (j + 1) * ATT_BK > kv_len;
+        const uint32_t bj = bias_s + (t & 1) * ATT_BK * 4;
+        if (it.general_bias) {                    // bias in units of raw scores: (s + bias/scale) * scale = s*scale + bias
+          const int key = j * ATT_BK + tg;
+          float bv = NEG_INF;
+          if (key < kv_len) bv = a.key_bias[static_cast<size_t>(b) * a.Sk + key] * 1.4426950408889634f * inv_sc;
+          sts_f32(bj + tg * 4, bv);
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + x) : "memory");
+        }
+        mbar_wait(&s_full[x], t & 1);
+        tc_fence_after();
+        uint32_t v[128];
+        tmem_ld_x32(tmem + lane_addr + x * 128, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+        tmem_ld_x32(tmem + lane_addr + x * 128 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+        tmem_ld_x32(tmem + lane_addr + x * 128 + 64, *reinterpret_cast<uint32_t(*)[32]>(&v[64]));
+        tmem_ld_x32(tmem + lane_addr + x * 128 + 96, *reinterpret_cast<uint32_t(*)[32]>(&v[96]));
+        tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive(&s_free[x]);                  // the tensor core may overwrite S_x with the next block now
+        if (x == 0 && t == 0 && tg == 0) mbar_arrive(b_go);
+        // ---- masked keys (only blocks that have any)
+        if (it.general_bias) {
+#pragma unroll
+          for (int i = 0; i < 128; i += 4) {
+            const uint4 bb = lds128(bj + i * 4);
+            v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(bb.x));
+            v[i + 1] = __float_as_uint(__uint_as_float(v[i + 1]) + __uint_as_float(bb.y));
+            v[i + 2] = __float_as_uint(__uint_as_float(v[i + 2]) + __uint_as_float(bb.z));
+            v[i + 3] = __float_as_uint(__uint_as_float(v[i + 3]) + __uint_as_float(bb.w));
+          }
+        } else if (partial) {
+          const int lim = kv_len - j * ATT_BK;    // keys [0, lim) of this block are kept
+#pragma unroll
+          for (int i = 0; i < 128; ++i) v[i] = (i < lim) ? v[i] : 0xff800000u;
+        }
+        // ---- row maximum
+        float m0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1])), m1 = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
+#pragma unroll
+        for (int i = 4; i < 128; i += 4) {
+          m0 = fmaxf(m0, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+          m1 = fmaxf(m1, fmaxf(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])));
+        }
+        const float mx = fmaxf(m0, m1) * sc;      // sc > 0
+        // ---- lazy rescale: keep the running reference max unless some row of this warp grew by more than 2^8
+        const float m_new = fmaxf(m, mx);
+        const bool grow = (m_new - m) > 8.0f || m == NEG_INF;
+        const bool rescale = __any_sync(0xffffffffu, grow);
+        float m_use = rescale ? m_new : m;
+        if (m_use == NEG_INF) m_use = 0.f;
+        const float alpha = rescale ? fast_exp2(m - m_use) : 1.0f;     // m == -inf -> 0
+        if (j > 0) {                              // P.V of block j-1 finished: P smem is free, O may be rescaled
+          mbar_wait(&o_full[x], (t - 1) & 1);
+          tc_fence_after();
+          if (rescale) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint32_t o[16];
+              tmem_ld_x16(tmem + lane_addr + 256 + x * 64 + c * 16, o);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st_x16(tmem + lane_addr + 256 + x * 64 + c * 16, o);
+            }
+            tmem_wait_st();
+          }
+        }
+        // ---- p = exp2(s * scale - m_use), row sum, fp16 P into the swizzled smem tile (16 chunks of 8 keys)
+        const float neg_m = -m_use;
+        float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 16; ++ch) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = ch * 8 + 2 * e;
+            float p0 = fast_exp2(fmaf(__uint_as_float(v[i]), sc, neg_m));
+            float p1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), sc, neg_m));
+            rs0 += p0;
+            rs1 += p1;
+            if (DROP) {                             // the row sum (softmax denominator) is taken before dropout
+              float k0, k1;
+              drop_pair(dbase + ((j * ATT_BK + i) >> 1), dseed, a.drop.thr16, a.drop.scale, k0, k1);
+              p0 *= k0;
+              p1 *= k1;
+            }
+            const __half2 hp = __floats2half2_rn(p0, p1);
+            pk[e] = *reinterpret_cast<const uint32_t*>(&hp);
+          }
+          sts128(p_row + (ch >> 3) * 16384 + (((ch & 7) ^ (r & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+        }
+        l = fmaf(l, alpha, rs0 + rs1);
+        m = (m_use == 0.f && m_new == NEG_INF) ? NEG_INF : m_use;
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(&p_full[x]);
+      }
+      // ---------------------------------------------------------------- finalise: O / l -> ctx, LSE
+      mbar_wait(&o_full[x], (t - 1) & 1);
+      tc_fence_after();
+      const float inv_l = l > 0.f ? 1.0f / l : 0.f;
+      uint32_t o[2][32];
+      tmem_ld_x32(tmem + lane_addr + 256 + x * 64, o[0]);
+      tmem_ld_x32(tmem + lane_addr + 256 + x * 64 + 32, o[1]);
+      tmem_wait_ld();
+      tc_fence_before();
+      uint32_t w[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const __half2 hv = __floats2half2_rn(__uint_as_float(o[k >> 4][2 * (k & 15)]) * inv_l, __uint_as_float(o[k >> 4][2 * (k & 15) + 1]) * inv_l);
+        w[k] = *reinterpret_cast<const uint32_t*>(&hv);
+      }
+      const int wrow0 = it.q0 + x * ATT_BQ + qd * 32;        // first query row of this warp
+      if (wrow0 + 32 <= a.Sq) {                              // one TMA store per warp from a swizzled staging patch (attn_fwd2.cuh)
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) sts128(p_row + ((ch ^ (r & 7)) << 4), w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmO, smem + S::OFF_P + x * S::P_BYTES + qd * 32 * 128, h * ATT_D, b * a.Sq + wrow0);
+          tma_commit_group();
+        }
+      } else if (qrow < a.Sq) {
+        __half* dst = a.out + (static_cast<size_t>(b) * a.Sq + qrow) * a.ld_out + h * ATT_D;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) *reinterpret_cast<uint4*>(dst + ch * 8) = make_uint4(w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
+      }
+      if (qrow < a.Sq && a.lse2) a.lse2[(static_cast<size_t>(b) * a.heads + h) * a.Sq + qrow] = (l > 0.f) ? (m + log2f(l)) : NEG_INF;
+    }
+    if (lane == 0) tma_wait_group_read<0>();      // staging memory stays valid until the bulk stores have read it
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace b200

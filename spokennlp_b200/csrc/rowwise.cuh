@@ -226,86 +226,115 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 3) ln_bwd_kernel(const __half*
 // slot-local named barrier (parity-double-buffered: one barrier per trip).
 constexpr int LNB_THREADS = 384;
 constexpr int LNB_R = 2;
+static_assert(LNB_R == 2, "the row-sum exchange below moves one float4 (2 rows x 2 sums) per warp");
 
-template <typename InT>
+__device__ __forceinline__ Vec8 unpack8(const uint4& raw) {
+  const __half2* h = reinterpret_cast<const __half2*>(&raw);
+  Vec8 r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(h[i]);
+    r.v[2 * i] = f.x;
+    r.v[2 * i + 1] = f.y;
+  }
+  return r;
+}
+
+// WPS = warps per row slot (tpr = 32 * WPS threads share a row)
+template <typename InT, int WPS>
 __global__ void __launch_bounds__(LNB_THREADS, 2) ln_bwd2_kernel(const __half* __restrict__ dy, const __half* __restrict__ dy2,
                                                                   const InT* __restrict__ x, const float* __restrict__ mean_in,
                                                                   const float* __restrict__ rstd_in, const float* __restrict__ gamma,
                                                                   __half* __restrict__ dx, float* __restrict__ dgamma,
                                                                   float* __restrict__ dbeta, float* __restrict__ dbias,
-                                                                  const float* __restrict__ alpha_ptr, int rows, int H, int tpr,
+                                                                  const float* __restrict__ alpha_ptr, int rows, int H,
                                                                   __half* __restrict__ dx_drop, DropCfg drop) {
-  extern __shared__ float red[];   // [3][slots][H] column sums, then [2 parities][slots][wps][2 * LNB_R] row-sum partials
-  const int slots = LNB_THREADS / tpr, wps = tpr >> 5;
+  extern __shared__ float red[];   // [3][slots][H] column sums, then [2 parities][slots][WPS] float4 row-sum partials
+  constexpr int tpr = 32 * WPS, slots = LNB_THREADS / tpr;
   const int slot = threadIdx.x / tpr, tl = threadIdx.x - slot * tpr;
   const int lane = threadIdx.x & 31, wis = tl >> 5;            // warp inside the slot
   const int c = tl * 8;
   const bool active = c < H;
-  float* part = red + 3 * slots * H;
+  float4* part = reinterpret_cast<float4*>(red + 3 * slots * H);
   const bool dropping = dx_drop != nullptr && drop.seed_base != nullptr;
   const uint32_t dseed = dropping ? drop_seed(drop) : 0u;
   const float inv_h = 1.0f / H;
-  Vec8 ag, ab, ad;               // gamma is re-read where needed (L1-resident): 8 fewer live registers
+  Vec8 ag, ab, ad;
 #pragma unroll
   for (int j = 0; j < 8; ++j) ag.v[j] = ab.v[j] = ad.v[j] = 0.f;
   int par = 0;
   for (int base = (blockIdx.x * slots + slot) * LNB_R; base < rows; base += gridDim.x * slots * LNB_R, par ^= 1) {
-    Vec8 xh[LNB_R], d[LNB_R];
-    float s[2 * LNB_R], rs[LNB_R];
+    // ---- every load of the trip is issued before anything is consumed (LNB_R rows x 48..64 bytes per thread in flight)
+    uint4 xr0[LNB_R], xr1[LNB_R], dr[LNB_R], d2r[LNB_R];
+    float mean[LNB_R], rs[LNB_R];
+    bool ok[LNB_R];
+#pragma unroll
+    for (int k = 0; k < LNB_R; ++k) {
+      const int row = base + k;
+      ok[k] = row < rows && active;
+      xr0[k] = xr1[k] = dr[k] = d2r[k] = make_uint4(0, 0, 0, 0);
+      mean[k] = rs[k] = 0.f;
+      if (ok[k]) {
+        const size_t off = static_cast<size_t>(row) * H + c;
+        xr0[k] = *reinterpret_cast<const uint4*>(x + off);
+        if (sizeof(InT) == 4) xr1[k] = *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(x + off) + 16);
+        dr[k] = *reinterpret_cast<const uint4*>(dy + off);
+        if (dy2) d2r[k] = *reinterpret_cast<const uint4*>(dy2 + off);
+        mean[k] = mean_in[row];
+        rs[k] = rstd_in[row];
+      }
+    }
     Vec8 gm;
 #pragma unroll
     for (int j = 0; j < 8; ++j) gm.v[j] = 0.f;
     if (active) gm = load8(gamma + c);
+    Vec8 xh[LNB_R], d[LNB_R];
+    float s[2 * LNB_R];
 #pragma unroll
     for (int k = 0; k < LNB_R; ++k) {
-      const int row = base + k;
+      Vec8 xv;
+      if (sizeof(InT) == 4) {
+        const float4 a4 = *reinterpret_cast<const float4*>(&xr0[k]), b4 = *reinterpret_cast<const float4*>(&xr1[k]);
+        xv.v[0] = a4.x; xv.v[1] = a4.y; xv.v[2] = a4.z; xv.v[3] = a4.w;
+        xv.v[4] = b4.x; xv.v[5] = b4.y; xv.v[6] = b4.z; xv.v[7] = b4.w;
+      } else {
+        xv = unpack8(xr0[k]);
+      }
+      d[k] = unpack8(dr[k]);
+      if (dy2) {
+        const Vec8 d2 = unpack8(d2r[k]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[k].v[j] += d2.v[j];
+      }
       s[2 * k] = s[2 * k + 1] = 0.f;
-      rs[k] = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) xh[k].v[j] = d[k].v[j] = 0.f;
-      if (row < rows && active) {
-        const size_t off = static_cast<size_t>(row) * H + c;
-        const Vec8 xv = load8(x + off);
-        d[k] = load8(dy + off);
-        if (dy2) {
-          const Vec8 d2 = load8(dy2 + off);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) d[k].v[j] += d2.v[j];
-        }
-        const float mean = mean_in[row];
-        rs[k] = rstd_in[row];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          xh[k].v[j] = (xv.v[j] - mean) * rs[k];
-          const float g = d[k].v[j] * gm.v[j];
-          s[2 * k] += g;
-          s[2 * k + 1] = fmaf(g, xh[k].v[j], s[2 * k + 1]);
-          ag.v[j] = fmaf(d[k].v[j], xh[k].v[j], ag.v[j]);
-          ab.v[j] += d[k].v[j];
-        }
+      for (int j = 0; j < 8; ++j) {
+        xh[k].v[j] = ok[k] ? (xv.v[j] - mean[k]) * rs[k] : 0.f;
+        const float g = d[k].v[j] * gm.v[j];
+        s[2 * k] += g;
+        s[2 * k + 1] = fmaf(g, xh[k].v[j], s[2 * k + 1]);
+        ag.v[j] = fmaf(d[k].v[j], xh[k].v[j], ag.v[j]);
+        ab.v[j] += d[k].v[j];
       }
     }
 #pragma unroll
     for (int k = 0; k < 2 * LNB_R; ++k) s[k] = warp_sum(s[k]);
-    if (wps > 1) {
-      float* mine = part + ((par * slots + slot) * wps) * (2 * LNB_R);
-      if (lane == 0) {
+    if (WPS > 1) {
+      float4* mine = part + (par * slots + slot) * WPS;
+      if (lane == 0) mine[wis] = make_float4(s[0], s[1], s[2], s[3]);
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "n"(tpr) : "memory");
+      float4 t = mine[0];
 #pragma unroll
-        for (int k = 0; k < 2 * LNB_R; ++k) mine[wis * 2 * LNB_R + k] = s[k];
+      for (int w = 1; w < WPS; ++w) {
+        const float4 u = mine[w];
+        t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
       }
-      asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(tpr) : "memory");
-#pragma unroll
-      for (int k = 0; k < 2 * LNB_R; ++k) {
-        float t = 0.f;
-        for (int w = 0; w < wps; ++w) t += mine[w * 2 * LNB_R + k];
-        s[k] = t;
-      }
+      s[0] = t.x; s[1] = t.y; s[2] = t.z; s[3] = t.w;
     }
-    if (active) gm = load8(gamma + c);
 #pragma unroll
     for (int k = 0; k < LNB_R; ++k) {
-      const int row = base + k;
-      if (row < rows && active) {
+      if (ok[k]) {
+        const int row = base + k;
         const float m1 = s[2 * k] * inv_h, m2 = s[2 * k + 1] * inv_h;
         Vec8 o;
 #pragma unroll
@@ -330,6 +359,7 @@ __global__ void __launch_bounds__(LNB_THREADS, 2) ln_bwd2_kernel(const __half* _
   const float alpha = alpha_ptr ? *alpha_ptr : 1.0f;
   for (int col = threadIdx.x; col < H; col += blockDim.x) {
     float a = 0.f, b = 0.f, dd = 0.f;
+#pragma unroll
     for (int w = 0; w < slots; ++w) {
       a += red[(0 * slots + w) * H + col];
       b += red[(1 * slots + w) * H + col];
