@@ -6,8 +6,9 @@ fall is not part of the algorithm.  The CUDA path instead hashes (step seed, sit
 regenerates the forward's mask.  This file repeats that hash on the host so the tests can hand the SAME masks to
 `bert_oracle` (its `masks=` argument) and compare values and gradients under dropout.
 
-Conventions: one 32-bit hash per PAIR of consecutive elements (low 16 bits -> even element, high 16 -> odd element); an
-element is kept iff its 16-bit lane >= round(p * 65536); kept elements are multiplied by 1/(1-p).
+Conventions: one 32-bit hash per PAIR of consecutive elements (bits [0,15) -> even element, bits [16,31) -> odd element);
+an element is kept iff its 15-bit lane >= round(p * 32768); kept elements are multiplied by 1/(1-p).  The pair index
+enters the hash by addition: h = fin((idx + seed) * 0x9E3779B1), fin = xorshift 15, multiply 0x85EBCA6B, xorshift 13.
   hidden / embedding / classifier-input sites, tensor [rows, H]:  element index = row * H + col
   attention-probability sites, tensor [B, heads, Sq, Sk]:         pair index = ((b*heads + h)*Sq + q) * ceil(Sk/2) + key//2
 Site ids: layer*8 + {0: probabilities, 1: attention output dense, 2: FFN output dense, 3/4: cross-attention}, 0xE000
@@ -22,7 +23,7 @@ M32 = np.uint64(0xFFFFFFFF)
 
 
 def _hash(idx: np.ndarray, seed: np.ndarray) -> np.ndarray:
-    h = ((idx.astype(np.uint64) ^ seed.astype(np.uint64)) * np.uint64(0x9E3779B1)) & M32
+    h = (((idx.astype(np.uint64) + seed.astype(np.uint64)) & M32) * np.uint64(0x9E3779B1)) & M32
     h ^= h >> np.uint64(15)
     h = (h * np.uint64(0x85EBCA6B)) & M32
     h ^= h >> np.uint64(13)
@@ -36,10 +37,10 @@ def site_seed(base_seed: int, site: int) -> np.ndarray:
 
 def _lanes(pairs: np.ndarray, base_seed: int, site: int, p: float):
     h = _hash(pairs, site_seed(base_seed, site))
-    thr = np.uint64(int(p * 65536.0 + 0.5))
+    thr = np.uint64(int(np.float32(p) * np.float32(32768.0) + np.float32(0.5)))
     scale = np.float32(1.0) / (np.float32(1.0) - np.float32(p))
-    lo = np.where((h & np.uint64(0xFFFF)) >= thr, scale, np.float32(0)).astype(np.float32)
-    hi = np.where((h >> np.uint64(16)) >= thr, scale, np.float32(0)).astype(np.float32)
+    lo = np.where((h & np.uint64(0x7FFF)) >= thr, scale, np.float32(0)).astype(np.float32)
+    hi = np.where(((h >> np.uint64(16)) & np.uint64(0x7FFF)) >= thr, scale, np.float32(0)).astype(np.float32)
     return lo, hi
 
 

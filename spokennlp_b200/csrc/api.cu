@@ -150,7 +150,7 @@ std::atomic<int> g_gemm_dbg{0};
 const DropCfg kNoDrop{nullptr, 0, 0, 1.0f};
 DropCfg make_drop(const uint32_t* seed, unsigned site, float p) {
   if (!seed || p <= 0.f) return kNoDrop;
-  return DropCfg{seed, site, static_cast<uint32_t>(p * 65536.0f + 0.5f), 1.0f / (1.0f - p)};
+  return DropCfg{seed, site, static_cast<uint32_t>(p * 32768.0f + 0.5f), 1.0f / (1.0f - p)};
 }
 
 template <int BN, int A_MN, int B_MN, int EPI, typename OutT>

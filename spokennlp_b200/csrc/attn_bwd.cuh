@@ -251,8 +251,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const int q = min(i * ATT_BQ + half * 64 + qi, a.Sq - 1);
             const uint32_t skp = static_cast<uint32_t>((a.Sk + 1) >> 1), kc = static_cast<uint32_t>(min(key, a.Sk - 1));
             const uint32_t e0 = (static_cast<uint32_t>(stat_base + q) * skp + (kc >> 1)) * 2u + (kc & 1u);   // (pair, lane) as the forward drew it
-            const float m0 = drop_one(e0, dseed, a.drop.thr16, a.drop.scale);
-            const float m1 = drop_one(e0 + 2u * skp, dseed, a.drop.thr16, a.drop.scale);
+            const float m0 = drop_one(e0, dseed, a.drop.thr15, a.drop.scale);
+            const float m1 = drop_one(e0 + 2u * skp, dseed, a.drop.thr15, a.drop.scale);
             pd0 *= m0; pd1 *= m1;
             g0 *= m0; g1 *= m1;
           }

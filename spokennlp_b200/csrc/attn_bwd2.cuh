@@ -290,7 +290,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           float pd0 = p0, pd1 = p1;
           if (DROP) {       // P_drop = P o mask/(1-p) feeds dV; dP flows back through the same mask; delta is unchanged
             float m0, m1;
-            drop_pair(dbase + e, dseed, a.drop.thr16, a.drop.scale, m0, m1);
+            drop_pair(dbase + e, dseed, a.drop.thr15, a.drop.scale, m0, m1);
             pd0 *= m0; pd1 *= m1;
             g0 *= m0; g1 *= m1;
           }

@@ -199,6 +199,8 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t dseed = DROP ? drop_seed(a.drop) : 0u;
     const uint32_t skp = static_cast<uint32_t>((a.Sk + 1) >> 1);
     const float sc = a.scale_log2;
+    const uint32_t dtt = a.drop.thr15 * 0x00010001u;
+    const uint32_t cs_bits = __float_as_uint(a.inv_sqrt_d * a.drop.scale);   // dP coefficient of a kept element
     uint8_t* dqs = smem + S::OFF_DQS + (warp - 2) * 4096;     // this warp's [32 q][32 d] fp32 staging patch
     const uint32_t dqs_row = smem_u32(dqs) + lane * 128;
     uint32_t ir = 0;                              // query blocks processed so far (barrier phases, dQ buffer)
@@ -287,7 +289,8 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           for (int c = 0; c < 64; ++c) sv[c] = (c < lim) ? sv[c] : 0xff800000u;
         }
         uint32_t pk[32], dk[32];                  // this thread's 64 P / dS values, packed fp16
-        const uint32_t dbase = DROP ? (static_cast<uint32_t>(stat_base + min(q, a.Sq - 1)) * skp + (static_cast<uint32_t>(kg0) >> 1)) : 0u;
+        // dropout: (pair + seed) * C1 of this row's first pair; consecutive pairs add C1 (ptx.cuh: drop_z)
+        const uint32_t dpre = DROP ? drop_premix(static_cast<uint32_t>(stat_base + min(q, a.Sq - 1)) * skp + (static_cast<uint32_t>(kg0) >> 1), dseed) : 0u;
         if (a.dbg & 0x40000) {
 #pragma unroll
           for (int e = 0; e < 32; ++e) pk[e] = dk[e] = sv[2 * e] ^ dp[2 * e + 1];
@@ -296,18 +299,19 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           for (int e = 0; e < 32; ++e) {
             const float p0 = fast_exp2(fmaf(__uint_as_float(sv[2 * e]), sc, neg_lse));
             const float p1 = fast_exp2(fmaf(__uint_as_float(sv[2 * e + 1]), sc, neg_lse));
-            float g0 = __uint_as_float(dp[2 * e]), g1 = __uint_as_float(dp[2 * e + 1]);
-            float pd0 = p0, pd1 = p1;
-            if (DROP) {       // P_drop = P o mask/(1-p) feeds dV; dP flows back through the same mask; delta is unchanged
-              float m0, m1;
-              drop_pair(dbase + e, dseed, a.drop.thr16, a.drop.scale, m0, m1);
-              pd0 *= m0; pd1 *= m1;
-              g0 *= m0; g1 *= m1;
-            }
-            const float d0 = p0 * fmaf(g0, a.inv_sqrt_d, ndc);          // P o (dP - delta) / sqrt(d)
-            const float d1 = p1 * fmaf(g1, a.inv_sqrt_d, ndc);
-            const __half2 hp = __floats2half2_rn(pd0, pd1), hd = __floats2half2_rn(d0, d1);
+            const float g0 = __uint_as_float(dp[2 * e]), g1 = __uint_as_float(dp[2 * e + 1]);
+            float c0 = a.inv_sqrt_d, c1 = a.inv_sqrt_d;
+            const __half2 hp = __floats2half2_rn(p0, p1);
             pk[e] = *reinterpret_cast<const uint32_t*>(&hp);
+            if (DROP) {       // P o mask feeds dV (its 1/(1-p) is applied to dV at the end); dP flows back through mask/(1-p)
+              const uint32_t z = drop_z(dpre + static_cast<uint32_t>(e) * kDropC1, dtt);
+              pk[e] &= drop_keep_h2(z);
+              c0 = __uint_as_float(drop_keep_lo(z) & cs_bits);
+              c1 = __uint_as_float(drop_keep_hi(z) & cs_bits);
+            }
+            const float d0 = p0 * fmaf(g0, c0, ndc);                    // P o (dP_eff - delta) / sqrt(d)
+            const float d1 = p1 * fmaf(g1, c1, ndc);
+            const __half2 hd = __floats2half2_rn(d0, d1);
             dk[e] = *reinterpret_cast<const uint32_t*>(&hd);
           }
         }
@@ -347,9 +351,10 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tmem_ld_x32(tmem + lane_addr + 256 + which * 64 + g * 32, o);
         tmem_wait_ld();
         uint32_t w[16];
+        const float osc = (DROP && which == 0) ? a.drop.scale : 1.0f;      // dV = (P o mask / (1-p))^T dO
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-          const __half2 hv = __floats2half2_rn(__uint_as_float(o[2 * k]), __uint_as_float(o[2 * k + 1]));
+          const __half2 hv = __floats2half2_rn(__uint_as_float(o[2 * k]) * osc, __uint_as_float(o[2 * k + 1]) * osc);
           w[k] = *reinterpret_cast<const uint32_t*>(&hv);
         }
         if (full_block) {

@@ -253,7 +253,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             rs1 += p1;
             if (DROP) {                               // the row sum (softmax denominator) is taken before dropout
               float m0, m1;
-              drop_pair(dbase + ((j * ATT_BK + c * 32) >> 1) + i, dseed, a.drop.thr16, a.drop.scale, m0, m1);
+              drop_pair(dbase + ((j * ATT_BK + c * 32) >> 1) + i, dseed, a.drop.thr15, a.drop.scale, m0, m1);
               p0 *= m0;
               p1 *= m1;
             }

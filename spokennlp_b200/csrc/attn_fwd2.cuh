@@ -240,7 +240,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             rs1 += p1;
             if (DROP) {                             // the row sum (softmax denominator) is taken before dropout
               float k0, k1;
-              drop_pair(dbase + ((j * ATT_BK + i) >> 1), dseed, a.drop.thr16, a.drop.scale, k0, k1);
+              drop_pair(dbase + ((j * ATT_BK + i) >> 1), dseed, a.drop.thr15, a.drop.scale, k0, k1);
               p0 *= k0;
               p1 *= k1;
             }

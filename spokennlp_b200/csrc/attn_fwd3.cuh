@@ -211,7 +211,9 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (x == 1 && !it.tileB) continue;
       const int b = it.b, h = it.h, kv_len = it.kv_len, n_blocks = it.n_blocks;
       const int qrow = it.q0 + x * ATT_BQ + r;
-      const uint32_t dbase = DROP ? static_cast<uint32_t>(((static_cast<size_t>(b) * a.heads + h) * a.Sq + min(qrow, a.Sq - 1)) * ((a.Sk + 1) >> 1)) : 0u;
+      // dropout: pair index of (row, key) = rowbase + key / 2; (pair + seed) * C1 is walked by adding multiples of C1
+      const uint32_t dpre = DROP ? drop_premix(static_cast<uint32_t>(((static_cast<size_t>(b) * a.heads + h) * a.Sq + min(qrow, a.Sq - 1)) * ((a.Sk + 1) >> 1)), dseed) : 0u;
+      const uint32_t dtt = a.drop.thr15 * 0x00010001u;
       float m = NEG_INF, l = 0.f;
       if (lane == 0) tma_wait_group_read<0>();    // the previous item's context store has read this warp's staging rows
       __syncwarp();
@@ -284,6 +286,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         // ---- p = exp2(s * scale - m_use), row sum, fp16 P into the swizzled smem tile (16 chunks of 8 keys)
         const float neg_m = -m_use;
+        const uint32_t dpre_j = dpre + static_cast<uint32_t>(j * (ATT_BK / 2)) * kDropC1;
         float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
         for (int ch = 0; ch < 16; ++ch) {
@@ -293,16 +296,12 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             const int i = ch * 8 + 2 * e;
             float p0 = fast_exp2(fmaf(__uint_as_float(v[i]), sc, neg_m));
             float p1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), sc, neg_m));
-            rs0 += p0;
+            rs0 += p0;                              // the row sum (softmax denominator) is taken before dropout
             rs1 += p1;
-            if (DROP) {                             // the row sum (softmax denominator) is taken before dropout
-              float k0, k1;
-              drop_pair(dbase + ((j * ATT_BK + i) >> 1), dseed, a.drop.thr16, a.drop.scale, k0, k1);
-              p0 *= k0;
-              p1 *= k1;
-            }
             const __half2 hp = __floats2half2_rn(p0, p1);
             pk[e] = *reinterpret_cast<const uint32_t*>(&hp);
+            if (DROP)                               // zero the dropped lanes of the packed pair; 1/(1-p) is applied to O at the end
+              pk[e] &= drop_keep_h2(drop_z(dpre_j + static_cast<uint32_t>(i >> 1) * kDropC1, dtt));
           }
           sts128(p_row + (ch >> 3) * 16384 + (((ch & 7) ^ (r & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
         }
@@ -315,7 +314,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       // ---------------------------------------------------------------- finalise: O / l -> ctx, LSE
       mbar_wait(&o_full[x], (t - 1) & 1);
       tc_fence_after();
-      const float inv_l = l > 0.f ? 1.0f / l : 0.f;
+      const float inv_l = (l > 0.f ? 1.0f / l : 0.f) * (DROP ? a.drop.scale : 1.0f);
       uint32_t o[2][32];
       tmem_ld_x32(tmem + lane_addr + 256 + x * 64, o[0]);
       tmem_ld_x32(tmem + lane_addr + 256 + x * 64 + 32, o[1]);

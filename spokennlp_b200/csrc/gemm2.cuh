@@ -325,7 +325,7 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
 #pragma unroll
           for (int i = 0; i < CW / 2; ++i) {
             float m0, m1;
-            drop_pair((e0 >> 1) + i, seed, g.drop.thr16, g.drop.scale, m0, m1);
+            drop_pair((e0 >> 1) + i, seed, g.drop.thr15, g.drop.scale, m0, m1);
             f[2 * i] *= m0;
             f[2 * i + 1] *= m1;
           }

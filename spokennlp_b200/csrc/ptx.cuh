@@ -220,34 +220,64 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 
 // ----------------------------------------------------------------------------- dropout (counter-based, stateless)
 // The keep/drop decision of element `idx` of a tensor is a pure function of (seed, idx): the backward regenerates the
-// forward's mask instead of storing it.  One 32-bit hash decides TWO consecutive elements (16 bits each: keep iff the
-// 16-bit lane >= thr16 = round(p * 65536), so p = 0.1 is met to 1e-5).  `seed` = per-step base seed (device memory, so a
-// replayed CUDA graph still draws fresh masks) mixed with a per-site constant.
+// forward's mask instead of storing it.  One 32-bit hash decides TWO consecutive elements (15 bits each: bits [0,15) for
+// the even element, bits [16,31) for the odd one; keep iff the lane >= thr15 = round(p * 32768), so p = 0.1 is met to
+// 6e-6).  `seed` = per-step base seed (device memory, so a replayed CUDA graph still draws fresh masks) mixed with a
+// per-site constant.  The index enters by ADDITION, so a kernel that walks consecutive pairs of one row pays one integer
+// add per pair for (idx + seed) * C1 (see drop_premix / drop_z) instead of an xor and a multiply.
 struct DropCfg {
   const uint32_t* seed_base;   // device pointer, null = dropout off
   uint32_t site;               // which dropout site of the model (layer * 8 + kind)
-  uint32_t thr16;              // round(p * 65536)
+  uint32_t thr15;              // round(p * 32768)
   float scale;                 // 1 / (1 - p)
 };
-__device__ __forceinline__ uint32_t drop_hash(uint32_t pair_idx, uint32_t seed) {
-  uint32_t h = (pair_idx ^ seed) * 0x9E3779B1u;
+constexpr uint32_t kDropC1 = 0x9E3779B1u, kDropC2 = 0x85EBCA6Bu;
+__device__ __forceinline__ uint32_t drop_premix(uint32_t pair_idx, uint32_t seed) { return (pair_idx + seed) * kDropC1; }
+__device__ __forceinline__ uint32_t drop_finish(uint32_t h) {      // h = drop_premix(...)
   h ^= h >> 15;
-  h *= 0x85EBCA6Bu;
+  h *= kDropC2;
   h ^= h >> 13;
   return h;
 }
+__device__ __forceinline__ uint32_t drop_hash(uint32_t pair_idx, uint32_t seed) { return drop_finish(drop_premix(pair_idx, seed)); }
 __device__ __forceinline__ uint32_t drop_seed(const DropCfg& d) {
   return drop_hash(d.site * 0x632BE5ABu + 0x7F4A7C15u, __ldg(d.seed_base));
 }
 // multipliers (0 or scale) for elements 2*pair_idx and 2*pair_idx+1
-__device__ __forceinline__ void drop_pair(uint32_t pair_idx, uint32_t seed, uint32_t thr16, float scale, float& m0, float& m1) {
+__device__ __forceinline__ void drop_pair(uint32_t pair_idx, uint32_t seed, uint32_t thr15, float scale, float& m0, float& m1) {
   const uint32_t h = drop_hash(pair_idx, seed);
-  m0 = (h & 0xFFFFu) >= thr16 ? scale : 0.f;
-  m1 = (h >> 16) >= thr16 ? scale : 0.f;
+  m0 = (h & 0x7FFFu) >= thr15 ? scale : 0.f;
+  m1 = ((h >> 16) & 0x7FFFu) >= thr15 ? scale : 0.f;
 }
-__device__ __forceinline__ float drop_one(uint32_t idx, uint32_t seed, uint32_t thr16, float scale) {
+__device__ __forceinline__ float drop_one(uint32_t idx, uint32_t seed, uint32_t thr15, float scale) {
   const uint32_t h = drop_hash(idx >> 1, seed);
-  return ((idx & 1) ? (h >> 16) : (h & 0xFFFFu)) >= thr16 ? scale : 0.f;
+  return (((idx & 1) ? (h >> 16) : h) & 0x7FFFu) >= thr15 ? scale : 0.f;
+}
+// Both decisions of a pair at once (SWAR), for the attention kernels where the mask costs more issue slots than the exp:
+// z = ((lane | 0x8000) - thr15) per 16-bit lane, so bit 15 / bit 31 of z say "keep" (no borrow crosses the lanes because
+// every lane is >= 0x8000 before the subtraction).  tt = thr15 * 0x00010001.
+__device__ __forceinline__ uint32_t drop_z(uint32_t premixed, uint32_t tt) {
+  uint32_t h = premixed;
+  h ^= h >> 15;
+  h *= kDropC2;
+  return ((h ^ (h >> 13)) | 0x80008000u) - tt;
+}
+// 0xFFFF in every 16-bit lane that is kept (for packed half2 data): byte-permute with sign replication of bytes 1 and 3
+__device__ __forceinline__ uint32_t drop_keep_h2(uint32_t z) {
+  uint32_t m;
+  asm("prmt.b32 %0, %1, %1, 0xBB99;" : "=r"(m) : "r"(z));
+  return m;
+}
+// 0xFFFFFFFF if the even (lo) / odd (hi) element of the pair is kept
+__device__ __forceinline__ uint32_t drop_keep_lo(uint32_t z) {
+  uint32_t m;
+  asm("prmt.b32 %0, %1, %1, 0x9999;" : "=r"(m) : "r"(z));
+  return m;
+}
+__device__ __forceinline__ uint32_t drop_keep_hi(uint32_t z) {
+  uint32_t m;
+  asm("prmt.b32 %0, %1, %1, 0xBBBB;" : "=r"(m) : "r"(z));
+  return m;
 }
 
 // ----------------------------------------------------------------------------- small math helpers

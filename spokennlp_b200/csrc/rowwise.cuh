@@ -50,7 +50,7 @@ __device__ __forceinline__ void drop8(Vec8& v, uint32_t e0, uint32_t seed, const
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     float m0, m1;
-    drop_pair((e0 >> 1) + i, seed, d.thr16, d.scale, m0, m1);
+    drop_pair((e0 >> 1) + i, seed, d.thr15, d.scale, m0, m1);
     v.v[2 * i] *= m0;
     v.v[2 * i + 1] *= m1;
   }
