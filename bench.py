@@ -221,6 +221,10 @@ def kernel_rooflines(torch, ops, peaks):
     y = torch.empty(M, H, device=dev, dtype=f16)
     t = time_kernel(torch, lambda: ops.layernorm_fwd(pre, g, b, 1e-12, y=y))
     out["layernorm_fwd"] = {"bound": "hbm", "achieved": M * H * (4 + 2) / t / 1e9, "unit": "GB/s", "ms": t * 1e3}
+    mean, rstd = torch.zeros(M, device=dev), torch.ones(M, device=dev)
+    dxl, dgl, dbl = torch.empty(M, H, device=dev, dtype=f16), torch.zeros(H, device=dev), torch.zeros(H, device=dev)
+    t = time_kernel(torch, lambda: ops.layernorm_bwd(y, pre, mean, rstd, g, dxl, dgl, dbl))
+    out["layernorm_bwd"] = {"bound": "hbm", "achieved": M * H * (2 + 4 + 2) / t / 1e9, "unit": "GB/s", "ms": t * 1e3}
     W = torch.randn(2, H, device=dev) * 0.02
     t = time_kernel(torch, lambda: ops.cls_head_fwd(y, W, torch.zeros(2, device=dev)))
     out["cls_head_fwd"] = {"bound": "hbm", "achieved": (M * H * 2 + M * 8) / t / 1e9, "unit": "GB/s", "ms": t * 1e3}
@@ -314,9 +318,12 @@ def run_b200_arm(args):
             "encoder_flop_util": {"flop_per_seq": FLOP_PER_SEQ, "achieved_tflops_per_gpu": value / world * FLOP_PER_SEQ / 1e12,
                                   "peak_tflops_sustained": peaks["bf16_tflops_sustained"], "peak_source": peak_src,
                                   "frac_of_sustained": value / world * FLOP_PER_SEQ / 1e12 / peaks["bf16_tflops_sustained"]},
-            "roofline": {"kernel": "gemm_f16_kernel<256,K,K,BIAS_GELU> (FFN-up 16384x3072x768)", "bound": "tensor",
-                         "achieved": dom["achieved"], "peak": dom["peak"], "unit": "TFLOP/s", "frac": dom["frac"], "traffic": None,
-                         "peak_source": peak_src + " bf16 burst (kernel timed alone)"},
+            # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed `ncu --set full` capture
+            # (profiles/r01d_kernel_metrics.md: 29.9 MB read + 141.5 MB written per launch; algorithmic: 25.2 MB x + 4.7 MB W
+            # read, 2 x 100.7 MB written = gelu(z) and gelu'(z))
+            "roofline": {"kernel": "gemm2_f16_kernel<256,K-major,K-major,BIAS_GELU> (FFN-up 16384x3072x768, 2-CTA tcgen05)",
+                         "bound": "tensor", "achieved": dom["achieved"], "peak": dom["peak"], "unit": "TFLOP/s", "frac": dom["frac"],
+                         "traffic": 171.4e6, "peak_source": peak_src + " bf16 burst (kernel timed alone)"},
             "kernels": kr,
             "e2e": {"value": e2e_value, "unit": "seq/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                     "ms_per_step": e2e_secs / args.steps * 1e3},
