@@ -292,14 +292,28 @@ def run_b200_arm(args):
     # end to end: pinned host batch -> H2D every step, loss read back every step
     h2d = sum(t.numel() * t.element_size() for t in host)
 
+    e2e_losses = []
+
     def e2e_step():
-        batch = [t.cuda(non_blocking=True) for t in host]
-        trainer.step(*batch)
-        return trainer.loss_value()          # D2H of the 2-float loss statistics (synchronises)
-    for _ in range(2):
+        # pinned host batch -> HBM, the step, and the D2H read of this step's loss statistics are all inside the timed
+        # region; the host consumes each loss one step late (DataParallelTrainer.step_from_host), so it never idles the GPU
+        e2e_losses.append(trainer.step_from_host(*host))
+    sampler2 = ClockSampler(local)
+    if rank == 0:
+        sampler2.start()                       # nvidia-smi needs a few hundred ms before its first sample
+    for _ in range(3):
         e2e_step()
-    e2e_secs = timed(e2e_step, args.steps)
+    trainer.drain()
+    del e2e_losses[:]
+
+    def e2e_run():
+        for _ in range(args.steps):
+            e2e_step()
+        e2e_losses.append(trainer.drain())     # the last step's loss is read inside the timed region as well
+    e2e_secs = timed(e2e_run, 1)
+    e2e_clocks = sampler2.stop() if rank == 0 else None
     e2e_value = world * BATCH * args.steps / e2e_secs
+    assert sum(l is not None for l in e2e_losses) == args.steps, "every timed step's loss must have been read back"
     loss = trainer.loss_value()
 
     if rank == 0:
@@ -326,7 +340,7 @@ def run_b200_arm(args):
                          "traffic": 171.4e6, "peak_source": peak_src + " bf16 burst (kernel timed alone)"},
             "kernels": kr,
             "e2e": {"value": e2e_value, "unit": "seq/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
-                    "ms_per_step": e2e_secs / args.steps * 1e3},
+                    "ms_per_step": e2e_secs / args.steps * 1e3, "sm_mhz": (e2e_clocks or {}).get("sm_mhz")},
             "gpu_launches": launches, "clocks": clocks, "final_loss": loss,
         }
         if cpu is not None:

@@ -171,6 +171,10 @@ int b200_set_hyper(float* hyper, float lr, float beta1, float beta2, float eps, 
                    void* stream);
 int b200_adamw_step_dev(float* p, const float* g, float* m, float* v, void* p16, size_t n, const float* hyper, const float* coef,
                         void* stream);
+/* Same, and the gradient buffer is zeroed on the way out: the next step's accumulating gradient reductions need no
+ * separate fill pass (the caller must not read `g` afterwards). */
+int b200_adamw_step_dev_zero(float* p, float* g, float* m, float* v, void* p16, size_t n, const float* hyper, const float* coef,
+                             void* stream);
 
 /*
  * Dropout-enabled variants (reference: nn.Dropout at bert_model.py:209 (embeddings), :338 (attention probabilities), :373 and

@@ -56,6 +56,7 @@ _PROTOS = {
     "b200_cls_head_bwd_drop": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p, C.c_uint, _f, _p],
     "b200_set_hyper": [_p, _f, _f, _f, _f, _f, _f, _f, _p],
     "b200_adamw_step_dev": [_p, _p, _p, _p, _p, _sz, _p, _p, _p],
+    "b200_adamw_step_dev_zero": [_p, _p, _p, _p, _p, _sz, _p, _p, _p],
 }
 _RESTYPE = {"b200_set_gemm_impl": None, "b200_set_gemm_debug": None, "b200_last_error": C.c_char_p, "b200_launch_count": _ll, "b200_version": _i, "b200_attn_bwd_workspace": _sz, "b200_ponet_workspace": _sz, "b200_ponet_bwd_workspace": _sz}
 

@@ -308,6 +308,9 @@ def set_hyper(hyper: Tensor, *, lr: float, beta1: float = 0.9, beta2: float = 0.
     L.check(rc, "b200_set_hyper")
 
 
-def adamw_step_dev(p: Tensor, g: Tensor, m: Tensor, v: Tensor, p16: Optional[Tensor], hyper: Tensor, coef: Optional[Tensor]) -> None:
-    rc = L.load().b200_adamw_step_dev(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(p16), p.numel(), _ptr(hyper), _ptr(coef), _stream())
+def adamw_step_dev(p: Tensor, g: Tensor, m: Tensor, v: Tensor, p16: Optional[Tensor], hyper: Tensor, coef: Optional[Tensor],
+                   zero_grad: bool = False) -> None:
+    """`zero_grad=True`: the kernel clears `g` after reading it (no separate fill pass before the next backward)."""
+    fn = L.load().b200_adamw_step_dev_zero if zero_grad else L.load().b200_adamw_step_dev
+    rc = fn(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(p16), p.numel(), _ptr(hyper), _ptr(coef), _stream())
     L.check(rc, "b200_adamw_step_dev")

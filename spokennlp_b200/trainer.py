@@ -95,6 +95,10 @@ class DataParallelTrainer:
         self._graph = None
         self._static = None
         self.kernels_per_step = 0
+        # AdamW clears the gradient buffer while it streams through it (0.44 GB less traffic per step than a separate fill);
+        # callers that want to inspect gradients AFTER optimizer_step set this to False
+        self.fused_zero_grad = True
+        self._grads_clean = True            # ensure_grad() zero-filled the buffer
         # dropout (HF config probabilities; TopicSegModel's classifier dropout = hidden_dropout_prob, bert_for_ts.py:66)
         self.p_hidden = float(getattr(cfg, "hidden_dropout_prob", 0.0)) if dropout else 0.0
         self.p_attn = float(getattr(cfg, "attention_probs_dropout_prob", 0.0)) if dropout else 0.0
@@ -117,7 +121,9 @@ class DataParallelTrainer:
         """Enqueue forward + backward for one local batch; returns the device scalar loss (no sync)."""
         eng, flat = self.engine, self.flat
         B, S = input_ids.shape
-        flat.grad32.zero_()
+        if not self._grads_clean:           # the fused optimizer step leaves the gradient buffer zeroed
+            flat.grad32.zero_()
+        self._grads_clean = False
         key_bias = kv_len = None
         if attention_mask is not None:
             key_bias, kv_len = ops.mask_to_bias(attention_mask)
@@ -157,7 +163,8 @@ class DataParallelTrainer:
         self.sumsq.zero_()
         ops.grad_sumsq(flat.grad32, self.sumsq)
         ops.clip_coef(self.sumsq, self.coef, self.max_grad_norm, 1.0 / self.world)
-        ops.adamw_step_dev(flat.flat32, flat.grad32, self.m, self.v, flat.flat16, self.hyper, self.coef)
+        ops.adamw_step_dev(flat.flat32, flat.grad32, self.m, self.v, flat.flat16, self.hyper, self.coef, zero_grad=self.fused_zero_grad)
+        self._grads_clean = self.fused_zero_grad
         flat.version = flat.cur_version()       # the fused step refreshed the fp16 mirror itself
 
     def _push_hyper(self) -> None:
@@ -231,6 +238,46 @@ class DataParallelTrainer:
     def loss_value(self) -> float:
         s = self.stats.tolist()     # device -> host read
         return s[0] / max(s[1], 1e-30)
+
+    # ---- end-to-end step: pinned host batch in, loss out ------------------------------------------------------------------
+    def step_from_host(self, input_ids, attention_mask, token_type_ids, labels) -> Optional[float]:
+        """One training step on a batch that lives in PINNED host memory: host->device copies of the four tensors, the step,
+        and a device->host read of its loss statistics, all enqueued on the current stream.  The loss of EVERY step is read
+        back, one step late: the call returns the loss of the previous step (None on the first call) after waiting only for
+        that step's copy event, so the host never idles the GPU between steps.  `drain()` returns the last step's loss."""
+        if self._static is not None and self._graph is not None:
+            for dst, src in zip(self._static, (input_ids, attention_mask, token_type_ids, labels)):
+                if dst is not None:
+                    dst.copy_(src, non_blocking=True)           # straight into the captured graph's input buffers
+            batch = self._static
+        else:
+            batch = [t.cuda(non_blocking=True) if t is not None else None for t in (input_ids, attention_mask, token_type_ids, labels)]
+        self.step(*batch)
+        if not hasattr(self, "_host_stats"):
+            self._host_stats = [torch.empty(2, dtype=torch.float32).pin_memory() for _ in range(2)]
+            self._host_events = [torch.cuda.Event(), torch.cuda.Event()]
+            self._host_pending = [False, False]
+            self._host_k = 0
+        k = self._host_k & 1
+        self._host_stats[k].copy_(self.stats, non_blocking=True)
+        self._host_events[k].record()
+        self._host_pending[k] = True
+        self._host_k += 1
+        return self._read_host_loss(k ^ 1)
+
+    def _read_host_loss(self, k: int) -> Optional[float]:
+        if not getattr(self, "_host_pending", [False, False])[k]:
+            return None
+        self._host_events[k].synchronize()
+        self._host_pending[k] = False
+        s = self._host_stats[k]
+        return float(s[0]) / max(float(s[1]), 1e-30)
+
+    def drain(self) -> Optional[float]:
+        """Loss of the most recent `step_from_host` call (waits for it)."""
+        if not hasattr(self, "_host_k") or self._host_k == 0:
+            return None
+        return self._read_host_loss((self._host_k - 1) & 1)
 
 
 class _Aliased:

@@ -216,3 +216,43 @@ def test_cuda_graph_replay_matches_eager_steps():
     assert losses[0][0] > losses[0][-1]                                   # it learns
     assert max(abs(a - b) for a, b in zip(*losses)) < 2e-4, losses
     assert rel_err(finals[1].cpu(), finals[0].cpu()) < 1e-4
+
+
+@pytest.mark.gpu
+def test_step_from_host_reads_every_loss_one_step_late():
+    """The end-to-end step (pinned host batch -> HBM -> step -> loss read-back) returns the SAME loss sequence as the
+    resident-batch step, each value one call late and the last one through drain() — eager and through the captured graph."""
+    BertConfig, BertModel = _setup()
+    from spokennlp_b200.trainer import DataParallelTrainer, TopicSegModel
+    g = _load("tiny_bert.pt")
+    cfg = BertConfig(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, **g["config"])
+    sd = {k: v for k, v in g["state_dict"].items() if not k.startswith("pooler")}
+    host = [g[k].clone().pin_memory() for k in ("input_ids", "attention_mask", "token_type_ids", "labels")]
+    dev = [t.cuda() for t in host]
+    seqs = []
+    for mode in ("resident", "host", "host+graph"):
+        model = TopicSegModel(cfg)
+        model.bert.load_state_dict(sd)
+        with torch.no_grad():
+            model.loss_calculator.classifier.weight.copy_(g["cls_w"])
+            model.loss_calculator.classifier.bias.copy_(g["cls_b"])
+        tr = DataParallelTrainer(model, lr=1e-3, total_steps=20)
+        if mode == "host+graph":
+            before = tr.flat.flat32.clone()
+            assert tr.capture(*dev, warmup=2)
+            tr.flat.flat32.copy_(before)
+            tr.flat.sync_half(force=True)
+            tr.m.zero_(); tr.v.zero_(); tr.step_idx = 0
+        ls = []
+        if mode == "resident":
+            for _ in range(4):
+                tr.step(*dev)
+                ls.append(tr.loss_value())
+        else:
+            out = [tr.step_from_host(*host) for _ in range(4)]
+            assert out[0] is None and all(o is not None for o in out[1:])
+            ls = out[1:] + [tr.drain()]
+            assert tr.drain() is None                                     # nothing pending any more
+        seqs.append(ls)
+    for other in seqs[1:]:
+        assert max(abs(a - b) for a, b in zip(seqs[0], other)) < 2e-4, seqs
