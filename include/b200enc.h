@@ -61,6 +61,10 @@ long long b200_launch_count(void);
 void b200_set_gemm_impl(int impl);
 /* measurement knobs for the 2-CTA GEMM (results become WRONG when non-zero): 1 skip A loads, 2 skip B loads, 4 skip MMA, 8 skip stores */
 void b200_set_gemm_debug(int bits);
+/* Persistent kernels (GEMM, attention: one CTA or CTA pair per SM) size their grids to min(device SMs, sms); 0 = all SMs.
+ * A data-parallel caller reserves the SMs its concurrently running NCCL kernels occupy, so that no compute CTA has to
+ * wait for a communication kernel to leave before it can start. */
+void b200_set_sm_limit(int sms);
 int b200_gemm_f16(const void* A, int lda, int a_layout, const void* B, int ldb, int b_layout, int M, int N, int K,
                   int epilogue, const float* bias, const void* aux, int ld_aux, void* out, int ld_out, int out_dtype,
                   void* out2, int ld_out2, const float* alpha, int k_splits, void* stream);

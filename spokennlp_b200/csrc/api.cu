@@ -114,6 +114,10 @@ int get_tmap(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_
   return B200_OK;
 }
 
+std::atomic<int> g_sm_limit{0};
+
+// SMs the persistent kernels (one CTA / CTA pair per SM) may occupy: the device's count, minus what the caller reserved
+// for concurrently running communication kernels (b200_set_sm_limit).
 int sm_count() {
   static int n = 0;
   if (!n) {
@@ -122,7 +126,10 @@ int sm_count() {
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
   }
-  return n;
+  const int lim = g_sm_limit.load(std::memory_order_relaxed);
+  int m = (lim > 0 && lim < n) ? lim : n;
+  if (m > 2) m &= ~1;                   // CTA pairs
+  return m;
 }
 
 template <typename K>
@@ -172,6 +179,7 @@ extern "C" {
 
 void b200_set_gemm_impl(int impl) { g_gemm_impl.store(impl == 1 ? 1 : 2); }
 void b200_set_gemm_debug(int bits) { g_gemm_dbg.store(bits); }
+void b200_set_sm_limit(int sms) { g_sm_limit.store(sms); }
 
 const char* b200_last_error(void) { return g_err.c_str(); }
 int b200_version(void) { return 100; }

@@ -58,7 +58,7 @@ _PROTOS = {
     "b200_adamw_step_dev": [_p, _p, _p, _p, _p, _sz, _p, _p, _p],
     "b200_adamw_step_dev_zero": [_p, _p, _p, _p, _p, _sz, _p, _p, _p],
 }
-_RESTYPE = {"b200_set_gemm_impl": None, "b200_set_gemm_debug": None, "b200_last_error": C.c_char_p, "b200_launch_count": _ll, "b200_version": _i, "b200_attn_bwd_workspace": _sz, "b200_ponet_workspace": _sz, "b200_ponet_bwd_workspace": _sz}
+_RESTYPE = {"b200_set_gemm_impl": None, "b200_set_gemm_debug": None, "b200_set_sm_limit": None, "b200_last_error": C.c_char_p, "b200_launch_count": _ll, "b200_version": _i, "b200_attn_bwd_workspace": _sz, "b200_ponet_workspace": _sz, "b200_ponet_bwd_workspace": _sz}
 
 _lock = threading.Lock()
 _lib = None
@@ -93,6 +93,7 @@ def load() -> C.CDLL:
                 getattr(lib, name).restype = rt
             lib.b200_set_gemm_impl.argtypes = [_i]
             lib.b200_set_gemm_debug.argtypes = [_i]
+            lib.b200_set_sm_limit.argtypes = [_i]
             _lib = lib
     return _lib
 

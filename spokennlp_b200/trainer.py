@@ -10,6 +10,7 @@ layer as soon as that layer's weight gradients are complete so that it overlaps 
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
@@ -81,6 +82,25 @@ class DataParallelTrainer:
         self.step_idx = 0
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank() if self.world > 1 else 0
+        # Overlapped gradient buckets run on a second NCCL communicator capped at a few CTAs, and the persistent compute
+        # kernels of the backward (one CTA per SM, static work split) leave that many SMs free: a compute CTA that has to
+        # wait for a communication kernel to vacate its SM delays its whole kernel.  The last bucket, which nothing
+        # overlaps, goes through the default communicator at full width.  B200_COMM_CTAS=0 switches this off.
+        self.comm_ctas, self.bg_group, self._sms = 0, None, 0
+        if self.world > 1 and self.device.type == "cuda" and dist.get_backend() == "nccl":
+            want = int(os.environ.get("B200_COMM_CTAS", "4"))
+            if want > 0:
+                try:
+                    opts = dist.ProcessGroupNCCL.Options()
+                    opts.config.max_ctas = want
+                    opts.config.min_ctas = 1
+                    self.bg_group = dist.new_group(pg_options=opts)     # collective call: every rank constructs its trainer
+                    self.comm_ctas = want
+                    self._sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+                except Exception as e:  # noqa: BLE001  (older NCCL / torch without per-communicator config)
+                    import warnings
+                    warnings.warn(f"capped background communicator unavailable ({type(e).__name__}: {e}); using the default one")
+                    self.bg_group, self.comm_ctas = None, 0
         self.scale = torch.tensor([loss_scale, 1.0 / loss_scale], dtype=torch.float32, device=self.device)
         self.stats = torch.zeros(2, dtype=torch.float32, device=self.device)
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=self.device)
@@ -107,15 +127,21 @@ class DataParallelTrainer:
         self.drop = DropPlan(self.seed, self.p_hidden, self.p_attn) if (self.p_hidden > 0 or self.p_attn > 0) else None
 
     # ------------------------------------------------------------------------------------------------------------
-    def _allreduce_slice(self, lo: int, hi: int) -> None:
+    def _allreduce_slice(self, lo: int, hi: int, group=None) -> None:
         if self.world > 1 and hi > lo:
-            self._works.append(allreduce_bucket(self.flat.grad32, lo, hi))
+            self._works.append(allreduce_bucket(self.flat.grad32, lo, hi, group=group))
 
     def _after_layer(self, i: int) -> None:
         if i >= 0:
-            self._allreduce_slice(*self.layer_slices[i])
+            self._allreduce_slice(*self.layer_slices[i], group=self.bg_group)      # overlaps the rest of the backward
         else:
-            self._allreduce_slice(*self.emb_slice)
+            self._allreduce_slice(*self.emb_slice)                                 # exposed: full-width communicator
+
+    def _reserve_comm_sms(self, on: bool) -> None:
+        if self.comm_ctas > 0:
+            from . import lib as _lib
+            reserve = int(os.environ.get("B200_COMM_RESERVE", str(self.comm_ctas)))
+            _lib.load().b200_set_sm_limit(self._sms - reserve if (on and reserve > 0) else 0)
 
     def forward_backward(self, input_ids, attention_mask, token_type_ids, labels) -> torch.Tensor:
         """Enqueue forward + backward for one local batch; returns the device scalar loss (no sync)."""
@@ -143,7 +169,11 @@ class DataParallelTrainer:
                          flat.viewg("loss_calculator.classifier.bias"), scale=self.scale[0:1], drop=drop_head)
         self._works = []
         # the head's gradients live in the last bucket, which is reduced right after the top layer's backward
-        eng.backward(saved, dh, self.scale[1:2], after_layer=self._after_layer)
+        self._reserve_comm_sms(True)
+        try:
+            eng.backward(saved, dh, self.scale[1:2], after_layer=self._after_layer)
+        finally:
+            self._reserve_comm_sms(False)
         self.last_logits = logits
         return self.stats
 
