@@ -234,12 +234,29 @@ def kernel_rooflines(torch, ops, peaks):
     return out
 
 
+def arm_watchdog(rank, seconds):
+    """A collective that never completes must not hang the caller for ever: after `seconds` without the bench finishing,
+    rank 0 prints a JSON line that says so and every rank leaves with exit code 3."""
+    def fire():
+        if rank == 0:
+            print(json.dumps({"metric": "512-tok seq/sec BERT-base topic-seg fine-tune", "value": None, "unit": "seq/s",
+                              "error": f"bench.py watchdog: no result after {seconds} s (hung collective or kernel?)"}), flush=True)
+        sys.stderr.write(f"bench.py watchdog fired on rank {rank}\n")
+        sys.stderr.flush()
+        os._exit(3)
+    t = threading.Timer(seconds, fire)
+    t.daemon = True
+    t.start()
+    return t
+
+
 def run_b200_arm(args):
     import torch
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    watchdog = arm_watchdog(rank, int(os.environ.get("B200_BENCH_WATCHDOG_S", "900")))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
@@ -275,7 +292,8 @@ def run_b200_arm(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) * 1e-3
 
-    graphed = False if args.no_graph else trainer.capture(*dev)
+    use_graph = not args.no_graph and os.environ.get("B200_DP_GRAPH", "1") != "0"
+    graphed = trainer.capture(*dev) if use_graph else False
     for _ in range(max(3, args.warmup)):
         trainer.step(*dev)
     sampler = ClockSampler(local)
@@ -346,14 +364,18 @@ def run_b200_arm(args):
         if cpu is not None:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
+    watchdog.cancel()
     if world > 1:
         # Tear-down: a captured step holds NCCL work; destroying the communicator (or letting the interpreter run the
         # destructors) while the graph is alive can block for ever.  Drop the graph, drain the device, meet the peers once
         # more, then leave without running NCCL's tear-down (the process is ending anyway).
-        trainer.release_graph()
-        barrier()
         sys.stdout.flush()
         sys.stderr.flush()
+        bye = threading.Timer(30.0, lambda: os._exit(0))     # the result is out: never let the farewell barrier hang the job
+        bye.daemon = True
+        bye.start()
+        trainer.release_graph()
+        barrier()
         os._exit(0)
 
 
