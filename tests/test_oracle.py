@@ -148,3 +148,34 @@ def test_dropout_sites_match_hf_training_mode(monkeypatch):
     # keep-rate of the hash
     keep = float((masks["emb"] > 0).float().mean())
     assert abs(keep - 0.9) < 0.02
+
+
+def test_dropout_hash_statistics():
+    """The counter-based mask (oracle/dropout_masks.py == ptx.cuh drop_hash) behaves like independent Bernoulli(1-p) draws:
+    keep rate within 4 sigma of 1-p for several (seed, site) pairs, no correlation between the two 15-bit lanes of a hash,
+    between neighbouring pairs, between rows, or between sites / steps."""
+    import numpy as np
+    from oracle import dropout_masks as D
+    p, rows, H = 0.1, 512, 768
+    n = rows * H
+    sigma = (p * (1 - p) / n) ** 0.5
+    ms = {}
+    for seed, site in ((0, 0), (1, 0), (1234567, 8 * 5 + 1), (2 ** 31 - 1, 0xE000)):
+        m = (D.hidden_mask(seed, site, p, rows, H).numpy() > 0).astype(np.float64)
+        ms[(seed, site)] = m
+        assert abs(m.mean() - (1 - p)) < 4 * sigma, (seed, site, m.mean())
+        c = m - m.mean()
+        var = (c * c).mean()
+        for name, a, b in (("lanes of one hash", c[:, 0::2], c[:, 1::2]), ("neighbouring pairs", c[:, :-2], c[:, 2:]),
+                           ("rows", c[:-1], c[1:])):
+            corr = (a * b).mean() / var
+            assert abs(corr) < 4.0 / (a.size ** 0.5), (seed, site, name, corr)
+    a, b = ms[(0, 0)] - ms[(0, 0)].mean(), ms[(1, 0)] - ms[(1, 0)].mean()
+    assert abs((a * b).mean() / (a * a).mean()) < 4.0 / (n ** 0.5)             # consecutive step seeds are unrelated
+    # attention-probability site: same checks along the key axis of one (batch, head)
+    pm = (D.prob_mask(77, 3 * 8, p, 1, 2, 256, 512).numpy() > 0).astype(np.float64)
+    assert abs(pm.mean() - (1 - p)) < 4 * (p * (1 - p) / pm.size) ** 0.5
+    c = pm - pm.mean()
+    assert abs((c[..., :-1] * c[..., 1:]).mean() / (c * c).mean()) < 4.0 / (c.size ** 0.5)
+    # the threshold is exact to 2^-15: p = 0.1 -> 3277 / 32768
+    assert int(np.float32(0.1) * np.float32(32768.0) + np.float32(0.5)) == 3277
