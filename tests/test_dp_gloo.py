@@ -31,6 +31,14 @@ def _worker(rank, world, port, q):
     # averaging is applied later as a multiplier: mean gradient == sum * (1 / world)
     ref_mean = sum(torch.randn(numel, generator=torch.Generator().manual_seed(100 + r)) for r in range(world)) / world
     ok = ok and torch.allclose(flat * (1.0 / world), ref_mean, atol=1e-6)
+    # the trainer can send the overlapped buckets through a second communicator and keep the last one on the default
+    # group: mixing groups per bucket gives the same sums
+    bg = dist.new_group(ranks=list(range(world)))
+    flat2 = torch.randn(numel, generator=torch.Generator().manual_seed(100 + rank))
+    works = [allreduce_bucket(flat2, lo, hi, group=(bg if i + 1 < len(buckets) else None)) for i, (lo, hi) in enumerate(buckets)]
+    for w in works:
+        w.wait()
+    ok = ok and torch.equal(flat2, whole)
     q.put((rank, ok))
     dist.destroy_process_group()
 
