@@ -93,3 +93,23 @@ def synthetic_document(n_tokens: int, seed: int, bos_id: int = 30522, vocab_lo: 
         labs.append(0 if float(torch.rand(1, generator=g)) < p_boundary else 1)
         total += n
     return sents, labs
+
+
+def synthetic_segments(B: int, S: int, seed: int, pad_from=None):
+    """SURVEY.md §8d config 3 inputs for PoNet: `segment_ids` as the reference driver builds them
+    (`ponet_topic_segmentation.py:564-596`: 0 for [CLS], runs of ~U[8,40] tokens numbered 1..k, k+1 on padding) and the
+    matching attention mask; row b is padded from position pad_from[b] on."""
+    g = torch.Generator().manual_seed(seed)
+    seg = torch.zeros(B, S, dtype=torch.long)
+    mask = torch.ones(B, S, dtype=torch.long)
+    for b in range(B):
+        end = S if pad_from is None else pad_from[b]
+        s, k = 1, 0
+        while s < end:
+            k += 1
+            ln = int(torch.randint(8, 41, (1,), generator=g))
+            seg[b, s:min(end, s + ln)] = k
+            s += ln
+        seg[b, end:] = k + 1
+        mask[b, end:] = 0
+    return seg, mask

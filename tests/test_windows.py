@@ -55,3 +55,15 @@ def test_collate_shapes():
     sents, labs = synthetic_document(3000, 5)
     ids, mask, tt, labels = collate(build_windows(sents, labs, S))
     assert ids.shape == mask.shape == tt.shape == labels.shape and ids.shape[1] == S and ids.dtype == torch.long
+
+
+def test_synthetic_segments_follow_the_driver_convention():
+    from spokennlp_b200.windows import synthetic_segments
+    seg, mask = synthetic_segments(2, 256, seed=3, pad_from=[256, 200])
+    assert seg[:, 0].tolist() == [0, 0] and mask[0].all() and mask[1, :200].all() and not mask[1, 200:].any()
+    for b, end in ((0, 256), (1, 200)):
+        body = seg[b, 1:end]
+        assert bool((body[1:] - body[:-1] >= 0).all()) and int(body[0]) == 1          # monotone runs numbered from 1
+        runs = torch.unique_consecutive(body, return_counts=True)[1]
+        assert int(runs[:-1].min()) >= 8 and int(runs.max()) <= 40
+        assert bool((seg[b, end:] == int(body.max()) + 1).all())

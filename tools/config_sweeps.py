@@ -78,7 +78,7 @@ for T in (2048, 4096, 8192, 16384, 32768):
          ms=t * 1e3)
 
 # ---- config 3: PoNet --------------------------------------------------------------------------------------------------
-from oracle.ponet_oracle import synth_segments  # noqa: E402  (synthetic segment ids only)
+from spokennlp_b200.windows import synthetic_segments as synth_segments  # noqa: E402
 from spokennlp_b200.modeling_ponet import PoNetConfig, PoNetModel  # noqa: E402
 
 pcfg = PoNetConfig(**{**{k: v for k, v in base.items()}, "max_position_embeddings": 4096})

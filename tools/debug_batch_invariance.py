@@ -13,8 +13,12 @@ torch.manual_seed(0)
 kw = dict(hidden_size=768, num_attention_heads=12, intermediate_size=3072, num_hidden_layers=2, vocab_size=30523,
           max_position_embeddings=512, type_vocab_size=2)
 m = BertModel(BertConfig(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, **kw))
-from oracle import bert_oracle as O  # noqa: E402  (debug tool: random non-zero biases / LN params)
-m.load_state_dict(O.random_state_dict(O.OracleConfig(**kw), seed=1))
+with torch.no_grad():                     # non-trivial biases / LayerNorm parameters (HF init leaves them at 0 / 1)
+    for name, prm in m.named_parameters():
+        if name.endswith("bias"):
+            prm.normal_(0.0, 0.02)
+        elif name.endswith("LayerNorm.weight"):
+            prm.add_(torch.randn_like(prm) * 0.05)
 m = m.cuda().eval()
 gen = torch.Generator().manual_seed(4)
 ids = torch.randint(1000, 30522, (32, 512), generator=gen).cuda()
