@@ -93,3 +93,18 @@ def test_every_ops_and_library_reference_resolves():
     src = open(os.path.join(pkg, "ops.py")).read()
     used = set(re.findall(r"\.(b200_[a-z0-9_]+)\(", src))
     assert used <= set(L.exported_symbols()), used - set(L.exported_symbols())
+
+
+def test_oracle_is_test_infrastructure_only():
+    """Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline leg may import oracle/ (the product path must
+    never route through the CPU restatement)."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pat = re.compile(r"^\s*(from\s+oracle\b|import\s+oracle\b)", re.M)
+    offenders = []
+    for base in ("spokennlp_b200", "tools"):
+        for dirpath, _, files in os.walk(os.path.join(root, base)):
+            for f in files:
+                if f.endswith(".py") and pat.search(open(os.path.join(dirpath, f)).read()):
+                    offenders.append(os.path.join(dirpath, f))
+    assert not offenders, offenders
