@@ -61,8 +61,7 @@ long long b200_launch_count(void);
 void b200_set_gemm_impl(int impl);
 /* measurement knobs.  Bits 1/2/4/8 (2-CTA GEMM: skip A loads / B loads / MMA / stores) and 0x10000/0x20000/0x40000 (attention
  * backward: skip dQ reductions / gradient MMAs / exp math) make results WRONG.  Kernel-generation selectors keep results
- * right and exist for A/B timing: 0x100000 first-generation attention kernels, 0x400000 second-generation (non-persistent)
- * attention kernels, 0x200000 first-generation LayerNorm backward. */
+ * right and exist for A/B timing: 0x100000 first-generation attention kernels, 0x200000 first-generation LayerNorm backward. */
 void b200_set_gemm_debug(int bits);
 /* Persistent kernels (GEMM, attention: one CTA or CTA pair per SM) size their grids to min(device SMs, sms); 0 = all SMs.
  * A data-parallel caller reserves the SMs its concurrently running NCCL kernels occupy, so that no compute CTA has to

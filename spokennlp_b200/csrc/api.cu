@@ -9,10 +9,8 @@
 
 #include "../../include/b200enc.h"
 #include "attn_bwd.cuh"
-#include "attn_bwd2.cuh"
 #include "attn_bwd3.cuh"
 #include "attn_fwd.cuh"
-#include "attn_fwd2.cuh"
 #include "attn_fwd3.cuh"
 #include "gemm.cuh"
 #include "gemm2.cuh"
@@ -299,25 +297,17 @@ int b200_attn_fwd_drop(const void* q, int ldq, int q_col0, const void* kv, int l
   AttnFwdArgs a{B, heads, Sq, Sk, q_col0, k_col0, v_col0, key_bias, kv_len, static_cast<__half*>(ctx), ld_out, lse2,
                 1.4426950408889634f / 8.0f, drop};
   dim3 grid((Sq + 2 * ATT_BQ - 1) / (2 * ATT_BQ), heads, B);
-  if (!(g_gemm_dbg.load() & 0x100000)) {      // default: second-generation kernel (0x100000 keeps the first one for A/B runs)
-    static int d0 = set_smem(attn_fwd2_kernel<false>, AttnFwdSmem::TOTAL);
-    static int d1 = set_smem(attn_fwd2_kernel<true>, AttnFwdSmem::TOTAL);
-    if (d0 != B200_OK || d1 != B200_OK) return d0 ? d0 : d1;
+  if (!(g_gemm_dbg.load() & 0x100000)) {      // default: persistent kernel, one CTA per SM walking (batch, head, query-pair) items
     CUtensorMap to;                             // context output fp16 [B*Sq, ld_out], 64 x 32 patches (one per softmax warp)
     if ((rc = get_tmap(ctx, static_cast<uint64_t>(B) * Sq, ld_out, ld_out, 32, &to))) return rc;
-    if (!(g_gemm_dbg.load() & 0x400000)) {    // default: persistent kernel, one CTA per SM walking (batch, head, query-pair) items
-      static int e0 = set_smem(attn_fwd3_kernel<false>, AttnFwd3Smem::TOTAL);
-      static int e1 = set_smem(attn_fwd3_kernel<true>, AttnFwd3Smem::TOTAL);
-      if (e0 != B200_OK || e1 != B200_OK) return e0 ? e0 : e1;
-      const long long items = static_cast<long long>(grid.x) * grid.y * grid.z;
-      const int ctas = items < sm_count() ? static_cast<int>(items) : sm_count();
-      if (drop.seed_base) attn_fwd3_kernel<true><<<ctas, ATT2_THREADS, AttnFwd3Smem::TOTAL, static_cast<cudaStream_t>(stream)>>>(tq, tkv, to, a);
-      else attn_fwd3_kernel<false><<<ctas, ATT2_THREADS, AttnFwd3Smem::TOTAL, static_cast<cudaStream_t>(stream)>>>(tq, tkv, to, a);
-      return check_launch("attn_fwd3_kernel");
-    }
-    if (drop.seed_base) attn_fwd2_kernel<true><<<grid, ATT2_THREADS, AttnFwdSmem::TOTAL, static_cast<cudaStream_t>(stream)>>>(tq, tkv, to, a);
-    else attn_fwd2_kernel<false><<<grid, ATT2_THREADS, AttnFwdSmem::TOTAL, static_cast<cudaStream_t>(stream)>>>(tq, tkv, to, a);
-    return check_launch("attn_fwd2_kernel");
+    static int e0 = set_smem(attn_fwd3_kernel<false>, AttnFwd3Smem::TOTAL);
+    static int e1 = set_smem(attn_fwd3_kernel<true>, AttnFwd3Smem::TOTAL);
+    if (e0 != B200_OK || e1 != B200_OK) return e0 ? e0 : e1;
+    const long long items = static_cast<long long>(grid.x) * grid.y * grid.z;
+    const int ctas = items < sm_count() ? static_cast<int>(items) : sm_count();
+    if (drop.seed_base) attn_fwd3_kernel<true><<<ctas, ATTP_THREADS, AttnFwd3Smem::TOTAL, static_cast<cudaStream_t>(stream)>>>(tq, tkv, to, a);
+    else attn_fwd3_kernel<false><<<ctas, ATTP_THREADS, AttnFwd3Smem::TOTAL, static_cast<cudaStream_t>(stream)>>>(tq, tkv, to, a);
+    return check_launch("attn_fwd3_kernel");
   }
   if (drop.seed_base) attn_fwd_kernel<true><<<grid, ATT_THREADS, AttnFwdSmem::TOTAL, static_cast<cudaStream_t>(stream)>>>(tq, tkv, a);
   else attn_fwd_kernel<false><<<grid, ATT_THREADS, AttnFwdSmem::TOTAL, static_cast<cudaStream_t>(stream)>>>(tq, tkv, a);

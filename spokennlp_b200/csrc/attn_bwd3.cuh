@@ -1,28 +1,57 @@
-// Fused attention backward, persistent version (same contract and workspace as attn_bwd.cuh / attn_bwd2.cuh).
+// Fused attention backward, production version (same contract and workspace as attn_bwd.cuh, which is kept as the first
+// generation for A/B runs) — the autograd of bert_model.py:309-350 for head_dim 64.
 //
-// attn_bwd2_kernel at the bench shape: 150 us, of which ~60 us are per-CTA fixed cost (Sk sweep, profiles/r01e) — launch,
-// TMEM allocation, the first K/V + Q/dO round trip, the pipeline ramp and the dK/dV drain — paid 10.4 times per SM because
-// a CTA owns the whole SM.  Here ONE CTA per SM stays resident and walks (batch, head, key-block) items:
+// One work item = one 128-key block of one (batch, head), walked over the 128-query blocks i:
+//     S  = Q_i K^T , dP = dO_i V^T                     (K-major operands, M = queries, N = 64 keys per half)
+//     P  = exp2(S c + bias_k - lse2_q),  dS = P o (dP - delta_q) / sqrt(d)          [CUDA cores, row per thread]
+//     dV += P^T  dO_i   (A = P  tile viewed MN-major, B = dO_i MN-major)            accumulates in TMEM over i
+//     dK += dS^T Q_i    (A = dS tile viewed MN-major, B = Q_i  MN-major)            accumulates in TMEM over i
+//     dQ_i = dS K       (A = dS K-major, B = K MN-major) -> fp32 TMA reduce-add into dq_acc
+// Inside an item (what changed against attn_bwd_kernel, profiles/r01d -> r01f):
+//   * natural orientation, TMEM lane == QUERY row: lse2 / delta are two registers per thread instead of two shared-memory
+//     loads per score, and the dropout mask is regenerated pairwise exactly as the forward drew it;
+//   * the score tile is split by KEY half between the two softmax groups, each with its own score buffers and barriers:
+//     S_g(i+1) and dP_g(i+1) are issued as soon as group g holds block i in registers, so the tensor core recomputes
+//     scores while the CUDA cores do the exp / dS math; group 1 starts half a period after group 0;
+//   * a 3-deep Q / dO ring keeps the operands of block i+1 resident that early;
+//   * dQ leaves as ONE TMA reduce-add per warp from a 128B-swizzled staging patch (8 scattered red.global.add.v4 per
+//     thread kept the LSU busy for ~2k cycles per block and stalled the next block on the register hazard); rows past Sq
+//     carry exact zeros (P = 0 there), so the box needs no row clipping inside a batch element.
+// Across items (Sk sweep, profiles/r01e: ~60 of 150 us were per-CTA fixed cost paid 10.4 times per SM): ONE CTA per SM
+// stays resident and walks (batch, head, key-block) items;
 //   * the TMA warp fetches Q_0 / dO_0 of the next item while the current one is still running and its K / V as soon as the
 //     last gradient MMAs have retired — that latency hides behind the dK / dV drain of the softmax warps,
 //   * barrier phases, the Q / dO ring position and the dQ ping-pong buffer come from running counters,
-//   * dK / dV leave through the dQ staging patches (free at that point), so the P / dS tiles never have to be protected
-//     across an item boundary.
-// Inside an item the schedule is attn_bwd2_kernel's (natural orientation, key halves half a period apart, early score
-// hand-back, dQ by TMA reduce-add).
+//   * dK / dV leave through the dQ staging patches (free at that point) as two TMA stores, so the P / dS tiles never have
+//     to be protected across an item boundary.
 //   warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 softmax group 0 (keys 0-63), warps 6-9 group 1 (keys 64-127)
 #pragma once
-#include "attn_bwd2.cuh"
+#include "attn_bwd.cuh"
 
 namespace b200 {
+
+constexpr int ATTB3_QDO_STAGES = 3;
+
+struct AttnBwd3Smem {
+  static constexpr int T = ATT_BK * ATT_D * 2;                 // 16 KB tile
+  static constexpr int OFF_K = 0;
+  static constexpr int OFF_V = OFF_K + T;
+  static constexpr int OFF_QDO = OFF_V + T;                    // 3 stages x (Q_i, dO_i)
+  static constexpr int OFF_P = OFF_QDO + ATTB3_QDO_STAGES * 2 * T;   // P  [128 q][128 keys] fp16 = 32 KB (two 64-key halves)
+  static constexpr int OFF_DS = OFF_P + 2 * T;                 // dS 32 KB
+  static constexpr int OFF_DQS = OFF_DS + 2 * T;               // dQ staging for the TMA reduction: 8 warps x [32 q][32 d] fp32 (4 KB each)
+  static constexpr int OFF_BIAS = OFF_DQS + 8 * 4096;          // [128] floats: additive bias of this item's keys (log2 units)
+  static constexpr int OFF_BAR = OFF_BIAS + ATT_BK * 4;
+  static constexpr int TOTAL = OFF_BAR + 256 + 1024;
+};
 
 template <bool DROP>
 __global__ void __launch_bounds__(ATTB_THREADS, 1)
 attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                  const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmDQ,
                  const __grid_constant__ CUtensorMap tmDKV, const AttnBwdArgs a) {
-  using S = AttnBwd2Smem;
-  constexpr int NST = ATTB2_QDO_STAGES;
+  using S = AttnBwd3Smem;
+  constexpr int NST = ATTB3_QDO_STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
@@ -144,7 +173,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const uint32_t st = qs % NST;
         if (i == 0) {
           // group 1's first scores of the item.  At the very start of the kernel they are held back until group 0 has pulled
-          // its own block out of TMEM, so that the two groups run half a period apart (attn_bwd2.cuh).
+          // its own block out of TMEM, so that the two groups run half a period apart (header).
           if (ir > 0) mbar_wait(&s_free[1], (ir - 1) & 1);
           else mbar_wait(&s_free[0], 0);
           tc_fence_after();

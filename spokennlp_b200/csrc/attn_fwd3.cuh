@@ -1,22 +1,35 @@
-// Fused attention forward, persistent version (same contract as attn_fwd.cuh / attn_fwd2.cuh).
+// Fused attention forward, production version (same contract as attn_fwd.cuh, which is kept as the first generation for
+// A/B runs): head_dim 64, fp16 operands, fp32 softmax statistics, context never materialises P in HBM.
 //
-// The Sk sweep of attn_fwd2_kernel (profiles/r01e) splits its 74 us at the bench shape into 41 us of per-key-block work and
-// 33 us of per-CTA fixed cost: launch, TMEM allocation, the first TMA round trip, the pipeline ramp and the output drain
-// are all exposed because one CTA owns the SM (200 KB of shared memory, 512 TMEM columns) and the next one cannot start
-// before it has left.  Here ONE CTA per SM stays resident and walks work items (batch, head, 256-query pair):
+// Inside one 128 x 128 score block (what changed against attn_fwd_kernel, profiles/r01d -> r01e):
+//   * ONE pass over the scores: a thread pulls its whole 128-key row out of TMEM into registers (4 back-to-back
+//     tcgen05.ld, one wait) instead of reading every score twice;
+//   * the score buffer is handed back to the tensor core as soon as it sits in registers (`s_free`), so S(j+1) is computed
+//     WHILE the softmax of block j runs — the softmax warps never wait for the MMA round trip;
+//   * each query tile has its own MMA-issuing warp, and tile B starts half a period after tile A: the MUFU (exp2, the
+//     busiest unit at d = 64: 8 clk per warp instruction) and the rest of a block alternate between the two tiles;
+//   * masking is a pre-pass that only runs in blocks that contain masked keys (prefix masks: an index compare; general
+//     additive bias: staged per block), so the common block carries ~4 instructions per score
+//     (FMNMX3/2 + FFMA + MUFU.EX2 + FADD + F2FP/2); dropout tests both lanes of a hash at once (ptx.cuh: drop_z);
+//   * a warp's 32 context rows leave as ONE TMA store from a 128B-swizzled staging patch (a thread-per-row st.global
+//     touches 32 different 128-byte lines per instruction and kept the LSU busy for ~1.4 us per CTA).
+// Across blocks (Sk sweep of the non-persistent form of this kernel, profiles/r01e: 74 us at the bench shape = 41 us of
+// per-block work + 33 us of per-CTA fixed cost — launch, TMEM allocation, first TMA round trip, pipeline ramp, output
+// drain, all exposed because one CTA owns the SM): ONE CTA per SM stays resident and walks (batch, head, 256-query pair)
+// items;
 //   * the TMA warp runs ahead across item boundaries (Q double-buffered by item parity, K and V in separate 2-stage rings
 //     — K_{j+1} is wanted a whole block earlier than V_{j+1}, so it must not queue behind it),
 //   * the MMA warps issue the first S of the next item while the softmax warps are still writing the previous context,
 //   * barrier phases come from running counters, so nothing is re-initialised between items.
-// Everything inside a block is attn_fwd2_kernel: one pass over the scores, early hand-back of the score buffer, the two
-// query tiles running half a period apart, TMA-stored context rows.
 //   warp 0       TMA producer
 //   warp 1, 2    MMA issuers for query tile A / B
 //   warps 3-10   softmax A (3-6) / softmax B (7-10): one thread per query row
 #pragma once
-#include "attn_fwd2.cuh"
+#include "attn_fwd.cuh"
 
 namespace b200 {
+
+constexpr int ATTP_THREADS = 352;
 
 struct AttnFwd3Smem {
   static constexpr int TILE = ATT_BQ * ATT_D * 2;                    // 16 KB: one Q / K / V tile
@@ -31,7 +44,7 @@ struct AttnFwd3Smem {
 };
 
 template <bool DROP>
-__global__ void __launch_bounds__(ATT2_THREADS, 1)
+__global__ void __launch_bounds__(ATTP_THREADS, 1)
 attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                  const __grid_constant__ CUtensorMap tmO, const AttnFwdArgs a) {
   using S = AttnFwd3Smem;
@@ -163,7 +176,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_wait(&q_full[buf], (n >> 1) & 1);
       mbar_wait(&k_full[kb & 1], (kb >> 1) & 1);
       if (t > 0) mbar_wait(&s_free[x], (t - 1) & 1);         // the previous block's score rows sit in registers
-      else if (x == 1) mbar_wait(b_go, 0);                   // tile B starts half a period after tile A (attn_fwd2.cuh)
+      else if (x == 1) mbar_wait(b_go, 0);                   // tile B starts half a period after tile A (header)
       tc_fence_after();
       if (lane == 0) issue_s(kb & 1, nb == 1);
       __syncwarp();
@@ -327,7 +340,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         w[k] = *reinterpret_cast<const uint32_t*>(&hv);
       }
       const int wrow0 = it.q0 + x * ATT_BQ + qd * 32;        // first query row of this warp
-      if (wrow0 + 32 <= a.Sq) {                              // one TMA store per warp from a swizzled staging patch (attn_fwd2.cuh)
+      if (wrow0 + 32 <= a.Sq) {                              // one TMA store per warp from a swizzled staging patch
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) sts128(p_row + ((ch ^ (r & 7)) << 4), w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
         fence_proxy_async_smem();

@@ -1,4 +1,4 @@
-"""A/B of the two attention kernel generations at the bench shape (B=32, S=512, 12 heads, d=64):
+"""A/B of the production attention kernels ("v2" below) against the first generation ("v1") at the bench shape (B=32, S=512, 12 heads, d=64):
 timing (CUDA events, kernel alone) with and without dropout, plus agreement of their outputs on the same inputs
 (b200_set_gemm_debug bit 0x100000 selects the first-generation kernels)."""
 import os

@@ -1,5 +1,6 @@
 """Attention kernels alone at the bench shape, for `ncu --set full` captures and for the Sk sweep that separates the
-per-CTA fixed cost from the per-key-block cost:  python tools/prof_attn.py [sweep]"""
+per-item fixed cost from the per-key-block cost:  python tools/prof_attn.py [sweep [debug bits ...]]
+(debug bits as in include/b200enc.h, e.g. `sweep 0 0x100000` compares the production kernels with the first generation)"""
 import os
 import sys
 
