@@ -108,3 +108,31 @@ def test_oracle_is_test_infrastructure_only():
                 if f.endswith(".py") and pat.search(open(os.path.join(dirpath, f)).read()):
                     offenders.append(os.path.join(dirpath, f))
     assert not offenders, offenders
+
+
+def test_bench_synthetic_batch_follows_the_spec():
+    """ids uniform in [1000, 30522) with [CLS] = 101 first and the added [BOS] id 30522 at every
+    position 1 + 20k; labels are -100 except at [BOS] positions (and on padding); disjoint seeded shards per rank."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    ids, mask, tt, labels = bench.synth_batch(torch, 32, 512, 1234)
+    assert ids.shape == mask.shape == tt.shape == labels.shape == (32, 512) and ids.dtype == torch.int64
+    bos = torch.arange(1, 512, 20)
+    assert bool((ids[:, 0] == 101).all()) and bool((ids[:, bos] == 30522).all()) and int(ids.max()) < bench.VOCAB
+    other = torch.ones(512, dtype=torch.bool)
+    other[0] = False
+    other[bos] = False
+    assert bool((ids[:, other] >= 1000).all()) and bool((ids[:, other] < 30522).all())
+    assert bool(mask.all()) and not bool(tt.any())
+    assert bool((labels[:, other] == -100).all()) and bool((labels[:, 0] == -100).all())
+    assert set(labels[:, bos].unique().tolist()) <= {0, 1} and 0.7 < float(labels[:, bos].float().mean()) < 0.95
+    ids2, _, _, _ = bench.synth_batch(torch, 32, 512, 1235)
+    assert not torch.equal(ids, ids2)                                        # rank r uses seed 1234 + r
+    pids, pmask, _, plabels = bench.synth_batch(torch, 8, 512, 7, padded=True)
+    lens = pmask.sum(1)
+    assert int(lens.min()) >= 256 and int(lens.max()) <= 512
+    assert bool((plabels[pmask == 0] == -100).all())
+    assert bench.FLOP_PER_SEQ == 3 * 12 * (24 * 512 * 768 * 768 + 4 * 512 * 512 * 768)   # fwd+bwd, SURVEY §8d
