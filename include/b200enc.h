@@ -44,6 +44,9 @@ extern "C" {
 
 const char* b200_last_error(void);
 int b200_version(void);
+/* sha1 over the sources this library was built from (csrc/ + this header), or "unknown" for a hand-run make; the
+ * Python binding compares it with the tree it runs in, so a stale library is rebuilt or refused instead of half-working */
+const char* b200_source_hash(void);
 /* number of kernels this library has launched in this process (bench.py reports it as gpu_launches) */
 long long b200_launch_count(void);
 

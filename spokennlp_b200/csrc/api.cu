@@ -181,6 +181,11 @@ void b200_set_sm_limit(int sms) { g_sm_limit.store(sms); }
 
 const char* b200_last_error(void) { return g_err.c_str(); }
 int b200_version(void) { return 100; }
+#ifndef B200_SRC_HASH
+#define B200_SRC_HASH "unknown"
+#endif
+static const char g_src_tag[] = "B200SRC:" B200_SRC_HASH;        // the binding also finds this tag by scanning the file
+const char* b200_source_hash(void) { return g_src_tag + 8; }
 long long b200_launch_count(void) { return g_launches.load(); }
 
 static int gemm_impl(const void* A, int lda, int a_layout, const void* B, int ldb, int b_layout, int M, int N, int K, int epilogue,

@@ -9,6 +9,7 @@ import ctypes as C
 import os
 import subprocess
 import threading
+from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200enc.so")
@@ -58,32 +59,74 @@ _PROTOS = {
     "b200_adamw_step_dev": [_p, _p, _p, _p, _p, _sz, _p, _p, _p],
     "b200_adamw_step_dev_zero": [_p, _p, _p, _p, _p, _sz, _p, _p, _p],
 }
-_RESTYPE = {"b200_set_gemm_impl": None, "b200_set_gemm_debug": None, "b200_set_sm_limit": None, "b200_last_error": C.c_char_p, "b200_launch_count": _ll, "b200_version": _i, "b200_attn_bwd_workspace": _sz, "b200_ponet_workspace": _sz, "b200_ponet_bwd_workspace": _sz}
+_RESTYPE = {"b200_set_gemm_impl": None, "b200_set_gemm_debug": None, "b200_set_sm_limit": None, "b200_last_error": C.c_char_p, "b200_launch_count": _ll, "b200_version": _i, "b200_source_hash": C.c_char_p, "b200_attn_bwd_workspace": _sz, "b200_ponet_workspace": _sz, "b200_ponet_bwd_workspace": _sz}
 
 _lock = threading.Lock()
 _lib = None
 
 
-def build(verbose: bool = False) -> str:
-    """Compile libb200enc.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
-    r = subprocess.run(["make", "-C", CSRC], capture_output=True, text=True)
-    if verbose or r.returncode != 0:
-        print(r.stdout[-4000:])
-        print(r.stderr[-4000:])
-    if r.returncode != 0:
-        raise RuntimeError("building libb200enc.so failed (see output above)")
+def source_hash() -> str:
+    """sha1 over everything libb200enc.so is compiled from (csrc/*.cu, *.cuh, *.inc, the Makefile, include/b200enc.h)."""
+    import hashlib
+    h = hashlib.sha1()
+    files = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".inc")) or f == "Makefile")
+    for path in [os.path.join(CSRC, f) for f in files] + [os.path.join(os.path.dirname(_HERE), "include", "b200enc.h")]:
+        h.update(os.path.basename(path).encode() + b"\0")
+        with open(path, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def built_hash() -> Optional[str]:
+    """Source hash recorded inside the library file on disk (read without loading it); None if there is no library,
+    'unknown' for a library from a hand-run `make`."""
+    if not os.path.exists(LIB_PATH):
+        return None
+    with open(LIB_PATH, "rb") as fh:
+        blob = fh.read()
+    i = blob.find(b"B200SRC:")
+    if i < 0:
+        return "unknown"
+    return blob[i + 8:blob.index(b"\0", i)].decode(errors="replace")
+
+
+def is_stale() -> bool:
+    b = built_hash()
+    return b is None or (b != "unknown" and b != source_hash())
+
+
+def build(verbose: bool = False, force: bool = False) -> str:
+    """Compile libb200enc.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).  The source hash is recorded
+    in the library; nothing is rebuilt when the library on disk already carries the hash of this tree.  Concurrent callers
+    (one process per GPU) serialise on a lock file."""
+    import fcntl
+    want = source_hash()
+    with open(os.path.join(CSRC, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and built_hash() == want:
+            return LIB_PATH
+        r = subprocess.run(["make", "-B", "-C", CSRC, f"SRC_HASH={want}"], capture_output=True, text=True)
+        if verbose or r.returncode != 0:
+            print(r.stdout[-4000:])
+            print(r.stderr[-4000:])
+        if r.returncode != 0:
+            raise RuntimeError("building libb200enc.so failed (see output above)")
     return LIB_PATH
 
 
 def load() -> C.CDLL:
-    """Load the library (never builds implicitly on the GPU box: the .so travels with the tree)."""
+    """Load the library.  There is no fallback: a missing library, or one built from other sources than this tree's, is
+    rebuilt when nvcc is available (the GPU box has the same toolchain) and otherwise refused — never half-used."""
     global _lib
     with _lock:
         if _lib is None:
-            if not os.path.exists(LIB_PATH):
-                raise RuntimeError(
-                    f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
-                    "(the B200 path has no CPU/PyTorch fallback)")
+            if is_stale():
+                import shutil
+                if shutil.which("nvcc") is None or shutil.which("make") is None:
+                    raise RuntimeError(
+                        f"{LIB_PATH} is missing or was built from different sources and nvcc is not on PATH: run "
+                        "`python -c 'import __graft_entry__ as g; g.build()'` (the B200 path has no CPU/PyTorch fallback)")
+                build()
             lib = C.CDLL(LIB_PATH)
             for name, argt in _PROTOS.items():
                 fn = getattr(lib, name)      # AttributeError here == header/library mismatch: fail loudly

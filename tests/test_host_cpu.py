@@ -13,9 +13,21 @@ from conftest import ROOT
 @pytest.fixture(scope="module")
 def lib():
     from spokennlp_b200 import lib as L
-    if not os.path.exists(L.LIB_PATH):
+    if L.is_stale():
         L.build()
     return L
+
+
+def test_library_carries_the_hash_of_the_sources_it_was_built_from(lib, tmp_path, monkeypatch):
+    """A library built from other sources than this tree's must be noticed (round 1 lost a GPU call to a stale .so)."""
+    assert lib.built_hash() == lib.source_hash() and not lib.is_stale()
+    assert lib.load().b200_source_hash().decode() == lib.source_hash()
+    fake = tmp_path / "libb200enc.so"
+    fake.write_bytes(b"\x7fELF....B200SRC:" + b"0" * 40 + b"\0....")
+    monkeypatch.setattr(lib, "LIB_PATH", str(fake))
+    assert lib.built_hash() == "0" * 40 and lib.is_stale()
+    monkeypatch.setattr(lib, "LIB_PATH", str(tmp_path / "absent.so"))
+    assert lib.built_hash() is None and lib.is_stale()
 
 
 def test_library_exports_every_declared_symbol(lib):
