@@ -218,6 +218,28 @@ int b200_cls_head_bwd_drop(const void* h, const float* logits, const int64_t* la
                            const float* scale, void* dh, float* dW, float* db, int rows, int H, int C, const uint32_t* seed, unsigned site,
                            float p, void* stream);
 
+/* ---- opt-in variants (written in round 1 after the GPU budget was spent; NOT on the default path until a
+ * GPU run has held them to the oracle) ---------------------------------------------------------------------------------
+ *
+ * b200_gemm_f16_resadd: out32[M,N] += drop(A[M,K] * B[N,K]^T + bias[n]).  `out` already holds the fp32 residual (what
+ *   LayerNorm wrote), so `LN(dropout(dense(x)) + residual)` (bert_model.py:371-375, :449-453) needs no residual read in the
+ *   epilogue: partial tiles leave through TMA reduce-add.  stream_k != 0 cuts the K blocks of all tiles into equal shares
+ *   per CTA pair (no straggler round for N = 768); results then depend on the fp32 summation order (last-bit differences).
+ * b200_gemm_f16_dgrad_delta: out16[M,N] = A[M,K] * B[K,N] (B row-major [K,N]: the output projection's dgrad), and
+ *   delta[b,h,q] = sum_d out[b*Sq+q, 64h+d] * ctx[b*Sq+q, 64h+d] — the row statistic of attention backward, written to the
+ *   head of the attention-backward workspace (b200_attn_bwd_delta_ptr) so that b200_attn_bwd_ext can skip its own pass.
+ * b200_attn_bwd_ext: b200_attn_bwd_drop + flags. */
+#define B200_ATTN_BWD_DELTA_READY 1   /* workspace already holds delta (from b200_gemm_f16_dgrad_delta) */
+int b200_gemm_f16_resadd(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias, float* out, int ld_out,
+                         const uint32_t* seed, unsigned site, float p, int stream_k, void* stream);
+int b200_gemm_f16_dgrad_delta(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const void* ctx, int ld_ctx, void* out,
+                              int ld_out, float* delta, int heads, int Sq, void* stream);
+float* b200_attn_bwd_delta_ptr(void* workspace);
+int b200_attn_bwd_ext(const void* q, int ldq, int q_col0, const void* kv, int ldkv, int k_col0, int v_col0, const void* dctx, int ld_dctx,
+                      const void* ctx, int ld_ctx, const float* key_bias, const int32_t* kv_len, const float* lse2, void* workspace,
+                      void* dq, int ld_dq, int dq_col0, void* dkv, int ld_dkv, int dk_col0, int dv_col0, int B, int heads, int Sq, int Sk,
+                      const uint32_t* seed, unsigned site, float p, int flags, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

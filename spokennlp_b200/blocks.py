@@ -21,6 +21,38 @@ Tensor = torch.Tensor
 F16, F32 = torch.float16, torch.float32
 
 
+class Experimental:
+    """Opt-in kernel variants written after round 1's GPU budget was spent.  They are OFF unless named in
+    the environment variable B200_EXP (comma-separated) or switched on here by a test / A-B tool; the default path is the
+    one the round-1 GPU runs validated.
+      resadd : output-dense + residual through b200_gemm_f16_resadd (in place on the fp32 residual stream, no aux reads)
+      streamk: with resadd, the stream-K schedule for those N = 768 GEMMs
+      delta  : attention-backward row statistic fused into the output projection's dgrad (b200_gemm_f16_dgrad_delta)"""
+    resadd = streamk = delta = False
+
+    @classmethod
+    def from_env(cls, value: Optional[str] = None) -> None:
+        import os
+        names = {n.strip() for n in (os.environ.get("B200_EXP", "") if value is None else value).split(",") if n.strip()}
+        unknown = names - {"resadd", "streamk", "delta"}
+        if unknown:
+            raise ValueError(f"B200_EXP: unknown variant(s) {sorted(unknown)}")
+        cls.resadd, cls.streamk, cls.delta = "resadd" in names or "streamk" in names, "streamk" in names, "delta" in names
+
+
+Experimental.from_env()
+
+
+def _out_dense_residual(h16: Tensor, w: Tensor, bias: Tensor, x32: Tensor, drop, owns_residual: bool) -> Tensor:
+    """pre = dropout(h16 @ w^T + bias) + x32, fp32 (BertSelfOutput / BertOutput before their LayerNorm).  `owns_residual`:
+    nobody else reads x32 afterwards, so the opt-in in-place variant may accumulate into it."""
+    if Experimental.resadd and owns_residual:
+        return ops.gemm_resadd(h16, w, x32, bias, drop=drop, stream_k=Experimental.streamk)
+    pre = torch.empty(h16.shape[0], w.shape[0], dtype=F32, device=h16.device)
+    ops.gemm(h16, w, pre, epilogue=ops.EPI_BIAS_RES32, bias=bias, aux=x32, drop=drop)
+    return pre
+
+
 @dataclass
 class AttnWeights:
     """Self-attention: wqkv [3H,H] / bqkv packed.  Cross-attention: wq [H,H], bq and wkv [2H,Hkv], bkv (key and value
@@ -75,9 +107,9 @@ class FfnSaved:
 
 def attn_block_fwd(p: AttnWeights, x16: Tensor, x32: Tensor, B: int, Sq: int, heads: int, eps: float, key_bias, kv_len, *,
                    save: bool, want_probs: bool = False, kv16: Optional[Tensor] = None, Sk: Optional[int] = None,
-                   drop_attn: Optional[ops.Dropout] = None, drop_hidden: Optional[ops.Dropout] = None):
+                   drop_attn: Optional[ops.Dropout] = None, drop_hidden: Optional[ops.Dropout] = None, owns_residual: bool = False):
     """bert_model.py:259-375 (BertSelfAttention + BertSelfOutput).  Returns (y16, y32, saved, probs).  `probs` are the
-    probabilities BEFORE dropout."""
+    probabilities BEFORE dropout.  `owns_residual`: the caller hands x32 over (it is not a hidden state anybody keeps)."""
     H, Mq, dev = heads * 64, B * Sq, x16.device
     cross = kv16 is not None
     Sk = Sk if cross else Sq
@@ -98,8 +130,7 @@ def attn_block_fwd(p: AttnWeights, x16: Tensor, x32: Tensor, B: int, Sq: int, he
     probs = None
     if want_probs:
         probs = ops.attn_probs(q, kv, lse2, B, heads, Sq, Sk, q_col0=cols["q_col0"], k_col0=cols["k_col0"], key_bias=key_bias)
-    pre = torch.empty(Mq, H, dtype=F32, device=dev)
-    ops.gemm(ctx, p.wo, pre, epilogue=ops.EPI_BIAS_RES32, bias=p.bo, aux=x32, drop=drop_hidden)
+    pre = _out_dense_residual(ctx, p.wo, p.bo, x32, drop_hidden, owns_residual)
     mean = torch.empty(Mq, dtype=F32, device=dev) if save else None
     rstd = torch.empty(Mq, dtype=F32, device=dev) if save else None
     y32 = torch.empty(Mq, H, dtype=F32, device=dev)
@@ -109,15 +140,15 @@ def attn_block_fwd(p: AttnWeights, x16: Tensor, x32: Tensor, B: int, Sq: int, he
     return y16, y32, sv, probs
 
 
-def ffn_block_fwd(p: FfnWeights, x16: Tensor, x32: Tensor, eps: float, *, save: bool, drop_hidden: Optional[ops.Dropout] = None):
+def ffn_block_fwd(p: FfnWeights, x16: Tensor, x32: Tensor, eps: float, *, save: bool, drop_hidden: Optional[ops.Dropout] = None,
+                  owns_residual: bool = False):
     """bert_model.py:436-453 (BertIntermediate + BertOutput).  Returns (y16, y32, saved)."""
     M, H, dev = x16.shape[0], x16.shape[1], x16.device
     inter = p.w1.shape[0]
     h = torch.empty(M, inter, dtype=F16, device=dev)
     dact = torch.empty(M, inter, dtype=F16, device=dev) if save else None
     ops.gemm(x16, p.w1, h, epilogue=ops.EPI_BIAS_GELU, bias=p.bf1, out2=dact)
-    pre = torch.empty(M, H, dtype=F32, device=dev)
-    ops.gemm(h, p.w2, pre, epilogue=ops.EPI_BIAS_RES32, bias=p.bf2, aux=x32, drop=drop_hidden)
+    pre = _out_dense_residual(h, p.w2, p.bf2, x32, drop_hidden, owns_residual)
     mean = torch.empty(M, dtype=F32, device=dev) if save else None
     rstd = torch.empty(M, dtype=F32, device=dev) if save else None
     y32 = torch.empty(M, H, dtype=F32, device=dev)
@@ -167,12 +198,16 @@ def attn_block_bwd(p: AttnWeights, g: AttnWeights, sv: AttnSaved, dy: Tensor, B:
     d_pre, d_den = _ln_bwd(dy, dy2, sv, p.g, g.g, g.b, g.bo, inv_scale)
     ops.gemm(d_den, sv.ctx, g.wo, a_layout=1, b_layout=1, epilogue=ops.EPI_ATOMIC, alpha=inv_scale, k_splits=ops.wgrad_splits(H, H, Mq))
     dctx = torch.empty(Mq, H, dtype=F16, device=dev)
-    ops.gemm(d_den, p.wo, dctx, b_layout=1)
+    fused_delta = Experimental.delta and not cross
+    if fused_delta:
+        ops.gemm_dgrad_delta(d_den, p.wo, sv.ctx, dctx, ws, B, heads, Sq)
+    else:
+        ops.gemm(d_den, p.wo, dctx, b_layout=1)
     dx = torch.empty(Mq, H, dtype=F16, device=dev)
     if not cross:
         dqkv = torch.empty(Mq, 3 * H, dtype=F16, device=dev)
         ops.attn_bwd(sv.q, sv.q, dctx, sv.ctx, sv.lse2, dqkv, dqkv, ws, B, heads, Sq, Sq, q_col0=0, k_col0=H, v_col0=2 * H, dq_col0=0,
-                     dk_col0=H, dv_col0=2 * H, key_bias=key_bias, kv_len=kv_len, drop=sv.drop_attn)
+                     dk_col0=H, dv_col0=2 * H, key_bias=key_bias, kv_len=kv_len, drop=sv.drop_attn, delta_ready=fused_delta)
         ops.colsum(dqkv, g.bqkv, inv_scale)
         ops.gemm(dqkv, sv.x16, g.wqkv, a_layout=1, b_layout=1, epilogue=ops.EPI_ATOMIC, alpha=inv_scale,
                  k_splits=ops.wgrad_splits(3 * H, H, Mq))

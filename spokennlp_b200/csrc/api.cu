@@ -208,14 +208,37 @@ int b200_gemm_f16_drop(const void* A, int lda, const void* B, int ldb, int M, in
                    make_drop(seed, site, p), stream);
 }
 
+int b200_gemm_f16_resadd(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias, float* out, int ld_out,
+                         const uint32_t* seed, unsigned site, float p, int stream_k, void* stream) {
+  if (p < 0.f || p >= 1.f) return fail(B200_ERR_SHAPE, "gemm_resadd: p must be in [0,1)");
+  if (g_gemm_impl.load() != 2) return fail(B200_ERR_SHAPE, "gemm_resadd: needs the 2-CTA kernel");
+  // k_splits = -1 selects the stream-K schedule inside the kernel (GemmArgs)
+  return gemm_impl(A, lda, 0, B, ldb, 0, M, N, K, EPI_RESADD, bias, nullptr, 0, out, ld_out, B200_DT_F32, nullptr, 0, nullptr,
+                   stream_k ? -1 : 1, make_drop(seed, site, p), stream);
+}
+
+int b200_gemm_f16_dgrad_delta(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const void* ctx, int ld_ctx, void* out,
+                              int ld_out, float* delta, int heads, int Sq, void* stream) {
+  if (!delta || heads <= 0 || Sq <= 0 || N != heads * 64 || (M % Sq))
+    return fail(B200_ERR_SHAPE, "gemm_dgrad_delta: need delta, N == heads*64 and M %% Sq == 0 (M=%d N=%d heads=%d Sq=%d)", M, N, heads, Sq);
+  if (g_gemm_impl.load() != 2) return fail(B200_ERR_SHAPE, "gemm_dgrad_delta: needs the 2-CTA kernel");
+  // delta and Sq travel in the out2 / ld_out2 slots (GemmArgs)
+  return gemm_impl(A, lda, 0, B, ldb, 1, M, N, K, EPI_STORE_DELTA, nullptr, ctx, ld_ctx, out, ld_out, B200_DT_F16, delta, Sq, nullptr, 1,
+                   kNoDrop, stream);
+}
+
 static int gemm_impl(const void* A, int lda, int a_layout, const void* B, int ldb, int b_layout, int M, int N, int K, int epilogue,
                      const float* bias, const void* aux, int ld_aux, void* out, int ld_out, int out_dtype, void* out2, int ld_out2,
                      const float* alpha, int k_splits, DropCfg drop, void* stream) {
   if (M <= 0 || N <= 0 || K <= 0) return fail(B200_ERR_SHAPE, "gemm: empty problem %dx%dx%d", M, N, K);
   if ((N % 4) || (ld_out % 4)) return fail(B200_ERR_SHAPE, "gemm: N and ld_out must be multiples of 4 (N=%d ld_out=%d)", N, ld_out);
   if (!A || !B || !out) return fail(B200_ERR_SHAPE, "gemm: null operand");
-  const bool needs_bias = epilogue == EPI_BIAS || epilogue == EPI_BIAS_GELU || epilogue == EPI_BIAS_RES || epilogue == EPI_BIAS_RES32;
-  const bool needs_aux = epilogue == EPI_BIAS_RES || epilogue == EPI_DGELU || epilogue == EPI_ADD || epilogue == EPI_BIAS_RES32;
+  const bool needs_bias = epilogue == EPI_BIAS || epilogue == EPI_BIAS_GELU || epilogue == EPI_BIAS_RES || epilogue == EPI_BIAS_RES32 ||
+                          epilogue == EPI_RESADD;
+  const bool needs_aux = epilogue == EPI_BIAS_RES || epilogue == EPI_DGELU || epilogue == EPI_ADD || epilogue == EPI_BIAS_RES32 ||
+                         epilogue == EPI_STORE_DELTA;
+  if ((epilogue == EPI_RESADD || epilogue == EPI_STORE_DELTA) && g_gemm_impl.load() != 2)
+    return fail(B200_ERR_SHAPE, "gemm: epilogue %d exists in the 2-CTA kernel only", epilogue);
   if (needs_bias && !bias) return fail(B200_ERR_SHAPE, "gemm: epilogue %d needs bias", epilogue);
   if (needs_aux && (!aux || (ld_aux % 4))) return fail(B200_ERR_SHAPE, "gemm: epilogue %d needs aux with ld%%4==0", epilogue);
   if (k_splits > 1 && epilogue != EPI_ATOMIC) return fail(B200_ERR_SHAPE, "gemm: split-K only with the atomic epilogue");
@@ -235,10 +258,11 @@ static int gemm_impl(const void* A, int lda, int a_layout, const void* B, int ld
     mp.aux = mp.out;
     mp.out2 = mp.out;
     if (epilogue == EPI_BIAS_GELU && out2 && (rc = get_tmap(out2, M, N, ld_out2, 32, &mp.out2))) return rc;
-    if ((needs_aux || out2) && ((N % 8) || (needs_aux && (ld_aux * (epilogue == EPI_BIAS_RES32 ? 4 : 2)) % 16) || (out2 && (ld_out2 % 8)) ||
-                                (needs_aux && (reinterpret_cast<uintptr_t>(aux) & 15)) || (out2 && (reinterpret_cast<uintptr_t>(out2) & 15))))
+    const bool has_out2 = out2 && epilogue != EPI_STORE_DELTA;       // (EPI_STORE_DELTA keeps its fp32 row statistic in the out2 slot)
+    if ((needs_aux || has_out2) && ((N % 8) || (needs_aux && (ld_aux * (epilogue == EPI_BIAS_RES32 ? 4 : 2)) % 16) || (has_out2 && (ld_out2 % 8)) ||
+                                (needs_aux && (reinterpret_cast<uintptr_t>(aux) & 15)) || (has_out2 && (reinterpret_cast<uintptr_t>(out2) & 15))))
       return fail(B200_ERR_SHAPE, "gemm: aux / out2 need N %% 8 == 0 and 16-byte aligned rows");
-    GemmArgs g2{M, N, K, k_splits > 0 ? k_splits : 1, bias, static_cast<const __half*>(aux), ld_aux, out, ld_out,
+    GemmArgs g2{M, N, K, (epilogue == EPI_RESADD && k_splits == -1) ? -1 : (k_splits > 0 ? k_splits : 1), bias, static_cast<const __half*>(aux), ld_aux, out, ld_out,
                 static_cast<__half*>(out2), ld_out2, alpha, drop, g_gemm_dbg.load()};
     switch (a_layout * 1000 + b_layout * 100 + epilogue * 10 + out_dtype) {
       case 0 * 1000 + 0 * 100 + EPI_STORE * 10 + B200_DT_F16: return launch_gemm2<BN, 0, 0, EPI_STORE, __half>(mp, g2, s);
@@ -252,6 +276,8 @@ static int gemm_impl(const void* A, int lda, int a_layout, const void* B, int ld
       case 0 * 1000 + 1 * 100 + EPI_ADD * 10 + B200_DT_F16: return launch_gemm2<BN, 0, 1, EPI_ADD, __half>(mp, g2, s);
       case 0 * 1000 + 1 * 100 + EPI_DGELU * 10 + B200_DT_F16: return launch_gemm2<BN, 0, 1, EPI_DGELU, __half>(mp, g2, s);
       case 1 * 1000 + 1 * 100 + EPI_ATOMIC * 10 + B200_DT_F32: return launch_gemm2<BN, 1, 1, EPI_ATOMIC, float>(mp, g2, s);
+      case 0 * 1000 + 0 * 100 + EPI_RESADD * 10 + B200_DT_F32: return launch_gemm2<BN, 0, 0, EPI_RESADD, float>(mp, g2, s);
+      case 0 * 1000 + 1 * 100 + EPI_STORE_DELTA * 10 + B200_DT_F16: return launch_gemm2<BN, 0, 1, EPI_STORE_DELTA, __half>(mp, g2, s);
       default:
         return fail(B200_ERR_SHAPE, "gemm: unsupported (a_layout=%d, b_layout=%d, epilogue=%d, out_dtype=%d)", a_layout, b_layout,
                     epilogue, out_dtype);

@@ -33,6 +33,11 @@ enum : int {
   EPI_ADD = 5,        // out = acc + aux[m,n]
   EPI_ATOMIC = 6,     // out(fp32) += alpha * acc   (split-K reduction with red.global.add)
   EPI_BIAS_RES32 = 7, // out = acc + bias[n] + aux32[m,n]   (fp32 residual stream)
+  // gemm2 only, opt-in:
+  EPI_RESADD = 8,     // out(fp32) += drop(acc + bias[n])  — out already holds the residual; TMA reduce-add, so the epilogue reads no
+                      // aux at all and a tile may be finished by several CTA pairs (stream-K schedule, GemmArgs::k_splits = -1)
+  EPI_STORE_DELTA = 9,// out = acc (fp16) and delta[b,h,q] = sum_d out[row, 64h+d] * aux[row, 64h+d]  (attention-backward row statistic
+                      // fused into the output-projection dgrad; aux = the forward's context, row = b*delta_S + q)
 };
 
 struct GemmArgs {
@@ -49,6 +54,10 @@ struct GemmArgs {
   DropCfg drop;         // dropout on (acc + bias) before the residual is added (EPI_BIAS_RES / EPI_BIAS_RES32, gemm2 only)
   int dbg;              // measurement knobs (gemm2 only): 1 skip A loads, 2 skip B loads, 4 skip MMA issue, 8 skip epilogue stores,
                         // bits 8..15: L2 prefetch distance in K blocks
+  // The opt-in epilogues reuse fields they do not otherwise need, so that this struct — and with it the machine code of
+  // every round-1 kernel — stays exactly as validated (tools/sass_diff.py):
+  //   EPI_RESADD      : k_splits == -1 selects the stream-K schedule (equal share of K blocks per CTA pair)
+  //   EPI_STORE_DELTA : out2 (as float*) = delta [B, N/64, ld_out2], ld_out2 = tokens per sequence (Sq)
 };
 
 template <int BN>

@@ -102,11 +102,15 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
   constexpr int G2_STAGES = S::STAGES;
   constexpr bool OUT32 = sizeof(OutT) == 4;
   constexpr int CW = OUT32 ? 32 : 64;                 // accumulator columns per staging slab (128 B of output per row)
-  constexpr bool HAS_AUX = EPI == EPI_BIAS_RES || EPI == EPI_BIAS_RES32 || EPI == EPI_DGELU || EPI == EPI_ADD;
-  constexpr bool HAS_BIAS = EPI == EPI_BIAS || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_RES || EPI == EPI_BIAS_RES32;
+  constexpr bool RESADD = EPI == EPI_RESADD;         // out32 += drop(acc + bias): residual already in `out`, TMA reduce-add
+  constexpr bool DELTA = EPI == EPI_STORE_DELTA;      // out16 = acc, delta[b,h,q] = <out row, aux row> per 64-column head
+  constexpr bool HAS_AUX = EPI == EPI_BIAS_RES || EPI == EPI_BIAS_RES32 || EPI == EPI_DGELU || EPI == EPI_ADD || DELTA;
+  constexpr bool HAS_BIAS = EPI == EPI_BIAS || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_RES || EPI == EPI_BIAS_RES32 || RESADD;
   static_assert(!(EPI == EPI_BIAS_RES32) || OUT32, "fp32 residual stream implies fp32 output");
   static_assert(!(EPI == EPI_BIAS_RES || EPI == EPI_DGELU || EPI == EPI_ADD || EPI == EPI_BIAS_GELU) || !OUT32, "fp16-aux epilogues write fp16");
   static_assert(!(EPI == EPI_ATOMIC) || OUT32, "split-K reduction is fp32");
+  static_assert(!RESADD || OUT32, "the residual stream is fp32");
+  static_assert(!DELTA || !OUT32, "the fused row statistic rides on the fp16 store (one 64-column chunk = one head)");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -129,6 +133,14 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
   const int splits = g.k_splits > 0 ? g.k_splits : 1;
   const int kb_per_split = (k_blocks + splits - 1) / splits;
   const int units = m_tiles * n_tiles * splits;
+  // Stream-K (EPI_RESADD with g.k_splits == -1): the K blocks of all tiles form one tile-major list that is cut into equal
+  // contiguous shares, one per CTA pair; a pair therefore walks (tail of a tile, whole tiles, head of a tile) segments and
+  // every segment is reduce-added into the output, so no tile waits for a straggler round (192 tiles on 74 pairs).
+  const bool sk = RESADD && g.k_splits == -1;
+  const long long sk_total = static_cast<long long>(m_tiles) * n_tiles * k_blocks;
+  const int sk_hi = sk ? static_cast<int>(sk_total * (pair + 1) / n_pairs) : 0;
+  const int u_begin = sk ? static_cast<int>(sk_total * pair / n_pairs) : pair;
+  const int u_end = sk ? sk_hi : units;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.a);
@@ -154,6 +166,14 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
   const uint32_t tmem_base = *tmem_slot;
 
   auto decode = [&](int u, int& mt, int& nt, int& kb0, int& kb1) {
+    if (sk) {                                             // u = position in the global K-block list
+      const int t = u / k_blocks;
+      nt = t % n_tiles;
+      mt = t / n_tiles;
+      kb0 = u - t * k_blocks;
+      kb1 = min(k_blocks, kb0 + (sk_hi - u));
+      return;
+    }
     const int sp = u % splits;
     const int t = u / splits;
     nt = t % n_tiles;
@@ -161,13 +181,14 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
     kb0 = sp * kb_per_split;
     kb1 = min(k_blocks, kb0 + kb_per_split);
   };
+  auto next_unit = [&](int u, int kb0, int kb1) { return sk ? u + (kb1 - kb0) : u + n_pairs; };
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int u = pair; u < units; u += n_pairs) {
-        int mt, nt, kb0, kb1;
+      int mt, nt, kb0, kb1;
+      for (int u = u_begin; u < u_end; u = next_unit(u, kb0, kb1)) {
         decode(u, mt, nt, kb0, kb1);
         const int m0 = mt * G2_BM + static_cast<int>(rank) * 128;          // this CTA's A rows
         const int n0 = nt * BN + static_cast<int>(rank) * (BN / 2);        // this CTA's half of the B tile
@@ -206,8 +227,8 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
     if (leader) {
       constexpr uint32_t idesc = make_idesc_f16(G2_BM, BN, A_MN, B_MN);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int u = pair; u < units; u += n_pairs) {
-        int mt, nt, kb0, kb1;
+      int mt, nt, kb0, kb1;
+      for (int u = u_begin; u < u_end; u = next_unit(u, kb0, kb1)) {
         decode(u, mt, nt, kb0, kb1);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -252,12 +273,13 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
     uint32_t acc = 0, acc_phase = 0, out_uses = 0;
     constexpr int NCH = BN / CW / 2;                      // chunks per warp per tile
     constexpr int AUX_ESZ = EPI == EPI_BIAS_RES32 ? 4 : 2;
+    int seg_kb0 = 0, seg_kb1 = 0;                         // K-block range of the unit last decoded by tile_origin
     auto tile_origin = [&](int u, int& row0, int& col0, bool& has_data) {
-      int mt, nt, kb0, kb1;
-      decode(u, mt, nt, kb0, kb1);
+      int mt, nt;
+      decode(u, mt, nt, seg_kb0, seg_kb1);
       row0 = mt * G2_BM + static_cast<int>(rank) * 128 + q * 32;      // first output row of this warp
       col0 = nt * BN + half * (BN / 2);                               // first output column of this warp
-      has_data = kb1 > kb0;
+      has_data = seg_kb1 > seg_kb0;
     };
     // 128 bytes of this thread's aux row for the chunk starting at column gc0 (zeros outside the matrix)
     auto load_aux = [&](uint4 (&dst)[8], int row, int gc0) {
@@ -270,16 +292,20 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
       }
     };
     uint4 aux_next[8];
-    if (HAS_AUX && pair < units) {
+    if (HAS_AUX && u_begin < u_end) {
       int r0, c0;
       bool hd;
-      tile_origin(pair, r0, c0, hd);
+      tile_origin(u_begin, r0, c0, hd);
       load_aux(aux_next, r0 + lane, c0);
     }
-    for (int u = pair; u < units; u += n_pairs) {
+    int kb0 = 0, kb1 = 0;
+    for (int u = u_begin; u < u_end; u = next_unit(u, kb0, kb1)) {
       int row0, col0;
       bool has_data;
       tile_origin(u, row0, col0, has_data);
+      kb0 = seg_kb0;
+      kb1 = seg_kb1;
+      const bool add_bias = !RESADD || kb0 == 0;          // a tile finished by several pairs gets its bias exactly once
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
@@ -310,7 +336,7 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
         float f[CW];
 #pragma unroll
         for (int i = 0; i < CW; ++i) f[i] = __uint_as_float(v[i]) * alpha;
-        if (HAS_BIAS) {
+        if (HAS_BIAS && add_bias) {
 #pragma unroll
           for (int i = 0; i < CW / 4; ++i) {
             float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -318,7 +344,7 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
             f[4 * i] += b4.x; f[4 * i + 1] += b4.y; f[4 * i + 2] += b4.z; f[4 * i + 3] += b4.w;
           }
         }
-        if ((EPI == EPI_BIAS_RES32 || EPI == EPI_BIAS_RES) && g.drop.seed_base != nullptr) {
+        if ((EPI == EPI_BIAS_RES32 || EPI == EPI_BIAS_RES || RESADD) && g.drop.seed_base != nullptr) {
           // hidden dropout of BertSelfOutput / BertOutput (bert_model.py:373,451): applied to dense(x)+bias, before the residual
           const uint32_t seed = drop_seed(g.drop);
           const uint32_t e0 = static_cast<uint32_t>(row0 + lane) * static_cast<uint32_t>(g.N) + static_cast<uint32_t>(gc0);
@@ -330,7 +356,7 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
             f[2 * i + 1] *= m1;
           }
         }
-        if (HAS_AUX) {
+        if (HAS_AUX && !DELTA) {
 #pragma unroll
           for (int ch = 0; ch < 8; ++ch) {
             const uint4 raw = araw[ch];
@@ -389,10 +415,24 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
 #pragma unroll
           for (int k = 0; k < 32; ++k) ow[k] = __float_as_uint(f[k]);
         } else {
+          float dsum = 0.f;
 #pragma unroll
           for (int k = 0; k < 32; ++k) {
             const __half2 hv = __floats2half2_rn(f[2 * k], f[2 * k + 1]);
             ow[k] = *reinterpret_cast<const uint32_t*>(&hv);
+            if (DELTA) {                                  // the statistic is taken on the ROUNDED output, the values attention backward reads
+              const float2 o2 = __half22float2(hv);
+              const float2 c2 = __half22float2(reinterpret_cast<const __half2*>(araw)[k]);
+              dsum = fmaf(o2.x, c2.x, dsum);
+              dsum = fmaf(o2.y, c2.y, dsum);
+            }
+          }
+          if (DELTA) {                                    // one 64-column chunk is one head: row (b, q), head gc0 / 64
+            const int row = row0 + lane;
+            if (has_data && row < g.M && gc0 < g.N) {
+              const int Sq = g.ld_out2, b = row / Sq;     // delta [B, N/64, Sq] rides in the out2 slot (see GemmArgs)
+              reinterpret_cast<float*>(g.out2)[(static_cast<size_t>(b) * (g.N >> 6) + (gc0 >> 6)) * Sq + (row - b * Sq)] = dsum;
+            }
           }
         }
         // double-buffered slab: the TMA store issued two chunks ago must have finished reading this buffer
@@ -406,7 +446,7 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
         __syncwarp();
         if (lane == 0) {
           if (has_data && !(g.dbg & 8)) {
-            if (EPI == EPI_ATOMIC) tma_reduce_add_2d(&maps.out, os_ptr, gc0, row0);
+            if (EPI == EPI_ATOMIC || RESADD) tma_reduce_add_2d(&maps.out, os_ptr, gc0, row0);
             else tma_store_2d(&maps.out, os_ptr, gc0, row0);
           }
           tma_commit_group();

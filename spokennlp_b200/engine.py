@@ -196,13 +196,15 @@ class EncoderEngine:
         return y16, y32
 
     def layer_forward(self, p: LayerViews, x: Tensor, x32: Tensor, B: int, S: int, key_bias, kv_len, save: bool,
-                      want_probs: bool = False, drop: Optional[DropPlan] = None, index: int = 0):
+                      want_probs: bool = False, drop: Optional[DropPlan] = None, index: int = 0, owns_input: bool = False):
         """One BertLayer (bert_model.py:518-553).  x: fp16 layer input (GEMM operand), x32: the same activations in fp32
         (residual stream: keeping the skip connection un-rounded holds the 12-layer hidden-state error under 1e-3)."""
         d = (lambda k: drop.layer(index, k)) if drop is not None else (lambda k: None)
         a16, a32, sva, probs = attn_block_fwd(p.attn, x, x32, B, S, self.heads, self.eps, key_bias, kv_len, save=save,
-                                              want_probs=want_probs, drop_attn=d(DropPlan.ATTN), drop_hidden=d(DropPlan.ATTN_OUT))
-        y16, y32, svf = ffn_block_fwd(p.ffn, a16, a32, self.eps, save=save, drop_hidden=d(DropPlan.FFN_OUT))
+                                              want_probs=want_probs, drop_attn=d(DropPlan.ATTN), drop_hidden=d(DropPlan.ATTN_OUT),
+                                              owns_residual=owns_input)
+        # a32 (the attention block's fp32 output) is never handed out, so the FFN block always owns its residual
+        y16, y32, svf = ffn_block_fwd(p.ffn, a16, a32, self.eps, save=save, drop_hidden=d(DropPlan.FFN_OUT), owns_residual=True)
         return y16, y32, (LayerSaved(attn=sva, ffn=svf) if save else None), probs
 
     def forward(self, ids, tt, pos, inputs_embeds, key_bias, kv_len, B: int, S: int, *, save: bool,
@@ -214,7 +216,9 @@ class EncoderEngine:
         saved = Saved(B=B, S=S, ids=ids, tt=tt, pos=pos, key_bias=key_bias, kv_len=kv_len, drop_emb=drop_emb) if save else None
         hiddens, probs_all = ([x32] if want_hidden else None), ([] if want_probs else None)
         for i in range(self.L):
-            x, x32, sv, probs = self.layer_forward(self.layer(i), x, x32, B, S, key_bias, kv_len, save, want_probs, drop, i)
+            # a layer input that is also returned as a hidden state must survive the layer (blocks.Experimental.resadd)
+            x, x32, sv, probs = self.layer_forward(self.layer(i), x, x32, B, S, key_bias, kv_len, save, want_probs, drop, i,
+                                                   owns_input=not want_hidden)
             if save:
                 saved.layers.append(sv)
             if want_hidden:

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200enc.so")
 CSRC = os.path.join(_HERE, "csrc")
 
-EPI_STORE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_DGELU, EPI_ADD, EPI_ATOMIC, EPI_BIAS_RES32 = range(8)
+EPI_STORE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_DGELU, EPI_ADD, EPI_ATOMIC, EPI_BIAS_RES32, EPI_RESADD, EPI_STORE_DELTA = range(10)
 DT_F16, DT_F32 = 0, 1
 
 _p, _i, _f, _sz, _ll = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_longlong
@@ -58,8 +58,13 @@ _PROTOS = {
     "b200_set_hyper": [_p, _f, _f, _f, _f, _f, _f, _f, _p],
     "b200_adamw_step_dev": [_p, _p, _p, _p, _p, _sz, _p, _p, _p],
     "b200_adamw_step_dev_zero": [_p, _p, _p, _p, _p, _sz, _p, _p, _p],
+    # opt-in variants (include/b200enc.h, last section)
+    "b200_gemm_f16_resadd": [_p, _i, _p, _i, _i, _i, _i, _p, _p, _i, _p, C.c_uint, _f, _i, _p],
+    "b200_gemm_f16_dgrad_delta": [_p, _i, _p, _i, _i, _i, _i, _p, _i, _p, _i, _p, _i, _i, _p],
+    "b200_attn_bwd_delta_ptr": [_p],
+    "b200_attn_bwd_ext": [_p, _i, _i, _p, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p, C.c_uint, _f, _i, _p],
 }
-_RESTYPE = {"b200_set_gemm_impl": None, "b200_set_gemm_debug": None, "b200_set_sm_limit": None, "b200_last_error": C.c_char_p, "b200_launch_count": _ll, "b200_version": _i, "b200_source_hash": C.c_char_p, "b200_attn_bwd_workspace": _sz, "b200_ponet_workspace": _sz, "b200_ponet_bwd_workspace": _sz}
+_RESTYPE = {"b200_set_gemm_impl": None, "b200_set_gemm_debug": None, "b200_set_sm_limit": None, "b200_last_error": C.c_char_p, "b200_launch_count": _ll, "b200_version": _i, "b200_source_hash": C.c_char_p, "b200_attn_bwd_workspace": _sz, "b200_ponet_workspace": _sz, "b200_ponet_bwd_workspace": _sz, "b200_attn_bwd_delta_ptr": _p}
 
 _lock = threading.Lock()
 _lib = None

@@ -79,6 +79,41 @@ def gemm(a: Tensor, b: Tensor, out: Tensor, *, a_layout: int = 0, b_layout: int 
     return out
 
 
+def gemm_resadd(a: Tensor, b: Tensor, out32: Tensor, bias: Tensor, *, drop: Optional["Dropout"] = None, stream_k: bool = False) -> Tensor:
+    """OPT-IN.  out32[M,N] += dropout(A @ B^T + bias): `out32` holds the fp32 residual on entry and the
+    pre-LayerNorm sum on return (b200_gemm_f16_resadd).  `stream_k` balances N = 768 shapes over the CTA pairs at the price
+    of an fp32 summation order that varies from run to run."""
+    _req(a, torch.float16, "A"), _req(b, torch.float16, "B"), _req(out32, torch.float32, "out32"), _req(bias, torch.float32, "bias")
+    M, K, N = a.shape[0], a.shape[1], b.shape[0]
+    if b.shape[1] != K or tuple(out32.shape) != (M, N) or bias.numel() != N:
+        raise L.B200Error(f"gemm_resadd: shape mismatch A{tuple(a.shape)} B{tuple(b.shape)} out{tuple(out32.shape)} bias{tuple(bias.shape)}")
+    seed, site, p = _drop_args(drop)
+    rc = L.load().b200_gemm_f16_resadd(_ptr(a), a.stride(0), _ptr(b), b.stride(0), M, N, K, _ptr(bias), _ptr(out32), out32.stride(0),
+                                       seed, site, p, 1 if stream_k else 0, _stream())
+    L.check(rc, "b200_gemm_f16_resadd")
+    return out32
+
+
+def attn_bwd_delta_view(workspace: Tensor, B: int, heads: int, Sq: int) -> Tensor:
+    """The [B, heads, Sq] fp32 row statistic at the head of the attention-backward workspace (b200_attn_bwd_delta_ptr)."""
+    return workspace[:B * heads * Sq].view(B, heads, Sq)
+
+
+def gemm_dgrad_delta(dy: Tensor, w: Tensor, ctx: Tensor, dctx: Tensor, workspace: Tensor, B: int, heads: int, Sq: int) -> Tensor:
+    """OPT-IN.  dctx = dy @ W (the output projection's dgrad, W row-major [out, in]) and, in the same epilogue,
+    delta[b,h,q] = <dctx row, ctx row> per head, written where `attn_bwd(..., delta_ready=True)` expects it."""
+    for t, n in ((dy, "dy"), (w, "W"), (ctx, "ctx"), (dctx, "dctx")):
+        _req(t, torch.float16, n)
+    M, K, N = dy.shape[0], dy.shape[1], w.shape[1]
+    if w.shape[0] != K or tuple(dctx.shape) != (M, N) or tuple(ctx.shape) != (M, N) or M != B * Sq or N != heads * 64:
+        raise L.B200Error(f"gemm_dgrad_delta: shape mismatch dy{tuple(dy.shape)} W{tuple(w.shape)} ctx{tuple(ctx.shape)} dctx{tuple(dctx.shape)}")
+    delta = attn_bwd_delta_view(_req(workspace, torch.float32, "workspace"), B, heads, Sq)
+    rc = L.load().b200_gemm_f16_dgrad_delta(_ptr(dy), dy.stride(0), _ptr(w), w.stride(0), M, N, K, _ptr(ctx), ctx.stride(0), _ptr(dctx),
+                                            dctx.stride(0), _ptr(delta), heads, Sq, _stream())
+    L.check(rc, "b200_gemm_f16_dgrad_delta")
+    return dctx
+
+
 def set_gemm_impl(impl: int) -> None:
     """2 (default): 2-CTA cta_group::2 GEMM with TMA epilogue; 1: single-CTA kernel (A/B measurements, tests)."""
     L.load().b200_set_gemm_impl(int(impl))
@@ -240,10 +275,19 @@ def attn_bwd_workspace(B: int, heads: int, Sq: int, device) -> Tensor:
 
 def attn_bwd(q: Tensor, kv: Tensor, dctx: Tensor, ctx: Tensor, lse2: Tensor, dq: Tensor, dkv: Tensor, workspace: Tensor,
              B: int, heads: int, Sq: int, Sk: int, *, q_col0: int, k_col0: int, v_col0: int, dq_col0: int, dk_col0: int,
-             dv_col0: int, key_bias: Optional[Tensor] = None, kv_len: Optional[Tensor] = None, drop=None) -> None:
+             dv_col0: int, key_bias: Optional[Tensor] = None, kv_len: Optional[Tensor] = None, drop=None,
+             delta_ready: bool = False) -> None:
+    """`delta_ready` (opt-in): the workspace already holds rowsum(dO o O) from `gemm_dgrad_delta`; skip that pass."""
     for t, n in ((q, "q"), (kv, "kv"), (dctx, "dctx"), (ctx, "ctx"), (dq, "dq"), (dkv, "dkv")):
         _req(t, torch.float16, n)
     seed, site, p = _drop_args(drop)
+    if delta_ready:
+        rc = L.load().b200_attn_bwd_ext(_ptr(q), q.stride(0), q_col0, _ptr(kv), kv.stride(0), k_col0, v_col0, _ptr(dctx), dctx.stride(0),
+                                        _ptr(ctx), ctx.stride(0), _ptr(key_bias), _ptr(kv_len), _ptr(lse2), _ptr(workspace), _ptr(dq),
+                                        dq.stride(0), dq_col0, _ptr(dkv), dkv.stride(0), dk_col0, dv_col0, B, heads, Sq, Sk, seed, site, p,
+                                        1, _stream())
+        L.check(rc, "b200_attn_bwd_ext")
+        return
     rc = L.load().b200_attn_bwd_drop(_ptr(q), q.stride(0), q_col0, _ptr(kv), kv.stride(0), k_col0, v_col0, _ptr(dctx), dctx.stride(0),
                                      _ptr(ctx), ctx.stride(0), _ptr(key_bias), _ptr(kv_len), _ptr(lse2), _ptr(workspace), _ptr(dq),
                                      dq.stride(0), dq_col0, _ptr(dkv), dkv.stride(0), dk_col0, dv_col0, B, heads, Sq, Sk, seed, site, p,
