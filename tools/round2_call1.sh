@@ -1,0 +1,22 @@
+#!/bin/bash
+# First GPU call of round 2 (one B200, ~6 min of box time):
+#   gpurun --timeout 600 -- 'bash tools/round2_call1.sh'
+# 1. the default GPU suite, 2. the opt-in variants' tests, each node in its own process (a trapped kernel cannot hide the
+# others), 3. kernel-level A/B, 4. bench.py with each variant set on the same box.  Everything lands in gpurun_out/.
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests -m gpu -x -q > gpurun_out/r2_gpu_suite.log 2>&1; tail -3 gpurun_out/r2_gpu_suite.log
+B200_RUN_EXPERIMENTAL=1 timeout 400 python tools/gpu_isolated.py tests/test_gpu_experimental.py --timeout 60 > gpurun_out/r2_experimental.log 2>&1
+grep -E "^(PASS|FAIL)|passed" gpurun_out/r2_experimental.log | tail -30
+timeout 120 python tools/variants_ab.py > gpurun_out/r2_variants_ab.jsonl 2> gpurun_out/r2_variants_ab.err; cat gpurun_out/r2_variants_ab.jsonl
+for exp in "" "resadd" "delta" "resadd,delta" "streamk,delta"; do
+  tag=${exp//,/_}; tag=${tag:-default}
+  B200_EXP="$exp" timeout 150 python bench.py --no-cpu-baseline --steps 20 > gpurun_out/r2_bench_$tag.json 2> gpurun_out/r2_bench_$tag.err
+  python - "$tag" <<'PY'
+import json, sys
+try:
+    d = json.loads(open(f"gpurun_out/r2_bench_{sys.argv[1]}.json").read().strip().splitlines()[-1])
+    print(sys.argv[1], round(d["value"], 1), "seq/s", round(d["ms_per_step"], 3), "ms  e2e", round(d["e2e"]["value"], 1), "loss", d["final_loss"], d["config"]["opt_in_variants"])
+except Exception as e:
+    print(sys.argv[1], "no result:", e)
+PY
+done
