@@ -45,7 +45,8 @@ struct AttnBwd3Smem {
   static constexpr int TOTAL = OFF_BAR + 256 + 1024;
 };
 
-template <bool DROP>
+// ELECT (opt-in): one `s_free` / `ds_full` arrival per softmax warp instead of one per thread (see attn_fwd3.cuh).
+template <bool DROP, bool ELECT = false>
 __global__ void __launch_bounds__(ATTB_THREADS, 1)
 attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                  const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmDQ,
@@ -84,9 +85,9 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
     for (int g = 0; g < 2; ++g) {
       mbar_init(&s_full[g], 1);
-      mbar_init(&s_free[g], 128);
+      mbar_init(&s_free[g], ELECT ? 4 : 128);
     }
-    mbar_init(ds_full, 256);
+    mbar_init(ds_full, ELECT ? 8 : 256);
     mbar_init(grad_done, 1);
     fence_mbar_init();
   }
@@ -302,7 +303,12 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tmem_ld_x32(tmem + lane_addr + 128 + g * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&dp[32]));
         tmem_wait_ld();
         tc_fence_before();
-        mbar_arrive(&s_free[g]);                  // the tensor core may overwrite S_g / dP_g with the next block now
+        if (ELECT) {                              // the tensor core may overwrite S_g / dP_g with the next block now
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_free[g]);
+        } else {
+          mbar_arrive(&s_free[g]);
+        }
         // masked keys: turn their scores into -inf (P = 0, dS = 0)
         if (it.general_bias) {
 #pragma unroll
@@ -358,7 +364,12 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         fence_proxy_async_smem();
         tc_fence_before();
-        mbar_arrive(ds_full);
+        if (ELECT) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(ds_full);
+        } else {
+          mbar_arrive(ds_full);
+        }
         // dQ of the previous block sits in the other TMEM buffer: reduce it into HBM off the critical path
         if (i > 0) drain_dq(ir - 1, i - 1);
       }

@@ -43,7 +43,9 @@ struct AttnFwd3Smem {
   static constexpr int TOTAL = OFF_BAR + 256 + 1024;
 };
 
-template <bool DROP>
+// ELECT (opt-in): the softmax warps signal `s_free` / `p_full` with ONE arrival per warp (after a warp-level
+// sync) instead of one per thread — 4 arrivals per barrier phase instead of 128 same-address mbarrier operations.
+template <bool DROP, bool ELECT = false>
 __global__ void __launch_bounds__(ATTP_THREADS, 1)
 attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                  const __grid_constant__ CUtensorMap tmO, const AttnFwdArgs a) {
@@ -80,8 +82,8 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 2);
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_free[i], 128);
-      mbar_init(&p_full[i], 128);
+      mbar_init(&s_free[i], ELECT ? 4 : 128);
+      mbar_init(&p_full[i], ELECT ? 4 : 128);
       mbar_init(&o_full[i], 1);
     }
     mbar_init(b_go, 1);
@@ -249,7 +251,12 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tmem_ld_x32(tmem + lane_addr + x * 128 + 96, *reinterpret_cast<uint32_t(*)[32]>(&v[96]));
         tmem_wait_ld();
         tc_fence_before();
-        mbar_arrive(&s_free[x]);                  // the tensor core may overwrite S_x with the next block now
+        if (ELECT) {                              // the tensor core may overwrite S_x with the next block now
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_free[x]);
+        } else {
+          mbar_arrive(&s_free[x]);
+        }
         if (x == 0 && t == 0 && tg == 0) mbar_arrive(b_go);
         // ---- masked keys (only blocks that have any)
         if (it.general_bias) {
@@ -322,7 +329,12 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         m = (m_use == 0.f && m_new == NEG_INF) ? NEG_INF : m_use;
         fence_proxy_async_smem();
         tc_fence_before();
-        mbar_arrive(&p_full[x]);
+        if (ELECT) {                              // every lane has fenced its own P rows; one lane publishes the warp's 32 rows
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[x]);
+        } else {
+          mbar_arrive(&p_full[x]);
+        }
       }
       // ---------------------------------------------------------------- finalise: O / l -> ctx, LSE
       mbar_wait(&o_full[x], (t - 1) & 1);

@@ -64,7 +64,7 @@ _PROTOS = {
     "b200_attn_bwd_delta_ptr": [_p],
     "b200_attn_bwd_ext": [_p, _i, _i, _p, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p, C.c_uint, _f, _i, _p],
 }
-_RESTYPE = {"b200_set_gemm_impl": None, "b200_set_gemm_debug": None, "b200_set_sm_limit": None, "b200_last_error": C.c_char_p, "b200_launch_count": _ll, "b200_version": _i, "b200_source_hash": C.c_char_p, "b200_attn_bwd_workspace": _sz, "b200_ponet_workspace": _sz, "b200_ponet_bwd_workspace": _sz, "b200_attn_bwd_delta_ptr": _p}
+_RESTYPE = {"b200_set_gemm_impl": None, "b200_set_gemm_debug": None, "b200_set_sm_limit": None, "b200_set_attn_variant": None, "b200_last_error": C.c_char_p, "b200_launch_count": _ll, "b200_version": _i, "b200_source_hash": C.c_char_p, "b200_attn_bwd_workspace": _sz, "b200_ponet_workspace": _sz, "b200_ponet_bwd_workspace": _sz, "b200_attn_bwd_delta_ptr": _p}
 
 _lock = threading.Lock()
 _lib = None
@@ -142,6 +142,7 @@ def load() -> C.CDLL:
             lib.b200_set_gemm_impl.argtypes = [_i]
             lib.b200_set_gemm_debug.argtypes = [_i]
             lib.b200_set_sm_limit.argtypes = [_i]
+            lib.b200_set_attn_variant.argtypes = [_i]
             _lib = lib
     return _lib
 

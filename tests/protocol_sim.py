@@ -116,7 +116,7 @@ def wait(bar: Bar, k: int):
 
 
 # ======================================================================================================= forward (attn_fwd3.cuh)
-def simulate_fwd(items, seed: int = 0, mutate: str = ""):
+def simulate_fwd(items, seed: int = 0, mutate: str = "", elect: bool = False):
     """items: list of (n_blocks, tileB) processed by ONE CTA in this order.  `mutate` plants a protocol bug (self-test of
     the checker): "no_k_empty" (the producer does not wait for the K stage to be released), "no_s_free" (the next score
     tile is issued without waiting for the softmax warps to have read the current one)."""
@@ -128,8 +128,9 @@ def simulate_fwd(items, seed: int = 0, mutate: str = ""):
     v_full = [Bar(f"v_full{i}", 1) for i in range(2)]
     v_empty = [Bar(f"v_empty{i}", 2) for i in range(2)]
     s_full = [Bar(f"s_full{x}", 1) for x in range(2)]
-    s_free = [Bar(f"s_free{x}", 128) for x in range(2)]
-    p_full = [Bar(f"p_full{x}", 128) for x in range(2)]
+    W = 1 if elect else 32            # arrivals a softmax warp contributes: one elected lane (ELECT kernels) or every lane
+    s_free = [Bar(f"s_free{x}", 4 * W) for x in range(2)]
+    p_full = [Bar(f"p_full{x}", 4 * W) for x in range(2)]
     o_full = [Bar(f"o_full{x}", 1) for x in range(2)]
     b_go = Bar("b_go", 1)
     Q = [Buf(f"Q{i}") for i in range(2)]
@@ -231,7 +232,7 @@ def simulate_fwd(items, seed: int = 0, mutate: str = ""):
                 yield wait(s_full[x], t)
                 S[x].read_now(("S", it, j))                     # tcgen05.ld + wait::ld
                 yield None
-                s_free[x].arrive(32)
+                s_free[x].arrive(W)
                 if x == 0 and t == 0 and w == 0:
                     b_go.arrive()
                 if j > 0:
@@ -242,7 +243,7 @@ def simulate_fwd(items, seed: int = 0, mutate: str = ""):
                     P[x].write(("P", it, j))                    # (all four warps write their own rows; one tag is enough)
                 else:
                     assert P[x].readers == 0, f"P{x} written while the previous P.V is still reading it"
-                p_full[x].arrive(32)
+                p_full[x].arrive(W)
                 t += 1
             yield wait(o_full[x], t - 1)
             O[x].read_now(("O", it, nb))
@@ -259,7 +260,7 @@ def simulate_fwd(items, seed: int = 0, mutate: str = ""):
 
 
 # ======================================================================================================= backward (attn_bwd3.cuh)
-def simulate_bwd(items, nq: int, seed: int = 0, mutate: str = ""):
+def simulate_bwd(items, nq: int, seed: int = 0, mutate: str = "", elect: bool = False):
     """items: list of booleans (True = live key block, False = dead block) processed by ONE CTA; nq query blocks each.
     `mutate`: "no_kv_empty" (K / V of the next item loaded without waiting for the last gradient MMAs), "two_stages"
     (the producer believes the Q / dO ring has its 3 stages while the consumer side releases only what it used — modelled
@@ -270,8 +271,9 @@ def simulate_bwd(items, nq: int, seed: int = 0, mutate: str = ""):
     qdo_full = [Bar(f"qdo_full{i}", 1) for i in range(NST)]
     qdo_empty = [Bar(f"qdo_empty{i}", 1) for i in range(NST)]
     s_full = [Bar(f"s_full{g}", 1) for g in range(2)]
-    s_free = [Bar(f"s_free{g}", 128) for g in range(2)]
-    ds_full, grad_done = Bar("ds_full", 256), Bar("grad_done", 1)
+    W = 1 if elect else 32
+    s_free = [Bar(f"s_free{g}", 4 * W) for g in range(2)]
+    ds_full, grad_done = Bar("ds_full", 8 * W), Bar("grad_done", 1)
     KV = Buf("KV")
     QDO = [Buf(f"QdO{i}") for i in range(NST)]
     SD = [Buf(f"S/dP{g}") for g in range(2)]
@@ -355,7 +357,7 @@ def simulate_bwd(items, nq: int, seed: int = 0, mutate: str = ""):
                 yield wait(s_full[g], ir)
                 SD[g].read_now(("S", it, i))
                 yield None
-                s_free[g].arrive(32)
+                s_free[g].arrive(W)
                 yield None                                       # exp / dS math
                 if i > 0 and mutate != "two_stages":
                     yield wait(grad_done, ir - 1)
@@ -363,7 +365,7 @@ def simulate_bwd(items, nq: int, seed: int = 0, mutate: str = ""):
                     PDS.write(("PdS", it, i))
                 else:
                     assert PDS.readers == 0, "P / dS written while gradient MMAs still read them"
-                ds_full.arrive(32)
+                ds_full.arrive(W)
                 if i > 0:
                     DQ[(ir - 1) & 1].read_now(("dQ", it, i - 1))
                     yield None

@@ -94,6 +94,43 @@ def test_dgrad_delta_matches_the_plain_dgrad_and_the_separate_row_statistic(B, S
     assert torch.isnan(ws[B * heads * S:]).all()                                           # nothing else in the workspace was touched
 
 
+@pytest.mark.parametrize("B,S,heads,masked,p", [(2, 256, 2, False, 0.0), (3, 512, 12, True, 0.0), (2, 300, 4, True, 0.1), (32, 512, 12, False, 0.1)])
+def test_attention_with_warp_elected_arrivals_matches_the_default_kernels(B, S, heads, masked, p):
+    """Same arithmetic, different hand-off signalling: context, LSE, dK and dV must be bit-identical; dQ is an fp32 reduce-add
+    over key blocks whose order varies from run to run in both variants."""
+    ops = _ops()
+    from spokennlp_b200 import lib
+    H, M = heads * 64, B * S
+    qkv = _rand16(M, 3 * H, seed=11)
+    dctx = _rand16(M, H, seed=12, scale=0.1)
+    mask = torch.ones(B, S, dtype=torch.long, device="cuda")
+    if masked:
+        mask[1, S - 77:] = 0
+    key_bias, kv_len = ops.mask_to_bias(mask)
+    seed = torch.tensor([4321], dtype=torch.int32, device="cuda")
+    drop = ops.Dropout(seed, 9, p) if p > 0 else None
+    cols = dict(q_col0=0, k_col0=H, v_col0=2 * H)
+    res = []
+    try:
+        for variant in (0, 1):
+            lib.load().b200_set_attn_variant(variant)
+            ctx = torch.empty(M, H, dtype=torch.float16, device="cuda")
+            lse = torch.empty(B, heads, S, device="cuda")
+            ops.attn_fwd(qkv, qkv, ctx, B, heads, S, S, key_bias=key_bias, kv_len=kv_len, lse2=lse, drop=drop, **cols)
+            dqkv = torch.zeros_like(qkv)
+            ws = ops.attn_bwd_workspace(B, heads, S, "cuda")
+            ops.attn_bwd(qkv, qkv, dctx, ctx, lse, dqkv, dqkv, ws, B, heads, S, S, dq_col0=0, dk_col0=H, dv_col0=2 * H,
+                         key_bias=key_bias, kv_len=kv_len, drop=drop, **cols)
+            torch.cuda.synchronize()
+            res.append((ctx, lse, dqkv))
+    finally:
+        lib.load().b200_set_attn_variant(0)
+    (c0, l0, g0), (c1, l1, g1) = res
+    assert torch.equal(c0, c1) and torch.equal(l0, l1)
+    assert torch.equal(g0[:, H:], g1[:, H:])                       # dK, dV
+    assert _rel(g1[:, :H], g0[:, :H]) < 2e-3                       # dQ: fp16 of an fp32 sum taken in a varying order
+
+
 def _tiny_step(variants: str, dropout: float):
     from transformers import BertConfig
     from spokennlp_b200.blocks import Experimental
@@ -123,7 +160,7 @@ def _tiny_step(variants: str, dropout: float):
 
 
 @pytest.mark.parametrize("dropout", [0.0, 0.1])
-@pytest.mark.parametrize("variants", ["resadd", "delta", "resadd,delta", "streamk,delta"])
+@pytest.mark.parametrize("variants", ["resadd", "delta", "resadd,delta", "streamk,delta", "elect", "resadd,delta,elect"])
 def test_training_step_with_variants_matches_the_default_path(variants, dropout):
     _ops()
     loss0, g0 = _tiny_step("", dropout)
@@ -133,4 +170,4 @@ def test_training_step_with_variants_matches_the_default_path(variants, dropout)
     else:
         assert abs(loss1 - loss0) < 1e-5
     # resadd alone leaves every saved activation bit-identical: only the wgrads' split-K reduction order differs between two runs
-    assert _rel(g1, g0) < (2e-3 if "streamk" in variants or "delta" in variants else 1e-5), _rel(g1, g0)
+    assert _rel(g1, g0) < (2e-3 if "streamk" in variants or "delta" in variants else 1e-5), _rel(g1, g0)      # (elect alone: same bits up to dQ / wgrad order)

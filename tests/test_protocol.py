@@ -26,6 +26,8 @@ def _fwd_mixes():
 def test_forward_protocol(mix):
     for seed in range(12):
         simulate_fwd(mix, seed=seed)
+    for seed in range(4):                      # attn_fwd3_kernel<.., ELECT = true>: one arrival per softmax warp, barrier counts 4
+        simulate_fwd(mix, seed=seed, elect=True)
 
 
 def _bwd_mixes():
@@ -41,6 +43,8 @@ def _bwd_mixes():
 def test_backward_protocol(items, nq):
     for seed in range(12):
         simulate_bwd(items, nq, seed=seed)
+    for seed in range(4):                      # attn_bwd3_kernel<.., ELECT = true>
+        simulate_bwd(items, nq, seed=seed, elect=True)
 
 
 @pytest.mark.parametrize("mutate", ["no_k_empty", "no_s_free"])

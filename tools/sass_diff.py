@@ -30,8 +30,20 @@ def functions(path):
 def main():
     a, b = functions(sys.argv[1]), functions(sys.argv[2])
     same = changed = 0
+    # a kernel whose template gained a defaulted parameter keeps its code but changes its mangled name
+    renamed = {}
+    for k in sorted(set(a) - set(b)):
+        for k2 in sorted(set(b) - set(a)):
+            if k2 not in renamed.values() and a[k] == b[k2] and k2.startswith(k[:k.index("I")]):
+                renamed[k] = k2
+                break
     for k in sorted(set(a) | set(b)):
-        if k not in a:
+        if k in renamed:
+            same += 1
+            print("RENAMED  ", k, "->", renamed[k], "(identical code)")
+        elif k in renamed.values():
+            continue
+        elif k not in a:
             print("NEW      ", k, len(b[k]))
         elif k not in b:
             print("REMOVED  ", k)
