@@ -10,7 +10,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from spokennlp_b200 import ops  # noqa: E402
+from spokennlp_b200 import lib, ops  # noqa: E402
 
 
 def timeit(fn, iters=30):
@@ -62,6 +62,18 @@ def main():
     print(json.dumps({"shape": "out_proj dgrad 16384x768x768 + attn_bwd", "dgrad_us": t0 * 1e6, "dgrad_delta_us": t1 * 1e6,
                       "attn_bwd_us": t2 * 1e6, "attn_bwd_delta_ready_us": t3 * 1e6,
                       "pair_before_us": (t0 + t2) * 1e6, "pair_after_us": (t1 + t3) * 1e6}), flush=True)
+    # persistent attention kernels: per-thread vs warp-elected mbarrier arrivals, with and without dropout
+    ctx2 = torch.empty(M, H, device=dev, dtype=f16)
+    lse2 = torch.empty(B, heads, S, device=dev)
+    for p in (0.0, 0.1):
+        drop = ops.Dropout(seed, 9, p) if p > 0 else None
+        row = {"shape": "attention B32 S512 h12", "dropout": p}
+        for variant, tag in ((0, "default"), (1, "elect")):
+            lib.load().b200_set_attn_variant(variant)
+            row[f"fwd_{tag}_us"] = 1e6 * timeit(lambda: ops.attn_fwd(qkv, qkv, ctx2, B, heads, S, S, q_col0=0, k_col0=H, v_col0=2 * H, lse2=lse2, drop=drop))
+            row[f"bwd_{tag}_us"] = 1e6 * timeit(lambda: ops.attn_bwd(qkv, qkv, dctx, ctx2, lse2, dqkv, dqkv, ws, B, heads, S, S, drop=drop, **kw))
+        lib.load().b200_set_attn_variant(0)
+        print(json.dumps(row), flush=True)
 
 
 if __name__ == "__main__":
