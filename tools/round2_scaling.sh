@@ -21,4 +21,11 @@ if [ "${STAGE2:-0}" = "1" ]; then
       echo "$1 n=$n rc=$?"; tail -c 300 gpurun_out/r2_scale_$1_n$n.json | cut -c1-300
     done
   done
+  # NCCL's own CTA cap on the single default communicator (no second communicator, no SM reservation)
+  for c in 4 8 16; do
+    NCCL_DEBUG=WARN NCCL_MAX_CTAS=$c B200_BENCH_WATCHDOG_S=170 timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 \
+      --master-addr 127.0.0.1 --master-port $((29900 + c)) bench.py --gpus 8 --steps 20 --warmup 3 \
+      > gpurun_out/r2_scale_maxctas${c}_n8.json 2> gpurun_out/r2_scale_maxctas${c}_n8.err
+    echo "NCCL_MAX_CTAS=$c n=8 rc=$?"; tail -c 300 gpurun_out/r2_scale_maxctas${c}_n8.json | cut -c1-300
+  done
 fi
