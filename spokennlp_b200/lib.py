@@ -97,7 +97,11 @@ def built_hash() -> Optional[str]:
 
 def is_stale() -> bool:
     b = built_hash()
-    return b is None or (b != "unknown" and b != source_hash())
+    if b is None:
+        return True
+    if b == "unknown" or not os.path.isdir(CSRC):      # hand-run make / a binary-only deployment: nothing to compare against
+        return False
+    return b != source_hash()
 
 
 def build(verbose: bool = False, force: bool = False) -> str:
