@@ -335,7 +335,7 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
         }
         float f[CW];
 #pragma unroll
-        for (int i = 0; i < CW; ++i) f[i] = __uint_as_float(v[i]) * alpha;
+        for (int i = 0; i < CW; ++i) f[i] = RESADD ? __uint_as_float(v[i]) : __uint_as_float(v[i]) * alpha;   // (the forward never scales)
         if (HAS_BIAS && add_bias) {
 #pragma unroll
           for (int i = 0; i < CW / 4; ++i) {
