@@ -197,6 +197,12 @@ def kernel_rooflines(torch, ops, peaks):
     t = time_kernel(torch, lambda: ops.gemm(x, w1, h, epilogue=ops.EPI_BIAS_GELU, bias=b1, out2=z))
     flops = 2.0 * M * H * I
     out["gemm_ffn_up_gelu"] = {"bound": "tensor", "achieved": flops / t / 1e12, "unit": "TFLOP/s", "ms": t * 1e3}
+    try:        # yardstick only (never on the product path): the library's plain fp16 GEMM of the same shape, no epilogue
+        tl = time_kernel(torch, lambda: torch.matmul(x, w1.t(), out=h))
+        out["gemm_ffn_up_gelu"]["cublas_plain_same_shape_tflops"] = flops / tl / 1e12
+    except Exception as e:  # noqa: BLE001
+        out["gemm_ffn_up_gelu"]["cublas_plain_same_shape_tflops"] = None
+        out["gemm_ffn_up_gelu"]["cublas_error"] = f"{type(e).__name__}: {e}"[:200]
     w2 = torch.randn(H, I, device=dev, dtype=f16) * 0.02
     pre = torch.empty(M, H, device=dev, dtype=torch.float32)
     bo = torch.zeros(H, device=dev)
