@@ -274,7 +274,7 @@ def run_b200_arm(args):
     from spokennlp_b200.trainer import DataParallelTrainer, TopicSegModel
 
     from spokennlp_b200.blocks import Experimental
-    opt_in = [n for n in ("resadd", "streamk", "delta", "elect") if getattr(Experimental, n)]
+    opt_in = [n for n in ("resadd", "streamk", "delta", "elect", "ewait") if getattr(Experimental, n)]
     torch.manual_seed(0)
     cfg = BertConfig(hidden_dropout_prob=args.dropout, attention_probs_dropout_prob=args.dropout, **CFG)
     model = TopicSegModel(cfg)

@@ -230,7 +230,8 @@ int b200_cls_head_bwd_drop(const void* h, const float* logits, const int64_t* la
  *   head of the attention-backward workspace (b200_attn_bwd_delta_ptr) so that b200_attn_bwd_ext can skip its own pass.
  * b200_attn_bwd_ext: b200_attn_bwd_drop + flags. */
 /* b200_set_attn_variant: bit 0 = the persistent attention kernels signal their softmax->MMA hand-offs with one mbarrier
- * arrival per warp instead of one per thread (same results; a scheduling experiment).  0 = round-1 kernels. */
+ * arrival per warp instead of one per thread; bit 1 (only together with bit 0) = the softmax warps also wait with one lane
+ * per warp.  Same results; scheduling experiments.  0 = round-1 kernels. */
 void b200_set_attn_variant(int bits);
 #define B200_ATTN_BWD_DELTA_READY 1   /* workspace already holds delta (from b200_gemm_f16_dgrad_delta) */
 int b200_gemm_f16_resadd(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias, float* out, int ld_out,

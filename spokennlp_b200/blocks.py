@@ -28,22 +28,24 @@ class Experimental:
       resadd : output-dense + residual through b200_gemm_f16_resadd (in place on the fp32 residual stream, no aux reads)
       streamk: with resadd, the stream-K schedule for those N = 768 GEMMs
       delta  : attention-backward row statistic fused into the output projection's dgrad (b200_gemm_f16_dgrad_delta)
-      elect  : persistent attention kernels with one mbarrier arrival per softmax warp (b200_set_attn_variant(1))"""
-    resadd = streamk = delta = elect = False
+      elect  : persistent attention kernels with one mbarrier arrival per softmax warp (b200_set_attn_variant(1))
+      ewait  : with elect, the softmax warps also wait with one lane per warp (b200_set_attn_variant(3))"""
+    resadd = streamk = delta = elect = ewait = False
     _elect_applied = False
 
     @classmethod
     def from_env(cls, value: Optional[str] = None) -> None:
         import os
         names = {n.strip() for n in (os.environ.get("B200_EXP", "") if value is None else value).split(",") if n.strip()}
-        unknown = names - {"resadd", "streamk", "delta", "elect"}
+        unknown = names - {"resadd", "streamk", "delta", "elect", "ewait"}
         if unknown:
             raise ValueError(f"B200_EXP: unknown variant(s) {sorted(unknown)}")
         cls.resadd, cls.streamk, cls.delta = "resadd" in names or "streamk" in names, "streamk" in names, "delta" in names
-        cls.elect = "elect" in names
+        cls.ewait = "ewait" in names
+        cls.elect = "elect" in names or cls.ewait
         if cls.elect or cls._elect_applied:              # a library-wide selector: touch the library only when it is (or was) in use
             from . import lib as _lib
-            _lib.load().b200_set_attn_variant(1 if cls.elect else 0)
+            _lib.load().b200_set_attn_variant(3 if cls.ewait else (1 if cls.elect else 0))
             cls._elect_applied = cls.elect
 
 

@@ -151,7 +151,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g,
 
 std::atomic<int> g_gemm_impl{2};
 std::atomic<int> g_gemm_dbg{0};
-std::atomic<int> g_attn_variant{0};      // b200_set_attn_variant: bit 0 = warp-elected mbarrier arrivals (opt-in)
+std::atomic<int> g_attn_variant{0};      // b200_set_attn_variant: bit 0 = warp-elected mbarrier arrivals, bit 1 (with bit 0) = warp-elected waits (opt-in)
 
 const DropCfg kNoDrop{nullptr, 0, 0, 1.0f};
 DropCfg make_drop(const uint32_t* seed, unsigned site, float p) {
@@ -338,12 +338,21 @@ int b200_attn_fwd_drop(const void* q, int ldq, int q_col0, const void* kv, int l
     if (e0 != B200_OK || e1 != B200_OK) return e0 ? e0 : e1;
     const long long items = static_cast<long long>(grid.x) * grid.y * grid.z;
     const int ctas = items < sm_count() ? static_cast<int>(items) : sm_count();
-    if (g_attn_variant.load() & 1) {            // opt-in: one mbarrier arrival per softmax warp
-      static int f0 = set_smem(attn_fwd3_kernel<false, true>, AttnFwd3Smem::TOTAL);
-      static int f1 = set_smem(attn_fwd3_kernel<true, true>, AttnFwd3Smem::TOTAL);
-      if (f0 != B200_OK || f1 != B200_OK) return f0 ? f0 : f1;
-      if (drop.seed_base) attn_fwd3_kernel<true, true><<<ctas, ATTP_THREADS, AttnFwd3Smem::TOTAL, static_cast<cudaStream_t>(stream)>>>(tq, tkv, to, a);
-      else attn_fwd3_kernel<false, true><<<ctas, ATTP_THREADS, AttnFwd3Smem::TOTAL, static_cast<cudaStream_t>(stream)>>>(tq, tkv, to, a);
+    const int var = g_attn_variant.load();
+    if (var & 1) {                              // opt-in: one mbarrier arrival (bit 1: and one waiting lane) per softmax warp
+      static int f0 = set_smem(attn_fwd3_kernel<false, 1>, AttnFwd3Smem::TOTAL);
+      static int f1 = set_smem(attn_fwd3_kernel<true, 1>, AttnFwd3Smem::TOTAL);
+      static int f2 = set_smem(attn_fwd3_kernel<false, 3>, AttnFwd3Smem::TOTAL);
+      static int f3 = set_smem(attn_fwd3_kernel<true, 3>, AttnFwd3Smem::TOTAL);
+      if (f0 != B200_OK || f1 != B200_OK || f2 != B200_OK || f3 != B200_OK) return f0 ? f0 : (f1 ? f1 : (f2 ? f2 : f3));
+      cudaStream_t st = static_cast<cudaStream_t>(stream);
+      if (var & 2) {
+        if (drop.seed_base) attn_fwd3_kernel<true, 3><<<ctas, ATTP_THREADS, AttnFwd3Smem::TOTAL, st>>>(tq, tkv, to, a);
+        else attn_fwd3_kernel<false, 3><<<ctas, ATTP_THREADS, AttnFwd3Smem::TOTAL, st>>>(tq, tkv, to, a);
+      } else {
+        if (drop.seed_base) attn_fwd3_kernel<true, 1><<<ctas, ATTP_THREADS, AttnFwd3Smem::TOTAL, st>>>(tq, tkv, to, a);
+        else attn_fwd3_kernel<false, 1><<<ctas, ATTP_THREADS, AttnFwd3Smem::TOTAL, st>>>(tq, tkv, to, a);
+      }
       return check_launch("attn_fwd3_kernel<elect>");
     }
     if (drop.seed_base) attn_fwd3_kernel<true><<<ctas, ATTP_THREADS, AttnFwd3Smem::TOTAL, static_cast<cudaStream_t>(stream)>>>(tq, tkv, to, a);

@@ -45,13 +45,15 @@ struct AttnBwd3Smem {
   static constexpr int TOTAL = OFF_BAR + 256 + 1024;
 };
 
-// ELECT (opt-in): one `s_free` / `ds_full` arrival per softmax warp instead of one per thread (see attn_fwd3.cuh).
-template <bool DROP, bool ELECT = false>
+// VAR (opt-in): bit 0 = one `s_free` / `ds_full` arrival per softmax warp instead of one per thread, bit 1 = the
+// softmax warps also wait with one lane per warp (see attn_fwd3.cuh).
+template <bool DROP, int VAR = 0>
 __global__ void __launch_bounds__(ATTB_THREADS, 1)
 attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                  const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmDQ,
                  const __grid_constant__ CUtensorMap tmDKV, const AttnBwdArgs a) {
   using S = AttnBwd3Smem;
+  constexpr bool ELECT = (VAR & 1) != 0, EWAIT = (VAR & 2) != 0;
   constexpr int NST = ATTB3_QDO_STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -234,6 +236,14 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     uint8_t* dqs = smem + S::OFF_DQS + (warp - 2) * 4096;     // this warp's [32 q][32 d] fp32 staging patch
     const uint32_t dqs_row = smem_u32(dqs) + lane * 128;
     uint32_t ir = 0;                              // query blocks processed so far (barrier phases, dQ buffer)
+    auto warp_wait = [&](uint64_t* bar, uint32_t parity) {
+      if (EWAIT) {
+        if (lane == 0) mbar_wait(bar, parity);
+        __syncwarp();
+      } else {
+        mbar_wait(bar, parity);
+      }
+    };
 
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const Item it = decode(item);
@@ -294,7 +304,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           lse_n = (qn < a.Sq) ? a.lse2[stat_base + qn] : INFINITY;
           del_n = (qn < a.Sq) ? a.delta[stat_base + qn] : 0.f;
         }
-        mbar_wait(&s_full[g], ir & 1);
+        warp_wait(&s_full[g], ir & 1);
         tc_fence_after();
         uint32_t sv[64], dp[64];
         tmem_ld_x32(tmem + lane_addr + g * 64, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
@@ -351,7 +361,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           }
         }
         if (i > 0) {                              // gradient MMAs of the previous block are done: its dQ is complete, P / dS are free
-          mbar_wait(grad_done, (ir - 1) & 1);
+          warp_wait(grad_done, (ir - 1) & 1);
           tc_fence_after();
         } else if (t == 0) {
           tma_wait_group_read<0>();               // the previous item's dK / dV stores have read the staging patches (see the epilogue)
@@ -374,7 +384,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (i > 0) drain_dq(ir - 1, i - 1);
       }
       // ------------------------------------------------------------------ item epilogue
-      mbar_wait(grad_done, (ir - 1) & 1);
+      warp_wait(grad_done, (ir - 1) & 1);
       tc_fence_after();
       drain_dq(ir - 1, nq - 1);
       // dV, dK: TMEM lane == key row; this thread owns 32 of the 64 d columns.  A full key block leaves as two TMA stores from

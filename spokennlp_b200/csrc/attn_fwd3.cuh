@@ -43,13 +43,15 @@ struct AttnFwd3Smem {
   static constexpr int TOTAL = OFF_BAR + 256 + 1024;
 };
 
-// ELECT (opt-in): the softmax warps signal `s_free` / `p_full` with ONE arrival per warp (after a warp-level
-// sync) instead of one per thread — 4 arrivals per barrier phase instead of 128 same-address mbarrier operations.
-template <bool DROP, bool ELECT = false>
+// VAR (opt-in).  Bit 0 (ELECT): the softmax warps signal `s_free` / `p_full` with ONE arrival per warp (after a
+// warp-level sync) instead of one per thread — 4 arrivals per barrier phase instead of 128 same-address mbarrier
+// operations.  Bit 1 (EWAIT): they also WAIT with one lane per warp (lane 0 polls, __syncwarp() releases the others).
+template <bool DROP, int VAR = 0>
 __global__ void __launch_bounds__(ATTP_THREADS, 1)
 attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                  const __grid_constant__ CUtensorMap tmO, const AttnFwdArgs a) {
   using S = AttnFwd3Smem;
+  constexpr bool ELECT = (VAR & 1) != 0, EWAIT = (VAR & 2) != 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
@@ -221,6 +223,14 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const float inv_sc = 1.0f / sc;
     const uint32_t dseed = DROP ? drop_seed(a.drop) : 0u;
     uint32_t t = 0;                               // blocks this tile has processed (barrier phases)
+    auto warp_wait = [&](uint64_t* bar, uint32_t parity) {
+      if (EWAIT) {
+        if (lane == 0) mbar_wait(bar, parity);
+        __syncwarp();
+      } else {
+        mbar_wait(bar, parity);
+      }
+    };
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const Item it = decode(item);
       if (x == 1 && !it.tileB) continue;
@@ -242,7 +252,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           sts_f32(bj + tg * 4, bv);
           asm volatile("bar.sync %0, 128;" ::"r"(1 + x) : "memory");
         }
-        mbar_wait(&s_full[x], t & 1);
+        warp_wait(&s_full[x], t & 1);
         tc_fence_after();
         uint32_t v[128];
         tmem_ld_x32(tmem + lane_addr + x * 128, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
@@ -289,7 +299,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (m_use == NEG_INF) m_use = 0.f;
         const float alpha = rescale ? fast_exp2(m - m_use) : 1.0f;     // m == -inf -> 0
         if (j > 0) {                              // P.V of block j-1 finished: P smem is free, O may be rescaled
-          mbar_wait(&o_full[x], (t - 1) & 1);
+          warp_wait(&o_full[x], (t - 1) & 1);
           tc_fence_after();
           if (rescale) {
 #pragma unroll
@@ -337,7 +347,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
       }
       // ---------------------------------------------------------------- finalise: O / l -> ctx, LSE
-      mbar_wait(&o_full[x], (t - 1) & 1);
+      warp_wait(&o_full[x], (t - 1) & 1);
       tc_fence_after();
       const float inv_l = (l > 0.f ? 1.0f / l : 0.f) * (DROP ? a.drop.scale : 1.0f);
       uint32_t o[2][32];

@@ -112,7 +112,7 @@ def test_attention_with_warp_elected_arrivals_matches_the_default_kernels(B, S, 
     cols = dict(q_col0=0, k_col0=H, v_col0=2 * H)
     res = []
     try:
-        for variant in (0, 1):
+        for variant in (0, 1, 3):
             lib.load().b200_set_attn_variant(variant)
             ctx = torch.empty(M, H, dtype=torch.float16, device="cuda")
             lse = torch.empty(B, heads, S, device="cuda")
@@ -125,10 +125,11 @@ def test_attention_with_warp_elected_arrivals_matches_the_default_kernels(B, S, 
             res.append((ctx, lse, dqkv))
     finally:
         lib.load().b200_set_attn_variant(0)
-    (c0, l0, g0), (c1, l1, g1) = res
-    assert torch.equal(c0, c1) and torch.equal(l0, l1)
-    assert torch.equal(g0[:, H:], g1[:, H:])                       # dK, dV
-    assert _rel(g1[:, :H], g0[:, :H]) < 2e-3                       # dQ: fp16 of an fp32 sum taken in a varying order
+    c0, l0, g0 = res[0]
+    for c1, l1, g1 in res[1:]:
+        assert torch.equal(c0, c1) and torch.equal(l0, l1)
+        assert torch.equal(g0[:, H:], g1[:, H:])                   # dK, dV
+        assert _rel(g1[:, :H], g0[:, :H]) < 2e-3                   # dQ: fp16 of an fp32 sum taken in a varying order
 
 
 def _tiny_step(variants: str, dropout: float):
@@ -160,7 +161,7 @@ def _tiny_step(variants: str, dropout: float):
 
 
 @pytest.mark.parametrize("dropout", [0.0, 0.1])
-@pytest.mark.parametrize("variants", ["resadd", "delta", "resadd,delta", "streamk,delta", "elect", "resadd,delta,elect"])
+@pytest.mark.parametrize("variants", ["resadd", "delta", "resadd,delta", "streamk,delta", "elect", "ewait", "resadd,delta,ewait"])
 def test_training_step_with_variants_matches_the_default_path(variants, dropout):
     _ops()
     loss0, g0 = _tiny_step("", dropout)

@@ -149,4 +149,4 @@ def test_unknown_variant_names_are_refused():
     with pytest.raises(ValueError):
         blocks.Experimental.from_env("resad")
     blocks.Experimental.from_env("")
-    assert not (blocks.Experimental.resadd or blocks.Experimental.streamk or blocks.Experimental.delta or blocks.Experimental.elect)
+    assert not (blocks.Experimental.resadd or blocks.Experimental.streamk or blocks.Experimental.delta or blocks.Experimental.elect or blocks.Experimental.ewait)

@@ -11,7 +11,7 @@ grep -E "^(PASS|FAIL)|passed" gpurun_out/r2_experimental.log | tail -30
 B200_RUN_EXPERIMENTAL=1 timeout 300 compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_experimental.py -q -x \
   -k "256-256-64 or 1024-768-768 or 300-768-1536 or 2-128-2 or 3-300-4" > gpurun_out/r2_sanitizer_memcheck.log 2>&1; tail -4 gpurun_out/r2_sanitizer_memcheck.log
 timeout 120 python tools/variants_ab.py > gpurun_out/r2_variants_ab.jsonl 2> gpurun_out/r2_variants_ab.err; cat gpurun_out/r2_variants_ab.jsonl
-for exp in "" "resadd" "delta" "elect" "resadd,delta" "resadd,delta,elect" "streamk,delta"; do
+for exp in "" "resadd" "delta" "elect" "ewait" "resadd,delta" "resadd,delta,ewait" "streamk,delta"; do
   tag=${exp//,/_}; tag=${tag:-default}
   B200_EXP="$exp" timeout 150 python bench.py --no-cpu-baseline --steps 20 > gpurun_out/r2_bench_$tag.json 2> gpurun_out/r2_bench_$tag.err
   python - "$tag" <<'PY'
