@@ -12,6 +12,7 @@ from tools.gemm_sweep import timeit  # noqa: E402
 
 heads, H = 12, 768
 so = lib.load()
+so.b200_set_attn_variant(int(os.environ.get("B200_ATTN_VARIANT", "0"), 0))     # 1 / 3: the opt-in hand-off variants
 torch.manual_seed(0)
 
 
