@@ -172,5 +172,5 @@ def test_training_step_with_variants_matches_the_default_path(variants, dropout)
         assert abs(loss1 - loss0) < 1e-5
     # resadd alone leaves every saved activation bit-identical: only the wgrads' split-K reduction order differs between two runs
     # without streamk / delta the two runs differ only by the order of fp32 reduce-adds (dQ over key blocks, split-K wgrads),
-    # which already varies between two runs of the default path: a few fp16 roundings of dQ flip (measured scale ~1e-5)
+    # which already varies between two runs of the default path: a few fp16 roundings of dQ flip (estimated scale ~1e-5)
     assert _rel(g1, g0) < (2e-3 if "streamk" in variants or "delta" in variants else 1e-4), _rel(g1, g0)
