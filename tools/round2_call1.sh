@@ -1,6 +1,6 @@
 #!/bin/bash
-# First GPU call of round 2 (one B200, ~6 min of box time):
-#   gpurun --timeout 600 -- 'bash tools/round2_call1.sh'
+# First GPU call of round 2 (one B200, ~12 min of box time):
+#   gpurun --timeout 900 -- 'bash tools/round2_call1.sh'
 # 1. the default GPU suite, 2. the opt-in variants' tests, each node in its own process (a trapped kernel cannot hide the
 # others), 3. kernel-level A/B, 4. bench.py with each variant set on the same box.  Everything lands in gpurun_out/.
 mkdir -p gpurun_out
@@ -11,9 +11,9 @@ grep -E "^(PASS|FAIL)|passed" gpurun_out/r2_experimental.log | tail -30
 B200_RUN_EXPERIMENTAL=1 timeout 300 compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_experimental.py -q -x \
   -k "256-256-64 or 1024-768-768 or 300-768-1536 or 2-128-2 or 3-300-4" > gpurun_out/r2_sanitizer_memcheck.log 2>&1; tail -4 gpurun_out/r2_sanitizer_memcheck.log
 timeout 120 python tools/variants_ab.py > gpurun_out/r2_variants_ab.jsonl 2> gpurun_out/r2_variants_ab.err; cat gpurun_out/r2_variants_ab.jsonl
-for exp in "" "resadd" "delta" "elect" "ewait" "resadd,delta" "resadd,delta,ewait" "streamk,delta"; do
+for exp in "" "resadd" "delta" "elect" "ewait" "resadd,delta,ewait" "streamk,delta,ewait"; do
   tag=${exp//,/_}; tag=${tag:-default}
-  B200_EXP="$exp" timeout 150 python bench.py --no-cpu-baseline --steps 20 > gpurun_out/r2_bench_$tag.json 2> gpurun_out/r2_bench_$tag.err
+  B200_EXP="$exp" timeout 150 python bench.py --no-cpu-baseline --steps 12 > gpurun_out/r2_bench_$tag.json 2> gpurun_out/r2_bench_$tag.err
   python - "$tag" <<'PY'
 import json, sys
 try:
