@@ -5,8 +5,14 @@
 # others), 3. kernel-level A/B, 4. bench.py with each variant set on the same box.  Everything lands in gpurun_out/.
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests -m gpu -x -q > gpurun_out/r2_gpu_suite.log 2>&1; tail -3 gpurun_out/r2_gpu_suite.log
-B200_RUN_EXPERIMENTAL=1 timeout 400 python tools/gpu_isolated.py tests/test_gpu_experimental.py --timeout 60 > gpurun_out/r2_experimental.log 2>&1
-grep -E "^(PASS|FAIL)|passed" gpurun_out/r2_experimental.log | tail -30
+# one process first (fast); only if something fails or traps, every node again in its own process
+if B200_RUN_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_gpu_experimental.py -q > gpurun_out/r2_experimental.log 2>&1; then
+  tail -2 gpurun_out/r2_experimental.log
+else
+  tail -5 gpurun_out/r2_experimental.log
+  B200_RUN_EXPERIMENTAL=1 timeout 600 python tools/gpu_isolated.py tests/test_gpu_experimental.py --timeout 60 > gpurun_out/r2_experimental_isolated.log 2>&1
+  grep -E "^(PASS|FAIL)|passed" gpurun_out/r2_experimental_isolated.log | tail -40
+fi
 # memcheck over the new template instantiations (small shapes; SURVEY §5: sanitizer pass per kernel)
 B200_RUN_EXPERIMENTAL=1 timeout 300 compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_experimental.py -q -x \
   -k "256-256-64 or 1024-768-768 or 300-768-1536 or 2-128-2 or 3-300-4" > gpurun_out/r2_sanitizer_memcheck.log 2>&1; tail -4 gpurun_out/r2_sanitizer_memcheck.log
