@@ -41,6 +41,10 @@ CASES = {
                        tssp_loss_weight=0.5),
     "cos_only": dict(do_da_ts=False, do_tssp=False, ts_score_predictor="cos", ts_score_predictor_cos_temp=0.5,
                      cl_loss_weight=0.0, tssp_loss_weight=0.0),
+    # edge cases: an example without labels, an example with a single label, class weights without focal, ts weight != 1
+    "ragged_weighted": dict(_ragged=True, do_da_ts=True, do_tssp=True, ts_score_predictor="lt", focal_loss_gamma=0.0,
+                            weight_label_zero=0.7, ts_loss_weight=0.5, cl_loss_weight=0.25, cl_temp=0.2,
+                            cl_anchor_level="eop_matrix", tssp_loss_weight=2.0),
 }
 DEFAULTS = dict(num_labels=2, classifier_dropout=None, do_da_ts=False, do_tssp=False, do_cssl=False, ts_score_predictor="lt",
                 ts_score_predictor_cos_temp=1, focal_loss_gamma=0.0, weight_label_zero=0.5, ts_loss_weight=1.0,
@@ -72,7 +76,28 @@ def main():
     h_rand = torch.randn(B, 2, S, H, generator=g)                  # stand-in encoder outputs for the heads-only goldens
     out = dict(config=KW, weight_seed=7, batch=batch, heads=heads, h_rand=h_rand, random_seed=RANDOM_SEED, cases={})
 
+    # ragged variant of the same batch: example 1 carries no label at all in either view, example 2 exactly one
+    ragged = {k: v.clone() for k, v in batch.items()}
+    for v in range(2):
+        ragged["labels"][1, v] = -100
+        ragged["extract_eop_segment_ids"][1, v] = 0
+        ragged["eop_index_for_aggregate_batch_eop_features"][1, v] = 0
+        ragged["sent_token_mask"][1, v] = -100
+        ragged["sent_pair_orders"][1, v] = -100
+        first = int((ragged["labels"][2, v] != -100).nonzero()[0])
+        keep = ragged["labels"][2, v, first].clone()
+        ragged["labels"][2, v] = -100
+        ragged["labels"][2, v, first] = keep
+        ragged["extract_eop_segment_ids"][2, v] = 0
+        ragged["extract_eop_segment_ids"][2, v, first] = 1
+        ragged["eop_index_for_aggregate_batch_eop_features"][2, v] = 0
+        ragged["eop_index_for_aggregate_batch_eop_features"][2, v, 1] = 1
+    out["batch_ragged"] = ragged
+    default_batch = batch
+
     for name, case in CASES.items():
+        batch = ragged if case.get("_ragged") else default_batch
+        case = {k: v for k, v in case.items() if not k.startswith("_")}
         cfg = make_cfg(case)
         lc = LossCalculator(cfg)
         with torch.no_grad():
@@ -83,7 +108,7 @@ def main():
         kw1 = dict(sent_token_mask=batch["sent_token_mask"][:, 1], sent_pair_orders=batch["sent_pair_orders"][:, 1], da_example_flag=True,
                    extract_eop_segment_ids=batch["extract_eop_segment_ids"][:, 1],
                    eop_index_for_aggregate_batch_eop_features=batch["eop_index_for_aggregate_batch_eop_features"][:, 1])
-        rec = {"case": case}
+        rec = {"case": case, "ragged": batch is ragged}
         # ---- heads only, forward (the reference's own LossCalculator.forward, no_grad)
         with torch.no_grad():
             random.seed(RANDOM_SEED)

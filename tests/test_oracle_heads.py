@@ -27,12 +27,13 @@ def _close(a, b, tol=2e-5):
     assert rel_err(a, b) < tol, rel_err(a, b)
 
 
-CASES = ["full_matrix", "focal_list", "cos_only"]
+CASES = ["full_matrix", "focal_list", "cos_only", "ragged_weighted"]
 
 
 @pytest.mark.parametrize("name", CASES)
 def test_heads_forward_and_gradients_match_the_reference_modules(gold, name):
-    rec, b = gold["cases"][name], gold["batch"]
+    rec = gold["cases"][name]
+    b = gold["batch_ragged"] if rec.get("ragged") else gold["batch"]
     cfg = _cfg(rec["case"])
     hw = T.HeadWeights(**{k: v.clone().requires_grad_(True) for k, v in gold["heads"].items()})
     h0 = gold["h_rand"][:, 0].clone().requires_grad_(True)
@@ -59,7 +60,8 @@ def test_heads_forward_and_gradients_match_the_reference_modules(gold, name):
 
 @pytest.mark.parametrize("name", CASES)
 def test_wrapper_forward_matches_the_reference_wrapper(gold, name):
-    rec, b = gold["cases"][name], gold["batch"]
+    rec = gold["cases"][name]
+    b = gold["batch_ragged"] if rec.get("ragged") else gold["batch"]
     cfg = _cfg(rec["case"])
     ocfg = O.OracleConfig(**gold["config"])
     sd = O.random_state_dict(ocfg, seed=gold["weight_seed"])

@@ -16,7 +16,7 @@ from conftest import GOLDEN, rel_err
 from oracle import bert_oracle as O
 from oracle import ts_heads_oracle as T
 
-CASES = ["full_matrix", "focal_list", "cos_only"]
+CASES = ["full_matrix", "focal_list", "cos_only", "ragged_weighted"]
 
 
 def _gold():
@@ -26,7 +26,7 @@ def _gold():
 def _run_wrapper(model, gold, name, device, grad=False):
     rec = gold["cases"][name]
     cfg = T.HeadsConfig(**{k: v for k, v in rec["case"].items() if k in T.HeadsConfig.__dataclass_fields__})
-    b = {k: v.to(device) for k, v in gold["batch"].items()}
+    b = {k: v.to(device) for k, v in (gold["batch_ragged"] if rec.get("ragged") else gold["batch"]).items()}
     hw = T.HeadWeights(**{k: v.to(device).clone().requires_grad_(grad) for k, v in gold["heads"].items()})
 
     def encode(ids, mask, tt):           # bert_for_ts.py:55-66: positional ids, kwargs, return_dict=False, outputs[0]
@@ -38,6 +38,10 @@ def _run_wrapper(model, gold, name, device, grad=False):
                                               b["extract_eop_segment_ids"], b["eop_index_for_aggregate_batch_eop_features"],
                                               b["sent_token_mask"], b["sent_pair_orders"])
     return cfg, rec, hw, loss, logits, cos
+
+
+def _labels(gold, rec):
+    return (gold["batch_ragged"] if rec.get("ragged") else gold["batch"])["labels"]
 
 
 def _check_forward(cfg, rec, loss, logits, cos, labels, tol):
@@ -68,7 +72,7 @@ def _hf_model(gold):
 def test_wrapper_on_hf_encoder_cpu(name):
     gold = _gold()
     cfg, rec, _, loss, logits, cos = _run_wrapper(_hf_model(gold), gold, name, "cpu")
-    _check_forward(cfg, rec, loss, logits, cos, gold["batch"]["labels"], 1e-5)
+    _check_forward(cfg, rec, loss, logits, cos, _labels(gold, rec), 1e-5)
 
 
 def _dropin(gold):
@@ -89,7 +93,7 @@ def _dropin(gold):
 def test_wrapper_on_dropin_encoder_matches_reference_wrapper(name):
     gold = _gold()
     cfg, rec, _, loss, logits, cos = _run_wrapper(_dropin(gold).eval(), gold, name, "cuda")
-    _check_forward(cfg, rec, loss, logits, cos, gold["batch"]["labels"], 1e-3)      # north_star: hidden states within 1e-3
+    _check_forward(cfg, rec, loss, logits, cos, _labels(gold, rec), 1e-3)      # north_star: hidden states within 1e-3
 
 
 @pytest.mark.gpu
