@@ -110,9 +110,14 @@ int b200_layernorm_bwd(const void* dy, const void* dy2, const void* x, int x_dty
 int b200_embed_ln_fwd(const int64_t* ids, const int64_t* tt, const int64_t* pos, const float* inputs_embeds, const float* word,
                       const float* pos_tab, const float* type_tab, const float* gamma, const float* beta, void* y, float* y32,
                       int rows, int S, int H, float eps, void* stream);
+/* Backward of the above (recomputes the pre-LN sum).  Gradients are ACCUMULATED into the fp32 tables, scaled by *alpha.
+ * pad_id: nn.Embedding(padding_idx=config.pad_token_id) semantics (bert_model.py:171) — rows gathered with that id take part
+ * in the forward but add nothing to dword; -1 = no padding index.  When the forward ran on inputs_embeds (ids == null) pass
+ * the same inputs_embeds; d_inputs_embeds (optional fp32 [rows,H]) then receives the gradient instead of dword. */
 int b200_embed_ln_bwd(const void* dy, const void* dy2, const int64_t* ids, const int64_t* tt, const int64_t* pos, const float* word,
                       const float* pos_tab, const float* type_tab, const float* gamma, float* dword, float* dpos, float* dtype_tab,
-                      float* dgamma, float* dbeta, const float* alpha, int rows, int S, int H, float eps, void* stream);
+                      float* dgamma, float* dbeta, const float* alpha, int rows, int S, int H, float eps, long long pad_id,
+                      const float* inputs_embeds, float* d_inputs_embeds, void* stream);
 
 /* Token-classification head: logits[rows,C] = h . W^T + b, C in {2,3} (LossCalculator.classifier, loss_calculator.py:17,42;
  * modeling_ponet.py:43,83-84; TSSP tssp.py:26-34).  argmax optional int32 [rows] (np.argmax, ts_sentence_seq_labeling.py:1143). */
@@ -172,6 +177,11 @@ int b200_attn_bwd(const void* q, int ldq, int q_col0, const void* kv, int ldkv, 
  * adamw_step skips the update when coef[1] == 0 and always refreshes the fp16 compute copy p16 (optional). */
 int b200_grad_sumsq(const float* g, size_t n, float* sumsq, void* stream);
 int b200_clip_coef(const float* sumsq, float max_norm, float grad_mult, float* coef, void* stream);
+/* as b200_clip_coef, plus dynamic loss scaling on the device (GradScaler semantics; replays inside a CUDA graph): a step with a
+ * non-finite norm is skipped, loss_scale = {scale, 1/scale} is multiplied by `backoff` and state[1] (skipped steps) counts it;
+ * after `growth_interval` consecutive finite steps the scale is multiplied by `growth`.  state = {good steps, skipped steps}. */
+int b200_clip_coef_scaled(const float* sumsq, float max_norm, float grad_mult, float* coef, float* loss_scale, float* state,
+                          int growth_interval, float backoff, float growth, float min_scale, float max_scale, void* stream);
 int b200_adamw_step(float* p, const float* g, float* m, float* v, void* p16, size_t n, float lr, float beta1, float beta2, float eps,
                     float weight_decay, float bias_corr1, float bias_corr2, const float* coef, void* stream);
 /* Same with the hyper-parameters {lr, beta1, beta2, eps, weight_decay, bias_corr1, bias_corr2, -} read from device memory, so a
@@ -203,8 +213,8 @@ int b200_embed_ln_fwd_drop(const int64_t* ids, const int64_t* tt, const int64_t*
                            int H, float eps, const uint32_t* seed, unsigned site, float p, void* stream);
 int b200_embed_ln_bwd_drop(const void* dy, const void* dy2, const int64_t* ids, const int64_t* tt, const int64_t* pos, const float* word,
                            const float* pos_tab, const float* type_tab, const float* gamma, float* dword, float* dpos, float* dtype_tab,
-                           float* dgamma, float* dbeta, const float* alpha, int rows, int S, int H, float eps, const uint32_t* seed,
-                           unsigned site, float p, void* stream);
+                           float* dgamma, float* dbeta, const float* alpha, int rows, int S, int H, float eps, long long pad_id,
+                           const float* inputs_embeds, float* d_inputs_embeds, const uint32_t* seed, unsigned site, float p, void* stream);
 int b200_attn_fwd_drop(const void* q, int ldq, int q_col0, const void* kv, int ldkv, int k_col0, int v_col0, const float* key_bias,
                        const int32_t* kv_len, void* ctx, int ld_out, float* lse2, int B, int heads, int Sq, int Sk, const uint32_t* seed,
                        unsigned site, float p, void* stream);

@@ -54,10 +54,11 @@ class OracleConfig:
     vocab_size: int = 30522
     max_position_embeddings: int = 512
     type_vocab_size: int = 2
+    pad_token_id: Optional[int] = 0      # nn.Embedding(padding_idx=config.pad_token_id): bert_model.py:171 (HF BertConfig default 0)
 
     @classmethod
     def from_hf(cls, cfg) -> "OracleConfig":
-        return cls(**{f: getattr(cfg, f) for f in cls.__dataclass_fields__})
+        return cls(**{f: getattr(cfg, f) for f in cls.__dataclass_fields__ if hasattr(cfg, f)})
 
 
 # ----------------------------------------------------------------------------
@@ -108,9 +109,12 @@ def embeddings(sd: Dict[str, Tensor], cfg: OracleConfig, input_ids: Tensor,
                position_ids: Optional[Tensor] = None,
                inputs_embeds: Optional[Tensor] = None,
                prefix: str = "embeddings.", masks: Optional[Dict[str, Tensor]] = None) -> Tensor:
-    """LN(word[ids] + type[tt] + pos[pos]) — bert_model.py:184-210; `masks["emb"]` = the dropout multiplier of :209."""
+    """LN(word[ids] + type[tt] + pos[pos]) — bert_model.py:184-210; `masks["emb"]` = the dropout multiplier of :209.
+    The word table is an nn.Embedding with padding_idx = pad_token_id (:171): the pad row is read like any other in the
+    forward and receives NO gradient in the backward (F.embedding's padding_idx does exactly that)."""
     if inputs_embeds is None:
-        inputs_embeds = sd[prefix + "word_embeddings.weight"][input_ids]
+        inputs_embeds = torch.nn.functional.embedding(input_ids, sd[prefix + "word_embeddings.weight"],
+                                                      padding_idx=getattr(cfg, "pad_token_id", None))
     B, S = inputs_embeds.shape[:2]
     if position_ids is None:
         position_ids = torch.arange(S)[None, :].expand(B, S)

@@ -134,6 +134,55 @@ def golden_tiny():
     print("tiny_bert: loss", float(loss), "wrapper loss", float(wout[0]))
 
 
+def golden_tiny_padidx():
+    """Same tiny BERT: (a) token id 0 (= pad_token_id, the word table's padding_idx — bert_model.py:171) at LIVE positions
+    that receive gradient, so the golden holds the reference's "pad row gets no gradient" behaviour; (b) the same forward
+    driven through `inputs_embeds` with gradients wrt the embeddings tensor and the remaining embedding parameters."""
+    kw = dict(hidden_size=128, num_attention_heads=2, intermediate_size=256, num_hidden_layers=2,
+              vocab_size=128, max_position_embeddings=128, type_vocab_size=2)
+    sd = random_state_dict(OracleConfig(**kw), seed=7)
+    m, cfg = hf_bert(kw, sd)
+    assert m.embeddings.word_embeddings.padding_idx == 0
+    B, S = 3, 128
+    ids, mask, tt, labels = synth_batch(B, S, kw["vocab_size"], seed=12)
+    g = torch.Generator().manual_seed(4)
+    for b in range(B):                               # pad id inside the attended range, some of them at labelled positions
+        n = int(mask[b].sum())
+        where = torch.randperm(n - 1, generator=g)[:6] + 1
+        ids[b, where] = 0
+        ids[b, 1 + 7 * b] = 0                        # positions 1, 8, 15 carry labels (synth_batch labels every 7th token)
+    tt[:, 40:] = 1
+    cls_w = torch.randn(2, 128, generator=g) * 0.05
+    cls_b = torch.randn(2, generator=g) * 0.05
+    m.train()                                        # dropout probabilities are 0
+
+    def run(**inp):
+        for p in m.parameters():
+            p.grad = None
+        w, b = cls_w.clone().requires_grad_(True), cls_b.clone().requires_grad_(True)
+        h = m(attention_mask=mask, token_type_ids=tt, return_dict=True, **inp).last_hidden_state
+        logits = h @ w.t() + b
+        # every live token contributes (mean of squares) in addition to the CE on labelled rows: padded-id rows get gradient
+        loss = torch.nn.CrossEntropyLoss()(logits.reshape(-1, 2), labels.reshape(-1)) + 0.1 * (h * mask[..., None]).pow(2).mean()
+        loss.backward()
+        grads = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+        grads["classifier.weight"], grads["classifier.bias"] = w.grad.clone(), b.grad.clone()
+        return loss.detach(), h.detach(), grads
+
+    loss, h, grads = run(input_ids=ids)
+    assert float(grads["embeddings.word_embeddings.weight"][0].abs().max()) == 0.0
+    emb = sd["embeddings.word_embeddings.weight"][ids].clone().requires_grad_(True)
+    loss_e, h_e, grads_e = run(inputs_embeds=emb)
+    assert "embeddings.word_embeddings.weight" not in grads_e
+    torch.save(dict(config=kw, weight_seed=7, input_ids=ids, attention_mask=mask, token_type_ids=tt, labels=labels,
+                    cls_w=cls_w, cls_b=cls_b, loss=loss, last_hidden_state=h, grads=grads,
+                    loss_embeds=loss_e, last_hidden_state_embeds=h_e, grads_embeds=grads_e, d_inputs_embeds=emb.grad.clone(),
+                    source="transformers %s BertModel(eager), padding_idx=%s" % (__import__("transformers").__version__,
+                                                                                 m.embeddings.word_embeddings.padding_idx)),
+               os.path.join(OUT, "tiny_bert_padidx.pt"))
+    print("tiny_bert_padidx: loss", float(loss), float(loss_e), "pad-row grad", float(grads["embeddings.word_embeddings.weight"][0].abs().max()))
+
+
 def golden_base():
     """BERT-base sized: weights regenerated from seed (not stored); store inputs and
     the reference's outputs for a [2,128] padded batch."""
@@ -209,6 +258,8 @@ def golden_mmvts_layers():
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
-    golden_tiny()
-    golden_base()
-    golden_mmvts_layers()
+    only = set(sys.argv[1:])                  # e.g. `python oracle/make_goldens.py tiny_padidx` re-mints one file
+    for name, fn in (("tiny", golden_tiny), ("tiny_padidx", golden_tiny_padidx), ("base", golden_base),
+                     ("mmvts_layers", golden_mmvts_layers)):
+        if not only or name in only:
+            fn()

@@ -533,28 +533,32 @@ int b200_embed_ln_fwd_drop(const int64_t* ids, const int64_t* tt, const int64_t*
 
 int b200_embed_ln_bwd_drop(const void* dy, const void* dy2, const int64_t* ids, const int64_t* tt, const int64_t* pos, const float* word,
                            const float* pos_tab, const float* type_tab, const float* gamma, float* dword, float* dpos, float* dtype_tab,
-                           float* dgamma, float* dbeta, const float* alpha, int rows, int S, int H, float eps, const uint32_t* seed,
-                           unsigned site, float p, void* stream);
+                           float* dgamma, float* dbeta, const float* alpha, int rows, int S, int H, float eps, long long pad_id,
+                           const float* inputs_embeds, float* d_inputs_embeds, const uint32_t* seed, unsigned site, float p, void* stream);
 
 int b200_embed_ln_bwd(const void* dy, const void* dy2, const int64_t* ids, const int64_t* tt, const int64_t* pos, const float* word,
                       const float* pos_tab, const float* type_tab, const float* gamma, float* dword, float* dpos, float* dtype_tab,
-                      float* dgamma, float* dbeta, const float* alpha, int rows, int S, int H, float eps, void* stream) {
+                      float* dgamma, float* dbeta, const float* alpha, int rows, int S, int H, float eps, long long pad_id,
+                      const float* inputs_embeds, float* d_inputs_embeds, void* stream) {
   return b200_embed_ln_bwd_drop(dy, dy2, ids, tt, pos, word, pos_tab, type_tab, gamma, dword, dpos, dtype_tab, dgamma, dbeta, alpha, rows, S, H,
-                                eps, nullptr, 0, 0.f, stream);
+                                eps, pad_id, inputs_embeds, d_inputs_embeds, nullptr, 0, 0.f, stream);
 }
 
 int b200_embed_ln_bwd_drop(const void* dy, const void* dy2, const int64_t* ids, const int64_t* tt, const int64_t* pos, const float* word,
                            const float* pos_tab, const float* type_tab, const float* gamma, float* dword, float* dpos, float* dtype_tab,
-                           float* dgamma, float* dbeta, const float* alpha, int rows, int S, int H, float eps, const uint32_t* seed,
-                           unsigned site, float p, void* stream) {
+                           float* dgamma, float* dbeta, const float* alpha, int rows, int S, int H, float eps, long long pad_id,
+                           const float* inputs_embeds, float* d_inputs_embeds, const uint32_t* seed, unsigned site, float p, void* stream) {
   if (int rc = check_row_shape("embed_ln_bwd", rows, H)) return rc;
+  if (!ids && !inputs_embeds) return fail(B200_ERR_SHAPE, "embed_ln_bwd: need input_ids or inputs_embeds (whichever the forward used)");
+  if (ids && !word) return fail(B200_ERR_SHAPE, "embed_ln_bwd: input_ids need the word table");
+  if (!dpos || !dtype_tab || !dgamma || !dbeta) return fail(B200_ERR_SHAPE, "embed_ln_bwd: null gradient table");
   int grid = (rows + ROW_WARPS - 1) / ROW_WARPS;
   if (grid > sm_count() * 4) grid = sm_count() * 4;
   static int c = set_smem(embed_ln_bwd_kernel, 3 * ROW_WARPS * ROW_MAXV * 256 * 4);
   if (c) return c;
   embed_ln_bwd_kernel<<<grid, ROW_WARPS * 32, 3 * ROW_WARPS * H * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __half*>(dy), static_cast<const __half*>(dy2), ids, tt, pos, word, pos_tab, type_tab, gamma, dword, dpos, dtype_tab,
-      dgamma, dbeta, alpha, rows, S, H, eps, make_drop(seed, site, p));
+      dgamma, dbeta, alpha, rows, S, H, eps, make_drop(seed, site, p), pad_id, inputs_embeds, d_inputs_embeds);
   return check_launch("embed_ln_bwd_kernel");
 }
 

@@ -76,6 +76,35 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
   }
 }
 
+// clip_coef_kernel + dynamic loss scaling (torch.cuda.amp.GradScaler semantics, on the device so that it also runs inside a
+// replayed CUDA graph): a step whose global gradient norm is not finite is skipped (coef[1] = 0), the loss scale is multiplied
+// by `backoff`, and state[1] counts it; after `growth_interval` consecutive good steps the scale is multiplied by `growth`.
+//   loss_scale = {scale, 1/scale} (read by the head's backward / the unscaling reductions of the NEXT step),
+//   state      = {consecutive good steps, skipped steps in total}.
+__global__ void clip_coef_scaled_kernel(const float* __restrict__ sumsq, float max_norm, float grad_mult, float* __restrict__ coef,
+                                        float* __restrict__ loss_scale, float* __restrict__ state, float growth_interval, float backoff,
+                                        float growth, float min_scale, float max_scale) {
+  const float norm = grad_mult * sqrtf(sumsq[0]);
+  const bool ok = isfinite(norm);
+  float c = 1.0f;
+  if (max_norm > 0.f && ok) c = fminf(1.0f, max_norm / (norm + 1e-6f));
+  coef[0] = ok ? c * grad_mult : 0.f;
+  coef[1] = ok ? 1.f : 0.f;
+  coef[2] = norm;
+  float sc = loss_scale[0], good = state[0];
+  if (!ok) {
+    sc = fmaxf(min_scale, sc * backoff);
+    good = 0.f;
+    state[1] += 1.f;
+  } else if (++good >= growth_interval) {
+    sc = fminf(max_scale, sc * growth);
+    good = 0.f;
+  }
+  state[0] = good;
+  loss_scale[0] = sc;
+  loss_scale[1] = 1.0f / sc;
+}
+
 // hyper = {lr, beta1, beta2, eps, weight_decay, bias_corr1, bias_corr2, -}: device-resident so that a captured CUDA graph
 // of the training step can be replayed with a new learning rate / step count every iteration.
 __global__ void set_hyper_kernel(float* __restrict__ hyper, float a, float b, float c, float d, float e, float f, float g, float h) {

@@ -426,7 +426,8 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) embed_ln_bwd_kernel(const __ha
                                                                        float* __restrict__ dpos, float* __restrict__ dtype_tab,
                                                                        float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                                        const float* __restrict__ alpha_ptr, int rows, int S, int H, float eps,
-                                                                       DropCfg drop) {
+                                                                       DropCfg drop, long long pad_id, const float* __restrict__ inputs_embeds,
+                                                                       float* __restrict__ d_inputs_embeds) {
   extern __shared__ float red[];   // [3][ROW_WARPS][H]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float alpha = alpha_ptr ? *alpha_ptr : 1.0f;
@@ -440,13 +441,19 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) embed_ln_bwd_kernel(const __ha
     if (i < nv) gm[i] = load8(gamma + (i * 32 + lane) * 8);
   }
   for (int row = blockIdx.x * ROW_WARPS + warp; row < rows; row += gridDim.x * ROW_WARPS) {
-    const size_t wi = static_cast<size_t>(ids[row]), pi = static_cast<size_t>(pos ? pos[row] : (row % S)), ti = static_cast<size_t>(tt ? tt[row] : 0);
+    // word row: gathered by id, or the caller's inputs_embeds row (then the gradient goes to d_inputs_embeds instead of the table).
+    // nn.Embedding(padding_idx=pad_token_id) (bert_model.py:171): the pad row takes part in the forward but receives NO gradient.
+    const long long wid = ids ? static_cast<long long>(ids[row]) : -1;
+    const size_t pi = static_cast<size_t>(pos ? pos[row] : (row % S)), ti = static_cast<size_t>(tt ? tt[row] : 0);
+    const float* wrow = ids ? word + static_cast<size_t>(wid) * H : inputs_embeds + static_cast<size_t>(row) * H;
+    float* dwrow = ids ? ((dword && wid != pad_id) ? dword + static_cast<size_t>(wid) * H : nullptr)
+                       : (d_inputs_embeds ? d_inputs_embeds + static_cast<size_t>(row) * H : nullptr);
     Vec8 v[ROW_MAXV];
 #pragma unroll
     for (int i = 0; i < ROW_MAXV; ++i)
       if (i < nv) {
         const int c = (i * 32 + lane) * 8;
-        const Vec8 a = load8(word + wi * H + c), b = load8(pos_tab + pi * H + c), d = load8(type_tab + ti * H + c);
+        const Vec8 a = load8(wrow + c), b = load8(pos_tab + pi * H + c), d = load8(type_tab + ti * H + c);
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[i].v[j] = a.v[j] + d.v[j] + b.v[j];
       }
@@ -484,8 +491,15 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) embed_ln_bwd_kernel(const __ha
         float dx[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) dx[j] = rstd * (g[i].v[j] - s1 - v[i].v[j] * s2) * alpha;
-        red_add_v4(dword + wi * H + c, dx[0], dx[1], dx[2], dx[3]);
-        red_add_v4(dword + wi * H + c + 4, dx[4], dx[5], dx[6], dx[7]);
+        if (dwrow) {
+          if (ids) {
+            red_add_v4(dwrow + c, dx[0], dx[1], dx[2], dx[3]);
+            red_add_v4(dwrow + c + 4, dx[4], dx[5], dx[6], dx[7]);
+          } else {                                      // one row per token: a plain store
+            *reinterpret_cast<float4*>(dwrow + c) = make_float4(dx[0], dx[1], dx[2], dx[3]);
+            *reinterpret_cast<float4*>(dwrow + c + 4) = make_float4(dx[4], dx[5], dx[6], dx[7]);
+          }
+        }
         red_add_v4(dpos + pi * H + c, dx[0], dx[1], dx[2], dx[3]);
         red_add_v4(dpos + pi * H + c + 4, dx[4], dx[5], dx[6], dx[7]);
         if (ti == 0) {

@@ -68,8 +68,23 @@ class FlatParams:
     def _sig(self):
         return tuple(p.data_ptr() for p in self.params.values())
 
-    def intact(self) -> bool:
-        return self._sig() == self.signature
+    def intact(self, named: Optional[Sequence[Tuple[str, torch.nn.Parameter]]] = None) -> bool:
+        """True while the packed buffers still ARE the module's parameters.  `named` = the module's CURRENT (name, Parameter)
+        list: a Parameter object that was replaced (older transformers' `resize_token_embeddings` -> `set_input_embeddings`,
+        `load_state_dict(assign=True)`, a swapped sub-module — ts_sentence_seq_labeling.py:284 resizes the vocabulary) leaves the
+        OLD object pointing into the flat buffer, so comparing only the packed objects' own data_ptrs would call a stale,
+        smaller table intact; the identity of every current parameter is compared as well."""
+        if self._sig() != self.signature:
+            return False
+        if named is None:
+            return True
+        if len(named) != len(self.names):
+            return False
+        for n, p in named:
+            q = self.params.get(n)
+            if q is not p or p.data_ptr() != self.flat32.data_ptr() + 4 * self.offsets[n] or p.shape != q.shape:
+                return False
+        return True
 
     def _view(self, flat: Tensor, name: str, n_extra: Sequence[str] = ()) -> Tensor:
         p = self.params[name]
@@ -127,6 +142,7 @@ class LayerSaved:
 class Saved:
     B: int = 0; S: int = 0
     ids: Optional[Tensor] = None; tt: Optional[Tensor] = None; pos: Optional[Tensor] = None
+    inputs_embeds: Optional[Tensor] = None
     key_bias: Optional[Tensor] = None; kv_len: Optional[Tensor] = None
     layers: List[LayerSaved] = field(default_factory=list)
     out: Tensor = None
@@ -154,10 +170,13 @@ class EncoderEngine:
     """Runs embeddings + L encoder layers on the packed parameters."""
 
     def __init__(self, flat: FlatParams, hidden: int, heads: int, inter: int, n_layers: int, eps: float,
-                 prefix_layers: str = "encoder.layer."):
+                 prefix_layers: str = "encoder.layer.", pad_id: Optional[int] = None):
+        """`pad_id` = config.pad_token_id: nn.Embedding(padding_idx=...) of BertEmbeddings (bert_model.py:171) — that row of
+        the word table takes part in the forward and receives no gradient."""
         assert hidden == heads * 64, "the sm_100a attention kernels are specialised for head_dim 64"
         self.flat, self.H, self.heads, self.I, self.L, self.eps = flat, hidden, heads, inter, n_layers, eps
         self.prefix = prefix_layers
+        self.pad_id = pad_id
 
     # ---- views -------------------------------------------------------------------------------------------------
     def _lv(self, i: int, kind: str) -> LayerViews:
@@ -213,7 +232,8 @@ class EncoderEngine:
         self.flat.sync_half()
         drop_emb = drop.at(DropPlan.EMB, drop.p_hidden) if drop is not None else None
         x, x32 = self.embed(ids, tt, pos, inputs_embeds, B, S, drop=drop_emb)
-        saved = Saved(B=B, S=S, ids=ids, tt=tt, pos=pos, key_bias=key_bias, kv_len=kv_len, drop_emb=drop_emb) if save else None
+        saved = Saved(B=B, S=S, ids=ids, tt=tt, pos=pos, inputs_embeds=inputs_embeds if ids is None else None, key_bias=key_bias,
+                      kv_len=kv_len, drop_emb=drop_emb) if save else None
         hiddens, probs_all = ([x32] if want_hidden else None), ([] if want_probs else None)
         for i in range(self.L):
             # a layer input that is also returned as a hidden state must survive the layer (blocks.Experimental.resadd)
@@ -239,9 +259,11 @@ class EncoderEngine:
         return dx
 
     def backward(self, saved: Saved, dy: Tensor, inv_scale: Optional[Tensor], *, embeddings: bool = True,
-                 after_layer=None) -> None:
+                 after_layer=None, want_d_inputs_embeds: bool = False) -> Optional[Tensor]:
         """Accumulates all parameter gradients into flat.grad32 (must exist).  `after_layer(i)` is called once layer
-        i's gradients are complete (the data-parallel trainer launches that layer's allreduce there)."""
+        i's gradients are complete (the data-parallel trainer launches that layer's allreduce there).  When the forward ran
+        on `inputs_embeds`, position / type / LayerNorm gradients are still produced and the gradient wrt `inputs_embeds`
+        (fp32 [B*S, H]) is returned if asked for."""
         B, S = saved.B, saved.S
         f = self.flat
         ws = ops.attn_bwd_workspace(B, self.heads, S, dy.device)
@@ -251,10 +273,15 @@ class EncoderEngine:
             saved.layers[i] = None          # release this layer's activations
             if after_layer is not None:
                 after_layer(i)
-        if embeddings and saved.ids is not None:
+        d_emb = None
+        if embeddings and (saved.ids is not None or saved.inputs_embeds is not None):
+            if saved.ids is None and want_d_inputs_embeds:
+                d_emb = torch.empty(B * S, self.H, dtype=torch.float32, device=dy.device)
             ops.embed_ln_bwd(dy, None, saved.ids, saved.tt, saved.pos, f.view32(EMB_NAMES[0]), f.view32(EMB_NAMES[1]),
                              f.view32(EMB_NAMES[2]), f.view32(EMB_NAMES[3]), f.viewg(EMB_NAMES[0]), f.viewg(EMB_NAMES[1]),
                              f.viewg(EMB_NAMES[2]), f.viewg(EMB_NAMES[3]), f.viewg(EMB_NAMES[4]), inv_scale, self.eps, B * S,
-                             S, self.H, drop=saved.drop_emb)
+                             S, self.H, drop=saved.drop_emb, pad_id=self.pad_id, inputs_embeds=saved.inputs_embeds,
+                             d_inputs_embeds=d_emb)
         if after_layer is not None:
             after_layer(-1)
+        return d_emb

@@ -29,7 +29,7 @@ _PROTOS = {
     "b200_layernorm_fwd": [_p, _i, _p, _p, _p, _p, _p, _p, _i, _i, _f, _p],
     "b200_layernorm_bwd": [_p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p],
     "b200_embed_ln_fwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _p],
-    "b200_embed_ln_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _p],
+    "b200_embed_ln_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _ll, _p, _p, _p],
     "b200_cls_head_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _p],
     "b200_ce_stats": [_p, _p, _p, _p, _i, _i, _p],
     "b200_cls_head_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
@@ -46,11 +46,12 @@ _PROTOS = {
     "b200_attn_bwd": [_p, _i, _i, _p, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "b200_grad_sumsq": [_p, _sz, _p, _p],
     "b200_clip_coef": [_p, _f, _f, _p, _p],
+    "b200_clip_coef_scaled": [_p, _f, _f, _p, _p, _p, _i, _f, _f, _f, _f, _p],
     "b200_adamw_step": [_p, _p, _p, _p, _p, _sz, _f, _f, _f, _f, _f, _f, _f, _p, _p],
     "b200_gemm_f16_drop": [_p, _i, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p, _i, _i, _p, C.c_uint, _f, _p],
     "b200_layernorm_bwd_drop": [_p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, C.c_uint, _f, _p],
     "b200_embed_ln_fwd_drop": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _p, C.c_uint, _f, _p],
-    "b200_embed_ln_bwd_drop": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _p, C.c_uint, _f, _p],
+    "b200_embed_ln_bwd_drop": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _ll, _p, _p, _p, C.c_uint, _f, _p],
     "b200_attn_fwd_drop": [_p, _i, _i, _p, _i, _i, _i, _p, _p, _p, _i, _p, _i, _i, _i, _i, _p, C.c_uint, _f, _p],
     "b200_attn_bwd_drop": [_p, _i, _i, _p, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p, C.c_uint, _f, _p],
     "b200_cls_head_fwd_drop": [_p, _p, _p, _p, _p, _i, _i, _i, _p, C.c_uint, _f, _p],

@@ -106,9 +106,11 @@ class _EncoderFn(torch.autograd.Function):
     by optional per-layer hidden states and attention probabilities (returned detached)."""
 
     @staticmethod
-    def forward(ctx, model, ids, tt, pos, inputs_embeds, key_bias, kv_len, B, S, want_hidden, want_probs, drop, *params):
+    def forward(ctx, model, ids, tt, pos, inputs_embeds, key_bias, kv_len, B, S, want_hidden, want_probs, drop, need_grad, *params):
+        # `need_grad` is decided by the module's forward, where the grad MODE is visible: ctx.needs_input_grad only mirrors
+        # requires_grad of the inputs and stays True under torch.no_grad() / in eval, which used to make every inference
+        # forward save all L layers' activations.
         eng: EncoderEngine = model._engine
-        need_grad = any(ctx.needs_input_grad[12:])
         x16, x32, saved, hiddens, probs = eng.forward(ids, tt, pos, inputs_embeds, key_bias, kv_len, B, S, save=need_grad,
                                                  want_hidden=want_hidden, want_probs=want_probs, drop=drop)
         ctx.model, ctx.saved, ctx.n_params = model, saved, len(params)
@@ -137,12 +139,14 @@ class _EncoderFn(torch.autograd.Function):
         ops.scale_cast_grad(g_last.view(-1), dy.view(-1), scale, slot, target=1024.0)
         keep, flat.grad32 = flat.grad32, torch.zeros_like(flat.flat32)       # fresh buffer: autograd owns the result
         try:
-            eng.backward(saved, dy, scale[1:2])
+            d_emb = eng.backward(saved, dy, scale[1:2], want_d_inputs_embeds=ctx.needs_input_grad[4])
             grads = tuple(flat.viewg(n) if flat.params[n].requires_grad else None for n in flat.names)
         finally:
             flat.grad32 = keep
         ctx.saved = None
-        return (None,) * 12 + grads
+        if d_emb is not None:
+            d_emb = d_emb.view(saved.B, saved.S, eng.H)
+        return (None,) * 4 + (d_emb,) + (None,) * 8 + grads
 
 
 # ---------------------------------------------------------------------------- the model
@@ -179,19 +183,19 @@ class BertModel(BertPreTrainedModel):
             names += layer_param_names(i)
         return [(n, own[n]) for n in names]
 
-    def b200_engine(self, device=None) -> EncoderEngine:
-        """(Re)build the packed parameter buffers if the module's parameters moved (``.to()``, resize, load)."""
+    def b200_engine(self, device=None, named=None) -> EncoderEngine:
+        """(Re)build the packed parameter buffers if the module's parameters moved or were replaced (``.to()``, resize, load)."""
         eng = self._engine
-        if eng is not None and eng.flat.intact():
+        named = named if named is not None else self._hot_named_params()
+        if eng is not None and eng.flat.intact(named):
             return eng
-        named = self._hot_named_params()
         device = device or named[0][1].device
         if torch.device(device).type != "cuda":
             raise B200Error("B200 BertModel runs on CUDA devices only (no CPU fallback): move the model with .cuda()")
         flat = FlatParams(named, device)
         c = self.config
         self._engine = EncoderEngine(flat, c.hidden_size, c.num_attention_heads, c.intermediate_size, c.num_hidden_layers,
-                                     float(c.layer_norm_eps))
+                                     float(c.layer_norm_eps), pad_id=self.embeddings.word_embeddings.padding_idx)
         return self._engine
 
     # ---- forward ---------------------------------------------------------------------------------------------------
@@ -211,7 +215,8 @@ class BertModel(BertPreTrainedModel):
         B, S = src.shape[0], src.shape[1]
         if S > cfg.max_position_embeddings and position_ids is None:
             raise ValueError(f"sequence length {S} > max_position_embeddings {cfg.max_position_embeddings}")
-        eng = self.b200_engine(src.device)
+        named = self._hot_named_params()
+        eng = self.b200_engine(src.device, named)
         drop = None
         if self.training and (cfg.hidden_dropout_prob > 0 or cfg.attention_probs_dropout_prob > 0):
             # one fresh base seed per forward, drawn from torch's CPU generator (so torch.manual_seed governs it, as it does
@@ -220,7 +225,7 @@ class BertModel(BertPreTrainedModel):
             drop = DropPlan(seed, cfg.hidden_dropout_prob, cfg.attention_probs_dropout_prob)
 
         ids = input_ids.contiguous().view(-1) if input_ids is not None else None
-        emb = inputs_embeds.contiguous().float().view(B * S, -1) if inputs_embeds is not None else None
+        emb = inputs_embeds.contiguous().float() if inputs_embeds is not None else None       # [B,S,H]; the kernels index it as [B*S,H]
         tt = token_type_ids.contiguous().view(-1) if token_type_ids is not None else None
         if position_ids is None:
             # honour an in-place edited buffer (ponet_topic_segmentation.py:471-482 rewrites embeddings.position_ids)
@@ -232,9 +237,10 @@ class BertModel(BertPreTrainedModel):
                 raise B200Error("attention_mask must be [batch, seq] (key padding mask)")
             key_bias, kv_len = ops.mask_to_bias(attention_mask)
 
-        params = [p for _, p in self._hot_named_params()]
+        params = [p for _, p in named]
+        need_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in params) or (emb is not None and emb.requires_grad))
         outs = _EncoderFn.apply(self, ids, tt, pos, emb, key_bias, kv_len, B, S, bool(output_hidden_states),
-                                bool(output_attentions), drop, *params)
+                                bool(output_attentions), drop, need_grad, *params)
         seq = outs[0]
         k = 1
         hidden_states = attentions = None

@@ -20,7 +20,7 @@ from torch import nn
 
 from . import ops
 from .blocks import (AttnWeights, FfnWeights, attn_block_bwd, attn_block_fwd, ffn_block_bwd, ffn_block_fwd)
-from .engine import FlatParams
+from .engine import DropPlan, FlatParams
 from .lib import B200Error
 from .modeling_bert import BertAttention, BertIntermediate, BertOutput
 
@@ -54,14 +54,30 @@ class _Packed(nn.Module):
 
     def _flat(self, device) -> FlatParams:
         f = getattr(self, "_flat_cache", None)
-        if f is not None and f.intact():
+        own = dict(self.named_parameters())
+        named = [(n, own[n]) for n in self._order]
+        if f is not None and f.intact(named):
             f.sync_half()
             return f
         if torch.device(device).type != "cuda":
             raise B200Error(f"{type(self).__name__} runs on CUDA devices only (no CPU fallback)")
-        own = dict(self.named_parameters())
-        object.__setattr__(self, "_flat_cache", FlatParams([(n, own[n]) for n in self._order], device))
+        object.__setattr__(self, "_flat_cache", FlatParams(named, device))
         return self._flat_cache
+
+    def _drop_plan(self, device) -> Optional[DropPlan]:
+        """The reference layers apply nn.Dropout to the attention probabilities and to both dense outputs
+        (bert_model.py:338,373,451; probabilities handed in at ca_encoder.py:40-44 / ma_encoder.py:33-37): in train mode with
+        p > 0 every forward draws one base seed (torch's CPU generator, so torch.manual_seed governs it) and the kernels derive
+        the per-site masks from it; the backward regenerates them."""
+        if not self.training or (self.p_hidden <= 0.0 and self.p_attn <= 0.0):
+            return None
+        seed = torch.randint(0, 2 ** 31 - 1, (1,), dtype=torch.int32).to(device, non_blocking=True)
+        return DropPlan(seed, self.p_hidden, self.p_attn)
+
+    def _need_grad(self, *inputs) -> bool:
+        if not torch.is_grad_enabled():
+            return False
+        return any(p.requires_grad for p in self.parameters()) or any(t is not None and t.requires_grad for t in inputs)
 
     @staticmethod
     def _attn_views(f: FlatParams, prefix: str, kind: str, cross: bool) -> AttnWeights:
@@ -84,26 +100,28 @@ class _LayerFn(torch.autograd.Function):
     """One self-attention layer or one cross layer as a single autograd node."""
 
     @staticmethod
-    def forward(ctx, layer, x, kv, self_bias, cross_bias, do_ffn, *params):
+    def forward(ctx, layer, x, kv, self_bias, cross_bias, do_ffn, drop, need_grad, *params):
+        # need_grad is decided by the module (grad MODE is not visible in ctx.needs_input_grad); drop: DropPlan or None
         f: FlatParams = layer._flat(x.device)
         B, N, H = x.shape
         heads, eps = layer.heads, layer.eps
-        need_grad = any(ctx.needs_input_grad[1:3]) or any(ctx.needs_input_grad[6:])
+        d = (lambda k: drop.layer(0, k)) if drop is not None else (lambda k: None)
         x32 = x.detach().to(F32).contiguous().view(B * N, H)
         x16 = _to16(x32)
         saved = []
         y16, y32, sv, _ = attn_block_fwd(layer._attn_views(f, "attention.", "p", False), x16, x32, B, N, heads, eps, self_bias, None,
-                                         save=need_grad)
+                                         save=need_grad, drop_attn=d(DropPlan.ATTN), drop_hidden=d(DropPlan.ATTN_OUT))
         saved.append(sv)
         Nk = None
         if kv is not None:
             Nk = kv.shape[1]
             kv16 = _to16(kv.detach().to(F32).contiguous().view(B * Nk, kv.shape[2]))
             y16, y32, sv, _ = attn_block_fwd(layer._attn_views(f, "crossattention.", "p", True), y16, y32, B, N, heads, eps, cross_bias,
-                                             None, save=need_grad, kv16=kv16, Sk=Nk)
+                                             None, save=need_grad, kv16=kv16, Sk=Nk, drop_attn=d(DropPlan.XATTN),
+                                             drop_hidden=d(DropPlan.XATTN_OUT))
             saved.append(sv)
         if do_ffn:
-            y16, y32, sv = ffn_block_fwd(layer._ffn_views(f, "p"), y16, y32, eps, save=need_grad)
+            y16, y32, sv = ffn_block_fwd(layer._ffn_views(f, "p"), y16, y32, eps, save=need_grad, drop_hidden=d(DropPlan.FFN_OUT))
             saved.append(sv)
         ctx.layer, ctx.saved, ctx.dims = layer, (saved if need_grad else None), (B, N, Nk, H, kv.shape[2] if kv is not None else 0)
         ctx.biases, ctx.do_ffn, ctx.has_kv = (self_bias, cross_bias), do_ffn, kv is not None
@@ -141,7 +159,7 @@ class _LayerFn(torch.autograd.Function):
         finally:
             f.grad32 = keep
         ctx.saved = None
-        return (None, dx32, dkv32, None, None, None) + grads
+        return (None, dx32, dkv32, None, None, None, None, None) + grads
 
 
 class BertSelfAttnLayer(_Packed):
@@ -157,6 +175,8 @@ class BertSelfAttnLayer(_Packed):
         self.intermediate = BertIntermediate(bert_config)
         self.output = BertOutput(bert_config)
         self.heads, self.eps = bert_config.num_attention_heads, float(bert_config.layer_norm_eps)
+        self.p_hidden = float(getattr(bert_config, "hidden_dropout_prob", 0.0) or 0.0)
+        self.p_attn = float(getattr(bert_config, "attention_probs_dropout_prob", 0.0) or 0.0)
 
     def forward(self, hidden_states, attention_mask, output_attentions=False):
         if output_attentions:
@@ -164,7 +184,8 @@ class BertSelfAttnLayer(_Packed):
         B, N, _ = hidden_states.shape
         bias = _mask_to_key_bias(attention_mask, B, N)
         own = dict(self.named_parameters())
-        y = _LayerFn.apply(self, hidden_states, None, bias, None, True, *[own[n] for n in self._order])
+        y = _LayerFn.apply(self, hidden_states, None, bias, None, True, self._drop_plan(hidden_states.device),
+                           self._need_grad(hidden_states), *[own[n] for n in self._order])
         return (y,)
 
 
@@ -184,6 +205,8 @@ class BertCrossLayer(_Packed):
         self.intermediate = BertIntermediate(config)
         self.output = BertOutput(config)
         self.heads, self.eps = config.num_attention_heads, float(config.layer_norm_eps)
+        self.p_hidden = float(getattr(config, "hidden_dropout_prob", 0.0) or 0.0)
+        self.p_attn = float(getattr(config, "attention_probs_dropout_prob", 0.0) or 0.0)
 
     def forward(self, hidden_states, encoder_hidden_states, attention_mask, encoder_attention_mask, output_attentions=False,
                 do_ffn=True):
@@ -193,7 +216,8 @@ class BertCrossLayer(_Packed):
         sb = _mask_to_key_bias(attention_mask, B, N)
         cb = _mask_to_key_bias(encoder_attention_mask, B, encoder_hidden_states.shape[1])
         own = dict(self.named_parameters())
-        y = _LayerFn.apply(self, hidden_states, encoder_hidden_states, sb, cb, bool(do_ffn), *[own[n] for n in self._order])
+        y = _LayerFn.apply(self, hidden_states, encoder_hidden_states, sb, cb, bool(do_ffn), self._drop_plan(hidden_states.device),
+                           self._need_grad(hidden_states, encoder_hidden_states), *[own[n] for n in self._order])
         return (y,)
 
 

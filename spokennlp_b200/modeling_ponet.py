@@ -23,7 +23,7 @@ from transformers.modeling_outputs import BaseModelOutputWithPoolingAndCrossAtte
 
 from . import ops
 from .blocks import FfnWeights, ffn_block_bwd, ffn_block_fwd
-from .engine import EMB_NAMES, FlatParams
+from .engine import EMB_NAMES, DropPlan, FlatParams
 from .lib import B200Error
 from .modeling_bert import BertEmbeddings, BertIntermediate, BertOutput, BertPooler, BertSelfOutput
 
@@ -85,15 +85,18 @@ class _PoNetFn(torch.autograd.Function):
     """Embeddings + L PoNet layers as one autograd node (same bridge as modeling_bert._EncoderFn)."""
 
     @staticmethod
-    def forward(ctx, model, ids, tt, pos, key_bias, seg, B, S, want_hidden, *params):
+    def forward(ctx, model, ids, tt, pos, key_bias, seg, B, S, want_hidden, drop, save, *params):
+        # `save` (= gradients will be asked for) is decided by the module, where the grad mode is visible; `drop`: DropPlan or
+        # None — hidden dropout after the embeddings, the attention output dense and the FFN output dense, as in BERT (PoNet's
+        # pooling mixer has no probabilities to drop).
         f: FlatParams = model._flat
         cfg = model.config
         H, heads, eps, dev = cfg.hidden_size, cfg.num_attention_heads, float(cfg.layer_norm_eps), ids.device
         M, nseg = B * S, S + 2
-        save = any(ctx.needs_input_grad[9:])
+        drop_emb = drop.at(DropPlan.EMB, drop.p_hidden) if drop is not None else None
         x32 = torch.empty(M, H, dtype=F32, device=dev)
         x16 = ops.embed_ln_fwd(ids, tt, pos, None, f.view32(EMB_NAMES[0]), f.view32(EMB_NAMES[1]), f.view32(EMB_NAMES[2]),
-                               f.view32(EMB_NAMES[3]), f.view32(EMB_NAMES[4]), eps, M, S, H, y32=x32)
+                               f.view32(EMB_NAMES[3]), f.view32(EMB_NAMES[4]), eps, M, S, H, y32=x32, drop=drop_emb)
         hiddens = [x32.view(B, S, H)] if want_hidden else []
         saved = []
         for i in range(cfg.num_hidden_layers):
@@ -103,18 +106,20 @@ class _PoNetFn(torch.autograd.Function):
             mix = torch.empty(M, H, dtype=F16, device=dev)
             ws = ops.ponet_mix_fwd(proj, seg, mix, B, S, heads, nseg, key_bias=key_bias)
             pre = torch.empty(M, H, dtype=F32, device=dev)
-            ops.gemm(mix, f.view16(n[10]), pre, epilogue=ops.EPI_BIAS_RES32, bias=f.view32(n[11]), aux=x32)
+            d_ao = drop.layer(i, DropPlan.ATTN_OUT) if drop is not None else None
+            ops.gemm(mix, f.view16(n[10]), pre, epilogue=ops.EPI_BIAS_RES32, bias=f.view32(n[11]), aux=x32, drop=d_ao)
             mean = torch.empty(M, dtype=F32, device=dev) if save else None
             rstd = torch.empty(M, dtype=F32, device=dev) if save else None
             a32 = torch.empty(M, H, dtype=F32, device=dev)
             a16 = ops.layernorm_fwd(pre, f.view32(n[12]), f.view32(n[13]), eps, y32=a32, mean=mean, rstd=rstd)
-            y16, y32, svf = ffn_block_fwd(_ffn_views(f, n, "p"), a16, a32, eps, save=save)
+            y16, y32, svf = ffn_block_fwd(_ffn_views(f, n, "p"), a16, a32, eps, save=save,
+                                          drop_hidden=drop.layer(i, DropPlan.FFN_OUT) if drop is not None else None)
             if save:
-                saved.append((x16, proj, ws, mix, pre, mean, rstd, svf))
+                saved.append((x16, proj, ws, mix, pre, mean, rstd, svf, d_ao))
             x16, x32 = y16, y32
             if want_hidden:
                 hiddens.append(x32.view(B, S, H))
-        ctx.model, ctx.saved, ctx.meta = model, (saved if save else None), (ids, tt, pos, key_bias, seg, B, S)
+        ctx.model, ctx.saved, ctx.meta = model, (saved if save else None), (ids, tt, pos, key_bias, seg, B, S, drop_emb)
         outs = [x32.view(B, S, H)] + (hiddens if want_hidden else [])
         ctx.mark_non_differentiable(*outs[1:])
         return tuple(outs)
@@ -124,7 +129,7 @@ class _PoNetFn(torch.autograd.Function):
         model, saved = ctx.model, ctx.saved
         if saved is None:
             raise B200Error("backward through a forward that ran without grad")
-        ids, tt, pos, key_bias, seg, B, S = ctx.meta
+        ids, tt, pos, key_bias, seg, B, S, drop_emb = ctx.meta
         f: FlatParams = model._flat
         cfg = model.config
         H, heads, eps, dev = cfg.hidden_size, cfg.num_attention_heads, float(cfg.layer_norm_eps), g_last.device
@@ -138,14 +143,20 @@ class _PoNetFn(torch.autograd.Function):
         try:
             for i in reversed(range(cfg.num_hidden_layers)):
                 n = ponet_layer_names(i)
-                x16, proj, ws, mix, pre, mean, rstd, svf = saved[i]
+                x16, proj, ws, mix, pre, mean, rstd, svf, d_ao = saved[i]
                 saved[i] = None
                 d_a = ffn_block_bwd(_ffn_views(f, n, "p"), _ffn_views(f, n, "g"), svf, dy, inv)
                 d_pre = torch.empty(M, H, dtype=F16, device=dev)
-                ops.layernorm_bwd(d_a, pre, mean, rstd, f.view32(n[12]), d_pre, f.viewg(n[12]), f.viewg(n[13]), dbias=f.viewg(n[11]), alpha=inv)
-                ops.gemm(d_pre, mix, f.viewg(n[10]), a_layout=1, b_layout=1, epilogue=ops.EPI_ATOMIC, alpha=inv, k_splits=ops.wgrad_splits(H, H, M))
+                d_den = d_pre                        # gradient wrt the dense output = d_pre x the regenerated dropout mask
+                if d_ao is not None and d_ao.p > 0.0:
+                    d_den = torch.empty_like(d_pre)
+                    ops.layernorm_bwd(d_a, pre, mean, rstd, f.view32(n[12]), d_pre, f.viewg(n[12]), f.viewg(n[13]), dbias=f.viewg(n[11]),
+                                      alpha=inv, dx_drop=d_den, drop=d_ao)
+                else:
+                    ops.layernorm_bwd(d_a, pre, mean, rstd, f.view32(n[12]), d_pre, f.viewg(n[12]), f.viewg(n[13]), dbias=f.viewg(n[11]), alpha=inv)
+                ops.gemm(d_den, mix, f.viewg(n[10]), a_layout=1, b_layout=1, epilogue=ops.EPI_ATOMIC, alpha=inv, k_splits=ops.wgrad_splits(H, H, M))
                 dmix = torch.empty(M, H, dtype=F16, device=dev)
-                ops.gemm(d_pre, f.view16(n[10]), dmix, b_layout=1)
+                ops.gemm(d_den, f.view16(n[10]), dmix, b_layout=1)
                 dproj = torch.empty(M, 5 * H, dtype=F16, device=dev)
                 ops.ponet_mix_bwd(proj, dmix, seg, ws, dproj, B, S, heads, nseg, key_bias=key_bias)
                 ops.colsum(dproj, f.viewg(n[5], tuple(n[6:10])), inv)
@@ -155,12 +166,13 @@ class _PoNetFn(torch.autograd.Function):
                 ops.gemm(dproj, f.view16(n[0], tuple(n[1:5])), dy, b_layout=1, epilogue=ops.EPI_ADD, aux=d_pre)
             ops.embed_ln_bwd(dy, None, ids, tt, pos, f.view32(EMB_NAMES[0]), f.view32(EMB_NAMES[1]), f.view32(EMB_NAMES[2]),
                              f.view32(EMB_NAMES[3]), f.viewg(EMB_NAMES[0]), f.viewg(EMB_NAMES[1]), f.viewg(EMB_NAMES[2]),
-                             f.viewg(EMB_NAMES[3]), f.viewg(EMB_NAMES[4]), inv, eps, M, S, H)
+                             f.viewg(EMB_NAMES[3]), f.viewg(EMB_NAMES[4]), inv, eps, M, S, H, drop=drop_emb,
+                             pad_id=model.embeddings.word_embeddings.padding_idx)
             grads = tuple(f.viewg(nm) if f.params[nm].requires_grad else None for nm in f.names)
         finally:
             f.grad32 = keep
         ctx.saved = None
-        return (None,) * 9 + grads
+        return (None,) * 11 + grads
 
 
 def _ffn_views(f: FlatParams, n, kind: str) -> FfnWeights:
@@ -194,16 +206,17 @@ class PoNetModel(nn.Module):
 
     def _packed(self, device) -> FlatParams:
         f = self._flat
-        if f is not None and f.intact():
-            f.sync_half()
-            return f
-        if torch.device(device).type != "cuda":
-            raise B200Error("B200 PoNetModel runs on CUDA devices only (no CPU fallback)")
         own = dict(self.named_parameters())
         names = list(EMB_NAMES)
         for i in range(self.config.num_hidden_layers):
             names += ponet_layer_names(i)
-        self._flat = FlatParams([(n, own[n]) for n in names], device)
+        named = [(n, own[n]) for n in names]
+        if f is not None and f.intact(named):        # also notices a replaced Parameter object (resize_token_embeddings)
+            f.sync_half()
+            return f
+        if torch.device(device).type != "cuda":
+            raise B200Error("B200 PoNetModel runs on CUDA devices only (no CPU fallback)")
+        self._flat = FlatParams(named, device)
         return self._flat
 
     def forward(self, input_ids=None, attention_mask=None, token_type_ids=None, segment_ids=None, position_ids=None, head_mask=None,
@@ -229,7 +242,14 @@ class PoNetModel(nn.Module):
             key_bias, _ = ops.mask_to_bias(attention_mask)
         seg = segment_ids.contiguous().to(torch.int64)
         params = [f.params[n] for n in f.names]
-        outs = _PoNetFn.apply(self, input_ids.contiguous().view(-1), tt, pos, key_bias, seg, B, S, bool(output_hidden_states), *params)
+        drop = None
+        p_hidden = float(getattr(cfg, "hidden_dropout_prob", 0.0) or 0.0)
+        if self.training and p_hidden > 0.0:
+            seed = torch.randint(0, 2 ** 31 - 1, (1,), dtype=torch.int32).to(input_ids.device, non_blocking=True)
+            drop = DropPlan(seed, p_hidden, 0.0)
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        outs = _PoNetFn.apply(self, input_ids.contiguous().view(-1), tt, pos, key_bias, seg, B, S, bool(output_hidden_states), drop,
+                              need_grad, *params)
         seq = outs[0]
         hs = None
         if output_hidden_states:

@@ -211,11 +211,14 @@ def embed_ln_fwd(ids, tt, pos, inputs_embeds, word, pos_tab, type_tab, gamma, be
 
 
 def embed_ln_bwd(dy, dy2, ids, tt, pos, word, pos_tab, type_tab, gamma, dword, dpos, dtype_tab, dgamma, dbeta, alpha, eps,
-                 rows, S, H, drop=None):
+                 rows, S, H, drop=None, *, pad_id: Optional[int] = None, inputs_embeds=None, d_inputs_embeds=None):
+    """`pad_id`: nn.Embedding's padding_idx (config.pad_token_id) — that row of dword receives nothing; None = no padding index.
+    `inputs_embeds` / `d_inputs_embeds`: the forward ran on caller-provided embeddings (ids is None)."""
     seed, site, p = _drop_args(drop)
     rc = L.load().b200_embed_ln_bwd_drop(_ptr(dy), _ptr(dy2), _ptr(ids), _ptr(tt), _ptr(pos), _ptr(word), _ptr(pos_tab),
                                          _ptr(type_tab), _ptr(gamma), _ptr(dword), _ptr(dpos), _ptr(dtype_tab), _ptr(dgamma),
-                                         _ptr(dbeta), _ptr(alpha), rows, S, H, float(eps), seed, site, p, _stream())
+                                         _ptr(dbeta), _ptr(alpha), rows, S, H, float(eps), -1 if pad_id is None else int(pad_id),
+                                         _ptr(inputs_embeds), _ptr(d_inputs_embeds), seed, site, p, _stream())
     L.check(rc, "b200_embed_ln_bwd")
 
 
@@ -302,6 +305,19 @@ def grad_sumsq(g: Tensor, sumsq: Tensor) -> Tensor:
 
 def clip_coef(sumsq: Tensor, coef: Tensor, max_norm: float, grad_mult: float = 1.0) -> Tensor:
     L.check(L.load().b200_clip_coef(_ptr(sumsq), float(max_norm), float(grad_mult), _ptr(coef), _stream()), "b200_clip_coef")
+    return coef
+
+
+def clip_coef_scaled(sumsq: Tensor, coef: Tensor, max_norm: float, grad_mult: float, loss_scale: Tensor, state: Tensor, *,
+                     growth_interval: int = 2000, backoff: float = 0.5, growth: float = 2.0, min_scale: float = 1.0,
+                     max_scale: float = 2.0 ** 24) -> Tensor:
+    """clip_coef + dynamic loss scaling on the device: `loss_scale` = fp32 [2] {scale, 1/scale}, `state` = fp32 [2]
+    {consecutive finite steps, skipped steps}."""
+    _req(loss_scale, torch.float32, "loss_scale")
+    _req(state, torch.float32, "state")
+    L.check(L.load().b200_clip_coef_scaled(_ptr(sumsq), float(max_norm), float(grad_mult), _ptr(coef), _ptr(loss_scale), _ptr(state),
+                                           int(growth_interval), float(backoff), float(growth), float(min_scale), float(max_scale),
+                                           _stream()), "b200_clip_coef_scaled")
     return coef
 
 

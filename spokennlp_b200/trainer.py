@@ -55,9 +55,12 @@ class TopicSegModel(nn.Module):
 class DataParallelTrainer:
     def __init__(self, model: TopicSegModel, *, lr: float = 5e-5, total_steps: int = 1000, max_grad_norm: float = 1.0,
                  weight_decay: float = 0.0, loss_scale: float = 32768.0, device: Optional[torch.device] = None,
-                 dropout: bool = True, seed: int = 0):
+                 dropout: bool = True, seed: int = 0, dynamic_loss_scale: bool = True, scale_growth_interval: int = 2000):
         """`dropout=True` honours the config's hidden_dropout_prob / attention_probs_dropout_prob (the reference trains with
-        both at 0.1); `seed` is the base of the per-step dropout seeds."""
+        both at 0.1); `seed` is the base of the per-step dropout seeds.  `loss_scale` is the INITIAL scale of the fp16
+        activation gradients; with `dynamic_loss_scale` a step whose gradient norm is not finite is skipped, halves the scale
+        and is counted (`skipped_steps()`), and the scale doubles again after `scale_growth_interval` finite steps — all on
+        the device, so a replayed CUDA graph adapts too."""
         self.model = model
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         cfg = model.config
@@ -73,7 +76,8 @@ class DataParallelTrainer:
         flat_alias = _Aliased(flat, "bert.")
         self.flat = flat
         self.engine = EncoderEngine(flat_alias, cfg.hidden_size, cfg.num_attention_heads, cfg.intermediate_size,
-                                    cfg.num_hidden_layers, float(cfg.layer_norm_eps))
+                                    cfg.num_hidden_layers, float(cfg.layer_norm_eps),
+                                    pad_id=model.bert.embeddings.word_embeddings.padding_idx)
         model.bert._engine = self.engine
         flat.ensure_grad()
         self.m = torch.zeros_like(flat.flat32)
@@ -104,6 +108,8 @@ class DataParallelTrainer:
                     warnings.warn(f"capped background communicator unavailable ({type(e).__name__}: {e}); using the default one")
                     self.bg_group, self.comm_ctas = None, 0
         self.scale = torch.tensor([loss_scale, 1.0 / loss_scale], dtype=torch.float32, device=self.device)
+        self.dynamic_loss_scale, self.scale_growth_interval = bool(dynamic_loss_scale), int(scale_growth_interval)
+        self.scale_state = torch.zeros(2, dtype=torch.float32, device=self.device)     # {consecutive finite steps, skipped steps}
         self.stats = torch.zeros(2, dtype=torch.float32, device=self.device)
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.coef = torch.zeros(3, dtype=torch.float32, device=self.device)
@@ -194,7 +200,11 @@ class DataParallelTrainer:
             self._push_hyper()
         self.sumsq.zero_()
         ops.grad_sumsq(flat.grad32, self.sumsq)
-        ops.clip_coef(self.sumsq, self.coef, self.max_grad_norm, 1.0 / self.world)
+        if self.dynamic_loss_scale:
+            ops.clip_coef_scaled(self.sumsq, self.coef, self.max_grad_norm, 1.0 / self.world, self.scale, self.scale_state,
+                                 growth_interval=self.scale_growth_interval)
+        else:
+            ops.clip_coef(self.sumsq, self.coef, self.max_grad_norm, 1.0 / self.world)
         ops.adamw_step_dev(flat.flat32, flat.grad32, self.m, self.v, flat.flat16, self.hyper, self.coef, zero_grad=self.fused_zero_grad)
         self._grads_clean = self.fused_zero_grad
         flat.version = flat.cur_version()       # the fused step refreshed the fp16 mirror itself
@@ -234,11 +244,26 @@ class DataParallelTrainer:
         self._static = [t.clone() if t is not None else None for t in (input_ids, attention_mask, token_type_ids, labels)]
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
+        # The warm-up steps are REAL steps (they must exercise every kernel, allocation and collective the capture will see),
+        # so everything they change is put back afterwards: parameters, their fp16 mirror, the moments, the loss scale, the
+        # step counter and learning-rate schedule — a captured run starts from the same state as an eager one.
+        flat = self.flat
+        snap = [t.clone() for t in (flat.flat32, flat.flat16, self.m, self.v, self.scale, self.scale_state)]
+        step0, clean0 = self.step_idx, self._grads_clean
         try:
             with torch.cuda.stream(side):
                 for _ in range(warmup):                       # warm-up off the capture: lazy init, allocator pools, NCCL
+                    self._push_seed()
                     self.forward_backward(*self._static)
                     self.optimizer_step()
+                for dst, src in zip((flat.flat32, flat.flat16, self.m, self.v, self.scale, self.scale_state), snap):
+                    dst.copy_(src)
+                if not self._grads_clean:
+                    flat.grad32.zero_()
+                    self._grads_clean = True
+            self.step_idx = step0
+            flat.version = flat.cur_version()                 # the fp16 mirror was restored together with the fp32 buffer
+            del snap, clean0
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
@@ -270,6 +295,13 @@ class DataParallelTrainer:
     def loss_value(self) -> float:
         s = self.stats.tolist()     # device -> host read
         return s[0] / max(s[1], 1e-30)
+
+    def skipped_steps(self) -> int:
+        """Optimizer steps skipped so far because the gradient norm was not finite (device -> host read)."""
+        return int(self.scale_state[1].item())
+
+    def loss_scale_value(self) -> float:
+        return float(self.scale[0].item())
 
     # ---- end-to-end step: pinned host batch in, loss out ------------------------------------------------------------------
     def step_from_host(self, input_ids, attention_mask, token_type_ids, labels) -> Optional[float]:

@@ -180,19 +180,43 @@ def test_embed_ln_fwd_bwd():
     gamma = 1 + 0.1 * torch.randn(H, generator=g, device="cuda")
     beta = 0.1 * torch.randn(H, generator=g, device="cuda")
     ids = torch.randint(0, V, (B, S), generator=g, device="cuda")
+    ids[:, 3::17] = 0                                   # the padding index at positions that DO receive gradient
     tt = torch.randint(0, 2, (B, S), generator=g, device="cuda")
     y = ops.embed_ln_fwd(ids, tt, None, None, word, pos_tab, type_tab, gamma, beta, 1e-12, B * S, S, H)
     params = [t.clone().requires_grad_(True) for t in (word, pos_tab, type_tab, gamma, beta)]
-    e = params[0][ids] + params[1][torch.arange(S, device="cuda")][None] + params[2][tt]
+    # nn.Embedding(padding_idx=0) semantics (bert_model.py:171): row 0 is read in the forward, gets no gradient
+    e = torch.nn.functional.embedding(ids, params[0], padding_idx=0) + params[1][torch.arange(S, device="cuda")][None] + params[2][tt]
     ref = torch.nn.functional.layer_norm(e, (H,), params[3], params[4], 1e-12)
     rel, msg = _err_report(y, ref.detach().reshape(B * S, H), "embed_ln_fwd")
     assert rel < 4e-4, msg
     dy = _rand16(B * S, H, seed=5, scale=0.01)
     ref.backward(dy.float().view(B, S, H))
     grads = [torch.zeros_like(t) for t in (word, pos_tab, type_tab, gamma, beta)]
-    ops.embed_ln_bwd(dy, None, ids, tt, None, word, pos_tab, type_tab, gamma, *grads, None, 1e-12, B * S, S, H)
+    ops.embed_ln_bwd(dy, None, ids, tt, None, word, pos_tab, type_tab, gamma, *grads, None, 1e-12, B * S, S, H, pad_id=0)
+    assert float(grads[0][0].abs().max()) == 0.0 and float(params[0].grad[0].abs().max()) == 0.0
     for got, p, nm in zip(grads, params, ("dword", "dpos", "dtype", "dgamma", "dbeta")):
         rel, msg = _err_report(got, p.grad, "embed_ln_bwd " + nm)
+        assert rel < 2e-4, msg
+    # without a padding index (pad_id=None -> -1) row 0 accumulates like any other row
+    grads2 = [torch.zeros_like(t) for t in (word, pos_tab, type_tab, gamma, beta)]
+    ops.embed_ln_bwd(dy, None, ids, tt, None, word, pos_tab, type_tab, gamma, *grads2, None, 1e-12, B * S, S, H)
+    assert float(grads2[0][0].abs().max()) > 0.0 and torch.equal(grads2[0][1:], grads[0][1:])
+    # forward on inputs_embeds: same outputs; the backward hands the word-path gradient to d_inputs_embeds
+    emb = word[ids].reshape(B * S, H).contiguous()
+    y2 = ops.embed_ln_fwd(None, tt, None, emb, word, pos_tab, type_tab, gamma, beta, 1e-12, B * S, S, H)
+    assert torch.equal(y2, y)
+    embp = emb.clone().requires_grad_(True)
+    params2 = [t.clone().requires_grad_(True) for t in (pos_tab, type_tab, gamma, beta)]
+    e2 = embp.view(B, S, H) + params2[0][torch.arange(S, device="cuda")][None] + params2[1][tt]
+    torch.nn.functional.layer_norm(e2, (H,), params2[2], params2[3], 1e-12).backward(dy.float().view(B, S, H))
+    grads3 = [torch.zeros_like(t) for t in (pos_tab, type_tab, gamma, beta)]
+    d_emb = torch.full_like(emb, float("nan"))
+    ops.embed_ln_bwd(dy, None, None, tt, None, None, pos_tab, type_tab, gamma, None, *grads3, None, 1e-12, B * S, S, H,
+                     inputs_embeds=emb, d_inputs_embeds=d_emb)
+    rel, msg = _err_report(d_emb, embp.grad, "embed_ln_bwd d_inputs_embeds")
+    assert rel < 2e-4, msg
+    for got, p, nm in zip(grads3, params2, ("dpos", "dtype", "dgamma", "dbeta")):
+        rel, msg = _err_report(got, p.grad, "embed_ln_bwd(inputs_embeds) " + nm)
         assert rel < 2e-4, msg
 
 

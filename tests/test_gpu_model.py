@@ -256,3 +256,147 @@ def test_step_from_host_reads_every_loss_one_step_late():
         seqs.append(ls)
     for other in seqs[1:]:
         assert max(abs(a - b) for a, b in zip(seqs[0], other)) < 2e-4, seqs
+
+
+def test_dropin_inputs_embeds_and_explicit_position_ids_paths():
+    """Two `BertModel.forward` arguments no reference call site uses (they all pass None) and no round-1 GPU test covered:
+    `inputs_embeds` (must equal the `input_ids` path fed with the same word vectors) and non-trivial `position_ids` (against
+    the CPU oracle), including the in-place edited `embeddings.position_ids` buffer (ponet_topic_segmentation.py:471-482)."""
+    BertConfig, BertModel = _setup()
+    from oracle import bert_oracle as O
+    kw = dict(hidden_size=128, num_attention_heads=2, intermediate_size=256, num_hidden_layers=2, vocab_size=128,
+              max_position_embeddings=128, type_vocab_size=2)
+    ocfg = O.OracleConfig(**kw)
+    sd = O.random_state_dict(ocfg, seed=7)
+    m = BertModel(BertConfig(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, **kw))
+    m.load_state_dict(sd, strict=False)
+    m = m.cuda().eval()
+    g = torch.Generator().manual_seed(3)
+    ids = torch.randint(5, 128, (2, 96), generator=g)
+    mask = torch.ones(2, 96, dtype=torch.long)
+    mask[1, 70:] = 0
+    tt = torch.zeros(2, 96, dtype=torch.long)
+    with torch.no_grad():
+        base = m(ids.cuda(), attention_mask=mask.cuda(), token_type_ids=tt.cuda())[0]
+        emb = m.embeddings.word_embeddings(ids.cuda())
+        via_embeds = m(inputs_embeds=emb, attention_mask=mask.cuda(), token_type_ids=tt.cuda())[0]
+    assert rel_err(via_embeds, base) < 1e-6, rel_err(via_embeds, base)
+    pos = (torch.arange(96)[None, :] % 32).expand(2, 96).contiguous()          # a tiled position table, as the PoNet driver builds
+    ref = O.bert_model(sd, ocfg, ids, mask, tt, position_ids=pos).last_hidden_state
+    with torch.no_grad():
+        got = m(ids.cuda(), attention_mask=mask.cuda(), token_type_ids=tt.cuda(), position_ids=pos.cuda())[0]
+    assert rel_err(got.cpu(), ref) < 1e-3, rel_err(got.cpu(), ref)
+    with torch.no_grad():
+        m.embeddings.position_ids[:, :96] = pos[:1].cuda()                     # in-place edit of the buffer
+        got2 = m(ids.cuda(), attention_mask=mask.cuda(), token_type_ids=tt.cuda())[0]
+    assert torch.equal(got2, got)
+
+
+def _padidx_loss(m, g, w, b, **inp):
+    h = m(attention_mask=g["attention_mask"].cuda(), token_type_ids=g["token_type_ids"].cuda(), **inp)[0]
+    logits = h @ w.t() + b
+    mask = g["attention_mask"].cuda()
+    loss = torch.nn.functional.cross_entropy(logits.view(-1, 2), g["labels"].cuda().view(-1)) + 0.1 * (h * mask[..., None]).pow(2).mean()
+    return loss, h
+
+
+def _check_grads(named, extra, ref_grads, tol=1e-2):
+    worst = 0.0
+    for k, ref in ref_grads.items():
+        got = extra[k].grad if k in extra else named[k].grad
+        assert got is not None, k
+        err, nrm = float((got.double().cpu() - ref.double()).norm()), float(ref.double().norm())
+        assert err <= tol * nrm + 2e-6, (k, err, nrm)
+        if nrm > 1e-5:
+            worst = max(worst, err / nrm)
+    return worst
+
+
+def test_pad_token_row_receives_no_gradient_golden():
+    """nn.Embedding(padding_idx=pad_token_id) (bert_model.py:171): token id 0 at LIVE positions that carry loss — the golden
+    (HF autograd, oracle/make_goldens.py::golden_tiny_padidx) has an exactly-zero pad row and so must the kernel; every other
+    gradient is held to the reference as well."""
+    BertConfig, BertModel = _setup()
+    g = _load("tiny_bert_padidx.pt")
+    from oracle import bert_oracle as O
+    sd = O.random_state_dict(O.OracleConfig(**g["config"]), seed=g["weight_seed"])
+    m, _ = _model_from(g["config"], sd, BertConfig, BertModel)
+    m.train()
+    assert int((g["input_ids"] == 0)[g["attention_mask"] == 1].sum()) >= 6
+    w, b = g["cls_w"].cuda().requires_grad_(True), g["cls_b"].cuda().requires_grad_(True)
+    loss, h = _padidx_loss(m, g, w, b, input_ids=g["input_ids"].cuda())
+    assert rel_err(h.detach().cpu(), g["last_hidden_state"]) < HID_TOL
+    assert abs(float(loss) - float(g["loss"])) < 5e-4
+    loss.backward()
+    named = dict(m.named_parameters())
+    dword = named["embeddings.word_embeddings.weight"].grad
+    assert float(dword[0].abs().max()) == 0.0                       # the pad row: exactly nothing
+    assert float(g["grads"]["embeddings.word_embeddings.weight"][0].abs().max()) == 0.0
+    worst = _check_grads(named, {"classifier.weight": w, "classifier.bias": b}, g["grads"])
+    print(f"pad-idx golden: worst relative gradient error {worst:.2e}")
+
+
+def test_inputs_embeds_backward_matches_reference_autograd():
+    """Training THROUGH inputs_embeds: gradients wrt the embeddings tensor, the position / type tables and the embedding
+    LayerNorm against HF autograd (same golden); the word table receives none."""
+    BertConfig, BertModel = _setup()
+    g = _load("tiny_bert_padidx.pt")
+    from oracle import bert_oracle as O
+    sd = O.random_state_dict(O.OracleConfig(**g["config"]), seed=g["weight_seed"])
+    m, _ = _model_from(g["config"], sd, BertConfig, BertModel)
+    m.train()
+    w, b = g["cls_w"].cuda().requires_grad_(True), g["cls_b"].cuda().requires_grad_(True)
+    emb = sd["embeddings.word_embeddings.weight"][g["input_ids"]].cuda().requires_grad_(True)
+    loss, h = _padidx_loss(m, g, w, b, inputs_embeds=emb)
+    assert rel_err(h.detach().cpu(), g["last_hidden_state_embeds"]) < HID_TOL
+    loss.backward()
+    named = dict(m.named_parameters())
+    wg = named["embeddings.word_embeddings.weight"].grad
+    assert wg is None or float(wg.abs().max()) == 0.0
+    _check_grads(named, {"classifier.weight": w, "classifier.bias": b}, g["grads_embeds"])
+    assert rel_err(emb.grad.cpu(), g["d_inputs_embeds"]) < 1e-2
+
+
+def test_eval_forward_saves_nothing_and_replaced_embedding_is_noticed():
+    """(a) under no_grad / in eval the autograd bridge must not keep activations (grad mode, not requires_grad, decides);
+    (b) replacing the word-embedding Parameter object (what older transformers' resize_token_embeddings does:
+    ts_sentence_seq_labeling.py:284) must re-pack — a stale table would gather out of bounds for the new ids."""
+    BertConfig, BertModel = _setup()
+    g = _load("tiny_bert.pt")
+    m, cfg = _model_from(g["config"], g["state_dict"], BertConfig, BertModel)
+    ids, mask = g["input_ids"].cuda(), g["attention_mask"].cuda()
+    with torch.no_grad():
+        out = m(ids, attention_mask=mask)[0]
+    assert out.grad_fn is None and not out.requires_grad
+    m.train()
+    torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
+    with torch.no_grad():
+        m(ids, attention_mask=mask)
+    torch.cuda.synchronize()
+    peak_nograd = torch.cuda.max_memory_allocated() - base
+    torch.cuda.reset_peak_memory_stats()
+    out = m(ids, attention_mask=mask)[0]
+    torch.cuda.synchronize()
+    peak_grad = torch.cuda.max_memory_allocated() - base
+    assert out.requires_grad and peak_nograd < 0.7 * peak_grad, (peak_nograd, peak_grad)
+    del out
+    m.eval()
+    V, H = cfg.vocab_size, cfg.hidden_size
+    new = torch.nn.Embedding(V + 3, H, padding_idx=0).cuda()
+    with torch.no_grad():
+        new.weight[:V] = m.embeddings.word_embeddings.weight
+        new.weight[V:] = 0.02 * torch.randn(3, H, device="cuda")
+    m.set_input_embeddings(new)                        # a NEW Parameter object; the old one still points into the flat buffer
+    ids2 = ids.clone()
+    ids2[:, 5] = V + 2
+    with torch.no_grad():
+        got = m(ids2, attention_mask=mask)[0]
+    from oracle import bert_oracle as O
+    sd2 = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    import dataclasses
+    ocfg = dataclasses.replace(O.OracleConfig(**g["config"]), vocab_size=V + 3)
+    ref = O.bert_model(sd2, ocfg, ids2.cpu(), g["attention_mask"]).last_hidden_state
+    assert rel_err(got.cpu(), ref) < HID_TOL
+

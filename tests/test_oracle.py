@@ -63,6 +63,41 @@ def test_tiny_gradients_match_reference_autograd():
     assert sd["pooler.dense.weight"].grad is None
 
 
+def _padidx_loss(sd, cfg, g, w, b, **inp):
+    h = O.bert_model(sd, cfg, inp.get("input_ids"), g["attention_mask"], g["token_type_ids"], inputs_embeds=inp.get("inputs_embeds")).last_hidden_state
+    logits = h @ w.t() + b
+    loss = torch.nn.functional.cross_entropy(logits.view(-1, 2), g["labels"].view(-1)) + 0.1 * (h * g["attention_mask"][..., None]).pow(2).mean()
+    return loss, h
+
+
+def test_pad_token_row_gets_no_gradient_like_the_reference():
+    """padding_idx of the word table (bert_model.py:171): id 0 at live, loss-carrying positions — HF autograd leaves row 0 of
+    the word-table gradient exactly zero, and so does the restatement; all other gradients agree."""
+    g = _load("tiny_bert_padidx.pt")
+    cfg = O.OracleConfig(**g["config"])
+    assert cfg.pad_token_id == 0
+    sd = {k: v.clone().requires_grad_(True) for k, v in O.random_state_dict(cfg, seed=g["weight_seed"]).items()}
+    w, b = g["cls_w"].clone().requires_grad_(True), g["cls_b"].clone().requires_grad_(True)
+    loss, h = _padidx_loss(sd, cfg, g, w, b, input_ids=g["input_ids"])
+    assert abs(float(loss) - float(g["loss"])) < 1e-5 and rel_err(h, g["last_hidden_state"]) < TOL
+    loss.backward()
+    assert float(sd["embeddings.word_embeddings.weight"].grad[0].abs().max()) == 0.0
+    for k, ref in g["grads"].items():
+        got = {"classifier.weight": w, "classifier.bias": b}.get(k, sd.get(k))
+        err = float((got.grad.double() - ref.double()).norm())
+        assert err <= 5e-5 * float(ref.double().norm()) + 1e-7, (k, err)
+    # the same forward through inputs_embeds: gradient wrt the embeddings tensor, none for the word table
+    sd = {k: v.clone().requires_grad_(True) for k, v in O.random_state_dict(cfg, seed=g["weight_seed"]).items()}
+    emb = sd["embeddings.word_embeddings.weight"].detach()[g["input_ids"]].clone().requires_grad_(True)
+    loss, h = _padidx_loss(sd, cfg, g, w, b, inputs_embeds=emb)
+    assert abs(float(loss) - float(g["loss_embeds"])) < 1e-5
+    loss.backward()
+    assert sd["embeddings.word_embeddings.weight"].grad is None
+    assert rel_err(emb.grad, g["d_inputs_embeds"]) < 5e-5
+    for k in ("embeddings.position_embeddings.weight", "embeddings.token_type_embeddings.weight", "embeddings.LayerNorm.weight"):
+        assert rel_err(sd[k].grad, g["grads_embeds"][k]) < 5e-5, k
+
+
 def test_bert_base_forward_matches_reference():
     g = _load("bert_base_2x128.pt")
     cfg = O.OracleConfig(**g["config"])
