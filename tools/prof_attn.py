@@ -24,9 +24,11 @@ def make(B, S):
     lse = torch.zeros(B, heads, S, device="cuda")
     dqkv = torch.zeros_like(qkv)
     ws = ops.attn_bwd_workspace(B, heads, S, "cuda")
-    fwd = lambda: ops.attn_fwd(qkv, qkv, ctx, B, heads, S, S, q_col0=0, k_col0=H, v_col0=2 * H, lse2=lse)
+    p = float(os.environ.get("B200_ATTN_DROP", "0"))       # e.g. 0.1: the training configuration (dropout on the probabilities)
+    drop = ops.Dropout(torch.tensor([7], dtype=torch.int32, device="cuda"), 9, p) if p > 0 else None
+    fwd = lambda: ops.attn_fwd(qkv, qkv, ctx, B, heads, S, S, q_col0=0, k_col0=H, v_col0=2 * H, lse2=lse, drop=drop)
     bwd = lambda: ops.attn_bwd(qkv, qkv, dctx, ctx, lse, dqkv, dqkv, ws, B, heads, S, S, q_col0=0, k_col0=H, v_col0=2 * H, dq_col0=0,
-                               dk_col0=H, dv_col0=2 * H)
+                               dk_col0=H, dv_col0=2 * H, drop=drop)
     return fwd, bwd
 
 

@@ -4,7 +4,7 @@
 # 1. the default GPU suite, 2. the opt-in variants' tests, each node in its own process (a trapped kernel cannot hide the
 # others), 3. kernel-level A/B, 4. bench.py with each variant set on the same box.  Everything lands in gpurun_out/.
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests -m gpu -x -q > gpurun_out/r2_gpu_suite.log 2>&1; tail -3 gpurun_out/r2_gpu_suite.log
+timeout 420 python -m pytest tests -m gpu -q > gpurun_out/r2_gpu_suite.log 2>&1; tail -15 gpurun_out/r2_gpu_suite.log
 # one process first (fast); only if something fails or traps, every node again in its own process
 if B200_RUN_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_gpu_experimental.py -q > gpurun_out/r2_experimental.log 2>&1; then
   tail -2 gpurun_out/r2_experimental.log
@@ -29,3 +29,6 @@ except Exception as e:
     print(sys.argv[1], "no result:", e)
 PY
 done
+# the persistent attention kernels as they run in training (dropout 0.1 on the probabilities): --set full + source-level stall sampling
+B200_ATTN_DROP=0.1 timeout 280 ncu --set full --clock-control none --import-source on -k regex:"attn_(fwd3|bwd3)_kernel" -c 2 \
+  -f -o gpurun_out/r2_attn_drop_v0 python tools/prof_attn.py > gpurun_out/r2_ncu_attn_drop_v0.log 2>&1; tail -2 gpurun_out/r2_ncu_attn_drop_v0.log
