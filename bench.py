@@ -274,7 +274,8 @@ def run_b200_arm(args):
     from spokennlp_b200.trainer import DataParallelTrainer, TopicSegModel
 
     from spokennlp_b200.blocks import Experimental
-    opt_in = [n for n in ("resadd", "streamk", "delta", "elect", "ewait") if getattr(Experimental, n)]
+    opt_in = [n for n in Experimental.active() if n not in Experimental.DEFAULT.split(",")]      # variants beyond the default set
+    off = [n for n in Experimental.DEFAULT.split(",") if n not in Experimental.active()]
     torch.manual_seed(0)
     cfg = BertConfig(hidden_dropout_prob=args.dropout, attention_probs_dropout_prob=args.dropout, **CFG)
     model = TopicSegModel(cfg)
@@ -359,6 +360,7 @@ def run_b200_arm(args):
                                    "(fwd + bwd + grad allreduce + clip + AdamW)", "seq_len": SEQ, "batch_per_gpu": BATCH,
                        "global_batch": BATCH * world, "parallelism": f"dp{world}", "dropout": args.dropout, "cuda_graph": bool(graphed),
                        "opt_in_variants": opt_in,        # B200_EXP; [] = the default, GPU-validated kernels
+                       "disabled_default_variants": off,
                        "l2": "per-step working set ~5.4 GB of activations >> 126 MB L2 (no explicit flush needed)"},
             "encoder_flop_util": {"flop_per_seq": FLOP_PER_SEQ, "achieved_tflops_per_gpu": value / world * FLOP_PER_SEQ / 1e12,
                                   "peak_tflops_sustained": peaks["bf16_tflops_sustained"], "peak_source": peak_src,

@@ -22,31 +22,41 @@ F16, F32 = torch.float16, torch.float32
 
 
 class Experimental:
-    """Opt-in kernel variants written after round 1's GPU budget was spent.  They are OFF unless named in
-    the environment variable B200_EXP (comma-separated) or switched on here by a test / A-B tool; the default path is the
-    one the round-1 GPU runs validated.
-      resadd : output-dense + residual through b200_gemm_f16_resadd (in place on the fp32 residual stream, no aux reads)
-      streamk: with resadd, the stream-K schedule for those N = 768 GEMMs
-      delta  : attention-backward row statistic fused into the output projection's dgrad (b200_gemm_f16_dgrad_delta)
-      elect  : persistent attention kernels with one mbarrier arrival per softmax warp (b200_set_attn_variant(1))
-      ewait  : with elect, the softmax warps also wait with one lane per warp (b200_set_attn_variant(3))"""
+    """Kernel-variant switches.  Three variants written after round 1 were validated and measured on a B200 in round 2
+    (profiles/r02a_variants_ab.jsonl, profiles/bench_r02a_*.json) and are now THE DEFAULT path:
+      resadd : output-dense + residual through b200_gemm_f16_resadd (in place on the fp32 residual stream, no aux reads):
+               out-proj 51 -> 28 us, FFN-down 81 -> 74 us per layer at the bench shape (64 -> 29 / 84 -> 74 with dropout)
+      delta  : attention-backward row statistic fused into the output projection's dgrad (b200_gemm_f16_dgrad_delta): -12 us/layer
+      elect  : persistent attention kernels with one mbarrier arrival per softmax warp: backward 211 -> 202 us with dropout
+    Two were measured slower and stay opt-in only for A/B runs:
+      streamk: stream-K schedule for the resadd GEMMs (74 -> 80 us on FFN-down: the extra reduce-adds cost more than the tail)
+      ewait  : softmax warps also WAIT with one lane per warp (+1-2 % on both attention kernels)
+    `B200_EXP` (comma-separated) names the variants to run; unset = the default set.  `B200_EXP=none` is the round-1 path."""
+    DEFAULT = "resadd,delta,elect"
     resadd = streamk = delta = elect = ewait = False
     _elect_applied = False
 
     @classmethod
     def from_env(cls, value: Optional[str] = None) -> None:
         import os
-        names = {n.strip() for n in (os.environ.get("B200_EXP", "") if value is None else value).split(",") if n.strip()}
+        raw = os.environ.get("B200_EXP") if value is None else value
+        if raw is None or raw.strip() == "default":
+            raw = cls.DEFAULT
+        names = {n.strip() for n in raw.split(",") if n.strip() and n.strip() != "none"}
         unknown = names - {"resadd", "streamk", "delta", "elect", "ewait"}
         if unknown:
             raise ValueError(f"B200_EXP: unknown variant(s) {sorted(unknown)}")
         cls.resadd, cls.streamk, cls.delta = "resadd" in names or "streamk" in names, "streamk" in names, "delta" in names
         cls.ewait = "ewait" in names
         cls.elect = "elect" in names or cls.ewait
-        if cls.elect or cls._elect_applied:              # a library-wide selector: touch the library only when it is (or was) in use
-            from . import lib as _lib
+        from . import lib as _lib
+        if _lib.is_loaded() or cls.elect != cls._elect_applied:      # a library-wide selector (the library's own default is `elect`)
             _lib.load().b200_set_attn_variant(3 if cls.ewait else (1 if cls.elect else 0))
             cls._elect_applied = cls.elect
+
+    @classmethod
+    def active(cls):
+        return [n for n in ("resadd", "streamk", "delta", "elect", "ewait") if getattr(cls, n)]
 
 
 Experimental.from_env()

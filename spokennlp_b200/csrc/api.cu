@@ -151,7 +151,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g,
 
 std::atomic<int> g_gemm_impl{2};
 std::atomic<int> g_gemm_dbg{0};
-std::atomic<int> g_attn_variant{0};      // b200_set_attn_variant: bit 0 = warp-elected mbarrier arrivals, bit 1 (with bit 0) = warp-elected waits (opt-in)
+std::atomic<int> g_attn_variant{1};      // b200_set_attn_variant: bit 0 = warp-elected mbarrier arrivals, bit 1 (with bit 0) = warp-elected waits (opt-in)
 
 const DropCfg kNoDrop{nullptr, 0, 0, 1.0f};
 DropCfg make_drop(const uint32_t* seed, unsigned site, float p) {

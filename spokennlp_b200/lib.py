@@ -152,6 +152,10 @@ def load() -> C.CDLL:
     return _lib
 
 
+def is_loaded() -> bool:
+    return _lib is not None
+
+
 def exported_symbols():
     return sorted(set(_PROTOS) | set(_RESTYPE))
 

@@ -1,18 +1,13 @@
-"""GPU parity of the OPT-IN kernel variants (blocks.Experimental): written after round 1's GPU budget was
-spent, so they have not run on a B200 yet.  They stay out of the default `-m gpu` suite until they have:
-
-    B200_RUN_EXPERIMENTAL=1 python -m pytest tests/test_gpu_experimental.py -q
-
-Each variant is held to the round-1 kernel it replaces (bit-exact where the arithmetic is the same, summation-order
-tolerance where it is not) and to an fp32 statement of the op."""
+"""GPU parity of the kernel variants (blocks.Experimental).  They first ran on a B200 in round 2
+(profiles/gpurun_logs/r02_call01.log): resadd, delta and elect became the default path, streamk and ewait stay selectable for
+A/B runs.  Each variant is held to the round-1 kernel it replaces (bit-exact where the arithmetic is the same,
+summation-order tolerance where it is not) and to an fp32 statement of the op."""
 import os
 
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("B200_RUN_EXPERIMENTAL", "0") != "1",
-                                 reason="opt-in variants: set B200_RUN_EXPERIMENTAL=1 (not yet validated on a B200)")]
+pytestmark = pytest.mark.gpu
 
 
 def _ops():
@@ -124,7 +119,8 @@ def test_attention_with_warp_elected_arrivals_matches_the_default_kernels(B, S, 
             torch.cuda.synchronize()
             res.append((ctx, lse, dqkv))
     finally:
-        lib.load().b200_set_attn_variant(0)
+        from spokennlp_b200.blocks import Experimental
+        Experimental.from_env(None)             # restores the library-wide selector to the active variant set
     c0, l0, g0 = res[0]
     for c1, l1, g1 in res[1:]:
         assert torch.equal(c0, c1) and torch.equal(l0, l1)
@@ -157,17 +153,19 @@ def _tiny_step(variants: str, dropout: float):
         grads = tr.flat.grad32.clone()
         return loss, grads
     finally:
-        Experimental.from_env("")
+        Experimental.from_env(None)
 
 
 @pytest.mark.parametrize("dropout", [0.0, 0.1])
 @pytest.mark.parametrize("variants", ["resadd", "delta", "resadd,delta", "streamk,delta", "elect", "ewait", "resadd,delta,ewait"])
 def test_training_step_with_variants_matches_the_default_path(variants, dropout):
     _ops()
-    loss0, g0 = _tiny_step("", dropout)
+    loss0, g0 = _tiny_step("none", dropout)
     loss1, g1 = _tiny_step(variants, dropout)
     if "streamk" not in variants:
-        assert loss1 == loss0                   # forward arithmetic is unchanged
+        # forward arithmetic is unchanged; the loss itself is a sum of per-row terms taken with fp32 atomics in a run-dependent
+        # order (ce_stats), so two runs of the SAME path already differ in the last bit (seen on the B200: 1.1e-7 relative)
+        assert abs(loss1 - loss0) <= 4e-7 * abs(loss0)
     else:
         assert abs(loss1 - loss0) < 1e-5
     # resadd alone leaves every saved activation bit-identical: only the wgrads' split-K reduction order differs between two runs

@@ -200,7 +200,8 @@ def test_embed_ln_fwd_bwd():
     # without a padding index (pad_id=None -> -1) row 0 accumulates like any other row
     grads2 = [torch.zeros_like(t) for t in (word, pos_tab, type_tab, gamma, beta)]
     ops.embed_ln_bwd(dy, None, ids, tt, None, word, pos_tab, type_tab, gamma, *grads2, None, 1e-12, B * S, S, H)
-    assert float(grads2[0][0].abs().max()) > 0.0 and torch.equal(grads2[0][1:], grads[0][1:])
+    assert float(grads2[0][0].abs().max()) > 0.0
+    assert float((grads2[0][1:] - grads[0][1:]).abs().max()) < 1e-5          # same sums; fp32 atomics land in a run-dependent order
     # forward on inputs_embeds: same outputs; the backward hands the word-path gradient to d_inputs_embeds
     emb = word[ids].reshape(B * S, H).contiguous()
     y2 = ops.embed_ln_fwd(None, tt, None, emb, word, pos_tab, type_tab, gamma, beta, 1e-12, B * S, S, H)

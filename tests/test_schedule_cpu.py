@@ -64,7 +64,7 @@ def rec(monkeypatch):
                          attn_bwd_workspace=lambda B, heads, Sq, device: torch.empty(B * heads * Sq * 65)).items():
         monkeypatch.setattr(ops, name, fn)
     yield r
-    blocks.Experimental.from_env("")
+    blocks.Experimental.from_env(None)          # back to the environment's / the default variant set
 
 
 H, HEADS, INTER, L, B, S = 128, 2, 256, 3, 2, 64
@@ -92,7 +92,8 @@ BWD_LAYER = ["layernorm_bwd", "gemm/epi6/a1b1", "gemm/epi4/a0b1", "colsum", "gem
              "layernorm_bwd", "gemm/epi6/a1b1", "gemm/epi0/a0b1", "attn_bwd", "colsum", "gemm/epi6/a1b1", "gemm/epi5/a0b1"]  # attention block
 
 
-def test_default_schedule_is_the_round1_schedule(rec):
+def test_round1_schedule_is_still_selectable(rec):
+    blocks.Experimental.from_env("none")
     eng = _engine()
     rec.calls.clear()
     x16, x32, saved, hiddens, probs = _forward(eng, save=True)
@@ -145,8 +146,25 @@ def test_delta_variant_replaces_the_plain_dgrad_and_skips_the_row_statistic_pass
     assert rec.names() == bwd * L + ["embed_ln_bwd"]
 
 
+def test_default_schedule_is_the_round2_validated_set(rec, monkeypatch):
+    """resadd + delta + elect were validated and measured on a B200 (profiles/r02a_*) and are the default."""
+    monkeypatch.delenv("B200_EXP", raising=False)
+    blocks.Experimental.from_env(None)
+    assert blocks.Experimental.active() == ["resadd", "delta", "elect"]
+    eng = _engine()
+    rec.calls.clear()
+    _, _, saved, _, _ = _forward(eng, save=True)
+    fwd = [n.replace("gemm/epi7/a0b0", "gemm_resadd") for n in FWD_LAYER]
+    assert rec.names() == ["embed_ln_fwd"] + fwd * L
+    rec.calls.clear()
+    eng.backward(saved, torch.empty(B * S, H, dtype=torch.float16), torch.ones(1))
+    bwd = [{"gemm/epi0/a0b1": "gemm_dgrad_delta", "attn_bwd": "attn_bwd/delta_ready"}.get(n, n) for n in BWD_LAYER]
+    assert rec.names() == bwd * L + ["embed_ln_bwd"]
+
+
 def test_unknown_variant_names_are_refused():
     with pytest.raises(ValueError):
         blocks.Experimental.from_env("resad")
-    blocks.Experimental.from_env("")
-    assert not (blocks.Experimental.resadd or blocks.Experimental.streamk or blocks.Experimental.delta or blocks.Experimental.elect or blocks.Experimental.ewait)
+    blocks.Experimental.from_env("none")
+    assert not blocks.Experimental.active()
+    blocks.Experimental.from_env(None)
