@@ -31,10 +31,14 @@ class Experimental:
     Two were measured slower and stay opt-in only for A/B runs:
       streamk: stream-K schedule for the resadd GEMMs (74 -> 80 us on FFN-down: the extra reduce-adds cost more than the tail)
       ewait  : softmax warps also WAIT with one lane per warp (+1-2 % on both attention kernels)
+    Under evaluation:
+      bwd16  : attention backward with sixteen softmax warps, 32 keys per thread (attn_bwd4.cuh)
+      fwd16  : attention forward with sixteen softmax warps, 64 keys per thread + row-maximum exchange (attn_fwd4.cuh)
     `B200_EXP` (comma-separated) names the variants to run; unset = the default set.  `B200_EXP=none` is the round-1 path."""
     DEFAULT = "resadd,delta,elect"
-    resadd = streamk = delta = elect = ewait = False
-    _elect_applied = False
+    resadd = streamk = delta = elect = ewait = bwd16 = fwd16 = False
+    _applied = 1                                  # the library's own default selector (elect)
+    NAMES = ("resadd", "streamk", "delta", "elect", "ewait", "bwd16", "fwd16")
 
     @classmethod
     def from_env(cls, value: Optional[str] = None) -> None:
@@ -43,20 +47,22 @@ class Experimental:
         if raw is None or raw.strip() == "default":
             raw = cls.DEFAULT
         names = {n.strip() for n in raw.split(",") if n.strip() and n.strip() != "none"}
-        unknown = names - {"resadd", "streamk", "delta", "elect", "ewait"}
+        unknown = names - set(cls.NAMES)
         if unknown:
             raise ValueError(f"B200_EXP: unknown variant(s) {sorted(unknown)}")
         cls.resadd, cls.streamk, cls.delta = "resadd" in names or "streamk" in names, "streamk" in names, "delta" in names
         cls.ewait = "ewait" in names
         cls.elect = "elect" in names or cls.ewait
+        cls.bwd16, cls.fwd16 = "bwd16" in names, "fwd16" in names
+        sel = (3 if cls.ewait else (1 if cls.elect else 0)) | (4 if cls.bwd16 else 0) | (8 if cls.fwd16 else 0)
         from . import lib as _lib
-        if _lib.is_loaded() or cls.elect != cls._elect_applied:      # a library-wide selector (the library's own default is `elect`)
-            _lib.load().b200_set_attn_variant(3 if cls.ewait else (1 if cls.elect else 0))
-            cls._elect_applied = cls.elect
+        if _lib.is_loaded() or sel != cls._applied:      # a library-wide selector (the library's own default is `elect`)
+            _lib.load().b200_set_attn_variant(sel)
+            cls._applied = sel
 
     @classmethod
     def active(cls):
-        return [n for n in ("resadd", "streamk", "delta", "elect", "ewait") if getattr(cls, n)]
+        return [n for n in cls.NAMES if getattr(cls, n)]
 
 
 Experimental.from_env()

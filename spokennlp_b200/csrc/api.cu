@@ -10,8 +10,10 @@
 #include "../../include/b200enc.h"
 #include "attn_bwd.cuh"
 #include "attn_bwd3.cuh"
+#include "attn_bwd4.cuh"
 #include "attn_fwd.cuh"
 #include "attn_fwd3.cuh"
+#include "attn_fwd4.cuh"
 #include "gemm.cuh"
 #include "gemm2.cuh"
 #include "optim.cuh"
@@ -339,7 +341,16 @@ int b200_attn_fwd_drop(const void* q, int ldq, int q_col0, const void* kv, int l
     const long long items = static_cast<long long>(grid.x) * grid.y * grid.z;
     const int ctas = items < sm_count() ? static_cast<int>(items) : sm_count();
     const int var = g_attn_variant.load();
-    if (var & 1) {                              // opt-in: one mbarrier arrival (bit 1: and one waiting lane) per softmax warp
+    if (var & 8) {                              // sixteen softmax warps, 64 keys per thread (attn_fwd4.cuh)
+      static int h0 = set_smem(attn_fwd4_kernel<false>, AttnFwd4Smem::TOTAL);
+      static int h1 = set_smem(attn_fwd4_kernel<true>, AttnFwd4Smem::TOTAL);
+      if (h0 != B200_OK || h1 != B200_OK) return h0 ? h0 : h1;
+      cudaStream_t st = static_cast<cudaStream_t>(stream);
+      if (drop.seed_base) attn_fwd4_kernel<true><<<ctas, ATTP4_THREADS, AttnFwd4Smem::TOTAL, st>>>(tq, tkv, to, a);
+      else attn_fwd4_kernel<false><<<ctas, ATTP4_THREADS, AttnFwd4Smem::TOTAL, st>>>(tq, tkv, to, a);
+      return check_launch("attn_fwd4_kernel");
+    }
+    if (var & 1) {                              // one mbarrier arrival (bit 1: and one waiting lane) per softmax warp
       static int f0 = set_smem(attn_fwd3_kernel<false, 1>, AttnFwd3Smem::TOTAL);
       static int f1 = set_smem(attn_fwd3_kernel<true, 1>, AttnFwd3Smem::TOTAL);
       static int f2 = set_smem(attn_fwd3_kernel<false, 3>, AttnFwd3Smem::TOTAL);

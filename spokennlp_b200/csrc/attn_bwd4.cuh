@@ -1,0 +1,403 @@
+// Fused attention backward, fourth generation: attn_bwd3_kernel's schedule (persistent CTA per SM walking (batch, head,
+// 128-key block) items; natural orientation, TMEM lane == query row; S / dP of block i+1 issued while block i is being
+// exponentiated; dQ by TMA reduce-add; dK / dV by TMA store) with SIXTEEN softmax warps instead of eight.
+//
+// Why (profiles/r02a_attn_drop_kernel_metrics.md, r02a_attn_roles.txt — the round-2 capture of attn_bwd3 with dropout on): the
+// eight softmax warps are never waiting for the tensor core (s_full waits: 1 % of their samples) and no pipe is busy (ALU 31 %,
+// XU 15 %, issue slots 35 %) — each warp issues one instruction per 6.8 cycles because its 885-instruction block body is a web
+// of fixed-latency dependencies (28 % "wait" stalls) that ptxas cannot interleave further with 128 live score / dP registers
+// out of 168, and two warps per scheduler cannot hide it.  Splitting a row's 64-key half between TWO threads (32 keys each)
+//   * halves the live registers per thread (64 score / dP values), which fits 16 + 2 warps = 576 threads x 112 registers,
+//   * puts four softmax warps on every scheduler, each with half the work,
+//   * needs no cross-thread exchange: lse / delta are per-row inputs, every P / dS element is independent.
+//   warp 0 TMA producer, warp 1 MMA issuer, warps 2-17 softmax: warp - 2 = 8 g + 4 s + quadrant slot
+//     g = key half (score columns [64g, 64g+64), own S / dP buffers and barriers), s = 32-key quarter inside the half.
+//   Softmax -> MMA hand-offs are one mbarrier arrival per warp (the `elect` variant measured in round 2).
+//   dQ is drained by the s = 0 warps (8 patches of [32 q][32 d], as before); dV leaves through the s = 0 warps and dK through
+//   the s = 1 warps, so the item epilogue's two tiles are converted in parallel.
+#pragma once
+#include "attn_bwd3.cuh"
+
+namespace b200 {
+
+constexpr int ATTB4_THREADS = 64 + 16 * 32;
+
+
+template <bool DROP>
+__global__ void __launch_bounds__(ATTB4_THREADS, 1)
+attn_bwd4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                 const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmDQ,
+                 const __grid_constant__ CUtensorMap tmDKV, const AttnBwdArgs a) {
+  using S = AttnBwd3Smem;
+  constexpr int NST = ATTB3_QDO_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
+  uint64_t* kv_full = bars;                   // 1
+  uint64_t* kv_empty = bars + 1;              // 1
+  uint64_t* qdo_full = bars + 2;              // 3
+  uint64_t* qdo_empty = qdo_full + NST;       // 3
+  uint64_t* s_full = qdo_empty + NST;         // 2 (one per key half)
+  uint64_t* s_free = s_full + 2;              // 2 (8 warp arrivals each)
+  uint64_t* ds_full = s_free + 2;             // 1 (16 warp arrivals)
+  uint64_t* grad_done = ds_full + 1;          // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(grad_done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nq = (a.Sq + ATT_BQ - 1) / ATT_BQ;
+  const int n_kb = (a.Sk + ATT_BK - 1) / ATT_BK;
+  const int n_items = a.B * a.heads * n_kb;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+    tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmDQ);
+    tma_prefetch_desc(&tmDKV);
+    mbar_init(kv_full, 1);
+    mbar_init(kv_empty, 1);
+    for (int i = 0; i < NST; ++i) {
+      mbar_init(&qdo_full[i], 1);
+      mbar_init(&qdo_empty[i], 1);
+    }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&s_full[g], 1);
+      mbar_init(&s_free[g], 8);
+    }
+    mbar_init(ds_full, 16);
+    mbar_init(grad_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  // TMEM columns: S [0,128) (half g at 64g)  dP [128,256)  dV [256,320)  dK [320,384)  dQ ping-pong [384,448) / [448,512)
+
+  struct Item {
+    int b, h, k0, kv_len;
+    bool general_bias, dead;
+  };
+  auto decode = [&](int item) {
+    Item it;
+    const int kbk = item % n_kb, bh = item / n_kb;
+    it.h = bh % a.heads;
+    it.b = bh / a.heads;
+    it.k0 = kbk * ATT_BK;
+    int kv = a.kv_len ? a.kv_len[it.b] : a.Sk;
+    it.general_bias = a.key_bias != nullptr && (a.kv_len == nullptr || kv < 0);   // see attn_fwd.cuh
+    it.kv_len = max(1, min(kv < 0 ? -kv : kv, a.Sk));
+    it.dead = it.k0 >= it.kv_len;      // every key of this block is masked: dK = dV = 0, no dQ contribution
+    return it;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t n = 0, qs = 0;           // live items seen, Q / dO ring position
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const Item it = decode(item);
+        if (it.dead) continue;
+        auto load_qdo = [&](int i) {
+          const uint32_t st = qs % NST, ph = (qs / NST) & 1;
+          mbar_wait(&qdo_empty[st], ph ^ 1);
+          mbar_expect_tx(&qdo_full[st], 2 * S::T);
+          uint8_t* dst = smem + S::OFF_QDO + st * 2 * S::T;
+          tma_load_2d(dst, &tmQ, &qdo_full[st], a.q_col0 + it.h * ATT_D, it.b * a.Sq + i * ATT_BQ);
+          tma_load_2d(dst + S::T, &tmDO, &qdo_full[st], it.h * ATT_D, it.b * a.Sq + i * ATT_BQ);
+          ++qs;
+        };
+        load_qdo(0);                    // the first Q / dO block does not wait for the item switch ...
+        mbar_wait(kv_empty, (n & 1) ^ 1);   // ... K / V do: the previous item's last gradient MMAs read them
+        mbar_expect_tx(kv_full, 2 * S::T);
+        tma_load_2d(smem + S::OFF_K, &tmKV, kv_full, a.k_col0 + it.h * ATT_D, it.b * a.Sk + it.k0);
+        tma_load_2d(smem + S::OFF_V, &tmKV, kv_full, a.v_col0 + it.h * ATT_D, it.b * a.Sk + it.k0);
+        for (int i = 1; i < nq; ++i) load_qdo(i);
+        ++n;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    constexpr uint32_t idesc_s = make_idesc_f16(128, 64, 0, 0);     // S_g, dP_g : both K-major, N = 64 keys
+    constexpr uint32_t idesc_t = make_idesc_f16(128, 64, 1, 1);     // dV, dK   : A and B MN-major
+    constexpr uint32_t idesc_q = make_idesc_f16(128, 64, 0, 1);     // dQ       : A K-major, B MN-major
+    const uint32_t ka = smem_u32(smem + S::OFF_K), va = smem_u32(smem + S::OFF_V);
+    const uint32_t pa = smem_u32(smem + S::OFF_P), dsa = smem_u32(smem + S::OFF_DS);
+    auto issue_scores = [&](uint32_t st, int g) {
+      const uint32_t qa = smem_u32(smem + S::OFF_QDO + st * 2 * S::T), doa = qa + S::T;
+      const uint32_t kg = ka + g * 64 * 128, vg = va + g * 64 * 128;            // rows [64g, 64g+64) of the K / V tiles
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+        umma_ss(tmem + g * 64, make_smem_desc(qa + kk * 32, 0, 1024), make_smem_desc(kg + kk * 32, 0, 1024), idesc_s, kk > 0);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+        umma_ss(tmem + 128 + g * 64, make_smem_desc(doa + kk * 32, 0, 1024), make_smem_desc(vg + kk * 32, 0, 1024), idesc_s, kk > 0);
+      umma_commit(&s_full[g]);
+    };
+    uint32_t n = 0, qs = 0, ir = 0;     // live items seen, Q / dO ring position, query blocks processed so far
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const Item it = decode(item);
+      if (it.dead) continue;
+      mbar_wait(kv_full, n & 1);
+      mbar_wait(&qdo_full[qs % NST], (qs / NST) & 1);
+      if (ir > 0) mbar_wait(&s_free[0], (ir - 1) & 1);      // group 0 holds its last block in registers
+      tc_fence_after();
+      if (lane == 0) issue_scores(qs % NST, 0);
+      __syncwarp();
+      for (int i = 0; i < nq; ++i, ++ir, ++qs) {
+        const uint32_t st = qs % NST;
+        if (i == 0) {
+          // group 1's first scores of the item.  At the very start of the kernel they are held back until group 0 has pulled
+          // its own block out of TMEM, so that the two groups run half a period apart (header).
+          if (ir > 0) mbar_wait(&s_free[1], (ir - 1) & 1);
+          else mbar_wait(&s_free[0], 0);
+          tc_fence_after();
+          if (lane == 0) issue_scores(st, 1);
+          __syncwarp();
+        }
+        if (i + 1 < nq) {                     // scores of the next block as soon as a group holds block i in registers
+          const uint32_t nst = (qs + 1) % NST;
+          mbar_wait(&qdo_full[nst], ((qs + 1) / NST) & 1);
+          for (int g = 0; g < 2; ++g) {
+            mbar_wait(&s_free[g], ir & 1);
+            tc_fence_after();
+            if (lane == 0) issue_scores(nst, g);
+            __syncwarp();
+          }
+        }
+        mbar_wait(ds_full, ir & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t qa = smem_u32(smem + S::OFF_QDO + st * 2 * S::T), doa = qa + S::T;
+          if (!(a.dbg & 0x20000)) {
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)        // dV += P^T dO_i      (K = 16 query rows per step)
+              umma_ss(tmem + 256, make_smem_desc(pa + kk * 2048, 16384, 1024), make_smem_desc(doa + kk * 2048, 8192, 1024), idesc_t,
+                      (i > 0 || kk > 0) ? 1u : 0u);
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)        // dK += dS^T Q_i
+              umma_ss(tmem + 320, make_smem_desc(dsa + kk * 2048, 16384, 1024), make_smem_desc(qa + kk * 2048, 8192, 1024), idesc_t,
+                      (i > 0 || kk > 0) ? 1u : 0u);
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)        // dQ_i = dS K         (K = 16 keys per step)
+              umma_ss(tmem + 384 + (ir & 1) * 64, make_smem_desc(dsa + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024),
+                      make_smem_desc(ka + kk * 2048, 8192, 1024), idesc_q, kk > 0);
+          }
+          umma_commit(&qdo_empty[st]);
+          umma_commit(grad_done);
+          if (i + 1 == nq) umma_commit(kv_empty);             // K / V of this item are dead once these MMAs retire
+        }
+        __syncwarp();
+      }
+      ++n;
+    }
+  } else {
+    const int sw = warp - 2;                      // 0..15
+    const int qd = warp & 3;                      // TMEM lane quadrant
+    const int g = sw >> 3;                        // key half (score columns [64g, 64g+64)); also which 32 of the 64 d columns
+    const int sq = (sw >> 2) & 1;                 // 32-key quarter inside the half; also: 0 = drains dQ / dV, 1 = drains dK
+    const int r = qd * 32 + lane;                 // query row inside the block == TMEM lane (key row for dV / dK)
+    const int t = threadIdx.x - 64;               // 0..511
+    const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
+    const uint32_t bias_s = smem_u32(smem + S::OFF_BIAS);
+    const uint32_t p_row = smem_u32(smem + S::OFF_P) + g * 16384 + r * 128;
+    const uint32_t ds_row = smem_u32(smem + S::OFF_DS) + g * 16384 + r * 128;
+    const uint32_t dseed = DROP ? drop_seed(a.drop) : 0u;
+    const uint32_t skp = static_cast<uint32_t>((a.Sk + 1) >> 1);
+    const float sc = a.scale_log2;
+    const uint32_t dtt = a.drop.thr15 * 0x00010001u;
+    const uint32_t cs_bits = __float_as_uint(a.inv_sqrt_d * a.drop.scale);   // dP coefficient of a kept element
+    uint8_t* dqs = smem + S::OFF_DQS + (g * 4 + (sw & 3)) * 4096;     // (sq == 0 warps) this warp's [32 q][32 d] fp32 staging patch
+    const uint32_t dqs_row = smem_u32(dqs) + lane * 128;
+    const int kcol = g * 64 + sq * 32;            // first score column of this thread
+    uint32_t ir = 0;                              // query blocks processed so far (barrier phases, dQ buffer)
+
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const Item it = decode(item);
+      const int b = it.b, h = it.h, k0 = it.k0, kv_len = it.kv_len;
+      if (it.dead) {
+        if (sw < 4 && k0 + r < a.Sk) {
+          const size_t row = static_cast<size_t>(b) * a.Sk + k0 + r;
+          const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            *reinterpret_cast<uint4*>(a.dk + row * a.ld_dkv + a.dk_col0 + h * ATT_D + i * 8) = z;
+            *reinterpret_cast<uint4*>(a.dv + row * a.ld_dkv + a.dv_col0 + h * ATT_D + i * 8) = z;
+          }
+        }
+        continue;
+      }
+      const size_t stat_base = (static_cast<size_t>(b) * a.heads + h) * a.Sq;
+      const int kg0 = k0 + kcol;                  // first key of this thread's columns
+      const int lim = kv_len - kg0;               // keys [0, lim) of this quarter are kept (prefix masks)
+      const bool partial = lim < 32;
+      if (it.general_bias) {                      // this item's 128 bias values (the barrier also fences the previous item's reads)
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (t < ATT_BK) {
+          const int key = k0 + t;
+          float bv = -INFINITY;
+          if (key < kv_len) bv = a.key_bias[static_cast<size_t>(b) * a.Sk + key] * 1.4426950408889634f;
+          sts_f32(bias_s + t * 4, bv);
+        }
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+      }
+
+      // dQ tile of block (ir_blk): TMEM lane == query row; one TMA reduce-add per (sq == 0) warp from its swizzled staging patch
+      auto drain_dq = [&](uint32_t ir_blk, int i) {
+        uint32_t o[32];
+        tmem_ld_x32(tmem + lane_addr + 384 + (ir_blk & 1) * 64 + g * 32, o);
+        tmem_wait_ld();
+        if (a.dbg & 0x10000) return;
+        if (lane == 0) tma_wait_group_read<0>();   // the previous reduction has finished reading the staging patch
+        __syncwarp();
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) sts128(dqs_row + ((ch ^ (lane & 7)) << 4), o[4 * ch], o[4 * ch + 1], o[4 * ch + 2], o[4 * ch + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_reduce_add_2d(&tmDQ, dqs, h * ATT_D + g * 32, b * a.Sq + i * ATT_BQ + qd * 32);
+          tma_commit_group();
+        }
+      };
+
+      // per-query statistics of block 0 (queries past Sq: lse = +inf -> P = 0, delta = 0)
+      float lse_n = (r < a.Sq) ? a.lse2[stat_base + r] : INFINITY;
+      float del_n = (r < a.Sq) ? a.delta[stat_base + r] : 0.f;
+      for (int i = 0; i < nq; ++i, ++ir) {
+        const float neg_lse = -lse_n, ndc = -del_n * a.inv_sqrt_d;
+        const int q = i * ATT_BQ + r;
+        if (i + 1 < nq) {                         // prefetch the next block's statistics
+          const int qn = q + ATT_BQ;
+          lse_n = (qn < a.Sq) ? a.lse2[stat_base + qn] : INFINITY;
+          del_n = (qn < a.Sq) ? a.delta[stat_base + qn] : 0.f;
+        }
+        mbar_wait(&s_full[g], ir & 1);
+        tc_fence_after();
+        uint32_t sv[32], dp[32];
+        tmem_ld_x32(tmem + lane_addr + kcol, sv);
+        tmem_ld_x32(tmem + lane_addr + 128 + kcol, dp);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();                             // the tensor core may overwrite S_g / dP_g with the next block once all 8 warps of the half hold theirs
+        if (lane == 0) mbar_arrive(&s_free[g]);
+        // masked keys: turn their scores into -inf (P = 0, dS = 0)
+        if (it.general_bias) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            const uint4 bb = lds128(bias_s + (kcol + c) * 4);
+            sv[c] = __float_as_uint(fmaf(__uint_as_float(bb.x), 1.0f / sc, __uint_as_float(sv[c])));
+            sv[c + 1] = __float_as_uint(fmaf(__uint_as_float(bb.y), 1.0f / sc, __uint_as_float(sv[c + 1])));
+            sv[c + 2] = __float_as_uint(fmaf(__uint_as_float(bb.z), 1.0f / sc, __uint_as_float(sv[c + 2])));
+            sv[c + 3] = __float_as_uint(fmaf(__uint_as_float(bb.w), 1.0f / sc, __uint_as_float(sv[c + 3])));
+          }
+        } else if (partial) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) sv[c] = (c < lim) ? sv[c] : 0xff800000u;
+        }
+        uint32_t pk[16], dk[16];                  // this thread's 32 P / dS values, packed fp16
+        // dropout: (pair + seed) * C1 of this row's first pair; consecutive pairs add C1 (ptx.cuh: drop_z)
+        const uint32_t dpre = DROP ? drop_premix(static_cast<uint32_t>(stat_base + min(q, a.Sq - 1)) * skp + (static_cast<uint32_t>(kg0) >> 1), dseed) : 0u;
+        if (a.dbg & 0x40000) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) pk[e] = dk[e] = sv[2 * e] ^ dp[2 * e + 1];
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float p0 = fast_exp2(fmaf(__uint_as_float(sv[2 * e]), sc, neg_lse));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(sv[2 * e + 1]), sc, neg_lse));
+            const float g0 = __uint_as_float(dp[2 * e]), g1 = __uint_as_float(dp[2 * e + 1]);
+            float c0 = a.inv_sqrt_d, c1 = a.inv_sqrt_d;
+            const __half2 hp = __floats2half2_rn(p0, p1);
+            pk[e] = *reinterpret_cast<const uint32_t*>(&hp);
+            if (DROP) {       // P o mask feeds dV (its 1/(1-p) is applied to dV at the end); dP flows back through mask/(1-p)
+              const uint32_t z = drop_z(dpre + static_cast<uint32_t>(e) * kDropC1, dtt);
+              pk[e] &= drop_keep_h2(z);
+              c0 = __uint_as_float(drop_keep_lo(z) & cs_bits);
+              c1 = __uint_as_float(drop_keep_hi(z) & cs_bits);
+            }
+            const float d0 = p0 * fmaf(g0, c0, ndc);                    // P o (dP_eff - delta) / sqrt(d)
+            const float d1 = p1 * fmaf(g1, c1, ndc);
+            const __half2 hd = __floats2half2_rn(d0, d1);
+            dk[e] = *reinterpret_cast<const uint32_t*>(&hd);
+          }
+        }
+        if (i > 0) {                              // gradient MMAs of the previous block are done: its dQ is complete, P / dS are free
+          mbar_wait(grad_done, (ir - 1) & 1);
+          tc_fence_after();
+        } else if (t == 0) {
+          tma_wait_group_read<0>();               // the previous item's dK / dV stores have read the staging patches (see the epilogue)
+        }
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {          // this thread's 64 bytes of the row: chunks 4 sq .. 4 sq + 3 of the 128-byte swizzled row
+          const int off = (((sq * 4 + ch) ^ (r & 7)) << 4);
+          sts128(p_row + off, pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+          sts128(ds_row + off, dk[4 * ch], dk[4 * ch + 1], dk[4 * ch + 2], dk[4 * ch + 3]);
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ds_full);
+        // dQ of the previous block sits in the other TMEM buffer: reduce it into HBM off the critical path
+        if (i > 0 && sq == 0) drain_dq(ir - 1, i - 1);
+      }
+      // ------------------------------------------------------------------ item epilogue
+      mbar_wait(grad_done, (ir - 1) & 1);
+      tc_fence_after();
+      if (sq == 0) drain_dq(ir - 1, nq - 1);
+      // dV (sq == 0 warps) / dK (sq == 1 warps): TMEM lane == key row; this thread owns 32 of the 64 d columns (g).  A full key
+      // block leaves as two TMA stores from the dQ staging patches ([128 keys][64 d] fp16 each); a block that straddles the end of
+      // the batch element stores directly.
+      const int key = k0 + r;
+      const bool full_block = k0 + ATT_BK <= a.Sk;
+      if (full_block) {
+        if (lane == 0) tma_wait_group_read<0>();  // every warp's last dQ reduction has read its patch ...
+        asm volatile("bar.sync 1, 512;" ::: "memory");   // ... before anybody overwrites it
+      }
+      {
+        const int which = sq;                     // 0 = dV, 1 = dK
+        uint32_t o[32];
+        tmem_ld_x32(tmem + lane_addr + 256 + which * 64 + g * 32, o);
+        tmem_wait_ld();
+        uint32_t w[16];
+        const float osc = (DROP && which == 0) ? a.drop.scale : 1.0f;      // dV = (P o mask / (1-p))^T dO
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const __half2 hv = __floats2half2_rn(__uint_as_float(o[2 * k]) * osc, __uint_as_float(o[2 * k + 1]) * osc);
+          w[k] = *reinterpret_cast<const uint32_t*>(&hv);
+        }
+        if (full_block) {
+          const uint32_t row_s = smem_u32(smem + S::OFF_DQS + which * S::T) + r * 128;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) sts128(row_s + (((g * 4 + e) ^ (r & 7)) << 4), w[4 * e], w[4 * e + 1], w[4 * e + 2], w[4 * e + 3]);
+        } else if (key < a.Sk) {
+          __half* dst = (which == 0 ? a.dv + a.dv_col0 : a.dk + a.dk_col0) + (static_cast<size_t>(b) * a.Sk + key) * a.ld_dkv + h * ATT_D + g * 32;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) *reinterpret_cast<uint4*>(dst + e * 8) = make_uint4(w[4 * e], w[4 * e + 1], w[4 * e + 2], w[4 * e + 3]);
+        }
+      }
+      tc_fence_before();
+      if (full_block) {
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (t == 0) {
+          tma_store_2d(&tmDKV, smem + S::OFF_DQS, a.dv_col0 + h * ATT_D, b * a.Sk + k0);
+          tma_store_2d(&tmDKV, smem + S::OFF_DQS + S::T, a.dk_col0 + h * ATT_D, b * a.Sk + k0);
+          tma_commit_group();
+        }
+      }
+    }
+    if (lane == 0) tma_wait_group_read<0>();      // staging memory stays valid until the bulk copies have read it
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace b200

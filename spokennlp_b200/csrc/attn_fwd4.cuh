@@ -1,0 +1,376 @@
+// Fused attention forward, fourth generation: attn_fwd3_kernel's schedule (persistent CTA per SM walking (batch, head,
+// 256-query pair) items; two 128-row query tiles half a period apart; S in TMEM handed back to the tensor core as soon as it
+// sits in registers; P via swizzled smem; context rows leave by TMA store) with SIXTEEN softmax warps instead of eight.
+//
+// Why (profiles/r02a_attn_drop_kernel_metrics.md, r02a_attn_roles.txt — the round-2 capture of attn_fwd3 with dropout on): the
+// softmax warps are the critical path (5 % of their samples wait on a barrier) yet issue only 0.46 instructions per cycle per
+// scheduler with no pipe above 42 %: two warps per scheduler, each walking a 1248-instruction block body with 128 live score
+// registers, cannot hide the fixed-latency dependencies (22 % "wait") and the MUFU queue (14 % "mio throttle").  Here a query
+// row's 128-key block is split between TWO threads (64 keys each) that sit in warps w and w + 4 of the tile's group (same TMEM
+// lane quadrant): four softmax warps per scheduler, 64 live scores per thread (96 registers at 19 warps).  The two halves of a
+// row must agree on the running maximum — the P tile and the O accumulator carry ONE scale per row — so they exchange their
+// block maxima through shared memory (one 64-thread named barrier per block), and their partial row sums once per item.
+//   warp 0       TMA producer
+//   warp 1, 2    MMA issuers for query tile A / B
+//   warps 3-18   softmax: warp - 3 = 8 x + 4 sh + quadrant slot; x = tile, sh = key half (keys [64 sh, 64 sh + 64) of the block)
+#pragma once
+#include "attn_fwd3.cuh"
+
+namespace b200 {
+
+constexpr int ATTP4_THREADS = 96 + 16 * 32;
+
+struct AttnFwd4Smem {
+  static constexpr int TILE = ATT_BQ * ATT_D * 2;                    // 16 KB: one Q / K / V tile
+  static constexpr int P_BYTES = ATT_BQ * ATT_BK * 2;                // 32 KB per query tile
+  static constexpr int OFF_Q = 0;                                    // [2 item parities][2 tiles]
+  static constexpr int OFF_K = OFF_Q + 4 * TILE;                     // [2 stages]
+  static constexpr int OFF_V = OFF_K + 2 * TILE;                     // [2 stages]
+  static constexpr int OFF_P = OFF_V + 2 * TILE;                     // [2 tiles]
+  static constexpr int OFF_BIAS = OFF_P + 2 * P_BYTES;               // [2 tiles][2 buffers][128] floats
+  static constexpr int OFF_XCH = OFF_BIAS + 2 * 2 * ATT_BK * 4;      // [2 tiles][3 buffers][2 halves][128 rows] floats: block maxima (0, 1) / row sums (2)
+  static constexpr int OFF_BAR = OFF_XCH + 2 * 3 * 2 * ATT_BQ * 4;
+  static constexpr int TOTAL = OFF_BAR + 256 + 1024;
+  static_assert(TOTAL <= 232448, "shared-memory plan");
+};
+
+template <bool DROP>
+__global__ void __launch_bounds__(ATTP4_THREADS, 1)
+attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                 const __grid_constant__ CUtensorMap tmO, const AttnFwdArgs a) {
+  using S = AttnFwd4Smem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
+  uint64_t* q_full = bars;             // 2
+  uint64_t* q_empty = bars + 2;        // 2 (one arrival per MMA warp)
+  uint64_t* k_full = bars + 4;         // 2
+  uint64_t* k_empty = bars + 6;        // 2 (one arrival per MMA warp)
+  uint64_t* v_full = bars + 8;         // 2
+  uint64_t* v_empty = bars + 10;       // 2 (one arrival per MMA warp)
+  uint64_t* s_full = bars + 12;        // 2 (per tile)
+  uint64_t* s_free = bars + 14;        // 2 (8 warp arrivals)
+  uint64_t* p_full = bars + 16;        // 2 (8 warp arrivals)
+  uint64_t* o_full = bars + 18;        // 2
+  uint64_t* b_go = bars + 20;          // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nqp = (a.Sq + 2 * ATT_BQ - 1) / (2 * ATT_BQ);
+  const int n_items = a.B * a.heads * nqp;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+    tma_prefetch_desc(&tmO);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 2);
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 2);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 2);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 8);
+      mbar_init(&p_full[i], 8);
+      mbar_init(&o_full[i], 1);
+    }
+    mbar_init(b_go, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  // TMEM columns: S_A [0,128)  S_B [128,256)  O_A [256,320)  O_B [320,384)
+
+  // per-item geometry, identical in every role
+  struct Item {
+    int b, h, q0, kv_len, n_blocks;
+    bool tileB, general_bias;
+  };
+  auto decode = [&](int item) {
+    Item it;
+    const int qp = item % nqp, bh = item / nqp;
+    it.h = bh % a.heads;
+    it.b = bh / a.heads;
+    it.q0 = qp * 2 * ATT_BQ;
+    it.tileB = (it.q0 + ATT_BQ) < a.Sq;
+    int kv = a.kv_len ? a.kv_len[it.b] : a.Sk;
+    it.general_bias = a.key_bias != nullptr && (a.kv_len == nullptr || kv < 0);   // see attn_fwd.cuh
+    it.kv_len = max(1, min(kv < 0 ? -kv : kv, a.Sk));
+    it.n_blocks = (it.kv_len + ATT_BK - 1) / ATT_BK;
+    return it;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t n = 0, kb = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+        const Item it = decode(item);
+        const uint32_t buf = n & 1;
+        mbar_wait(&q_empty[buf], ((n >> 1) & 1) ^ 1);
+        mbar_expect_tx(&q_full[buf], (it.tileB ? 2 : 1) * S::TILE);
+        uint8_t* qd = smem + S::OFF_Q + buf * 2 * S::TILE;
+        tma_load_2d(qd, &tmQ, &q_full[buf], a.q_col0 + it.h * ATT_D, it.b * a.Sq + it.q0);
+        if (it.tileB) tma_load_2d(qd + S::TILE, &tmQ, &q_full[buf], a.q_col0 + it.h * ATT_D, it.b * a.Sq + it.q0 + ATT_BQ);
+        for (int j = 0; j < it.n_blocks; ++j, ++kb) {
+          const uint32_t s = kb & 1, ph = (kb >> 1) & 1;
+          mbar_wait(&k_empty[s], ph ^ 1);
+          mbar_expect_tx(&k_full[s], S::TILE);
+          tma_load_2d(smem + S::OFF_K + s * S::TILE, &tmKV, &k_full[s], a.k_col0 + it.h * ATT_D, it.b * a.Sk + j * ATT_BK);
+          mbar_wait(&v_empty[s], ph ^ 1);
+          mbar_expect_tx(&v_full[s], S::TILE);
+          tma_load_2d(smem + S::OFF_V + s * S::TILE, &tmKV, &v_full[s], a.v_col0 + it.h * ATT_D, it.b * a.Sk + j * ATT_BK);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp <= 2) {
+    // ------------------------------------------------------------------ MMA issuer of query tile x
+    const int x = warp - 1;
+    constexpr uint32_t idesc_s = make_idesc_f16(128, ATT_BK, 0, 0);
+    constexpr uint32_t idesc_o = make_idesc_f16(128, ATT_D, 0, 1);
+    const uint32_t pa = smem_u32(smem + S::OFF_P + x * S::P_BYTES);
+    uint32_t n = 0, kb = 0, t = 0;     // items seen, K/V ring position, blocks this tile has processed
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+      const Item it = decode(item);
+      const uint32_t buf = n & 1;
+      const int nb = it.n_blocks;
+      if (x == 1 && !it.tileB) {       // no second tile in this item: keep the shared rings' arrival counts balanced
+        mbar_wait(&q_full[buf], (n >> 1) & 1);
+        if (lane == 0) mbar_arrive(&q_empty[buf]);
+        for (int j = 0; j < nb; ++j, ++kb) {
+          const uint32_t s = kb & 1, ph = (kb >> 1) & 1;
+          mbar_wait(&k_full[s], ph);
+          if (lane == 0) mbar_arrive(&k_empty[s]);
+          mbar_wait(&v_full[s], ph);
+          if (lane == 0) mbar_arrive(&v_empty[s]);
+        }
+        __syncwarp();
+        continue;
+      }
+      const uint32_t qa = smem_u32(smem + S::OFF_Q + (buf * 2 + x) * S::TILE);
+      auto issue_s = [&](uint32_t s, bool last) {          // S_x = Q_x K^T from K ring stage s
+        const uint32_t ka = smem_u32(smem + S::OFF_K + s * S::TILE);
+#pragma unroll
+        for (int kk = 0; kk < ATT_D / 16; ++kk)
+          umma_ss(tmem + x * 128, make_smem_desc(qa + kk * 32, 0, 1024), make_smem_desc(ka + kk * 32, 0, 1024), idesc_s, kk > 0);
+        umma_commit(&s_full[x]);
+        umma_commit(&k_empty[s]);
+        if (last) umma_commit(&q_empty[buf]);                // Q of this item is not needed after its last score block
+      };
+      mbar_wait(&q_full[buf], (n >> 1) & 1);
+      mbar_wait(&k_full[kb & 1], (kb >> 1) & 1);
+      if (t > 0) mbar_wait(&s_free[x], (t - 1) & 1);         // the previous block's score rows sit in registers
+      else if (x == 1) mbar_wait(b_go, 0);                   // tile B starts half a period after tile A (header)
+      tc_fence_after();
+      if (lane == 0) issue_s(kb & 1, nb == 1);
+      __syncwarp();
+      for (int j = 0; j < nb; ++j, ++t, ++kb) {
+        const uint32_t s = kb & 1, ph = (kb >> 1) & 1;
+        if (j + 1 < nb) {                                    // next scores as soon as the softmax threads hold block j
+          const uint32_t s1 = (kb + 1) & 1, ph1 = ((kb + 1) >> 1) & 1;
+          mbar_wait(&k_full[s1], ph1);
+          mbar_wait(&s_free[x], t & 1);
+          tc_fence_after();
+          if (lane == 0) issue_s(s1, j + 2 == nb);
+          __syncwarp();
+        }
+        mbar_wait(&p_full[x], t & 1);
+        mbar_wait(&v_full[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t va = smem_u32(smem + S::OFF_V + s * S::TILE);
+#pragma unroll
+          for (int kk = 0; kk < ATT_BK / 16; ++kk)
+            umma_ss(tmem + 256 + x * 64, make_smem_desc(pa + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024),
+                    make_smem_desc(va + kk * 2048, 8192, 1024), idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+          umma_commit(&o_full[x]);
+          umma_commit(&v_empty[s]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax groups
+    const int sw = warp - 3;                      // 0..15
+    const int x = sw >> 3;                        // 0 = tile A, 1 = tile B
+    const int sh = (sw >> 2) & 1;                 // key half of the block this thread exponentiates; also its 32 of the 64 context columns
+    const int qd = warp & 3;                      // TMEM lane quadrant of this warp
+    const int r = qd * 32 + lane;                 // row inside the query tile
+    const int tg = (sw & 7) * 32 + lane;          // 0..255 inside the tile's group (bias staging)
+    const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
+    const uint32_t bias_s = smem_u32(smem + S::OFF_BIAS) + x * 2 * ATT_BK * 4;
+    const uint32_t xch = smem_u32(smem + S::OFF_XCH) + x * (3 * 2 * ATT_BQ * 4);       // [3 buffers][2 halves][128 rows]
+    const uint32_t p_row = smem_u32(smem + S::OFF_P + x * S::P_BYTES) + r * 128;
+    const int pair_bar = 1 + x * 4 + qd;          // named barrier of the two warps that share this tile's rows [32 qd, 32 qd + 32)
+    const int tile_bar = 9 + x;                   // named barrier of the tile's 8 warps (general-bias staging)
+    const float NEG_INF = -INFINITY;
+    const float sc = a.scale_log2;
+    const float inv_sc = 1.0f / sc;
+    const uint32_t dseed = DROP ? drop_seed(a.drop) : 0u;
+    uint32_t t = 0;                               // blocks this tile has processed (barrier phases)
+    // value of the partner thread (same row, other key half): write mine, 64-thread barrier, read the partner's
+    auto exchange = [&](uint32_t buf, float mine) {
+      sts_f32(xch + ((buf * 2 + sh) * ATT_BQ + r) * 4, mine);
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      return lds_f32(xch + ((buf * 2 + (sh ^ 1)) * ATT_BQ + r) * 4);
+    };
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const Item it = decode(item);
+      if (x == 1 && !it.tileB) continue;
+      const int b = it.b, h = it.h, kv_len = it.kv_len, n_blocks = it.n_blocks;
+      const int qrow = it.q0 + x * ATT_BQ + r;
+      // dropout: pair index of (row, key) = rowbase + key / 2; (pair + seed) * C1 is walked by adding multiples of C1
+      const uint32_t dpre = DROP ? drop_premix(static_cast<uint32_t>(((static_cast<size_t>(b) * a.heads + h) * a.Sq + min(qrow, a.Sq - 1)) * ((a.Sk + 1) >> 1)) + sh * 32, dseed) : 0u;
+      const uint32_t dtt = a.drop.thr15 * 0x00010001u;
+      float m = NEG_INF, l = 0.f;                 // l: this thread's share of the row sum
+      if (lane == 0) tma_wait_group_read<0>();    // the previous item's context store has read this warp's staging rows
+      __syncwarp();
+      for (int j = 0; j < n_blocks; ++j, ++t) {
+        const int lim = kv_len - j * ATT_BK - sh * 64;    // keys [0, lim) of this thread's half are kept (prefix masks)
+        const bool partial = lim < 64;
+        const uint32_t bj = bias_s + (t & 1) * ATT_BK * 4;
+        if (it.general_bias) {                    // bias in units of raw scores: (s + bias/scale) * scale = s*scale + bias
+          if (tg < ATT_BK) {
+            const int key = j * ATT_BK + tg;
+            float bv = NEG_INF;
+            if (key < kv_len) bv = a.key_bias[static_cast<size_t>(b) * a.Sk + key] * 1.4426950408889634f * inv_sc;
+            sts_f32(bj + tg * 4, bv);
+          }
+          asm volatile("bar.sync %0, 256;" ::"r"(tile_bar) : "memory");
+        }
+        mbar_wait(&s_full[x], t & 1);
+        tc_fence_after();
+        uint32_t v[64];
+        tmem_ld_x32(tmem + lane_addr + x * 128 + sh * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+        tmem_ld_x32(tmem + lane_addr + x * 128 + sh * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();                             // the tensor core may overwrite S_x with the next block once all 8 warps hold theirs
+        if (lane == 0) mbar_arrive(&s_free[x]);
+        if (x == 0 && t == 0 && tg == 0) mbar_arrive(b_go);
+        // ---- masked keys (only blocks that have any)
+        if (it.general_bias) {
+#pragma unroll
+          for (int i = 0; i < 64; i += 4) {
+            const uint4 bb = lds128(bj + (sh * 64 + i) * 4);
+            v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(bb.x));
+            v[i + 1] = __float_as_uint(__uint_as_float(v[i + 1]) + __uint_as_float(bb.y));
+            v[i + 2] = __float_as_uint(__uint_as_float(v[i + 2]) + __uint_as_float(bb.z));
+            v[i + 3] = __float_as_uint(__uint_as_float(v[i + 3]) + __uint_as_float(bb.w));
+          }
+        } else if (partial) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) v[i] = (i < lim) ? v[i] : 0xff800000u;
+        }
+        // ---- row maximum: this half's, then the row's (exchange with the partner thread)
+        float m0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1])), m1 = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
+#pragma unroll
+        for (int i = 4; i < 64; i += 4) {
+          m0 = fmaxf(m0, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+          m1 = fmaxf(m1, fmaxf(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])));
+        }
+        float mx = fmaxf(m0, m1) * sc;            // sc > 0
+        mx = fmaxf(mx, exchange(t & 1, mx));
+        // ---- lazy rescale: keep the running reference max unless some row of this warp grew by more than 2^8 (both warps of
+        // a row pair see the same rows and the same maxima, so they take the same decision)
+        const float m_new = fmaxf(m, mx);
+        const bool grow = (m_new - m) > 8.0f || m == NEG_INF;
+        const bool rescale = __any_sync(0xffffffffu, grow);
+        float m_use = rescale ? m_new : m;
+        if (m_use == NEG_INF) m_use = 0.f;
+        const float alpha = rescale ? fast_exp2(m - m_use) : 1.0f;     // m == -inf -> 0
+        if (j > 0) {                              // P.V of block j-1 finished: P smem is free, O may be rescaled
+          mbar_wait(&o_full[x], (t - 1) & 1);
+          tc_fence_after();
+          if (rescale) {                          // this thread's 32 of the row's 64 accumulator columns
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              uint32_t o[16];
+              tmem_ld_x16(tmem + lane_addr + 256 + x * 64 + sh * 32 + c * 16, o);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st_x16(tmem + lane_addr + 256 + x * 64 + sh * 32 + c * 16, o);
+            }
+            tmem_wait_st();
+          }
+        }
+        // ---- p = exp2(s * scale - m_use), row sum, fp16 P into the swizzled smem tile (this thread: 8 chunks of 8 keys)
+        const float neg_m = -m_use;
+        const uint32_t dpre_j = dpre + static_cast<uint32_t>(j * (ATT_BK / 2)) * kDropC1;
+        float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = ch * 8 + 2 * e;
+            float p0 = fast_exp2(fmaf(__uint_as_float(v[i]), sc, neg_m));
+            float p1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), sc, neg_m));
+            rs0 += p0;                              // the row sum (softmax denominator) is taken before dropout
+            rs1 += p1;
+            const __half2 hp = __floats2half2_rn(p0, p1);
+            pk[e] = *reinterpret_cast<const uint32_t*>(&hp);
+            if (DROP)                               // zero the dropped lanes of the packed pair; 1/(1-p) is applied to O at the end
+              pk[e] &= drop_keep_h2(drop_z(dpre_j + static_cast<uint32_t>(i >> 1) * kDropC1, dtt));
+          }
+          sts128(p_row + sh * 16384 + ((ch ^ (r & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+        }
+        l = fmaf(l, alpha, rs0 + rs1);
+        m = (m_use == 0.f && m_new == NEG_INF) ? NEG_INF : m_use;
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();                             // every lane has fenced its own P rows; one lane publishes the warp's share
+        if (lane == 0) mbar_arrive(&p_full[x]);
+      }
+      // ---------------------------------------------------------------- finalise: O / l -> ctx, LSE
+      l += exchange(2, l);                        // (its own buffer: the block maxima alternate between 0 and 1)
+      mbar_wait(&o_full[x], (t - 1) & 1);
+      tc_fence_after();
+      const float inv_l = (l > 0.f ? 1.0f / l : 0.f) * (DROP ? a.drop.scale : 1.0f);
+      uint32_t o[32];
+      tmem_ld_x32(tmem + lane_addr + 256 + x * 64 + sh * 32, o);
+      tmem_wait_ld();
+      tc_fence_before();
+      uint32_t w[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const __half2 hv = __floats2half2_rn(__uint_as_float(o[2 * k]) * inv_l, __uint_as_float(o[2 * k + 1]) * inv_l);
+        w[k] = *reinterpret_cast<const uint32_t*>(&hv);
+      }
+      const int wrow0 = it.q0 + x * ATT_BQ + qd * 32;        // first query row of this warp pair
+      if (wrow0 + 32 <= a.Sq) {                              // one TMA store per warp pair from a swizzled staging patch
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) sts128(p_row + (((sh * 4 + ch) ^ (r & 7)) << 4), w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
+        fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        if (sh == 0 && lane == 0) {
+          tma_store_2d(&tmO, smem + S::OFF_P + x * S::P_BYTES + qd * 32 * 128, h * ATT_D, b * a.Sq + wrow0);
+          tma_commit_group();
+        }
+      } else if (qrow < a.Sq) {
+        __half* dst = a.out + (static_cast<size_t>(b) * a.Sq + qrow) * a.ld_out + h * ATT_D + sh * 32;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) *reinterpret_cast<uint4*>(dst + ch * 8) = make_uint4(w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
+      }
+      if (sh == 0 && qrow < a.Sq && a.lse2) a.lse2[(static_cast<size_t>(b) * a.heads + h) * a.Sq + qrow] = (l > 0.f) ? (m + log2f(l)) : NEG_INF;
+    }
+    if (lane == 0) tma_wait_group_read<0>();      // staging memory stays valid until the bulk stores have read it
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace b200

@@ -68,7 +68,7 @@ def main():
     for p in (0.0, 0.1):
         drop = ops.Dropout(seed, 9, p) if p > 0 else None
         row = {"shape": "attention B32 S512 h12", "dropout": p}
-        for variant, tag in ((0, "default"), (1, "elect"), (3, "elect_wait")):
+        for variant, tag in ((0, "default"), (1, "elect"), (3, "elect_wait"), (4, "bwd16"), (8, "fwd16")):
             lib.load().b200_set_attn_variant(variant)
             row[f"fwd_{tag}_us"] = 1e6 * timeit(lambda: ops.attn_fwd(qkv, qkv, ctx2, B, heads, S, S, q_col0=0, k_col0=H, v_col0=2 * H, lse2=lse2, drop=drop))
             row[f"bwd_{tag}_us"] = 1e6 * timeit(lambda: ops.attn_bwd(qkv, qkv, dctx, ctx2, lse2, dqkv, dqkv, ws, B, heads, S, S, drop=drop, **kw))
