@@ -57,18 +57,14 @@ long long b200_launch_count(void);
  * Replaces torch.nn.functional.linear and its autograd (dgrad: b_layout=1 on the same weight; wgrad:
  * a_layout=b_layout=1 on dY and X) — SURVEY.md K2, K4, K5, K6, K8.
  * Supported (a_layout,b_layout,epilogue,out_dtype): (0,0,{STORE,BIAS,BIAS_GELU,BIAS_RES,BIAS_RES32},{F16,F32*}),
- * (0,1,{STORE,ADD,DGELU},F16), (1,1,ATOMIC,F32).  (*F32 for STORE, BIAS, BIAS_RES (single-CTA kernel only), BIAS_RES32; BIAS_RES32 is F32-only.)
+ * (0,1,{STORE,ADD,DGELU},F16), (1,1,ATOMIC,F32).  (*F32 for STORE, BIAS and BIAS_RES32; BIAS_RES32 is F32-only.)
  * alpha: optional device scalar multiplied into the accumulator.  k_splits > 1 only with EPI_ATOMIC.
  */
-/* 2 (default): 2-CTA cta_group::2 kernel with TMA epilogue; 1: single-CTA kernel (kept for A/B measurements) */
-void b200_set_gemm_impl(int impl);
-/* measurement knobs.  Bits 1/2/4/8 (2-CTA GEMM: skip A loads / B loads / MMA / stores) and 0x10000/0x20000/0x40000 (attention
- * backward: skip dQ reductions / gradient MMAs / exp math) make results WRONG.  Kernel-generation selectors keep results
- * right and exist for A/B timing: 0x100000 first-generation attention kernels, 0x200000 first-generation LayerNorm backward. */
-void b200_set_gemm_debug(int bits);
-/* Persistent kernels (GEMM, attention: one CTA or CTA pair per SM) size their grids to min(device SMs, sms); 0 = all SMs.
+/* The library keeps no result-affecting global state (no kernel selectors, no debug switches: the round-1 A/B knobs were
+ * removed once their measurements were in profiles/).  The one process-wide setting is a RESOURCE reservation:
+ * persistent kernels (GEMM, attention: one CTA or CTA pair per SM) size their grids to min(device SMs, sms); 0 = all SMs.
  * A data-parallel caller reserves the SMs its concurrently running NCCL kernels occupy, so that no compute CTA has to
- * wait for a communication kernel to leave before it can start. */
+ * wait for a communication kernel to leave before it can start.  Results do not depend on it. */
 void b200_set_sm_limit(int sms);
 int b200_gemm_f16(const void* A, int lda, int a_layout, const void* B, int ldb, int b_layout, int M, int N, int K,
                   int epilogue, const float* bias, const void* aux, int ld_aux, void* out, int ld_out, int out_dtype,
@@ -228,26 +224,28 @@ int b200_cls_head_bwd_drop(const void* h, const float* logits, const int64_t* la
                            const float* scale, void* dh, float* dW, float* db, int rows, int H, int C, const uint32_t* seed, unsigned site,
                            float p, void* stream);
 
-/* ---- opt-in variants (written in round 1 after the GPU budget was spent; NOT on the default path until a
- * GPU run has held them to the oracle) ---------------------------------------------------------------------------------
+/* ---- fused epilogue variants (written after round 1, validated and measured on a B200 in round 2 — profiles/r02a_* —
+ * and used by the default layer schedule, spokennlp_b200/blocks.py) -------------------------------------------------------
  *
  * b200_gemm_f16_resadd: out32[M,N] += drop(A[M,K] * B[N,K]^T + bias[n]).  `out` already holds the fp32 residual (what
  *   LayerNorm wrote), so `LN(dropout(dense(x)) + residual)` (bert_model.py:371-375, :449-453) needs no residual read in the
- *   epilogue: partial tiles leave through TMA reduce-add.  stream_k != 0 cuts the K blocks of all tiles into equal shares
- *   per CTA pair (no straggler round for N = 768); results then depend on the fp32 summation order (last-bit differences).
+ *   epilogue: tiles leave through TMA reduce-add.
  * b200_gemm_f16_dgrad_delta: out16[M,N] = A[M,K] * B[K,N] (B row-major [K,N]: the output projection's dgrad), and
  *   delta[b,h,q] = sum_d out[b*Sq+q, 64h+d] * ctx[b*Sq+q, 64h+d] — the row statistic of attention backward, written to the
  *   head of the attention-backward workspace (b200_attn_bwd_delta_ptr) so that b200_attn_bwd_ext can skip its own pass.
+ * b200_gemm_f16_dgelu_colsum: dz = (A . W) o dact (the FFN-down dgrad with the dGELU epilogue: A = d_dense [M,K] fp16,
+ *   W [K,N] row-major = the dense layer's [out,in] weight read MN-major in place, dact = gelu'(z) saved by the forward) AND,
+ *   in the same epilogue, colsum[n] += *col_alpha * sum_m dz[m,n] — the bias gradient of BertIntermediate.dense
+ *   (bert_model.py:436-439), taken from the fp16-rounded tile while it sits in the store staging slab instead of re-reading
+ *   dz from HBM (b200_colsum).
  * b200_attn_bwd_ext: b200_attn_bwd_drop + flags. */
-/* b200_set_attn_variant: bit 0 = the persistent attention kernels signal their softmax->MMA hand-offs with one mbarrier
- * arrival per warp instead of one per thread; bit 1 (only together with bit 0) = the softmax warps also wait with one lane
- * per warp.  Same results; scheduling experiments.  0 = round-1 kernels. */
-void b200_set_attn_variant(int bits);
 #define B200_ATTN_BWD_DELTA_READY 1   /* workspace already holds delta (from b200_gemm_f16_dgrad_delta) */
 int b200_gemm_f16_resadd(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias, float* out, int ld_out,
-                         const uint32_t* seed, unsigned site, float p, int stream_k, void* stream);
+                         const uint32_t* seed, unsigned site, float p, void* stream);
 int b200_gemm_f16_dgrad_delta(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const void* ctx, int ld_ctx, void* out,
                               int ld_out, float* delta, int heads, int Sq, void* stream);
+int b200_gemm_f16_dgelu_colsum(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const void* dact, int ld_dact, void* out,
+                               int ld_out, float* colsum, const float* col_alpha, void* stream);
 float* b200_attn_bwd_delta_ptr(void* workspace);
 int b200_attn_bwd_ext(const void* q, int ldq, int q_col0, const void* kv, int ldkv, int k_col0, int v_col0, const void* dctx, int ld_dctx,
                       const void* ctx, int ld_ctx, const float* key_bias, const int32_t* kv_len, const float* lse2, void* workspace,

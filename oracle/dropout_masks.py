@@ -6,11 +6,15 @@ fall is not part of the algorithm.  The CUDA path instead hashes (step seed, sit
 regenerates the forward's mask.  This file repeats that hash on the host so the tests can hand the SAME masks to
 `bert_oracle` (its `masks=` argument) and compare values and gradients under dropout.
 
-Conventions: one 32-bit hash per PAIR of consecutive elements (bits [0,15) -> even element, bits [16,31) -> odd element);
-an element is kept iff its 15-bit lane >= round(p * 32768); kept elements are multiplied by 1/(1-p).  The pair index
-enters the hash by addition: h = fin((idx + seed) * 0x9E3779B1), fin = xorshift 15, multiply 0x85EBCA6B, xorshift 13.
-  hidden / embedding / classifier-input sites, tensor [rows, H]:  element index = row * H + col
-  attention-probability sites, tensor [B, heads, Sq, Sk]:         pair index = ((b*heads + h)*Sq + q) * ceil(Sk/2) + key//2
+Conventions.  The index enters the hash by addition: h = fin((idx + seed) * 0x9E3779B1), fin = xorshift 15, multiply
+0x85EBCA6B, xorshift 13.
+  hidden / embedding / classifier-input sites, tensor [rows, H]: one 32-bit hash per PAIR of consecutive elements (bits
+    [0,15) -> even element, bits [16,31) -> odd element), pair index = (row * H + col) // 2; an element is kept iff its 15-bit
+    lane >= round(p * 32768); kept elements are multiplied by 1/(1-p).
+  attention-probability sites, tensor [B, heads, Sq, Sk]: one hash per FOUR consecutive keys (the attention kernels are
+    instruction-issue bound; ptx.cuh: drop4_z), quad index = ((b*heads + h)*Sq + q) * ceil(Sk/4) + key//4, lane l = key % 4
+    -> bits [8l, 8l+7); kept iff lane >= thr[l] where the four thresholds sum to t = round(512 p) (thr[l] = t//4 + (l < t%4));
+    kept elements are multiplied by 512 / (512 - t), the inverse of the EFFECTIVE keep rate (p = 0.1: t = 51, rate 0.0996).
 Site ids: layer*8 + {0: probabilities, 1: attention output dense, 2: FFN output dense, 3/4: cross-attention}, 0xE000
 embeddings, 0xE001 classifier input (spokennlp_b200/engine.py: DropPlan).
 """
@@ -52,11 +56,17 @@ def hidden_mask(base_seed: int, site: int, p: float, rows: int, H: int) -> torch
 
 
 def prob_mask(base_seed: int, site: int, p: float, B: int, heads: int, Sq: int, Sk: int) -> torch.Tensor:
-    """[B, heads, Sq, Sk] multipliers."""
-    skp = (Sk + 1) // 2
-    pairs = np.arange(B * heads * Sq * skp, dtype=np.uint64)
-    lo, hi = _lanes(pairs, base_seed, site, p)
-    full = np.stack([lo, hi], axis=1).reshape(B, heads, Sq, 2 * skp)
+    """[B, heads, Sq, Sk] multipliers (quad format, see the module docstring)."""
+    skq = (Sk + 3) // 4
+    quads = np.arange(B * heads * Sq * skq, dtype=np.uint64)
+    h = _hash(quads, site_seed(base_seed, site))
+    t = int(np.float32(p) * np.float32(512.0) + np.float32(0.5))
+    scale = np.float32(512.0) / (np.float32(512.0) - np.float32(t))
+    lanes = []
+    for l in range(4):
+        thr = np.uint64(t // 4 + (1 if l < t % 4 else 0))
+        lanes.append(np.where(((h >> np.uint64(8 * l)) & np.uint64(0x7F)) >= thr, scale, np.float32(0)).astype(np.float32))
+    full = np.stack(lanes, axis=1).reshape(B, heads, Sq, 4 * skq)
     return torch.from_numpy(np.ascontiguousarray(full[..., :Sk]))
 
 

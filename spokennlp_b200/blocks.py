@@ -22,23 +22,19 @@ F16, F32 = torch.float16, torch.float32
 
 
 class Experimental:
-    """Kernel-variant switches.  Three variants written after round 1 were validated and measured on a B200 in round 2
-    (profiles/r02a_variants_ab.jsonl, profiles/bench_r02a_*.json) and are now THE DEFAULT path:
+    """Host-side schedule switches: which fused entry points a layer calls.  Nothing here is library state — each switch picks
+    between two sequences of C-ABI calls that compute the same thing.  All three were validated and measured on a B200 in
+    round 2 (profiles/r02a_variants_ab.jsonl, bench_r02a_*.json, r02c_*) and are ON by default:
       resadd : output-dense + residual through b200_gemm_f16_resadd (in place on the fp32 residual stream, no aux reads):
                out-proj 51 -> 28 us, FFN-down 81 -> 74 us per layer at the bench shape (64 -> 29 / 84 -> 74 with dropout)
       delta  : attention-backward row statistic fused into the output projection's dgrad (b200_gemm_f16_dgrad_delta): -12 us/layer
-      elect  : persistent attention kernels with one mbarrier arrival per softmax warp: backward 211 -> 202 us with dropout
-    Two were measured slower and stay opt-in only for A/B runs:
-      streamk: stream-K schedule for the resadd GEMMs (74 -> 80 us on FFN-down: the extra reduce-adds cost more than the tail)
-      ewait  : softmax warps also WAIT with one lane per warp (+1-2 % on both attention kernels)
-    Under evaluation:
-      bwd16  : attention backward with sixteen softmax warps, 32 keys per thread (attn_bwd4.cuh)
-      fwd16  : attention forward with sixteen softmax warps, 64 keys per thread + row-maximum exchange (attn_fwd4.cuh)
-    `B200_EXP` (comma-separated) names the variants to run; unset = the default set.  `B200_EXP=none` is the round-1 path."""
-    DEFAULT = "resadd,delta,elect"
-    resadd = streamk = delta = elect = ewait = bwd16 = fwd16 = False
-    _applied = 1                                  # the library's own default selector (elect)
-    NAMES = ("resadd", "streamk", "delta", "elect", "ewait", "bwd16", "fwd16")
+      colsum : bias gradient of the FFN-up dense summed inside the FFN-down dgrad's dGELU epilogue (b200_gemm_f16_dgelu_colsum)
+    `B200_EXP` (comma-separated) names the switches to turn on instead of the default set; `B200_EXP=none` is the round-1
+    schedule.  (Measured and dropped in round 2: a stream-K schedule for the resadd GEMMs, lane-elected mbarrier WAITS in the
+    attention kernels, and sixteen-warp attention kernels — DESIGN.md §9.)"""
+    DEFAULT = "resadd,delta,colsum"
+    NAMES = ("resadd", "delta", "colsum")
+    resadd = delta = colsum = False
 
     @classmethod
     def from_env(cls, value: Optional[str] = None) -> None:
@@ -49,16 +45,9 @@ class Experimental:
         names = {n.strip() for n in raw.split(",") if n.strip() and n.strip() != "none"}
         unknown = names - set(cls.NAMES)
         if unknown:
-            raise ValueError(f"B200_EXP: unknown variant(s) {sorted(unknown)}")
-        cls.resadd, cls.streamk, cls.delta = "resadd" in names or "streamk" in names, "streamk" in names, "delta" in names
-        cls.ewait = "ewait" in names
-        cls.elect = "elect" in names or cls.ewait
-        cls.bwd16, cls.fwd16 = "bwd16" in names, "fwd16" in names
-        sel = (3 if cls.ewait else (1 if cls.elect else 0)) | (4 if cls.bwd16 else 0) | (8 if cls.fwd16 else 0)
-        from . import lib as _lib
-        if _lib.is_loaded() or sel != cls._applied:      # a library-wide selector (the library's own default is `elect`)
-            _lib.load().b200_set_attn_variant(sel)
-            cls._applied = sel
+            raise ValueError(f"B200_EXP: unknown switch(es) {sorted(unknown)}")
+        for n in cls.NAMES:
+            setattr(cls, n, n in names)
 
     @classmethod
     def active(cls):
@@ -70,9 +59,9 @@ Experimental.from_env()
 
 def _out_dense_residual(h16: Tensor, w: Tensor, bias: Tensor, x32: Tensor, drop, owns_residual: bool) -> Tensor:
     """pre = dropout(h16 @ w^T + bias) + x32, fp32 (BertSelfOutput / BertOutput before their LayerNorm).  `owns_residual`:
-    nobody else reads x32 afterwards, so the opt-in in-place variant may accumulate into it."""
+    nobody else reads x32 afterwards, so the in-place variant may accumulate into it."""
     if Experimental.resadd and owns_residual:
-        return ops.gemm_resadd(h16, w, x32, bias, drop=drop, stream_k=Experimental.streamk)
+        return ops.gemm_resadd(h16, w, x32, bias, drop=drop)
     pre = torch.empty(h16.shape[0], w.shape[0], dtype=F32, device=h16.device)
     ops.gemm(h16, w, pre, epilogue=ops.EPI_BIAS_RES32, bias=bias, aux=x32, drop=drop)
     return pre
@@ -205,8 +194,11 @@ def ffn_block_bwd(p: FfnWeights, g: FfnWeights, sv: FfnSaved, dy: Tensor, inv_sc
     d_pre, d_den = _ln_bwd(dy, dy2, sv, p.g, g.g, g.b, g.bf2, inv_scale)
     ops.gemm(d_den, sv.h, g.w2, a_layout=1, b_layout=1, epilogue=ops.EPI_ATOMIC, alpha=inv_scale, k_splits=ops.wgrad_splits(H, inter, M))
     dz = torch.empty(M, inter, dtype=F16, device=dev)
-    ops.gemm(d_den, p.w2, dz, b_layout=1, epilogue=ops.EPI_DGELU, aux=sv.dact)
-    ops.colsum(dz, g.bf1, inv_scale)
+    if Experimental.colsum:                      # bias gradient of the intermediate dense taken in the dgrad's epilogue
+        ops.gemm_dgelu_colsum(d_den, p.w2, sv.dact, dz, g.bf1, inv_scale)
+    else:
+        ops.gemm(d_den, p.w2, dz, b_layout=1, epilogue=ops.EPI_DGELU, aux=sv.dact)
+        ops.colsum(dz, g.bf1, inv_scale)
     ops.gemm(dz, sv.x16, g.w1, a_layout=1, b_layout=1, epilogue=ops.EPI_ATOMIC, alpha=inv_scale, k_splits=ops.wgrad_splits(inter, H, M))
     dx = torch.empty(M, H, dtype=F16, device=dev)
     ops.gemm(dz, p.w1, dx, b_layout=1, epilogue=ops.EPI_ADD, aux=d_pre)

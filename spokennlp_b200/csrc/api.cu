@@ -10,10 +10,8 @@
 #include "../../include/b200enc.h"
 #include "attn_bwd.cuh"
 #include "attn_bwd3.cuh"
-#include "attn_bwd4.cuh"
 #include "attn_fwd.cuh"
 #include "attn_fwd3.cuh"
-#include "attn_fwd4.cuh"
 #include "gemm.cuh"
 #include "gemm2.cuh"
 #include "optim.cuh"
@@ -139,26 +137,19 @@ int set_smem(K kern, int bytes) {
   return B200_OK;
 }
 
-template <int BN, int A_MN, int B_MN, int EPI, typename OutT>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, cudaStream_t s) {
-  auto kern = gemm_f16_kernel<BN, A_MN, B_MN, EPI, OutT>;
-  static int configured = set_smem(kern, GemmSmem<BN>::TOTAL);
-  if (configured != B200_OK) return configured;
-  const int m_tiles = (g.M + GEMM_BM - 1) / GEMM_BM, n_tiles = (g.N + BN - 1) / BN;
-  const int units = m_tiles * n_tiles * (g.k_splits > 0 ? g.k_splits : 1);
-  const int grid = units < sm_count() ? units : sm_count();
-  kern<<<grid, GEMM_THREADS, GemmSmem<BN>::TOTAL, s>>>(ta, tb, g);
-  return check_launch("gemm_f16_kernel");
-}
-
-std::atomic<int> g_gemm_impl{2};
-std::atomic<int> g_gemm_dbg{0};
-std::atomic<int> g_attn_variant{1};      // b200_set_attn_variant: bit 0 = warp-elected mbarrier arrivals, bit 1 (with bit 0) = warp-elected waits (opt-in)
 
 const DropCfg kNoDrop{nullptr, 0, 0, 1.0f};
 DropCfg make_drop(const uint32_t* seed, unsigned site, float p) {
   if (!seed || p <= 0.f) return kNoDrop;
   return DropCfg{seed, site, static_cast<uint32_t>(p * 32768.0f + 0.5f), 1.0f / (1.0f - p)};
+}
+// attention-probability sites (ptx.cuh: drop4_z): four 7-bit lane thresholds whose sum is round(512 p), packed one per byte
+DropCfg make_drop_attn(const uint32_t* seed, unsigned site, float p) {
+  if (!seed || p <= 0.f) return kNoDrop;
+  const uint32_t t = static_cast<uint32_t>(p * 512.0f + 0.5f);
+  uint32_t tt = 0;
+  for (uint32_t l = 0; l < 4; ++l) tt |= (t / 4 + (l < t % 4 ? 1u : 0u)) << (8 * l);
+  return DropCfg{seed, site, tt, 512.0f / (512.0f - static_cast<float>(t))};
 }
 
 template <int BN, int A_MN, int B_MN, int EPI, typename OutT>
@@ -178,10 +169,7 @@ int launch_gemm2(const Gemm2Maps& maps, const GemmArgs& g, cudaStream_t s) {
 
 extern "C" {
 
-void b200_set_gemm_impl(int impl) { g_gemm_impl.store(impl == 1 ? 1 : 2); }
-void b200_set_gemm_debug(int bits) { g_gemm_dbg.store(bits); }
 void b200_set_sm_limit(int sms) { g_sm_limit.store(sms); }
-void b200_set_attn_variant(int bits) { g_attn_variant.store(bits); }
 
 const char* b200_last_error(void) { return g_err.c_str(); }
 int b200_version(void) { return 100; }
@@ -194,7 +182,7 @@ long long b200_launch_count(void) { return g_launches.load(); }
 
 static int gemm_impl(const void* A, int lda, int a_layout, const void* B, int ldb, int b_layout, int M, int N, int K, int epilogue,
                      const float* bias, const void* aux, int ld_aux, void* out, int ld_out, int out_dtype, void* out2, int ld_out2,
-                     const float* alpha, int k_splits, DropCfg drop, void* stream);
+                     const float* alpha, int k_splits, DropCfg drop, void* stream, float* colsum = nullptr, const float* col_alpha = nullptr);
 
 int b200_gemm_f16(const void* A, int lda, int a_layout, const void* B, int ldb, int b_layout, int M, int N, int K, int epilogue,
                   const float* bias, const void* aux, int ld_aux, void* out, int ld_out, int out_dtype, void* out2, int ld_out2,
@@ -207,25 +195,28 @@ int b200_gemm_f16_drop(const void* A, int lda, const void* B, int ldb, int M, in
                        int ld_aux, void* out, int ld_out, int out_dtype, const uint32_t* seed, unsigned site, float p, void* stream) {
   if (epilogue != EPI_BIAS_RES32 && epilogue != EPI_BIAS_RES) return fail(B200_ERR_SHAPE, "gemm_drop: dropout is fused into the residual epilogues only");
   if (p < 0.f || p >= 1.f) return fail(B200_ERR_SHAPE, "gemm_drop: p must be in [0,1)");
-  if (g_gemm_impl.load() != 2 && seed && p > 0.f) return fail(B200_ERR_SHAPE, "gemm_drop: dropout needs the 2-CTA kernel");
   return gemm_impl(A, lda, 0, B, ldb, 0, M, N, K, epilogue, bias, aux, ld_aux, out, ld_out, out_dtype, nullptr, 0, nullptr, 1,
                    make_drop(seed, site, p), stream);
 }
 
 int b200_gemm_f16_resadd(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias, float* out, int ld_out,
-                         const uint32_t* seed, unsigned site, float p, int stream_k, void* stream) {
+                         const uint32_t* seed, unsigned site, float p, void* stream) {
   if (p < 0.f || p >= 1.f) return fail(B200_ERR_SHAPE, "gemm_resadd: p must be in [0,1)");
-  if (g_gemm_impl.load() != 2) return fail(B200_ERR_SHAPE, "gemm_resadd: needs the 2-CTA kernel");
-  // k_splits = -1 selects the stream-K schedule inside the kernel (GemmArgs)
-  return gemm_impl(A, lda, 0, B, ldb, 0, M, N, K, EPI_RESADD, bias, nullptr, 0, out, ld_out, B200_DT_F32, nullptr, 0, nullptr,
-                   stream_k ? -1 : 1, make_drop(seed, site, p), stream);
+  return gemm_impl(A, lda, 0, B, ldb, 0, M, N, K, EPI_RESADD, bias, nullptr, 0, out, ld_out, B200_DT_F32, nullptr, 0, nullptr, 1,
+                   make_drop(seed, site, p), stream);
+}
+
+int b200_gemm_f16_dgelu_colsum(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const void* dact, int ld_dact, void* out,
+                               int ld_out, float* colsum, const float* col_alpha, void* stream) {
+  if (!colsum) return fail(B200_ERR_SHAPE, "gemm_dgelu_colsum: colsum is required (use b200_gemm_f16 for the plain epilogue)");
+  return gemm_impl(A, lda, 0, B, ldb, 1, M, N, K, EPI_DGELU, nullptr, dact, ld_dact, out, ld_out, B200_DT_F16, nullptr, 0, nullptr, 1, kNoDrop,
+                   stream, colsum, col_alpha);
 }
 
 int b200_gemm_f16_dgrad_delta(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const void* ctx, int ld_ctx, void* out,
                               int ld_out, float* delta, int heads, int Sq, void* stream) {
   if (!delta || heads <= 0 || Sq <= 0 || N != heads * 64 || (M % Sq))
     return fail(B200_ERR_SHAPE, "gemm_dgrad_delta: need delta, N == heads*64 and M %% Sq == 0 (M=%d N=%d heads=%d Sq=%d)", M, N, heads, Sq);
-  if (g_gemm_impl.load() != 2) return fail(B200_ERR_SHAPE, "gemm_dgrad_delta: needs the 2-CTA kernel");
   // delta and Sq travel in the out2 / ld_out2 slots (GemmArgs)
   return gemm_impl(A, lda, 0, B, ldb, 1, M, N, K, EPI_STORE_DELTA, nullptr, ctx, ld_ctx, out, ld_out, B200_DT_F16, delta, Sq, nullptr, 1,
                    kNoDrop, stream);
@@ -233,7 +224,8 @@ int b200_gemm_f16_dgrad_delta(const void* A, int lda, const void* B, int ldb, in
 
 static int gemm_impl(const void* A, int lda, int a_layout, const void* B, int ldb, int b_layout, int M, int N, int K, int epilogue,
                      const float* bias, const void* aux, int ld_aux, void* out, int ld_out, int out_dtype, void* out2, int ld_out2,
-                     const float* alpha, int k_splits, DropCfg drop, void* stream) {
+                     const float* alpha, int k_splits, DropCfg drop, void* stream, float* colsum, const float* col_alpha) {
+  if (colsum && epilogue != EPI_DGELU) return fail(B200_ERR_SHAPE, "gemm: the fused column sum rides on the EPI_DGELU epilogue only");
   if (M <= 0 || N <= 0 || K <= 0) return fail(B200_ERR_SHAPE, "gemm: empty problem %dx%dx%d", M, N, K);
   if ((N % 4) || (ld_out % 4)) return fail(B200_ERR_SHAPE, "gemm: N and ld_out must be multiples of 4 (N=%d ld_out=%d)", N, ld_out);
   if (!A || !B || !out) return fail(B200_ERR_SHAPE, "gemm: null operand");
@@ -241,74 +233,43 @@ static int gemm_impl(const void* A, int lda, int a_layout, const void* B, int ld
                           epilogue == EPI_RESADD;
   const bool needs_aux = epilogue == EPI_BIAS_RES || epilogue == EPI_DGELU || epilogue == EPI_ADD || epilogue == EPI_BIAS_RES32 ||
                          epilogue == EPI_STORE_DELTA;
-  if ((epilogue == EPI_RESADD || epilogue == EPI_STORE_DELTA) && g_gemm_impl.load() != 2)
-    return fail(B200_ERR_SHAPE, "gemm: epilogue %d exists in the 2-CTA kernel only", epilogue);
   if (needs_bias && !bias) return fail(B200_ERR_SHAPE, "gemm: epilogue %d needs bias", epilogue);
   if (needs_aux && (!aux || (ld_aux % 4))) return fail(B200_ERR_SHAPE, "gemm: epilogue %d needs aux with ld%%4==0", epilogue);
   if (k_splits > 1 && epilogue != EPI_ATOMIC) return fail(B200_ERR_SHAPE, "gemm: split-K only with the atomic epilogue");
   constexpr int BN = 256;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int rc;
-  const bool v2_ok = !(epilogue == EPI_BIAS_RES && out_dtype == B200_DT_F32);
-  if (g_gemm_impl.load() == 2 && v2_ok) {
-    // 2-CTA path: per-CTA operand boxes are 128 rows (K-major) / 64x64 (MN-major); epilogue slabs are 32 rows x 128 B
-    Gemm2Maps mp;
-    rc = a_layout == 0 ? get_tmap(A, M, K, lda, 128, &mp.a) : get_tmap(A, K, M, lda, GEMM_BK, &mp.a);
-    if (rc) return rc;
-    rc = b_layout == 0 ? get_tmap(B, N, K, ldb, BN / 2, &mp.b) : get_tmap(B, K, N, ldb, GEMM_BK, &mp.b);
-    if (rc) return rc;
-    const bool o32 = out_dtype == B200_DT_F32;
-    if ((rc = get_tmap(out, M, N, ld_out, 32, &mp.out, o32))) return rc;
-    mp.aux = mp.out;
-    mp.out2 = mp.out;
-    if (epilogue == EPI_BIAS_GELU && out2 && (rc = get_tmap(out2, M, N, ld_out2, 32, &mp.out2))) return rc;
-    const bool has_out2 = out2 && epilogue != EPI_STORE_DELTA;       // (EPI_STORE_DELTA keeps its fp32 row statistic in the out2 slot)
-    if ((needs_aux || has_out2) && ((N % 8) || (needs_aux && (ld_aux * (epilogue == EPI_BIAS_RES32 ? 4 : 2)) % 16) || (has_out2 && (ld_out2 % 8)) ||
-                                (needs_aux && (reinterpret_cast<uintptr_t>(aux) & 15)) || (has_out2 && (reinterpret_cast<uintptr_t>(out2) & 15))))
-      return fail(B200_ERR_SHAPE, "gemm: aux / out2 need N %% 8 == 0 and 16-byte aligned rows");
-    GemmArgs g2{M, N, K, (epilogue == EPI_RESADD && k_splits == -1) ? -1 : (k_splits > 0 ? k_splits : 1), bias, static_cast<const __half*>(aux), ld_aux, out, ld_out,
-                static_cast<__half*>(out2), ld_out2, alpha, drop, g_gemm_dbg.load()};
-    switch (a_layout * 1000 + b_layout * 100 + epilogue * 10 + out_dtype) {
-      case 0 * 1000 + 0 * 100 + EPI_STORE * 10 + B200_DT_F16: return launch_gemm2<BN, 0, 0, EPI_STORE, __half>(mp, g2, s);
-      case 0 * 1000 + 0 * 100 + EPI_STORE * 10 + B200_DT_F32: return launch_gemm2<BN, 0, 0, EPI_STORE, float>(mp, g2, s);
-      case 0 * 1000 + 0 * 100 + EPI_BIAS * 10 + B200_DT_F16: return launch_gemm2<BN, 0, 0, EPI_BIAS, __half>(mp, g2, s);
-      case 0 * 1000 + 0 * 100 + EPI_BIAS * 10 + B200_DT_F32: return launch_gemm2<BN, 0, 0, EPI_BIAS, float>(mp, g2, s);
-      case 0 * 1000 + 0 * 100 + EPI_BIAS_GELU * 10 + B200_DT_F16: return launch_gemm2<BN, 0, 0, EPI_BIAS_GELU, __half>(mp, g2, s);
-      case 0 * 1000 + 0 * 100 + EPI_BIAS_RES * 10 + B200_DT_F16: return launch_gemm2<BN, 0, 0, EPI_BIAS_RES, __half>(mp, g2, s);
-      case 0 * 1000 + 0 * 100 + EPI_BIAS_RES32 * 10 + B200_DT_F32: return launch_gemm2<BN, 0, 0, EPI_BIAS_RES32, float>(mp, g2, s);
-      case 0 * 1000 + 1 * 100 + EPI_STORE * 10 + B200_DT_F16: return launch_gemm2<BN, 0, 1, EPI_STORE, __half>(mp, g2, s);
-      case 0 * 1000 + 1 * 100 + EPI_ADD * 10 + B200_DT_F16: return launch_gemm2<BN, 0, 1, EPI_ADD, __half>(mp, g2, s);
-      case 0 * 1000 + 1 * 100 + EPI_DGELU * 10 + B200_DT_F16: return launch_gemm2<BN, 0, 1, EPI_DGELU, __half>(mp, g2, s);
-      case 1 * 1000 + 1 * 100 + EPI_ATOMIC * 10 + B200_DT_F32: return launch_gemm2<BN, 1, 1, EPI_ATOMIC, float>(mp, g2, s);
-      case 0 * 1000 + 0 * 100 + EPI_RESADD * 10 + B200_DT_F32: return launch_gemm2<BN, 0, 0, EPI_RESADD, float>(mp, g2, s);
-      case 0 * 1000 + 1 * 100 + EPI_STORE_DELTA * 10 + B200_DT_F16: return launch_gemm2<BN, 0, 1, EPI_STORE_DELTA, __half>(mp, g2, s);
-      default:
-        return fail(B200_ERR_SHAPE, "gemm: unsupported (a_layout=%d, b_layout=%d, epilogue=%d, out_dtype=%d)", a_layout, b_layout,
-                    epilogue, out_dtype);
-    }
-  }
-  CUtensorMap ta, tb;
-  // K-major operand: matrix [MN, K], box 64(K) x tile rows.  MN-major operand: matrix [K, MN], box 64(MN) x 64(K rows).
-  rc = a_layout == 0 ? get_tmap(A, M, K, lda, GEMM_BM, &ta) : get_tmap(A, K, M, lda, GEMM_BK, &ta);
+  // 2-CTA path: per-CTA operand boxes are 128 rows (K-major) / 64x64 (MN-major); epilogue slabs are 32 rows x 128 B
+  Gemm2Maps mp;
+  rc = a_layout == 0 ? get_tmap(A, M, K, lda, 128, &mp.a) : get_tmap(A, K, M, lda, GEMM_BK, &mp.a);
   if (rc) return rc;
-  rc = b_layout == 0 ? get_tmap(B, N, K, ldb, BN, &tb) : get_tmap(B, K, N, ldb, GEMM_BK, &tb);
+  rc = b_layout == 0 ? get_tmap(B, N, K, ldb, BN / 2, &mp.b) : get_tmap(B, K, N, ldb, GEMM_BK, &mp.b);
   if (rc) return rc;
-  GemmArgs g{M, N, K, k_splits > 0 ? k_splits : 1, bias, static_cast<const __half*>(aux), ld_aux, out, ld_out,
-             static_cast<__half*>(out2), ld_out2, alpha, DropCfg{nullptr, 0, 0, 1.0f}, 0};
-  const int key = a_layout * 1000 + b_layout * 100 + epilogue * 10 + out_dtype;
-  switch (key) {
-    case 0 * 1000 + 0 * 100 + EPI_STORE * 10 + B200_DT_F16: return launch_gemm<BN, 0, 0, EPI_STORE, __half>(ta, tb, g, s);
-    case 0 * 1000 + 0 * 100 + EPI_STORE * 10 + B200_DT_F32: return launch_gemm<BN, 0, 0, EPI_STORE, float>(ta, tb, g, s);
-    case 0 * 1000 + 0 * 100 + EPI_BIAS * 10 + B200_DT_F16: return launch_gemm<BN, 0, 0, EPI_BIAS, __half>(ta, tb, g, s);
-    case 0 * 1000 + 0 * 100 + EPI_BIAS * 10 + B200_DT_F32: return launch_gemm<BN, 0, 0, EPI_BIAS, float>(ta, tb, g, s);
-    case 0 * 1000 + 0 * 100 + EPI_BIAS_GELU * 10 + B200_DT_F16: return launch_gemm<BN, 0, 0, EPI_BIAS_GELU, __half>(ta, tb, g, s);
-    case 0 * 1000 + 0 * 100 + EPI_BIAS_RES * 10 + B200_DT_F16: return launch_gemm<BN, 0, 0, EPI_BIAS_RES, __half>(ta, tb, g, s);
-    case 0 * 1000 + 0 * 100 + EPI_BIAS_RES * 10 + B200_DT_F32: return launch_gemm<BN, 0, 0, EPI_BIAS_RES, float>(ta, tb, g, s);
-    case 0 * 1000 + 0 * 100 + EPI_BIAS_RES32 * 10 + B200_DT_F32: return launch_gemm<BN, 0, 0, EPI_BIAS_RES32, float>(ta, tb, g, s);
-    case 0 * 1000 + 1 * 100 + EPI_STORE * 10 + B200_DT_F16: return launch_gemm<BN, 0, 1, EPI_STORE, __half>(ta, tb, g, s);
-    case 0 * 1000 + 1 * 100 + EPI_ADD * 10 + B200_DT_F16: return launch_gemm<BN, 0, 1, EPI_ADD, __half>(ta, tb, g, s);
-    case 0 * 1000 + 1 * 100 + EPI_DGELU * 10 + B200_DT_F16: return launch_gemm<BN, 0, 1, EPI_DGELU, __half>(ta, tb, g, s);
-    case 1 * 1000 + 1 * 100 + EPI_ATOMIC * 10 + B200_DT_F32: return launch_gemm<BN, 1, 1, EPI_ATOMIC, float>(ta, tb, g, s);
+  const bool o32 = out_dtype == B200_DT_F32;
+  if ((rc = get_tmap(out, M, N, ld_out, 32, &mp.out, o32))) return rc;
+  mp.aux = mp.out;
+  mp.out2 = mp.out;
+  if (epilogue == EPI_BIAS_GELU && out2 && (rc = get_tmap(out2, M, N, ld_out2, 32, &mp.out2))) return rc;
+  const bool has_out2 = out2 && epilogue != EPI_STORE_DELTA;       // (EPI_STORE_DELTA keeps its fp32 row statistic in the out2 slot)
+  if ((needs_aux || has_out2) && ((N % 8) || (needs_aux && (ld_aux * (epilogue == EPI_BIAS_RES32 ? 4 : 2)) % 16) || (has_out2 && (ld_out2 % 8)) ||
+                              (needs_aux && (reinterpret_cast<uintptr_t>(aux) & 15)) || (has_out2 && (reinterpret_cast<uintptr_t>(out2) & 15))))
+    return fail(B200_ERR_SHAPE, "gemm: aux / out2 need N %% 8 == 0 and 16-byte aligned rows");
+  GemmArgs g2{M, N, K, k_splits > 0 ? k_splits : 1, bias, static_cast<const __half*>(aux), ld_aux, out, ld_out,
+              static_cast<__half*>(out2), ld_out2, alpha, drop, colsum, col_alpha};
+  switch (a_layout * 1000 + b_layout * 100 + epilogue * 10 + out_dtype) {
+    case 0 * 1000 + 0 * 100 + EPI_STORE * 10 + B200_DT_F16: return launch_gemm2<BN, 0, 0, EPI_STORE, __half>(mp, g2, s);
+    case 0 * 1000 + 0 * 100 + EPI_STORE * 10 + B200_DT_F32: return launch_gemm2<BN, 0, 0, EPI_STORE, float>(mp, g2, s);
+    case 0 * 1000 + 0 * 100 + EPI_BIAS * 10 + B200_DT_F16: return launch_gemm2<BN, 0, 0, EPI_BIAS, __half>(mp, g2, s);
+    case 0 * 1000 + 0 * 100 + EPI_BIAS * 10 + B200_DT_F32: return launch_gemm2<BN, 0, 0, EPI_BIAS, float>(mp, g2, s);
+    case 0 * 1000 + 0 * 100 + EPI_BIAS_GELU * 10 + B200_DT_F16: return launch_gemm2<BN, 0, 0, EPI_BIAS_GELU, __half>(mp, g2, s);
+    case 0 * 1000 + 0 * 100 + EPI_BIAS_RES * 10 + B200_DT_F16: return launch_gemm2<BN, 0, 0, EPI_BIAS_RES, __half>(mp, g2, s);
+    case 0 * 1000 + 0 * 100 + EPI_BIAS_RES32 * 10 + B200_DT_F32: return launch_gemm2<BN, 0, 0, EPI_BIAS_RES32, float>(mp, g2, s);
+    case 0 * 1000 + 1 * 100 + EPI_STORE * 10 + B200_DT_F16: return launch_gemm2<BN, 0, 1, EPI_STORE, __half>(mp, g2, s);
+    case 0 * 1000 + 1 * 100 + EPI_ADD * 10 + B200_DT_F16: return launch_gemm2<BN, 0, 1, EPI_ADD, __half>(mp, g2, s);
+    case 0 * 1000 + 1 * 100 + EPI_DGELU * 10 + B200_DT_F16: return launch_gemm2<BN, 0, 1, EPI_DGELU, __half>(mp, g2, s);
+    case 1 * 1000 + 1 * 100 + EPI_ATOMIC * 10 + B200_DT_F32: return launch_gemm2<BN, 1, 1, EPI_ATOMIC, float>(mp, g2, s);
+    case 0 * 1000 + 0 * 100 + EPI_RESADD * 10 + B200_DT_F32: return launch_gemm2<BN, 0, 0, EPI_RESADD, float>(mp, g2, s);
+    case 0 * 1000 + 1 * 100 + EPI_STORE_DELTA * 10 + B200_DT_F16: return launch_gemm2<BN, 0, 1, EPI_STORE_DELTA, __half>(mp, g2, s);
     default:
       return fail(B200_ERR_SHAPE, "gemm: unsupported (a_layout=%d, b_layout=%d, epilogue=%d, out_dtype=%d)", a_layout, b_layout,
                   epilogue, out_dtype);
@@ -320,59 +281,26 @@ int b200_attn_fwd_drop(const void* q, int ldq, int q_col0, const void* kv, int l
                        unsigned site, float p, void* stream) {
   if (B <= 0 || heads <= 0 || Sq <= 0 || Sk <= 0) return fail(B200_ERR_SHAPE, "attn_fwd: empty problem");
   if ((q_col0 % 8) || (k_col0 % 8) || (v_col0 % 8) || (ld_out % 8)) return fail(B200_ERR_SHAPE, "attn_fwd: column offsets / ld_out must be multiples of 8");
-  const DropCfg drop = make_drop(seed, site, p);
-  CUtensorMap tq, tkv;
+  if (p < 0.f || p > 0.9f) return fail(B200_ERR_SHAPE, "attn_fwd: dropout probability %g outside [0, 0.9]", p);
+  const DropCfg drop = make_drop_attn(seed, site, p);
+  CUtensorMap tq, tkv, to;
   int rc = get_tmap(q, static_cast<uint64_t>(B) * Sq, ldq, ldq, ATT_BQ, &tq);
   if (rc) return rc;
   rc = get_tmap(kv, static_cast<uint64_t>(B) * Sk, ldkv, ldkv, ATT_BK, &tkv);
   if (rc) return rc;
-  static int c0 = set_smem(attn_fwd_kernel<false>, AttnFwdSmem::TOTAL);
-  static int c1 = set_smem(attn_fwd_kernel<true>, AttnFwdSmem::TOTAL);
-  if (c0 != B200_OK || c1 != B200_OK) return c0 ? c0 : c1;
-  AttnFwdArgs a{B, heads, Sq, Sk, q_col0, k_col0, v_col0, key_bias, kv_len, static_cast<__half*>(ctx), ld_out, lse2,
-                1.4426950408889634f / 8.0f, drop};
-  dim3 grid((Sq + 2 * ATT_BQ - 1) / (2 * ATT_BQ), heads, B);
-  if (!(g_gemm_dbg.load() & 0x100000)) {      // default: persistent kernel, one CTA per SM walking (batch, head, query-pair) items
-    CUtensorMap to;                             // context output fp16 [B*Sq, ld_out], 64 x 32 patches (one per softmax warp)
-    if ((rc = get_tmap(ctx, static_cast<uint64_t>(B) * Sq, ld_out, ld_out, 32, &to))) return rc;
-    static int e0 = set_smem(attn_fwd3_kernel<false>, AttnFwd3Smem::TOTAL);
-    static int e1 = set_smem(attn_fwd3_kernel<true>, AttnFwd3Smem::TOTAL);
-    if (e0 != B200_OK || e1 != B200_OK) return e0 ? e0 : e1;
-    const long long items = static_cast<long long>(grid.x) * grid.y * grid.z;
-    const int ctas = items < sm_count() ? static_cast<int>(items) : sm_count();
-    const int var = g_attn_variant.load();
-    if (var & 8) {                              // sixteen softmax warps, 64 keys per thread (attn_fwd4.cuh)
-      static int h0 = set_smem(attn_fwd4_kernel<false>, AttnFwd4Smem::TOTAL);
-      static int h1 = set_smem(attn_fwd4_kernel<true>, AttnFwd4Smem::TOTAL);
-      if (h0 != B200_OK || h1 != B200_OK) return h0 ? h0 : h1;
-      cudaStream_t st = static_cast<cudaStream_t>(stream);
-      if (drop.seed_base) attn_fwd4_kernel<true><<<ctas, ATTP4_THREADS, AttnFwd4Smem::TOTAL, st>>>(tq, tkv, to, a);
-      else attn_fwd4_kernel<false><<<ctas, ATTP4_THREADS, AttnFwd4Smem::TOTAL, st>>>(tq, tkv, to, a);
-      return check_launch("attn_fwd4_kernel");
-    }
-    if (var & 1) {                              // one mbarrier arrival (bit 1: and one waiting lane) per softmax warp
-      static int f0 = set_smem(attn_fwd3_kernel<false, 1>, AttnFwd3Smem::TOTAL);
-      static int f1 = set_smem(attn_fwd3_kernel<true, 1>, AttnFwd3Smem::TOTAL);
-      static int f2 = set_smem(attn_fwd3_kernel<false, 3>, AttnFwd3Smem::TOTAL);
-      static int f3 = set_smem(attn_fwd3_kernel<true, 3>, AttnFwd3Smem::TOTAL);
-      if (f0 != B200_OK || f1 != B200_OK || f2 != B200_OK || f3 != B200_OK) return f0 ? f0 : (f1 ? f1 : (f2 ? f2 : f3));
-      cudaStream_t st = static_cast<cudaStream_t>(stream);
-      if (var & 2) {
-        if (drop.seed_base) attn_fwd3_kernel<true, 3><<<ctas, ATTP_THREADS, AttnFwd3Smem::TOTAL, st>>>(tq, tkv, to, a);
-        else attn_fwd3_kernel<false, 3><<<ctas, ATTP_THREADS, AttnFwd3Smem::TOTAL, st>>>(tq, tkv, to, a);
-      } else {
-        if (drop.seed_base) attn_fwd3_kernel<true, 1><<<ctas, ATTP_THREADS, AttnFwd3Smem::TOTAL, st>>>(tq, tkv, to, a);
-        else attn_fwd3_kernel<false, 1><<<ctas, ATTP_THREADS, AttnFwd3Smem::TOTAL, st>>>(tq, tkv, to, a);
-      }
-      return check_launch("attn_fwd3_kernel<elect>");
-    }
-    if (drop.seed_base) attn_fwd3_kernel<true><<<ctas, ATTP_THREADS, AttnFwd3Smem::TOTAL, static_cast<cudaStream_t>(stream)>>>(tq, tkv, to, a);
-    else attn_fwd3_kernel<false><<<ctas, ATTP_THREADS, AttnFwd3Smem::TOTAL, static_cast<cudaStream_t>(stream)>>>(tq, tkv, to, a);
-    return check_launch("attn_fwd3_kernel");
-  }
-  if (drop.seed_base) attn_fwd_kernel<true><<<grid, ATT_THREADS, AttnFwdSmem::TOTAL, static_cast<cudaStream_t>(stream)>>>(tq, tkv, a);
-  else attn_fwd_kernel<false><<<grid, ATT_THREADS, AttnFwdSmem::TOTAL, static_cast<cudaStream_t>(stream)>>>(tq, tkv, a);
-  return check_launch("attn_fwd_kernel");
+  // context output fp16 [B*Sq, ld_out], 64 x 32 patches (one per softmax warp)
+  if ((rc = get_tmap(ctx, static_cast<uint64_t>(B) * Sq, ld_out, ld_out, 32, &to))) return rc;
+  static int e0 = set_smem(attn_fwd3_kernel<false>, AttnFwd3Smem::TOTAL);
+  static int e1 = set_smem(attn_fwd3_kernel<true>, AttnFwd3Smem::TOTAL);
+  if (e0 != B200_OK || e1 != B200_OK) return e0 ? e0 : e1;
+  AttnFwdArgs a{B, heads, Sq, Sk, q_col0, k_col0, v_col0, key_bias, kv_len, static_cast<__half*>(ctx), ld_out, lse2, kAttScaleLog2, drop};
+  // persistent kernel, one CTA per SM walking (batch, head, 256-query pair) items
+  const long long items = static_cast<long long>((Sq + 2 * ATT_BQ - 1) / (2 * ATT_BQ)) * heads * B;
+  const int ctas = items < sm_count() ? static_cast<int>(items) : sm_count();
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (drop.seed_base) attn_fwd3_kernel<true><<<ctas, ATTP_THREADS, AttnFwd3Smem::TOTAL, st>>>(tq, tkv, to, a);
+  else attn_fwd3_kernel<false><<<ctas, ATTP_THREADS, AttnFwd3Smem::TOTAL, st>>>(tq, tkv, to, a);
+  return check_launch("attn_fwd3_kernel");
 }
 
 int b200_attn_fwd(const void* q, int ldq, int q_col0, const void* kv, int ldkv, int k_col0, int v_col0, const float* key_bias,
@@ -477,7 +405,7 @@ static int layernorm_bwd_impl(const void* dy, const void* dy2, const void* x, in
                               void* stream) {
   if (int rc = check_row_shape("layernorm_bwd", rows, H)) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (!(g_gemm_dbg.load() & 0x200000)) {      // default: second-generation kernel (0x200000 keeps the first one for A/B runs)
+  {
     const int wps = (H / 8 + 31) / 32, tpr = 32 * wps, slots = LNB_THREADS / tpr;     // wps in 1..4 (H <= 1024)
     int grid2 = (rows + slots * LNB_R - 1) / (slots * LNB_R);
     if (grid2 > sm_count() * 2) grid2 = sm_count() * 2;
@@ -501,24 +429,6 @@ static int layernorm_bwd_impl(const void* dy, const void* dy2, const void* x, in
 #undef B200_LNB2
     return check_launch("ln_bwd2_kernel");
   }
-  int grid = (rows + ROW_WARPS - 1) / ROW_WARPS;
-  const int cap = sm_count() * 3;        // 3 resident CTAs per SM: one wave, and 3x fewer column-sum atomics than an oversubscribed grid
-  if (grid > cap) grid = cap;
-  const size_t smem = 3 * ROW_WARPS * H * sizeof(float);
-  if (x_dtype == B200_DT_F32) {
-    static int c = set_smem(ln_bwd_kernel<float>, 3 * ROW_WARPS * ROW_MAXV * 256 * 4);
-    if (c) return c;
-    ln_bwd_kernel<float><<<grid, ROW_WARPS * 32, smem, s>>>(static_cast<const __half*>(dy), static_cast<const __half*>(dy2), static_cast<const float*>(x),
-                                                           mean, rstd, gamma, static_cast<__half*>(dx), dgamma, dbeta, dbias, alpha, rows, H,
-                                                           static_cast<__half*>(dx_drop), drop);
-  } else {
-    static int c = set_smem(ln_bwd_kernel<__half>, 3 * ROW_WARPS * ROW_MAXV * 256 * 4);
-    if (c) return c;
-    ln_bwd_kernel<__half><<<grid, ROW_WARPS * 32, smem, s>>>(static_cast<const __half*>(dy), static_cast<const __half*>(dy2), static_cast<const __half*>(x),
-                                                            mean, rstd, gamma, static_cast<__half*>(dx), dgamma, dbeta, dbias, alpha, rows, H,
-                                                            static_cast<__half*>(dx_drop), drop);
-  }
-  return check_launch("ln_bwd_kernel");
 }
 
 int b200_embed_ln_fwd_drop(const int64_t* ids, const int64_t* tt, const int64_t* pos, const float* inputs_embeds, const float* word,
@@ -584,10 +494,11 @@ int b200_cls_head_fwd_drop(const void* h, const float* W, const float* b, float*
                            const uint32_t* seed, unsigned site, float p, void* stream) {
   if (int rc = check_row_shape("cls_head_fwd", rows, H)) return rc;
   const DropCfg drop = make_drop(seed, site, p);
-  const int grid = (rows + ROW_WARPS - 1) / ROW_WARPS;
+  int grid = (rows + CLS_WARPS * CLS_RPW - 1) / (CLS_WARPS * CLS_RPW);
+  if (grid > sm_count() * 8) grid = sm_count() * 8;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (C == 2) cls_head_fwd_kernel<2><<<grid, ROW_WARPS * 32, 0, s>>>(static_cast<const __half*>(h), W, b, logits, argmax, rows, H, drop);
-  else if (C == 3) cls_head_fwd_kernel<3><<<grid, ROW_WARPS * 32, 0, s>>>(static_cast<const __half*>(h), W, b, logits, argmax, rows, H, drop);
+  if (C == 2) cls_head_fwd_kernel<2, __half><<<grid, CLS_WARPS * 32, 0, s>>>(static_cast<const __half*>(h), W, b, logits, argmax, rows, H, drop);
+  else if (C == 3) cls_head_fwd_kernel<3, __half><<<grid, CLS_WARPS * 32, 0, s>>>(static_cast<const __half*>(h), W, b, logits, argmax, rows, H, drop);
   else return fail(B200_ERR_SHAPE, "cls_head_fwd: C=%d (2 or 3)", C);
   return check_launch("cls_head_fwd_kernel");
 }

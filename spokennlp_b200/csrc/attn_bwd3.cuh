@@ -45,15 +45,12 @@ struct AttnBwd3Smem {
   static constexpr int TOTAL = OFF_BAR + 256 + 1024;
 };
 
-// VAR (opt-in): bit 0 = one `s_free` / `ds_full` arrival per softmax warp instead of one per thread, bit 1 = the
-// softmax warps also wait with one lane per warp (see attn_fwd3.cuh).
-template <bool DROP, int VAR = 0>
+template <bool DROP>
 __global__ void __launch_bounds__(ATTB_THREADS, 1)
 attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                  const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmDQ,
                  const __grid_constant__ CUtensorMap tmDKV, const AttnBwdArgs a) {
   using S = AttnBwd3Smem;
-  constexpr bool ELECT = (VAR & 1) != 0, EWAIT = (VAR & 2) != 0;
   constexpr int NST = ATTB3_QDO_STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -63,8 +60,8 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* qdo_full = bars + 2;              // 3
   uint64_t* qdo_empty = qdo_full + NST;       // 3
   uint64_t* s_full = qdo_empty + NST;         // 2 (one per key half)
-  uint64_t* s_free = s_full + 2;              // 2 (128 arrivals each)
-  uint64_t* ds_full = s_free + 2;             // 1 (256 arrivals)
+  uint64_t* s_free = s_full + 2;              // 2 (one arrival per softmax warp of the half)
+  uint64_t* ds_full = s_free + 2;             // 1 (one arrival per softmax warp)
   uint64_t* grad_done = ds_full + 1;          // 1
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(grad_done + 1);
 
@@ -87,9 +84,9 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
     for (int g = 0; g < 2; ++g) {
       mbar_init(&s_full[g], 1);
-      mbar_init(&s_free[g], ELECT ? 4 : 128);
+      mbar_init(&s_free[g], 4);
     }
-    mbar_init(ds_full, ELECT ? 8 : 256);
+    mbar_init(ds_full, 8);
     mbar_init(grad_done, 1);
     fence_mbar_init();
   }
@@ -197,7 +194,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tc_fence_after();
         if (lane == 0) {
           const uint32_t qa = smem_u32(smem + S::OFF_QDO + st * 2 * S::T), doa = qa + S::T;
-          if (!(a.dbg & 0x20000)) {
+          {
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk)        // dV += P^T dO_i      (K = 16 query rows per step)
               umma_ss(tmem + 256, make_smem_desc(pa + kk * 2048, 16384, 1024), make_smem_desc(doa + kk * 2048, 8192, 1024), idesc_t,
@@ -229,22 +226,13 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t p_row = smem_u32(smem + S::OFF_P) + g * 16384 + r * 128;
     const uint32_t ds_row = smem_u32(smem + S::OFF_DS) + g * 16384 + r * 128;
     const uint32_t dseed = DROP ? drop_seed(a.drop) : 0u;
-    const uint32_t skp = static_cast<uint32_t>((a.Sk + 1) >> 1);
-    const float sc = a.scale_log2;
-    const uint32_t dtt = a.drop.thr15 * 0x00010001u;
+    const uint32_t skq = static_cast<uint32_t>((a.Sk + 3) >> 2);       // dropout quads per score row (ptx.cuh: drop4_z)
+    constexpr float sc = kAttScaleLog2;
+    const uint32_t dtt = a.drop.thr15;            // the four packed lane thresholds
     const uint32_t cs_bits = __float_as_uint(a.inv_sqrt_d * a.drop.scale);   // dP coefficient of a kept element
     uint8_t* dqs = smem + S::OFF_DQS + (warp - 2) * 4096;     // this warp's [32 q][32 d] fp32 staging patch
     const uint32_t dqs_row = smem_u32(dqs) + lane * 128;
     uint32_t ir = 0;                              // query blocks processed so far (barrier phases, dQ buffer)
-    auto warp_wait = [&](uint64_t* bar, uint32_t parity) {
-      if (EWAIT) {
-        if (lane == 0) mbar_wait(bar, parity);
-        __syncwarp();
-      } else {
-        mbar_wait(bar, parity);
-      }
-    };
-
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const Item it = decode(item);
       const int b = it.b, h = it.h, k0 = it.k0, kv_len = it.kv_len;
@@ -280,7 +268,6 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         uint32_t o[32];
         tmem_ld_x32(tmem + lane_addr + 384 + (ir_blk & 1) * 64 + g * 32, o);
         tmem_wait_ld();
-        if (a.dbg & 0x10000) return;
         if (lane == 0) tma_wait_group_read<0>();   // the previous reduction has finished reading the staging patch
         __syncwarp();
 #pragma unroll
@@ -304,7 +291,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           lse_n = (qn < a.Sq) ? a.lse2[stat_base + qn] : INFINITY;
           del_n = (qn < a.Sq) ? a.delta[stat_base + qn] : 0.f;
         }
-        warp_wait(&s_full[g], ir & 1);
+        mbar_wait(&s_full[g], ir & 1);
         tc_fence_after();
         uint32_t sv[64], dp[64];
         tmem_ld_x32(tmem + lane_addr + g * 64, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
@@ -313,12 +300,8 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tmem_ld_x32(tmem + lane_addr + 128 + g * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&dp[32]));
         tmem_wait_ld();
         tc_fence_before();
-        if (ELECT) {                              // the tensor core may overwrite S_g / dP_g with the next block now
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&s_free[g]);
-        } else {
-          mbar_arrive(&s_free[g]);
-        }
+        __syncwarp();                             // the tensor core may overwrite S_g / dP_g with the next block now
+        if (lane == 0) mbar_arrive(&s_free[g]);
         // masked keys: turn their scores into -inf (P = 0, dS = 0)
         if (it.general_bias) {
 #pragma unroll
@@ -334,34 +317,34 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           for (int c = 0; c < 64; ++c) sv[c] = (c < lim) ? sv[c] : 0xff800000u;
         }
         uint32_t pk[32], dk[32];                  // this thread's 64 P / dS values, packed fp16
-        // dropout: (pair + seed) * C1 of this row's first pair; consecutive pairs add C1 (ptx.cuh: drop_z)
-        const uint32_t dpre = DROP ? drop_premix(static_cast<uint32_t>(stat_base + min(q, a.Sq - 1)) * skp + (static_cast<uint32_t>(kg0) >> 1), dseed) : 0u;
-        if (a.dbg & 0x40000) {
+        // dropout: (quad + seed) * C1 of this row's first quad; consecutive quads add C1 (ptx.cuh: drop4_z)
+        const uint32_t dpre = DROP ? drop_premix(static_cast<uint32_t>(stat_base + min(q, a.Sq - 1)) * skq + (static_cast<uint32_t>(kg0) >> 2), dseed) : 0u;
+        const uint64_t nl2 = pack2(neg_lse, neg_lse), sc2 = pack2(sc, sc), ndc2 = pack2(ndc, ndc);
+        const uint64_t cc2 = pack2(a.inv_sqrt_d, a.inv_sqrt_d);
 #pragma unroll
-          for (int e = 0; e < 32; ++e) pk[e] = dk[e] = sv[2 * e] ^ dp[2 * e + 1];
-        } else {
+        for (int qd4 = 0; qd4 < 16; ++qd4) {      // four keys (one dropout quad) per step, two packed fp32 pairs
+          const uint32_t z = DROP ? drop4_z(dpre + static_cast<uint32_t>(qd4) * kDropC1, dtt) : 0u;
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const float p0 = fast_exp2(fmaf(__uint_as_float(sv[2 * e]), sc, neg_lse));
-            const float p1 = fast_exp2(fmaf(__uint_as_float(sv[2 * e + 1]), sc, neg_lse));
-            const float g0 = __uint_as_float(dp[2 * e]), g1 = __uint_as_float(dp[2 * e + 1]);
-            float c0 = a.inv_sqrt_d, c1 = a.inv_sqrt_d;
+          for (int hf = 0; hf < 2; ++hf) {
+            const int e = qd4 * 2 + hf;
+            float x0, x1;
+            unpack2(fma2(pack2u(sv[2 * e], sv[2 * e + 1]), sc2, nl2), x0, x1);
+            const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
             const __half2 hp = __floats2half2_rn(p0, p1);
             pk[e] = *reinterpret_cast<const uint32_t*>(&hp);
+            uint64_t c2 = cc2;
             if (DROP) {       // P o mask feeds dV (its 1/(1-p) is applied to dV at the end); dP flows back through mask/(1-p)
-              const uint32_t z = drop_z(dpre + static_cast<uint32_t>(e) * kDropC1, dtt);
-              pk[e] &= drop_keep_h2(z);
-              c0 = __uint_as_float(drop_keep_lo(z) & cs_bits);
-              c1 = __uint_as_float(drop_keep_hi(z) & cs_bits);
+              pk[e] &= hf ? drop4_keep_h2_hi(z) : drop4_keep_h2_lo(z);
+              c2 = pack2u((hf ? drop4_keep<2>(z) : drop4_keep<0>(z)) & cs_bits, (hf ? drop4_keep<3>(z) : drop4_keep<1>(z)) & cs_bits);
             }
-            const float d0 = p0 * fmaf(g0, c0, ndc);                    // P o (dP_eff - delta) / sqrt(d)
-            const float d1 = p1 * fmaf(g1, c1, ndc);
+            float d0, d1;                                                 // P o (dP_eff - delta) / sqrt(d), two per instruction
+            unpack2(mul2(pack2(p0, p1), fma2(pack2u(dp[2 * e], dp[2 * e + 1]), c2, ndc2)), d0, d1);
             const __half2 hd = __floats2half2_rn(d0, d1);
             dk[e] = *reinterpret_cast<const uint32_t*>(&hd);
           }
         }
         if (i > 0) {                              // gradient MMAs of the previous block are done: its dQ is complete, P / dS are free
-          warp_wait(grad_done, (ir - 1) & 1);
+          mbar_wait(grad_done, (ir - 1) & 1);
           tc_fence_after();
         } else if (t == 0) {
           tma_wait_group_read<0>();               // the previous item's dK / dV stores have read the staging patches (see the epilogue)
@@ -374,17 +357,13 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         fence_proxy_async_smem();
         tc_fence_before();
-        if (ELECT) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(ds_full);
-        } else {
-          mbar_arrive(ds_full);
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ds_full);
         // dQ of the previous block sits in the other TMEM buffer: reduce it into HBM off the critical path
         if (i > 0) drain_dq(ir - 1, i - 1);
       }
       // ------------------------------------------------------------------ item epilogue
-      warp_wait(grad_done, (ir - 1) & 1);
+      mbar_wait(grad_done, (ir - 1) & 1);
       tc_fence_after();
       drain_dq(ir - 1, nq - 1);
       // dV, dK: TMEM lane == key row; this thread owns 32 of the 64 d columns.  A full key block leaves as two TMA stores from

@@ -43,15 +43,11 @@ struct AttnFwd3Smem {
   static constexpr int TOTAL = OFF_BAR + 256 + 1024;
 };
 
-// VAR (opt-in).  Bit 0 (ELECT): the softmax warps signal `s_free` / `p_full` with ONE arrival per warp (after a
-// warp-level sync) instead of one per thread — 4 arrivals per barrier phase instead of 128 same-address mbarrier
-// operations.  Bit 1 (EWAIT): they also WAIT with one lane per warp (lane 0 polls, __syncwarp() releases the others).
-template <bool DROP, int VAR = 0>
+template <bool DROP>
 __global__ void __launch_bounds__(ATTP_THREADS, 1)
 attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                  const __grid_constant__ CUtensorMap tmO, const AttnFwdArgs a) {
   using S = AttnFwd3Smem;
-  constexpr bool ELECT = (VAR & 1) != 0, EWAIT = (VAR & 2) != 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
@@ -62,8 +58,8 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* v_full = bars + 8;         // 2
   uint64_t* v_empty = bars + 10;       // 2 (one arrival per MMA warp)
   uint64_t* s_full = bars + 12;        // 2 (per tile)
-  uint64_t* s_free = bars + 14;        // 2 (128 arrivals)
-  uint64_t* p_full = bars + 16;        // 2 (128 arrivals)
+  uint64_t* s_free = bars + 14;        // 2 (one arrival per softmax warp)
+  uint64_t* p_full = bars + 16;        // 2 (one arrival per softmax warp)
   uint64_t* o_full = bars + 18;        // 2
   uint64_t* b_go = bars + 20;          // 1
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
@@ -84,8 +80,8 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 2);
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_free[i], ELECT ? 4 : 128);
-      mbar_init(&p_full[i], ELECT ? 4 : 128);
+      mbar_init(&s_free[i], 4);
+      mbar_init(&p_full[i], 4);
       mbar_init(&o_full[i], 1);
     }
     mbar_init(b_go, 1);
@@ -219,26 +215,18 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t bias_s = smem_u32(smem + S::OFF_BIAS) + x * 2 * ATT_BK * 4;
     const uint32_t p_row = smem_u32(smem + S::OFF_P + x * S::P_BYTES) + r * 128;
     const float NEG_INF = -INFINITY;
-    const float sc = a.scale_log2;
-    const float inv_sc = 1.0f / sc;
+    constexpr float sc = kAttScaleLog2;           // log2(e) / sqrt(64): an immediate operand of the packed FMA below
+    constexpr float inv_sc = 1.0f / kAttScaleLog2;
     const uint32_t dseed = DROP ? drop_seed(a.drop) : 0u;
     uint32_t t = 0;                               // blocks this tile has processed (barrier phases)
-    auto warp_wait = [&](uint64_t* bar, uint32_t parity) {
-      if (EWAIT) {
-        if (lane == 0) mbar_wait(bar, parity);
-        __syncwarp();
-      } else {
-        mbar_wait(bar, parity);
-      }
-    };
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const Item it = decode(item);
       if (x == 1 && !it.tileB) continue;
       const int b = it.b, h = it.h, kv_len = it.kv_len, n_blocks = it.n_blocks;
       const int qrow = it.q0 + x * ATT_BQ + r;
-      // dropout: pair index of (row, key) = rowbase + key / 2; (pair + seed) * C1 is walked by adding multiples of C1
-      const uint32_t dpre = DROP ? drop_premix(static_cast<uint32_t>(((static_cast<size_t>(b) * a.heads + h) * a.Sq + min(qrow, a.Sq - 1)) * ((a.Sk + 1) >> 1)), dseed) : 0u;
-      const uint32_t dtt = a.drop.thr15 * 0x00010001u;
+      // dropout: quad index of (row, key) = rowbase + key / 4; (quad + seed) * C1 is walked by adding multiples of C1 (ptx.cuh: drop4_z)
+      const uint32_t dpre = DROP ? drop_premix(static_cast<uint32_t>(((static_cast<size_t>(b) * a.heads + h) * a.Sq + min(qrow, a.Sq - 1)) * ((a.Sk + 3) >> 2)), dseed) : 0u;
+      const uint32_t dtt = a.drop.thr15;          // the four packed lane thresholds
       float m = NEG_INF, l = 0.f;
       if (lane == 0) tma_wait_group_read<0>();    // the previous item's context store has read this warp's staging rows
       __syncwarp();
@@ -252,7 +240,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           sts_f32(bj + tg * 4, bv);
           asm volatile("bar.sync %0, 128;" ::"r"(1 + x) : "memory");
         }
-        warp_wait(&s_full[x], t & 1);
+        mbar_wait(&s_full[x], t & 1);
         tc_fence_after();
         uint32_t v[128];
         tmem_ld_x32(tmem + lane_addr + x * 128, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
@@ -261,12 +249,8 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tmem_ld_x32(tmem + lane_addr + x * 128 + 96, *reinterpret_cast<uint32_t(*)[32]>(&v[96]));
         tmem_wait_ld();
         tc_fence_before();
-        if (ELECT) {                              // the tensor core may overwrite S_x with the next block now
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&s_free[x]);
-        } else {
-          mbar_arrive(&s_free[x]);
-        }
+        __syncwarp();                             // the tensor core may overwrite S_x with the next block now:
+        if (lane == 0) mbar_arrive(&s_free[x]);   // one arrival per warp (128 same-address arrivals cost 9 us per backward, r02a)
         if (x == 0 && t == 0 && tg == 0) mbar_arrive(b_go);
         // ---- masked keys (only blocks that have any)
         if (it.general_bias) {
@@ -299,7 +283,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (m_use == NEG_INF) m_use = 0.f;
         const float alpha = rescale ? fast_exp2(m - m_use) : 1.0f;     // m == -inf -> 0
         if (j > 0) {                              // P.V of block j-1 finished: P smem is free, O may be rescaled
-          warp_wait(&o_full[x], (t - 1) & 1);
+          mbar_wait(&o_full[x], (t - 1) & 1);
           tc_fence_after();
           if (rescale) {
 #pragma unroll
@@ -307,47 +291,55 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
               uint32_t o[16];
               tmem_ld_x16(tmem + lane_addr + 256 + x * 64 + c * 16, o);
               tmem_wait_ld();
+              const uint64_t al2 = pack2(alpha, alpha);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              for (int i = 0; i < 16; i += 2) {
+                float r0, r1;
+                unpack2(mul2(pack2u(o[i], o[i + 1]), al2), r0, r1);
+                o[i] = __float_as_uint(r0);
+                o[i + 1] = __float_as_uint(r1);
+              }
               tmem_st_x16(tmem + lane_addr + 256 + x * 64 + c * 16, o);
             }
             tmem_wait_st();
           }
         }
         // ---- p = exp2(s * scale - m_use), row sum, fp16 P into the swizzled smem tile (16 chunks of 8 keys)
-        const float neg_m = -m_use;
-        const uint32_t dpre_j = dpre + static_cast<uint32_t>(j * (ATT_BK / 2)) * kDropC1;
-        float rs0 = 0.f, rs1 = 0.f;
+        const uint64_t nm2 = pack2(-m_use, -m_use), sc2 = pack2(sc, sc);
+        const uint32_t dpre_j = dpre + static_cast<uint32_t>(j * (ATT_BK / 4)) * kDropC1;
+        uint64_t rs2 = pack2(0.f, 0.f);
 #pragma unroll
         for (int ch = 0; ch < 16; ++ch) {
-          uint32_t pk[4];
+          uint32_t pk[4], z[2];
+          if (DROP) {                               // this chunk's 8 keys = quads 2 ch, 2 ch + 1 of the block
+            z[0] = drop4_z(dpre_j + static_cast<uint32_t>(2 * ch) * kDropC1, dtt);
+            z[1] = drop4_z(dpre_j + static_cast<uint32_t>(2 * ch + 1) * kDropC1, dtt);
+          }
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int i = ch * 8 + 2 * e;
-            float p0 = fast_exp2(fmaf(__uint_as_float(v[i]), sc, neg_m));
-            float p1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), sc, neg_m));
-            rs0 += p0;                              // the row sum (softmax denominator) is taken before dropout
-            rs1 += p1;
+            float x0, x1;
+            unpack2(fma2(pack2u(v[i], v[i + 1]), sc2, nm2), x0, x1);        // two exponents per instruction
+            const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+            rs2 = add2(rs2, pack2(p0, p1));         // the row sum (softmax denominator) is taken before dropout
             const __half2 hp = __floats2half2_rn(p0, p1);
             pk[e] = *reinterpret_cast<const uint32_t*>(&hp);
             if (DROP)                               // zero the dropped lanes of the packed pair; 1/(1-p) is applied to O at the end
-              pk[e] &= drop_keep_h2(drop_z(dpre_j + static_cast<uint32_t>(i >> 1) * kDropC1, dtt));
+              pk[e] &= (e & 1) ? drop4_keep_h2_hi(z[e >> 1]) : drop4_keep_h2_lo(z[e >> 1]);
           }
           sts128(p_row + (ch >> 3) * 16384 + (((ch & 7) ^ (r & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
         }
+        float rs0, rs1;
+        unpack2(rs2, rs0, rs1);
         l = fmaf(l, alpha, rs0 + rs1);
         m = (m_use == 0.f && m_new == NEG_INF) ? NEG_INF : m_use;
         fence_proxy_async_smem();
         tc_fence_before();
-        if (ELECT) {                              // every lane has fenced its own P rows; one lane publishes the warp's 32 rows
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&p_full[x]);
-        } else {
-          mbar_arrive(&p_full[x]);
-        }
+        __syncwarp();                             // every lane has fenced its own P rows; one lane publishes the warp's 32 rows
+        if (lane == 0) mbar_arrive(&p_full[x]);
       }
       // ---------------------------------------------------------------- finalise: O / l -> ctx, LSE
-      warp_wait(&o_full[x], (t - 1) & 1);
+      mbar_wait(&o_full[x], (t - 1) & 1);
       tc_fence_after();
       const float inv_l = (l > 0.f ? 1.0f / l : 0.f) * (DROP ? a.drop.scale : 1.0f);
       uint32_t o[2][32];

@@ -133,14 +133,7 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
   const int splits = g.k_splits > 0 ? g.k_splits : 1;
   const int kb_per_split = (k_blocks + splits - 1) / splits;
   const int units = m_tiles * n_tiles * splits;
-  // Stream-K (EPI_RESADD with g.k_splits == -1): the K blocks of all tiles form one tile-major list that is cut into equal
-  // contiguous shares, one per CTA pair; a pair therefore walks (tail of a tile, whole tiles, head of a tile) segments and
-  // every segment is reduce-added into the output, so no tile waits for a straggler round (192 tiles on 74 pairs).
-  const bool sk = RESADD && g.k_splits == -1;
-  const long long sk_total = static_cast<long long>(m_tiles) * n_tiles * k_blocks;
-  const int sk_hi = sk ? static_cast<int>(sk_total * (pair + 1) / n_pairs) : 0;
-  const int u_begin = sk ? static_cast<int>(sk_total * pair / n_pairs) : pair;
-  const int u_end = sk ? sk_hi : units;
+  const int u_begin = pair, u_end = units;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.a);
@@ -166,14 +159,6 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
   const uint32_t tmem_base = *tmem_slot;
 
   auto decode = [&](int u, int& mt, int& nt, int& kb0, int& kb1) {
-    if (sk) {                                             // u = position in the global K-block list
-      const int t = u / k_blocks;
-      nt = t % n_tiles;
-      mt = t / n_tiles;
-      kb0 = u - t * k_blocks;
-      kb1 = min(k_blocks, kb0 + (sk_hi - u));
-      return;
-    }
     const int sp = u % splits;
     const int t = u / splits;
     nt = t % n_tiles;
@@ -181,7 +166,7 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
     kb0 = sp * kb_per_split;
     kb1 = min(k_blocks, kb0 + kb_per_split);
   };
-  auto next_unit = [&](int u, int kb0, int kb1) { return sk ? u + (kb1 - kb0) : u + n_pairs; };
+  auto next_unit = [&](int u, int, int) { return u + n_pairs; };
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
@@ -195,27 +180,21 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           const uint32_t full0 = mapa_u32(smem_u32(&full_bar[stage]), 0);   // the leader's barrier collects both CTAs' bytes
-          const bool ld_a = !(g.dbg & 1) || kb == kb0, ld_b = !(g.dbg & 2) || kb == kb0;
-          if (leader) mbar_expect_tx(&full_bar[stage], 2 * ((ld_a ? S::A_BYTES : 0) + (ld_b ? S::B_BYTES : 0)));
-          if (!ld_a && !ld_b && !leader) { /* nothing to fetch */ }
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * (S::A_BYTES + S::B_BYTES));
           uint8_t* a_dst = sA + stage * S::A_BYTES;
           uint8_t* b_dst = sB + stage * S::B_BYTES;
           const int k0 = kb * GEMM_BK;
-          if (ld_a) {
-            if (A_MN) {
+          if (A_MN) {
 #pragma unroll
-              for (int j = 0; j < 2; ++j) tma_load_2d_cg2(a_dst + j * 8192, &maps.a, full0, m0 + 64 * j, k0);
-            } else {
-              tma_load_2d_cg2(a_dst, &maps.a, full0, k0, m0);
-            }
+            for (int j = 0; j < 2; ++j) tma_load_2d_cg2(a_dst + j * 8192, &maps.a, full0, m0 + 64 * j, k0);
+          } else {
+            tma_load_2d_cg2(a_dst, &maps.a, full0, k0, m0);
           }
-          if (ld_b) {
-            if (B_MN) {
+          if (B_MN) {
 #pragma unroll
-              for (int j = 0; j < BN / 128; ++j) tma_load_2d_cg2(b_dst + j * 8192, &maps.b, full0, n0 + 64 * j, k0);
-            } else {
-              tma_load_2d_cg2(b_dst, &maps.b, full0, k0, n0);
-            }
+            for (int j = 0; j < BN / 128; ++j) tma_load_2d_cg2(b_dst + j * 8192, &maps.b, full0, n0 + 64 * j, k0);
+          } else {
+            tma_load_2d_cg2(b_dst, &maps.b, full0, k0, n0);
           }
           if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
         }
@@ -243,7 +222,7 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
             for (int kk = 0; kk < GEMM_BK / 16; ++kk) {
               const uint64_t da = A_MN ? make_smem_desc(a_addr + kk * 2048, 8192, 1024) : make_smem_desc(a_addr + kk * 32, 0, 1024);
               const uint64_t db = B_MN ? make_smem_desc(b_addr + kk * 2048, 8192, 1024) : make_smem_desc(b_addr + kk * 32, 0, 1024);
-              if (!(g.dbg & 4)) umma2_ss(d_tmem, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+              umma2_ss(d_tmem, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
             }
             umma2_commit_mc(&empty_bar[stage]);
             if (kb == kb1 - 1) umma2_commit_mc(&tfull_bar[acc]);
@@ -305,7 +284,6 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
       tile_origin(u, row0, col0, has_data);
       kb0 = seg_kb0;
       kb1 = seg_kb1;
-      const bool add_bias = !RESADD || kb0 == 0;          // a tile finished by several pairs gets its bias exactly once
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
@@ -336,7 +314,7 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
         float f[CW];
 #pragma unroll
         for (int i = 0; i < CW; ++i) f[i] = RESADD ? __uint_as_float(v[i]) : __uint_as_float(v[i]) * alpha;   // (the forward never scales)
-        if (HAS_BIAS && add_bias) {
+        if (HAS_BIAS) {
 #pragma unroll
           for (int i = 0; i < CW / 4; ++i) {
             float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -404,7 +382,7 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            if (has_data && !(g.dbg & 8)) {
+            if (has_data) {
               tma_store_2d(&maps.out, out_s, gc0, row0);
               if (g.out2) tma_store_2d(&maps.out2, out_s + S::SLAB, gc0, row0);
             }
@@ -445,11 +423,30 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          if (has_data && !(g.dbg & 8)) {
+          if (has_data) {
             if (EPI == EPI_ATOMIC || RESADD) tma_reduce_add_2d(&maps.out, os_ptr, gc0, row0);
             else tma_store_2d(&maps.out, os_ptr, gc0, row0);
           }
           tma_commit_group();
+        }
+        if (EPI == EPI_DGELU && g.colsum != nullptr && has_data) {
+          // Fused bias gradient (replaces a separate column-sum pass that re-read the whole [M, N] tensor from HBM): the warp's
+          // 32 rows x 64 columns sit in the slab as fp16; lane l owns columns gc0 + 2l, 2l + 1 = 32-bit word l of every row
+          // (word w of row r lives in chunk (w >> 2) ^ (r & 7): all lanes read one row per step, distinct banks).  Rows past M
+          // hold exact zeros (their A rows and aux were zero-filled).
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) {
+            uint32_t wv;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wv) : "r"(os + rr * 128 + ((((lane >> 2) ^ (rr & 7)) << 4) | ((lane & 3) << 2))) : "memory");
+            const float2 x = __half22float2(*reinterpret_cast<const __half2*>(&wv));
+            s0 += x.x;
+            s1 += x.y;
+          }
+          const float ca = g.col_alpha ? __ldg(g.col_alpha) : 1.0f;
+          const int cc = gc0 + 2 * lane;
+          if (cc < g.N) atomicAdd(g.colsum + cc, s0 * ca);
+          if (cc + 1 < g.N) atomicAdd(g.colsum + cc + 1, s1 * ca);
         }
         ++out_uses;
       }

@@ -280,6 +280,61 @@ __device__ __forceinline__ uint32_t drop_keep_hi(uint32_t z) {
   return m;
 }
 
+// Attention-probability sites draw ONE hash per FOUR consecutive keys (7-bit lanes, one per byte): the persistent attention
+// kernels are instruction-issue bound (profiles/r02a: 0.46 warp instructions per cycle per scheduler, ~0.5 is what 3-register
+// operand instructions sustain), and the pair-wise mask above cost 8.5 instructions per pair — more than the softmax itself.
+//   quad index = ((b * heads + h) * Sq + q) * ceil(Sk / 4) + key / 4;   lane l = key & 3 -> bits [8l, 8l + 7) of the hash;
+//   element kept iff lane >= thr[l], the four thresholds dithered so that their sum is round(512 p) (p = 0.1: 13,13,13,12 ->
+//   an effective drop rate of 51/512 = 0.0996); kept elements are scaled by 512 / (512 - sum) — unbiased for that rate.
+// DropCfg carries the packed thresholds in `thr15` and that scale in `scale` for these sites (api.cu: make_drop_attn).
+__device__ __forceinline__ uint32_t drop4_z(uint32_t premixed, uint32_t tt) {   // bit 7 of byte l of the result = "keep lane l"
+  uint32_t h = premixed;
+  h ^= h >> 15;
+  h *= kDropC2;
+  return ((h ^ (h >> 13)) | 0x80808080u) - tt;       // every byte is >= 0x80 before the subtraction: no borrow crosses the lanes
+}
+template <uint32_t SEL>
+__device__ __forceinline__ uint32_t prmt_sel(uint32_t z) {                      // byte permute with sign replication (selector nibble | 8)
+  uint32_t m;
+  asm("prmt.b32 %0, %1, %1, %2;" : "=r"(m) : "r"(z), "n"(SEL));
+  return m;
+}
+// 0xFFFF per kept half of the packed pair (lanes 0,1 / lanes 2,3); 0xFFFFFFFF if lane l is kept
+__device__ __forceinline__ uint32_t drop4_keep_h2_lo(uint32_t z) { return prmt_sel<0x9988>(z); }
+__device__ __forceinline__ uint32_t drop4_keep_h2_hi(uint32_t z) { return prmt_sel<0xBBAA>(z); }
+template <int L>
+__device__ __forceinline__ uint32_t drop4_keep(uint32_t z) { return prmt_sel<0x8888u + 0x1111u * L>(z); }
+
+// ----------------------------------------------------------------------------- packed fp32 pairs (FFMA2 / FADD2 / FMUL2)
+// sm_100 executes two fp32 operations per instruction on an aligned register pair: half the issue slots for the softmax /
+// epilogue arithmetic of kernels that are issue-bound.  pack2 / unpack2 are register renames when the pair is adjacent.
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t pack2u(uint32_t a, uint32_t b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 // ----------------------------------------------------------------------------- small math helpers
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

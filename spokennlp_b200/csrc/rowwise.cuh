@@ -123,104 +123,10 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) ln_fwd_kernel(const InT* __res
 // dgamma += alpha * sum_rows dy * xhat;  dbeta += alpha * sum_rows dy;  dbias += alpha * sum_rows dx (optional: the
 // bias of the dense layer that produced the pre-LN sum).  `dy2` (optional) is a second upstream gradient added to dy
 // (the residual branch that by-passes the next block).
-template <typename InT>
-__global__ void __launch_bounds__(ROW_WARPS * 32, 3) ln_bwd_kernel(const __half* __restrict__ dy, const __half* __restrict__ dy2,
-                                                                    const InT* __restrict__ x, const float* __restrict__ mean_in,
-                                                                    const float* __restrict__ rstd_in, const float* __restrict__ gamma,
-                                                                    __half* __restrict__ dx, float* __restrict__ dgamma,
-                                                                    float* __restrict__ dbeta, float* __restrict__ dbias,
-                                                                    const float* __restrict__ alpha_ptr, int rows, int H,
-                                                                    __half* __restrict__ dx_drop, DropCfg drop) {
-  // dx_drop (optional): dx times the forward's dropout mask of the dense output that fed this LayerNorm — the gradient the
-  // dense layer's dgrad / wgrad / bias-grad consume, while the un-masked dx continues along the residual branch.
-  extern __shared__ float red[];   // [3][ROW_WARPS][H]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nv = lane_vecs(H, lane);
-  const bool dropping = dx_drop != nullptr && drop.seed_base != nullptr;
-  const uint32_t dseed = dropping ? drop_seed(drop) : 0u;
-  Vec8 ag[ROW_MAXV], ab[ROW_MAXV], ad[ROW_MAXV];
-#pragma unroll
-  for (int i = 0; i < ROW_MAXV; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) ag[i].v[j] = ab[i].v[j] = ad[i].v[j] = 0.f;
 
-  for (int row = blockIdx.x * ROW_WARPS + warp; row < rows; row += gridDim.x * ROW_WARPS) {
-    const float mean = mean_in[row], rstd = rstd_in[row];
-    Vec8 xh[ROW_MAXV], d[ROW_MAXV];          // gamma is re-read per row (L1-resident) to keep the register footprint at 3 CTAs/SM
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < ROW_MAXV; ++i)
-      if (i < nv) {
-        const int c = (i * 32 + lane) * 8;
-        const size_t off = static_cast<size_t>(row) * H + c;
-        const Vec8 xv = load8(x + off);
-        d[i] = load8(dy + off);
-        if (dy2) {
-          const Vec8 d2 = load8(dy2 + off);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) d[i].v[j] += d2.v[j];
-        }
-        const Vec8 gm = load8(gamma + c);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          xh[i].v[j] = (xv.v[j] - mean) * rstd;
-          const float g = d[i].v[j] * gm.v[j];
-          s1 += g;
-          s2 = fmaf(g, xh[i].v[j], s2);
-          ag[i].v[j] = fmaf(d[i].v[j], xh[i].v[j], ag[i].v[j]);
-          ab[i].v[j] += d[i].v[j];
-        }
-      }
-    s1 = warp_sum(s1) / H;
-    s2 = warp_sum(s2) / H;
-#pragma unroll
-    for (int i = 0; i < ROW_MAXV; ++i)
-      if (i < nv) {
-        const int c = (i * 32 + lane) * 8;
-        const Vec8 gm = load8(gamma + c);
-        Vec8 o;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o.v[j] = rstd * (d[i].v[j] * gm.v[j] - s1 - xh[i].v[j] * s2);
-        store8(dx + static_cast<size_t>(row) * H + c, o);
-        if (dropping) {
-          drop8(o, static_cast<uint32_t>(row) * static_cast<uint32_t>(H) + c, dseed, drop);
-          store8(dx_drop + static_cast<size_t>(row) * H + c, o);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) ad[i].v[j] += o.v[j];
-      }
-  }
-  // block reduction of the column sums, then one atomic per column per block
-  float* rg = red;
-  float* rb = red + ROW_WARPS * H;
-  float* rd = red + 2 * ROW_WARPS * H;
-#pragma unroll
-  for (int i = 0; i < ROW_MAXV; ++i)
-    if (i < nv) {
-      const int c = (i * 32 + lane) * 8;
-      store8(rg + warp * H + c, ag[i]);
-      store8(rb + warp * H + c, ab[i]);
-      store8(rd + warp * H + c, ad[i]);
-    }
-  __syncthreads();
-  const float alpha = alpha_ptr ? *alpha_ptr : 1.0f;
-  for (int c = threadIdx.x; c < H; c += blockDim.x) {
-    float a = 0.f, b = 0.f, d = 0.f;
-#pragma unroll
-    for (int w = 0; w < ROW_WARPS; ++w) {
-      a += rg[w * H + c];
-      b += rb[w * H + c];
-      d += rd[w * H + c];
-    }
-    atomicAdd(dgamma + c, a * alpha);
-    atomicAdd(dbeta + c, b * alpha);
-    if (dbias) atomicAdd(dbias + c, d * alpha);
-  }
-}
-
-// Second-generation LayerNorm backward.  ln_bwd_kernel keeps a whole row per warp, which costs 72 accumulator registers per
-// lane for the three column sums (dgamma, dbeta, dbias): 168 registers, 12 resident warps per SM, one row in flight per
-// warp — 2.4 TB/s (profiles/r01d).  Here a row is spread over `tpr` threads (one 8-column chunk each, so the column sums
+// The first generation kept a whole row per warp, which cost 72 accumulator registers per lane for the three column sums
+// (dgamma, dbeta, dbias): 168 registers, 12 resident warps per SM, one row in flight per warp — 2.4 TB/s (profiles/r01d; removed in
+// round 2, git 01a2ca4 keeps it).  Here a row is spread over `tpr` threads (one 8-column chunk each, so the column sums
 // are 24 registers), a CTA runs 384 / tpr independent row slots, and every slot pulls LNB_R rows per trip, so an SM keeps
 // 24 warps x LNB_R rows of loads in flight.  The per-row sums cross the slot's warps through shared memory behind a
 // slot-local named barrier (parity-double-buffered: one barrier per trip).
@@ -540,41 +446,95 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) embed_ln_bwd_kernel(const __ha
 // ------------------------------------------------------------------------------------------------ K11: token-cls head
 // logits[row, c] = h[row,:] . W[c,:] + b[c]   (C <= 4 classes; Linear(H -> 2/3): loss_calculator.py:17,42,
 // modeling_ponet.py:43,83-84).  HBM-bound GEMV-like: each warp streams one row with 128-bit loads.
-template <int C>
-__global__ void __launch_bounds__(ROW_WARPS * 32) cls_head_fwd_kernel(const __half* __restrict__ h, const float* __restrict__ W,
+// Each warp owns CLS_RPW consecutive rows per trip and issues ALL of their 128-bit loads before the first use (a row of H = 768
+// halves is only 3 loads per lane: one row per warp left ~1.5 KB in flight per warp and the kernel at 0.14-0.28 of the HBM
+// roofline, profiles/r01g); the C weight rows are loop-invariant and live in registers.  Grid-stride over row groups.
+constexpr int CLS_RPW = 4;
+constexpr int CLS_WARPS = 8;
+// eight elements as they sit in memory (fp16: one 128-bit word, fp32: two): what a load keeps in flight; converted at the use
+template <typename T> struct Raw8;
+template <> struct Raw8<__half> {
+  uint4 a;
+  __device__ __forceinline__ void load(const __half* p) { a = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ Vec8 get() const {
+    const __half2* hp = reinterpret_cast<const __half2*>(&a);
+    Vec8 r;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(hp[i]);
+      r.v[2 * i] = f.x;
+      r.v[2 * i + 1] = f.y;
+    }
+    return r;
+  }
+};
+template <> struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = *reinterpret_cast<const float4*>(p);
+    b = *reinterpret_cast<const float4*>(p + 4);
+  }
+  __device__ __forceinline__ Vec8 get() const {
+    Vec8 r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+  }
+};
+template <int C, typename T>
+__global__ void __launch_bounds__(CLS_WARPS * 32) cls_head_fwd_kernel(const T* __restrict__ h, const float* __restrict__ W,
                                                                        const float* __restrict__ b, float* __restrict__ logits,
                                                                        int32_t* __restrict__ argmax_out, int rows, int H, DropCfg drop) {
   const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
-  if (row >= rows) return;
   const int nv = lane_vecs(H, lane);
   const uint32_t dseed = drop.seed_base ? drop_seed(drop) : 0u;
-  float acc[C];
+  Vec8 w[C][ROW_MAXV];
 #pragma unroll
-  for (int c = 0; c < C; ++c) acc[c] = 0.f;
+  for (int c = 0; c < C; ++c)
 #pragma unroll
-  for (int i = 0; i < ROW_MAXV; ++i)
-    if (i < nv) {
-      const int col = (i * 32 + lane) * 8;
-      Vec8 x = load8(h + static_cast<size_t>(row) * H + col);
-      if (drop.seed_base) drop8(x, static_cast<uint32_t>(row) * static_cast<uint32_t>(H) + col, dseed, drop);   // bert_for_ts.py:66-67
+    for (int i = 0; i < ROW_MAXV; ++i)
+      if (i < nv) w[c][i] = load8(W + static_cast<size_t>(c) * H + (i * 32 + lane) * 8);
+  float bias[C];
 #pragma unroll
-      for (int c = 0; c < C; ++c) {
-        const Vec8 w = load8(W + static_cast<size_t>(c) * H + col);
+  for (int c = 0; c < C; ++c) bias[c] = b[c];
+  const int groups = (rows + CLS_RPW - 1) / CLS_RPW;
+  for (int grp = blockIdx.x * CLS_WARPS + (threadIdx.x >> 5); grp < groups; grp += gridDim.x * CLS_WARPS) {
+    const int row0 = grp * CLS_RPW;
+    Raw8<T> x[CLS_RPW][ROW_MAXV];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[c] = fmaf(x.v[j], w.v[j], acc[c]);
+    for (int rr = 0; rr < CLS_RPW; ++rr)
+#pragma unroll
+      for (int i = 0; i < ROW_MAXV; ++i)
+        if (i < nv && row0 + rr < rows) x[rr][i].load(h + static_cast<size_t>(row0 + rr) * H + (i * 32 + lane) * 8);
+#pragma unroll
+    for (int rr = 0; rr < CLS_RPW; ++rr) {
+      const int row = row0 + rr;
+      if (row >= rows) break;
+      float acc[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[c] = 0.f;
+#pragma unroll
+      for (int i = 0; i < ROW_MAXV; ++i)
+        if (i < nv) {
+          Vec8 xv = x[rr][i].get();
+          if (drop.seed_base) drop8(xv, static_cast<uint32_t>(row) * static_cast<uint32_t>(H) + (i * 32 + lane) * 8, dseed, drop);   // bert_for_ts.py:66-67
+#pragma unroll
+          for (int c = 0; c < C; ++c)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[c] = fmaf(xv.v[j], w[c][i].v[j], acc[c]);
+        }
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[c] = warp_sum(acc[c]) + bias[c];
+      if (lane == 0) {
+        int best = 0;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          logits[static_cast<size_t>(row) * C + c] = acc[c];
+          if (acc[c] > acc[best]) best = c;     // first maximum wins, like np.argmax
+        }
+        if (argmax_out) argmax_out[row] = best;
       }
     }
-#pragma unroll
-  for (int c = 0; c < C; ++c) acc[c] = warp_sum(acc[c]) + b[c];
-  if (lane == 0) {
-    int best = 0;
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-      logits[static_cast<size_t>(row) * C + c] = acc[c];
-      if (acc[c] > acc[best]) best = c;     // first maximum wins, like np.argmax
-    }
-    if (argmax_out) argmax_out[row] = best;
   }
 }
 

@@ -60,12 +60,13 @@ _PROTOS = {
     "b200_adamw_step_dev": [_p, _p, _p, _p, _p, _sz, _p, _p, _p],
     "b200_adamw_step_dev_zero": [_p, _p, _p, _p, _p, _sz, _p, _p, _p],
     # opt-in variants (include/b200enc.h, last section)
-    "b200_gemm_f16_resadd": [_p, _i, _p, _i, _i, _i, _i, _p, _p, _i, _p, C.c_uint, _f, _i, _p],
+    "b200_gemm_f16_resadd": [_p, _i, _p, _i, _i, _i, _i, _p, _p, _i, _p, C.c_uint, _f, _p],
+    "b200_gemm_f16_dgelu_colsum": [_p, _i, _p, _i, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p],
     "b200_gemm_f16_dgrad_delta": [_p, _i, _p, _i, _i, _i, _i, _p, _i, _p, _i, _p, _i, _i, _p],
     "b200_attn_bwd_delta_ptr": [_p],
     "b200_attn_bwd_ext": [_p, _i, _i, _p, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p, C.c_uint, _f, _i, _p],
 }
-_RESTYPE = {"b200_set_gemm_impl": None, "b200_set_gemm_debug": None, "b200_set_sm_limit": None, "b200_set_attn_variant": None, "b200_last_error": C.c_char_p, "b200_launch_count": _ll, "b200_version": _i, "b200_source_hash": C.c_char_p, "b200_attn_bwd_workspace": _sz, "b200_ponet_workspace": _sz, "b200_ponet_bwd_workspace": _sz, "b200_attn_bwd_delta_ptr": _p}
+_RESTYPE = {"b200_set_sm_limit": None, "b200_last_error": C.c_char_p, "b200_launch_count": _ll, "b200_version": _i, "b200_source_hash": C.c_char_p, "b200_attn_bwd_workspace": _sz, "b200_ponet_workspace": _sz, "b200_ponet_bwd_workspace": _sz, "b200_attn_bwd_delta_ptr": _p}
 
 _lock = threading.Lock()
 _lib = None
@@ -144,10 +145,7 @@ def load() -> C.CDLL:
                 fn.restype = _RESTYPE.get(name, _i)
             for name, rt in _RESTYPE.items():
                 getattr(lib, name).restype = rt
-            lib.b200_set_gemm_impl.argtypes = [_i]
-            lib.b200_set_gemm_debug.argtypes = [_i]
             lib.b200_set_sm_limit.argtypes = [_i]
-            lib.b200_set_attn_variant.argtypes = [_i]
             _lib = lib
     return _lib
 

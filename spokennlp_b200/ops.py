@@ -79,17 +79,16 @@ def gemm(a: Tensor, b: Tensor, out: Tensor, *, a_layout: int = 0, b_layout: int 
     return out
 
 
-def gemm_resadd(a: Tensor, b: Tensor, out32: Tensor, bias: Tensor, *, drop: Optional["Dropout"] = None, stream_k: bool = False) -> Tensor:
-    """OPT-IN.  out32[M,N] += dropout(A @ B^T + bias): `out32` holds the fp32 residual on entry and the
-    pre-LayerNorm sum on return (b200_gemm_f16_resadd).  `stream_k` balances N = 768 shapes over the CTA pairs at the price
-    of an fp32 summation order that varies from run to run."""
+def gemm_resadd(a: Tensor, b: Tensor, out32: Tensor, bias: Tensor, *, drop: Optional["Dropout"] = None) -> Tensor:
+    """out32[M,N] += dropout(A @ B^T + bias): `out32` holds the fp32 residual on entry and the pre-LayerNorm sum on return
+    (b200_gemm_f16_resadd)."""
     _req(a, torch.float16, "A"), _req(b, torch.float16, "B"), _req(out32, torch.float32, "out32"), _req(bias, torch.float32, "bias")
     M, K, N = a.shape[0], a.shape[1], b.shape[0]
     if b.shape[1] != K or tuple(out32.shape) != (M, N) or bias.numel() != N:
         raise L.B200Error(f"gemm_resadd: shape mismatch A{tuple(a.shape)} B{tuple(b.shape)} out{tuple(out32.shape)} bias{tuple(bias.shape)}")
     seed, site, p = _drop_args(drop)
     rc = L.load().b200_gemm_f16_resadd(_ptr(a), a.stride(0), _ptr(b), b.stride(0), M, N, K, _ptr(bias), _ptr(out32), out32.stride(0),
-                                       seed, site, p, 1 if stream_k else 0, _stream())
+                                       seed, site, p, _stream())
     L.check(rc, "b200_gemm_f16_resadd")
     return out32
 
@@ -99,8 +98,22 @@ def attn_bwd_delta_view(workspace: Tensor, B: int, heads: int, Sq: int) -> Tenso
     return workspace[:B * heads * Sq].view(B, heads, Sq)
 
 
+def gemm_dgelu_colsum(d_dense: Tensor, w: Tensor, dact: Tensor, dz: Tensor, colsum: Tensor, col_alpha: Optional[Tensor] = None) -> Tensor:
+    """dz = (d_dense @ W) * dact and colsum += col_alpha * dz.sum(0) in one kernel (W row-major [out, in] = [K, N])."""
+    for t, n in ((d_dense, "d_dense"), (w, "W"), (dact, "dact"), (dz, "dz")):
+        _req(t, torch.float16, n)
+    _req(colsum, torch.float32, "colsum")
+    M, K, N = d_dense.shape[0], d_dense.shape[1], w.shape[1]
+    if w.shape[0] != K or tuple(dz.shape) != (M, N) or tuple(dact.shape) != (M, N) or colsum.numel() != N:
+        raise L.B200Error(f"gemm_dgelu_colsum: shape mismatch d_dense{tuple(d_dense.shape)} W{tuple(w.shape)} dact{tuple(dact.shape)} colsum{tuple(colsum.shape)}")
+    rc = L.load().b200_gemm_f16_dgelu_colsum(_ptr(d_dense), d_dense.stride(0), _ptr(w), w.stride(0), M, N, K, _ptr(dact), dact.stride(0),
+                                             _ptr(dz), dz.stride(0), _ptr(colsum), _ptr(col_alpha), _stream())
+    L.check(rc, "b200_gemm_f16_dgelu_colsum")
+    return dz
+
+
 def gemm_dgrad_delta(dy: Tensor, w: Tensor, ctx: Tensor, dctx: Tensor, workspace: Tensor, B: int, heads: int, Sq: int) -> Tensor:
-    """OPT-IN.  dctx = dy @ W (the output projection's dgrad, W row-major [out, in]) and, in the same epilogue,
+    """dctx = dy @ W (the output projection's dgrad, W row-major [out, in]) and, in the same epilogue,
     delta[b,h,q] = <dctx row, ctx row> per head, written where `attn_bwd(..., delta_ready=True)` expects it."""
     for t, n in ((dy, "dy"), (w, "W"), (ctx, "ctx"), (dctx, "dctx")):
         _req(t, torch.float16, n)
@@ -112,11 +125,6 @@ def gemm_dgrad_delta(dy: Tensor, w: Tensor, ctx: Tensor, dctx: Tensor, workspace
                                             dctx.stride(0), _ptr(delta), heads, Sq, _stream())
     L.check(rc, "b200_gemm_f16_dgrad_delta")
     return dctx
-
-
-def set_gemm_impl(impl: int) -> None:
-    """2 (default): 2-CTA cta_group::2 GEMM with TMA epilogue; 1: single-CTA kernel (A/B measurements, tests)."""
-    L.load().b200_set_gemm_impl(int(impl))
 
 
 def wgrad_splits(M_out: int, N_in: int, K_tokens: int, sms: int = 148) -> int:

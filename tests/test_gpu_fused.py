@@ -1,7 +1,7 @@
-"""GPU parity of the kernel variants (blocks.Experimental).  They first ran on a B200 in round 2
-(profiles/gpurun_logs/r02_call01.log): resadd, delta and elect became the default path, streamk and ewait stay selectable for
-A/B runs.  Each variant is held to the round-1 kernel it replaces (bit-exact where the arithmetic is the same,
-summation-order tolerance where it is not) and to an fp32 statement of the op."""
+"""GPU parity of the fused epilogue entry points the default layer schedule uses (blocks.Experimental: resadd, delta, colsum;
+DESIGN.md §9).  Each is held to the unfused kernel pair it replaces (bit-exact where the arithmetic is the same,
+summation-order tolerance where it is not) and to an fp32 statement of the op; the training step is compared between the
+fused and the round-1 schedules."""
 import os
 
 import pytest
@@ -15,7 +15,6 @@ def _ops():
         pytest.skip("needs a GPU")
     torch.backends.cuda.matmul.allow_tf32 = False
     from spokennlp_b200 import ops
-    ops.set_gemm_impl(2)
     return ops
 
 
@@ -29,8 +28,7 @@ def _rel(a, b):
 
 
 @pytest.mark.parametrize("M,N,K", [(256, 256, 64), (1024, 768, 768), (300, 768, 1536), (16384, 768, 768), (16384, 768, 3072)])
-@pytest.mark.parametrize("stream_k", [False, True], ids=["tile-per-pair", "stream-k"])
-def test_resadd_matches_fp32_statement_and_the_res32_epilogue(M, N, K, stream_k):
+def test_resadd_matches_fp32_statement_and_the_res32_epilogue(M, N, K):
     ops = _ops()
     a, w = _rand16(M, K, seed=1), _rand16(N, K, seed=2, scale=0.05)
     bias = torch.randn(N, device="cuda") * 0.1
@@ -39,16 +37,13 @@ def test_resadd_matches_fp32_statement_and_the_res32_epilogue(M, N, K, stream_k)
     old = torch.empty(M, N, dtype=torch.float32, device="cuda")
     ops.gemm(a, w, old, epilogue=ops.EPI_BIAS_RES32, bias=bias, aux=res)
     new = res.clone()
-    ops.gemm_resadd(a, w, new, bias, stream_k=stream_k)
+    ops.gemm_resadd(a, w, new, bias)
     assert _rel(new, ref) < 1e-5, (_rel(new, ref), _rel(old, ref))
-    if not stream_k:            # same fp32 operations in the same order, the residual added last either way: identical bits
-        assert torch.equal(new, old), float((new - old).abs().max())
-    else:                       # partial sums of a tile meet in a run-dependent order
-        assert _rel(new, old) < 2e-6
+    # same fp32 operations in the same order, the residual added last either way: identical bits
+    assert torch.equal(new, old), float((new - old).abs().max())
 
 
-@pytest.mark.parametrize("stream_k", [False, True], ids=["tile-per-pair", "stream-k"])
-def test_resadd_dropout_draws_the_same_mask_as_the_res32_epilogue(stream_k):
+def test_resadd_dropout_draws_the_same_mask_as_the_res32_epilogue():
     ops = _ops()
     M, N, K = 2048, 768, 3072
     a, w = _rand16(M, K, seed=3), _rand16(N, K, seed=4, scale=0.05)
@@ -59,14 +54,11 @@ def test_resadd_dropout_draws_the_same_mask_as_the_res32_epilogue(stream_k):
     old = torch.empty(M, N, dtype=torch.float32, device="cuda")
     ops.gemm(a, w, old, epilogue=ops.EPI_BIAS_RES32, bias=bias, aux=res, drop=drop)
     new = res.clone()
-    ops.gemm_resadd(a, w, new, bias, drop=drop, stream_k=stream_k)
+    ops.gemm_resadd(a, w, new, bias, drop=drop)
     dropped_old, dropped_new = (old == res), (new == res)
     assert torch.equal(dropped_old, dropped_new)                    # the very same elements fell
     assert 0.08 < float(dropped_new.float().mean()) < 0.12
-    if not stream_k:
-        assert torch.equal(new, old)
-    else:
-        assert _rel(new, old) < 2e-6
+    assert torch.equal(new, old)
 
 
 @pytest.mark.parametrize("B,S,heads", [(2, 128, 2), (3, 300, 4), (32, 512, 12)])
@@ -89,50 +81,24 @@ def test_dgrad_delta_matches_the_plain_dgrad_and_the_separate_row_statistic(B, S
     assert torch.isnan(ws[B * heads * S:]).all()                                           # nothing else in the workspace was touched
 
 
-@pytest.mark.parametrize("B,S,heads,masked,p", [(2, 256, 2, False, 0.0), (3, 512, 12, True, 0.0), (2, 300, 4, True, 0.1), (32, 512, 12, False, 0.1)])
-def test_attention_with_warp_elected_arrivals_matches_the_default_kernels(B, S, heads, masked, p):
-    """Same arithmetic, different hand-off signalling: context, LSE, dK and dV must be bit-identical; dQ is an fp32 reduce-add
-    over key blocks whose order varies from run to run in both variants."""
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (300, 776, 1536), (1024, 3072, 768), (16384, 3072, 768)])
+def test_dgelu_colsum_matches_the_plain_epilogue_and_the_separate_column_sum(M, N, K):
+    """dz must be bit-identical to the plain EPI_DGELU GEMM; the fused bias gradient is the column sum of the fp16-ROUNDED dz
+    (what b200_colsum reads back from HBM), scaled by *col_alpha."""
     ops = _ops()
-    from spokennlp_b200 import lib
-    H, M = heads * 64, B * S
-    qkv = _rand16(M, 3 * H, seed=11)
-    dctx = _rand16(M, H, seed=12, scale=0.1)
-    mask = torch.ones(B, S, dtype=torch.long, device="cuda")
-    if masked:
-        mask[1, S - 77:] = 0
-    key_bias, kv_len = ops.mask_to_bias(mask)
-    seed = torch.tensor([4321], dtype=torch.int32, device="cuda")
-    drop = ops.Dropout(seed, 9, p) if p > 0 else None
-    cols = dict(q_col0=0, k_col0=H, v_col0=2 * H)
-    res = []
-    try:
-        for variant in (0, 1, 3, 4, 8, 12):     # 4: attn_bwd4_kernel, 8: attn_fwd4_kernel (sixteen softmax warps each)
-            lib.load().b200_set_attn_variant(variant)
-            ctx = torch.empty(M, H, dtype=torch.float16, device="cuda")
-            lse = torch.empty(B, heads, S, device="cuda")
-            ops.attn_fwd(qkv, qkv, ctx, B, heads, S, S, key_bias=key_bias, kv_len=kv_len, lse2=lse, drop=drop, **cols)
-            dqkv = torch.zeros_like(qkv)
-            ws = ops.attn_bwd_workspace(B, heads, S, "cuda")
-            ops.attn_bwd(qkv, qkv, dctx, ctx, lse, dqkv, dqkv, ws, B, heads, S, S, dq_col0=0, dk_col0=H, dv_col0=2 * H,
-                         key_bias=key_bias, kv_len=kv_len, drop=drop, **cols)
-            torch.cuda.synchronize()
-            res.append((ctx, lse, dqkv))
-    finally:
-        from spokennlp_b200.blocks import Experimental
-        Experimental.from_env(None)             # restores the library-wide selector to the active variant set
-    c0, l0, g0 = res[0]
-    for variant, (c1, l1, g1) in zip((1, 3, 4, 8, 12), res[1:]):
-        if variant & 8:
-            # the two halves of a row add their partial row sums in a different order than one thread walking 128 keys:
-            # LSE / context agree to fp32 / fp16 rounding, the P tile fed to the tensor core is bit-identical
-            assert _rel(l1, l0) < 1e-6 and _rel(c1, c0) < 1e-3, (variant, _rel(l1, l0), _rel(c1, c0))
-            assert float((c1.float() - c0.float()).abs().max()) <= 2 ** -10 * float(c0.float().abs().max())
-            assert _rel(g1[:, H:], g0[:, H:]) < 2e-3
-        else:
-            assert torch.equal(c0, c1) and torch.equal(l0, l1), variant
-            assert torch.equal(g0[:, H:], g1[:, H:]), variant      # dK, dV
-        assert _rel(g1[:, :H], g0[:, :H]) < 2e-3                   # dQ: fp16 of an fp32 sum taken in a varying order
+    dy, w = _rand16(M, K, seed=21), _rand16(K, N, seed=22, scale=0.05)          # W row-major [out = K, in = N]
+    dact = _rand16(M, N, seed=23).abs().clamp_max(1.2)
+    plain = torch.empty(M, N, dtype=torch.float16, device="cuda")
+    ops.gemm(dy, w, plain, b_layout=1, epilogue=ops.EPI_DGELU, aux=dact)
+    alpha = torch.tensor([0.25], device="cuda")
+    want = torch.full((N,), 3.0, device="cuda")
+    ops.colsum(plain, want, alpha)
+    fused = torch.empty_like(plain)
+    got = torch.full((N,), 3.0, device="cuda")                                  # accumulates (+=)
+    ops.gemm_dgelu_colsum(dy, w, dact, fused, got, alpha)
+    assert torch.equal(fused, plain)
+    ref = 3.0 + 0.25 * plain.double().sum(0)
+    assert _rel(got, ref) < 1e-5 and _rel(want, ref) < 1e-5, (_rel(got, ref), _rel(want, ref))
 
 
 def _tiny_step(variants: str, dropout: float):
@@ -164,19 +130,16 @@ def _tiny_step(variants: str, dropout: float):
 
 
 @pytest.mark.parametrize("dropout", [0.0, 0.1])
-@pytest.mark.parametrize("variants", ["resadd", "delta", "resadd,delta", "streamk,delta", "elect", "ewait", "resadd,delta,ewait", "bwd16", "fwd16", "resadd,delta,elect,bwd16,fwd16"])
-def test_training_step_with_variants_matches_the_default_path(variants, dropout):
+@pytest.mark.parametrize("variants", ["resadd", "delta", "colsum", "resadd,delta", "resadd,delta,colsum"])
+def test_training_step_with_fused_schedules_matches_the_round1_schedule(variants, dropout):
     _ops()
     loss0, g0 = _tiny_step("none", dropout)
     loss1, g1 = _tiny_step(variants, dropout)
-    loose = "streamk" in variants or "fwd16" in variants          # forward summation order differs
-    if not loose:
+    if True:
         # forward arithmetic is unchanged; the loss itself is a sum of per-row terms taken with fp32 atomics in a run-dependent
         # order (ce_stats), so two runs of the SAME path already differ in the last bit (seen on the B200: 1.1e-7 relative)
         assert abs(loss1 - loss0) <= 4e-7 * abs(loss0)
-    else:
-        assert abs(loss1 - loss0) < 1e-5
     # resadd alone leaves every saved activation bit-identical: only the wgrads' split-K reduction order differs between two runs
-    # without streamk / delta the two runs differ only by the order of fp32 reduce-adds (dQ over key blocks, split-K wgrads),
+    # without delta the two runs differ only by the order of fp32 reduce-adds (dQ over key blocks, split-K wgrads),
     # which already varies between two runs of the default path: a few fp16 roundings of dQ flip (estimated scale ~1e-5)
-    assert _rel(g1, g0) < (2e-3 if loose or "delta" in variants else 1e-4), _rel(g1, g0)
+    assert _rel(g1, g0) < (2e-3 if "delta" in variants else 1e-4), _rel(g1, g0)

@@ -39,15 +39,12 @@ def _err_report(got, ref, name, block=64):
     return rel, "\n".join(msg)
 
 
-@pytest.fixture(params=[2, 1], ids=["gemm2cta", "gemm1cta"])
-def gemm_impl(request):
-    """Run GEMM tests through both kernels: the 2-CTA production path and the single-CTA one."""
+@pytest.fixture
+def gemm_impl():
+    """(kept as a fixture so the GEMM tests skip cleanly without a GPU; the single-CTA first generation was removed in round 2)"""
     if not torch.cuda.is_available():
         pytest.skip("needs a GPU")
-    from spokennlp_b200 import ops
-    ops.set_gemm_impl(request.param)
-    yield request.param
-    ops.set_gemm_impl(2)
+    yield 2
 
 
 def _rand16(*shape, scale=1.0, seed=0):

@@ -25,8 +25,8 @@ def rec(monkeypatch):
         r.calls.append((f"gemm/epi{epilogue}/a{a_layout}b{b_layout}", dict(out=out, aux=aux)))
         return out
 
-    def gemm_resadd(a, b, out32, bias, *, drop=None, stream_k=False):
-        r.calls.append(("gemm_resadd" + ("/streamk" if stream_k else ""), dict(out=out32)))
+    def gemm_resadd(a, b, out32, bias, *, drop=None):
+        r.calls.append(("gemm_resadd", dict(out=out32)))
         return out32
 
     def gemm_dgrad_delta(dy, w, ctx, dctx, ws, B, heads, Sq):
@@ -57,7 +57,7 @@ def rec(monkeypatch):
             r.calls.append((name, {}))
             return ret(*a, **k) if ret else None
         return f
-    for name, fn in dict(gemm=gemm, gemm_resadd=gemm_resadd, gemm_dgrad_delta=gemm_dgrad_delta, attn_fwd=attn_fwd, attn_bwd=attn_bwd,
+    for name, fn in dict(gemm=gemm, gemm_resadd=gemm_resadd, gemm_dgrad_delta=gemm_dgrad_delta, gemm_dgelu_colsum=simple("gemm_dgelu_colsum"), attn_fwd=attn_fwd, attn_bwd=attn_bwd,
                          layernorm_fwd=layernorm_fwd, layernorm_bwd=layernorm_bwd, embed_ln_fwd=embed_ln_fwd,
                          embed_ln_bwd=simple("embed_ln_bwd"), colsum=simple("colsum"),
                          cast_f32_to_f16=simple("cast_f32_to_f16"),
@@ -103,7 +103,7 @@ def test_round1_schedule_is_still_selectable(rec):
     assert rec.names() == BWD_LAYER * L + ["embed_ln_bwd"]
 
 
-@pytest.mark.parametrize("variants,name", [("resadd", "gemm_resadd"), ("streamk", "gemm_resadd/streamk")])
+@pytest.mark.parametrize("variants,name", [("resadd", "gemm_resadd")])
 def test_resadd_accumulates_in_place_only_into_buffers_the_engine_owns(rec, variants, name):
     blocks.Experimental.from_env(variants)
     eng = _engine()
@@ -147,10 +147,10 @@ def test_delta_variant_replaces_the_plain_dgrad_and_skips_the_row_statistic_pass
 
 
 def test_default_schedule_is_the_round2_validated_set(rec, monkeypatch):
-    """resadd + delta + elect were validated and measured on a B200 (profiles/r02a_*) and are the default."""
+    """resadd + delta + colsum were validated and measured on a B200 (profiles/r02a_*, r02c_*) and are the default."""
     monkeypatch.delenv("B200_EXP", raising=False)
     blocks.Experimental.from_env(None)
-    assert blocks.Experimental.active() == ["resadd", "delta", "elect"]
+    assert blocks.Experimental.active() == ["resadd", "delta", "colsum"]
     eng = _engine()
     rec.calls.clear()
     _, _, saved, _, _ = _forward(eng, save=True)
@@ -159,6 +159,20 @@ def test_default_schedule_is_the_round2_validated_set(rec, monkeypatch):
     rec.calls.clear()
     eng.backward(saved, torch.empty(B * S, H, dtype=torch.float16), torch.ones(1))
     bwd = [{"gemm/epi0/a0b1": "gemm_dgrad_delta", "attn_bwd": "attn_bwd/delta_ready"}.get(n, n) for n in BWD_LAYER]
+    assert bwd[2:4] == ["gemm/epi4/a0b1", "colsum"]
+    bwd[2:4] = ["gemm_dgelu_colsum"]
+    assert rec.names() == bwd * L + ["embed_ln_bwd"]
+
+
+def test_colsum_variant_folds_the_ffn_bias_gradient_into_the_dgelu_dgrad(rec):
+    blocks.Experimental.from_env("colsum")
+    eng = _engine()
+    _, _, saved, _, _ = _forward(eng, save=True)
+    rec.calls.clear()
+    eng.backward(saved, torch.empty(B * S, H, dtype=torch.float16), torch.ones(1))
+    bwd = list(BWD_LAYER)
+    assert bwd[2:4] == ["gemm/epi4/a0b1", "colsum"]
+    bwd[2:4] = ["gemm_dgelu_colsum"]
     assert rec.names() == bwd * L + ["embed_ln_bwd"]
 
 

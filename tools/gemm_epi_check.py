@@ -6,7 +6,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from spokennlp_b200 import lib, ops  # noqa: E402
-from tools.gemm_sweep import timeit  # noqa: E402
+from tools.timing import timeit  # noqa: E402
 
 torch.backends.cuda.matmul.allow_tf32 = False
 M, H, I = int(os.environ.get("M", 16384)), 768, 3072

@@ -1,6 +1,5 @@
 """Attention kernels alone at the bench shape, for `ncu --set full` captures and for the Sk sweep that separates the
-per-item fixed cost from the per-key-block cost:  python tools/prof_attn.py [sweep [debug bits ...]]
-(debug bits as in include/b200enc.h, e.g. `sweep 0 0x100000` compares the production kernels with the first generation)"""
+per-item fixed cost from the per-key-block cost:  [B200_ATTN_DROP=0.1] python tools/prof_attn.py [sweep | ln]"""
 import os
 import sys
 
@@ -8,11 +7,10 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from spokennlp_b200 import lib, ops  # noqa: E402
-from tools.gemm_sweep import timeit  # noqa: E402
+from tools.timing import timeit  # noqa: E402
 
 heads, H = 12, 768
 so = lib.load()
-so.b200_set_attn_variant(int(os.environ.get("B200_ATTN_VARIANT", "0"), 0))     # 1 / 3: the opt-in hand-off variants
 torch.manual_seed(0)
 
 
@@ -33,16 +31,13 @@ def make(B, S):
 
 
 if len(sys.argv) > 1 and sys.argv[1] == "sweep":
-    for dbg in [int(x, 0) for x in (sys.argv[2:] or ["0"])]:
-        so.b200_set_gemm_debug(dbg)
-        for B, S in ((128, 128), (64, 256), (32, 512), (16, 1024), (8, 2048)):
-            fwd, bwd = make(B, S)
-            fwd(); bwd()
-            tf, tb = timeit(fwd), timeit(bwd)
-            fl = 4.0 * B * S * S * H
-            print(f"dbg={dbg:#x} B={B:4d} S={S:5d}: fwd {tf * 1e6:7.1f} us ({fl / tf / 1e12:5.0f} TF)  bwd(+delta,memset,cast) {tb * 1e6:7.1f} us ({2 * fl / tb / 1e12:5.0f} TF)",
-                  flush=True)
-    so.b200_set_gemm_debug(0)
+    for B, S in ((128, 128), (64, 256), (32, 512), (16, 1024), (8, 2048)):
+        fwd, bwd = make(B, S)
+        fwd(); bwd()
+        tf, tb = timeit(fwd), timeit(bwd)
+        fl = 4.0 * B * S * S * H
+        print(f"B={B:4d} S={S:5d}: fwd {tf * 1e6:7.1f} us ({fl / tf / 1e12:5.0f} TF)  bwd(+delta,memset,cast) {tb * 1e6:7.1f} us ({2 * fl / tb / 1e12:5.0f} TF)",
+              flush=True)
 elif len(sys.argv) <= 1:
     fwd, bwd = make(32, 512)
     fwd(); bwd()
