@@ -495,7 +495,7 @@ int b200_cls_head_fwd_drop(const void* h, const float* W, const float* b, float*
   if (int rc = check_row_shape("cls_head_fwd", rows, H)) return rc;
   const DropCfg drop = make_drop(seed, site, p);
   int grid = (rows + CLS_WARPS * CLS_RPW - 1) / (CLS_WARPS * CLS_RPW);
-  if (grid > sm_count() * 8) grid = sm_count() * 8;
+  if (grid > sm_count()) grid = sm_count();      // one resident CTA per SM (217 registers x 256 threads), contiguous rows per warp
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (C == 2) cls_head_fwd_kernel<2, __half><<<grid, CLS_WARPS * 32, 0, s>>>(static_cast<const __half*>(h), W, b, logits, argmax, rows, H, drop);
   else if (C == 3) cls_head_fwd_kernel<3, __half><<<grid, CLS_WARPS * 32, 0, s>>>(static_cast<const __half*>(h), W, b, logits, argmax, rows, H, drop);

@@ -313,13 +313,19 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
         }
         float f[CW];
 #pragma unroll
-        for (int i = 0; i < CW; ++i) f[i] = RESADD ? __uint_as_float(v[i]) : __uint_as_float(v[i]) * alpha;   // (the forward never scales)
+        for (int i = 0; i < CW; ++i) f[i] = __uint_as_float(v[i]);
+        if (!RESADD && g.alpha != nullptr) {            // in practice only the wgrad reduction scales (one uniform branch elsewhere)
+          const uint64_t al2 = pack2(alpha, alpha);
+#pragma unroll
+          for (int i = 0; i < CW; i += 2) unpack2(mul2(pack2(f[i], f[i + 1]), al2), f[i], f[i + 1]);
+        }
         if (HAS_BIAS) {
 #pragma unroll
           for (int i = 0; i < CW / 4; ++i) {
             float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (gc0 + 4 * i < g.N) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + gc0 + 4 * i));
-            f[4 * i] += b4.x; f[4 * i + 1] += b4.y; f[4 * i + 2] += b4.z; f[4 * i + 3] += b4.w;
+            unpack2(add2(pack2(f[4 * i], f[4 * i + 1]), pack2(b4.x, b4.y)), f[4 * i], f[4 * i + 1]);
+            unpack2(add2(pack2(f[4 * i + 2], f[4 * i + 3]), pack2(b4.z, b4.w)), f[4 * i + 2], f[4 * i + 3]);
           }
         }
         if ((EPI == EPI_BIAS_RES32 || EPI == EPI_BIAS_RES || RESADD) && g.drop.seed_base != nullptr) {
@@ -327,11 +333,12 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
           const uint32_t seed = drop_seed(g.drop);
           const uint32_t e0 = static_cast<uint32_t>(row0 + lane) * static_cast<uint32_t>(g.N) + static_cast<uint32_t>(gc0);
 #pragma unroll
-          for (int i = 0; i < CW / 2; ++i) {
-            float m0, m1;
-            drop_pair((e0 >> 1) + i, seed, g.drop.thr15, g.drop.scale, m0, m1);
-            f[2 * i] *= m0;
-            f[2 * i + 1] *= m1;
+          const uint32_t pre0 = drop_premix(e0 >> 1, seed), tt = g.drop.thr15 * 0x00010001u;
+          const uint64_t sc2 = pack2(g.drop.scale, g.drop.scale);
+          for (int i = 0; i < CW / 2; ++i) {     // both decisions of a pair from one SWAR compare, the 1/(1-p) as one packed multiply
+            const uint32_t z = drop_z(pre0 + static_cast<uint32_t>(i) * kDropC1, tt);
+            const uint64_t kept = pack2u(__float_as_uint(f[2 * i]) & drop_keep_lo(z), __float_as_uint(f[2 * i + 1]) & drop_keep_hi(z));
+            unpack2(mul2(kept, sc2), f[2 * i], f[2 * i + 1]);
           }
         }
         if (HAS_AUX && !DELTA) {
@@ -363,8 +370,10 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
 #pragma unroll
           for (int k = 0; k < 32; ++k) {
             float y0, y1, d0, d1;
-            gelu_erf_both(f[2 * k], y0, d0);
-            gelu_erf_both(f[2 * k + 1], y1, d1);
+            uint64_t y2, d2;
+            gelu_erf_both2(pack2(f[2 * k], f[2 * k + 1]), y2, d2);
+            unpack2(y2, y0, y1);
+            unpack2(d2, d0, d1);
             const __half2 hz = __floats2half2_rn(d0, d1), hh = __floats2half2_rn(y0, y1);
             zw[k] = *reinterpret_cast<const uint32_t*>(&hz);
             ow[k] = *reinterpret_cast<const uint32_t*>(&hh);

@@ -395,6 +395,31 @@ __device__ __forceinline__ void gelu_erf_both(float x, float& y, float& dy) {
   y = x * cdf;
   dy = fmaf(x, 0.7978845608028654f * he, cdf);                                // Phi(x) + x * phi(x)
 }
+// Two elements at a time on packed fp32 pairs: the GEMM epilogue that applies this is issue-bound (8 epilogue warps, ~0.5
+// instructions per cycle per scheduler), and 21.5 scalar instructions per element left half of it exposed behind a K = 768
+// mainloop.  Same arithmetic as gelu_erf_both; the 0.5 is folded into the exponent, the sign select into a
+// sign-bit transfer: cdf = 0.5 + copysign(0.5 - tail, x).
+__device__ __forceinline__ void gelu_erf_both2(uint64_t x2, uint64_t& y2, uint64_t& dy2) {
+  float x0, x1;
+  unpack2(x2, x0, x1);
+  const float t0 = fast_rcp(fmaf(fabsf(x0), 0.2316418882f, 1.0f)), t1 = fast_rcp(fmaf(fabsf(x1), 0.2316418882f, 1.0f));
+  const uint64_t t2 = pack2(t0, t1);
+  float a0, a1;
+  unpack2(fma2(mul2(x2, x2), pack2(-0.7213475204444817f, -0.7213475204444817f), pack2(-1.0f, -1.0f)), a0, a1);
+  const uint64_t he2 = pack2(fast_exp2(a0), fast_exp2(a1));                   // 0.5 * exp(-x^2/2)
+  uint64_t poly = fma2(t2, pack2(1.061405429f, 1.061405429f), pack2(-1.453152027f, -1.453152027f));
+  poly = fma2(poly, t2, pack2(1.421413741f, 1.421413741f));
+  poly = fma2(poly, t2, pack2(-0.284496736f, -0.284496736f));
+  poly = fma2(poly, t2, pack2(0.254829592f, 0.254829592f));
+  const uint64_t tail = mul2(mul2(poly, t2), he2);                            // 1 - Phi(|x|)
+  float q0, q1;
+  unpack2(fma2(tail, pack2(-1.0f, -1.0f), pack2(0.5f, 0.5f)), q0, q1);         // 0.5 - tail  (>= 0)
+  q0 = __uint_as_float(__float_as_uint(q0) ^ (__float_as_uint(x0) & 0x80000000u));
+  q1 = __uint_as_float(__float_as_uint(q1) ^ (__float_as_uint(x1) & 0x80000000u));
+  const uint64_t cdf = add2(pack2(q0, q1), pack2(0.5f, 0.5f));
+  y2 = mul2(x2, cdf);
+  dy2 = fma2(x2, mul2(he2, pack2(0.7978845608028654f, 0.7978845608028654f)), cdf);      // Phi(x) + x * phi(x)
+}
 __device__ __forceinline__ float gelu_erf(float x) {
   float y, dy;
   gelu_erf_both(x, y, dy);

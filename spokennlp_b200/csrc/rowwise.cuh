@@ -497,19 +497,22 @@ __global__ void __launch_bounds__(CLS_WARPS * 32) cls_head_fwd_kernel(const T* _
   float bias[C];
 #pragma unroll
   for (int c = 0; c < C; ++c) bias[c] = b[c];
-  const int groups = (rows + CLS_RPW - 1) / CLS_RPW;
-  for (int grp = blockIdx.x * CLS_WARPS + (threadIdx.x >> 5); grp < groups; grp += gridDim.x * CLS_WARPS) {
-    const int row0 = grp * CLS_RPW;
+  // every warp owns one contiguous range of rows (so the C weight rows are fetched once per warp, not once per row group:
+  // at 4 rows per group they were as many bytes as the activations) and walks it CLS_RPW rows at a time
+  const int n_warps = gridDim.x * CLS_WARPS, wid = blockIdx.x * CLS_WARPS + (threadIdx.x >> 5);
+  const int per_warp = (rows + n_warps - 1) / n_warps;
+  const int row_end = min(rows, (wid + 1) * per_warp);
+  for (int row0 = wid * per_warp; row0 < row_end; row0 += CLS_RPW) {
     Raw8<T> x[CLS_RPW][ROW_MAXV];
 #pragma unroll
     for (int rr = 0; rr < CLS_RPW; ++rr)
 #pragma unroll
       for (int i = 0; i < ROW_MAXV; ++i)
-        if (i < nv && row0 + rr < rows) x[rr][i].load(h + static_cast<size_t>(row0 + rr) * H + (i * 32 + lane) * 8);
+        if (i < nv && row0 + rr < row_end) x[rr][i].load(h + static_cast<size_t>(row0 + rr) * H + (i * 32 + lane) * 8);
 #pragma unroll
     for (int rr = 0; rr < CLS_RPW; ++rr) {
       const int row = row0 + rr;
-      if (row >= rows) break;
+      if (row >= row_end) break;
       float acc[C];
 #pragma unroll
       for (int c = 0; c < C; ++c) acc[c] = 0.f;

@@ -200,13 +200,13 @@ def test_cuda_graph_replay_matches_eager_steps():
             model.loss_calculator.classifier.bias.copy_(g["cls_b"])
         tr = DataParallelTrainer(model, lr=1e-3, total_steps=20)
         if graphed:
-            before = tr.flat.flat32.clone()
+            before, before16 = tr.flat.flat32.clone(), tr.flat.flat16.clone()
             assert tr.capture(*batch, warmup=2)
-            # the warm-up steps of capture() really trained: rewind so both runs start from the same point
-            tr.flat.flat32.copy_(before)
-            tr.flat.sync_half(force=True)
-            tr.m.zero_(); tr.v.zero_(); tr.step_idx = 0
-            assert tr.kernels_per_step > 50
+            # capture() warms up with REAL steps and then puts everything back: parameters, fp16 mirror, moments, loss scale, step
+            assert torch.equal(tr.flat.flat32, before) and torch.equal(tr.flat.flat16, before16)
+            assert float(tr.m.abs().max()) == 0.0 and float(tr.v.abs().max()) == 0.0 and tr.step_idx == 0
+            assert float(tr.flat.grad32.abs().max()) == 0.0 and tr.skipped_steps() == 0
+            assert tr.kernels_per_step > 40
         ls = []
         for _ in range(4):
             tr.step(*batch)
