@@ -252,6 +252,65 @@ int b200_attn_bwd_ext(const void* q, int ldq, int q_col0, const void* kv, int ld
                       void* dq, int ld_dq, int dq_col0, void* dkv, int ld_dkv, int dk_col0, int dv_col0, int B, int heads, int Sq, int Sk,
                       const uint32_t* seed, unsigned site, float p, int flags, void* stream);
 
+/* ---- loss heads of the topic-segmentation wrapper on the labelled [BOS] rows (csrc/heads.cuh) ---------
+ * Replaces the per-example Python loops, boolean-mask gathers and host syncs of
+ *   emnlp2023-topic_segmentation/src/models/modules/loss_calculator.py:38-71, utils.py:116-182, tssp.py:26-34, cssl.py:20-273.
+ * All activations are fp32 (the dtype the drop-in encoder hands to autograd).  Index lists are int32 device arrays:
+ *   b200_heads_compact    positions with key != ignore, row-major: idx (flat b*S+s), ex (example), rank (inside the example),
+ *                         cnt/start [B], totals = {n, max cnt} (read back by the host once; depends on the labels only)
+ *   b200_heads_topic_ids  topic id of every labelled row (cssl.py:252-263)
+ *   gather/scatter_rows   R[i] = h[idx[i]] / dh[idx[i]] += scale * dR[i]
+ *   segmax_fwd/bwd        cssl.py:236-247 segment amax + slot gather (gradient split evenly between ties)
+ *   normalize(_bwd)       x / max(|x|, eps): the operands of F.cosine_similarity
+ *   pair_cos_fwd/bwd      utils.py:116-138 cosine of each labelled row with the next one of its example (cyclic), / temp,
+ *                         scattered into out[b, rank] (caller pre-fills -100)
+ *   bce_fwd/bwd           the "cos" score predictor's BCE-with-logits terms (loss_calculator.py:45-49)
+ *   cssl_matrix_fwd/bwd   cssl.py:20-72 ("eop_matrix"): out[0] += weight * loss; E [n,n], num, den, coef feed the backward
+ *   cssl_list_fwd/bwd     cssl.py:86-166 ("eop_list") on host-drawn index lists pos [kp,n], neg [kn,n]
+ *   rows_ce_fwd/bwd       Linear(H,C) + CE on compact rows (TSSP, tssp.py:26-34): stats[0] += sum nll
+ *   cls_fwd / focal_stats / cls_bwd   the full-position Linear(H,C) head with CE or FocalLoss (utils.py:141-182) on fp32
+ *                         activations: stats = {sum w nll, sum w, sum_i (1-p_i)^gamma}; dh/dW/db are ACCUMULATED.
+ * Backward entry points take `scale` (host) and `gscale` (optional device scalar: the upstream gradient of the loss). */
+int b200_heads_compact(const int64_t* key, long long ignore, int B, int S, int32_t* tmp, int32_t* cnt, int32_t* start, int32_t*
+    totals, int32_t* idx, int32_t* ex, int32_t* rank, void* stream);
+int b200_heads_gather_keys(const int64_t* key, const int32_t* idx, int n, int32_t* vals, void* stream);
+int b200_heads_topic_ids(const int32_t* lab, const int32_t* ex, int n, int32_t* seg, void* stream);
+int b200_heads_gather_rows(const float* h, const int32_t* idx, int n, int H, float* R, void* stream);
+int b200_heads_scatter_rows(const float* dR, const int32_t* idx, int n, int H, float scale, float* dh, void* stream);
+int b200_heads_segmax_fwd(const float* h, const int64_t* seg_ids, const int32_t* slot_ex, const int32_t* slot_id, int nf, int S,
+    int H, float* F, void* stream);
+int b200_heads_segmax_bwd(const float* h, const int64_t* seg_ids, const int32_t* slot_ex, const int32_t* slot_id, const float*
+    F, const float* dF, int nf, int S, int H, float scale, float* dh, void* stream);
+int b200_heads_normalize(const float* X, int n, int H, float eps, float* Xn, float* inv, void* stream);
+int b200_heads_normalize_bwd(const float* Xn, const float* inv, const float* dXn, int n, int H, float scale, const float*
+    gscale, float* dX, void* stream);
+int b200_heads_pair_cos_fwd(const float* Rn, const int32_t* ex, const int32_t* rank, const int32_t* start, const int32_t* cnt,
+    int n, int H, float temp, float* cos_rows, float* out, int ld, void* stream);
+int b200_heads_pair_cos_bwd(const float* Rn, const int32_t* ex, const int32_t* rank, const int32_t* start, const int32_t* cnt,
+    const float* g, int n, int H, float temp, float* dRn, void* stream);
+int b200_heads_bce_fwd(const float* cos_rows, const int32_t* lab, int n, float* stats, void* stream);
+int b200_heads_bce_bwd(const float* cos_rows, const int32_t* lab, int n, float scale, const float* gscale, float* g, void*
+    stream);
+int b200_heads_cssl_matrix_fwd(const float* Fn, const int32_t* seg, int n, int H, float temp, float weight, float* E, float*
+    num, float* den, float* coef, float* out, void* stream);
+int b200_heads_cssl_matrix_bwd(const float* Fn, const int32_t* seg, const float* E, const float* num, const float* den, const
+    float* coef, int n, int H, float temp, float* dFn, void* stream);
+int b200_heads_cssl_list_fwd(const float* Fn, const int32_t* pos, const int32_t* neg, int kp, int kn, int n, int H, float temp,
+    float weight, float* out, float* gw, void* stream);
+int b200_heads_cssl_list_bwd(const float* Fn, const int32_t* pos, const int32_t* neg, const float* gw, int kp, int kn, int n,
+    int H, float* dFn, void* stream);
+int b200_heads_rows_ce_fwd(const float* R, const float* W, const float* bias, const int32_t* tgt, int n, int H, int C, float*
+    probs, float* stats, void* stream);
+int b200_heads_rows_ce_bwd(const float* R, const float* W, const int32_t* tgt, const float* probs, int n, int H, int C, float
+    scale, const float* gscale, float* dR, float* dW, float* db, void* stream);
+int b200_heads_cls_fwd(const float* h, const float* W, const float* b, float* logits, int32_t* argmax, int rows, int H, int C,
+    void* stream);
+int b200_heads_focal_stats(const float* logits, const int64_t* labels, const float* class_weight, float gamma, int rows, int C,
+    float* stats, void* stream);
+int b200_heads_cls_bwd(const float* h, const float* logits, const int64_t* labels, const float* class_weight, const float*
+    stats, const float* W, float gamma, float scale, const float* gscale, int rows, int H, int C, float* dh, float* dW, float*
+    db, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

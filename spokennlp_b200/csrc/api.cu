@@ -14,6 +14,7 @@
 #include "attn_fwd3.cuh"
 #include "gemm.cuh"
 #include "gemm2.cuh"
+#include "heads.cuh"
 #include "optim.cuh"
 #include "ponet.cuh"
 #include "rowwise.cuh"
@@ -495,10 +496,10 @@ int b200_cls_head_fwd_drop(const void* h, const float* W, const float* b, float*
   if (int rc = check_row_shape("cls_head_fwd", rows, H)) return rc;
   const DropCfg drop = make_drop(seed, site, p);
   int grid = (rows + CLS_WARPS * CLS_RPW - 1) / (CLS_WARPS * CLS_RPW);
-  if (grid > sm_count()) grid = sm_count();      // one resident CTA per SM (217 registers x 256 threads), contiguous rows per warp
+  if (grid > sm_count()) grid = sm_count();      // one resident CTA per SM (~240 registers x 256 threads), contiguous rows per warp
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (C == 2) cls_head_fwd_kernel<2, __half><<<grid, CLS_WARPS * 32, 0, s>>>(static_cast<const __half*>(h), W, b, logits, argmax, rows, H, drop);
-  else if (C == 3) cls_head_fwd_kernel<3, __half><<<grid, CLS_WARPS * 32, 0, s>>>(static_cast<const __half*>(h), W, b, logits, argmax, rows, H, drop);
+  if (C == 2) cls_head_fwd_kernel<2, __half><<<grid, CLS_WARPS * 32, static_cast<size_t>(C) * H * sizeof(float), s>>>(static_cast<const __half*>(h), W, b, logits, argmax, rows, H, drop);
+  else if (C == 3) cls_head_fwd_kernel<3, __half><<<grid, CLS_WARPS * 32, static_cast<size_t>(C) * H * sizeof(float), s>>>(static_cast<const __half*>(h), W, b, logits, argmax, rows, H, drop);
   else return fail(B200_ERR_SHAPE, "cls_head_fwd: C=%d (2 or 3)", C);
   return check_launch("cls_head_fwd_kernel");
 }
@@ -678,3 +679,4 @@ int b200_ponet_mix_bwd(const void* proj, int ld, const void* dout, const float* 
 }  // extern "C"
 
 #include "api_train.inc"
+#include "api_heads.inc"

@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) embed_ln_bwd_kernel(const __ha
 // Each warp owns CLS_RPW consecutive rows per trip and issues ALL of their 128-bit loads before the first use (a row of H = 768
 // halves is only 3 loads per lane: one row per warp left ~1.5 KB in flight per warp and the kernel at 0.14-0.28 of the HBM
 // roofline, profiles/r01g); the C weight rows are loop-invariant and live in registers.  Grid-stride over row groups.
-constexpr int CLS_RPW = 4;
+constexpr int CLS_RPW = 8;            // rows in flight per warp for 2-byte activations (4 for fp32: same bytes)
 constexpr int CLS_WARPS = 8;
 // eight elements as they sit in memory (fp16: one 128-bit word, fp32: two): what a load keeps in flight; converted at the use
 template <typename T> struct Raw8;
@@ -485,55 +485,63 @@ template <int C, typename T>
 __global__ void __launch_bounds__(CLS_WARPS * 32) cls_head_fwd_kernel(const T* __restrict__ h, const float* __restrict__ W,
                                                                        const float* __restrict__ b, float* __restrict__ logits,
                                                                        int32_t* __restrict__ argmax_out, int rows, int H, DropCfg drop) {
-  const int lane = threadIdx.x & 31;
+  extern __shared__ float w_s[];            // [C][H]: the weight rows, read back 128 bits per lane (conflict-free), so that the
+  const int lane = threadIdx.x & 31;        // registers hold activations in flight instead of loop-invariant weights
+  for (int k = threadIdx.x; k < C * H; k += blockDim.x) w_s[k] = W[k];
+  __syncthreads();
   const int nv = lane_vecs(H, lane);
   const uint32_t dseed = drop.seed_base ? drop_seed(drop) : 0u;
-  Vec8 w[C][ROW_MAXV];
-#pragma unroll
-  for (int c = 0; c < C; ++c)
-#pragma unroll
-    for (int i = 0; i < ROW_MAXV; ++i)
-      if (i < nv) w[c][i] = load8(W + static_cast<size_t>(c) * H + (i * 32 + lane) * 8);
   float bias[C];
 #pragma unroll
   for (int c = 0; c < C; ++c) bias[c] = b[c];
-  // every warp owns one contiguous range of rows (so the C weight rows are fetched once per warp, not once per row group:
-  // at 4 rows per group they were as many bytes as the activations) and walks it CLS_RPW rows at a time
+  // every warp owns one contiguous range of rows and walks it CLS_RPW rows at a time, all loads of a trip issued up front
   const int n_warps = gridDim.x * CLS_WARPS, wid = blockIdx.x * CLS_WARPS + (threadIdx.x >> 5);
   const int per_warp = (rows + n_warps - 1) / n_warps;
   const int row_end = min(rows, (wid + 1) * per_warp);
-  for (int row0 = wid * per_warp; row0 < row_end; row0 += CLS_RPW) {
-    Raw8<T> x[CLS_RPW][ROW_MAXV];
+  constexpr int RPW = sizeof(T) == 2 ? CLS_RPW : CLS_RPW / 2;
+  for (int row0 = wid * per_warp; row0 < row_end; row0 += RPW) {
+    Raw8<T> x[RPW][ROW_MAXV];
 #pragma unroll
-    for (int rr = 0; rr < CLS_RPW; ++rr)
+    for (int rr = 0; rr < RPW; ++rr)
 #pragma unroll
       for (int i = 0; i < ROW_MAXV; ++i)
         if (i < nv && row0 + rr < row_end) x[rr][i].load(h + static_cast<size_t>(row0 + rr) * H + (i * 32 + lane) * 8);
+    float acc[RPW][C];
 #pragma unroll
-    for (int rr = 0; rr < CLS_RPW; ++rr) {
+    for (int rr = 0; rr < RPW; ++rr)
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[rr][c] = 0.f;
+#pragma unroll
+    for (int i = 0; i < ROW_MAXV; ++i)
+      if (i < nv) {
+        const int col = (i * 32 + lane) * 8;
+        Vec8 w[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) w[c] = load8(w_s + c * H + col);
+#pragma unroll
+        for (int rr = 0; rr < RPW; ++rr)
+          if (row0 + rr < row_end) {
+            Vec8 xv = x[rr][i].get();
+            if (drop.seed_base) drop8(xv, static_cast<uint32_t>(row0 + rr) * static_cast<uint32_t>(H) + col, dseed, drop);   // bert_for_ts.py:66-67
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[rr][c] = fmaf(xv.v[j], w[c].v[j], acc[rr][c]);
+          }
+      }
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr) {
       const int row = row0 + rr;
       if (row >= row_end) break;
-      float acc[C];
+      float a[C];
 #pragma unroll
-      for (int c = 0; c < C; ++c) acc[c] = 0.f;
-#pragma unroll
-      for (int i = 0; i < ROW_MAXV; ++i)
-        if (i < nv) {
-          Vec8 xv = x[rr][i].get();
-          if (drop.seed_base) drop8(xv, static_cast<uint32_t>(row) * static_cast<uint32_t>(H) + (i * 32 + lane) * 8, dseed, drop);   // bert_for_ts.py:66-67
-#pragma unroll
-          for (int c = 0; c < C; ++c)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[c] = fmaf(xv.v[j], w[c][i].v[j], acc[c]);
-        }
-#pragma unroll
-      for (int c = 0; c < C; ++c) acc[c] = warp_sum(acc[c]) + bias[c];
+      for (int c = 0; c < C; ++c) a[c] = warp_sum(acc[rr][c]) + bias[c];
       if (lane == 0) {
         int best = 0;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-          logits[static_cast<size_t>(row) * C + c] = acc[c];
-          if (acc[c] > acc[best]) best = c;     // first maximum wins, like np.argmax
+          logits[static_cast<size_t>(row) * C + c] = a[c];
+          if (a[c] > a[best]) best = c;     // first maximum wins, like np.argmax
         }
         if (argmax_out) argmax_out[row] = best;
       }

@@ -59,7 +59,30 @@ _PROTOS = {
     "b200_set_hyper": [_p, _f, _f, _f, _f, _f, _f, _f, _p],
     "b200_adamw_step_dev": [_p, _p, _p, _p, _p, _sz, _p, _p, _p],
     "b200_adamw_step_dev_zero": [_p, _p, _p, _p, _p, _sz, _p, _p, _p],
-    # opt-in variants (include/b200enc.h, last section)
+    # loss heads on the labelled rows (csrc/heads.cuh)
+    "b200_heads_compact": [_p, _ll, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p],
+    "b200_heads_gather_keys": [_p, _p, _i, _p, _p],
+    "b200_heads_topic_ids": [_p, _p, _i, _p, _p],
+    "b200_heads_gather_rows": [_p, _p, _i, _i, _p, _p],
+    "b200_heads_scatter_rows": [_p, _p, _i, _i, _f, _p, _p],
+    "b200_heads_segmax_fwd": [_p, _p, _p, _p, _i, _i, _i, _p, _p],
+    "b200_heads_segmax_bwd": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _p, _p],
+    "b200_heads_normalize": [_p, _i, _i, _f, _p, _p, _p],
+    "b200_heads_normalize_bwd": [_p, _p, _p, _i, _i, _f, _p, _p, _p],
+    "b200_heads_pair_cos_fwd": [_p, _p, _p, _p, _p, _i, _i, _f, _p, _p, _i, _p],
+    "b200_heads_pair_cos_bwd": [_p, _p, _p, _p, _p, _p, _i, _i, _f, _p, _p],
+    "b200_heads_bce_fwd": [_p, _p, _i, _p, _p],
+    "b200_heads_bce_bwd": [_p, _p, _i, _f, _p, _p, _p],
+    "b200_heads_cssl_matrix_fwd": [_p, _p, _i, _i, _f, _f, _p, _p, _p, _p, _p, _p],
+    "b200_heads_cssl_matrix_bwd": [_p, _p, _p, _p, _p, _p, _i, _i, _f, _p, _p],
+    "b200_heads_cssl_list_fwd": [_p, _p, _p, _i, _i, _i, _i, _f, _f, _p, _p, _p],
+    "b200_heads_cssl_list_bwd": [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p],
+    "b200_heads_rows_ce_fwd": [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p],
+    "b200_heads_rows_ce_bwd": [_p, _p, _p, _p, _i, _i, _i, _f, _p, _p, _p, _p, _p],
+    "b200_heads_cls_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "b200_heads_focal_stats": [_p, _p, _p, _f, _i, _i, _p, _p],
+    "b200_heads_cls_bwd": [_p, _p, _p, _p, _p, _p, _f, _f, _p, _i, _i, _i, _p, _p, _p, _p],
+    # fused epilogue variants
     "b200_gemm_f16_resadd": [_p, _i, _p, _i, _i, _i, _i, _p, _p, _i, _p, C.c_uint, _f, _p],
     "b200_gemm_f16_dgelu_colsum": [_p, _i, _p, _i, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p],
     "b200_gemm_f16_dgrad_delta": [_p, _i, _p, _i, _i, _i, _i, _p, _i, _p, _i, _p, _i, _i, _p],
