@@ -182,7 +182,7 @@ def time_kernel(torch, fn, iters=20, warmup=3):
     return e0.elapsed_time(e1) / iters * 1e-3
 
 
-def kernel_rooflines(torch, ops, peaks):
+def kernel_rooflines(torch, ops, lib, peaks, dropout):
     """Live per-kernel numbers on the bench shapes (each kernel timed alone with CUDA events on the launch stream;
     operands >> L2 for the big GEMMs)."""
     M, H, I = BATCH * SEQ, 768, 3072
@@ -203,36 +203,62 @@ def kernel_rooflines(torch, ops, peaks):
     except Exception as e:  # noqa: BLE001
         out["gemm_ffn_up_gelu"]["cublas_plain_same_shape_tflops"] = None
         out["gemm_ffn_up_gelu"]["cublas_error"] = f"{type(e).__name__}: {e}"[:200]
+    # the remaining kernels are timed AS THE STEP RUNS THEM: dropout 0.1 where the training step has it, the fused entry points
+    # of the default schedule (in-place residual accumulate, row statistic ready), every buffer allocated outside the timed calls
+    seed = torch.tensor([7], dtype=torch.int32, device=dev)
+    p = float(dropout)
+    drop_h = ops.Dropout(seed, 2, p) if p > 0 else None
+    drop_a = ops.Dropout(seed, 0, p) if p > 0 else None
     w2 = torch.randn(H, I, device=dev, dtype=f16) * 0.02
-    pre = torch.empty(M, H, device=dev, dtype=torch.float32)
+    pre = torch.randn(M, H, device=dev, dtype=torch.float32)
     bo = torch.zeros(H, device=dev)
-    x32 = torch.randn(M, H, device=dev)
-    t = time_kernel(torch, lambda: ops.gemm(h, w2, pre, epilogue=ops.EPI_BIAS_RES32, bias=bo, aux=x32))
-    out["gemm_ffn_down_res"] = {"bound": "tensor", "achieved": flops / t / 1e12, "unit": "TFLOP/s", "ms": t * 1e3}
+    t = time_kernel(torch, lambda: ops.gemm_resadd(h, w2, pre, bo, drop=drop_h))
+    out["gemm_ffn_down_res"] = {"bound": "tensor", "achieved": flops / t / 1e12, "unit": "TFLOP/s", "ms": t * 1e3, "dropout": p}
+    ctx = torch.randn(M, H, device=dev, dtype=f16)
+    wo = torch.randn(H, H, device=dev, dtype=f16) * 0.02
+    t = time_kernel(torch, lambda: ops.gemm_resadd(ctx, wo, pre, bo, drop=drop_h))
+    out["gemm_out_proj_res"] = {"bound": "tensor", "achieved": 2.0 * M * H * H / t / 1e12, "unit": "TFLOP/s", "ms": t * 1e3, "dropout": p}
     gw = torch.zeros(I, H, device=dev)
     t = time_kernel(torch, lambda: ops.gemm(h, x, gw, a_layout=1, b_layout=1, epilogue=ops.EPI_ATOMIC, k_splits=ops.wgrad_splits(I, H, M)))
     out["gemm_wgrad_ffn_up"] = {"bound": "tensor", "achieved": flops / t / 1e12, "unit": "TFLOP/s", "ms": t * 1e3}
+    dz, db1 = torch.empty(M, I, device=dev, dtype=f16), torch.zeros(I, device=dev)
+    t = time_kernel(torch, lambda: ops.gemm_dgelu_colsum(x, w2, z, dz, db1))
+    out["gemm_dgrad_ffn_down_dgelu_colsum"] = {"bound": "tensor", "achieved": flops / t / 1e12, "unit": "TFLOP/s", "ms": t * 1e3}
     qkv = torch.randn(M, 3 * H, device=dev, dtype=f16)
-    ctx = torch.empty(M, H, device=dev, dtype=f16)
     lse = torch.empty(BATCH, 12, SEQ, device=dev)
-    t = time_kernel(torch, lambda: ops.attn_fwd(qkv, qkv, ctx, BATCH, 12, SEQ, SEQ, q_col0=0, k_col0=H, v_col0=2 * H, lse2=lse))
+    t = time_kernel(torch, lambda: ops.attn_fwd(qkv, qkv, ctx, BATCH, 12, SEQ, SEQ, q_col0=0, k_col0=H, v_col0=2 * H, lse2=lse, drop=drop_a))
     aflops = 4.0 * BATCH * SEQ * SEQ * H
-    out["attn_fwd"] = {"bound": "tensor", "achieved": aflops / t / 1e12, "unit": "TFLOP/s", "ms": t * 1e3}
+    out["attn_fwd"] = {"bound": "tensor", "achieved": aflops / t / 1e12, "unit": "TFLOP/s", "ms": t * 1e3, "dropout": p}
     dqkv = torch.empty_like(qkv)
     ws = ops.attn_bwd_workspace(BATCH, 12, SEQ, dev)
-    t = time_kernel(torch, lambda: ops.attn_bwd(qkv, qkv, ctx, ctx, lse, dqkv, dqkv, ws, BATCH, 12, SEQ, SEQ, q_col0=0, k_col0=H,
-                                                v_col0=2 * H, dq_col0=0, dk_col0=H, dv_col0=2 * H))
-    out["attn_bwd"] = {"bound": "tensor", "achieved": 2 * aflops / t / 1e12, "unit": "TFLOP/s", "ms": t * 1e3}
+    dctx = torch.randn(M, H, device=dev, dtype=f16) * 0.1
+    ops.gemm_dgrad_delta(dctx, wo, ctx, dctx.clone(), ws, BATCH, 12, SEQ)          # fills the row statistic once
+    t = time_kernel(torch, lambda: ops.attn_bwd(qkv, qkv, dctx, ctx, lse, dqkv, dqkv, ws, BATCH, 12, SEQ, SEQ, q_col0=0, k_col0=H,
+                                                v_col0=2 * H, dq_col0=0, dk_col0=H, dv_col0=2 * H, drop=drop_a, delta_ready=True))
+    out["attn_bwd"] = {"bound": "tensor", "achieved": 2 * aflops / t / 1e12, "unit": "TFLOP/s", "ms": t * 1e3, "dropout": p,
+                       "includes": "dq_acc memset + attn_bwd3_kernel + dq_cast_kernel (row statistic from the out-proj dgrad epilogue)"}
     g, b = torch.ones(H, device=dev), torch.zeros(H, device=dev)
     y = torch.empty(M, H, device=dev, dtype=f16)
-    t = time_kernel(torch, lambda: ops.layernorm_fwd(pre, g, b, 1e-12, y=y))
-    out["layernorm_fwd"] = {"bound": "hbm", "achieved": M * H * (4 + 2) / t / 1e9, "unit": "GB/s", "ms": t * 1e3}
+    y32 = torch.empty(M, H, device=dev)
     mean, rstd = torch.zeros(M, device=dev), torch.ones(M, device=dev)
-    dxl, dgl, dbl = torch.empty(M, H, device=dev, dtype=f16), torch.zeros(H, device=dev), torch.zeros(H, device=dev)
-    t = time_kernel(torch, lambda: ops.layernorm_bwd(y, pre, mean, rstd, g, dxl, dgl, dbl))
-    out["layernorm_bwd"] = {"bound": "hbm", "achieved": M * H * (2 + 4 + 2) / t / 1e9, "unit": "GB/s", "ms": t * 1e3}
-    W = torch.randn(2, H, device=dev) * 0.02
-    t = time_kernel(torch, lambda: ops.cls_head_fwd(y, W, torch.zeros(2, device=dev)))
+    t = time_kernel(torch, lambda: ops.layernorm_fwd(pre, g, b, 1e-12, y=y, y32=y32, mean=mean, rstd=rstd))
+    out["layernorm_fwd"] = {"bound": "hbm", "achieved": M * H * (4 + 2 + 4) / t / 1e9, "unit": "GB/s", "ms": t * 1e3,
+                            "bytes": "read fp32 pre-LN sum, write fp16 operand copy + fp32 residual copy (7680 B/row)"}
+    dxl, dxd = torch.empty(M, H, device=dev, dtype=f16), torch.empty(M, H, device=dev, dtype=f16)
+    dgl, dbl, dbias = torch.zeros(H, device=dev), torch.zeros(H, device=dev), torch.zeros(H, device=dev)
+    if drop_h is not None:
+        t = time_kernel(torch, lambda: ops.layernorm_bwd(y, pre, mean, rstd, g, dxl, dgl, dbl, dbias=dbias, dx_drop=dxd, drop=drop_h))
+        nbytes = M * H * (2 + 4 + 2 + 2)
+    else:
+        t = time_kernel(torch, lambda: ops.layernorm_bwd(y, pre, mean, rstd, g, dxl, dgl, dbl, dbias=dbias))
+        nbytes = M * H * (2 + 4 + 2)
+    out["layernorm_bwd"] = {"bound": "hbm", "achieved": nbytes / t / 1e9, "unit": "GB/s", "ms": t * 1e3, "dropout": p}
+    W, bcls = torch.randn(2, H, device=dev) * 0.02, torch.zeros(2, device=dev)
+    logits = torch.empty(M, 2, device=dev)
+    import ctypes as C
+    so, st = lib.load(), C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    vp = lambda tns: C.c_void_p(tns.data_ptr())
+    t = time_kernel(torch, lambda: so.b200_cls_head_fwd(vp(y), vp(W), vp(bcls), vp(logits), None, M, H, 2, st), iters=50)
     out["cls_head_fwd"] = {"bound": "hbm", "achieved": (M * H * 2 + M * 8) / t / 1e9, "unit": "GB/s", "ms": t * 1e3}
     for v in out.values():
         peak = peaks["bf16_tflops"] if v["bound"] == "tensor" else peaks["hbm_gbs"]
@@ -347,10 +373,43 @@ def run_b200_arm(args):
     assert sum(l is not None for l in e2e_losses) == args.steps, "every timed step's loss must have been read back"
     loss = trainer.loss_value()
 
+    # sustained: the same resident-batch step for >= args.sustained_s seconds with its own clock sample, so that the fraction of
+    # the SUSTAINED peak is measured under sustained clocks (the 20-step headline lasts 0.3 s and runs at burst clocks)
+    sustained = None
+    if args.sustained_s > 0:
+        n_sus = max(args.steps, int(args.sustained_s / (secs / args.steps)) + 1)
+        sampler3 = ClockSampler(local)
+        if rank == 0:
+            sampler3.start()
+        sus_secs = timed(lambda: trainer.step(*dev), n_sus)
+        sus_clocks = sampler3.stop() if rank == 0 else None
+        sustained = {"value": world * BATCH * n_sus / sus_secs, "unit": "seq/s", "steps": n_sus, "seconds": sus_secs,
+                     "ms_per_step": sus_secs / n_sus * 1e3, "clocks": sus_clocks}
+
+    # padded: SURVEY.md §8d's second input variant — right-padded windows with valid lengths ~U[256, 512] (what the reference's
+    # collator produces for the last window of a document).  Same step on the same shapes; attention skips fully masked key blocks.
+    padded = None
+    if args.padded:
+        phost = synth_batch(torch, BATCH, SEQ, 4321 + rank, padded=True)
+        pdev = [t.cuda() for t in phost]
+        fill = float(phost[1].float().mean())
+        for _ in range(3):                     # (a captured step replays as is: masks and lengths are read from device memory)
+            trainer.step(*pdev)
+        p_secs = timed(lambda: trainer.step(*pdev), args.steps)
+        padded = {"value": world * BATCH * args.steps / p_secs, "unit": "seq/s", "ms_per_step": p_secs / args.steps * 1e3,
+                  "mean_fill": fill, "tokens_per_s": world * BATCH * SEQ * fill * args.steps / p_secs,
+                  "ideal_if_padding_were_free": value / fill,
+                  "note": "rows are padded windows; seq/s counts windows"}
+
     if rank == 0:
         peaks, peak_src = load_peaks()
-        kr = kernel_rooflines(torch, ops, peaks)
+        kr = kernel_rooflines(torch, ops, lib, peaks, args.dropout)
         dom = kr["gemm_ffn_up_gelu"]
+        traffic = {}
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_kernel.json")))
+        except Exception:  # noqa: BLE001
+            pass
         cpu = time_cpu_reference(torch, steps=3, warmup=1, batch=2, dropout=args.dropout) if (world == 1 and not args.no_cpu_baseline) else None
         line = {
             "metric": "512-tok seq/sec BERT-base topic-seg fine-tune", "value": value, "unit": "seq/s", "n_gpus": world,
@@ -365,17 +424,24 @@ def run_b200_arm(args):
             "encoder_flop_util": {"flop_per_seq": FLOP_PER_SEQ, "achieved_tflops_per_gpu": value / world * FLOP_PER_SEQ / 1e12,
                                   "peak_tflops_sustained": peaks["bf16_tflops_sustained"], "peak_source": peak_src,
                                   "frac_of_sustained": value / world * FLOP_PER_SEQ / 1e12 / peaks["bf16_tflops_sustained"]},
-            # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed `ncu --set full` capture
-            # (profiles/r01d_kernel_metrics.md: 29.9 MB read + 141.5 MB written per launch; algorithmic: 25.2 MB x + 4.7 MB W
-            # read, 2 x 100.7 MB written = gelu(z) and gelu'(z))
+            # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this kernel per launch, READ from the committed artefact of
+            # an `ncu --set full` capture (profiles/roofline_kernel.json, written by tools/roofline_traffic.py); null if absent.
+            # Algorithmic bytes: 25.2 MB x + 4.7 MB W read, 2 x 100.7 MB written (gelu(z) and gelu'(z): both are training outputs).
             "roofline": {"kernel": "gemm2_f16_kernel<256,K-major,K-major,BIAS_GELU> (FFN-up 16384x3072x768, 2-CTA tcgen05)",
                          "bound": "tensor", "achieved": dom["achieved"], "peak": dom["peak"], "unit": "TFLOP/s", "frac": dom["frac"],
-                         "traffic": 171.4e6, "peak_source": peak_src + " bf16 burst (kernel timed alone)"},
+                         "traffic": traffic.get("dram_bytes"), "traffic_source": traffic.get("source"),
+                         "algorithmic_bytes": 2 * BATCH * SEQ * 768 + 2 * 768 * 3072 + 2 * 2 * BATCH * SEQ * 3072,
+                         "peak_source": peak_src + " bf16 burst (kernel timed alone)"},
             "kernels": kr,
             "e2e": {"value": e2e_value, "unit": "seq/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                     "ms_per_step": e2e_secs / args.steps * 1e3, "sm_mhz": (e2e_clocks or {}).get("sm_mhz")},
             "gpu_launches": launches, "clocks": clocks, "final_loss": loss,
         }
+        if sustained is not None:
+            sustained["frac_of_sustained_peak"] = sustained["value"] / world * FLOP_PER_SEQ / 1e12 / peaks["bf16_tflops_sustained"]
+            line["sustained"] = sustained
+        if padded is not None:
+            line["padded"] = padded
         if cpu is not None:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
@@ -403,6 +469,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dropout", type=float, default=0.1, help="hidden / attention-probability / classifier dropout (reference default 0.1)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph of the step")
+    ap.add_argument("--sustained-s", type=float, default=3.0, help="length of the extra sustained-clock run in seconds (0 = skip)")
+    ap.add_argument("--no-padded", dest="padded", action="store_false", help="skip the padded-window sub-record")
     args = ap.parse_args()
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
         # convenience: re-launch under torch.distributed.run, one rank per GPU (what the driver does itself)

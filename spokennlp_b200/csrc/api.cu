@@ -498,9 +498,13 @@ int b200_cls_head_fwd_drop(const void* h, const float* W, const float* b, float*
   int grid = (rows + CLS_WARPS * CLS_RPW - 1) / (CLS_WARPS * CLS_RPW);
   if (grid > sm_count()) grid = sm_count();      // one resident CTA per SM (~240 registers x 256 threads), contiguous rows per warp
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (C == 2) cls_head_fwd_kernel<2, __half><<<grid, CLS_WARPS * 32, static_cast<size_t>(C) * H * sizeof(float), s>>>(static_cast<const __half*>(h), W, b, logits, argmax, rows, H, drop);
-  else if (C == 3) cls_head_fwd_kernel<3, __half><<<grid, CLS_WARPS * 32, static_cast<size_t>(C) * H * sizeof(float), s>>>(static_cast<const __half*>(h), W, b, logits, argmax, rows, H, drop);
-  else return fail(B200_ERR_SHAPE, "cls_head_fwd: C=%d (2 or 3)", C);
+  if (C != 2 && C != 3) return fail(B200_ERR_SHAPE, "cls_head_fwd: C=%d (2 or 3)", C);
+  const int nvec = (H + 255) / 256;
+  const size_t wsm = static_cast<size_t>(C) * H * sizeof(float);
+#define B200_CLS(CC, NV) cls_head_fwd_kernel<CC, __half, NV><<<grid, CLS_WARPS * 32, wsm, s>>>(static_cast<const __half*>(h), W, b, logits, argmax, rows, H, drop)
+  if (C == 2) { if (nvec == 1) B200_CLS(2, 1); else if (nvec == 2) B200_CLS(2, 2); else if (nvec == 3) B200_CLS(2, 3); else B200_CLS(2, 4); }
+  else { if (nvec == 1) B200_CLS(3, 1); else if (nvec == 2) B200_CLS(3, 2); else if (nvec == 3) B200_CLS(3, 3); else B200_CLS(3, 4); }
+#undef B200_CLS
   return check_launch("cls_head_fwd_kernel");
 }
 

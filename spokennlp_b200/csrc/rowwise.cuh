@@ -449,8 +449,8 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) embed_ln_bwd_kernel(const __ha
 // Each warp owns CLS_RPW consecutive rows per trip and issues ALL of their 128-bit loads before the first use (a row of H = 768
 // halves is only 3 loads per lane: one row per warp left ~1.5 KB in flight per warp and the kernel at 0.14-0.28 of the HBM
 // roofline, profiles/r01g); the C weight rows are loop-invariant and live in registers.  Grid-stride over row groups.
-constexpr int CLS_RPW = 8;            // rows in flight per warp for 2-byte activations (4 for fp32: same bytes)
-constexpr int CLS_WARPS = 8;
+constexpr int CLS_RPW = 7;            // rows in flight per warp for 2-byte activations (fp32: 4): 16384 rows / (148 SMs x 16 warps) = 6.9,
+constexpr int CLS_WARPS = 16;         // so the bench shape is ONE trip per warp with every load issued up front
 // eight elements as they sit in memory (fp16: one 128-bit word, fp32: two): what a load keeps in flight; converted at the use
 template <typename T> struct Raw8;
 template <> struct Raw8<__half> {
@@ -481,8 +481,9 @@ template <> struct Raw8<float> {
     return r;
   }
 };
-template <int C, typename T>
-__global__ void __launch_bounds__(CLS_WARPS * 32) cls_head_fwd_kernel(const T* __restrict__ h, const float* __restrict__ W,
+// NV = 8-wide vectors per lane = ceil(H / 256): a template parameter so that the in-flight rows cost NV (not ROW_MAXV) registers each
+template <int C, typename T, int NV>
+__global__ void __launch_bounds__(CLS_WARPS * 32, 1) cls_head_fwd_kernel(const T* __restrict__ h, const float* __restrict__ W,
                                                                        const float* __restrict__ b, float* __restrict__ logits,
                                                                        int32_t* __restrict__ argmax_out, int rows, int H, DropCfg drop) {
   extern __shared__ float w_s[];            // [C][H]: the weight rows, read back 128 bits per lane (conflict-free), so that the
@@ -498,13 +499,13 @@ __global__ void __launch_bounds__(CLS_WARPS * 32) cls_head_fwd_kernel(const T* _
   const int n_warps = gridDim.x * CLS_WARPS, wid = blockIdx.x * CLS_WARPS + (threadIdx.x >> 5);
   const int per_warp = (rows + n_warps - 1) / n_warps;
   const int row_end = min(rows, (wid + 1) * per_warp);
-  constexpr int RPW = sizeof(T) == 2 ? CLS_RPW : CLS_RPW / 2;
+  constexpr int RPW = sizeof(T) == 2 ? CLS_RPW : 4;
   for (int row0 = wid * per_warp; row0 < row_end; row0 += RPW) {
-    Raw8<T> x[RPW][ROW_MAXV];
+    Raw8<T> x[RPW][NV];
 #pragma unroll
     for (int rr = 0; rr < RPW; ++rr)
 #pragma unroll
-      for (int i = 0; i < ROW_MAXV; ++i)
+      for (int i = 0; i < NV; ++i)
         if (i < nv && row0 + rr < row_end) x[rr][i].load(h + static_cast<size_t>(row0 + rr) * H + (i * 32 + lane) * 8);
     float acc[RPW][C];
 #pragma unroll
@@ -512,7 +513,7 @@ __global__ void __launch_bounds__(CLS_WARPS * 32) cls_head_fwd_kernel(const T* _
 #pragma unroll
       for (int c = 0; c < C; ++c) acc[rr][c] = 0.f;
 #pragma unroll
-    for (int i = 0; i < ROW_MAXV; ++i)
+    for (int i = 0; i < NV; ++i)
       if (i < nv) {
         const int col = (i * 32 + lane) * 8;
         Vec8 w[C];
