@@ -327,11 +327,10 @@ def run_b200_arm(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) * 1e-3
 
-    # The captured step (NCCL collectives inside the CUDA graph) was measured on 1 and 2 GPUs in round 1; beyond that the
-    # eager step — the same kernels and collectives, launched one by one — is the default until the captured one has been
-    # run there too (B200_DP_GRAPH=1 forces the graph, =0 forces eager).  Eager cost on 2 GPUs: 3 %.
+    # The whole step, NCCL collectives included, is replayed from one CUDA graph at every GPU count (B200_DP_GRAPH=0 forces the
+    # eager step: the same kernels and collectives launched one by one, 3 % slower on 2 GPUs in round 1).
     dp_graph = os.environ.get("B200_DP_GRAPH", "auto")
-    use_graph = not args.no_graph and (dp_graph == "1" or (dp_graph == "auto" and world <= 2))
+    use_graph = not args.no_graph and dp_graph != "0"
     graphed = trainer.capture(*dev) if use_graph else False
     for _ in range(max(3, args.warmup)):
         trainer.step(*dev)
@@ -401,6 +400,21 @@ def run_b200_arm(args):
                   "ideal_if_padding_were_free": value / fill,
                   "note": "rows are padded windows; seq/s counts windows"}
 
+    # the gradient exchange alone (N > 1): one layer bucket and the trailing embeddings bucket, NCCL timed with CUDA events,
+    # bus bandwidth = 2 (N-1)/N x bytes / time (the figure nccl-tests reports; 725 GB/s measured on this pool at 1 GiB)
+    nccl = None
+    if world > 1:
+        nccl = {}
+        g32 = trainer.flat.grad32
+        for name, (lo, hi) in (("layer_bucket", trainer.layer_slices[0]), ("embeddings_bucket", trainer.emb_slice)):
+            buf = torch.zeros(hi - lo, dtype=g32.dtype, device=g32.device)
+            for grp_name, grp in (("default", None), ("background", trainer.bg_group)):
+                if grp_name == "background" and grp is None:
+                    continue
+                t = timed(lambda: dist.all_reduce(buf, group=grp), 10) / 10
+                nccl[f"{name}_{grp_name}"] = {"bytes": buf.numel() * 4, "ms": t * 1e3, "busbw_GBps": 2 * (world - 1) / world * buf.numel() * 4 / t / 1e9}
+        nccl["comm_ctas_background"] = trainer.comm_ctas
+
     if rank == 0:
         peaks, peak_src = load_peaks()
         kr = kernel_rooflines(torch, ops, lib, peaks, args.dropout)
@@ -442,6 +456,8 @@ def run_b200_arm(args):
             line["sustained"] = sustained
         if padded is not None:
             line["padded"] = padded
+        if nccl is not None:
+            line["nccl"] = nccl
         if cpu is not None:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)

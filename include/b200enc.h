@@ -311,6 +311,24 @@ int b200_heads_cls_bwd(const float* h, const float* logits, const int64_t* label
     stats, const float* W, float gamma, float scale, const float* gscale, int rows, int H, int C, float* dh, float* dW, float*
     db, void* stream);
 
+/* ---- packed (variable-length) rows: SURVEY.md §8f rank 2 --------------------------------------------------------------------
+ * The reference right-pads every window to max_seq_length (ts_sentence_seq_labeling.py:862-873) and the encoder computes the
+ * padding.  Packing keeps only the valid tokens: b200_heads_compact on the attention mask (ignore = 0) IS the packer — idx =
+ * flat positions of the valid tokens in row-major order, start = cu_seqlens [B+1], ex / rank = sequence and position of every
+ * packed row, totals = {rows, longest sequence}.  Every row-wise kernel and GEMM then runs on `rows` rows; attention walks
+ * sequence b over rows [cu[b], cu[b+1]) with S_max shaping lse2 and the dropout indices (so a packed run draws the same
+ * attention masks as the padded one).  b200_gather_i64 packs ids / token types / labels; b200_unpack_rows scatters fp32 rows back
+ * into the padded layout. */
+int b200_gather_i64(const int64_t* key, const int32_t* idx, int n, int64_t* out, void* stream);
+int b200_unpack_rows(const float* src, const int32_t* idx, int n, int H, float* dst, void* stream);
+int b200_attn_fwd_varlen(const void* qkv, int ld, int q_col0, int k_col0, int v_col0, const int32_t* cu_seqlens, long long rows, void* ctx,
+                         int ld_out, float* lse2, int B, int heads, int S_max, const uint32_t* seed, unsigned site, float p, void* stream);
+size_t b200_attn_bwd_workspace_varlen(int B, int heads, int S_max, long long rows);
+int b200_attn_bwd_varlen(const void* qkv, int ld, int q_col0, int k_col0, int v_col0, const void* dctx, int ld_dctx, const void* ctx, int ld_ctx,
+                         const int32_t* cu_seqlens, const int32_t* row_ex, const int32_t* row_rank, long long rows, const float* lse2,
+                         void* workspace, void* dqkv, int ld_d, int dq_col0, int dk_col0, int dv_col0, int B, int heads, int S_max,
+                         const uint32_t* seed, unsigned site, float p, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

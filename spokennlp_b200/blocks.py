@@ -104,6 +104,7 @@ class AttnSaved:
     pre: Tensor = None
     mean: Tensor = None
     rstd: Tensor = None
+    pack: Optional[ops.RowIndex] = None          # packed rows
     drop_attn: Optional[ops.Dropout] = None      # dropout on the attention probabilities (bert_model.py:338)
     drop_hidden: Optional[ops.Dropout] = None    # dropout on the output dense, before the residual (bert_model.py:373)
 
@@ -121,10 +122,12 @@ class FfnSaved:
 
 def attn_block_fwd(p: AttnWeights, x16: Tensor, x32: Tensor, B: int, Sq: int, heads: int, eps: float, key_bias, kv_len, *,
                    save: bool, want_probs: bool = False, kv16: Optional[Tensor] = None, Sk: Optional[int] = None,
-                   drop_attn: Optional[ops.Dropout] = None, drop_hidden: Optional[ops.Dropout] = None, owns_residual: bool = False):
+                   drop_attn: Optional[ops.Dropout] = None, drop_hidden: Optional[ops.Dropout] = None, owns_residual: bool = False,
+                   pack: Optional[ops.RowIndex] = None):
     """bert_model.py:259-375 (BertSelfAttention + BertSelfOutput).  Returns (y16, y32, saved, probs).  `probs` are the
-    probabilities BEFORE dropout.  `owns_residual`: the caller hands x32 over (it is not a hidden state anybody keeps)."""
-    H, Mq, dev = heads * 64, B * Sq, x16.device
+    probabilities BEFORE dropout.  `owns_residual`: the caller hands x32 over (it is not a hidden state anybody keeps).
+    `pack`: the rows are PACKED valid tokens (Sq = the padded length)."""
+    H, Mq, dev = heads * 64, x16.shape[0], x16.device
     cross = kv16 is not None
     Sk = Sk if cross else Sq
     if cross:
@@ -140,9 +143,11 @@ def attn_block_fwd(p: AttnWeights, x16: Tensor, x32: Tensor, B: int, Sq: int, he
         cols = dict(q_col0=0, k_col0=H, v_col0=2 * H)
     ctx = torch.empty(Mq, H, dtype=F16, device=dev)
     lse2 = torch.empty(B, heads, Sq, dtype=F32, device=dev) if (save or want_probs) else None
-    ops.attn_fwd(q, kv, ctx, B, heads, Sq, Sk, key_bias=key_bias, kv_len=kv_len, lse2=lse2, drop=drop_attn, **cols)
+    ops.attn_fwd(q, kv, ctx, B, heads, Sq, Sk, key_bias=key_bias, kv_len=kv_len, lse2=lse2, drop=drop_attn, pack=pack, **cols)
     probs = None
     if want_probs:
+        if pack is not None:
+            raise ops.L.B200Error("output_attentions is not available on packed rows")
         probs = ops.attn_probs(q, kv, lse2, B, heads, Sq, Sk, q_col0=cols["q_col0"], k_col0=cols["k_col0"], key_bias=key_bias)
     pre = _out_dense_residual(ctx, p.wo, p.bo, x32, drop_hidden, owns_residual)
     mean = torch.empty(Mq, dtype=F32, device=dev) if save else None
@@ -150,7 +155,7 @@ def attn_block_fwd(p: AttnWeights, x16: Tensor, x32: Tensor, B: int, Sq: int, he
     y32 = torch.empty(Mq, H, dtype=F32, device=dev)
     y16 = ops.layernorm_fwd(pre, p.g, p.b, eps, y32=y32, mean=mean, rstd=rstd)
     sv = AttnSaved(x16=x16, kv16=kv16, q=q, kv=kv if cross else None, ctx=ctx, lse2=lse2, pre=pre, mean=mean, rstd=rstd,
-                   drop_attn=drop_attn, drop_hidden=drop_hidden) if save else None
+                   drop_attn=drop_attn, drop_hidden=drop_hidden, pack=pack) if save else None
     return y16, y32, sv, probs
 
 
@@ -209,13 +214,13 @@ def attn_block_bwd(p: AttnWeights, g: AttnWeights, sv: AttnSaved, dy: Tensor, B:
                    inv_scale, ws: Tensor, *, Sk: Optional[int] = None, dy2: Optional[Tensor] = None):
     """Backward of attn_block_fwd.  Returns (dx, dkv_src): gradient wrt the block input (projection path + residual
     path) and, for cross-attention, wrt the fp16 K/V source (else None)."""
-    H, Mq, dev = heads * 64, B * Sq, dy.device
+    H, Mq, dev = heads * 64, dy.shape[0], dy.device
     cross = sv.kv16 is not None
     Sk = Sk if cross else Sq
     d_pre, d_den = _ln_bwd(dy, dy2, sv, p.g, g.g, g.b, g.bo, inv_scale)
     ops.gemm(d_den, sv.ctx, g.wo, a_layout=1, b_layout=1, epilogue=ops.EPI_ATOMIC, alpha=inv_scale, k_splits=ops.wgrad_splits(H, H, Mq))
     dctx = torch.empty(Mq, H, dtype=F16, device=dev)
-    fused_delta = Experimental.delta and not cross
+    fused_delta = Experimental.delta and not cross and sv.pack is None     # (the fused epilogue maps rows to sequences by division)
     if fused_delta:
         ops.gemm_dgrad_delta(d_den, p.wo, sv.ctx, dctx, ws, B, heads, Sq)
     else:
@@ -224,7 +229,7 @@ def attn_block_bwd(p: AttnWeights, g: AttnWeights, sv: AttnSaved, dy: Tensor, B:
     if not cross:
         dqkv = torch.empty(Mq, 3 * H, dtype=F16, device=dev)
         ops.attn_bwd(sv.q, sv.q, dctx, sv.ctx, sv.lse2, dqkv, dqkv, ws, B, heads, Sq, Sq, q_col0=0, k_col0=H, v_col0=2 * H, dq_col0=0,
-                     dk_col0=H, dv_col0=2 * H, key_bias=key_bias, kv_len=kv_len, drop=sv.drop_attn, delta_ready=fused_delta)
+                     dk_col0=H, dv_col0=2 * H, key_bias=key_bias, kv_len=kv_len, drop=sv.drop_attn, delta_ready=fused_delta, pack=sv.pack)
         ops.colsum(dqkv, g.bqkv, inv_scale)
         ops.gemm(dqkv, sv.x16, g.wqkv, a_layout=1, b_layout=1, epilogue=ops.EPI_ATOMIC, alpha=inv_scale,
                  k_splits=ops.wgrad_splits(3 * H, H, Mq))

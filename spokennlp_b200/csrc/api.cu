@@ -277,24 +277,26 @@ static int gemm_impl(const void* A, int lda, int a_layout, const void* B, int ld
   }
 }
 
-int b200_attn_fwd_drop(const void* q, int ldq, int q_col0, const void* kv, int ldkv, int k_col0, int v_col0, const float* key_bias,
-                       const int32_t* kv_len, void* ctx, int ld_out, float* lse2, int B, int heads, int Sq, int Sk, const uint32_t* seed,
-                       unsigned site, float p, void* stream) {
-  if (B <= 0 || heads <= 0 || Sq <= 0 || Sk <= 0) return fail(B200_ERR_SHAPE, "attn_fwd: empty problem");
+static int attn_fwd_impl(const void* q, int ldq, int q_col0, const void* kv, int ldkv, int k_col0, int v_col0, const float* key_bias,
+                         const int32_t* kv_len, void* ctx, int ld_out, float* lse2, int B, int heads, int Sq, int Sk, const uint32_t* seed,
+                         unsigned site, float p, const int32_t* cu_seqlens, long long rows, void* stream) {
+  if (B <= 0 || heads <= 0 || Sq <= 0 || Sk <= 0 || rows <= 0) return fail(B200_ERR_SHAPE, "attn_fwd: empty problem");
   if ((q_col0 % 8) || (k_col0 % 8) || (v_col0 % 8) || (ld_out % 8)) return fail(B200_ERR_SHAPE, "attn_fwd: column offsets / ld_out must be multiples of 8");
   if (p < 0.f || p > 0.9f) return fail(B200_ERR_SHAPE, "attn_fwd: dropout probability %g outside [0, 0.9]", p);
   const DropCfg drop = make_drop_attn(seed, site, p);
+  const uint64_t rq = cu_seqlens ? static_cast<uint64_t>(rows) : static_cast<uint64_t>(B) * Sq;
+  const uint64_t rk = cu_seqlens ? static_cast<uint64_t>(rows) : static_cast<uint64_t>(B) * Sk;
   CUtensorMap tq, tkv, to;
-  int rc = get_tmap(q, static_cast<uint64_t>(B) * Sq, ldq, ldq, ATT_BQ, &tq);
+  int rc = get_tmap(q, rq, ldq, ldq, ATT_BQ, &tq);
   if (rc) return rc;
-  rc = get_tmap(kv, static_cast<uint64_t>(B) * Sk, ldkv, ldkv, ATT_BK, &tkv);
+  rc = get_tmap(kv, rk, ldkv, ldkv, ATT_BK, &tkv);
   if (rc) return rc;
-  // context output fp16 [B*Sq, ld_out], 64 x 32 patches (one per softmax warp)
-  if ((rc = get_tmap(ctx, static_cast<uint64_t>(B) * Sq, ld_out, ld_out, 32, &to))) return rc;
+  // context output fp16 [rows, ld_out], 64 x 32 patches (one per softmax warp)
+  if ((rc = get_tmap(ctx, rq, ld_out, ld_out, 32, &to))) return rc;
   static int e0 = set_smem(attn_fwd3_kernel<false>, AttnFwd3Smem::TOTAL);
   static int e1 = set_smem(attn_fwd3_kernel<true>, AttnFwd3Smem::TOTAL);
   if (e0 != B200_OK || e1 != B200_OK) return e0 ? e0 : e1;
-  AttnFwdArgs a{B, heads, Sq, Sk, q_col0, k_col0, v_col0, key_bias, kv_len, static_cast<__half*>(ctx), ld_out, lse2, kAttScaleLog2, drop};
+  AttnFwdArgs a{B, heads, Sq, Sk, q_col0, k_col0, v_col0, key_bias, kv_len, static_cast<__half*>(ctx), ld_out, lse2, kAttScaleLog2, drop, cu_seqlens};
   // persistent kernel, one CTA per SM walking (batch, head, 256-query pair) items
   const long long items = static_cast<long long>((Sq + 2 * ATT_BQ - 1) / (2 * ATT_BQ)) * heads * B;
   const int ctas = items < sm_count() ? static_cast<int>(items) : sm_count();
@@ -302,6 +304,20 @@ int b200_attn_fwd_drop(const void* q, int ldq, int q_col0, const void* kv, int l
   if (drop.seed_base) attn_fwd3_kernel<true><<<ctas, ATTP_THREADS, AttnFwd3Smem::TOTAL, st>>>(tq, tkv, to, a);
   else attn_fwd3_kernel<false><<<ctas, ATTP_THREADS, AttnFwd3Smem::TOTAL, st>>>(tq, tkv, to, a);
   return check_launch("attn_fwd3_kernel");
+}
+
+int b200_attn_fwd_drop(const void* q, int ldq, int q_col0, const void* kv, int ldkv, int k_col0, int v_col0, const float* key_bias,
+                       const int32_t* kv_len, void* ctx, int ld_out, float* lse2, int B, int heads, int Sq, int Sk, const uint32_t* seed,
+                       unsigned site, float p, void* stream) {
+  return attn_fwd_impl(q, ldq, q_col0, kv, ldkv, k_col0, v_col0, key_bias, kv_len, ctx, ld_out, lse2, B, heads, Sq, Sk, seed, site, p, nullptr,
+                       static_cast<long long>(B) * Sq, stream);
+}
+
+int b200_attn_fwd_varlen(const void* qkv, int ld, int q_col0, int k_col0, int v_col0, const int32_t* cu_seqlens, long long rows, void* ctx, int ld_out,
+                         float* lse2, int B, int heads, int S_max, const uint32_t* seed, unsigned site, float p, void* stream) {
+  if (!cu_seqlens) return fail(B200_ERR_SHAPE, "attn_fwd_varlen: cu_seqlens is required");
+  return attn_fwd_impl(qkv, ld, q_col0, qkv, ld, k_col0, v_col0, nullptr, nullptr, ctx, ld_out, lse2, B, heads, S_max, S_max, seed, site, p,
+                       cu_seqlens, rows, stream);
 }
 
 int b200_attn_fwd(const void* q, int ldq, int q_col0, const void* kv, int ldkv, int k_col0, int v_col0, const float* key_bias,

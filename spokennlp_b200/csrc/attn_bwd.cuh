@@ -25,15 +25,19 @@ struct AttnBwdArgs {
   float scale_log2;                 // log2(e)/sqrt(d)
   float inv_sqrt_d;
   DropCfg drop;                     // the forward's attention-probability dropout (mask regenerated here)
+  const int* cu_seqlens;            // [B+1] or null: packed rows, as in AttnFwdArgs (Sq / Sk = the maximum length)
 };
 
 // delta[b,h,q] = sum_d dO[q, 64h+d] * O[q, 64h+d]   (one warp per token row; 8 lanes share a head)
+// Packed rows (row_ex / row_rank non-null): row r belongs to sequence row_ex[r] at position row_rank[r]; delta keeps its padded
+// [B, heads, Sq] layout.
 __global__ void __launch_bounds__(128) attn_delta_kernel(const __half* __restrict__ dout, int ld_do, const __half* __restrict__ out, int ld_o,
-                                                         float* __restrict__ delta, int B, int heads, int Sq) {
+                                                         float* __restrict__ delta, int rows, int heads, int Sq,
+                                                         const int* __restrict__ row_ex, const int* __restrict__ row_rank) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (row >= B * Sq) return;
-  const int b = row / Sq, q = row % Sq;
+  if (row >= rows) return;
+  const int b = row_ex ? row_ex[row] : row / Sq, q = row_rank ? row_rank[row] : row % Sq;
   const int nvec = heads * 8;
   for (int v = lane; v < nvec; v += 32) {
     const uint4 ra = *reinterpret_cast<const uint4*>(dout + static_cast<size_t>(row) * ld_do + v * 8);

@@ -66,7 +66,6 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(grad_done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nq = (a.Sq + ATT_BQ - 1) / ATT_BQ;
   const int n_kb = (a.Sk + ATT_BK - 1) / ATT_BK;
   const int n_items = a.B * a.heads * n_kb;
 
@@ -102,6 +101,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
   struct Item {
     int b, h, k0, kv_len;
+    int qrow0, krow0, sq, sk, nq;     // first row of this sequence in the Q / KV buffers, its query / key counts, query blocks
     bool general_bias, dead;
   };
   auto decode = [&](int item) {
@@ -110,10 +110,23 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     it.h = bh % a.heads;
     it.b = bh / a.heads;
     it.k0 = kbk * ATT_BK;
-    int kv = a.kv_len ? a.kv_len[it.b] : a.Sk;
-    it.general_bias = a.key_bias != nullptr && (a.kv_len == nullptr || kv < 0);   // see attn_fwd.cuh
-    it.kv_len = max(1, min(kv < 0 ? -kv : kv, a.Sk));
-    it.dead = it.k0 >= it.kv_len;      // every key of this block is masked: dK = dV = 0, no dQ contribution
+    if (a.cu_seqlens) {               // packed rows: the sequence's own length bounds queries and keys
+      const int r0 = a.cu_seqlens[it.b], len = a.cu_seqlens[it.b + 1] - r0;
+      it.qrow0 = it.krow0 = r0;
+      it.sq = it.sk = len;
+      it.general_bias = false;
+      it.kv_len = max(1, len);
+    } else {
+      it.qrow0 = it.b * a.Sq;
+      it.krow0 = it.b * a.Sk;
+      it.sq = a.Sq;
+      it.sk = a.Sk;
+      int kv = a.kv_len ? a.kv_len[it.b] : a.Sk;
+      it.general_bias = a.key_bias != nullptr && (a.kv_len == nullptr || kv < 0);   // see attn_fwd.cuh
+      it.kv_len = max(1, min(kv < 0 ? -kv : kv, a.Sk));
+    }
+    it.nq = (it.sq + ATT_BQ - 1) / ATT_BQ;
+    it.dead = it.k0 >= it.kv_len || it.nq == 0;      // every key of this block is masked: dK = dV = 0, no dQ contribution
     return it;
   };
 
@@ -128,16 +141,16 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           mbar_wait(&qdo_empty[st], ph ^ 1);
           mbar_expect_tx(&qdo_full[st], 2 * S::T);
           uint8_t* dst = smem + S::OFF_QDO + st * 2 * S::T;
-          tma_load_2d(dst, &tmQ, &qdo_full[st], a.q_col0 + it.h * ATT_D, it.b * a.Sq + i * ATT_BQ);
-          tma_load_2d(dst + S::T, &tmDO, &qdo_full[st], it.h * ATT_D, it.b * a.Sq + i * ATT_BQ);
+          tma_load_2d(dst, &tmQ, &qdo_full[st], a.q_col0 + it.h * ATT_D, it.qrow0 + i * ATT_BQ);
+          tma_load_2d(dst + S::T, &tmDO, &qdo_full[st], it.h * ATT_D, it.qrow0 + i * ATT_BQ);
           ++qs;
         };
         load_qdo(0);                    // the first Q / dO block does not wait for the item switch ...
         mbar_wait(kv_empty, (n & 1) ^ 1);   // ... K / V do: the previous item's last gradient MMAs read them
         mbar_expect_tx(kv_full, 2 * S::T);
-        tma_load_2d(smem + S::OFF_K, &tmKV, kv_full, a.k_col0 + it.h * ATT_D, it.b * a.Sk + it.k0);
-        tma_load_2d(smem + S::OFF_V, &tmKV, kv_full, a.v_col0 + it.h * ATT_D, it.b * a.Sk + it.k0);
-        for (int i = 1; i < nq; ++i) load_qdo(i);
+        tma_load_2d(smem + S::OFF_K, &tmKV, kv_full, a.k_col0 + it.h * ATT_D, it.krow0 + it.k0);
+        tma_load_2d(smem + S::OFF_V, &tmKV, kv_full, a.v_col0 + it.h * ATT_D, it.krow0 + it.k0);
+        for (int i = 1; i < it.nq; ++i) load_qdo(i);
         ++n;
       }
     }
@@ -163,6 +176,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const Item it = decode(item);
       if (it.dead) continue;
+      const int nq = it.nq;
       mbar_wait(kv_full, n & 1);
       mbar_wait(&qdo_full[qs % NST], (qs / NST) & 1);
       if (ir > 0) mbar_wait(&s_free[0], (ir - 1) & 1);      // group 0 holds its last block in registers
@@ -235,10 +249,10 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     uint32_t ir = 0;                              // query blocks processed so far (barrier phases, dQ buffer)
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const Item it = decode(item);
-      const int b = it.b, h = it.h, k0 = it.k0, kv_len = it.kv_len;
+      const int b = it.b, h = it.h, k0 = it.k0, kv_len = it.kv_len, nq = it.nq;
       if (it.dead) {
-        if (warp < 6 && k0 + r < a.Sk) {
-          const size_t row = static_cast<size_t>(b) * a.Sk + k0 + r;
+        if (warp < 6 && k0 + r < it.sk) {
+          const size_t row = static_cast<size_t>(it.krow0) + k0 + r;
           const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -275,21 +289,21 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_reduce_add_2d(&tmDQ, dqs, h * ATT_D + g * 32, b * a.Sq + i * ATT_BQ + qd * 32);
+          tma_reduce_add_2d(&tmDQ, dqs, h * ATT_D + g * 32, it.qrow0 + i * ATT_BQ + qd * 32);
           tma_commit_group();
         }
       };
 
       // per-query statistics of block 0 (queries past Sq: lse = +inf -> P = 0, delta = 0)
-      float lse_n = (r < a.Sq) ? a.lse2[stat_base + r] : INFINITY;
-      float del_n = (r < a.Sq) ? a.delta[stat_base + r] : 0.f;
+      float lse_n = (r < it.sq) ? a.lse2[stat_base + r] : INFINITY;
+      float del_n = (r < it.sq) ? a.delta[stat_base + r] : 0.f;
       for (int i = 0; i < nq; ++i, ++ir) {
         const float neg_lse = -lse_n, ndc = -del_n * a.inv_sqrt_d;
         const int q = i * ATT_BQ + r;
         if (i + 1 < nq) {                         // prefetch the next block's statistics
           const int qn = q + ATT_BQ;
-          lse_n = (qn < a.Sq) ? a.lse2[stat_base + qn] : INFINITY;
-          del_n = (qn < a.Sq) ? a.delta[stat_base + qn] : 0.f;
+          lse_n = (qn < it.sq) ? a.lse2[stat_base + qn] : INFINITY;
+          del_n = (qn < it.sq) ? a.delta[stat_base + qn] : 0.f;
         }
         mbar_wait(&s_full[g], ir & 1);
         tc_fence_after();
@@ -369,7 +383,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       // dV, dK: TMEM lane == key row; this thread owns 32 of the 64 d columns.  A full key block leaves as two TMA stores from
       // the dQ staging patches ([128 keys][64 d] fp16 each); a block that straddles the end of the batch element stores directly.
       const int key = k0 + r;
-      const bool full_block = k0 + ATT_BK <= a.Sk;
+      const bool full_block = k0 + ATT_BK <= it.sk;      // (packed rows: a tile must not run into the next sequence)
       if (full_block) {
         if (lane == 0) tma_wait_group_read<0>();  // every warp's last dQ reduction has read its patch ...
         asm volatile("bar.sync 1, 256;" ::: "memory");   // ... before anybody overwrites it
@@ -390,8 +404,8 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           const uint32_t row_s = smem_u32(smem + S::OFF_DQS + which * S::T) + r * 128;
 #pragma unroll
           for (int e = 0; e < 4; ++e) sts128(row_s + (((g * 4 + e) ^ (r & 7)) << 4), w[4 * e], w[4 * e + 1], w[4 * e + 2], w[4 * e + 3]);
-        } else if (key < a.Sk) {
-          __half* dst = (which == 0 ? a.dv + a.dv_col0 : a.dk + a.dk_col0) + (static_cast<size_t>(b) * a.Sk + key) * a.ld_dkv + h * ATT_D + g * 32;
+        } else if (key < it.sk) {
+          __half* dst = (which == 0 ? a.dv + a.dv_col0 : a.dk + a.dk_col0) + (static_cast<size_t>(it.krow0) + key) * a.ld_dkv + h * ATT_D + g * 32;
 #pragma unroll
           for (int e = 0; e < 4; ++e) *reinterpret_cast<uint4*>(dst + e * 8) = make_uint4(w[4 * e], w[4 * e + 1], w[4 * e + 2], w[4 * e + 3]);
         }
@@ -401,8 +415,8 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         fence_proxy_async_smem();
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (t == 0) {
-          tma_store_2d(&tmDKV, smem + S::OFF_DQS, a.dv_col0 + h * ATT_D, b * a.Sk + k0);
-          tma_store_2d(&tmDKV, smem + S::OFF_DQS + S::T, a.dk_col0 + h * ATT_D, b * a.Sk + k0);
+          tma_store_2d(&tmDKV, smem + S::OFF_DQS, a.dv_col0 + h * ATT_D, it.krow0 + k0);
+          tma_store_2d(&tmDKV, smem + S::OFF_DQS + S::T, a.dk_col0 + h * ATT_D, it.krow0 + k0);
           tma_commit_group();
         }
       }

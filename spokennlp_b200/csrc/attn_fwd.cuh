@@ -29,6 +29,10 @@ struct AttnFwdArgs {
   float* lse2;                       // [B, heads, Sq] log2-domain log-sum-exp (for backward), may be null
   float scale_log2;                  // log2(e) / sqrt(d)
   DropCfg drop;                      // attention-probability dropout (bert_model.py:338), off when seed_base is null
+  const int* cu_seqlens;             // [B+1] or null.  Non-null = PACKED rows: sequence b occupies rows
+                                     // [cu[b], cu[b+1]) of the Q / KV / output buffers, its length is both its query and its key
+                                     // count, and Sq / Sk are the MAXIMUM length (they still shape lse2 / the dropout indices, so a
+                                     // packed run draws the same masks as the padded one).  Self-attention only.
 };
 
 // Materialised attention probabilities for `output_attentions=True` (ditto/evaluation_ditto.py:121-127 reads the

@@ -100,7 +100,8 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   // per-item geometry, identical in every role
   struct Item {
     int b, h, q0, kv_len, n_blocks;
-    bool tileB, general_bias;
+    int qrow0, krow0, sq;              // first row of this sequence in the Q / KV buffers, its query count
+    bool tileB, general_bias, skip;
   };
   auto decode = [&](int item) {
     Item it;
@@ -108,10 +109,23 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     it.h = bh % a.heads;
     it.b = bh / a.heads;
     it.q0 = qp * 2 * ATT_BQ;
-    it.tileB = (it.q0 + ATT_BQ) < a.Sq;
-    int kv = a.kv_len ? a.kv_len[it.b] : a.Sk;
-    it.general_bias = a.key_bias != nullptr && (a.kv_len == nullptr || kv < 0);   // see attn_fwd.cuh
-    it.kv_len = max(1, min(kv < 0 ? -kv : kv, a.Sk));
+    if (a.cu_seqlens) {                // packed rows: the sequence's own length bounds queries and keys
+      const int r0 = a.cu_seqlens[it.b], len = a.cu_seqlens[it.b + 1] - r0;
+      it.qrow0 = it.krow0 = r0;
+      it.sq = len;
+      it.skip = it.q0 >= len;          // a shorter sequence has fewer query pairs than the longest one
+      it.general_bias = false;
+      it.kv_len = max(1, len);
+    } else {
+      it.qrow0 = it.b * a.Sq;
+      it.krow0 = it.b * a.Sk;
+      it.sq = a.Sq;
+      it.skip = false;
+      int kv = a.kv_len ? a.kv_len[it.b] : a.Sk;
+      it.general_bias = a.key_bias != nullptr && (a.kv_len == nullptr || kv < 0);   // see attn_fwd.cuh
+      it.kv_len = max(1, min(kv < 0 ? -kv : kv, a.Sk));
+    }
+    it.tileB = (it.q0 + ATT_BQ) < it.sq;
     it.n_blocks = (it.kv_len + ATT_BK - 1) / ATT_BK;
     return it;
   };
@@ -121,20 +135,21 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       uint32_t n = 0, kb = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
         const Item it = decode(item);
+        if (it.skip) { --n; continue; }          // (the loop header still counts it)
         const uint32_t buf = n & 1;
         mbar_wait(&q_empty[buf], ((n >> 1) & 1) ^ 1);
         mbar_expect_tx(&q_full[buf], (it.tileB ? 2 : 1) * S::TILE);
         uint8_t* qd = smem + S::OFF_Q + buf * 2 * S::TILE;
-        tma_load_2d(qd, &tmQ, &q_full[buf], a.q_col0 + it.h * ATT_D, it.b * a.Sq + it.q0);
-        if (it.tileB) tma_load_2d(qd + S::TILE, &tmQ, &q_full[buf], a.q_col0 + it.h * ATT_D, it.b * a.Sq + it.q0 + ATT_BQ);
+        tma_load_2d(qd, &tmQ, &q_full[buf], a.q_col0 + it.h * ATT_D, it.qrow0 + it.q0);
+        if (it.tileB) tma_load_2d(qd + S::TILE, &tmQ, &q_full[buf], a.q_col0 + it.h * ATT_D, it.qrow0 + it.q0 + ATT_BQ);
         for (int j = 0; j < it.n_blocks; ++j, ++kb) {
           const uint32_t s = kb & 1, ph = (kb >> 1) & 1;
           mbar_wait(&k_empty[s], ph ^ 1);
           mbar_expect_tx(&k_full[s], S::TILE);
-          tma_load_2d(smem + S::OFF_K + s * S::TILE, &tmKV, &k_full[s], a.k_col0 + it.h * ATT_D, it.b * a.Sk + j * ATT_BK);
+          tma_load_2d(smem + S::OFF_K + s * S::TILE, &tmKV, &k_full[s], a.k_col0 + it.h * ATT_D, it.krow0 + j * ATT_BK);
           mbar_wait(&v_empty[s], ph ^ 1);
           mbar_expect_tx(&v_full[s], S::TILE);
-          tma_load_2d(smem + S::OFF_V + s * S::TILE, &tmKV, &v_full[s], a.v_col0 + it.h * ATT_D, it.b * a.Sk + j * ATT_BK);
+          tma_load_2d(smem + S::OFF_V + s * S::TILE, &tmKV, &v_full[s], a.v_col0 + it.h * ATT_D, it.krow0 + j * ATT_BK);
         }
       }
     }
@@ -148,6 +163,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     uint32_t n = 0, kb = 0, t = 0;     // items seen, K/V ring position, blocks this tile has processed
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
       const Item it = decode(item);
+      if (it.skip) { --n; continue; }
       const uint32_t buf = n & 1;
       const int nb = it.n_blocks;
       if (x == 1 && !it.tileB) {       // no second tile in this item: keep the shared rings' arrival counts balanced
@@ -221,7 +237,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     uint32_t t = 0;                               // blocks this tile has processed (barrier phases)
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const Item it = decode(item);
-      if (x == 1 && !it.tileB) continue;
+      if (it.skip || (x == 1 && !it.tileB)) continue;
       const int b = it.b, h = it.h, kv_len = it.kv_len, n_blocks = it.n_blocks;
       const int qrow = it.q0 + x * ATT_BQ + r;
       // dropout: quad index of (row, key) = rowbase + key / 4; (quad + seed) * C1 is walked by adding multiples of C1 (ptx.cuh: drop4_z)
@@ -354,21 +370,21 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         w[k] = *reinterpret_cast<const uint32_t*>(&hv);
       }
       const int wrow0 = it.q0 + x * ATT_BQ + qd * 32;        // first query row of this warp
-      if (wrow0 + 32 <= a.Sq) {                              // one TMA store per warp from a swizzled staging patch
+      if (wrow0 + 32 <= it.sq) {                             // one TMA store per warp from a swizzled staging patch (never across a sequence end)
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) sts128(p_row + ((ch ^ (r & 7)) << 4), w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&tmO, smem + S::OFF_P + x * S::P_BYTES + qd * 32 * 128, h * ATT_D, b * a.Sq + wrow0);
+          tma_store_2d(&tmO, smem + S::OFF_P + x * S::P_BYTES + qd * 32 * 128, h * ATT_D, it.qrow0 + wrow0);
           tma_commit_group();
         }
-      } else if (qrow < a.Sq) {
-        __half* dst = a.out + (static_cast<size_t>(b) * a.Sq + qrow) * a.ld_out + h * ATT_D;
+      } else if (qrow < it.sq) {
+        __half* dst = a.out + (static_cast<size_t>(it.qrow0) + qrow) * a.ld_out + h * ATT_D;
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) *reinterpret_cast<uint4*>(dst + ch * 8) = make_uint4(w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
       }
-      if (qrow < a.Sq && a.lse2) a.lse2[(static_cast<size_t>(b) * a.heads + h) * a.Sq + qrow] = (l > 0.f) ? (m + log2f(l)) : NEG_INF;
+      if (qrow < it.sq && a.lse2) a.lse2[(static_cast<size_t>(b) * a.heads + h) * a.Sq + qrow] = (l > 0.f) ? (m + log2f(l)) : NEG_INF;
     }
     if (lane == 0) tma_wait_group_read<0>();      // staging memory stays valid until the bulk stores have read it
   }

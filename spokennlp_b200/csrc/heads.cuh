@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(1024) heads_compact_finish_kernel(const int32_
       acc += cnt[b];
       mx = max(mx, cnt[b]);
     }
+    start[B] = acc;                     // start has B + 1 entries: it doubles as cu_seqlens of the packed layout
     total_s = acc;
     max_s = mx;
     totals[0] = acc;
@@ -84,6 +85,21 @@ __global__ void __launch_bounds__(1024) heads_compact_finish_kernel(const int32_
 __global__ void heads_gather_keys_kernel(const int64_t* __restrict__ key, const int32_t* __restrict__ idx, int n, int32_t* __restrict__ vals) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) vals[i] = static_cast<int32_t>(key[idx[i]]);
+}
+
+// out[i] = key[idx[i]] (int64 -> int64): token ids / token types / labels of the packed rows
+__global__ void heads_gather_i64_kernel(const int64_t* __restrict__ key, const int32_t* __restrict__ idx, int n, int64_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = key[idx[i]];
+}
+// dst[idx[i], :] = src[i, :] (fp32 rows): packed activations back into the padded [B*S, H] layout the HF interface returns
+__global__ void __launch_bounds__(HD_WARPS * 32) heads_unpack_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, int n, int H,
+                                                                         float* __restrict__ dst) {
+  const int row = blockIdx.x * HD_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float4* a = reinterpret_cast<const float4*>(src + static_cast<size_t>(row) * H);
+  float4* d = reinterpret_cast<float4*>(dst + static_cast<size_t>(idx[row]) * H);
+  for (int c = lane; c < H / 4; c += 32) d[c] = a[c];
 }
 
 // topic ids of the labelled rows (cssl.py:252-263 / utils.py:29-40): consecutive rows share an id until a row labelled 0

@@ -144,6 +144,7 @@ class Saved:
     ids: Optional[Tensor] = None; tt: Optional[Tensor] = None; pos: Optional[Tensor] = None
     inputs_embeds: Optional[Tensor] = None
     key_bias: Optional[Tensor] = None; kv_len: Optional[Tensor] = None
+    pack: Optional[ops.RowIndex] = None
     layers: List[LayerSaved] = field(default_factory=list)
     out: Tensor = None
     drop_emb: Optional[ops.Dropout] = None
@@ -205,40 +206,47 @@ class EncoderEngine:
         return c[key]
 
     # ---- forward -----------------------------------------------------------------------------------------------
-    def embed(self, ids, tt, pos, inputs_embeds, B, S, drop=None):
-        """Returns the embedding output twice: fp16 (tensor-core operand) and fp32 (residual stream)."""
+    def embed(self, ids, tt, pos, inputs_embeds, B, S, drop=None, rows: Optional[int] = None):
+        """Returns the embedding output twice: fp16 (tensor-core operand) and fp32 (residual stream).  `rows`: packed row count."""
         f = self.flat
-        y32 = torch.empty(B * S, self.H, dtype=torch.float32, device=f.flat32.device)
+        M = B * S if rows is None else rows
+        y32 = torch.empty(M, self.H, dtype=torch.float32, device=f.flat32.device)
         y16 = ops.embed_ln_fwd(ids, tt, pos, inputs_embeds, f.view32(EMB_NAMES[0]), f.view32(EMB_NAMES[1]),
-                               f.view32(EMB_NAMES[2]), f.view32(EMB_NAMES[3]), f.view32(EMB_NAMES[4]), self.eps, B * S, S,
+                               f.view32(EMB_NAMES[2]), f.view32(EMB_NAMES[3]), f.view32(EMB_NAMES[4]), self.eps, M, S,
                                self.H, y32=y32, drop=drop)
         return y16, y32
 
     def layer_forward(self, p: LayerViews, x: Tensor, x32: Tensor, B: int, S: int, key_bias, kv_len, save: bool,
-                      want_probs: bool = False, drop: Optional[DropPlan] = None, index: int = 0, owns_input: bool = False):
+                      want_probs: bool = False, drop: Optional[DropPlan] = None, index: int = 0, owns_input: bool = False,
+                      pack: Optional[ops.RowIndex] = None):
         """One BertLayer (bert_model.py:518-553).  x: fp16 layer input (GEMM operand), x32: the same activations in fp32
         (residual stream: keeping the skip connection un-rounded holds the 12-layer hidden-state error under 1e-3)."""
         d = (lambda k: drop.layer(index, k)) if drop is not None else (lambda k: None)
         a16, a32, sva, probs = attn_block_fwd(p.attn, x, x32, B, S, self.heads, self.eps, key_bias, kv_len, save=save,
                                               want_probs=want_probs, drop_attn=d(DropPlan.ATTN), drop_hidden=d(DropPlan.ATTN_OUT),
-                                              owns_residual=owns_input)
+                                              owns_residual=owns_input, pack=pack)
         # a32 (the attention block's fp32 output) is never handed out, so the FFN block always owns its residual
         y16, y32, svf = ffn_block_fwd(p.ffn, a16, a32, self.eps, save=save, drop_hidden=d(DropPlan.FFN_OUT), owns_residual=True)
         return y16, y32, (LayerSaved(attn=sva, ffn=svf) if save else None), probs
 
     def forward(self, ids, tt, pos, inputs_embeds, key_bias, kv_len, B: int, S: int, *, save: bool,
-                want_hidden: bool = False, want_probs: bool = False, drop: Optional[DropPlan] = None):
-        """`drop` (training only) turns on the reference's dropout sites; None = eval / p=0."""
+                want_hidden: bool = False, want_probs: bool = False, drop: Optional[DropPlan] = None,
+                pack: Optional[ops.RowIndex] = None):
+        """`drop` (training only) turns on the reference's dropout sites; None = eval / p=0.  `pack` (ops.compact_rows of the
+        attention mask): ids / tt / pos are the PACKED valid tokens (pos = position inside the sequence) and every kernel runs on
+        pack.n rows instead of B*S; key_bias / kv_len must be None (the sequence lengths ARE the mask)."""
         self.flat.sync_half()
+        if pack is not None and (key_bias is not None or kv_len is not None or inputs_embeds is not None or pos is None):
+            raise ops.L.B200Error("packed rows: pass packed ids / token types / positions and no key mask")
         drop_emb = drop.at(DropPlan.EMB, drop.p_hidden) if drop is not None else None
-        x, x32 = self.embed(ids, tt, pos, inputs_embeds, B, S, drop=drop_emb)
+        x, x32 = self.embed(ids, tt, pos, inputs_embeds, B, S, drop=drop_emb, rows=None if pack is None else pack.n)
         saved = Saved(B=B, S=S, ids=ids, tt=tt, pos=pos, inputs_embeds=inputs_embeds if ids is None else None, key_bias=key_bias,
-                      kv_len=kv_len, drop_emb=drop_emb) if save else None
+                      kv_len=kv_len, pack=pack, drop_emb=drop_emb) if save else None
         hiddens, probs_all = ([x32] if want_hidden else None), ([] if want_probs else None)
         for i in range(self.L):
             # a layer input that is also returned as a hidden state must survive the layer (blocks.Experimental.resadd)
             x, x32, sv, probs = self.layer_forward(self.layer(i), x, x32, B, S, key_bias, kv_len, save, want_probs, drop, i,
-                                                   owns_input=not want_hidden)
+                                                   owns_input=not want_hidden, pack=pack)
             if save:
                 saved.layers.append(sv)
             if want_hidden:
@@ -266,7 +274,8 @@ class EncoderEngine:
         (fp32 [B*S, H]) is returned if asked for."""
         B, S = saved.B, saved.S
         f = self.flat
-        ws = ops.attn_bwd_workspace(B, self.heads, S, dy.device)
+        rows = B * S if saved.pack is None else saved.pack.n
+        ws = ops.attn_bwd_workspace(B, self.heads, S, dy.device, rows=None if saved.pack is None else rows)
         for i in reversed(range(self.L)):
             dy = self.layer_backward(self.layer(i), self.layer_grads(i), saved.layers[i], dy, B, S, saved.key_bias,
                                      saved.kv_len, inv_scale, ws)
@@ -276,10 +285,10 @@ class EncoderEngine:
         d_emb = None
         if embeddings and (saved.ids is not None or saved.inputs_embeds is not None):
             if saved.ids is None and want_d_inputs_embeds:
-                d_emb = torch.empty(B * S, self.H, dtype=torch.float32, device=dy.device)
+                d_emb = torch.empty(rows, self.H, dtype=torch.float32, device=dy.device)
             ops.embed_ln_bwd(dy, None, saved.ids, saved.tt, saved.pos, f.view32(EMB_NAMES[0]), f.view32(EMB_NAMES[1]),
                              f.view32(EMB_NAMES[2]), f.view32(EMB_NAMES[3]), f.viewg(EMB_NAMES[0]), f.viewg(EMB_NAMES[1]),
-                             f.viewg(EMB_NAMES[2]), f.viewg(EMB_NAMES[3]), f.viewg(EMB_NAMES[4]), inv_scale, self.eps, B * S,
+                             f.viewg(EMB_NAMES[2]), f.viewg(EMB_NAMES[3]), f.viewg(EMB_NAMES[4]), inv_scale, self.eps, rows,
                              S, self.H, drop=saved.drop_emb, pad_id=self.pad_id, inputs_embeds=saved.inputs_embeds,
                              d_inputs_embeds=d_emb)
         if after_layer is not None:

@@ -43,34 +43,7 @@ def _chk(rc: int, what: str) -> None:
     L.check(rc, what)
 
 
-@dataclass
-class RowIndex:
-    """Compaction of a [B, S] key tensor: positions with key != ignore in row-major order."""
-    idx: Tensor       # [n] flat position b*S + s
-    ex: Tensor        # [n] example
-    rank: Tensor      # [n] position inside its example's list
-    cnt: Tensor       # [B]
-    start: Tensor     # [B]
-    n: int
-    max_n: int
-
-
-def compact(key: Tensor, ignore: int) -> RowIndex:
-    if not key.is_cuda:
-        raise B200Error("heads: expected CUDA tensors (the B200 path has no CPU fallback)")
-    key = key.contiguous()
-    if key.dtype != torch.int64:
-        key = key.to(torch.int64)
-    B, S = key.shape
-    dev = key.device
-    tmp = torch.empty(B * S, dtype=I32, device=dev)
-    cnt, start = torch.empty(B, dtype=I32, device=dev), torch.empty(B, dtype=I32, device=dev)
-    totals = torch.empty(2, dtype=I32, device=dev)
-    idx, ex, rank = (torch.empty(B * S, dtype=I32, device=dev) for _ in range(3))
-    _chk(L.load().b200_heads_compact(_p(key), int(ignore), B, S, _p(tmp), _p(cnt), _p(start), _p(totals), _p(idx), _p(ex), _p(rank), _st()),
-         "b200_heads_compact")
-    n, max_n = totals.tolist()                     # the one host read: sizes of everything below
-    return RowIndex(idx[:n], ex[:n], rank[:n], cnt, start, int(n), int(max_n))
+from .ops import RowIndex, compact_rows as compact  # noqa: E402  (the compaction of the labelled positions doubles as the padding packer)
 
 
 def gather_keys(key: Tensor, rows: RowIndex) -> Tensor:

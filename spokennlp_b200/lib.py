@@ -59,6 +59,12 @@ _PROTOS = {
     "b200_set_hyper": [_p, _f, _f, _f, _f, _f, _f, _f, _p],
     "b200_adamw_step_dev": [_p, _p, _p, _p, _p, _sz, _p, _p, _p],
     "b200_adamw_step_dev_zero": [_p, _p, _p, _p, _p, _sz, _p, _p, _p],
+    # packed rows
+    "b200_gather_i64": [_p, _p, _i, _p, _p],
+    "b200_unpack_rows": [_p, _p, _i, _i, _p, _p],
+    "b200_attn_fwd_varlen": [_p, _i, _i, _i, _i, _p, _ll, _p, _i, _p, _i, _i, _i, _p, C.c_uint, _f, _p],
+    "b200_attn_bwd_workspace_varlen": [_i, _i, _i, _ll],
+    "b200_attn_bwd_varlen": [_p, _i, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p, _ll, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, C.c_uint, _f, _p],
     # loss heads on the labelled rows (csrc/heads.cuh)
     "b200_heads_compact": [_p, _ll, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p],
     "b200_heads_gather_keys": [_p, _p, _i, _p, _p],
@@ -89,7 +95,7 @@ _PROTOS = {
     "b200_attn_bwd_delta_ptr": [_p],
     "b200_attn_bwd_ext": [_p, _i, _i, _p, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p, C.c_uint, _f, _i, _p],
 }
-_RESTYPE = {"b200_set_sm_limit": None, "b200_last_error": C.c_char_p, "b200_launch_count": _ll, "b200_version": _i, "b200_source_hash": C.c_char_p, "b200_attn_bwd_workspace": _sz, "b200_ponet_workspace": _sz, "b200_ponet_bwd_workspace": _sz, "b200_attn_bwd_delta_ptr": _p}
+_RESTYPE = {"b200_set_sm_limit": None, "b200_last_error": C.c_char_p, "b200_launch_count": _ll, "b200_version": _i, "b200_source_hash": C.c_char_p, "b200_attn_bwd_workspace": _sz, "b200_attn_bwd_workspace_varlen": _sz, "b200_ponet_workspace": _sz, "b200_ponet_bwd_workspace": _sz, "b200_attn_bwd_delta_ptr": _p}
 
 _lock = threading.Lock()
 _lib = None

@@ -51,6 +51,50 @@ def _dt(t: Tensor) -> int:
     return DT_F32 if t.dtype == torch.float32 else DT_F16
 
 
+class RowIndex:
+    """Compaction of a [B, S] key tensor: the positions with key != ignore in row-major order (b200_heads_compact).  On an
+    attention mask (ignore = 0) this IS the packed layout of SURVEY.md §8f rank 2: `start` = cu_seqlens [B+1], `idx` = flat
+    position of every packed row, `ex` / `rank` = its sequence and position inside it, n = rows, max_n = longest sequence."""
+    __slots__ = ("idx", "ex", "rank", "cnt", "start", "n", "max_n", "B", "S")
+
+    def __init__(self, idx, ex, rank, cnt, start, n, max_n, B, S):
+        self.idx, self.ex, self.rank, self.cnt, self.start, self.n, self.max_n, self.B, self.S = idx, ex, rank, cnt, start, n, max_n, B, S
+
+
+def compact_rows(key: Tensor, ignore: int) -> RowIndex:
+    """One host read (8 bytes: row count and longest list) sizes everything downstream."""
+    if not key.is_cuda:
+        raise L.B200Error("compact_rows: expected a CUDA tensor (the B200 path has no CPU fallback)")
+    key = key.contiguous()
+    if key.dtype != torch.int64:
+        key = key.to(torch.int64)
+    B, S = key.shape
+    dev = key.device
+    i32 = torch.int32
+    tmp = torch.empty(B * S, dtype=i32, device=dev)
+    cnt, start = torch.empty(B, dtype=i32, device=dev), torch.empty(B + 1, dtype=i32, device=dev)
+    totals = torch.empty(2, dtype=i32, device=dev)
+    idx, ex, rank = (torch.empty(B * S, dtype=i32, device=dev) for _ in range(3))
+    L.check(L.load().b200_heads_compact(_ptr(key), int(ignore), B, S, _ptr(tmp), _ptr(cnt), _ptr(start), _ptr(totals), _ptr(idx), _ptr(ex),
+                                        _ptr(rank), _stream()), "b200_heads_compact")
+    n, max_n = totals.tolist()
+    return RowIndex(idx[:n], ex[:n], rank[:n], cnt, start, int(n), int(max_n), B, S)
+
+
+def gather_i64(key: Tensor, rows: RowIndex) -> Tensor:
+    key = _req(key.contiguous().view(-1), torch.int64, "key")
+    out = torch.empty(rows.n, dtype=torch.int64, device=key.device)
+    L.check(L.load().b200_gather_i64(_ptr(key), _ptr(rows.idx), rows.n, _ptr(out), _stream()), "b200_gather_i64")
+    return out
+
+
+def unpack_rows(src: Tensor, rows: RowIndex, dst: Tensor) -> Tensor:
+    """dst[idx[i]] = src[i] (fp32 rows): packed activations back into the padded [B*S, H] layout."""
+    _req(src, torch.float32, "src"), _req(dst, torch.float32, "dst")
+    L.check(L.load().b200_unpack_rows(_ptr(src), _ptr(rows.idx), rows.n, src.shape[1], _ptr(dst), _stream()), "b200_unpack_rows")
+    return dst
+
+
 def gemm(a: Tensor, b: Tensor, out: Tensor, *, a_layout: int = 0, b_layout: int = 0, epilogue: int = EPI_STORE,
          bias: Optional[Tensor] = None, aux: Optional[Tensor] = None, out2: Optional[Tensor] = None,
          alpha: Optional[Tensor] = None, k_splits: int = 1, drop: Optional["Dropout"] = None) -> Tensor:
@@ -148,9 +192,17 @@ def wgrad_splits(M_out: int, N_in: int, K_tokens: int, sms: int = 148) -> int:
 
 def attn_fwd(q: Tensor, kv: Tensor, ctx: Tensor, B: int, heads: int, Sq: int, Sk: int, *, q_col0: int, k_col0: int,
              v_col0: int, key_bias: Optional[Tensor] = None, kv_len: Optional[Tensor] = None,
-             lse2: Optional[Tensor] = None, drop: Optional["Dropout"] = None) -> Tensor:
+             lse2: Optional[Tensor] = None, drop: Optional["Dropout"] = None, pack: Optional[RowIndex] = None) -> Tensor:
+    """`pack`: q / kv / ctx hold PACKED rows (sequence b = rows [cu[b], cu[b+1])); Sq = Sk = the padded length."""
     _req(q, torch.float16, "q"), _req(kv, torch.float16, "kv"), _req(ctx, torch.float16, "ctx")
     seed, site, p = _drop_args(drop)
+    if pack is not None:
+        if kv is not q or key_bias is not None or kv_len is not None:
+            raise L.B200Error("attn_fwd: packed rows are for self-attention without an extra key mask")
+        rc = L.load().b200_attn_fwd_varlen(_ptr(q), q.stride(0), q_col0, k_col0, v_col0, _ptr(pack.start), pack.n, _ptr(ctx), ctx.stride(0),
+                                           _ptr(lse2), B, heads, Sq, seed, site, p, _stream())
+        L.check(rc, "b200_attn_fwd_varlen")
+        return ctx
     rc = L.load().b200_attn_fwd_drop(_ptr(q), q.stride(0), q_col0, _ptr(kv), kv.stride(0), k_col0, v_col0, _ptr(key_bias),
                                      _ptr(kv_len), _ptr(ctx), ctx.stride(0), _ptr(lse2), B, heads, Sq, Sk, seed, site, p, _stream())
     L.check(rc, "b200_attn_fwd")
@@ -279,19 +331,28 @@ def scale_cast_grad(src: Tensor, dst: Tensor, scale: Tensor, amax_slot: Tensor, 
     return dst
 
 
-def attn_bwd_workspace(B: int, heads: int, Sq: int, device) -> Tensor:
-    n = int(L.load().b200_attn_bwd_workspace(B, heads, Sq))
+def attn_bwd_workspace(B: int, heads: int, Sq: int, device, rows: Optional[int] = None) -> Tensor:
+    """`rows`: packed row count (the dQ accumulator then has that many rows; the row statistic keeps its padded layout)."""
+    n = int(L.load().b200_attn_bwd_workspace(B, heads, Sq) if rows is None else L.load().b200_attn_bwd_workspace_varlen(B, heads, Sq, rows))
     return torch.empty(n // 4, dtype=torch.float32, device=device)
 
 
 def attn_bwd(q: Tensor, kv: Tensor, dctx: Tensor, ctx: Tensor, lse2: Tensor, dq: Tensor, dkv: Tensor, workspace: Tensor,
              B: int, heads: int, Sq: int, Sk: int, *, q_col0: int, k_col0: int, v_col0: int, dq_col0: int, dk_col0: int,
              dv_col0: int, key_bias: Optional[Tensor] = None, kv_len: Optional[Tensor] = None, drop=None,
-             delta_ready: bool = False) -> None:
-    """`delta_ready` (opt-in): the workspace already holds rowsum(dO o O) from `gemm_dgrad_delta`; skip that pass."""
+             delta_ready: bool = False, pack: Optional[RowIndex] = None) -> None:
+    """`delta_ready`: the workspace already holds rowsum(dO o O) from `gemm_dgrad_delta`; skip that pass.  `pack`: packed rows."""
     for t, n in ((q, "q"), (kv, "kv"), (dctx, "dctx"), (ctx, "ctx"), (dq, "dq"), (dkv, "dkv")):
         _req(t, torch.float16, n)
     seed, site, p = _drop_args(drop)
+    if pack is not None:
+        if kv is not q or dkv is not dq or delta_ready or key_bias is not None or kv_len is not None:
+            raise L.B200Error("attn_bwd: packed rows are for self-attention (one packed QKV / dQKV buffer, own row-statistic pass)")
+        rc = L.load().b200_attn_bwd_varlen(_ptr(q), q.stride(0), q_col0, k_col0, v_col0, _ptr(dctx), dctx.stride(0), _ptr(ctx), ctx.stride(0),
+                                           _ptr(pack.start), _ptr(pack.ex), _ptr(pack.rank), pack.n, _ptr(lse2), _ptr(workspace), _ptr(dq),
+                                           dq.stride(0), dq_col0, dk_col0, dv_col0, B, heads, Sq, seed, site, p, _stream())
+        L.check(rc, "b200_attn_bwd_varlen")
+        return
     if delta_ready:
         rc = L.load().b200_attn_bwd_ext(_ptr(q), q.stride(0), q_col0, _ptr(kv), kv.stride(0), k_col0, v_col0, _ptr(dctx), dctx.stride(0),
                                         _ptr(ctx), ctx.stride(0), _ptr(key_bias), _ptr(kv_len), _ptr(lse2), _ptr(workspace), _ptr(dq),

@@ -151,20 +151,29 @@ class DataParallelTrainer:
             reserve = int(os.environ.get("B200_COMM_RESERVE", str(self.comm_ctas)))
             _lib.load().b200_set_sm_limit(self._sms - reserve if (on and reserve > 0) else 0)
 
-    def forward_backward(self, input_ids, attention_mask, token_type_ids, labels) -> torch.Tensor:
-        """Enqueue forward + backward for one local batch; returns the device scalar loss (no sync)."""
+    def forward_backward(self, input_ids, attention_mask, token_type_ids, labels, pack: bool = False) -> torch.Tensor:
+        """Enqueue forward + backward for one local batch; returns the device scalar loss (no sync).
+        `pack=True`: the right-padded windows are packed — only the valid tokens go through the
+        encoder, attention walks the sequences by cu_seqlens — at the price of ONE 8-byte host read (the packed row count sizes
+        the activation buffers), so a packed step is launched eagerly, not replayed from a CUDA graph."""
         eng, flat = self.engine, self.flat
         B, S = input_ids.shape
         if not self._grads_clean:           # the fused optimizer step leaves the gradient buffer zeroed
             flat.grad32.zero_()
         self._grads_clean = False
-        key_bias = kv_len = None
-        if attention_mask is not None:
-            key_bias, kv_len = ops.mask_to_bias(attention_mask)
+        key_bias = kv_len = rows = None
         pos = None  # arange(S) per row
         ids = input_ids.contiguous().view(-1)
         tt = token_type_ids.contiguous().view(-1) if token_type_ids is not None else None
-        x16, _, saved, _, _ = eng.forward(ids, tt, pos, None, key_bias, kv_len, B, S, save=True, drop=self.drop)
+        if pack and attention_mask is not None:
+            rows = ops.compact_rows(attention_mask, 0)
+            ids = ops.gather_i64(ids, rows)
+            tt = ops.gather_i64(tt, rows) if tt is not None else None
+            labels = ops.gather_i64(labels, rows)
+            pos = rows.rank.to(torch.int64)
+        elif attention_mask is not None:
+            key_bias, kv_len = ops.mask_to_bias(attention_mask)
+        x16, _, saved, _, _ = eng.forward(ids, tt, pos, None, key_bias, kv_len, B, S, save=True, drop=self.drop, pack=rows)
         drop_head = self.drop.at(DropPlan.HEAD, self.p_hidden) if self.drop is not None else None
         W32 = flat.view32("loss_calculator.classifier.weight")
         b32 = flat.view32("loss_calculator.classifier.bias")
@@ -227,11 +236,11 @@ class DataParallelTrainer:
         self._graph = None
         torch.cuda.synchronize()
 
-    def step(self, input_ids, attention_mask, token_type_ids, labels) -> torch.Tensor:
-        if self._graph is not None:
+    def step(self, input_ids, attention_mask, token_type_ids, labels, pack: bool = False) -> torch.Tensor:
+        if self._graph is not None and not pack:
             return self._replay(input_ids, attention_mask, token_type_ids, labels)
         self._push_seed()
-        stats = self.forward_backward(input_ids, attention_mask, token_type_ids, labels)
+        stats = self.forward_backward(input_ids, attention_mask, token_type_ids, labels, pack=pack)
         self.optimizer_step()
         return stats
 

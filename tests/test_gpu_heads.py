@@ -97,7 +97,7 @@ def test_compaction_topic_ids_and_degenerate_inputs():
     # a1 a2 a3 | b1 | c1 c2 || (next example) d1 | e1 e2   (label 0 closes a topic, the end of an example closes one too)
     labels = torch.tensor([[-100, 1, 1, 0, 0, 1, 1, -100], [-100, 0, 1, 1, -100, -100, -100, -100]]).cuda()
     rows = Hd.compact(labels, -100)
-    assert rows.n == 9 and rows.max_n == 6 and rows.cnt.tolist() == [6, 3] and rows.start.tolist() == [0, 6]
+    assert rows.n == 9 and rows.max_n == 6 and rows.cnt.tolist() == [6, 3] and rows.start.tolist() == [0, 6, 9]
     assert rows.idx.tolist() == [1, 2, 3, 4, 5, 6, 9, 10, 11] and rows.rank.tolist() == [0, 1, 2, 3, 4, 5, 0, 1, 2]
     lab = Hd.gather_keys(labels, rows)
     seg = torch.empty(rows.n, dtype=torch.int32, device="cuda")
