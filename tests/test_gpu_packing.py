@@ -29,6 +29,9 @@ def test_packed_attention_matches_the_padded_kernels(lens, S, heads, p):
     qkv = (torch.randn(B * S, 3 * H, generator=g) * 0.7).half().cuda()
     dctx = (torch.randn(B * S, H, generator=g) * 0.3).half().cuda()
     mask = _mask(lens, S)
+    # padded QUERY rows are real rows of the padded run (they attend to the valid keys); they only contribute to dK / dV if they
+    # carry gradient, which they do not in the model (no loss on padding, nobody reads their keys) — and must not here
+    dctx = torch.where(mask.bool().view(-1, 1), dctx, torch.zeros_like(dctx))
     key_bias, kv_len = ops.mask_to_bias(mask)
     seed = torch.tensor([77], dtype=torch.int32, device="cuda")
     drop = ops.Dropout(seed, 3, p) if p > 0 else None
