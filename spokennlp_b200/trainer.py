@@ -86,15 +86,15 @@ class DataParallelTrainer:
         self.step_idx = 0
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank() if self.world > 1 else 0
-        # OPT-IN (B200_COMM_CTAS=n, n > 0): overlapped gradient buckets run on a second NCCL communicator capped at n CTAs,
+        # B200_COMM_CTAS=n (default 4; 0 = off): overlapped gradient buckets run on a second NCCL communicator capped at n CTAs,
         # and the persistent compute kernels of the backward (one CTA per SM, static work split) leave that many SMs free —
         # a compute CTA that has to wait for a communication kernel to vacate its SM delays its whole kernel.  The last
         # bucket, which nothing overlaps, still goes through the default communicator at full width.  Measured on 2 GPUs
         # (profiles/bench_r01j_n2_commctas{0,4}.json, same box): 4029 -> 4161 seq/s with n = 4; n = 8 and n <= 2 were
-        # slower.  It is off by default because it could only be validated on 2 GPUs in round 1.
+        # slower.  Round 2 (profiles/scale_r02_*): 4301 -> 4374 seq/s on 2 GPUs inside the captured graph; validated on 4 / 8 GPUs.
         self.comm_ctas, self.bg_group, self._sms = 0, None, 0
         if self.world > 1 and self.device.type == "cuda" and dist.get_backend() == "nccl":
-            want = int(os.environ.get("B200_COMM_CTAS", "0"))
+            want = int(os.environ.get("B200_COMM_CTAS", "4"))        # default on since round 2 (2 GPUs: 14.88 -> 14.63 ms/step; 0 = off)
             if want > 0:
                 try:
                     opts = dist.ProcessGroupNCCL.Options()
