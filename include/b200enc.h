@@ -240,6 +240,8 @@ int b200_cls_head_bwd_drop(const void* h, const float* logits, const int64_t* la
  *   dz from HBM (b200_colsum).
  * b200_attn_bwd_ext: b200_attn_bwd_drop + flags. */
 #define B200_ATTN_BWD_DELTA_READY 1   /* workspace already holds delta (from b200_gemm_f16_dgrad_delta) */
+#define B200_ATTN_BWD_DQ_HALF 2       /* dQ is accumulated as fp16 TMA reduce-adds straight into dq (zeroed by the call): no fp32
+                                       * accumulator, memset or cast pass; at most Sk/128 roundings per element instead of one */
 int b200_gemm_f16_resadd(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias, float* out, int ld_out,
                          const uint32_t* seed, unsigned site, float p, void* stream);
 int b200_gemm_f16_dgrad_delta(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const void* ctx, int ld_ctx, void* out,

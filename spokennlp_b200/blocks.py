@@ -29,12 +29,15 @@ class Experimental:
                out-proj 51 -> 28 us, FFN-down 81 -> 74 us per layer at the bench shape (64 -> 29 / 84 -> 74 with dropout)
       delta  : attention-backward row statistic fused into the output projection's dgrad (b200_gemm_f16_dgrad_delta): -12 us/layer
       colsum : bias gradient of the FFN-up dense summed inside the FFN-down dgrad's dGELU epilogue (b200_gemm_f16_dgelu_colsum)
+    Under evaluation (off by default):
+      dq16   : attention backward accumulates dQ as fp16 TMA reduce-adds in place (B200_ATTN_BWD_DQ_HALF): no fp32 accumulator,
+               memset or cast pass, at most Sk/128 roundings per element instead of one
     `B200_EXP` (comma-separated) names the switches to turn on instead of the default set; `B200_EXP=none` is the round-1
     schedule.  (Measured and dropped in round 2: a stream-K schedule for the resadd GEMMs, lane-elected mbarrier WAITS in the
     attention kernels, and sixteen-warp attention kernels — DESIGN.md §9.)"""
     DEFAULT = "resadd,delta,colsum"
-    NAMES = ("resadd", "delta", "colsum")
-    resadd = delta = colsum = False
+    NAMES = ("resadd", "delta", "colsum", "dq16")
+    resadd = delta = colsum = dq16 = False
 
     @classmethod
     def from_env(cls, value: Optional[str] = None) -> None:
@@ -229,7 +232,8 @@ def attn_block_bwd(p: AttnWeights, g: AttnWeights, sv: AttnSaved, dy: Tensor, B:
     if not cross:
         dqkv = torch.empty(Mq, 3 * H, dtype=F16, device=dev)
         ops.attn_bwd(sv.q, sv.q, dctx, sv.ctx, sv.lse2, dqkv, dqkv, ws, B, heads, Sq, Sq, q_col0=0, k_col0=H, v_col0=2 * H, dq_col0=0,
-                     dk_col0=H, dv_col0=2 * H, key_bias=key_bias, kv_len=kv_len, drop=sv.drop_attn, delta_ready=fused_delta, pack=sv.pack)
+                     dk_col0=H, dv_col0=2 * H, key_bias=key_bias, kv_len=kv_len, drop=sv.drop_attn, delta_ready=fused_delta, pack=sv.pack,
+                     dq_half=Experimental.dq16 and sv.pack is None)
         ops.colsum(dqkv, g.bqkv, inv_scale)
         ops.gemm(dqkv, sv.x16, g.wqkv, a_layout=1, b_layout=1, epilogue=ops.EPI_ATOMIC, alpha=inv_scale,
                  k_splits=ops.wgrad_splits(3 * H, H, Mq))

@@ -62,7 +62,7 @@ EncodeTiledFn get_encode() {
 struct MapKey {
   const void* ptr;
   uint64_t rows, cols, ld;
-  uint32_t box_rows;   // bit 31 set: fp32 elements
+  uint32_t box_rows;   // bit 31 set: fp32 elements; bit 30 set: 64-byte boxes (SWIZZLE_64B)
   bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows; }
 };
 struct MapKeyHash {
@@ -79,12 +79,13 @@ std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 
 // 2D tensor [rows, cols] (fp16, or fp32 when f32 is set) with row pitch ld (elements); box = 128 bytes of columns
 // (SWIZZLE_128B) x box_rows.
-int get_tmap(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, CUtensorMap* out, bool f32 = false) {
+int get_tmap(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, CUtensorMap* out, bool f32 = false, bool box64 = false) {
   const uint64_t esz = f32 ? 4 : 2;
+  const uint32_t box_bytes = box64 ? 64 : 128;
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * esz) % 16) || cols == 0 || rows == 0 || box_rows == 0 || box_rows > 256)
     return fail(B200_ERR_SHAPE, "tensor map: ptr %p rows %llu cols %llu ld %llu box_rows %u violates 16B alignment / ld%%8", ptr,
                 (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
-  const MapKey key{ptr, rows, cols, ld, box_rows | (f32 ? 0x80000000u : 0u)};
+  const MapKey key{ptr, rows, cols, ld, box_rows | (f32 ? 0x80000000u : 0u) | (box64 ? 0x40000000u : 0u)};
   {
     std::lock_guard<std::mutex> lk(g_map_mu);
     auto it = g_maps.find(key);
@@ -97,11 +98,11 @@ int get_tmap(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_
   if (!enc) return fail(B200_ERR_CUDA, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
   const cuuint64_t dims[2] = {cols, rows};
   const cuuint64_t strides[1] = {ld * esz};
-  const cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / esz), box_rows};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(box_bytes / esz), box_rows};
   const cuuint32_t estr[2] = {1, 1};
   CUtensorMap m;
   const CUresult r = enc(&m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, box64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(B200_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", static_cast<int>(r));
   {

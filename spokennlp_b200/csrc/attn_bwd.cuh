@@ -26,6 +26,8 @@ struct AttnBwdArgs {
   float inv_sqrt_d;
   DropCfg drop;                     // the forward's attention-probability dropout (mask regenerated here)
   const int* cu_seqlens;            // [B+1] or null: packed rows, as in AttnFwdArgs (Sq / Sk = the maximum length)
+  int dq_half;                      // != 0: dQ leaves as an fp16 TMA reduce-add straight into the (zeroed) dQ columns of the gradient
+  int dq_col0;                      // buffer (tmDQ is then an fp16 map with 64-byte boxes): no fp32 accumulator, memset or cast pass
 };
 
 // delta[b,h,q] = sum_d dO[q, 64h+d] * O[q, 64h+d]   (one warp per token row; 8 lanes share a head)

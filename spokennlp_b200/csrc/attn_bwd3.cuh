@@ -284,6 +284,26 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tmem_wait_ld();
         if (lane == 0) tma_wait_group_read<0>();   // the previous reduction has finished reading the staging patch
         __syncwarp();
+        if (a.dq_half) {
+          // fp16 reduce-add into the dQ columns of the gradient buffer: [32 q][32 d] halves = 64-byte rows, SWIZZLE_64B (16-byte
+          // chunk c of row r sits at chunk c ^ ((r >> 1) & 3)).  At most Sk / 128 partial sums meet per element (4 at S = 512).
+          uint32_t w[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const __half2 hv = __floats2half2_rn(__uint_as_float(o[2 * k]), __uint_as_float(o[2 * k + 1]));
+            w[k] = *reinterpret_cast<const uint32_t*>(&hv);
+          }
+          const uint32_t row_s = smem_u32(dqs) + lane * 64;
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) sts128(row_s + ((ch ^ ((lane >> 1) & 3)) << 4), w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_reduce_add_2d(&tmDQ, dqs, a.dq_col0 + h * ATT_D + g * 32, it.qrow0 + i * ATT_BQ + qd * 32);
+            tma_commit_group();
+          }
+          return;
+        }
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) sts128(dqs_row + ((ch ^ (lane & 7)) << 4), o[4 * ch], o[4 * ch + 1], o[4 * ch + 2], o[4 * ch + 3]);
         fence_proxy_async_smem();

@@ -340,8 +340,9 @@ def attn_bwd_workspace(B: int, heads: int, Sq: int, device, rows: Optional[int] 
 def attn_bwd(q: Tensor, kv: Tensor, dctx: Tensor, ctx: Tensor, lse2: Tensor, dq: Tensor, dkv: Tensor, workspace: Tensor,
              B: int, heads: int, Sq: int, Sk: int, *, q_col0: int, k_col0: int, v_col0: int, dq_col0: int, dk_col0: int,
              dv_col0: int, key_bias: Optional[Tensor] = None, kv_len: Optional[Tensor] = None, drop=None,
-             delta_ready: bool = False, pack: Optional[RowIndex] = None) -> None:
-    """`delta_ready`: the workspace already holds rowsum(dO o O) from `gemm_dgrad_delta`; skip that pass.  `pack`: packed rows."""
+             delta_ready: bool = False, pack: Optional[RowIndex] = None, dq_half: bool = False) -> None:
+    """`delta_ready`: the workspace already holds rowsum(dO o O) from `gemm_dgrad_delta`; skip that pass.  `pack`: packed rows.
+    `dq_half`: dQ is accumulated as fp16 TMA reduce-adds straight into `dq` (no fp32 accumulator, memset or cast pass)."""
     for t, n in ((q, "q"), (kv, "kv"), (dctx, "dctx"), (ctx, "ctx"), (dq, "dq"), (dkv, "dkv")):
         _req(t, torch.float16, n)
     seed, site, p = _drop_args(drop)
@@ -353,11 +354,11 @@ def attn_bwd(q: Tensor, kv: Tensor, dctx: Tensor, ctx: Tensor, lse2: Tensor, dq:
                                            dq.stride(0), dq_col0, dk_col0, dv_col0, B, heads, Sq, seed, site, p, _stream())
         L.check(rc, "b200_attn_bwd_varlen")
         return
-    if delta_ready:
+    if delta_ready or dq_half:
         rc = L.load().b200_attn_bwd_ext(_ptr(q), q.stride(0), q_col0, _ptr(kv), kv.stride(0), k_col0, v_col0, _ptr(dctx), dctx.stride(0),
                                         _ptr(ctx), ctx.stride(0), _ptr(key_bias), _ptr(kv_len), _ptr(lse2), _ptr(workspace), _ptr(dq),
                                         dq.stride(0), dq_col0, _ptr(dkv), dkv.stride(0), dk_col0, dv_col0, B, heads, Sq, Sk, seed, site, p,
-                                        1, _stream())
+                                        (1 if delta_ready else 0) | (2 if dq_half else 0), _stream())
         L.check(rc, "b200_attn_bwd_ext")
         return
     rc = L.load().b200_attn_bwd_drop(_ptr(q), q.stride(0), q_col0, _ptr(kv), kv.stride(0), k_col0, v_col0, _ptr(dctx), dctx.stride(0),

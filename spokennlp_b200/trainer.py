@@ -200,15 +200,25 @@ class DataParallelTrainer:
     def optimizer_step(self, *, advance: bool = True) -> None:
         """Global-norm clip + fused AdamW over the flat buffers.  Hyper-parameters are read from device memory
         (`self.hyper`, written by `_push_hyper`) so the same launches can live inside a captured CUDA graph."""
-        for w in self._works:
-            w.wait()
-        self._works = []
         flat = self.flat
         if advance:
             self.step_idx += 1
             self._push_hyper()
         self.sumsq.zero_()
-        ops.grad_sumsq(flat.grad32, self.sumsq)
+        if len(self._works) > 1:
+            # the trailing embeddings bucket is the one exposed collective of the step (95 MB, ~0.4 ms on 8 GPUs): the norm of
+            # everything else (78 % of the gradient bytes) is summed while it is still in flight
+            for w in self._works[:-1]:
+                w.wait()
+            lo = self.emb_slice[1]
+            ops.grad_sumsq(flat.grad32[lo:], self.sumsq)
+            self._works[-1].wait()
+            ops.grad_sumsq(flat.grad32[:lo], self.sumsq)
+        else:
+            for w in self._works:
+                w.wait()
+            ops.grad_sumsq(flat.grad32, self.sumsq)
+        self._works = []
         if self.dynamic_loss_scale:
             ops.clip_coef_scaled(self.sumsq, self.coef, self.max_grad_norm, 1.0 / self.world, self.scale, self.scale_state,
                                  growth_interval=self.scale_growth_interval)
