@@ -23,19 +23,18 @@ F16, F32 = torch.float16, torch.float32
 
 class Experimental:
     """Host-side schedule switches: which fused entry points a layer calls.  Nothing here is library state — each switch picks
-    between two sequences of C-ABI calls that compute the same thing.  All three were validated and measured on a B200 in
-    round 2 (profiles/r02a_variants_ab.jsonl, bench_r02a_*.json, r02c_*) and are ON by default:
+    between two sequences of C-ABI calls that compute the same thing.  All four were validated and measured on a B200 in
+    round 2 (profiles/r02a_variants_ab.jsonl, bench_r02a_*.json, r02c_*, bench_r02i_*) and are ON by default:
       resadd : output-dense + residual through b200_gemm_f16_resadd (in place on the fp32 residual stream, no aux reads):
                out-proj 51 -> 28 us, FFN-down 81 -> 74 us per layer at the bench shape (64 -> 29 / 84 -> 74 with dropout)
       delta  : attention-backward row statistic fused into the output projection's dgrad (b200_gemm_f16_dgrad_delta): -12 us/layer
       colsum : bias gradient of the FFN-up dense summed inside the FFN-down dgrad's dGELU epilogue (b200_gemm_f16_dgelu_colsum)
-    Under evaluation (off by default):
       dq16   : attention backward accumulates dQ as fp16 TMA reduce-adds in place (B200_ATTN_BWD_DQ_HALF): no fp32 accumulator,
-               memset or cast pass, at most Sk/128 roundings per element instead of one
+               memset or cast pass, at most Sk/128 roundings per element instead of one; 13.99 -> 13.70 ms/step on one box
     `B200_EXP` (comma-separated) names the switches to turn on instead of the default set; `B200_EXP=none` is the round-1
     schedule.  (Measured and dropped in round 2: a stream-K schedule for the resadd GEMMs, lane-elected mbarrier WAITS in the
     attention kernels, and sixteen-warp attention kernels — DESIGN.md §9.)"""
-    DEFAULT = "resadd,delta,colsum"
+    DEFAULT = "resadd,delta,colsum,dq16"
     NAMES = ("resadd", "delta", "colsum", "dq16")
     resadd = delta = colsum = dq16 = False
 

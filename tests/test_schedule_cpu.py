@@ -147,10 +147,10 @@ def test_delta_variant_replaces_the_plain_dgrad_and_skips_the_row_statistic_pass
 
 
 def test_default_schedule_is_the_round2_validated_set(rec, monkeypatch):
-    """resadd + delta + colsum were validated and measured on a B200 (profiles/r02a_*, r02c_*) and are the default."""
+    """resadd + delta + colsum + dq16 were validated and measured on a B200 (profiles/r02a_*, r02c_*) and are the default."""
     monkeypatch.delenv("B200_EXP", raising=False)
     blocks.Experimental.from_env(None)
-    assert blocks.Experimental.active() == ["resadd", "delta", "colsum"]
+    assert blocks.Experimental.active() == ["resadd", "delta", "colsum", "dq16"]
     eng = _engine()
     rec.calls.clear()
     _, _, saved, _, _ = _forward(eng, save=True)
