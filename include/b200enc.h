@@ -41,6 +41,7 @@ extern "C" {
 
 #define B200_DT_F16 0
 #define B200_DT_F32 1
+#define B200_DT_BF16 2 /* b200_gemm_bf16 only */
 
 const char* b200_last_error(void);
 int b200_version(void);
@@ -330,6 +331,16 @@ int b200_attn_bwd_varlen(const void* qkv, int ld, int q_col0, int k_col0, int v_
                          const int32_t* cu_seqlens, const int32_t* row_ex, const int32_t* row_rank, long long rows, const float* lse2,
                          void* workspace, void* dqkv, int ld_d, int dq_col0, int dk_col0, int dv_col0, int B, int heads, int S_max,
                          const uint32_t* seed, unsigned site, float p, void* stream);
+
+/* ---- bf16 operands (BASELINE config 4: "mmvts ... fine-tune bf16") ----------------------------------------------------------
+ * The same 2-CTA tcgen05 GEMM with bf16 A / B (instruction-descriptor formats 1/1, fp32 accumulation): forward Linear
+ * (a_layout = b_layout = 0; EPI_STORE / EPI_BIAS; result bf16 or fp32), dgrad (b_layout = 1, EPI_STORE, bf16) and wgrad
+ * (a_layout = b_layout = 1, EPI_ATOMIC split-K, fp32).  Same tensor-core rate as fp16, 8 mantissa bits: the hidden-state
+ * parity bar of the BERT path (1e-3) is NOT met with bf16 operands (5.4e-3 at layer 12), which is why the encoder
+ * runs fp16; the mmvts projector (the largest GEMM of that model, K up to 3328) offers it as an option and reports its error. */
+int b200_gemm_bf16(const void* A, int lda, int a_layout, const void* B, int ldb, int b_layout, int M, int N, int K, int epilogue, const float* bias,
+                   void* out, int ld_out, int out_dtype, const float* alpha, int k_splits, void* stream);
+int b200_cast_f32_to_bf16(const float* src, void* dst, size_t n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -140,6 +140,12 @@ int set_smem(K kern, int bytes) {
 }
 
 
+// grid of a streaming kernel over n8 8-element vectors
+int stream_grid(size_t n8) {
+  size_t g = (n8 + 255) / 256;
+  const size_t cap = static_cast<size_t>(sm_count()) * 16;
+  return static_cast<int>(g < cap ? (g ? g : 1) : cap);
+}
 const DropCfg kNoDrop{nullptr, 0, 0, 1.0f};
 DropCfg make_drop(const uint32_t* seed, unsigned site, float p) {
   if (!seed || p <= 0.f) return kNoDrop;
@@ -154,9 +160,9 @@ DropCfg make_drop_attn(const uint32_t* seed, unsigned site, float p) {
   return DropCfg{seed, site, tt, 512.0f / (512.0f - static_cast<float>(t))};
 }
 
-template <int BN, int A_MN, int B_MN, int EPI, typename OutT>
+template <int BN, int A_MN, int B_MN, int EPI, typename OutT, bool BF16IN = false>
 int launch_gemm2(const Gemm2Maps& maps, const GemmArgs& g, cudaStream_t s) {
-  auto kern = gemm2_f16_kernel<BN, A_MN, B_MN, EPI, OutT>;
+  auto kern = gemm2_f16_kernel<BN, A_MN, B_MN, EPI, OutT, BF16IN>;
   static int configured = set_smem(kern, Gemm2Smem<BN, EPI>::TOTAL);
   if (configured != B200_OK) return configured;
   const int m_tiles = (g.M + G2_BM - 1) / G2_BM, n_tiles = (g.N + BN - 1) / BN;
@@ -206,6 +212,43 @@ int b200_gemm_f16_resadd(const void* A, int lda, const void* B, int ldb, int M, 
   if (p < 0.f || p >= 1.f) return fail(B200_ERR_SHAPE, "gemm_resadd: p must be in [0,1)");
   return gemm_impl(A, lda, 0, B, ldb, 0, M, N, K, EPI_RESADD, bias, nullptr, 0, out, ld_out, B200_DT_F32, nullptr, 0, nullptr, 1,
                    make_drop(seed, site, p), stream);
+}
+
+/* bf16 operands (A, B bf16; fp32 accumulate): forward Linear (K-major x K-major: STORE / BIAS, result bf16 or fp32), dgrad
+ * (b_layout = 1, STORE, bf16) and wgrad (a_layout = b_layout = 1, ATOMIC split-K, fp32). */
+int b200_gemm_bf16(const void* A, int lda, int a_layout, const void* B, int ldb, int b_layout, int M, int N, int K, int epilogue, const float* bias,
+                   void* out, int ld_out, int out_dtype, const float* alpha, int k_splits, void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0 || !A || !B || !out) return fail(B200_ERR_SHAPE, "gemm_bf16: empty problem or null operand");
+  if ((N % 8) || (ld_out % 4)) return fail(B200_ERR_SHAPE, "gemm_bf16: N %% 8 and ld_out %% 4 required (N=%d ld_out=%d)", N, ld_out);
+  if (epilogue == EPI_BIAS && !bias) return fail(B200_ERR_SHAPE, "gemm_bf16: EPI_BIAS needs bias");
+  if (k_splits > 1 && epilogue != EPI_ATOMIC) return fail(B200_ERR_SHAPE, "gemm_bf16: split-K only with the atomic epilogue");
+  constexpr int BN = 256;
+  Gemm2Maps mp;
+  int rc = a_layout == 0 ? get_tmap(A, M, K, lda, 128, &mp.a) : get_tmap(A, K, M, lda, GEMM_BK, &mp.a);      // (2-byte elements: the fp16 map moves bf16 bits alike)
+  if (rc) return rc;
+  rc = b_layout == 0 ? get_tmap(B, N, K, ldb, BN / 2, &mp.b) : get_tmap(B, K, N, ldb, GEMM_BK, &mp.b);
+  if (rc) return rc;
+  if ((rc = get_tmap(out, M, N, ld_out, 32, &mp.out, out_dtype == B200_DT_F32))) return rc;
+  mp.aux = mp.out;
+  mp.out2 = mp.out;
+  GemmArgs g{M, N, K, k_splits > 0 ? k_splits : 1, bias, nullptr, 0, out, ld_out, nullptr, 0, alpha, kNoDrop, nullptr, nullptr};
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (a_layout * 1000 + b_layout * 100 + epilogue * 10 + out_dtype) {
+    case 0 * 1000 + 0 * 100 + EPI_STORE * 10 + B200_DT_BF16: return launch_gemm2<BN, 0, 0, EPI_STORE, __nv_bfloat16>(mp, g, s);
+    case 0 * 1000 + 0 * 100 + EPI_BIAS * 10 + B200_DT_BF16: return launch_gemm2<BN, 0, 0, EPI_BIAS, __nv_bfloat16>(mp, g, s);
+    case 0 * 1000 + 0 * 100 + EPI_STORE * 10 + B200_DT_F32: return launch_gemm2<BN, 0, 0, EPI_STORE, float, true>(mp, g, s);
+    case 0 * 1000 + 0 * 100 + EPI_BIAS * 10 + B200_DT_F32: return launch_gemm2<BN, 0, 0, EPI_BIAS, float, true>(mp, g, s);
+    case 0 * 1000 + 1 * 100 + EPI_STORE * 10 + B200_DT_BF16: return launch_gemm2<BN, 0, 1, EPI_STORE, __nv_bfloat16>(mp, g, s);
+    case 1 * 1000 + 1 * 100 + EPI_ATOMIC * 10 + B200_DT_F32: return launch_gemm2<BN, 1, 1, EPI_ATOMIC, float, true>(mp, g, s);
+    default:
+      return fail(B200_ERR_SHAPE, "gemm_bf16: unsupported (a_layout=%d, b_layout=%d, epilogue=%d, out_dtype=%d)", a_layout, b_layout, epilogue, out_dtype);
+  }
+}
+
+int b200_cast_f32_to_bf16(const float* src, void* dst, size_t n, void* stream) {
+  if (n % 8) return fail(B200_ERR_SHAPE, "cast: n %% 8 != 0");
+  cast_f32_bf16_kernel<<<stream_grid(n / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, static_cast<__nv_bfloat16*>(dst), n / 8);
+  return check_launch("cast_f32_bf16_kernel");
 }
 
 int b200_gemm_f16_dgelu_colsum(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const void* dact, int ld_dact, void* out,
@@ -580,12 +623,6 @@ int b200_colsum(const void* dy, int ld, float* db, const float* alpha, int rows,
   return check_launch("colsum_kernel");
 }
 
-static int stream_grid(size_t n8) {
-  size_t g = (n8 + 255) / 256;
-  const size_t cap = static_cast<size_t>(sm_count()) * 16;
-  return static_cast<int>(g < cap ? (g ? g : 1) : cap);
-}
-
 int b200_cast_f32_to_f16(const float* src, void* dst, size_t n, void* stream) {
   if (n % 8) return fail(B200_ERR_SHAPE, "cast: n %% 8 != 0");
   cast_f32_f16_kernel<<<stream_grid(n / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, static_cast<__half*>(dst), n / 8);
@@ -646,13 +683,13 @@ int b200_ponet_mix_fwd(const void* proj, int ld, const float* key_bias, const in
   int rc;
   if ((rc = check_launch("fill_f32_kernel"))) return rc;
   const __half* p = static_cast<const __half*>(proj);
-  ponet_qsum_kernel<<<dim3(nchunks, B), H / 8, 0, s>>>(p, ld, key_bias, qsum, cnt, S, H);
+  ponet_qsum_kernel<<<dim3((S + PONET_QSUM_POS - 1) / PONET_QSUM_POS, B), H / 8, 0, s>>>(p, ld, key_bias, qsum, cnt, S, H);
   if ((rc = check_launch("ponet_qsum_kernel"))) return rc;
   ponet_global_part_kernel<<<dim3(nchunks, heads, B), 128, 0, s>>>(p, ld, key_bias, qsum, cnt, part, S, H, heads);
   if ((rc = check_launch("ponet_global_part_kernel"))) return rc;
   ponet_global_comb_kernel<<<dim3(heads, B), 64, 0, s>>>(part, g, nchunks, H, heads);
   if ((rc = check_launch("ponet_global_comb_kernel"))) return rc;
-  ponet_segmax_kernel<<<dim3((S + 63) / 64, B), H / 8, 0, s>>>(p, ld, key_bias, segment_ids, segmax, S, H, nseg);
+  ponet_segmax_kernel<<<dim3((S + PONET_RUN_POS - 1) / PONET_RUN_POS, B), H / 8, 0, s>>>(p, ld, key_bias, segment_ids, segmax, S, H, nseg);
   if ((rc = check_launch("ponet_segmax_kernel"))) return rc;
   ponet_mix_kernel<<<(B * S + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, s>>>(p, ld, key_bias, segment_ids, g, segmax,
                                                                                  static_cast<__half*>(out), B, S, H, nseg);
@@ -685,7 +722,7 @@ int b200_ponet_mix_bwd(const void* proj, int ld, const void* dout, const float* 
   const __half* p = static_cast<const __half*>(proj);
   const __half* d = static_cast<const __half*>(dout);
   int rc;
-  ponet_bwd_sums_kernel<<<dim3((S + 63) / 64, B), H / 8, 0, s>>>(p, ld, d, key_bias, segment_ids, segmax, dg, segsum, segties, S, H, nseg);
+  ponet_bwd_sums_kernel<<<dim3((S + PONET_RUN_POS - 1) / PONET_RUN_POS, B), H / 8, 0, s>>>(p, ld, d, key_bias, segment_ids, segmax, dg, segsum, segties, S, H, nseg);
   if ((rc = check_launch("ponet_bwd_sums_kernel"))) return rc;
   ponet_global_lse_kernel<<<dim3(heads, B), 32, 0, s>>>(part, lse, nchunks, heads);
   if ((rc = check_launch("ponet_global_lse_kernel"))) return rc;

@@ -12,6 +12,8 @@
 //     Auxiliary row-major inputs (residual, saved activation derivative) are read 128 contiguous bytes per thread
 //     straight into registers one chunk ahead of their use.
 #pragma once
+#include <type_traits>
+
 #include "gemm.cuh"
 
 namespace b200 {
@@ -95,12 +97,16 @@ __device__ __forceinline__ uint32_t slab_chunk(uint32_t slab_saddr, int row, int
   return slab_saddr + row * 128 + ((chunk ^ (row & 7)) << 4);
 }
 
-template <int BN, int A_MN, int B_MN, int EPI, typename OutT>
+// OutT = __half / float, or __nv_bfloat16: bf16 OPERANDS (and a bf16 or — with OutT float via BF16IN — fp32 result) for the plain
+// epilogues (SURVEY.md config 4's bf16 arm: same tensor-core rate, 8 mantissa bits instead of 11).
+template <int BN, int A_MN, int B_MN, int EPI, typename OutT, bool BF16IN = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
   using S = Gemm2Smem<BN, EPI>;
   constexpr int G2_STAGES = S::STAGES;
   constexpr bool OUT32 = sizeof(OutT) == 4;
+  constexpr bool BF16 = BF16IN || std::is_same<OutT, __nv_bfloat16>::value;
+  static_assert(!BF16 || EPI == EPI_STORE || EPI == EPI_BIAS || EPI == EPI_ATOMIC, "bf16 operands: plain epilogues only");
   constexpr int CW = OUT32 ? 32 : 64;                 // accumulator columns per staging slab (128 B of output per row)
   constexpr bool RESADD = EPI == EPI_RESADD;         // out32 += drop(acc + bias): residual already in `out`, TMA reduce-add
   constexpr bool DELTA = EPI == EPI_STORE_DELTA;      // out16 = acc, delta[b,h,q] = <out row, aux row> per 64-column head
@@ -204,7 +210,7 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     if (leader) {
-      constexpr uint32_t idesc = make_idesc_f16(G2_BM, BN, A_MN, B_MN);
+      constexpr uint32_t idesc = make_idesc_f16(G2_BM, BN, A_MN, B_MN, BF16 ? 1 : 0);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       int mt, nt, kb0, kb1;
       for (int u = u_begin; u < u_end; u = next_unit(u, kb0, kb1)) {
@@ -407,6 +413,10 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
           for (int k = 0; k < 32; ++k) {
             const __half2 hv = __floats2half2_rn(f[2 * k], f[2 * k + 1]);
             ow[k] = *reinterpret_cast<const uint32_t*>(&hv);
+            if (std::is_same<OutT, __nv_bfloat16>::value) {
+              const __nv_bfloat162 bv = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+              ow[k] = *reinterpret_cast<const uint32_t*>(&bv);
+            }
             if (DELTA) {                                  // the statistic is taken on the ROUNDED output, the values attention backward reads
               const float2 o2 = __half22float2(hv);
               const float2 c2 = __half22float2(reinterpret_cast<const __half2*>(araw)[k]);

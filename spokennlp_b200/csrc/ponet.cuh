@@ -16,20 +16,26 @@
 namespace b200 {
 
 constexpr float PONET_NEG = -10000.0f;
+// Positions walked serially by one thread of the streaming kernels below.  At the BASELINE shape ([2, 4096]) the batch offers no
+// parallelism, so the grids must come from the sequence: 128 / 64 positions per block gave 64-128 blocks of 96 threads and
+// latency-bound kernels (profiles/r02_hbm_rooflines.md: 0.12 of the HBM peak); 16 gives 512 blocks.
+constexpr int PONET_QSUM_POS = 16;
+constexpr int PONET_RUN_POS = 16;
 
 __device__ __forceinline__ void atomic_max_f32(float* addr, float v) {
   if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
   else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
 
-// grid (ceil(S/128), B), block H/8 threads (each owns 8 columns)
+// grid (ceil(S/PONET_QSUM_POS), B), block H/8 threads (each owns 8 columns)
 __global__ void ponet_qsum_kernel(const __half* __restrict__ proj, int ld, const float* __restrict__ key_bias, float* __restrict__ qsum,
                                   float* __restrict__ cnt, int S, int H) {
-  const int b = blockIdx.y, s0 = blockIdx.x * 128, c = threadIdx.x * 8;
+  const int b = blockIdx.y, s0 = blockIdx.x * PONET_QSUM_POS, c = threadIdx.x * 8;
   if (c >= H) return;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   int n = 0;
-  for (int s = s0; s < min(S, s0 + 128); ++s) {
+#pragma unroll 4
+  for (int s = s0; s < min(S, s0 + PONET_QSUM_POS); ++s) {
     if (key_bias && key_bias[static_cast<size_t>(b) * S + s] != 0.f) continue;
     const Vec8 v = load8(proj + (static_cast<size_t>(b) * S + s) * ld + c);
 #pragma unroll
@@ -104,14 +110,14 @@ __global__ void ponet_global_comb_kernel(const float* __restrict__ part, float* 
   g[static_cast<size_t>(b) * H + h * 64 + d] = l > 0.f ? acc / l : 0.f;
 }
 
-// grid (ceil(S/64), B), block H/8.  segmax must be pre-filled with -inf.
+// grid (ceil(S/PONET_RUN_POS), B), block H/8.  segmax must be pre-filled with -inf.
 __global__ void ponet_segmax_kernel(const __half* __restrict__ proj, int ld, const float* __restrict__ key_bias,
                                     const int64_t* __restrict__ seg, float* __restrict__ segmax, int S, int H, int nseg) {
-  const int b = blockIdx.y, s0 = blockIdx.x * 64, c = threadIdx.x * 8;
+  const int b = blockIdx.y, s0 = blockIdx.x * PONET_RUN_POS, c = threadIdx.x * 8;
   if (c >= H) return;
   float run[8];
   long cur = -1;
-  for (int s = s0; s < min(S, s0 + 64); ++s) {
+  for (int s = s0; s < min(S, s0 + PONET_RUN_POS); ++s) {
     const long id = seg[static_cast<size_t>(b) * S + s];
     const bool pad = key_bias && key_bias[static_cast<size_t>(b) * S + s] != 0.f;
     Vec8 v;
@@ -207,7 +213,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) ponet_mix_kernel(const __half*
 __global__ void ponet_bwd_sums_kernel(const __half* __restrict__ proj, int ld, const __half* __restrict__ dout, const float* __restrict__ key_bias,
                                       const int64_t* __restrict__ seg, const float* __restrict__ segmax, float* __restrict__ dg,
                                       float* __restrict__ segsum, float* __restrict__ segties, int S, int H, int nseg) {
-  const int b = blockIdx.y, s0 = blockIdx.x * 64, c = threadIdx.x * 8;
+  const int b = blockIdx.y, s0 = blockIdx.x * PONET_RUN_POS, c = threadIdx.x * 8;
   if (c >= H) return;
   float run[8], tot[8], ties[8];
   Vec8 mx;
@@ -224,7 +230,7 @@ __global__ void ponet_bwd_sums_kernel(const __half* __restrict__ proj, int ld, c
       }
     }
   };
-  for (int s = s0; s < min(S, s0 + 64); ++s) {
+  for (int s = s0; s < min(S, s0 + PONET_RUN_POS); ++s) {
     const size_t row = static_cast<size_t>(b) * S + s;
     const long id = seg[row];
     if (id != cur) {

@@ -3,6 +3,7 @@
 // PTX ISA "tcgen05 matrix descriptors" / "instruction descriptor" tables.
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -204,11 +205,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 
-// Instruction descriptor for kind::f16, fp16 A/B, fp32 accumulate.
-//   [4,6) c_format (1 = f32)  [7,10) a_format (0 = f16)  [10,13) b_format  [15] a_major  [16] b_major (1 = MN-major)
+// Instruction descriptor for kind::f16, fp16 (or bf16) A/B, fp32 accumulate.
+//   [4,6) c_format (1 = f32)  [7,10) a_format (0 = f16, 1 = bf16)  [10,13) b_format  [15] a_major  [16] b_major (1 = MN-major)
 //   [17,23) N >> 3   [24,29) M >> 4
-__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (0u << 7) | (0u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_mn_major, int b_mn_major, int bf16_operands = 0) {
+  return (1u << 4) | (static_cast<uint32_t>(bf16_operands) << 7) | (static_cast<uint32_t>(bf16_operands) << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
          (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }

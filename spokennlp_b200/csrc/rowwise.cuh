@@ -704,6 +704,17 @@ __global__ void cast_f32_f16_kernel(const float* __restrict__ src, __half* __res
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n8; i += static_cast<size_t>(gridDim.x) * blockDim.x)
     store8(dst + i * 8, load8(src + i * 8));
 }
+// fp32 -> bf16 (operands of the bf16 GEMM arm)
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n8) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n8; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const Vec8 v = load8(src + i * 8);
+    uint4 raw;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(v.v[2 * k], v.v[2 * k + 1]);
+    *reinterpret_cast<uint4*>(dst + i * 8) = raw;
+  }
+}
 // fp16 -> fp32
 __global__ void cast_f16_f32_kernel(const __half* __restrict__ src, float* __restrict__ dst, size_t n8) {
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n8; i += static_cast<size_t>(gridDim.x) * blockDim.x)

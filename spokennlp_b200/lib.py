@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libb200enc.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 EPI_STORE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_DGELU, EPI_ADD, EPI_ATOMIC, EPI_BIAS_RES32, EPI_RESADD, EPI_STORE_DELTA = range(10)
-DT_F16, DT_F32 = 0, 1
+DT_F16, DT_F32, DT_BF16 = 0, 1, 2
 
 _p, _i, _f, _sz, _ll = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_longlong
 
@@ -59,6 +59,9 @@ _PROTOS = {
     "b200_set_hyper": [_p, _f, _f, _f, _f, _f, _f, _f, _p],
     "b200_adamw_step_dev": [_p, _p, _p, _p, _p, _sz, _p, _p, _p],
     "b200_adamw_step_dev_zero": [_p, _p, _p, _p, _p, _sz, _p, _p, _p],
+    # bf16 operands (config 4)
+    "b200_gemm_bf16": [_p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p, _i, _p],
+    "b200_cast_f32_to_bf16": [_p, _p, _sz, _p],
     # packed rows
     "b200_gather_i64": [_p, _p, _i, _p, _p],
     "b200_unpack_rows": [_p, _p, _i, _i, _p, _p],

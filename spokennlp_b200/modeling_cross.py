@@ -296,14 +296,20 @@ class _ProjFn(torch.autograd.Function):
     """y = LayerNorm(x W^T + b)  (linear_projector.py:21-30; dropout is applied by the caller module)."""
 
     @staticmethod
-    def forward(ctx, x, W, b, gamma, beta, eps):
+    def forward(ctx, x, W, b, gamma, beta, eps, bf16=False):
+        """`bf16`: the forward contraction runs on bf16 operands (BASELINE config 4's bf16 arm — what a bf16 autocast would feed
+        the tensor cores; same rate, 8 mantissa bits); the backward keeps fp16 operands under the loss scale."""
         shp = x.shape
         x32 = x.detach().to(F32).contiguous().view(-1, shp[-1])
         M, dev = x32.shape[0], x.device
         x16, W16 = _to16(x32), _to16(W.detach().contiguous())
         H = W.shape[0]
         pre = torch.empty(M, H, dtype=F32, device=dev)
-        ops.gemm(x16, W16, pre, epilogue=ops.EPI_BIAS, bias=b.detach())
+        if bf16:
+            ops.gemm_bf16(ops.cast_f32_to_bf16(x32), ops.cast_f32_to_bf16(W.detach().to(F32).contiguous()), pre, epilogue=ops.EPI_BIAS,
+                          bias=b.detach())
+        else:
+            ops.gemm(x16, W16, pre, epilogue=ops.EPI_BIAS, bias=b.detach())
         mean, rstd = torch.empty(M, dtype=F32, device=dev), torch.empty(M, dtype=F32, device=dev)
         y32 = torch.empty(M, H, dtype=F32, device=dev)
         ops.layernorm_fwd(pre, gamma.detach(), beta.detach(), eps, y32=y32, mean=mean, rstd=rstd)
@@ -329,7 +335,7 @@ class _ProjFn(torch.autograd.Function):
         dx16 = torch.empty(M, K, dtype=F16, device=dev)
         ops.gemm(d_pre, W16, dx16, b_layout=1)
         dx = ops.unscale_cast_grad(dx16, torch.empty(ctx.shp, dtype=F32, device=dev), scale)
-        return dx, dW, dbias, dg, db, None
+        return dx, dW, dbias, dg, db, None, None
 
 
 class LinearProjector(nn.Module):
@@ -337,6 +343,10 @@ class LinearProjector(nn.Module):
 
     def __init__(self, config):
         super().__init__()
+        # "bf16": run the projection GEMMs on bf16 operands (config attribute `b200_operand_dtype`, default "fp16")
+        self.operand_dtype = getattr(config, "b200_operand_dtype", "fp16")
+        if self.operand_dtype not in ("fp16", "bf16"):
+            raise B200Error(f"b200_operand_dtype must be 'fp16' or 'bf16', got {self.operand_dtype!r}")
         for name, dim in (("text", config.hidden_size), ("vis", config.hidden_size_vis), ("audio", config.hidden_size_audio)):
             if dim % 8:
                 raise B200Error(f"LinearProjector input width {dim} must be a multiple of 8")
@@ -348,7 +358,8 @@ class LinearProjector(nn.Module):
         if x is None:
             return None
         lin, ln = getattr(self, f"proj_{name}"), getattr(self, f"layernorm_{name}")
-        return getattr(self, f"dropout_{name}")(_ProjFn.apply(x, lin.weight, lin.bias, ln.weight, ln.bias, float(ln.eps)))
+        return getattr(self, f"dropout_{name}")(_ProjFn.apply(x, lin.weight, lin.bias, ln.weight, ln.bias, float(ln.eps),
+                                                              self.operand_dtype == "bf16"))
 
     def forward(self, text_feature=None, vis_feature=None, audio_feature=None):
         return self._one("text", text_feature), self._one("vis", vis_feature), self._one("audio", audio_feature)

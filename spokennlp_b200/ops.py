@@ -51,6 +51,29 @@ def _dt(t: Tensor) -> int:
     return DT_F32 if t.dtype == torch.float32 else DT_F16
 
 
+def cast_f32_to_bf16(src: Tensor, dst: Optional[Tensor] = None) -> Tensor:
+    _req(src, torch.float32, "src")
+    if dst is None:
+        dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    L.check(L.load().b200_cast_f32_to_bf16(_ptr(src), _ptr(dst), src.numel(), _stream()), "b200_cast_f32_to_bf16")
+    return dst
+
+
+def gemm_bf16(a: Tensor, b: Tensor, out: Tensor, *, a_layout: int = 0, b_layout: int = 0, epilogue: int = EPI_STORE,
+              bias: Optional[Tensor] = None, alpha: Optional[Tensor] = None, k_splits: int = 1) -> Tensor:
+    """bf16-operand form of `gemm` (plain epilogues: STORE / BIAS forward, STORE dgrad, ATOMIC wgrad); out bf16 or fp32."""
+    _req(a, torch.bfloat16, "A"), _req(b, torch.bfloat16, "B")
+    if out.dtype not in (torch.bfloat16, torch.float32):
+        raise L.B200Error(f"gemm_bf16: out must be bf16 or fp32, got {out.dtype}")
+    M = a.shape[1] if a_layout else a.shape[0]
+    K = a.shape[0] if a_layout else a.shape[1]
+    N = b.shape[1] if b_layout else b.shape[0]
+    rc = L.load().b200_gemm_bf16(_ptr(a), a.stride(0), a_layout, _ptr(b), b.stride(0), b_layout, M, N, K, epilogue, _ptr(bias), _ptr(out),
+                                 out.stride(0), L.DT_F32 if out.dtype == torch.float32 else L.DT_BF16, _ptr(alpha), k_splits, _stream())
+    L.check(rc, "b200_gemm_bf16")
+    return out
+
+
 class RowIndex:
     """Compaction of a [B, S] key tensor: the positions with key != ignore in row-major order (b200_heads_compact).  On an
     attention mask (ignore = 0) this IS the packed layout of SURVEY.md §8f rank 2: `start` = cu_seqlens [B+1], `idx` = flat

@@ -168,3 +168,34 @@ def test_training_step_with_fused_schedules_matches_the_round1_schedule(variants
     # without delta the two runs differ only by the order of fp32 reduce-adds (dQ over key blocks, split-K wgrads),
     # which already varies between two runs of the default path: a few fp16 roundings of dQ flip (estimated scale ~1e-5)
     assert _rel(g1, g0) < (2e-3 if "delta" in variants or "dq16" in variants else 1e-4), _rel(g1, g0)
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (300, 768, 1536), (4800, 768, 3328)])
+def test_bf16_operand_gemm_forward_dgrad_wgrad(M, N, K):
+    """BASELINE config 4's bf16 arm at the GEMM level: bf16 A / B with fp32 accumulation against an fp64 product of the SAME
+    bf16-rounded operands (so the bar is accumulation order + output rounding, not operand rounding)."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(41)
+    x = (torch.randn(M, K, generator=g, device="cuda")).to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g, device="cuda") * 0.05).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda") * 0.1
+    ref = x.double() @ w.double().t() + bias.double()
+    out32 = torch.empty(M, N, device="cuda")
+    ops.gemm_bf16(x, w, out32, epilogue=ops.EPI_BIAS, bias=bias)
+    assert _rel(out32, ref) < 1e-5, _rel(out32, ref)
+    out16 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm_bf16(x, w, out16, epilogue=ops.EPI_BIAS, bias=bias)
+    assert _rel(out16.float(), ref) < 4e-3 and torch.equal(out16, out32.to(torch.bfloat16))          # bf16 rounding of the fp32 result
+    dy = (torch.randn(M, N, generator=g, device="cuda") * 0.1).to(torch.bfloat16)
+    dx = torch.empty(M, K, device="cuda", dtype=torch.bfloat16)
+    ops.gemm_bf16(dy, w, dx, b_layout=1)                                                            # dgrad: dy @ W, W read MN-major in place
+    assert _rel(dx.float(), dy.double() @ w.double()) < 4e-3
+    dw = torch.zeros(N, K, device="cuda")
+    ops.gemm_bf16(dy, x, dw, a_layout=1, b_layout=1, epilogue=ops.EPI_ATOMIC, k_splits=ops.wgrad_splits(N, K, M))      # wgrad: dy^T @ x
+    assert _rel(dw, dy.double().t() @ x.double()) < 1e-5
+    # the same contraction on fp16 operands of the same fp32 values, for the error the bf16 arm costs (reported, not asserted tight)
+    xf, wf = x.float(), w.float()
+    o16 = torch.empty(M, N, device="cuda")
+    ops.gemm(xf.half(), wf.half(), o16, epilogue=ops.EPI_BIAS, bias=bias)
+    print(f"bf16 arm [{M}x{N}x{K}]: fp32-out error {_rel(out32, ref):.2e} (vs fp16 operands of the bf16 values {_rel(o16, ref):.2e})")
+

@@ -81,6 +81,20 @@ def main():
     t1 = timeit(lambda: ops.gemm(x, w1, hbuf, epilogue=ops.EPI_BIAS, bias=b1))
     print(json.dumps({"shape": "ffn_up 16384x3072x768", "bias_gelu_us": t0 * 1e6, "bias_only_us": t1 * 1e6,
                       "bias_gelu_tflops": 2.0 * M * I * H / 1e12 / t0, "bias_only_tflops": 2.0 * M * I * H / 1e12 / t1}), flush=True)
+    # BASELINE config 4's bf16 arm: the mmvts projector contraction (visual features, K = 3328) on bf16 against fp16 operands
+    Mv, Kv = 16 * 300, 3328
+    xv = torch.randn(Mv, Kv, device=dev)
+    wv = torch.randn(H, Kv, device=dev) * 0.02
+    ov = torch.empty(Mv, H, device=dev)
+    bv = torch.zeros(H, device=dev)
+    x16v, w16v = xv.half(), wv.half()
+    xbv, wbv = xv.to(torch.bfloat16), wv.to(torch.bfloat16)
+    t0 = timeit(lambda: ops.gemm(x16v, w16v, ov, epilogue=ops.EPI_BIAS, bias=bv))
+    e16 = float((ov.double() - (xv.double() @ wv.double().t())).norm() / (xv.double() @ wv.double().t()).norm())
+    t1 = timeit(lambda: ops.gemm_bf16(xbv, wbv, ov, epilogue=ops.EPI_BIAS, bias=bv))
+    eb = float((ov.double() - (xv.double() @ wv.double().t())).norm() / (xv.double() @ wv.double().t()).norm())
+    print(json.dumps({"shape": f"mmvts projector {Mv}x{H}x{Kv}", "fp16_us": t0 * 1e6, "bf16_us": t1 * 1e6, "fp16_rel_err_vs_fp32": e16,
+                      "bf16_rel_err_vs_fp32": eb, "tflops_bf16": 2.0 * Mv * H * Kv / 1e12 / t1}), flush=True)
     # token-classification head (HBM-bound: 25 MB of fp16 activations per launch)
     W = torch.randn(2, H, device=dev) * 0.02
     bb = torch.zeros(2, device=dev)
