@@ -187,6 +187,15 @@ int b200_version(void) { return 100; }
 static const char g_src_tag[] = "B200SRC:" B200_SRC_HASH;        // the binding also finds this tag by scanning the file
 const char* b200_source_hash(void) { return g_src_tag + 8; }
 long long b200_launch_count(void) { return g_launches.load(); }
+#ifdef B200_ATT_TRACE
+// trace build only (tools/attn_trace.py): copy out the timeline records of CTA 0 (dst: [16 warps][4096], counts: [16])
+int b200_att_trace_read(unsigned long long* dst, unsigned int* counts) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(counts, b200::g_att_trace_n, 16 * sizeof(unsigned int));
+  cudaMemcpyFromSymbol(dst, b200::g_att_trace, 16 * b200::kAttTraceCap * sizeof(unsigned long long));
+  return 0;
+}
+#endif
 
 static int gemm_impl(const void* A, int lda, int a_layout, const void* B, int ldb, int b_layout, int M, int N, int K, int epilogue,
                      const float* bias, const void* aux, int ld_aux, void* out, int ld_out, int out_dtype, void* out2, int ld_out2,
@@ -667,7 +676,7 @@ size_t b200_ponet_workspace(int B, int S, int H, int heads, int nseg) {
 
 int b200_ponet_mix_fwd(const void* proj, int ld, const float* key_bias, const int64_t* segment_ids, void* workspace, void* out, int B, int S,
                        int H, int heads, int nseg, void* stream) {
-  if (B <= 0 || S <= 0 || H != heads * 64 || (H % 8) || (ld % 8) || nseg <= 0) return fail(B200_ERR_SHAPE, "ponet_mix_fwd: bad shape");
+  if (B <= 0 || S <= 0 || H != heads * 64 || H > PONET_MAX_H || (ld % 8) || nseg <= 0) return fail(B200_ERR_SHAPE, "ponet_mix_fwd: bad shape");
   if (!proj || !segment_ids || !workspace || !out) return fail(B200_ERR_SHAPE, "ponet_mix_fwd: null pointer");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int nchunks = (S + 127) / 128;
@@ -683,7 +692,8 @@ int b200_ponet_mix_fwd(const void* proj, int ld, const float* key_bias, const in
   int rc;
   if ((rc = check_launch("fill_f32_kernel"))) return rc;
   const __half* p = static_cast<const __half*>(proj);
-  ponet_qsum_kernel<<<dim3((S + PONET_QSUM_POS - 1) / PONET_QSUM_POS, B), H / 8, 0, s>>>(p, ld, key_bias, qsum, cnt, S, H);
+  constexpr int qsum_pos = PONET_GROUPS * PONET_QSUM_ROUNDS * PONET_QSUM_POS;
+  ponet_qsum_kernel<<<dim3((S + qsum_pos - 1) / qsum_pos, B), dim3(H / 8, PONET_GROUPS), 0, s>>>(p, ld, key_bias, qsum, cnt, S, H);
   if ((rc = check_launch("ponet_qsum_kernel"))) return rc;
   ponet_global_part_kernel<<<dim3(nchunks, heads, B), 128, 0, s>>>(p, ld, key_bias, qsum, cnt, part, S, H, heads);
   if ((rc = check_launch("ponet_global_part_kernel"))) return rc;
@@ -702,7 +712,7 @@ size_t b200_ponet_bwd_workspace(int B, int S, int H, int heads, int nseg) {
 
 int b200_ponet_mix_bwd(const void* proj, int ld, const void* dout, const float* key_bias, const int64_t* segment_ids, const void* fwd_workspace,
                        void* bwd_workspace, void* dproj, int ld_d, int B, int S, int H, int heads, int nseg, void* stream) {
-  if (B <= 0 || S <= 0 || H != heads * 64 || (ld % 8) || (ld_d % 8) || nseg <= 0) return fail(B200_ERR_SHAPE, "ponet_mix_bwd: bad shape");
+  if (B <= 0 || S <= 0 || H != heads * 64 || H > 1024 || (ld % 8) || (ld_d % 8) || nseg <= 0) return fail(B200_ERR_SHAPE, "ponet_mix_bwd: bad shape");
   if (!proj || !dout || !segment_ids || !fwd_workspace || !bwd_workspace || !dproj) return fail(B200_ERR_SHAPE, "ponet_mix_bwd: null pointer");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int nchunks = (S + 127) / 128;
@@ -722,14 +732,14 @@ int b200_ponet_mix_bwd(const void* proj, int ld, const void* dout, const float* 
   const __half* p = static_cast<const __half*>(proj);
   const __half* d = static_cast<const __half*>(dout);
   int rc;
-  ponet_bwd_sums_kernel<<<dim3((S + PONET_RUN_POS - 1) / PONET_RUN_POS, B), H / 8, 0, s>>>(p, ld, d, key_bias, segment_ids, segmax, dg, segsum, segties, S, H, nseg);
+  ponet_bwd_sums_kernel<<<dim3((S + PONET_GROUPS * PONET_RUN_POS - 1) / (PONET_GROUPS * PONET_RUN_POS), B), dim3(H / 8, PONET_GROUPS), 0, s>>>(p, ld, d, key_bias, segment_ids, segmax, dg, segsum, segties, S, H, nseg);
   if ((rc = check_launch("ponet_bwd_sums_kernel"))) return rc;
   ponet_global_lse_kernel<<<dim3(heads, B), 32, 0, s>>>(part, lse, nchunks, heads);
   if ((rc = check_launch("ponet_global_lse_kernel"))) return rc;
   ponet_bwd_global_kernel<<<dim3(nchunks, heads, B), 128, 0, s>>>(p, ld, key_bias, qsum, cnt, g, lse, dg, dqbar, static_cast<__half*>(dproj), ld_d,
                                                                   S, H, heads);
   if ((rc = check_launch("ponet_bwd_global_kernel"))) return rc;
-  ponet_bwd_rows_kernel<<<(B * S + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, s>>>(p, ld, d, key_bias, segment_ids, g, segmax, segsum, segties, dqbar, cnt,
+  ponet_bwd_rows_kernel<<<dim3((S + PONET_ROWS_POS - 1) / PONET_ROWS_POS, B), H / 8, 0, s>>>(p, ld, d, key_bias, segment_ids, g, segmax, segsum, segties, dqbar, cnt,
                                                                                       static_cast<__half*>(dproj), ld_d, B, S, H, nseg);
   return check_launch("ponet_bwd_rows_kernel");
 }

@@ -66,6 +66,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(grad_done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  ATT_TRACE_INIT;
   const int n_kb = (a.Sk + ATT_BK - 1) / ATT_BK;
   const int n_items = a.B * a.heads * n_kb;
 
@@ -171,6 +172,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       for (int kk = 0; kk < 4; ++kk)
         umma_ss(tmem + 128 + g * 64, make_smem_desc(doa + kk * 32, 0, 1024), make_smem_desc(vg + kk * 32, 0, 1024), idesc_s, kk > 0);
       umma_commit(&s_full[g]);
+      ATT_TRACE(10 + g);                          // S_g / dP_g issued
     };
     uint32_t n = 0, qs = 0, ir = 0;     // live items seen, Q / dO ring position, query blocks processed so far
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -181,7 +183,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_wait(&qdo_full[qs % NST], (qs / NST) & 1);
       if (ir > 0) mbar_wait(&s_free[0], (ir - 1) & 1);      // group 0 holds its last block in registers
       tc_fence_after();
-      if (lane == 0) issue_scores(qs % NST, 0);
+      if (elect_one_sync()) issue_scores(qs % NST, 0);
       __syncwarp();
       for (int i = 0; i < nq; ++i, ++ir, ++qs) {
         const uint32_t st = qs % NST;
@@ -191,7 +193,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           if (ir > 0) mbar_wait(&s_free[1], (ir - 1) & 1);
           else mbar_wait(&s_free[0], 0);
           tc_fence_after();
-          if (lane == 0) issue_scores(st, 1);
+          if (elect_one_sync()) issue_scores(st, 1);
           __syncwarp();
         }
         if (i + 1 < nq) {                     // scores of the next block as soon as a group holds block i in registers
@@ -200,13 +202,14 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           for (int g = 0; g < 2; ++g) {
             mbar_wait(&s_free[g], ir & 1);
             tc_fence_after();
-            if (lane == 0) issue_scores(nst, g);
+            if (elect_one_sync()) issue_scores(nst, g);
             __syncwarp();
           }
         }
         mbar_wait(ds_full, ir & 1);
         tc_fence_after();
-        if (lane == 0) {
+        ATT_TRACE(13);                            // P / dS arrived
+        if (elect_one_sync()) {
           const uint32_t qa = smem_u32(smem + S::OFF_QDO + st * 2 * S::T), doa = qa + S::T;
           {
 #pragma unroll
@@ -224,6 +227,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           }
           umma_commit(&qdo_empty[st]);
           umma_commit(grad_done);
+          ATT_TRACE(12);                          // gradient MMAs issued
           if (i + 1 == nq) umma_commit(kv_empty);             // K / V of this item are dead once these MMAs retire
         }
         __syncwarp();
@@ -325,8 +329,10 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           lse_n = (qn < it.sq) ? a.lse2[stat_base + qn] : INFINITY;
           del_n = (qn < it.sq) ? a.delta[stat_base + qn] : 0.f;
         }
+        ATT_TRACE(1);                             // waiting for S / dP
         mbar_wait(&s_full[g], ir & 1);
         tc_fence_after();
+        ATT_TRACE(2);                             // S / dP arrived
         uint32_t sv[64], dp[64];
         tmem_ld_x32(tmem + lane_addr + g * 64, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
         tmem_ld_x32(tmem + lane_addr + g * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
@@ -336,6 +342,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tc_fence_before();
         __syncwarp();                             // the tensor core may overwrite S_g / dP_g with the next block now
         if (lane == 0) mbar_arrive(&s_free[g]);
+        ATT_TRACE(3);                             // scores in registers
         // masked keys: turn their scores into -inf (P = 0, dS = 0)
         if (it.general_bias) {
 #pragma unroll
@@ -377,9 +384,11 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             dk[e] = *reinterpret_cast<const uint32_t*>(&hd);
           }
         }
+        ATT_TRACE(4);                             // P / dS computed, waiting for the previous block's gradient MMAs
         if (i > 0) {                              // gradient MMAs of the previous block are done: its dQ is complete, P / dS are free
           mbar_wait(grad_done, (ir - 1) & 1);
           tc_fence_after();
+          ATT_TRACE(5);                           // P / dS tiles free
         } else if (t == 0) {
           tma_wait_group_read<0>();               // the previous item's dK / dV stores have read the staging patches (see the epilogue)
         }
@@ -393,12 +402,15 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(ds_full);
+        ATT_TRACE(6);                             // P / dS published
         // dQ of the previous block sits in the other TMEM buffer: reduce it into HBM off the critical path
         if (i > 0) drain_dq(ir - 1, i - 1);
+        ATT_TRACE(7);                             // previous dQ drained
       }
       // ------------------------------------------------------------------ item epilogue
       mbar_wait(grad_done, (ir - 1) & 1);
       tc_fence_after();
+      ATT_TRACE(8);                               // last gradient MMAs done
       drain_dq(ir - 1, nq - 1);
       // dV, dK: TMEM lane == key row; this thread owns 32 of the 64 d columns.  A full key block leaves as two TMA stores from
       // the dQ staging patches ([128 keys][64 d] fp16 each); a block that straddles the end of the batch element stores directly.
@@ -440,10 +452,12 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           tma_commit_group();
         }
       }
+      ATT_TRACE(9);                               // dK / dV on their way
     }
     if (lane == 0) tma_wait_group_read<0>();      // staging memory stays valid until the bulk copies have read it
   }
 
+  ATT_TRACE_FINI;
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {

@@ -65,6 +65,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  ATT_TRACE_INIT;
   const int nqp = (a.Sq + 2 * ATT_BQ - 1) / (2 * ATT_BQ);
   const int n_items = a.B * a.heads * nqp;
 
@@ -187,6 +188,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           umma_ss(tmem + x * 128, make_smem_desc(qa + kk * 32, 0, 1024), make_smem_desc(ka + kk * 32, 0, 1024), idesc_s, kk > 0);
         umma_commit(&s_full[x]);
         umma_commit(&k_empty[s]);
+        ATT_TRACE(10);                            // S issued
         if (last) umma_commit(&q_empty[buf]);                // Q of this item is not needed after its last score block
       };
       mbar_wait(&q_full[buf], (n >> 1) & 1);
@@ -194,7 +196,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (t > 0) mbar_wait(&s_free[x], (t - 1) & 1);         // the previous block's score rows sit in registers
       else if (x == 1) mbar_wait(b_go, 0);                   // tile B starts half a period after tile A (header)
       tc_fence_after();
-      if (lane == 0) issue_s(kb & 1, nb == 1);
+      if (elect_one_sync()) issue_s(kb & 1, nb == 1);
       __syncwarp();
       for (int j = 0; j < nb; ++j, ++t, ++kb) {
         const uint32_t s = kb & 1, ph = (kb >> 1) & 1;
@@ -203,13 +205,13 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           mbar_wait(&k_full[s1], ph1);
           mbar_wait(&s_free[x], t & 1);
           tc_fence_after();
-          if (lane == 0) issue_s(s1, j + 2 == nb);
+          if (elect_one_sync()) issue_s(s1, j + 2 == nb);
           __syncwarp();
         }
         mbar_wait(&p_full[x], t & 1);
         mbar_wait(&v_full[s], ph);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one_sync()) {
           const uint32_t va = smem_u32(smem + S::OFF_V + s * S::TILE);
 #pragma unroll
           for (int kk = 0; kk < ATT_BK / 16; ++kk)
@@ -217,6 +219,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     make_smem_desc(va + kk * 2048, 8192, 1024), idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
           umma_commit(&o_full[x]);
           umma_commit(&v_empty[s]);
+          ATT_TRACE(11);                          // P.V issued
         }
         __syncwarp();
       }
@@ -235,6 +238,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     constexpr float inv_sc = 1.0f / kAttScaleLog2;
     const uint32_t dseed = DROP ? drop_seed(a.drop) : 0u;
     uint32_t t = 0;                               // blocks this tile has processed (barrier phases)
+    if (x == 1) asm volatile("bar.arrive 3, 256;" ::: "memory");      // tile A opens
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const Item it = decode(item);
       if (it.skip || (x == 1 && !it.tileB)) continue;
@@ -256,8 +260,10 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           sts_f32(bj + tg * 4, bv);
           asm volatile("bar.sync %0, 128;" ::"r"(1 + x) : "memory");
         }
+        ATT_TRACE(1);                             // waiting for S
         mbar_wait(&s_full[x], t & 1);
         tc_fence_after();
+        ATT_TRACE(2);                             // S arrived
         uint32_t v[128];
         tmem_ld_x32(tmem + lane_addr + x * 128, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
         tmem_ld_x32(tmem + lane_addr + x * 128 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
@@ -268,6 +274,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         __syncwarp();                             // the tensor core may overwrite S_x with the next block now:
         if (lane == 0) mbar_arrive(&s_free[x]);   // one arrival per warp (128 same-address arrivals cost 9 us per backward, r02a)
         if (x == 0 && t == 0 && tg == 0) mbar_arrive(b_go);
+        ATT_TRACE(3);                             // scores in registers
         // ---- masked keys (only blocks that have any)
         if (it.general_bias) {
 #pragma unroll
@@ -298,9 +305,11 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         float m_use = rescale ? m_new : m;
         if (m_use == NEG_INF) m_use = 0.f;
         const float alpha = rescale ? fast_exp2(m - m_use) : 1.0f;     // m == -inf -> 0
+        ATT_TRACE(4);                             // row max done, waiting for O(j-1)
         if (j > 0) {                              // P.V of block j-1 finished: P smem is free, O may be rescaled
           mbar_wait(&o_full[x], (t - 1) & 1);
           tc_fence_after();
+          ATT_TRACE(rescale ? 6 : 5);             // O(j-1) arrived (6: this block rescales)
           if (rescale) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -320,6 +329,11 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             tmem_wait_st();
           }
         }
+        // ---- the two tiles take turns in the exp2 section (MUFU-bound: two warps of a sub-partition inside it at once each take
+        //      twice as long, and then both sit in the latency-bound rest of a block — barrier waits, TMEM loads — together;
+        //      profiles/r02m_trace_fwd.txt: 2850 clk for the section against ~1300 alone, 4400 per block).  A token passes
+        //      A -> B -> A -> ... through two named barriers; both tiles of an item have the same number of key blocks.
+        if (it.tileB) asm volatile("bar.sync %0, 256;" ::"r"(3 + x) : "memory");
         // ---- p = exp2(s * scale - m_use), row sum, fp16 P into the swizzled smem tile (16 chunks of 8 keys)
         const uint64_t nm2 = pack2(-m_use, -m_use), sc2 = pack2(sc, sc);
         const uint32_t dpre_j = dpre + static_cast<uint32_t>(j * (ATT_BK / 4)) * kDropC1;
@@ -353,10 +367,13 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tc_fence_before();
         __syncwarp();                             // every lane has fenced its own P rows; one lane publishes the warp's 32 rows
         if (lane == 0) mbar_arrive(&p_full[x]);
+        if (it.tileB) asm volatile("bar.arrive %0, 256;" ::"r"(3 + (x ^ 1)) : "memory");      // the other tile's turn
+        ATT_TRACE(7);                             // P published
       }
       // ---------------------------------------------------------------- finalise: O / l -> ctx, LSE
       mbar_wait(&o_full[x], (t - 1) & 1);
       tc_fence_after();
+      ATT_TRACE(8);                               // last O arrived
       const float inv_l = (l > 0.f ? 1.0f / l : 0.f) * (DROP ? a.drop.scale : 1.0f);
       uint32_t o[2][32];
       tmem_ld_x32(tmem + lane_addr + 256 + x * 64, o[0]);
@@ -385,10 +402,12 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         for (int ch = 0; ch < 8; ++ch) *reinterpret_cast<uint4*>(dst + ch * 8) = make_uint4(w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
       }
       if (qrow < it.sq && a.lse2) a.lse2[(static_cast<size_t>(b) * a.heads + h) * a.Sq + qrow] = (l > 0.f) ? (m + log2f(l)) : NEG_INF;
+      ATT_TRACE(9);                               // item finalised
     }
     if (lane == 0) tma_wait_group_read<0>();      // staging memory stays valid until the bulk stores have read it
   }
 
+  ATT_TRACE_FINI;
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {

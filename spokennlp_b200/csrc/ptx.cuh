@@ -14,6 +14,30 @@ namespace b200 {
 #define B200_SPIN_LIMIT_CYCLES (6000000000ll)   // ~3-4 s at B200 clocks: turn a protocol deadlock into a trap
 #endif
 
+// Timeline instrumentation for tools/attn_trace.py (a separate -DB200_ATT_TRACE build, never the product library): lane 0 of
+// every warp of CTA 0 appends (event, clock) records to its own buffer (a plain store: an atomic slot counter cost ~600 clk per
+// record and bent the timeline).  Compiled out otherwise.
+#ifdef B200_ATT_TRACE
+constexpr int kAttTraceCap = 4096;                       // records per warp
+__device__ unsigned long long g_att_trace[16 * kAttTraceCap];
+__device__ unsigned int g_att_trace_n[16];
+#define ATT_TRACE_INIT unsigned int att_trace_i_ = 0
+#define ATT_TRACE(ev)                                                                                                    \
+  do {                                                                                                                   \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && att_trace_i_ < kAttTraceCap)                                       \
+      g_att_trace[(threadIdx.x >> 5) * kAttTraceCap + att_trace_i_++] =                                                  \
+          (static_cast<unsigned long long>(ev) << 48) | (static_cast<unsigned long long>(clock64()) & 0xFFFFFFFFFFFFull); \
+  } while (0)
+#define ATT_TRACE_FINI                                                                                                   \
+  do {                                                                                                                   \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_att_trace_n[threadIdx.x >> 5] = att_trace_i_;                      \
+  } while (0)
+#else
+#define ATT_TRACE_INIT
+#define ATT_TRACE(ev)
+#define ATT_TRACE_FINI
+#endif
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -55,6 +79,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       __trap();
     }
   }
+}
+
+// One lane of a converged warp.  Guarding a tcgen05.mma / tcgen05.commit sequence with this instead of `lane == 0` matters: ptxas
+// knows a single thread is active and moves the operands to uniform registers directly (4-5 instructions per MMA); after a lane
+// compare it wraps every MMA in an ELECT / broadcast loop with a branch (10+ instructions, ~90 clk per MMA in the attention
+// backward, whose single issuing warp then set the pace of the whole kernel: 40 MMAs x 90 clk per 3.9 k clk block, r02r).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(p));
+  return p != 0;
 }
 
 // explicit shared-window accesses (the dynamic-smem base is re-aligned by hand, so the compiler cannot prove the
