@@ -185,6 +185,7 @@ def time_kernel(torch, fn, iters=20, warmup=3):
 def kernel_rooflines(torch, ops, lib, peaks, dropout):
     """Live per-kernel numbers on the bench shapes (each kernel timed alone with CUDA events on the launch stream;
     operands >> L2 for the big GEMMs)."""
+    from spokennlp_b200 import blocks
     M, H, I = BATCH * SEQ, 768, 3072
     dev = "cuda"
     f16 = torch.float16
@@ -234,9 +235,11 @@ def kernel_rooflines(torch, ops, lib, peaks, dropout):
     dctx = torch.randn(M, H, device=dev, dtype=f16) * 0.1
     ops.gemm_dgrad_delta(dctx, wo, ctx, dctx.clone(), ws, BATCH, 12, SEQ)          # fills the row statistic once
     t = time_kernel(torch, lambda: ops.attn_bwd(qkv, qkv, dctx, ctx, lse, dqkv, dqkv, ws, BATCH, 12, SEQ, SEQ, q_col0=0, k_col0=H,
-                                                v_col0=2 * H, dq_col0=0, dk_col0=H, dv_col0=2 * H, drop=drop_a, delta_ready=True))
+                                                v_col0=2 * H, dq_col0=0, dk_col0=H, dv_col0=2 * H, drop=drop_a, delta_ready=True,
+                                                dq_half="dq16" in blocks.Experimental.active()))
     out["attn_bwd"] = {"bound": "tensor", "achieved": 2 * aflops / t / 1e12, "unit": "TFLOP/s", "ms": t * 1e3, "dropout": p,
-                       "includes": "dq_acc memset + attn_bwd3_kernel + dq_cast_kernel (row statistic from the out-proj dgrad epilogue)"}
+                       "includes": ("memset of the dQ columns + attn_bwd3_kernel (dQ as fp16 TMA reduce-adds" if "dq16" in blocks.Experimental.active()
+                                    else "dq_acc memset + attn_bwd3_kernel + dq_cast_kernel (") + "; row statistic from the out-proj dgrad epilogue)"}
     g, b = torch.ones(H, device=dev), torch.zeros(H, device=dev)
     y = torch.empty(M, H, device=dev, dtype=f16)
     y32 = torch.empty(M, H, device=dev)

@@ -29,14 +29,21 @@ struct Gemm2Smem {
   static constexpr int B_BYTES = (BN / 2) * GEMM_BK * 2;     // 16 KB : this CTA's half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int SLAB = 32 * 128;                      // 4 KB : 32 rows x 128 B staging slab
-  static constexpr int SLABS = 2;                             // double-buffered output slab per epilogue warp
+#ifndef G2_SLABS
+#define G2_SLABS 2
+#endif
+#ifndef G2_STAGE_CAP
+#define G2_STAGE_CAP 16
+#endif
+  static constexpr int SLABS = EPI == EPI_BIAS_GELU ? 2 : G2_SLABS;     // output slabs per epilogue warp (GELU: one per output)
   static constexpr int EPI_PER_WARP = SLABS * SLAB;
   static constexpr int EPI_WARPS = 8;
-  static constexpr int STAGES = (G2_SMEM_MAX - 1024 - 512 - EPI_WARPS * EPI_PER_WARP) / STAGE_BYTES;
+  static constexpr int STAGES_FIT = (G2_SMEM_MAX - 1024 - 512 - EPI_WARPS * EPI_PER_WARP) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT < G2_STAGE_CAP ? STAGES_FIT : G2_STAGE_CAP;
   static constexpr int OFF_EPI = STAGES * STAGE_BYTES;
   static constexpr int OFF_BAR = OFF_EPI + EPI_WARPS * EPI_PER_WARP;
   static constexpr int TOTAL = OFF_BAR + 512 + 1024;
-  static_assert(STAGES >= 4 && TOTAL <= G2_SMEM_MAX, "shared-memory plan");
+  static_assert(STAGES >= 2 && TOTAL <= G2_SMEM_MAX, "shared-memory plan");
 };
 
 // ------------------------------------------------------------------------------------------------ cluster helpers
@@ -433,8 +440,8 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
           }
         }
         // double-buffered slab: the TMA store issued two chunks ago must have finished reading this buffer
-        uint8_t* os_ptr = out_s + (out_uses & 1) * S::SLAB;
-        if (lane == 0) tma_wait_group_read<1>();
+        uint8_t* os_ptr = out_s + (out_uses % S::SLABS) * S::SLAB;
+        if (lane == 0) tma_wait_group_read<S::SLABS - 1>();
         __syncwarp();
         const uint32_t os = smem_u32(os_ptr);
 #pragma unroll
