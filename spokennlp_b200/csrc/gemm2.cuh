@@ -228,7 +228,7 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one_sync()) {                  // (not `lane == 0`: see ptx.cuh — 4-5 instead of 10+ instructions per MMA)
             const uint32_t a_addr = smem_u32(sA + stage * S::A_BYTES);
             const uint32_t b_addr = smem_u32(sB + stage * S::B_BYTES);
 #pragma unroll
@@ -243,7 +243,7 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
           __syncwarp();
           if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
         }
-        if (kb1 <= kb0 && lane == 0) umma2_commit_mc(&tfull_bar[acc]);
+        if (kb1 <= kb0 && elect_one_sync()) umma2_commit_mc(&tfull_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
