@@ -183,15 +183,19 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      int mt, nt, kb0, kb1;
-      for (int u = u_begin; u < u_end; u = next_unit(u, kb0, kb1)) {
-        decode(u, mt, nt, kb0, kb1);
-        const int m0 = mt * G2_BM + static_cast<int>(rank) * 128;          // this CTA's A rows
-        const int n0 = nt * BN + static_cast<int>(rank) * (BN / 2);        // this CTA's half of the B tile
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // The whole warp walks the loop; one elected lane issues (see ptx.cuh: elect_one_sync).
+    uint32_t stage = 0, phase = 0;
+    int mt, nt, kb0, kb1;
+    for (int u = u_begin; u < u_end; u = next_unit(u, kb0, kb1)) {
+      decode(u, mt, nt, kb0, kb1);
+      const int m0 = mt * G2_BM + static_cast<int>(rank) * 128;          // this CTA's A rows
+      const int n0 = nt * BN + static_cast<int>(rank) * (BN / 2);        // this CTA's half of the B tile
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one_sync()) {
+#ifdef G2_DIAG_NO_TMA                                     // diagnostic build (tools/gemm_stages.py): the mainloop without its loads
+          if (leader) mbar_arrive(&full_bar[stage]);
+#else
           const uint32_t full0 = mapa_u32(smem_u32(&full_bar[stage]), 0);   // the leader's barrier collects both CTAs' bytes
           if (leader) mbar_expect_tx(&full_bar[stage], 2 * (S::A_BYTES + S::B_BYTES));
           uint8_t* a_dst = sA + stage * S::A_BYTES;
@@ -209,11 +213,12 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
           } else {
             tma_load_2d_cg2(b_dst, &maps.b, full0, k0, n0);
           }
-          if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+#endif
         }
+        __syncwarp();
+        if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     if (leader) {
@@ -235,7 +240,11 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
             for (int kk = 0; kk < GEMM_BK / 16; ++kk) {
               const uint64_t da = A_MN ? make_smem_desc(a_addr + kk * 2048, 8192, 1024) : make_smem_desc(a_addr + kk * 32, 0, 1024);
               const uint64_t db = B_MN ? make_smem_desc(b_addr + kk * 2048, 8192, 1024) : make_smem_desc(b_addr + kk * 32, 0, 1024);
+#ifndef G2_DIAG_NO_MMA                                    // diagnostic build: the load pipeline without the MMAs
               umma2_ss(d_tmem, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+#else
+              (void)da; (void)db;
+#endif
             }
             umma2_commit_mc(&empty_bar[stage]);
             if (kb == kb1 - 1) umma2_commit_mc(&tfull_bar[acc]);
@@ -384,7 +393,12 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
           for (int k = 0; k < 32; ++k) {
             float y0, y1, d0, d1;
             uint64_t y2, d2;
+#ifdef G2_DIAG_NO_ERF                                     // diagnostic build: both outputs stored, no erf math
+            y2 = pack2(f[2 * k], f[2 * k + 1]);
+            d2 = y2;
+#else
             gelu_erf_both2(pack2(f[2 * k], f[2 * k + 1]), y2, d2);
+#endif
             unpack2(y2, y0, y1);
             unpack2(d2, d0, d1);
             const __half2 hz = __floats2half2_rn(d0, d1), hh = __floats2half2_rn(y0, y1);
@@ -406,7 +420,9 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
           if (lane == 0) {
             if (has_data) {
               tma_store_2d(&maps.out, out_s, gc0, row0);
+#ifndef G2_DIAG_NO_OUT2                                   // diagnostic build: erf math, derivative not stored
               if (g.out2) tma_store_2d(&maps.out2, out_s + S::SLAB, gc0, row0);
+#endif
             }
             tma_commit_group();
           }
