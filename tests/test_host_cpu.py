@@ -148,3 +148,29 @@ def test_bench_synthetic_batch_follows_the_spec():
     assert int(lens.min()) >= 256 and int(lens.max()) <= 512
     assert bool((plabels[pmask == 0] == -100).all())
     assert bench.FLOP_PER_SEQ == 3 * 12 * (24 * 512 * 768 * 768 + 4 * 512 * 512 * 768)   # fwd+bwd, SURVEY §8d
+
+
+def test_mma_issue_sites_are_guarded_by_elect_not_by_a_lane_compare():
+    """A `tcgen05.mma` sequence under `if (lane == 0)` compiles to an ELECT / broadcast loop with a branch per MMA (~90 clk
+    per MMA in the attention backward, 6-25 % on the GEMM shapes); under `elect_one_sync()` it is 4-5 uniform instructions.  Hold the
+    kernels to the latter: no umma call may sit within a few lines of a lane-0 guard."""
+    import re
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "spokennlp_b200", "csrc")
+    bad, seen = [], 0
+    for name in ("gemm2.cuh", "attn_fwd3.cuh", "attn_bwd3.cuh"):
+        lines = open(os.path.join(csrc, name)).read().split("\n")
+        for i, line in enumerate(lines):
+            if re.search(r"\bissue_(s|scores)\(", line) and "auto" not in line:          # call site of an issuing lambda
+                seen += 1
+                if "elect_one_sync()" not in line:
+                    bad.append(f"{name}:{i + 1}")
+            elif re.search(r"\bumma2?_(ss|ts)\(", line):
+                for j in range(i - 1, -1, -1):                                          # the block (or lambda) this call sits in
+                    if re.search(r"auto issue_\w+ = ", lines[j]):
+                        break
+                    if re.match(r"\s*if \(.*\) \{", lines[j]):
+                        seen += 1
+                        if "elect_one_sync()" not in lines[j]:
+                            bad.append(f"{name}:{i + 1}")
+                        break
+    assert seen >= 8 and not bad, f"MMA issue guarded by a lane compare at {bad} ({seen} sites seen)"
