@@ -1,0 +1,10 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 400 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_dropout.py tests/test_gpu_packing.py tests/test_gpu_cross.py -q -x -m gpu 2>&1 | tail -3
+timeout 300 python tools/attn_scaling.py 2> gpurun_out/r3e_attn_scaling.err | tee gpurun_out/r3e_attn_scaling.jsonl | head -2 | cut -c1-200
+timeout 400 python bench.py --no-padded > gpurun_out/r3e_bench.json 2> gpurun_out/r3e_bench.err; python - <<'PY'
+import json
+r=json.loads(open('gpurun_out/r3e_bench.json').read().strip().splitlines()[-1])
+print(r['value'], r['ms_per_step'], 'e2e', r['e2e']['value'], r['clocks'], r['encoder_flop_util']['frac_of_sustained'], r['roofline']['frac'])
+print({k:round(v['ms']*1e3,1) for k,v in r['kernels'].items()})
+PY
