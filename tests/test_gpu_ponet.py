@@ -14,7 +14,7 @@ def _setup():
     torch.backends.cuda.matmul.allow_tf32 = False
 
 
-@pytest.mark.parametrize("B,S,heads,pad", [(2, 256, 2, [256, 180]), (1, 1000, 2, [777]), (2, 4096, 12, [4096, 3500])])
+@pytest.mark.parametrize("B,S,heads,pad", [(2, 256, 2, [256, 180]), (1, 1000, 2, [777]), (3, 77, 4, [77, 1, 40]), (2, 4096, 12, [4096, 3500])])
 def test_ponet_mixer_matches_restatement(B, S, heads, pad):
     _setup()
     from oracle import ponet_oracle as P
@@ -58,16 +58,18 @@ def test_ponet_model_forward_matches_restatement():
     assert torch.allclose(tup[0], out.last_hidden_state, atol=1e-4, rtol=1e-4) and tup[1] is None
 
 
-def test_ponet_mixer_backward_matches_restatement_autograd():
+@pytest.mark.parametrize("B,S,heads,pad", [(2, 512, 2, [512, 333]), (1, 1003, 2, [777]), (3, 77, 4, [77, 1, 40]), (2, 4096, 12, [4096, 3500])])
+def test_ponet_mixer_backward_matches_restatement_autograd(B, S, heads, pad):
+    """Sequence lengths that are no multiple of the kernels' position blocks (8 / 16 / 64 / 128), a sequence with a single kept token,
+    and the BASELINE shape (12 heads: 96-thread column blocks, 4 position groups per block)."""
     _setup()
     from oracle import ponet_oracle as P
     from spokennlp_b200 import ops
-    B, S, heads = 2, 512, 2
     H = heads * 64
     g = torch.Generator().manual_seed(9)
     proj = torch.randn(B, S, 5 * H, generator=g).half()
     dout = (torch.randn(B, S, H, generator=g) * 0.5).half()
-    seg, mask = P.synth_segments(B, S, seed=4, pad_from=[512, 333])
+    seg, mask = P.synth_segments(B, S, seed=4, pad_from=pad)
     pf = proj.float().requires_grad_(True)
     ref = P.ponet_mixer(pf[..., :H], pf[..., H:2 * H], pf[..., 2 * H:3 * H], pf[..., 3 * H:4 * H], pf[..., 4 * H:], mask, seg, heads)
     ref.backward(dout.float())

@@ -108,19 +108,21 @@ conf = types.SimpleNamespace(hidden_size=768, num_cross_encoder_layers=1, num_cr
                              max_seq_length=2048, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, ce_kv_hidden_size=1536,
                              hidden_size_vis=3328, hidden_size_audio=768)
 proj = LinearProjector(conf).cuda()
-tfeat, vfeat, afeat = torch.randn(1, 300, 768).cuda(), torch.randn(1, 300, 3328).cuda(), torch.randn(1, 300, 768).cuda()
-cmask = torch.ones(1, 300).cuda()
-cmask[:, 250:] = 0
-for name, enc in (("ma", MergeAttentionEncoder(conf).cuda()), ("ca", CoAttentionEncoder(conf).cuda())):
-    def step():
-        for m in (proj, enc):
-            for p in m.parameters():
-                p.grad = None
-        a, b, c = proj(tfeat, vfeat, afeat)
-        t_, v_, a_ = enc(cmask, a, b, c)
-        (t_.mean() + v_.mean() + a_.mean()).backward()
-    t = timeit(step, iters=5, warm=2)
-    emit(config=4, workload=f"mmvts projector + {name} cross encoder, N=300 clips, fwd+bwd", samples_per_s=1 / t, ms=t * 1e3)
+encs = (("ma", MergeAttentionEncoder(conf).cuda()), ("ca", CoAttentionEncoder(conf).cuda()))
+for bs in (1, 16, 64):          # one video per step is ~400 launches over 300 token rows (launch-bound); batches show the kernels' rate
+    tfeat, vfeat, afeat = torch.randn(bs, 300, 768).cuda(), torch.randn(bs, 300, 3328).cuda(), torch.randn(bs, 300, 768).cuda()
+    cmask = torch.ones(bs, 300).cuda()
+    cmask[:, 250:] = 0
+    for name, enc in encs:
+        def step():
+            for m in (proj, enc):
+                for p in m.parameters():
+                    p.grad = None
+            a, b, c = proj(tfeat, vfeat, afeat)
+            t_, v_, a_ = enc(cmask, a, b, c)
+            (t_.mean() + v_.mean() + a_.mean()).backward()
+        t = timeit(step, iters=5, warm=2)
+        emit(config=4, workload=f"mmvts projector + {name} cross encoder, N=300 clips, batch {bs}, fwd+bwd", samples_per_s=bs / t, ms=t * 1e3)
 
 os.makedirs("gpurun_out", exist_ok=True)
 with open("gpurun_out/config_sweeps.jsonl", "w") as f:
