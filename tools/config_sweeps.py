@@ -123,6 +123,21 @@ for bs in (1, 16, 64):          # one video per step is ~400 launches over 300 t
             (t_.mean() + v_.mean() + a_.mean()).backward()
         t = timeit(step, iters=5, warm=2)
         emit(config=4, workload=f"mmvts projector + {name} cross encoder, N=300 clips, batch {bs}, fwd+bwd", samples_per_s=bs / t, ms=t * 1e3)
+        if bs <= 16:                # the same step replayed from one CUDA graph (spokennlp_b200.graphs.GraphedStep)
+            from spokennlp_b200.graphs import GraphedStep
+
+            def gstep(tf, vf, af, cm, enc=enc):
+                for m in (proj, enc):
+                    for p in m.parameters():
+                        p.grad = None
+                a, b, c = proj(tf, vf, af)
+                t_, v_, a_ = enc(cm, a, b, c)
+                loss = t_.mean() + v_.mean() + a_.mean()
+                loss.backward()
+                return loss.detach()
+            gs = GraphedStep(gstep, (tfeat, vfeat, afeat, cmask))
+            t = timeit(lambda: gs(tfeat, vfeat, afeat, cmask), iters=10, warm=2)
+            emit(config=4, workload=f"mmvts projector + {name} cross encoder, N=300 clips, batch {bs}, fwd+bwd, CUDA graph", samples_per_s=bs / t, ms=t * 1e3)
 
 os.makedirs("gpurun_out", exist_ok=True)
 with open("gpurun_out/config_sweeps.jsonl", "w") as f:
