@@ -19,6 +19,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import ops
+from .lib import B200Error
 from .blocks import AttnSaved, AttnWeights, FfnSaved, FfnWeights, attn_block_bwd, attn_block_fwd, ffn_block_bwd, ffn_block_fwd
 
 Tensor = torch.Tensor
@@ -112,9 +113,11 @@ class FlatParams:
         return sum(p._version for p in self.params.values())
 
     def sync_half(self, force: bool = False) -> None:
-        """Refresh the fp16 mirror if any parameter was modified in place since the last refresh."""
+        """Refresh the fp16 mirror if any parameter was modified in place since the last refresh.  Under stream capture the refresh is
+        always issued, so that it becomes part of the graph: a replay after an optimizer step must see the new weights, and the version
+        check only runs at capture time (spokennlp_b200.graphs.GraphedStep)."""
         v = self.cur_version()
-        if force or v != self.version:
+        if force or v != self.version or (self.flat32.is_cuda and torch.cuda.is_current_stream_capturing()):
             ops.cast_f32_to_f16(self.flat32, self.flat16)
             self.version = v
 
@@ -124,6 +127,22 @@ class FlatParams:
         elif zero:
             self.grad32.zero_()
         return self.grad32
+
+
+def next_drop_seed(owner, device) -> Tensor:
+    """The base dropout seed of one forward of `owner` (a drop-in module): an int32 [1] device tensor that stays untouched until that
+    forward's backward has regenerated its masks.  The module's running seed lives on the device and advances there (one add per
+    forward; this call's copy is handed out), so a forward captured into a CUDA graph draws fresh masks on every replay; its first
+    value comes from torch's CPU generator, so `torch.manual_seed` governs it as it governs `nn.Dropout` in the reference."""
+    base = owner.__dict__.get("_b200_seed_dev")
+    if base is None or base.device != torch.device(device):
+        if torch.cuda.is_current_stream_capturing():
+            raise B200Error("run the step once before capturing it: the dropout seed is created on first use")
+        base = torch.randint(0, 2 ** 31 - 1, (1,), dtype=torch.int32).to(device)
+        object.__setattr__(owner, "_b200_seed_dev", base)
+    else:
+        base.add_(0x632BE5AB)                       # (int32 wrap-around is fine: the kernels hash seed, site and element index)
+    return base.clone()
 
 
 @dataclass

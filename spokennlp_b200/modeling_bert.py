@@ -20,7 +20,7 @@ from transformers.modeling_outputs import BaseModelOutputWithPoolingAndCrossAtte
 from transformers.models.bert.modeling_bert import BertPreTrainedModel
 
 from . import ops
-from .engine import EMB_NAMES, DropPlan, EncoderEngine, FlatParams, layer_param_names
+from .engine import EMB_NAMES, DropPlan, EncoderEngine, FlatParams, layer_param_names, next_drop_seed
 from .lib import B200Error
 
 
@@ -219,10 +219,10 @@ class BertModel(BertPreTrainedModel):
         eng = self.b200_engine(src.device, named)
         drop = None
         if self.training and (cfg.hidden_dropout_prob > 0 or cfg.attention_probs_dropout_prob > 0):
-            # one fresh base seed per forward, drawn from torch's CPU generator (so torch.manual_seed governs it, as it does
-            # nn.Dropout in the reference); the tensor lives in the saved state until this forward's backward has run
-            seed = torch.randint(0, 2 ** 31 - 1, (1,), dtype=torch.int32).to(src.device, non_blocking=True)
-            drop = DropPlan(seed, cfg.hidden_dropout_prob, cfg.attention_probs_dropout_prob)
+            # one base seed per forward (engine.next_drop_seed: first value from torch's CPU generator, so torch.manual_seed governs it as
+            # it does nn.Dropout in the reference; advanced on the device); the tensor lives in the saved state until this forward's
+            # backward has run
+            drop = DropPlan(next_drop_seed(self, src.device), cfg.hidden_dropout_prob, cfg.attention_probs_dropout_prob)
 
         ids = input_ids.contiguous().view(-1) if input_ids is not None else None
         emb = inputs_embeds.contiguous().float() if inputs_embeds is not None else None       # [B,S,H]; the kernels index it as [B*S,H]

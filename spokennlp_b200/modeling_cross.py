@@ -20,7 +20,7 @@ from torch import nn
 
 from . import ops
 from .blocks import (AttnWeights, FfnWeights, attn_block_bwd, attn_block_fwd, ffn_block_bwd, ffn_block_fwd)
-from .engine import DropPlan, FlatParams
+from .engine import DropPlan, FlatParams, next_drop_seed
 from .lib import B200Error
 from .modeling_bert import BertAttention, BertIntermediate, BertOutput
 
@@ -57,9 +57,7 @@ class _Packed(nn.Module):
         own = dict(self.named_parameters())
         named = [(n, own[n]) for n in self._order]
         if f is not None and f.intact(named):
-            # under stream capture the refresh of the fp16 operand mirror becomes part of the graph: a replay after an optimizer
-            # step must see the new weights, and the version check below only runs at capture time
-            f.sync_half(force=torch.cuda.is_current_stream_capturing())
+            f.sync_half()
             return f
         if torch.device(device).type != "cuda":
             raise B200Error(f"{type(self).__name__} runs on CUDA devices only (no CPU fallback)")
@@ -73,17 +71,7 @@ class _Packed(nn.Module):
         the per-site masks from it; the backward regenerates them."""
         if not self.training or (self.p_hidden <= 0.0 and self.p_attn <= 0.0):
             return None
-        # The base seed lives on the device and advances there (one add per forward, a copy handed to this call's plan), so a forward
-        # captured into a CUDA graph draws fresh masks on every replay; its first value comes from torch's CPU generator.
-        base = getattr(self, "_seed_dev", None)
-        if base is None or base.device != torch.device(device):
-            if torch.cuda.is_current_stream_capturing():
-                raise B200Error("run the step once before capturing it: the dropout seed is created on first use")
-            base = torch.randint(0, 2 ** 31 - 1, (1,), dtype=torch.int32).to(device)
-            object.__setattr__(self, "_seed_dev", base)
-        else:
-            base.add_(0x632BE5AB)                   # (int32 wrap-around is fine: the kernels hash seed, site and element index)
-        return DropPlan(base.clone(), self.p_hidden, self.p_attn)
+        return DropPlan(next_drop_seed(self, device), self.p_hidden, self.p_attn)
 
     def _need_grad(self, *inputs) -> bool:
         if not torch.is_grad_enabled():

@@ -23,7 +23,7 @@ from transformers.modeling_outputs import BaseModelOutputWithPoolingAndCrossAtte
 
 from . import ops
 from .blocks import FfnWeights, ffn_block_bwd, ffn_block_fwd
-from .engine import EMB_NAMES, DropPlan, FlatParams
+from .engine import EMB_NAMES, DropPlan, FlatParams, next_drop_seed
 from .lib import B200Error
 from .modeling_bert import BertEmbeddings, BertIntermediate, BertOutput, BertPooler, BertSelfOutput
 
@@ -245,8 +245,7 @@ class PoNetModel(nn.Module):
         drop = None
         p_hidden = float(getattr(cfg, "hidden_dropout_prob", 0.0) or 0.0)
         if self.training and p_hidden > 0.0:
-            seed = torch.randint(0, 2 ** 31 - 1, (1,), dtype=torch.int32).to(input_ids.device, non_blocking=True)
-            drop = DropPlan(seed, p_hidden, 0.0)
+            drop = DropPlan(next_drop_seed(self, input_ids.device), p_hidden, 0.0)
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         outs = _PoNetFn.apply(self, input_ids.contiguous().view(-1), tt, pos, key_bias, seg, B, S, bool(output_hidden_states), drop,
                               need_grad, *params)
