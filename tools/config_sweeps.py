@@ -100,6 +100,22 @@ emit(config=3, workload="PoNet-base [2,4096] fwd+bwd (drop-in autograd path)", s
 with torch.no_grad():
     t = timeit(lambda: ponet(pid, attention_mask=pmask, segment_ids=seg, return_dict=True), iters=5, warm=2)
 emit(config=3, workload="PoNet-base [2,4096] fwd", seq_per_s=2 / t, tokens_per_s=8192 / t, ms=t * 1e3)
+from spokennlp_b200.graphs import GraphedStep  # noqa: E402
+
+
+def ponet_gstep(i, a):
+    for p in ponet.parameters():
+        p.grad = None
+    out = ponet(i, attention_mask=a, segment_ids=seg, return_dict=True).last_hidden_state
+    loss = out.float().mean()
+    loss.backward()
+    return loss.detach()
+
+
+pgs = GraphedStep(ponet_gstep, (pid, pmask))
+t = timeit(lambda: pgs(pid, pmask), iters=10, warm=2)
+emit(config=3, workload="PoNet-base [2,4096] fwd+bwd, CUDA graph", seq_per_s=2 / t, tokens_per_s=8192 / t, ms=t * 1e3)
+del pgs
 
 # ---- config 4: mmvts cross encoders -------------------------------------------------------------------------------
 from spokennlp_b200.modeling_cross import CoAttentionEncoder, LinearProjector, MergeAttentionEncoder  # noqa: E402
