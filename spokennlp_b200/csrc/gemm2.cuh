@@ -197,7 +197,13 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
           if (leader) mbar_arrive(&full_bar[stage]);
 #else
           const uint32_t full0 = mapa_u32(smem_u32(&full_bar[stage]), 0);   // the leader's barrier collects both CTAs' bytes
+#ifdef G2_DIAG_HALF_B                                     // diagnostic build: every other k-block skips its B loads (-25 % L2 reads)
+          const bool skip_b = (kb & 1) != 0;
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * (S::A_BYTES + (skip_b ? 0 : S::B_BYTES)));
+#else
+          const bool skip_b = false;
           if (leader) mbar_expect_tx(&full_bar[stage], 2 * (S::A_BYTES + S::B_BYTES));
+#endif
           uint8_t* a_dst = sA + stage * S::A_BYTES;
           uint8_t* b_dst = sB + stage * S::B_BYTES;
           const int k0 = kb * GEMM_BK;
@@ -207,7 +213,8 @@ gemm2_f16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmArgs g) {
           } else {
             tma_load_2d_cg2(a_dst, &maps.a, full0, k0, m0);
           }
-          if (B_MN) {
+          if (skip_b) {
+          } else if (B_MN) {
 #pragma unroll
             for (int j = 0; j < BN / 128; ++j) tma_load_2d_cg2(b_dst + j * 8192, &maps.b, full0, n0 + 64 * j, k0);
           } else {
