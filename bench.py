@@ -386,6 +386,8 @@ def run_b200_arm(args):
     kr = None
     if rank == 0:
         peaks, peak_src = load_peaks()
+        torch.cuda.synchronize()
+        time.sleep(1.5)                        # (the burst peaks were taken on an idle part: let the power state of the timed loops decay)
         kr = kernel_rooflines(torch, ops, lib, peaks, args.dropout)
 
     # sustained: the same resident-batch step for >= args.sustained_s seconds with its own clock sample, so that the fraction of
