@@ -476,9 +476,9 @@ static int layernorm_bwd_impl(const void* dy, const void* dy2, const void* x, in
   if (int rc = check_row_shape("layernorm_bwd", rows, H)) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   {
-    const int wps = (H / 8 + 31) / 32, tpr = 32 * wps, slots = LNB_THREADS / tpr;     // wps in 1..4 (H <= 1024)
+    const int wps = (H / 8 + 31) / 32, tpr = 32 * wps, threads = lnb_threads(wps), slots = threads / tpr;     // wps in 1..4 (H <= 1024)
     int grid2 = (rows + slots * LNB_R - 1) / (slots * LNB_R);
-    if (grid2 > sm_count() * 2) grid2 = sm_count() * 2;
+    if (grid2 > sm_count() * lnb_ctas(wps)) grid2 = sm_count() * lnb_ctas(wps);
     const size_t smem2 = 3 * slots * H * sizeof(float) + 2 * slots * wps * 16;
     const __half* dyh = static_cast<const __half*>(dy);
     const __half* dy2h = static_cast<const __half*>(dy2);
@@ -488,7 +488,7 @@ static int layernorm_bwd_impl(const void* dy, const void* dy2, const void* x, in
   do {                                                                                                                           \
     static int c = set_smem(ln_bwd2_kernel<T, W>, 64 * 1024);                                                                    \
     if (c) return c;                                                                                                             \
-    ln_bwd2_kernel<T, W><<<grid2, LNB_THREADS, smem2, s>>>(dyh, dy2h, static_cast<const T*>(x), mean, rstd, gamma, dxh, dgamma, \
+    ln_bwd2_kernel<T, W><<<grid2, threads, smem2, s>>>(dyh, dy2h, static_cast<const T*>(x), mean, rstd, gamma, dxh, dgamma, \
                                                           dbeta, dbias, alpha, rows, H, dxd, drop);                              \
   } while (0)
     if (x_dtype == B200_DT_F32) {

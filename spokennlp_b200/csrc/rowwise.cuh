@@ -127,10 +127,13 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) ln_fwd_kernel(const InT* __res
 // The first generation kept a whole row per warp, which cost 72 accumulator registers per lane for the three column sums
 // (dgamma, dbeta, dbias): 168 registers, 12 resident warps per SM, one row in flight per warp — 2.4 TB/s (profiles/r01d; removed in
 // round 2, git 01a2ca4 keeps it).  Here a row is spread over `tpr` threads (one 8-column chunk each, so the column sums
-// are 24 registers), a CTA runs 384 / tpr independent row slots, and every slot pulls LNB_R rows per trip, so an SM keeps
+// are 24 registers), a CTA runs lnb_threads / tpr independent row slots, and every slot pulls LNB_R rows per trip, so an SM keeps
 // 24 warps x LNB_R rows of loads in flight.  The per-row sums cross the slot's warps through shared memory behind a
 // slot-local named barrier (parity-double-buffered: one barrier per trip).
-constexpr int LNB_THREADS = 384;
+// CTA size: 768 threads per SM either way, but four CTAs of 192 threads (two row slots each at H = 768) interleave their load
+// and compute phases better than two of 384 (30.7 -> 28.3 us with dropout at the bench shape; eight of 96 are worse: 33.5 us).
+constexpr int lnb_threads(int wps) { return wps == 4 ? 256 : 192; }      // a multiple of tpr = 32 wps
+constexpr int lnb_ctas(int wps) { return 768 / lnb_threads(wps); }
 constexpr int LNB_R = 2;
 static_assert(LNB_R == 2, "the row-sum exchange below moves one float4 (2 rows x 2 sums) per warp");
 
@@ -148,7 +151,7 @@ __device__ __forceinline__ Vec8 unpack8(const uint4& raw) {
 
 // WPS = warps per row slot (tpr = 32 * WPS threads share a row)
 template <typename InT, int WPS>
-__global__ void __launch_bounds__(LNB_THREADS, 2) ln_bwd2_kernel(const __half* __restrict__ dy, const __half* __restrict__ dy2,
+__global__ void __launch_bounds__(lnb_threads(WPS), lnb_ctas(WPS)) ln_bwd2_kernel(const __half* __restrict__ dy, const __half* __restrict__ dy2,
                                                                   const InT* __restrict__ x, const float* __restrict__ mean_in,
                                                                   const float* __restrict__ rstd_in, const float* __restrict__ gamma,
                                                                   __half* __restrict__ dx, float* __restrict__ dgamma,
@@ -156,7 +159,7 @@ __global__ void __launch_bounds__(LNB_THREADS, 2) ln_bwd2_kernel(const __half* _
                                                                   const float* __restrict__ alpha_ptr, int rows, int H,
                                                                   __half* __restrict__ dx_drop, DropCfg drop) {
   extern __shared__ float red[];   // [3][slots][H] column sums, then [2 parities][slots][WPS] float4 row-sum partials
-  constexpr int tpr = 32 * WPS, slots = LNB_THREADS / tpr;
+  constexpr int tpr = 32 * WPS, slots = lnb_threads(WPS) / tpr;
   const int slot = threadIdx.x / tpr, tl = threadIdx.x - slot * tpr;
   const int lane = threadIdx.x & 31, wis = tl >> 5;            // warp inside the slot
   const int c = tl * 8;
