@@ -62,7 +62,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t0 = index, [], None, None
 
     def start(self):
         try:
@@ -74,14 +74,22 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def begin(self):
+        """The timed region starts now: nvidia-smi takes a few hundred ms to produce its first sample, so the sampler is started
+        well before a 0.3 s region and only the samples taken from here on are reported."""
+        self.t0 = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t1 = time.time()
+        time.sleep(0.05)                       # (a sample is printed a little after it was taken)
         self.proc.terminate()
+        inside = [r for t, r in self.rows if self.t0 is None or self.t0 <= t <= t1 + 0.05]
         sm, mx, reasons, pw = [], [], set(), []
-        for r in self.rows:
+        for r in (inside or [r for _, r in self.rows[-3:]]):
             try:
                 sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
             except Exception:
@@ -341,12 +349,16 @@ def run_b200_arm(args):
     dp_graph = os.environ.get("B200_DP_GRAPH", "auto")
     use_graph = not args.no_graph and dp_graph != "0"
     graphed = trainer.capture(*dev) if use_graph else False
-    for _ in range(max(3, args.warmup)):
-        trainer.step(*dev)
+    # every timed loop of this file starts the same way: an idle part (set-up and graph capture leave it warm), then the warm-up steps
+    torch.cuda.synchronize()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    time.sleep(1.0)
+    for _ in range(max(3, args.warmup)):
+        trainer.step(*dev)
     l0 = lib.launch_count()
+    sampler.begin()
     secs = timed(lambda: trainer.step(*dev), args.steps)
     launches = lib.launch_count() - l0
     if graphed:       # replayed launches are not seen by the host-side counter: kernels per captured step x steps
@@ -366,6 +378,8 @@ def run_b200_arm(args):
     sampler2 = ClockSampler(local)
     if rank == 0:
         sampler2.start()                       # nvidia-smi needs a few hundred ms before its first sample
+    torch.cuda.synchronize()
+    time.sleep(1.0)                            # same starting point as the resident-batch loop above: an idle part, then 3 warm-up steps
     for _ in range(3):
         e2e_step()
     trainer.drain()
@@ -375,6 +389,7 @@ def run_b200_arm(args):
         for _ in range(args.steps):
             e2e_step()
         e2e_losses.append(trainer.drain())     # the last step's loss is read inside the timed region as well
+    sampler2.begin()
     e2e_secs = timed(e2e_run, 1)
     e2e_clocks = sampler2.stop() if rank == 0 else None
     e2e_value = world * BATCH * args.steps / e2e_secs
