@@ -7,8 +7,10 @@
 A "step" = one fine-tuning step on one synthetic batch of 32 x 512-token windows per GPU (BASELINE config 2,
 SURVEY.md §8d): embeddings -> 12 encoder layers -> token-cls head -> CE -> full backward -> gradient allreduce ->
 clip(1.0) -> AdamW.  value = whole-job sequences/s with the batch already resident in HBM; e2e = same through
-`DataParallelTrainer.step_from_host` with pinned-host inputs copied every step and the loss read back.
-Prints ONE JSON line (rank 0).
+`DataParallelTrainer.step_from_host` with pinned-host inputs copied every step and the loss read back.  Both loops start from an idle
+part (1 s) plus their warm-up steps; `sustained` repeats the resident-batch step for >= 3 s under its own clock sample.  `roofline` /
+`kernels` time each hot kernel alone as the best of five short bursts (the way the burst peaks in MEASURED_PEAKS.json were taken),
+before the sustained run.  Prints ONE JSON line (rank 0).
 """
 from __future__ import annotations
 
