@@ -174,3 +174,39 @@ def test_mma_issue_sites_are_guarded_by_elect_not_by_a_lane_compare():
                             bad.append(f"{name}:{i + 1}")
                         break
     assert seen >= 8 and not bad, f"MMA issue guarded by a lane compare at {bad} ({seen} sites seen)"
+
+
+def test_clock_sampler_reports_only_samples_of_the_timed_region():
+    """bench.ClockSampler is started well before a 0.3 s timed region (nvidia-smi needs a few hundred ms to produce a sample): only the
+    samples taken after begin() may reach the JSON line, and a region that caught none falls back to the last samples before it."""
+    import sys
+    import time
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+
+    class _Proc:
+        def terminate(self):
+            pass
+    s = bench.ClockSampler(0)
+    s.proc = _Proc()
+    now = time.time()
+    row = lambda mhz, cap: ["0", str(mhz), "1965", "400.0", "Not Active", "Not Active", "Not Active", "Active" if cap else "Not Active"]
+    s.rows = [(now - 2.0, row(300, False)), (now - 1.5, row(500, False))]
+    s.t0 = now - 1.0
+    s.rows += [(now - 0.5, row(1800, True)), (now - 0.2, row(1700, True))]
+    out = s.stop()
+    assert out["samples"] == 2 and out["sm_mhz"] == 1750.0 and out["reasons"] == ["sw_power_cap"]
+    s2 = bench.ClockSampler(0)
+    s2.proc = _Proc()
+    s2.rows = [(now - 2.0, row(300, False)), (now - 1.5, row(500, False))]
+    s2.t0 = now - 1.0
+    out2 = s2.stop()
+    assert out2["samples"] == 2 and out2["sm_mhz"] == 400.0          # nothing inside: the last samples before the region
+
+
+def test_graphed_step_refuses_cpu_tensors():
+    import torch
+    from spokennlp_b200.graphs import GraphedStep
+    from spokennlp_b200.lib import B200Error
+    with pytest.raises(B200Error):
+        GraphedStep(lambda x: x, (torch.zeros(2),))
